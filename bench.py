@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 k-mer counting engine.
+
+Metric (BASELINE.json): k-mers counted per second, whole job.
+Workload at N=1 (BASELINE.json configs[1], SURVEY.md §8d "C2"): k=21, incremental
+counting with 10 chunks over 10 M synthetic 150 bp reads (50 Mbp genome, 1 %
+substitutions, 0.1 % N, seed 2), 1 B200.  At N>1 the same per-GPU load is kept
+(weak scaling): 10 M reads and 50 Mbp of genome per GPU, table sharded by k-mer
+hash, k-mers routed with an NCCL all-to-all.
+
+A "step" = one full pass of the hot path over the whole input:
+    reset table -> pack (ASCII -> 2-bit) -> per chunk: extract + insert -> histogram snapshot
+`value`  : inputs already resident in HBM (device-generated reads).
+`e2e`    : the same job through the C-ABI call a host makes (skm_ingest_batch with
+           pinned HOST buffers): H2D copies and the D2H of the histograms are inside
+           the timed region.
+Timing: CUDA events on the stream the engine launches on (a torch stream handed to
+the ctx), barrier + synchronize on both sides, max over ranks.  Inputs (1.5 GB) and
+table (8.6 GB) are far larger than L2 (126 MB), so no explicit L2 flush is needed.
+
+`--impl reference` times the reference's CPU algorithm (the C oracle port — the
+Rust reference cannot be built here) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+K = 21
+CHUNKS = 10
+HISTO_MAX = 10000
+READ_LEN = 150
+READS_PER_GPU = 10_000_000
+GENOME_PER_GPU = 50_000_000
+SUB_RATE = 0.01
+N_RATE = 0.001
+SEED = 2
+DISTINCT_HINT_PER_GPU = 320_000_000
+CPU_SAMPLE_READS = 300_000
+B_ALG_PER_KMER = 64.0      # 32 B sector in + 32 B sector out per k-mer occurrence
+B_ALG_PER_BASE = 0.375     # packed stream read by the extract kernels: 2-bit code + 1-bit break mask
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples drawing the most power
+        order = np.argsort(power)[len(power) // 2:]
+        return {"sm_mhz": float(np.median(np.asarray(sm)[order])), "sm_max_mhz": float(max(mx)),
+                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port), bounded sample
+# ----------------------------------------------------------------------------
+
+def cpu_sample(n_reads, genome_len):
+    """One bounded CPU pass: the first n_reads reads of the workload, k=21, 10 chunks."""
+    from oracle import oracle as o
+    reads = o.synth_reads(SEED, genome_len, READ_LEN, SUB_RATE, N_RATE, 0, n_reads)
+    t0 = time.perf_counter()
+    run = o.Run(K, CHUNKS, HISTO_MAX)
+    run.push_lines(reads)
+    run.finish()
+    dt = time.perf_counter() - t0
+    return run, reads, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.cpu_sample_reads
+    genome = GENOME_PER_GPU * args.gpus
+    times, kmers = [], 0
+    for i in range(args.warmup + args.steps):
+        run, _, dt = cpu_sample(n, genome)
+        kmers = run.n_kmers_ingested
+        if i >= args.warmup:
+            times.append(dt)
+        del run
+    t = float(np.mean(times))
+    v = kmers / t
+    sample = (f"first {n} reads of the workload (k={K}, chunks={CHUNKS}); full algorithm: per-chunk tables, "
+              f"ordered merge, incremental histogram; one pass per step")
+    line = {
+        "impl": "reference", "metric": "kmers_counted_per_sec", "value": v, "unit": "kmers/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "kmers/s", "cores": 1, "kind": "port", "sample": sample,
+                         "note": "C oracle port of sharkmer src/kmer + src/io.rs (Rust reference cannot be "
+                                 "built here: no cargo); the reference counts on 1 thread regardless of -t"},
+        "e2e": {"value": v, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus):
+    return {"workload": f"C2: k={K}, {CHUNKS} chunks, {READS_PER_GPU * n_gpus} synthetic {READ_LEN} bp reads "
+                        f"({GENOME_PER_GPU * n_gpus} bp genome, {SUB_RATE} sub, {N_RATE} N, seed {SEED})",
+            "k": K, "chunks": CHUNKS, "reads": READS_PER_GPU * n_gpus, "read_len": READ_LEN,
+            "genome_len": GENOME_PER_GPU * n_gpus, "histo_max": HISTO_MAX,
+            "l2": "inputs (1.5 GB/GPU) and table (8.6 GB/GPU) exceed L2; no flush needed",
+            "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs: reads split, table sharded by k-mer hash, NCCL all-to-all"}
+
+
+# ----------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sharkmer_b200 import _lib, kmer
+    from oracle import oracle as o  # thresholds + cpu_baseline leg only
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_reads_total = args.reads_per_gpu * world
+    genome = GENOME_PER_GPU * world * args.reads_per_gpu // READS_PER_GPU
+    genome = max(genome, 1000)
+    mode = {"auto": _lib.INSERT_AUTO, "direct": _lib.INSERT_DIRECT, "partitioned": _lib.INSERT_PARTITIONED}[args.mode]
+    hint = int(DISTINCT_HINT_PER_GPU * args.reads_per_gpu / READS_PER_GPU)
+
+    stream = torch.cuda.Stream(device=dev)
+    eng = kmer.Engine(K, CHUNKS, HISTO_MAX, capacity_hint=hint, device=local_rank, insert_mode=mode,
+                      n_ranks=world, rank=rank, stream=stream.cuda_stream)
+    st, nt = o.rate_to_thresh(SUB_RATE), o.rate_to_thresh(N_RATE)
+    line = READ_LEN + 1
+
+    # ---- inputs: chunk c holds the reads of batches b = c (mod CHUNKS) (src/io.rs:355-361);
+    #      rank r takes the r-th contiguous slice of every chunk's 1000-read batches ---------------
+    d_bufs, h_bufs, n_local = [], [], []
+    for c in range(CHUNKS):
+        n_batches_c = len(range(c, (n_reads_total + 999) // 1000, CHUNKS))
+        lo, hi = n_batches_c * rank // world, n_batches_c * (rank + 1) // world
+        first, n = lo * 1000, (hi - lo) * 1000
+        # (n_reads_total is a multiple of 1000 * CHUNKS in every configuration used here)
+        t = torch.empty(n * line, dtype=torch.uint8, device=dev)
+        eng.synth_device(SEED, genome, READ_LEN, st, nt, c, CHUNKS, first, n, t.data_ptr())
+        d_bufs.append(t)
+        n_local.append(n)
+    torch.cuda.synchronize()
+    if not args.no_e2e:
+        for t in d_bufs:
+            h = torch.empty(t.numel(), dtype=torch.uint8, pin_memory=True)
+            h.copy_(t)
+            h_bufs.append(h)
+        torch.cuda.synchronize()
+    in_bytes = sum(t.numel() for t in d_bufs)
+
+    # ---- one step -------------------------------------------------------------------------------
+    def exchange_and_insert(c):
+        d_ptr, counts = eng.route_chunk(c, world)
+        send = torch.as_tensor(counts.astype(np.int64), device=dev)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+        rc = recv.cpu().numpy()
+        n_send, n_recv = int(counts.sum()), int(rc.sum())
+        src = _as_tensor(d_ptr, n_send, dev)
+        dst = torch.empty(max(n_recv, 1), dtype=torch.int64, device=dev)
+        with torch.cuda.stream(stream):
+            dist.all_to_all_single(dst[:n_recv], src, output_split_sizes=rc.tolist(),
+                                   input_split_sizes=counts.astype(np.int64).tolist())
+        stream.synchronize()
+        eng.insert_kmers_device(dst.data_ptr(), n_recv)
+        eng.snapshot_histogram(c)
+
+    def step(host_buffers: bool):
+        eng.reset()
+        for c in range(CHUNKS):
+            if host_buffers:
+                eng.ingest_ptr(c, h_bufs[c].data_ptr(), h_bufs[c].numel(), _lib.INGEST_ASYNC)
+            else:
+                eng.ingest_device(c, d_bufs[c].data_ptr(), d_bufs[c].numel())
+        if world == 1:
+            eng.finalize()
+            return eng.histogram(CHUNKS - 1)
+        eng.finalize_external()
+        for c in range(CHUNKS):
+            exchange_and_insert(c)
+        cols = np.stack([eng.histogram(c) for c in range(CHUNKS)]).astype(np.int64)
+        tcols = torch.as_tensor(cols, device=dev)
+        dist.all_reduce(tcols)
+        return tcols[-1].cpu().numpy().astype(np.uint64)
+
+    def timed(host_buffers: bool, steps: int, warmup: int):
+        for _ in range(warmup):
+            step(host_buffers)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            hist = step(host_buffers)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tm = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms, wall = float(tm[0]), float(tm[1]) / 1e3
+        return ms / steps, wall * 1e3 / steps, hist
+
+    # ---- parity guard before timing: GPU vs oracle on the bounded CPU sample (rank 0, N=1) ------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        run, reads, dt = cpu_sample(args.cpu_sample_reads, genome)
+        chk = kmer.Engine(K, CHUNKS, HISTO_MAX, capacity_hint=int(hint * args.cpu_sample_reads / args.reads_per_gpu) + 1000,
+                          device=local_rank, insert_mode=mode)
+        nb = args.cpu_sample_reads // 1000
+        for b in range(nb):
+            chk.ingest_batch(b % CHUNKS, reads[b * 1000 * line:(b + 1) * 1000 * line])
+        chk.finalize()
+        ok = chk.digest() == run.table().digest() and all(
+            (chk.histogram(c) == run.histogram(c)).all() for c in range(CHUNKS))
+        if not ok:
+            raise SystemExit("PARITY FAILURE: GPU table/histograms differ from the oracle on the CPU sample")
+        chk.close()
+        cpu = {"value": run.n_kmers_ingested / dt, "unit": "kmers/s", "cores": 1, "kind": "port",
+               "sample": f"first {args.cpu_sample_reads} reads of the workload, same k/chunks; "
+                         f"{dt:.1f} s; GPU result on this sample checked bit-exact (table digest + 10 histograms)"}
+        del run, reads
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, ms_wall, hist_dev = timed(False, args.steps, args.warmup)
+    stt = eng.stage_times()
+    tot = eng.totals()
+    digest_dev = eng.digest() if world == 1 else None
+    e2e = None
+    if not args.no_e2e:
+        ms_e2e, ms_e2e_wall, hist_e2e = timed(True, args.steps, args.warmup)
+        if not (hist_e2e == hist_dev).all():
+            raise SystemExit("PARITY FAILURE: host-buffer run and device-buffer run disagree")
+        if world == 1 and eng.digest() != digest_dev:
+            raise SystemExit("PARITY FAILURE: table digest differs between runs")
+        st2 = eng.stage_times()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- totals over ranks ------------------------------------------------------------------------
+    n_kmers_local = sum(eng.chunk_totals(c).n_kmers for c in range(CHUNKS))
+    n_bases_local = in_bytes - sum(n_local)
+    if world > 1:
+        tt = torch.tensor([n_kmers_local, n_bases_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(tt)
+        n_kmers, n_bases = int(tt[0]), int(tt[1])
+    else:
+        n_kmers, n_bases = n_kmers_local, n_bases_local
+        assert tot.n_kmers == n_kmers  # conservation: table mass == windows extracted
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        value = n_kmers / (ms_dev / 1e3)
+        # dominant kernel: the insert kernels (fused extract+insert, or list insert in partitioned mode)
+        n_ins = max(1, stt.launches[4])
+        ins_ms_per_launch = stt.insert / n_ins
+        alg_bytes_per_launch = (n_kmers_local * B_ALG_PER_KMER +
+                                (stt.insert_bases if stt.insert_bases else 0) * B_ALG_PER_BASE) / n_ins
+        if stt.insert_bases == 0:  # partitioned: the insert kernel reads the 8-byte k-mer list instead
+            alg_bytes_per_launch = n_kmers_local * (B_ALG_PER_KMER + 8.0) / n_ins
+        achieved = alg_bytes_per_launch / (ins_ms_per_launch * 1e-3) / 1e9
+        out = {
+            "metric": "kmers_counted_per_sec", "value": value, "unit": "kmers/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": workload_config(world),
+            "bases_per_sec": n_bases / (ms_dev / 1e3),
+            "ms_per_step_wall": ms_wall,
+            "insert_mode": args.mode,
+            "n_kmers": n_kmers, "n_distinct_rank0": int(tot.n_unique),
+            "stage_ms": {"pack": stt.pack, "count": stt.count, "partition": stt.partition, "insert": stt.insert,
+                         "histogram": stt.histogram, "grow": stt.grow, "finalize": stt.total_finalize},
+            "table": {"slots": int(stt.table_capacity), "bytes": int(stt.table_bytes),
+                      "load": float(tot.n_unique) / float(stt.table_capacity), "grows": int(stt.n_grows)},
+            "roofline": {"bound": "hbm", "kernel": "extract_insert_kernel" if stt.insert_bases else "insert_sorted_list_kernel",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "launches_per_step": int(n_ins), "ms_per_launch": ins_ms_per_launch,
+                         "algorithmic_bytes": "64 B per k-mer occurrence (sector in + sector out) + 0.375 B per packed base read",
+                         "kmers_per_sec_in_kernel": n_kmers_local / (stt.insert * 1e-3)},
+            "gpu_launches": int(stt.kernel_launches) * args.steps,
+            "clocks": clocks,
+        }
+        if args.gups:
+            g = {}
+            for name, var in (("load+red", 0), ("red_only", 1), ("load_only", 2)):
+                ms = eng.bench_gups(int(np.log2(stt.table_capacity)), 1 << 28, 3, var)
+                g[name] = (1 << 28) / (ms * 1e-3)
+            out["gups"] = g
+            out["roofline"]["random_access_frac"] = out["roofline"]["kmers_per_sec_in_kernel"] / g["load+red"]
+        if e2e is None and not args.no_e2e:
+            out["e2e"] = {"value": n_kmers / (ms_e2e / 1e3), "unit": "kmers/s",
+                          "h2d_bytes_per_step": int(in_bytes) * world,
+                          "d2h_bytes_per_step": int(CHUNKS * (HISTO_MAX + 2) * 8 + 64) * world,
+                          "ms_per_step": ms_e2e, "ms_per_step_wall": ms_e2e_wall,
+                          "stage_ms": {"h2d": st2.h2d, "pack": st2.pack, "insert": st2.insert, "histogram": st2.histogram},
+                          "api": "skm_ingest_batch(pinned host buffers) x10 -> skm_finalize -> skm_histogram"}
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+class _CudaArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+
+def _as_tensor(ptr, n, dev):
+    import torch
+    if n == 0:
+        return torch.empty(0, dtype=torch.int64, device=dev)
+    return torch.as_tensor(_CudaArray(ptr, n), device=dev)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "direct", "partitioned"])
+    ap.add_argument("--reads-per-gpu", type=int, default=READS_PER_GPU)
+    ap.add_argument("--cpu-sample-reads", type=int, default=CPU_SAMPLE_READS)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gups", action="store_true", help="also measure the random-access roofline probe")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

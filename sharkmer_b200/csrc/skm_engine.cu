@@ -1,0 +1,1254 @@
+// skm_engine.cu — host side of the C ABI (include/sharkmer_b200.h).
+//
+// One ctx = one GPU = one table partition.  Reads are staged in HBM as 2-bit
+// codes + break mask per chunk (pack kernel runs at ingest time, in stream
+// order); skm_finalize then walks the chunks in index order — extract+insert,
+// histogram snapshot — which is what consolidate_and_histogram's merge loop
+// computes (src/io.rs:1016-1047): column i of the histogram is the histogram of
+// the table that holds every read of chunks 0..i.
+//
+// There is no CPU fallback anywhere in this file.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sharkmer_b200.h"
+#include "skm_kernels.cuh"
+
+using namespace skm;
+
+namespace {
+
+constexpr double kMaxLoad = 0.70;       // grow before the table is fuller than this
+constexpr double kTargetLoad = 0.60;    // load at capacity_hint
+constexpr uint64_t kMinTile = 1ull << 22;  // k-mers; smallest tile worth a launch near the limit
+constexpr uint32_t kMinLog2Cap = 16;
+constexpr uint32_t kMaxBuckets = 4096;
+constexpr uint64_t kMaxListKmers = 1ull << 30;  // k-mer list budget per partition pass (8 GiB)
+
+enum Stage { ST_H2D, ST_PACK, ST_COUNT, ST_PART, ST_INSERT, ST_HISTO, ST_GROW, ST_FINALIZE, ST_N };
+
+struct Segment {
+    uint64_t *codes = nullptr;
+    uint32_t *breaks = nullptr;
+    uint64_t n_units = 0;
+    uint64_t n_bytes = 0;
+};
+
+struct ChunkState {
+    std::vector<Segment> segs;
+    uint64_t n_bytes = 0;       // staged bytes incl. separators
+    uint64_t n_windows_host = 0;
+    bool counted = false;
+};
+
+struct TimedSpan {
+    cudaEvent_t a, b;
+    int stage;
+};
+
+}  // namespace
+
+struct skm_ctx {
+    skm_params p{};
+    int device = 0;
+    uint32_t n_chunks = 1;
+    uint32_t n_ranks = 1;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    int sm_count = 148;
+
+    Slot *table = nullptr;
+    uint32_t log2cap = 0;
+    uint64_t capacity = 0;
+    uint64_t distinct_ub = 0;   // upper bound on occupied slots (host-side bookkeeping)
+
+    ChunkCounters *d_cc = nullptr;  // n_chunks
+    GlobalCounters *d_gc = nullptr;
+    unsigned long long *d_bins = nullptr;   // histo_max + 2
+    HistoTotals *d_tot = nullptr;
+    uint64_t *h_pinned = nullptr;           // small pinned scratch for read-backs
+    size_t h_pinned_words = 0;
+
+    std::vector<ChunkState> chunks;
+    std::vector<std::vector<uint64_t>> histos;  // per chunk snapshot
+    std::vector<bool> have_histo;
+    std::vector<ChunkCounters> h_cc;
+    HistoTotals last_tot{};
+    bool have_tot = false;
+    uint64_t n_bases_read = 0;
+    std::vector<uint64_t> chunk_bases_read;
+    uint64_t pos_base = 0;  // running byte position for error reports
+    bool finalized = false;
+    bool sticky_error = false;
+
+    // routing / partition scratch
+    unsigned long long *d_bucket_counts = nullptr, *d_bucket_offsets = nullptr, *d_bucket_cursors = nullptr;
+    unsigned long long *d_list = nullptr;
+    uint64_t list_cap = 0;
+
+    float stage_ms[ST_N] = {0};
+    uint32_t stage_launches[ST_N] = {0};
+    uint64_t insert_kmers = 0, insert_bases = 0;
+    bool own_stream = true;
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
+    uint32_t launches = 0;
+    uint32_t n_grows = 0;
+
+    std::string err;
+    std::mutex mu;
+};
+
+namespace {
+
+int32_t fail(skm_ctx *c, int32_t code, const char *fmt, ...) {
+    if (c) {
+        char buf[1024];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(c, e_ == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA,           \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+cudaEvent_t get_event(skm_ctx *c) {
+    if (!c->event_pool.empty()) {
+        cudaEvent_t e = c->event_pool.back();
+        c->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct Span {
+    skm_ctx *c;
+    cudaStream_t s;
+    TimedSpan t;
+    Span(skm_ctx *c_, int stage, cudaStream_t s_) : c(c_), s(s_) {
+        t.stage = stage;
+        t.a = get_event(c);
+        t.b = get_event(c);
+        cudaEventRecord(t.a, s);
+    }
+    ~Span() {
+        cudaEventRecord(t.b, s);
+        c->spans.push_back(t);
+    }
+};
+
+// Call only after the streams are synchronised.
+void collect_spans(skm_ctx *c) {
+    for (auto &t : c->spans) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) c->stage_ms[t.stage] += ms;
+        c->event_pool.push_back(t.a);
+        c->event_pool.push_back(t.b);
+    }
+    c->spans.clear();
+}
+
+uint32_t ceil_log2(uint64_t v) {
+    uint32_t l = 0;
+    while ((1ull << l) < v) l++;
+    return l;
+}
+
+inline uint32_t grid_for(uint64_t n, uint32_t block) { return (uint32_t)((n + block - 1) / block); }
+
+int32_t alloc_table(skm_ctx *c, uint32_t log2cap, Slot **out) {
+    Slot *t = nullptr;
+    const uint64_t cap = 1ull << log2cap;
+    CU(cudaMallocAsync((void **)&t, cap * sizeof(Slot), c->stream));
+    table_clear_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(t, cap);
+    c->launches++;
+    CU(cudaGetLastError());
+    *out = t;
+    return SKM_OK;
+}
+
+int32_t read_distinct(skm_ctx *c, uint64_t *out) {
+    CU(cudaMemcpyAsync(c->h_pinned, &c->d_gc->n_distinct, sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = c->h_pinned[0];
+    return SKM_OK;
+}
+
+int32_t grow_table(skm_ctx *c, uint32_t new_log2cap) {
+    Span sp(c, ST_GROW, c->stream);
+    Slot *nt = nullptr;
+    int32_t rc = alloc_table(c, new_log2cap, &nt);
+    if (rc) return rc;
+    rehash_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity, nt, new_log2cap);
+    c->launches++;
+    c->stage_launches[ST_GROW]++;
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(c->table, c->stream));
+    c->table = nt;
+    c->log2cap = new_log2cap;
+    c->capacity = 1ull << new_log2cap;
+    c->n_grows++;
+    return SKM_OK;
+}
+
+// Make room for `want` more k-mers if possible; returns how many may be
+// inserted now without risking load > kMaxLoad (>= min(want, kMinTile)).
+int32_t reserve_headroom(skm_ctx *c, uint64_t want, uint64_t *granted) {
+    auto headroom = [&]() -> uint64_t {
+        const uint64_t limit = (uint64_t)(kMaxLoad * (double)c->capacity);
+        return limit > c->distinct_ub ? limit - c->distinct_ub : 0;
+    };
+    const uint64_t need = std::min(want, kMinTile);
+    if (headroom() < need) {
+        // the bound counts every inserted k-mer as new; tighten it with the real count
+        uint64_t d = 0;
+        int32_t rc = read_distinct(c, &d);
+        if (rc) return rc;
+        c->distinct_ub = d;
+        if (headroom() < need) {
+            uint32_t nl = c->log2cap + 1;
+            while ((uint64_t)(kTargetLoad * (double)(1ull << nl)) < d + need * 4) nl++;
+            rc = grow_table(c, nl);
+            if (rc) return rc;
+        }
+    }
+    *granted = std::min(want, headroom());
+    return SKM_OK;
+}
+
+int32_t ensure_list(skm_ctx *c, uint64_t n) {
+    if (n <= c->list_cap) return SKM_OK;
+    if (c->d_list) CU(cudaFreeAsync(c->d_list, c->stream));
+    c->d_list = nullptr;
+    c->list_cap = 0;
+    CU(cudaMallocAsync((void **)&c->d_list, std::max<uint64_t>(n, 1024) * sizeof(uint64_t), c->stream));
+    c->list_cap = std::max<uint64_t>(n, 1024);
+    return SKM_OK;
+}
+
+// ---- direct mode: fused extract + insert over one segment -------------------
+int32_t insert_segment_direct(skm_ctx *c, const Segment &sg, uint32_t chunk) {
+    uint64_t u = 0;
+    while (u < sg.n_units) {
+        uint64_t granted = 0;
+        int32_t rc = reserve_headroom(c, (sg.n_units - u) * 32, &granted);
+        if (rc) return rc;
+        uint64_t tile_units = std::max<uint64_t>(granted / 32, 1);
+        tile_units = std::min(tile_units, sg.n_units - u);
+        {
+            Span sp(c, ST_INSERT, c->stream);
+            extract_insert_kernel<<<grid_for(tile_units, 256), 256, 0, c->stream>>>(
+                sg.codes, sg.breaks, u, u + tile_units, c->p.k, c->table, c->log2cap, &c->d_cc[chunk],
+                c->d_gc);
+            c->launches++;
+            c->stage_launches[ST_INSERT]++;
+            c->insert_bases += std::min(tile_units * 32, sg.n_bytes - u * 32);
+        }
+        CU(cudaGetLastError());
+        c->distinct_ub += tile_units * 32;
+        u += tile_units;
+    }
+    return SKM_OK;
+}
+
+uint32_t partition_log2_buckets(const skm_ctx *c) {
+    // regions of <= 2 MiB (2^17 slots), at most kMaxBuckets
+    int l = (int)c->log2cap - 17;
+    if (l < 0) l = 0;
+    uint32_t maxl = ceil_log2(kMaxBuckets);
+    return std::min<uint32_t>((uint32_t)l, maxl);
+}
+
+// Bucket the k-mers of segments [s0, s1) of a chunk.  On return d_list holds them
+// grouped by bucket; h_counts (optional) receives the per-bucket counts.
+int32_t bucket_segments(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn fn,
+                        uint32_t n_buckets, uint64_t *total_out, uint64_t *h_counts) {
+    const ChunkState &cs = c->chunks[chunk];
+    CU(cudaMemsetAsync(c->d_bucket_counts, 0, (n_buckets + 1) * sizeof(uint64_t), c->stream));
+    {
+        Span sp(c, ST_COUNT, c->stream);
+        for (size_t s = s0; s < s1; s++) {
+            const Segment &sg = cs.segs[s];
+            if (!sg.n_units) continue;
+            bucket_count_kernel<<<grid_for(sg.n_units, 256), 256, n_buckets * sizeof(uint32_t), c->stream>>>(
+                sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_counts,
+                &c->d_cc[chunk]);
+            c->launches++;
+            c->stage_launches[ST_COUNT]++;
+        }
+        bucket_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_bucket_counts, n_buckets, c->d_bucket_offsets,
+                                                       c->d_bucket_cursors);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    // total (and optionally the counts) back to the host
+    CU(cudaMemcpyAsync(c->h_pinned, c->d_bucket_offsets + n_buckets, sizeof(uint64_t),
+                       cudaMemcpyDeviceToHost, c->stream));
+    if (h_counts)
+        CU(cudaMemcpyAsync(c->h_pinned + 1, c->d_bucket_counts, n_buckets * sizeof(uint64_t),
+                           cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const uint64_t total = c->h_pinned[0];
+    if (h_counts) memcpy(h_counts, c->h_pinned + 1, n_buckets * sizeof(uint64_t));
+    int32_t rc = ensure_list(c, total);
+    if (rc) return rc;
+    {
+        Span sp(c, ST_PART, c->stream);
+        const size_t smem = ((n_buckets + 1) & ~1u) * sizeof(uint32_t) + n_buckets * sizeof(uint64_t);
+        for (size_t s = s0; s < s1; s++) {
+            const Segment &sg = cs.segs[s];
+            if (!sg.n_units) continue;
+            bucket_scatter_kernel<<<grid_for(sg.n_units, 256), 256, smem, c->stream>>>(
+                sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, c->d_list);
+            c->launches++;
+            c->stage_launches[ST_PART]++;
+        }
+    }
+    CU(cudaGetLastError());
+    *total_out = total;
+    return SKM_OK;
+}
+
+int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, uint64_t n, bool sorted) {
+    uint64_t i = 0;
+    while (i < n) {
+        uint64_t granted = 0;
+        int32_t rc = reserve_headroom(c, n - i, &granted);
+        if (rc) return rc;
+        granted = std::max<uint64_t>(std::min(granted, n - i), 1);
+        {
+            Span sp(c, ST_INSERT, c->stream);
+            if (sorted)
+                insert_sorted_list_kernel<<<grid_for(granted, 256), 256, 0, c->stream>>>(
+                    d_kmers + i, granted, c->table, c->log2cap, c->d_gc);
+            else
+                insert_list_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_kmers + i, granted, c->table,
+                                                                           c->log2cap, c->d_gc);
+            c->launches++;
+            c->stage_launches[ST_INSERT]++;
+            c->insert_kmers += granted;
+        }
+        CU(cudaGetLastError());
+        c->distinct_ub += granted;
+        i += granted;
+    }
+    return SKM_OK;
+}
+
+// ---- partitioned mode: bucket by table region, then insert region by region --
+int32_t insert_chunk_partitioned(skm_ctx *c, uint32_t chunk) {
+    const ChunkState &cs = c->chunks[chunk];
+    size_t s0 = 0;
+    while (s0 < cs.segs.size()) {
+        // group segments up to the list budget
+        size_t s1 = s0;
+        uint64_t bytes = 0;
+        while (s1 < cs.segs.size() && (s1 == s0 || bytes + cs.segs[s1].n_bytes <= kMaxListKmers)) {
+            bytes += cs.segs[s1].n_bytes;
+            s1++;
+        }
+        // the table must not grow between bucketing and inserting (buckets are table regions)
+        uint64_t granted = 0;
+        int32_t rc = reserve_headroom(c, bytes, &granted);
+        if (rc) return rc;
+        if (granted < bytes) {
+            // not enough guaranteed headroom for the whole group: tighten or grow until it fits
+            uint64_t d = 0;
+            rc = read_distinct(c, &d);
+            if (rc) return rc;
+            c->distinct_ub = d;
+            uint32_t nl = c->log2cap;
+            while ((uint64_t)(kMaxLoad * (double)(1ull << nl)) < d + bytes) nl++;
+            if (nl != c->log2cap) {
+                rc = grow_table(c, nl);
+                if (rc) return rc;
+            }
+        }
+        BucketFn fn;
+        fn.mode = 1;
+        fn.n_ranks = 1;
+        fn.log2cap = c->log2cap;
+        fn.log2buckets = partition_log2_buckets(c);
+        const uint32_t n_buckets = 1u << fn.log2buckets;
+        uint64_t total = 0;
+        rc = bucket_segments(c, chunk, s0, s1, fn, n_buckets, &total, nullptr);
+        if (rc) return rc;
+        rc = insert_list(c, c->d_list, total, true);
+        if (rc) return rc;
+        s0 = s1;
+    }
+    return SKM_OK;
+}
+
+int32_t snapshot_histogram(skm_ctx *c, uint32_t chunk_i, bool want_digest) {
+    const uint64_t nb = c->p.histo_max + 2;
+    CU(cudaMemsetAsync(c->d_bins, 0, nb * sizeof(uint64_t), c->stream));
+    CU(cudaMemsetAsync(c->d_tot, 0, sizeof(HistoTotals), c->stream));
+    const uint32_t n_smem_bins = (uint32_t)std::min<uint64_t>(nb, 12288);
+    const size_t smem = (kLowBins * 32 + n_smem_bins) * sizeof(uint32_t);
+    {
+        Span sp(c, ST_HISTO, c->stream);
+        histogram_kernel<<<c->sm_count * 4, 512, smem, c->stream>>>(c->table, c->capacity, c->p.histo_max,
+                                                                    n_smem_bins, c->d_bins, c->d_tot,
+                                                                    want_digest ? 1 : 0);
+        c->launches++;
+        c->stage_launches[ST_HISTO]++;
+    }
+    CU(cudaGetLastError());
+    if (chunk_i < c->n_chunks) {
+        c->histos[chunk_i].assign(nb, 0);
+        CU(cudaMemcpyAsync(c->histos[chunk_i].data(), c->d_bins, nb * sizeof(uint64_t),
+                           cudaMemcpyDeviceToHost, c->stream));
+        c->have_histo[chunk_i] = true;
+    }
+    CU(cudaMemcpyAsync(&c->last_tot, c->d_tot, sizeof(HistoTotals), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_tot = true;
+    return SKM_OK;
+}
+
+int32_t check_sticky(skm_ctx *c) {
+    // requires stream sync done by the caller
+    GlobalCounters gc;
+    CU(cudaMemcpy(&gc, c->d_gc, sizeof gc, cudaMemcpyDeviceToHost));
+    if (gc.first_bad != ~0ull) {
+        c->sticky_error = true;
+        const unsigned ch = (unsigned)(gc.first_bad & 0xFF);
+        const unsigned long long pos = gc.first_bad >> 8;
+        char shown[8];
+        if (ch >= 0x20 && ch < 0x7F)
+            snprintf(shown, sizeof shown, "%c", (char)ch);
+        else
+            snprintf(shown, sizeof shown, "\\x%02x", ch);
+        // text of src/kmer/encoding.rs:353-356, plus where it was found
+        return fail(c, SKM_ERR_INVALID_BASE,
+                    "Invalid character '%s' in sequence. Only ACGTN allowed. (byte %llu of the ingested stream)",
+                    shown, pos);
+    }
+    return SKM_OK;
+}
+
+int32_t refresh_chunk_counters(skm_ctx *c) {
+    CU(cudaMemcpy(c->h_cc.data(), c->d_cc, c->n_chunks * sizeof(ChunkCounters), cudaMemcpyDeviceToHost));
+    return SKM_OK;
+}
+
+// Stage one batch that is already in device memory.
+int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t n_bytes) {
+    if (n_bytes == 0) return SKM_OK;
+    Segment sg;
+    sg.n_bytes = n_bytes;
+    sg.n_units = (n_bytes + 31) / 32;
+    CU(cudaMallocAsync((void **)&sg.codes, sg.n_units * sizeof(uint64_t), c->stream));
+    CU(cudaMallocAsync((void **)&sg.breaks, sg.n_units * sizeof(uint32_t), c->stream));
+    {
+        Span sp(c, ST_PACK, c->stream);
+        pack_kernel<<<grid_for(sg.n_units, 256), 256, 0, c->stream>>>(d_seqs, n_bytes, c->pos_base, sg.codes,
+                                                                      sg.breaks, sg.n_units, &c->d_cc[chunk],
+                                                                      c->d_gc);
+        c->launches++;
+        c->stage_launches[ST_PACK]++;
+    }
+    CU(cudaGetLastError());
+    c->pos_base += n_bytes;
+    c->chunks[chunk].segs.push_back(sg);
+    c->chunks[chunk].n_bytes += n_bytes;
+    return SKM_OK;
+}
+
+int32_t check_ingest_args(skm_ctx *c, uint32_t chunk, const void *p, uint64_t n) {
+    if (!c) return SKM_ERR_INVALID_ARG;
+    if (c->finalized) return fail(c, SKM_ERR_STATE, "ingest after finalize");
+    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index %u out of range (n_chunks %u)", chunk, c->n_chunks);
+    if (n && !p) return fail(c, SKM_ERR_INVALID_ARG, "null buffer");
+    return SKM_OK;
+}
+
+}  // namespace
+
+// ============================================================================
+// C ABI
+// ============================================================================
+
+extern "C" {
+
+uint32_t skm_abi_version(void) { return SKM_ABI_VERSION; }
+
+int32_t skm_create(const skm_params *params, skm_ctx **out) {
+    if (!params || !out) return SKM_ERR_INVALID_ARG;
+    *out = nullptr;
+    skm_ctx *c = new (std::nothrow) skm_ctx();
+    if (!c) return SKM_ERR_OOM;
+    *out = c;  // returned even on failure so the caller can read skm_last_error, then destroy
+    if (params->struct_size != sizeof(skm_params))
+        return fail(c, SKM_ERR_INVALID_ARG, "skm_params.struct_size %u != %zu", params->struct_size, sizeof(skm_params));
+    c->p = *params;
+    // src/cli.rs:662-667
+    if (c->p.k < 1 || c->p.k >= 32) return fail(c, SKM_ERR_INVALID_ARG, "k must be less than 32 (and at least 1), got %u", c->p.k);
+    if (c->p.k % 2 == 0) return fail(c, SKM_ERR_INVALID_ARG, "k must be odd, got %u", c->p.k);
+    // src/cli.rs:668-673
+    if (c->p.histo_max < 1 || c->p.histo_max > 1000000)
+        return fail(c, SKM_ERR_INVALID_ARG, "histo_max must be between 1 and 1000000, got %llu", (unsigned long long)c->p.histo_max);
+    c->n_chunks = c->p.chunks == 0 ? 1 : c->p.chunks;  // src/io.rs:378
+    c->n_ranks = c->p.n_ranks == 0 ? 1 : c->p.n_ranks;
+    if (c->p.rank >= c->n_ranks) return fail(c, SKM_ERR_INVALID_ARG, "rank %u >= n_ranks %u", c->p.rank, c->n_ranks);
+    if (c->n_ranks > kMaxBuckets) return fail(c, SKM_ERR_INVALID_ARG, "n_ranks too large");
+    if (c->p.insert_mode > SKM_INSERT_PARTITIONED) return fail(c, SKM_ERR_INVALID_ARG, "bad insert_mode");
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(c, SKM_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+    int dev = c->p.device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    if (dev >= n_dev) return fail(c, SKM_ERR_INVALID_ARG, "device %d out of range (%d devices)", dev, n_dev);
+    c->device = dev;
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    c->sm_count = prop.multiProcessorCount;
+    if (c->p.stream) {
+        c->stream = (cudaStream_t)(uintptr_t)c->p.stream;
+        c->own_stream = false;
+    } else {
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    }
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    // keep freed blocks in the stream-ordered pool (staging buffers are recycled every batch)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    CU(cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CU(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+
+    CU(cudaMalloc((void **)&c->d_cc, c->n_chunks * sizeof(ChunkCounters)));
+    CU(cudaMemset(c->d_cc, 0, c->n_chunks * sizeof(ChunkCounters)));
+    CU(cudaMalloc((void **)&c->d_gc, sizeof(GlobalCounters)));
+    GlobalCounters gc{};
+    gc.first_bad = ~0ull;
+    CU(cudaMemcpy(c->d_gc, &gc, sizeof gc, cudaMemcpyHostToDevice));
+    CU(cudaMalloc((void **)&c->d_bins, (c->p.histo_max + 2) * sizeof(uint64_t)));
+    CU(cudaMalloc((void **)&c->d_tot, sizeof(HistoTotals)));
+    c->h_pinned_words = kMaxBuckets + 16;
+    CU(cudaMallocHost((void **)&c->h_pinned, c->h_pinned_words * sizeof(uint64_t)));
+    CU(cudaMalloc((void **)&c->d_bucket_counts, (kMaxBuckets + 1) * sizeof(uint64_t)));
+    CU(cudaMalloc((void **)&c->d_bucket_offsets, (kMaxBuckets + 1) * sizeof(uint64_t)));
+    CU(cudaMalloc((void **)&c->d_bucket_cursors, (kMaxBuckets + 1) * sizeof(uint64_t)));
+
+    c->chunks.resize(c->n_chunks);
+    c->histos.resize(c->n_chunks);
+    c->have_histo.assign(c->n_chunks, false);
+    c->h_cc.assign(c->n_chunks, ChunkCounters{});
+    c->chunk_bases_read.assign(c->n_chunks, 0);
+
+    uint32_t l2 = kMinLog2Cap;
+    if (c->p.capacity_hint) l2 = std::max(l2, ceil_log2((uint64_t)((double)c->p.capacity_hint / kTargetLoad) + 1));
+    if (l2 > 36) return fail(c, SKM_ERR_INVALID_ARG, "capacity_hint too large");
+    int32_t rc = alloc_table(c, l2, &c->table);
+    if (rc) return rc;
+    c->log2cap = l2;
+    c->capacity = 1ull << l2;
+    CU(cudaStreamSynchronize(c->stream));
+    return SKM_OK;
+}
+
+void skm_destroy(skm_ctx *c) {
+    if (!c) return;
+    if (c->stream) {
+        DeviceGuard g(c->device);
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->copy_stream);
+        for (auto &cs : c->chunks)
+            for (auto &sg : cs.segs) {
+                cudaFree(sg.codes);
+                cudaFree(sg.breaks);
+            }
+        cudaFree(c->table);
+        cudaFree(c->d_cc);
+        cudaFree(c->d_gc);
+        cudaFree(c->d_bins);
+        cudaFree(c->d_tot);
+        cudaFree(c->d_bucket_counts);
+        cudaFree(c->d_bucket_offsets);
+        cudaFree(c->d_bucket_cursors);
+        cudaFree(c->d_list);
+        cudaFreeHost(c->h_pinned);
+        for (auto &t : c->spans) {
+            cudaEventDestroy(t.a);
+            cudaEventDestroy(t.b);
+        }
+        for (auto e : c->event_pool) cudaEventDestroy(e);
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        cudaStreamDestroy(c->copy_stream);
+    }
+    delete c;
+}
+
+const char *skm_last_error(const skm_ctx *c) { return c ? c->err.c_str() : "null ctx"; }
+
+int32_t skm_pinned_alloc(skm_ctx *c, size_t bytes, void **out) {
+    if (!c || !out) return SKM_ERR_INVALID_ARG;
+    DeviceGuard g(c->device);
+    CU(cudaMallocHost(out, bytes ? bytes : 1));
+    return SKM_OK;
+}
+
+int32_t skm_pinned_free(skm_ctx *c, void *ptr) {
+    if (!c) return SKM_ERR_INVALID_ARG;
+    DeviceGuard g(c->device);
+    CU(cudaFreeHost(ptr));
+    return SKM_OK;
+}
+
+int32_t skm_device_alloc(skm_ctx *c, size_t bytes, void **out) {
+    if (!c || !out) return SKM_ERR_INVALID_ARG;
+    DeviceGuard g(c->device);
+    CU(cudaMalloc(out, bytes ? bytes : 1));
+    return SKM_OK;
+}
+
+int32_t skm_device_free(skm_ctx *c, void *ptr) {
+    if (!c) return SKM_ERR_INVALID_ARG;
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(ptr));
+    return SKM_OK;
+}
+
+int32_t skm_memcpy_d2h(skm_ctx *c, void *dst, const void *d_src, size_t bytes) {
+    if (!c) return SKM_ERR_INVALID_ARG;
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return SKM_OK;
+}
+
+int32_t skm_memcpy_h2d(skm_ctx *c, void *d_dst, const void *src, size_t bytes) {
+    if (!c) return SKM_ERR_INVALID_ARG;
+    DeviceGuard g(c->device);
+    CU(cudaMemcpy(d_dst, src, bytes, cudaMemcpyHostToDevice));
+    return SKM_OK;
+}
+
+int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64_t n_bytes, uint32_t flags) {
+    int32_t rc = check_ingest_args(c, chunk, seqs, n_bytes);
+    if (rc) return rc;
+    if (n_bytes == 0) return SKM_OK;
+    if (seqs[n_bytes - 1] != '\n')
+        return fail(c, SKM_ERR_INVALID_ARG, "batch must end with a newline-terminated sequence line");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    uint8_t *d_raw = nullptr;
+    CU(cudaMallocAsync((void **)&d_raw, n_bytes, c->stream));
+    {
+        Span sp(c, ST_H2D, c->stream);
+        CU(cudaMemcpyAsync(d_raw, seqs, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (!(flags & SKM_INGEST_ASYNC)) CU(cudaStreamSynchronize(c->stream));
+    rc = stage_device(c, chunk, d_raw, n_bytes);
+    CU(cudaFreeAsync(d_raw, c->stream));
+    return rc;
+}
+
+int32_t skm_ingest_reads(skm_ctx *c, uint32_t chunk, const uint8_t *bases, const uint64_t *offsets,
+                         uint64_t n_reads) {
+    int32_t rc = check_ingest_args(c, chunk, offsets, n_reads);
+    if (rc) return rc;
+    if (n_reads == 0) return SKM_OK;
+    const uint64_t n_bases = offsets[n_reads] - offsets[0];
+    if (n_bases && !bases) return fail(c, SKM_ERR_INVALID_ARG, "null buffer");
+    for (uint64_t i = 0; i < n_reads; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(c, SKM_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    uint8_t *d_bases = nullptr, *d_lines = nullptr;
+    uint64_t *d_off = nullptr;
+    const uint64_t n_out = offsets[n_reads] + n_reads;  // dst offset of read r = offsets[r] + r
+    CU(cudaMallocAsync((void **)&d_bases, offsets[n_reads] + 1, c->stream));
+    CU(cudaMallocAsync((void **)&d_off, (n_reads + 1) * sizeof(uint64_t), c->stream));
+    CU(cudaMallocAsync((void **)&d_lines, n_out, c->stream));
+    {
+        Span sp(c, ST_H2D, c->stream);
+        if (offsets[n_reads])
+            CU(cudaMemcpyAsync(d_bases, bases, offsets[n_reads], cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_off, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    add_separators_kernel<<<grid_for(n_reads * 32, 256), 256, 0, c->stream>>>(d_bases, d_off, n_reads, d_lines);
+    c->launches++;
+    CU(cudaGetLastError());
+    // bytes before offsets[0] are not part of any read: skip them
+    rc = stage_device(c, chunk, d_lines + offsets[0], n_out - offsets[0]);
+    CU(cudaFreeAsync(d_bases, c->stream));
+    CU(cudaFreeAsync(d_off, c->stream));
+    CU(cudaFreeAsync(d_lines, c->stream));
+    return rc;
+}
+
+int32_t skm_ingest_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t n_bytes) {
+    int32_t rc = check_ingest_args(c, chunk, d_seqs, n_bytes);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    return stage_device(c, chunk, d_seqs, n_bytes);
+}
+
+int32_t skm_sync(skm_ctx *c) {
+    if (!c) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    collect_spans(c);
+    return check_sticky(c);
+}
+
+static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
+    if (c->finalized) return fail(c, SKM_ERR_STATE, "finalize called twice");
+    CU(cudaStreamSynchronize(c->stream));
+    int32_t rc = check_sticky(c);  // an invalid base aborts the run before anything is counted
+    if (rc) return rc;
+    rc = refresh_chunk_counters(c);
+    if (rc) return rc;
+    uint64_t n_reads = 0;
+    for (auto &cc : c->h_cc) n_reads += cc.n_reads;
+    if (n_reads == 0 && run_chunk_loop)  // src/io.rs:578-580
+        return fail(c, SKM_ERR_NO_READS, "No reads were ingested. Check that input files contain valid FASTQ records.");
+    c->finalized = true;
+    if (!run_chunk_loop) return SKM_OK;
+
+    cudaEvent_t e0 = get_event(c), e1 = get_event(c);
+    cudaEventRecord(e0, c->stream);
+    for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
+        ChunkState &cs = c->chunks[ch];
+        uint32_t mode = c->p.insert_mode;
+        if (mode == SKM_INSERT_AUTO) mode = SKM_INSERT_DIRECT;
+        if (mode == SKM_INSERT_PARTITIONED) {
+            rc = insert_chunk_partitioned(c, ch);
+            if (rc) return rc;
+        } else {
+            for (auto &sg : cs.segs) {
+                rc = insert_segment_direct(c, sg, ch);
+                if (rc) return rc;
+            }
+        }
+        for (auto &sg : cs.segs) {  // drop(chunk), src/io.rs:1025
+            CU(cudaFreeAsync(sg.codes, c->stream));
+            CU(cudaFreeAsync(sg.breaks, c->stream));
+            sg.codes = nullptr;
+            sg.breaks = nullptr;
+        }
+        cs.counted = true;
+        if (c->p.chunks > 0) {
+            rc = snapshot_histogram(c, ch, false);
+            if (rc) return rc;
+        }
+    }
+    if (c->p.chunks == 0) {
+        // totals for the conservation check (no histogram is kept, as in the reference)
+        rc = snapshot_histogram(c, c->n_chunks /* no column */, false);
+        if (rc) return rc;
+    }
+    cudaEventRecord(e1, c->stream);
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->stage_ms[ST_FINALIZE] += ms;
+    c->event_pool.push_back(e0);
+    c->event_pool.push_back(e1);
+    collect_spans(c);
+    rc = refresh_chunk_counters(c);
+    if (rc) return rc;
+
+    // conservation identities (src/io.rs:1042-1047, 1120-1132)
+    uint64_t n_windows = 0;
+    for (auto &cc : c->h_cc) n_windows += cc.n_windows;
+    uint64_t d = 0;
+    rc = read_distinct(c, &d);
+    if (rc) return rc;
+    c->distinct_ub = d;
+    if (c->last_tot.n_saturated == 0 && c->last_tot.n_kmers != n_windows)
+        return fail(c, SKM_ERR_CONSERVATION,
+                    "The total count of hashed kmers (%llu) does not equal the number of ingested kmers (%llu)",
+                    (unsigned long long)c->last_tot.n_kmers, (unsigned long long)n_windows);
+    if (c->last_tot.n_distinct != d)
+        return fail(c, SKM_ERR_CONSERVATION,
+                    "The total count of unique kmers in the histogram (%llu) does not equal the total count of hashed kmers (%llu)",
+                    (unsigned long long)c->last_tot.n_distinct, (unsigned long long)d);
+    if (c->p.chunks > 0) {
+        const std::vector<uint64_t> &h = c->histos[c->n_chunks - 1];
+        uint64_t uniq = 0;
+        for (size_t i = 1; i < h.size(); i++) uniq += h[i];
+        if (uniq != d)
+            return fail(c, SKM_ERR_CONSERVATION,
+                        "The total count of unique kmers in the histogram (%llu) does not equal the total count of hashed kmers (%llu)",
+                        (unsigned long long)uniq, (unsigned long long)d);
+    }
+    return SKM_OK;
+}
+
+int32_t skm_finalize(skm_ctx *c) {
+    if (!c) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    return finalize_common(c, true);
+}
+
+int32_t skm_reset(skm_ctx *c) {
+    if (!c) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    for (auto &cs : c->chunks) {
+        for (auto &sg : cs.segs) {
+            if (sg.codes) CU(cudaFreeAsync(sg.codes, c->stream));
+            if (sg.breaks) CU(cudaFreeAsync(sg.breaks, c->stream));
+        }
+        cs = ChunkState{};
+    }
+    table_clear_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(c->d_cc, 0, c->n_chunks * sizeof(ChunkCounters), c->stream));
+    GlobalCounters gc{};
+    gc.first_bad = ~0ull;
+    CU(cudaMemcpyAsync(c->d_gc, &gc, sizeof gc, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    collect_spans(c);
+    for (int i = 0; i < ST_N; i++) {
+        c->stage_ms[i] = 0;
+        c->stage_launches[i] = 0;
+    }
+    c->insert_kmers = c->insert_bases = 0;
+    c->launches = 0;
+    c->n_grows = 0;
+    c->distinct_ub = 0;
+    c->pos_base = 0;
+    c->have_tot = false;
+    c->finalized = false;
+    c->sticky_error = false;
+    c->have_histo.assign(c->n_chunks, false);
+    c->h_cc.assign(c->n_chunks, ChunkCounters{});
+    c->err.clear();
+    return SKM_OK;
+}
+
+int32_t skm_finalize_external(skm_ctx *c) {
+    if (!c) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    return finalize_common(c, false);
+}
+
+int32_t skm_histogram(skm_ctx *c, uint32_t chunk_i, uint64_t *out, uint64_t out_len) {
+    if (!c || !out) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (chunk_i >= c->n_chunks || !c->have_histo[chunk_i])
+        return fail(c, SKM_ERR_STATE, "no histogram snapshot for chunk %u (chunks=%u, finalized=%d)", chunk_i, c->p.chunks, (int)c->finalized);
+    if (out_len < c->p.histo_max + 2) return fail(c, SKM_ERR_INVALID_ARG, "histogram buffer too small");
+    memcpy(out, c->histos[chunk_i].data(), (c->p.histo_max + 2) * sizeof(uint64_t));
+    return SKM_OK;
+}
+
+static int32_t refresh_totals(skm_ctx *c) {
+    // table-wide totals come from a histogram pass; refresh if the table changed since
+    int32_t rc = SKM_OK;
+    if (!c->have_tot) rc = snapshot_histogram(c, c->n_chunks, false);
+    return rc;
+}
+
+int32_t skm_totals_get(skm_ctx *c, skm_totals *out) {
+    if (!c || !out) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    int32_t rc = refresh_chunk_counters(c);
+    if (rc) return rc;
+    rc = refresh_totals(c);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    for (uint32_t i = 0; i < c->n_chunks; i++) {
+        out->n_reads += c->h_cc[i].n_reads;
+        out->n_bases += c->h_cc[i].n_bases;
+        out->n_bases_read += c->chunks[i].n_bytes - c->h_cc[i].n_reads;
+    }
+    out->n_kmers = c->last_tot.n_kmers;
+    out->n_unique = c->last_tot.n_distinct;
+    out->n_saturated = c->last_tot.n_saturated;
+    if (c->p.chunks > 0 && c->have_histo[c->n_chunks - 1]) out->n_singletons = c->histos[c->n_chunks - 1][1];
+    return SKM_OK;
+}
+
+int32_t skm_chunk_totals(skm_ctx *c, uint32_t chunk, skm_totals *out) {
+    if (!c || !out) return SKM_ERR_INVALID_ARG;
+    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    int32_t rc = refresh_chunk_counters(c);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    out->n_reads = c->h_cc[chunk].n_reads;
+    out->n_bases = c->h_cc[chunk].n_bases;
+    out->n_bases_read = c->chunks[chunk].n_bytes - c->h_cc[chunk].n_reads;
+    out->n_kmers = c->h_cc[chunk].n_windows;  // Chunk::get_n_kmers: occurrences counted for this chunk
+    return SKM_OK;
+}
+
+int32_t skm_stage_times(skm_ctx *c, skm_stage_ms *out) {
+    if (!c || !out) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    collect_spans(c);
+    out->h2d = c->stage_ms[ST_H2D];
+    out->pack = c->stage_ms[ST_PACK];
+    out->count = c->stage_ms[ST_COUNT];
+    out->partition = c->stage_ms[ST_PART];
+    out->insert = c->stage_ms[ST_INSERT];
+    out->histogram = c->stage_ms[ST_HISTO];
+    out->grow = c->stage_ms[ST_GROW];
+    out->total_finalize = c->stage_ms[ST_FINALIZE];
+    for (int i = 0; i < 8; i++) out->launches[i] = c->stage_launches[i];
+    out->insert_kmers = c->insert_kmers;
+    out->insert_bases = c->insert_bases;
+    out->kernel_launches = c->launches;
+    out->n_grows = c->n_grows;
+    out->table_capacity = c->capacity;
+    out->table_bytes = c->capacity * sizeof(Slot);
+    return SKM_OK;
+}
+
+int32_t skm_table_len(skm_ctx *c, uint64_t *out) {
+    if (!c || !out) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    return read_distinct(c, out);
+}
+
+int32_t skm_export(skm_ctx *c, uint64_t *keys, uint32_t *counts, uint64_t cap, int32_t sorted, uint64_t *n_out) {
+    if (!c || !n_out) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    uint64_t n = 0;
+    int32_t rc = read_distinct(c, &n);
+    if (rc) return rc;
+    *n_out = n;
+    if (!keys && !counts) return SKM_OK;  // size query
+    if (!keys || !counts || cap < n)
+        return fail(c, SKM_ERR_INVALID_ARG, "export buffers too small: need %llu", (unsigned long long)n);
+    if (n == 0) return SKM_OK;
+    unsigned long long *d_keys = nullptr, *d_cursor = nullptr;
+    uint32_t *d_counts = nullptr;
+    CU(cudaMallocAsync((void **)&d_keys, n * sizeof(uint64_t), c->stream));
+    CU(cudaMallocAsync((void **)&d_counts, n * sizeof(uint32_t), c->stream));
+    CU(cudaMallocAsync((void **)&d_cursor, sizeof(uint64_t), c->stream));
+    CU(cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), c->stream));
+    export_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity, d_keys, d_counts, n, d_cursor);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(keys, d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(counts, d_counts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_pinned, d_cursor, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFreeAsync(d_keys, c->stream));
+    CU(cudaFreeAsync(d_counts, c->stream));
+    CU(cudaFreeAsync(d_cursor, c->stream));
+    if (c->h_pinned[0] != n)
+        return fail(c, SKM_ERR_CONSERVATION, "export found %llu occupied slots, expected %llu",
+                    (unsigned long long)c->h_pinned[0], (unsigned long long)n);
+    if (sorted) {
+        // presentation order only (host): the table itself has no order
+        std::vector<uint64_t> idx(n);
+        for (uint64_t i = 0; i < n; i++) idx[i] = i;
+        std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return keys[a] < keys[b]; });
+        std::vector<uint64_t> k2(n);
+        std::vector<uint32_t> c2(n);
+        for (uint64_t i = 0; i < n; i++) {
+            k2[i] = keys[idx[i]];
+            c2[i] = counts[idx[i]];
+        }
+        memcpy(keys, k2.data(), n * sizeof(uint64_t));
+        memcpy(counts, c2.data(), n * sizeof(uint32_t));
+    }
+    return SKM_OK;
+}
+
+int32_t skm_table_digest(skm_ctx *c, uint64_t *out) {
+    if (!c || !out) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    int32_t rc = snapshot_histogram(c, c->n_chunks, true);
+    if (rc) return rc;
+    *out = c->last_tot.digest;
+    return SKM_OK;
+}
+
+int32_t skm_lookup_batch(skm_ctx *c, const uint64_t *kmers, uint64_t n, uint32_t min_count, int32_t mode,
+                         uint32_t *counts, uint8_t *found) {
+    if (!c || (n && !kmers) || mode < 0 || mode > SKM_LOOKUP_EITHER) return SKM_ERR_INVALID_ARG;
+    if (n == 0) return SKM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    unsigned long long *d_q = nullptr;
+    uint32_t *d_c = nullptr;
+    uint8_t *d_f = nullptr;
+    CU(cudaMallocAsync((void **)&d_q, n * sizeof(uint64_t), c->stream));
+    CU(cudaMallocAsync((void **)&d_c, n * sizeof(uint32_t), c->stream));
+    CU(cudaMallocAsync((void **)&d_f, n, c->stream));
+    CU(cudaMemcpyAsync(d_q, kmers, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    lookup_kernel<<<std::min<uint32_t>(grid_for(n, 256), c->sm_count * 8), 256, 0, c->stream>>>(
+        c->table, c->log2cap, c->p.k, d_q, n, min_count, mode, d_c, d_f);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (counts) CU(cudaMemcpyAsync(counts, d_c, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (found) CU(cudaMemcpyAsync(found, d_f, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFreeAsync(d_q, c->stream));
+    CU(cudaFreeAsync(d_c, c->stream));
+    CU(cudaFreeAsync(d_f, c->stream));
+    return SKM_OK;
+}
+
+int32_t skm_insert_counts(skm_ctx *c, const uint64_t *keys, const uint32_t *counts, uint64_t n) {
+    if (!c || (n && (!keys || !counts))) return SKM_ERR_INVALID_ARG;
+    if (n == 0) return SKM_OK;
+    for (uint64_t i = 0; i < n; i++)
+        if (keys[i] == SKM_EMPTY_KEY) return fail(c, SKM_ERR_INVALID_ARG, "key %llu is the EMPTY sentinel (k <= 31 keys never are)", (unsigned long long)i);
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    unsigned long long *d_k = nullptr;
+    uint32_t *d_c = nullptr;
+    CU(cudaMallocAsync((void **)&d_k, n * sizeof(uint64_t), c->stream));
+    CU(cudaMallocAsync((void **)&d_c, n * sizeof(uint32_t), c->stream));
+    CU(cudaMemcpyAsync(d_k, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_c, counts, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    uint64_t i = 0;
+    while (i < n) {
+        uint64_t granted = 0;
+        int32_t rc = reserve_headroom(c, n - i, &granted);
+        if (rc) return rc;
+        granted = std::max<uint64_t>(std::min(granted, n - i), 1);
+        insert_pairs_kernel<<<std::min<uint32_t>(grid_for(granted, 256), c->sm_count * 8), 256, 0, c->stream>>>(
+            d_k + i, d_c + i, granted, c->table, c->log2cap, c->d_gc);
+        c->launches++;
+        CU(cudaGetLastError());
+        c->distinct_ub += granted;
+        i += granted;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFreeAsync(d_k, c->stream));
+    CU(cudaFreeAsync(d_c, c->stream));
+    c->have_tot = false;
+    return SKM_OK;
+}
+
+// ---- multi-GPU building blocks -------------------------------------------------
+
+int32_t skm_route_chunk(skm_ctx *c, uint32_t chunk, uint64_t **d_kmers, uint64_t *send_counts) {
+    if (!c || !d_kmers || !send_counts) return SKM_ERR_INVALID_ARG;
+    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    if (c->chunks[chunk].counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
+    BucketFn fn;
+    fn.mode = 0;
+    fn.n_ranks = c->n_ranks;
+    fn.log2cap = c->log2cap;
+    fn.log2buckets = 0;
+    uint64_t total = 0;
+    ChunkState &cs = c->chunks[chunk];
+    int32_t rc = bucket_segments(c, chunk, 0, cs.segs.size(), fn, c->n_ranks, &total, send_counts);
+    if (rc) return rc;
+    for (auto &sg : cs.segs) {
+        CU(cudaFreeAsync(sg.codes, c->stream));
+        CU(cudaFreeAsync(sg.breaks, c->stream));
+        sg.codes = nullptr;
+        sg.breaks = nullptr;
+    }
+    cs.counted = true;
+    CU(cudaStreamSynchronize(c->stream));
+    *d_kmers = (uint64_t *)c->d_list;
+    return SKM_OK;
+}
+
+int32_t skm_insert_kmers_device(skm_ctx *c, const uint64_t *d_kmers, uint64_t n) {
+    if (!c || (n && !d_kmers)) return SKM_ERR_INVALID_ARG;
+    if (n == 0) return SKM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    int32_t rc = insert_list(c, (const unsigned long long *)d_kmers, n, false);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_tot = false;
+    return SKM_OK;
+}
+
+int32_t skm_snapshot_histogram(skm_ctx *c, uint32_t chunk_i) {
+    if (!c) return SKM_ERR_INVALID_ARG;
+    if (chunk_i >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    return snapshot_histogram(c, chunk_i, false);
+}
+
+// ---- diagnostics -----------------------------------------------------------------
+
+static int32_t pack_host_input(skm_ctx *c, const uint8_t *seqs, uint64_t n_bytes, Segment *sg, uint8_t **d_raw_out) {
+    uint8_t *d_raw = nullptr;
+    sg->n_bytes = n_bytes;
+    sg->n_units = (n_bytes + 31) / 32;
+    CU(cudaMallocAsync((void **)&d_raw, n_bytes + 1, c->stream));
+    CU(cudaMemcpyAsync(d_raw, seqs, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMallocAsync((void **)&sg->codes, (sg->n_units + 1) * sizeof(uint64_t), c->stream));
+    CU(cudaMallocAsync((void **)&sg->breaks, (sg->n_units + 1) * sizeof(uint32_t), c->stream));
+    ChunkCounters *d_cc = nullptr;
+    GlobalCounters *d_gc = nullptr;
+    CU(cudaMallocAsync((void **)&d_cc, sizeof(ChunkCounters), c->stream));
+    CU(cudaMallocAsync((void **)&d_gc, sizeof(GlobalCounters), c->stream));
+    CU(cudaMemsetAsync(d_cc, 0, sizeof(ChunkCounters), c->stream));
+    CU(cudaMemsetAsync(d_gc, 0xFF, sizeof(GlobalCounters), c->stream));
+    pack_kernel<<<grid_for(sg->n_units, 256), 256, 0, c->stream>>>(d_raw, n_bytes, 0, sg->codes, sg->breaks,
+                                                                  sg->n_units, d_cc, d_gc);
+    c->launches++;
+    CU(cudaGetLastError());
+    GlobalCounters gc;
+    CU(cudaMemcpyAsync(&gc, d_gc, sizeof gc, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFreeAsync(d_cc, c->stream));
+    CU(cudaFreeAsync(d_gc, c->stream));
+    *d_raw_out = d_raw;
+    if (gc.first_bad != ~0ull) {
+        CU(cudaFreeAsync(d_raw, c->stream));
+        CU(cudaFreeAsync(sg->codes, c->stream));
+        CU(cudaFreeAsync(sg->breaks, c->stream));
+        const unsigned ch = (unsigned)(gc.first_bad & 0xFF);
+        return fail(c, SKM_ERR_INVALID_BASE,
+                    "Invalid character '%c' in sequence. Only ACGTN allowed. (byte %llu of the ingested stream)",
+                    (ch >= 0x20 && ch < 0x7F) ? (char)ch : '?', (unsigned long long)(gc.first_bad >> 8));
+    }
+    return SKM_OK;
+}
+
+int32_t skm_extract_kmers(skm_ctx *c, const uint8_t *seqs, uint64_t n_bytes, uint64_t *out) {
+    if (!c || (n_bytes && (!seqs || !out))) return SKM_ERR_INVALID_ARG;
+    if (n_bytes == 0) return SKM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    Segment sg;
+    uint8_t *d_raw = nullptr;
+    int32_t rc = pack_host_input(c, seqs, n_bytes, &sg, &d_raw);
+    if (rc) return rc;
+    unsigned long long *d_out = nullptr;
+    CU(cudaMallocAsync((void **)&d_out, n_bytes * sizeof(uint64_t), c->stream));
+    extract_positions_kernel<<<grid_for(sg.n_units, 256), 256, 0, c->stream>>>(sg.codes, sg.breaks, sg.n_units,
+                                                                               n_bytes, c->p.k, d_out);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_out, n_bytes * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFreeAsync(d_out, c->stream));
+    CU(cudaFreeAsync(d_raw, c->stream));
+    CU(cudaFreeAsync(sg.codes, c->stream));
+    CU(cudaFreeAsync(sg.breaks, c->stream));
+    return SKM_OK;
+}
+
+int32_t skm_pack(skm_ctx *c, const uint8_t *seqs, uint64_t n_bytes, uint64_t *codes, uint32_t *breaks) {
+    if (!c || (n_bytes && (!seqs || !codes || !breaks))) return SKM_ERR_INVALID_ARG;
+    if (n_bytes == 0) return SKM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    Segment sg;
+    uint8_t *d_raw = nullptr;
+    int32_t rc = pack_host_input(c, seqs, n_bytes, &sg, &d_raw);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(codes, sg.codes, sg.n_units * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(breaks, sg.breaks, sg.n_units * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFreeAsync(d_raw, c->stream));
+    CU(cudaFreeAsync(sg.codes, c->stream));
+    CU(cudaFreeAsync(sg.breaks, c->stream));
+    return SKM_OK;
+}
+
+int32_t skm_synth_device(skm_ctx *c, uint64_t seed, uint64_t genome_len, uint32_t read_len, uint32_t sub_thresh,
+                         uint32_t n_thresh, uint32_t chunk_index, uint32_t n_chunks, uint64_t first, uint64_t n,
+                         uint8_t *d_out) {
+    if (!c || (n && !d_out)) return SKM_ERR_INVALID_ARG;
+    if (genome_len < read_len || read_len == 0 || n_chunks == 0) return fail(c, SKM_ERR_INVALID_ARG, "bad synth parameters");
+    if (n == 0) return SKM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    skm_synth_params sp{seed, genome_len, read_len, sub_thresh, n_thresh, 0};
+    synth_kernel<<<c->sm_count * 16, 256, 0, c->stream>>>(sp, chunk_index, n_chunks, first, n, d_out);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return SKM_OK;
+}
+
+int32_t skm_bench_gups(skm_ctx *c, uint32_t log2_slots, uint64_t n_updates, uint32_t iters, int32_t variant,
+                       float *ms_out) {
+    if (!c || !ms_out || log2_slots < 10 || log2_slots > 36 || iters == 0) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    Slot *t = nullptr;
+    const uint64_t cap = 1ull << log2_slots;
+    CU(cudaMalloc((void **)&t, cap * sizeof(Slot)));
+    CU(cudaMemsetAsync(t, 0, cap * sizeof(Slot), c->stream));
+    unsigned long long *d_sink = nullptr;
+    CU(cudaMalloc((void **)&d_sink, 8));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    const uint32_t grid = c->sm_count * 8;
+    gups_kernel<<<grid, 256, 0, c->stream>>>(t, log2_slots, n_updates, 1, variant, d_sink);  // warm-up
+    cudaEventRecord(a, c->stream);
+    for (uint32_t i = 0; i < iters; i++)
+        gups_kernel<<<grid, 256, 0, c->stream>>>(t, log2_slots, n_updates, 1000003ull * (i + 2), variant, d_sink);
+    cudaEventRecord(b, c->stream);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    *ms_out = ms / iters;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(t);
+    cudaFree(d_sink);
+    return SKM_OK;
+}
+
+}  // extern "C"

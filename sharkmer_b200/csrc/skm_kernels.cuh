@@ -1,0 +1,691 @@
+// skm_kernels.cuh — device code of the B200 k-mer counting engine (sm_100a).
+//
+// Data layout in HBM
+//   staged reads : codes[u]  u64, 32 bases per word, 2 bits/base, first base in the
+//                  most significant bits (the bit order of Read::from_str,
+//                  src/kmer/encoding.rs:60-95), A=0 C=1 G=2 T=3;
+//                  breaks[u] u32, 1 bit/base, MSB-first, 1 = no base here
+//                  ('N', the '\n' that ends a read, or padding past the end).
+//   count table  : open addressing, linear probing, 16-byte slots
+//                  { u64 key ; u64 count }, EMPTY key = all ones.  Two slots per
+//                  32-byte DRAM sector, so one probe = one sector.  Counts are
+//                  held in 64 bits on the device and reported as
+//                  min(count, u32::MAX): identical to the reference's chain of
+//                  u32 saturating adds (src/kmer/counting.rs:82-92,171-202) because
+//                  saturating addition of non-negative terms equals the clamped sum.
+//
+// All kernels are integer / byte work bounded by HBM (streaming or random
+// sector access); no tensor cores are involved.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/skm_common.h"
+
+namespace skm {
+
+struct __align__(16) Slot {
+    unsigned long long key;
+    unsigned long long count;
+};
+
+struct ChunkCounters {          // one per chunk, device memory
+    unsigned long long n_reads;   // '\n' seen by the pack kernel
+    unsigned long long n_bases;   // A/C/G/T seen by the pack kernel
+    unsigned long long n_windows; // valid k-mer windows seen by the extract kernels
+    unsigned long long pad;
+};
+
+struct GlobalCounters {         // one per ctx, device memory
+    unsigned long long first_bad;   // min over (byte position << 8 | byte) of invalid bytes; ~0 = none
+    unsigned long long n_distinct;  // keys claimed so far
+    unsigned long long scratch[6];
+};
+
+struct HistoTotals {
+    unsigned long long n_distinct;
+    unsigned long long n_kmers;      // sum of min(count, u32::MAX)
+    unsigned long long n_saturated;  // slots with count >= u32::MAX
+    unsigned long long digest;       // wrapping sum of skm_pair_digest
+};
+
+static constexpr uint32_t kU32Max = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ uint4 ld_nc_v4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 0x80 in every byte of v that is zero (exact, no borrow artefacts)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t v) {
+    return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+}
+
+// Reverse-complement of 32 packed bases (MSB-first): complement, then reverse
+// the order of the 2-bit groups.
+__device__ __forceinline__ uint64_t rc64(uint64_t x) {
+    x = ~x;
+    x = __brevll(x);  // reverses bits; fix the order inside each pair
+    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+}
+
+// ---------------------------------------------------------------------------
+// (1) pack: ASCII -> 2-bit codes + break mask.   1 B read + 0.375 B written / base
+//     One thread = 32 input bytes = two 128-bit loads -> one u64 + one u32.
+//     Also: n_reads ('\n'), n_bases (ACGT) and the first invalid byte
+//     (anything but A,C,G,T,N,'\n'): the reference aborts on it
+//     (src/kmer/encoding.rs:353-356), so it is reported, never masked.
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ void pack_word(uint32_t w, uint32_t &code8, uint32_t &valid4,
+                                          uint32_t &n_nl, uint32_t &bad) {
+    uint32_t x = (w >> 1) & 0x03030303u;  // A0 C1 G3 T2
+    x ^= (x >> 1) & 0x01010101u;          // A0 C1 G2 T3 (encoding.rs:341-345)
+    code8 = (x * 0x40100401u) >> 24;      // c0<<6 | c1<<4 | c2<<2 | c3
+    const uint32_t acgt = zero_bytes(w ^ 0x41414141u) | zero_bytes(w ^ 0x43434343u) |
+                          zero_bytes(w ^ 0x47474747u) | zero_bytes(w ^ 0x54545454u);
+    const uint32_t is_n = zero_bytes(w ^ 0x4E4E4E4Eu);
+    const uint32_t is_nl = zero_bytes(w ^ 0x0A0A0A0Au);
+    valid4 = (((acgt >> 7) & 0x01010101u) * 0x08040201u) >> 24 & 0xFu;  // byte0 -> bit 3
+    n_nl = __popc(is_nl);
+    bad = ~(acgt | is_n | is_nl) & 0x80808080u;
+}
+
+__global__ void __launch_bounds__(256)
+pack_kernel(const uint8_t *__restrict__ in, uint64_t n_bytes, uint64_t pos_base,
+            uint64_t *__restrict__ codes, uint32_t *__restrict__ breaks, uint64_t n_units,
+            ChunkCounters *__restrict__ cc, GlobalCounters *__restrict__ gc) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long my_reads = 0, my_bases = 0;
+    if (u < n_units) {
+        const uint64_t off = u * 32;
+        uint32_t w[8];
+        const bool full = off + 32 <= n_bytes;
+        if (full && ((reinterpret_cast<uintptr_t>(in) & 15) == 0)) {
+            const uint4 a = ld_nc_v4(reinterpret_cast<const uint4 *>(in + off));
+            const uint4 b = ld_nc_v4(reinterpret_cast<const uint4 *>(in + off) + 1);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+            w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint64_t p = off + 4 * i + j;
+                    // past the end: 0xFF is neither a base nor a newline; masked below
+                    const uint32_t byte = p < n_bytes ? in[p] : 0xFFu;
+                    v |= byte << (8 * j);
+                }
+                w[i] = v;
+            }
+        }
+        uint64_t code = 0;
+        uint32_t valid = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t c8, v4, nl, bad;
+            pack_word(w[i], c8, v4, nl, bad);
+            if (!full) {  // ignore bytes past the end
+                const uint64_t p = off + 4 * i;
+                uint32_t keep = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (p + j < n_bytes) keep |= 0x80u << (8 * j);
+                bad &= keep;
+                // v4 / nl cannot be set by 0xFF filler bytes
+            }
+            code |= (uint64_t)c8 << (56 - 8 * i);
+            valid |= v4 << (28 - 4 * i);
+            my_reads += nl;
+            if (bad) {
+                const int j = (__ffs(bad) - 1) >> 3;
+                const unsigned long long p = pos_base + off + 4 * i + j;
+                atomicMin(&gc->first_bad, (p << 8) | ((w[i] >> (8 * j)) & 0xFFu));
+            }
+        }
+        my_bases = __popc(valid);
+        codes[u] = code;
+        breaks[u] = ~valid;
+    }
+    my_reads = warp_sum(my_reads);
+    my_bases = warp_sum(my_bases);
+    if ((threadIdx.x & 31) == 0) {
+        if (my_reads) atomicAdd(&cc->n_reads, my_reads);
+        if (my_bases) atomicAdd(&cc->n_bases, my_bases);
+    }
+}
+
+// Concatenated bases + offsets -> newline-terminated lines (skm_ingest_reads).
+// One warp per read; dst offset of read r = offsets[r] + r.
+__global__ void __launch_bounds__(256)
+add_separators_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
+                      uint64_t n_reads, uint8_t *__restrict__ out) {
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (r >= n_reads) return;
+    const uint64_t a = offsets[r], b = offsets[r + 1];
+    for (uint64_t i = a + lane; i < b; i += 32) out[i + r] = bases[i];
+    if (lane == 0) out[b + r] = '\n';
+}
+
+// ---------------------------------------------------------------------------
+// (2) extract: rolling canonical k-mers from the packed stream.
+//     One thread = one 32-base unit.  It needs the k-1 <= 30 bases before its
+//     unit: the previous unit's words arrive by warp shuffle from the lane
+//     below (lane 0 re-loads them: an L1/L2 hit).  State update per base is the
+//     reference's (src/kmer/encoding.rs:359-367):
+//        fwd = (fwd << 2 | b) & mask ; rev = rev >> 2 | (3-b) << 2(k-1)
+//        n_valid = 0 at a break, else +1 ; emit min(fwd, rev) iff n_valid >= k
+//     A break ('N', end of read, padding) resets n_valid exactly as the
+//     reference's N branch does (encoding.rs:346-351); a new read starts after
+//     every '\n', so no window spans two reads.
+// ---------------------------------------------------------------------------
+
+struct UnitInput {
+    uint64_t cur, prev;
+    uint32_t inv, prev_inv;
+};
+
+__device__ __forceinline__ UnitInput load_unit(const uint64_t *__restrict__ codes,
+                                               const uint32_t *__restrict__ breaks, uint64_t u,
+                                               uint64_t u_end) {
+    UnitInput in;
+    const bool active = u < u_end;
+    in.cur = active ? codes[u] : 0ull;
+    in.inv = active ? breaks[u] : 0xFFFFFFFFu;
+    in.prev = __shfl_up_sync(0xffffffffu, in.cur, 1);
+    in.prev_inv = __shfl_up_sync(0xffffffffu, in.inv, 1);
+    if ((threadIdx.x & 31) == 0) {
+        if (active && u > 0) {
+            in.prev = codes[u - 1];
+            in.prev_inv = breaks[u - 1];
+        } else {
+            in.prev = 0;
+            in.prev_inv = 0xFFFFFFFFu;  // nothing before the first unit
+        }
+    }
+    return in;
+}
+
+template <class Emit>
+__device__ __forceinline__ uint32_t extract_unit(const UnitInput &in, uint32_t k, Emit &&emit) {
+    if (in.inv == 0xFFFFFFFFu) return 0;  // no base in this unit
+    const uint64_t kmask = (1ull << (2 * k)) - 1;  // k <= 31
+    const uint32_t top = 2 * (k - 1);
+    uint64_t fwd = in.prev;
+    uint64_t rev = rc64(in.prev) >> (64 - 2 * k);  // revcomp of the last k bases before the unit
+    uint32_t n_valid = in.prev_inv ? (uint32_t)(__ffs(in.prev_inv) - 1) : 32u;
+    uint32_t n_emitted = 0;
+#pragma unroll 8
+    for (int j = 0; j < 32; j++) {
+        const uint64_t b = (in.cur >> (62 - 2 * j)) & 3ull;
+        fwd = (fwd << 2) | b;
+        rev = (rev >> 2) | ((3ull - b) << top);
+        const bool brk = (in.inv >> (31 - j)) & 1u;
+        n_valid = brk ? 0u : n_valid + 1u;
+        if (n_valid >= k) {
+            const uint64_t f = fwd & kmask;
+            emit(f < rev ? f : rev, j);
+            n_emitted++;
+        }
+    }
+    return n_emitted;
+}
+
+// Diagnostic / parity kernel: out[p] = canonical k-mer of the window ending at
+// byte p of the segment, or EMPTY.
+__global__ void __launch_bounds__(256)
+extract_positions_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
+                         uint64_t n_units, uint64_t n_bytes, uint32_t k,
+                         unsigned long long *__restrict__ out) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const UnitInput in = load_unit(codes, breaks, u, n_units);
+    if (u >= n_units) return;
+    for (int j = 0; j < 32; j++)
+        if (u * 32 + j < n_bytes) out[u * 32 + j] = SKM_EMPTY_KEY;
+    extract_unit(in, k, [&](uint64_t kmer, int j) {
+        if (u * 32 + j < n_bytes) out[u * 32 + j] = kmer;
+    });
+}
+
+// ---------------------------------------------------------------------------
+// (3) insert: open-addressing upsert.  One probe = one key load (ld.cg: L2,
+//     the point of coherence); a hit costs one RED.ADD.64 on the same sector;
+//     a miss on EMPTY costs one atomicCAS.  Keys only ever change EMPTY -> key,
+//     so a plain load can never see a stale "other key".
+//     Returns true when this call claimed a new slot.
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ bool table_upsert(Slot *__restrict__ table, uint32_t log2cap,
+                                             uint64_t kmer, unsigned long long add) {
+    const uint64_t capmask = (1ull << log2cap) - 1;
+    uint64_t s = skm_home_slot(skm_hash_kmer(kmer), log2cap);
+    for (;;) {
+        unsigned long long key = ld_cg_u64(&table[s].key);
+        if (key == SKM_EMPTY_KEY) {
+            key = atomicCAS(&table[s].key, (unsigned long long)SKM_EMPTY_KEY,
+                            (unsigned long long)kmer);
+            if (key == SKM_EMPTY_KEY) {
+                red_add_u64(&table[s].count, add);
+                return true;
+            }
+        }
+        if (key == kmer) {
+            red_add_u64(&table[s].count, add);
+            return false;
+        }
+        s = (s + 1) & capmask;
+    }
+}
+
+// Fused extract + insert ("direct" mode): k-mers never touch HBM.
+__global__ void __launch_bounds__(256)
+extract_insert_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
+                      uint64_t u_begin, uint64_t u_end, uint32_t k, Slot *__restrict__ table, uint32_t log2cap,
+                      ChunkCounters *__restrict__ cc, GlobalCounters *__restrict__ gc) {
+    const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const UnitInput in = load_unit(codes, breaks, u, u_end);
+    unsigned long long n_new = 0;
+    unsigned long long n_win =
+        extract_unit(in, k, [&](uint64_t kmer, int) { n_new += table_upsert(table, log2cap, kmer, 1ull); });
+    n_new = warp_sum(n_new);
+    n_win = warp_sum(n_win);
+    if ((threadIdx.x & 31) == 0) {
+        if (n_new) atomicAdd(&gc->n_distinct, n_new);
+        if (n_win) atomicAdd(&cc->n_windows, n_win);
+    }
+}
+
+// Extract to a flat k-mer list (multi-GPU routing with one rank, tests).
+// Two passes over the packed reads: count windows per unit block, then write.
+__global__ void __launch_bounds__(256)
+count_windows_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
+                     uint64_t u_begin, uint64_t u_end, uint32_t k, ChunkCounters *__restrict__ cc) {
+    const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const UnitInput in = load_unit(codes, breaks, u, u_end);
+    unsigned long long n_win = extract_unit(in, k, [&](uint64_t, int) {});
+    n_win = warp_sum(n_win);
+    if ((threadIdx.x & 31) == 0 && n_win) atomicAdd(&cc->n_windows, n_win);
+}
+
+// Insert a flat list of k-mers (received from other ranks, or a bucket list).
+__global__ void __launch_bounds__(256)
+insert_list_kernel(const unsigned long long *__restrict__ kmers, uint64_t n,
+                   Slot *__restrict__ table, uint32_t log2cap, GlobalCounters *__restrict__ gc) {
+    unsigned long long n_new = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        n_new += table_upsert(table, log2cap, kmers[i], 1ull);
+    n_new = warp_sum(n_new);
+    if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(&gc->n_distinct, n_new);
+}
+
+// KmerCounts::insert / extend (src/kmer/counting.rs:152-166): pre-counted pairs.
+__global__ void __launch_bounds__(256)
+insert_pairs_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ counts,
+                    uint64_t n, Slot *__restrict__ table, uint32_t log2cap,
+                    GlobalCounters *__restrict__ gc) {
+    unsigned long long n_new = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        n_new += table_upsert(table, log2cap, keys[i], (unsigned long long)counts[i]);
+    n_new = warp_sum(n_new);
+    if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(&gc->n_distinct, n_new);
+}
+
+__global__ void __launch_bounds__(256) table_clear_kernel(Slot *__restrict__ table, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 v;
+        v.x = v.y = 0xFFFFFFFFu;
+        v.z = v.w = 0u;
+        reinterpret_cast<uint4 *>(table)[i] = v;
+    }
+}
+
+// Grow: re-insert every occupied slot of the old table into the new one.
+__global__ void __launch_bounds__(256)
+rehash_kernel(const Slot *__restrict__ old_table, uint64_t old_cap, Slot *__restrict__ table,
+              uint32_t log2cap) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < old_cap;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = ld_nc_v4(reinterpret_cast<const uint4 *>(old_table) + i);
+        const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
+        if (key == SKM_EMPTY_KEY) continue;
+        const unsigned long long cnt = ((unsigned long long)v.w << 32) | v.z;
+        table_upsert(table, log2cap, key, cnt);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// (4) histogram of the whole table (one streaming pass, 16 B / slot).
+//     Shared-memory privatised bins: counts 1..63 go to a lane-private copy
+//     (address = bin*32 + lane: no bank conflicts, no same-address
+//     serialisation on the singleton bin); 64 <= count < n_smem_bins go to one
+//     shared copy; the rest (rare) straight to global.  Bin histo_max+1 collects
+//     every count > histo_max (src/kmer/histogram.rs:80-84,125-134).
+// ---------------------------------------------------------------------------
+
+static constexpr int kLowBins = 64;
+
+__global__ void __launch_bounds__(512)
+histogram_kernel(const Slot *__restrict__ table, uint64_t capacity, uint64_t histo_max,
+                 uint32_t n_smem_bins, unsigned long long *__restrict__ g_bins,
+                 HistoTotals *__restrict__ totals, int want_digest) {
+    extern __shared__ uint32_t smem[];
+    uint32_t *low = smem;                      // kLowBins * 32
+    uint32_t *bins = smem + kLowBins * 32;     // n_smem_bins
+    for (uint32_t i = threadIdx.x; i < kLowBins * 32 + n_smem_bins; i += blockDim.x) smem[i] = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    unsigned long long n_distinct = 0, n_kmers = 0, n_sat = 0, digest = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = ld_nc_v4(reinterpret_cast<const uint4 *>(table) + i);
+        const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
+        if (key == SKM_EMPTY_KEY) continue;
+        unsigned long long cnt = ((unsigned long long)v.w << 32) | v.z;
+        if (cnt >= kU32Max) {
+            cnt = kU32Max;
+            n_sat++;
+        }
+        n_distinct++;
+        n_kmers += cnt;
+        if (want_digest) digest += skm_pair_digest(key, (uint32_t)cnt);
+        const unsigned long long bin = cnt > histo_max ? histo_max + 1 : cnt;
+        if (bin < (unsigned long long)kLowBins)
+            atomicAdd(&low[(uint32_t)bin * 32 + lane], 1u);
+        else if (bin < n_smem_bins)
+            atomicAdd(&bins[(uint32_t)bin], 1u);
+        else
+            atomicAdd(&g_bins[bin], 1ull);
+    }
+    __syncthreads();
+    // flush: low bins are summed over their 32 lane copies
+    for (uint32_t b = threadIdx.x; b < (uint32_t)kLowBins; b += blockDim.x) {
+        unsigned long long s = 0;
+        for (int l = 0; l < 32; l++) s += low[b * 32 + ((l + b) & 31)];
+        if (s) {
+            const unsigned long long dst = (unsigned long long)b > histo_max ? histo_max + 1 : b;
+            atomicAdd(&g_bins[dst], s);
+        }
+    }
+    for (uint32_t b = kLowBins + threadIdx.x; b < n_smem_bins; b += blockDim.x) {
+        const uint32_t s = bins[b];
+        if (s) atomicAdd(&g_bins[b], (unsigned long long)s);
+    }
+    n_distinct = warp_sum(n_distinct);
+    n_kmers = warp_sum(n_kmers);
+    n_sat = warp_sum(n_sat);
+    digest = warp_sum(digest);
+    if (lane == 0) {
+        if (n_distinct) atomicAdd(&totals->n_distinct, n_distinct);
+        if (n_kmers) atomicAdd(&totals->n_kmers, n_kmers);
+        if (n_sat) atomicAdd(&totals->n_saturated, n_sat);
+        if (digest) atomicAdd(&totals->digest, digest);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// read side: export (compaction) and batched lookups
+// ---------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+export_kernel(const Slot *__restrict__ table, uint64_t capacity, unsigned long long *__restrict__ keys,
+              uint32_t *__restrict__ counts, uint64_t out_cap, unsigned long long *__restrict__ cursor) {
+    const uint32_t lane = threadIdx.x & 31;
+    // uniform trip count per warp so the ballots below are well formed
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t n_iter = (capacity + stride - 1) / stride;
+    for (uint64_t it = 0; it < n_iter; it++) {
+        const uint64_t i = first + it * stride;
+        unsigned long long key = SKM_EMPTY_KEY, cnt = 0;
+        if (i < capacity) {
+            const uint4 v = ld_nc_v4(reinterpret_cast<const uint4 *>(table) + i);
+            key = ((unsigned long long)v.y << 32) | v.x;
+            cnt = ((unsigned long long)v.w << 32) | v.z;
+        }
+        const bool occ = key != SKM_EMPTY_KEY;
+        const uint32_t m = __ballot_sync(0xffffffffu, occ);
+        if (m == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (occ) {
+            const unsigned long long o = base + __popc(m & ((1u << lane) - 1));
+            if (o < out_cap) {
+                keys[o] = key;
+                counts[o] = cnt >= kU32Max ? kU32Max : (uint32_t)cnt;
+            }
+        }
+    }
+}
+
+// FilteredKmerCounts::get_canonical_count / KmerCounts::get_count / get_canonical
+// (src/kmer/counting.rs:205-222,328-342).  mode 0: probe min(kmer, revcomp);
+// mode 1: probe the k-mer as given; mode 2: probe as given, else the revcomp.
+__device__ __forceinline__ bool table_find(const Slot *__restrict__ table, uint32_t log2cap, uint64_t q,
+                                           uint32_t &count) {
+    if (q == SKM_EMPTY_KEY) return false;
+    const uint64_t capmask = (1ull << log2cap) - 1;
+    uint64_t s = skm_home_slot(skm_hash_kmer(q), log2cap);
+    for (;;) {
+        const uint4 v = *(reinterpret_cast<const uint4 *>(table) + s);
+        const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
+        if (key == q) {
+            const unsigned long long cnt = ((unsigned long long)v.w << 32) | v.z;
+            count = cnt >= kU32Max ? kU32Max : (uint32_t)cnt;
+            return true;
+        }
+        if (key == SKM_EMPTY_KEY) return false;
+        s = (s + 1) & capmask;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+lookup_kernel(const Slot *__restrict__ table, uint32_t log2cap, uint32_t k,
+              const unsigned long long *__restrict__ kmers, uint64_t n, uint32_t min_count,
+              int mode, uint32_t *__restrict__ counts, uint8_t *__restrict__ found) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t q = kmers[i];
+        const uint64_t rc = skm_revcomp_kmer(q, k);
+        uint32_t c = 0;
+        bool hit;
+        if (mode == 0)
+            hit = table_find(table, log2cap, q < rc ? q : rc, c);
+        else if (mode == 1)
+            hit = table_find(table, log2cap, q, c);
+        else
+            hit = table_find(table, log2cap, q, c) || table_find(table, log2cap, rc, c);
+        if (hit && c < min_count) {
+            hit = false;
+            c = 0;
+        }
+        if (!hit) c = 0;
+        if (counts) counts[i] = c;
+        if (found) found[i] = hit ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// bucketing by hash: multi-GPU routing (bucket = owner rank) and the
+// partitioned insert (bucket = top bits of the home slot, so each bucket is a
+// contiguous table region that fits in L2).  Exact two-pass scheme:
+//   pass 1  per-bucket counts (shared-memory counters, one global add per
+//           non-empty bucket per CTA)
+//   scan    exclusive prefix sum over buckets (single CTA)
+//   pass 2  each CTA reserves its slice of every bucket with one global atomic
+//           per bucket, then its threads scatter their k-mers; neighbouring
+//           CTAs fill neighbouring 8-byte cells, so L2 merges them into full
+//           sectors before they reach DRAM.
+// ---------------------------------------------------------------------------
+
+struct BucketFn {
+    uint32_t mode;      // 0: owner rank, 1: table region
+    uint32_t n_ranks;
+    uint32_t log2cap;
+    uint32_t log2buckets;
+    __device__ __forceinline__ uint32_t operator()(uint64_t kmer) const {
+        const uint64_t h = skm_hash_kmer(kmer);
+        if (mode == 0) return skm_owner_rank(h, n_ranks);
+        return (uint32_t)(skm_home_slot(h, log2cap) >> (log2cap - log2buckets));
+    }
+};
+
+__global__ void __launch_bounds__(256)
+bucket_count_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
+                    uint64_t u_begin, uint64_t u_end, uint32_t k, BucketFn fn, uint32_t n_buckets,
+                    unsigned long long *__restrict__ g_counts, ChunkCounters *__restrict__ cc) {
+    extern __shared__ uint32_t s_cnt[];
+    for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const UnitInput in = load_unit(codes, breaks, u, u_end);
+    unsigned long long n_win =
+        extract_unit(in, k, [&](uint64_t kmer, int) { atomicAdd(&s_cnt[fn(kmer)], 1u); });
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) {
+        const uint32_t c = s_cnt[i];
+        if (c) atomicAdd(&g_counts[i], (unsigned long long)c);
+    }
+    n_win = warp_sum(n_win);
+    if ((threadIdx.x & 31) == 0 && n_win) atomicAdd(&cc->n_windows, n_win);
+}
+
+// offsets[b] = sum of counts[0..b); cursors[b] = offsets[b]; offsets[n] = total
+__global__ void __launch_bounds__(1024)
+bucket_scan_kernel(const unsigned long long *__restrict__ counts, uint32_t n_buckets,
+                   unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ cursors) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t per = (n_buckets + blockDim.x - 1) / blockDim.x;
+    const uint32_t a = threadIdx.x * per;
+    unsigned long long s = 0;
+    for (uint32_t i = a; i < a + per && i < n_buckets; i++) s += counts[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (uint32_t i = 0; i < blockDim.x; i++) {
+            const unsigned long long t = part[i];
+            part[i] = run;
+            run += t;
+        }
+        offsets[n_buckets] = run;
+    }
+    __syncthreads();
+    unsigned long long run = part[threadIdx.x];
+    for (uint32_t i = a; i < a + per && i < n_buckets; i++) {
+        offsets[i] = run;
+        cursors[i] = run;
+        run += counts[i];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
+                      uint64_t u_begin, uint64_t u_end, uint32_t k, BucketFn fn, uint32_t n_buckets,
+                      unsigned long long *__restrict__ cursors, unsigned long long *__restrict__ out) {
+    extern __shared__ uint32_t s_mem[];
+    uint32_t *s_cnt = s_mem;                                   // n_buckets: counts, then local ranks
+    unsigned long long *s_base =
+        reinterpret_cast<unsigned long long *>(s_mem + ((n_buckets + 1) & ~1u));  // n_buckets
+    for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const UnitInput in = load_unit(codes, breaks, u, u_end);
+    // round 1: this CTA's count per bucket
+    extract_unit(in, k, [&](uint64_t kmer, int) { atomicAdd(&s_cnt[fn(kmer)], 1u); });
+    __syncthreads();
+    // reserve this CTA's slice of every non-empty bucket
+    for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) {
+        const uint32_t c = s_cnt[i];
+        s_base[i] = c ? atomicAdd(&cursors[i], (unsigned long long)c) : 0ull;
+        s_cnt[i] = 0;
+    }
+    __syncthreads();
+    // round 2: re-extract (ALU is free here) and scatter
+    extract_unit(in, k, [&](uint64_t kmer, int) {
+        const uint32_t b = fn(kmer);
+        const uint32_t r = atomicAdd(&s_cnt[b], 1u);
+        out[s_base[b] + r] = kmer;
+    });
+}
+
+// Partitioned insert: the k-mer list is grouped by table region; CTAs walk it
+// in order, so at any moment the chip works on a few neighbouring regions that
+// stay resident in L2.
+__global__ void __launch_bounds__(256)
+insert_sorted_list_kernel(const unsigned long long *__restrict__ kmers, uint64_t n,
+                          Slot *__restrict__ table, uint32_t log2cap,
+                          GlobalCounters *__restrict__ gc) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long n_new = 0;
+    if (i < n) n_new = table_upsert(table, log2cap, kmers[i], 1ull);
+    n_new = warp_sum(n_new);
+    if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(&gc->n_distinct, n_new);
+}
+
+// ---------------------------------------------------------------------------
+// synthetic reads on the device (bench / tests)
+// ---------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+synth_kernel(skm_synth_params p, uint32_t chunk_index, uint32_t n_chunks, uint64_t first, uint64_t n,
+             uint8_t *__restrict__ out) {
+    const uint64_t line = (uint64_t)p.read_len + 1;
+    const uint64_t total = n * line;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r_local = first + i / line;
+        const uint32_t j = (uint32_t)(i % line);
+        const uint64_t r = skm_chunk_read_to_global(r_local, chunk_index, n_chunks);
+        out[i] = j == p.read_len ? (uint8_t)'\n' : skm_synth_read_base(&p, r, j);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// random-access roofline probe
+// ---------------------------------------------------------------------------
+
+// variant 0: key load + RED.ADD.64 (what an insert hit does); 1: RED only; 2: load only
+__global__ void __launch_bounds__(256)
+gups_kernel(Slot *__restrict__ table, uint32_t log2cap, uint64_t n, uint64_t salt, int variant,
+            unsigned long long *__restrict__ sink) {
+    unsigned long long acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = skm_home_slot(skm_mix64(i + salt), log2cap);
+        if (variant != 1) acc += ld_cg_u64(&table[s].key);
+        if (variant != 2) red_add_u64(&table[s].count, 1ull);
+    }
+    if (acc == 0x123456789ull) *sink = acc;
+}
+
+}  // namespace skm

@@ -1,0 +1,396 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle (and the committed goldens) on the same seeded inputs.  Bit-exact: this is
+integer work, so every comparison is equality."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
+EMPTY = 0xFFFFFFFFFFFFFFFF
+U32_MAX = 0xFFFFFFFF
+
+
+@pytest.fixture(scope="module")
+def skm():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from sharkmer_b200 import kmer
+    return kmer
+
+
+def lines(seqs):
+    return ("\n".join(seqs) + "\n").encode() if seqs else b""
+
+
+# ---- (1) pack kernel: the reference's packed-layout KATs (src/kmer/mod.rs:61-111) ----------
+
+def test_pack_layout_kats(skm):
+    e = skm.Engine(9)
+    codes, breaks = e.pack(b"CGTAATGCGGCGA\n")
+    top = int(codes[0])
+    assert [(top >> s) & 0xFF for s in (56, 48, 40)] == [0b01101100, 0b00111001, 0b10100110]
+    assert (top >> 38) & 3 == 0  # 13th base 'A'
+    assert int(breaks[0]) == (0xFFFFFFFF >> 13)  # 13 bases, then newline + padding are breaks
+    codes, breaks = e.pack(b"C\n")
+    assert int(codes[0]) >> 56 == 0b01000000 and int(breaks[0]) == 0x7FFFFFFF
+    # N is a break; bases after it keep their positions
+    codes, breaks = e.pack(b"CGTANATGCGGCGA\n")
+    assert int(breaks[0]) >> 17 == 0b000010000000001  # first 15 positions: N at 4, newline at 14
+    # long input: every 32-base unit, unaligned tail
+    rng = random.Random(1)
+    s = "".join(rng.choice("ACGT") for _ in range(1000))
+    codes, breaks = e.pack(lines([s]))
+    for u in range(len(codes)):
+        want = 0
+        for j in range(32):
+            p = u * 32 + j
+            want = (want << 2) | ("ACGT".index(s[p]) if p < len(s) else 0)
+        got = int(codes[u])
+        nb = min(32, max(0, len(s) - u * 32))
+        if nb:
+            assert got >> (64 - 2 * nb) == want >> (64 - 2 * nb), u
+        valid_mask = ((1 << nb) - 1) << (32 - nb)
+        assert int(breaks[u]) == (~valid_mask) & 0xFFFFFFFF, u
+
+
+# ---- (2) extract kernel: order-exact against kmers_from_ascii -----------------------------------
+
+CASES = ["CGTAATGCGGCGA", "CGTANATGCGGCGA", "NCGTANATGCGGCGA", "NCGTANATGCGGCGANN",
+         "NNCGTANATGCGGCGA", "TANCACN", "NTANCACNAGAAAATC", "AAAA", "ACGTACGTACGT", "", "N", "A"]
+
+
+def check_extract(skm, oracle, seqs, k):
+    e = skm.Engine(k)
+    buf = lines(seqs)
+    out = e.extract_kmers(buf)
+    pos = 0
+    for s in seqs:
+        got = [int(v) for v in out[pos:pos + len(s) + 1] if int(v) != EMPTY]
+        assert got == oracle.kmers_from_ascii(s, k), (s[:60], k)
+        assert int(out[pos + len(s)]) == EMPTY  # nothing ends on a separator
+        pos += len(s) + 1
+
+
+def test_extract_reference_kats(skm, oracle):  # src/kmer/mod.rs:179-278
+    e = skm.Engine(9)
+    out = e.extract_kmers(b"CGTAATGCGGCG\n")
+    got = [int(v) for v in out if int(v) != EMPTY]
+    assert got == [0b01_1001_0011_1100_0110, 0b01_0110_0100_1111_0001, 0b10_0101_1001_0011_1100,
+                   0b00_0011_1001_1010_0110]
+    for k in (3, 5, 9, 11):
+        check_extract(skm, oracle, CASES, k)
+    assert skm.kmers_from_ascii("ACGT", 9) == []
+    assert len(skm.kmers_from_ascii("ACGTACGTA", 9)) == 1
+
+
+@pytest.mark.parametrize("k", [1, 3, 15, 21, 25, 31])
+def test_extract_random_reads(skm, oracle, k):
+    rng = random.Random(k)
+    seqs = []
+    for i in range(3000):
+        L = rng.choice([0, 1, 2, k - 1, k, k + 1, 31, 32, 33, 63, 64, 65, 100, 150, 151, 250])
+        s = "".join(rng.choice("ACGT") if rng.random() > 0.03 else "N" for _ in range(max(0, L)))
+        seqs.append(s)
+    check_extract(skm, oracle, seqs, k)
+
+
+def test_extract_unaligned_tail_sizes(skm, oracle):
+    rng = random.Random(5)
+    for n in list(range(1, 70)) + [127, 128, 129, 255, 256, 257, 8191, 8192, 8193]:
+        s = "".join(rng.choice("ACGT") for _ in range(n - 1))
+        check_extract(skm, oracle, [s], 5)
+
+
+# ---- (3) counting: sorted table, histograms, totals ---------------------------------------------
+
+def run_oracle(oracle, reads, k, chunks, hmax):
+    run = oracle.Run(k, chunks, hmax)
+    run.push_lines(reads)
+    run.finish()
+    return run
+
+
+def run_gpu(skm, reads, k, chunks, hmax, read_len, mode=0, capacity_hint=0, batches_per_call=3):
+    """Feeds the engine the way src/io.rs does: 1000-read batches, round-robin over chunks."""
+    e = skm.Engine(k, chunks, hmax, capacity_hint=capacity_hint, insert_mode=mode)
+    n_chunks = max(1, chunks)
+    line = read_len + 1
+    n_reads = len(reads) // line
+    per_chunk = [[] for _ in range(n_chunks)]
+    for b in range((n_reads + 999) // 1000):
+        per_chunk[b % n_chunks].append(reads[b * 1000 * line:min((b + 1) * 1000, n_reads) * line])
+    # several batches of one chunk may share a call, in order
+    for c in range(n_chunks):
+        bl = per_chunk[c]
+        for i in range(0, len(bl), batches_per_call):
+            e.ingest_batch(c, np.concatenate(bl[i:i + batches_per_call]))
+    e.finalize()
+    return e
+
+
+def compare(e, run, chunks):
+    keys, counts = e.export(sorted=True)
+    okeys, ocounts = run.table().export_sorted()
+    assert keys.size == okeys.size
+    assert (keys == okeys).all() and (counts == ocounts).all()
+    assert e.digest() == run.table().digest()
+    t = e.totals()
+    assert (t.n_reads, t.n_bases, t.n_bases_read, t.n_kmers, t.n_unique) == (
+        run.n_reads_ingested, run.n_bases_ingested, run.n_bases_read, run.n_kmers_ingested, okeys.size)
+    for c in range(run.n_chunks):
+        ct = e.chunk_totals(c)
+        assert (ct.n_reads, ct.n_bases, ct.n_kmers) == run.chunk_totals(c), c
+    for c in range(chunks):
+        assert (e.histogram(c) == run.histogram(c)).all(), c
+    if chunks:
+        assert t.n_singletons == run.n_singletons()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("k,chunks", [(21, 10), (31, 0), (31, 1), (25, 3), (1, 2), (15, 4)])
+def test_count_parity_vs_oracle(skm, oracle, k, chunks, mode):
+    L = 150
+    reads = oracle.synth_reads(seed=100 + k, genome_len=60_000, read_len=L, sub_rate=0.01, n_rate=0.001,
+                               first=0, n=23_456)
+    run = run_oracle(oracle, reads, k, chunks, 200)
+    e = run_gpu(skm, reads, k, chunks, 200, L, mode=mode)
+    compare(e, run, chunks)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_count_parity_goldens(skm, oracle, mode):
+    """Committed goldens (tests/golden/synth_cases.json, made by make_golden.py)."""
+    cases = json.load(open(os.path.join(GOLDEN_DIR, "synth_cases.json")))
+    for name, g in cases.items():
+        reads = oracle.synth_reads(g["seed"], g["genome_len"], g["read_len"], g["sub_rate"], g["n_rate"], 0, g["n_reads"])
+        e = run_gpu(skm, reads, g["k"], g["chunks"], g["histo_max"], g["read_len"], mode=mode)
+        t = e.totals()
+        assert (t.n_unique, t.n_kmers, t.n_bases) == (g["n_unique"], g["n_kmers"], g["n_bases_ingested"]), name
+        assert e.digest() == g["digest"], name
+        for c in range(g["chunks"]):
+            assert e.histogram(c).tolist() == g["histograms"][c], (name, c)
+        for c, want in enumerate(g["chunk_totals"]):
+            ct = e.chunk_totals(c)
+            assert [ct.n_reads, ct.n_bases, ct.n_kmers] == want, (name, c)
+
+
+def test_18s_golden(skm):  # src/pcr/mod.rs:1236-1247,1336-1342
+    gold = json.load(open(os.path.join(GOLDEN_DIR, "pcr_18s_k21.json")))
+    s = open(os.path.join(GOLDEN_DIR, "pcr_18s_read.txt")).read().strip()
+    kc = skm.KmerCounts(21)
+    for _ in range(10):
+        kc.ingest_seq(s)
+    assert kc.len() == len(s) - 21 + 1 == gold["n_distinct"]
+    assert kc.get_n_kmers() == gold["n_kmers"]
+    keys, counts = kc.export_sorted()
+    assert (counts == 10).all()
+    assert kc.digest() == gold["digest"]
+    # the same through the batch path
+    e = skm.Engine(21, chunks=1)
+    e.ingest_batch(0, lines([s] * 10))
+    e.finalize()
+    assert e.digest() == gold["digest"] and e.histogram(0)[10] == 1812
+
+
+def test_table_growth_from_tiny(skm, oracle):
+    """capacity_hint = 0: the table starts at 2^16 slots and must grow several times."""
+    L = 100
+    reads = oracle.synth_reads(seed=77, genome_len=3_000_000, read_len=L, sub_rate=0.02, n_rate=0.0, first=0, n=40_000)
+    for mode in (1, 2):
+        e = run_gpu(skm, reads, 31, 2, 100, L, mode=mode, capacity_hint=0)
+        run = run_oracle(oracle, reads, 31, 2, 100)
+        assert e.stage_times().n_grows >= 3
+        compare(e, run, 2)
+
+
+def test_ingest_reads_offsets_form(skm, oracle):
+    rng = random.Random(3)
+    seqs = ["".join(rng.choice("ACGTN" if rng.random() < 0.05 else "ACGT") for _ in range(rng.choice([0, 5, 31, 32, 90, 150])))
+            for _ in range(5000)]
+    bases = "".join(seqs).encode()
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(s) for s in seqs])
+    e = skm.Engine(21, chunks=1, histo_max=50)
+    e.ingest_reads(0, bases, offs)
+    e.finalize()
+    run = oracle.Run(21, 1, 50)
+    for s in seqs:
+        run.push_seq(s)
+    run.finish()
+    compare(e, run, 1)
+
+
+def test_invalid_base_is_an_error(skm):  # src/kmer/encoding.rs:353-356
+    for bad, ch in ((b"ACGTACGTaCGTACGT\n", "a"), (b"ACGT\nACGRT\n", "R"), (b"AC GT\n", " ")):
+        e = skm.Engine(3, chunks=1)
+        e.ingest_batch(0, bad)
+        with pytest.raises(skm.SkmError) as err:
+            e.finalize()
+        assert err.value.code == 2
+        assert f"Invalid character '{ch}' in sequence. Only ACGTN allowed." in str(err.value)
+    with pytest.raises(skm.SkmError):
+        skm.KmerCounts(3).ingest_seq("ACGU")
+
+
+def test_no_reads_is_an_error(skm):  # src/io.rs:578-580
+    e = skm.Engine(21, chunks=1)
+    with pytest.raises(skm.SkmError) as err:
+        e.finalize()
+    assert err.value.code == 8 and "No reads were ingested" in str(err.value)
+
+
+def test_empty_reads_are_counted(skm, oracle):
+    e = skm.Engine(5, chunks=1)
+    e.ingest_batch(0, b"\n\nACGTACG\n\nNNNNNNN\nAC\n")
+    e.finalize()
+    t = e.totals()
+    assert (t.n_reads, t.n_bases, t.n_bases_read, t.n_kmers) == (6, 9, 16, 3)
+
+
+# ---- (4) KmerCounts API behaviour (src/kmer/counting.rs:365-510) ----------------------------------
+
+def test_counts_api_kats(skm):
+    kc = skm.KmerCounts(5)
+    assert kc.get_k() == 5 and kc.is_empty() and kc.len() == 0 and kc.get_n_kmers() == 0
+    kc.insert(42, 3)
+    assert kc.get_count(42) == 3 and kc.contains(42) and not kc.contains(99)
+    kc.insert(42, 7)
+    assert kc.get_count(42) == 10 and kc.len() == 1
+    s = skm.KmerCounts(5)
+    s.insert(1, U32_MAX)
+    s.insert(1, 1)
+    assert s.get_count(1) == U32_MAX  # saturating
+    a, b = skm.KmerCounts(5), skm.KmerCounts(5)
+    a.insert(1, 10); a.insert(2, 20); b.insert(2, 5); b.insert(3, 15)
+    a.extend(b)
+    assert (a.get_count(1), a.get_count(2), a.get_count(3)) == (10, 25, 15)
+    with pytest.raises(skm.SkmError):
+        a.extend(skm.KmerCounts(7))
+    m = skm.KmerCounts(5)
+    assert m.get_median_count() == 0
+    m.insert(1, 10); m.insert(2, 20)
+    assert m.get_median_count() == 15
+    m.insert(3, 30)
+    assert m.get_median_count() == 20 and m.get_max_count() == 30
+    f = skm.KmerCounts(5)
+    f.insert(1, 2); f.insert(2, 10)
+    fv = f.filtered_view(5)
+    assert fv.get_canonical(1) is None and fv.get_canonical(2) == 10
+    assert fv.get_canonical_count(1) == 0 and fv.get_canonical_count(2) == 10
+    g = skm.KmerCounts(3)
+    g.ingest_seq("ACGT")
+    assert g.get_n_unique_kmers() == 1 and g.get_n_kmers() == 2
+
+
+def test_histogram_kat(skm):  # src/kmer/mod.rs:288-305
+    kc = skm.KmerCounts(11)
+    for kmer, c in ((1, 5), (20, 5), (2, 7), (11, 11), (12, 12)):
+        kc.insert(kmer, c)
+    v = skm.Histogram.from_kmer_counts(kc, 10).get_vector()
+    assert v.tolist() == [0, 0, 0, 0, 0, 2, 0, 1, 0, 0, 0, 2]
+
+
+def test_saturation_in_histogram(skm):
+    e = skm.Engine(5, chunks=1, histo_max=10)
+    e.insert_counts([1, 2, 3], [U32_MAX, U32_MAX - 1, 7])
+    e.insert_counts([1, 2], [5, 5])
+    e.snapshot_histogram(0)
+    h = e.histogram(0)
+    assert h[7] == 1 and h[11] == 2
+    t = e.totals()
+    assert t.n_saturated == 2 and t.n_kmers == 2 * U32_MAX + 7
+    c, f = e.lookup([1, 2, 3, 4], 0, 1)
+    assert c.tolist() == [U32_MAX, U32_MAX, 7, 0] and f.tolist() == [True, True, True, False]
+
+
+def test_lookup_batch_vs_oracle(skm, oracle):
+    L = 120
+    reads = oracle.synth_reads(seed=5, genome_len=30_000, read_len=L, sub_rate=0.01, n_rate=0.0, first=0, n=8_000)
+    run = run_oracle(oracle, reads, 25, 0, 100)
+    e = run_gpu(skm, reads, 25, 0, 100, L)
+    keys, _ = run.table().export_sorted()
+    rng = np.random.default_rng(0)
+    q = np.concatenate([keys[::7], rng.integers(0, 1 << 50, 5000, dtype=np.uint64)])
+    # query in a random orientation
+    flip = rng.random(q.size) < 0.5
+    qq = np.array([skm.revcomp_kmer(int(x), 25) if f else int(x) for x, f in zip(q, flip)], dtype=np.uint64)
+    for min_count in (0, 2, 5):
+        got, found = e.lookup(qq, min_count)
+        fv = run.table().filtered_view(min_count)
+        want = np.array([fv.get_canonical_count(int(x)) for x in qq], dtype=np.uint32)
+        assert (got == want).all()
+        wantf = np.array([fv.get_canonical(int(x)) is not None for x in qq])
+        _, found2 = e.lookup(qq, min_count, 2)
+        assert (found2 == wantf).all()
+
+
+# ---- (5) synthetic generator: device == host, bit for bit ------------------------------------------
+
+def test_device_synth_matches_host(skm, oracle):
+    e = skm.Engine(21)
+    L, n, n_chunks = 150, 2345, 3
+    for c in range(n_chunks):
+        d = e.device_alloc(n * (L + 1))
+        e.synth_device(9, 1_000_000, L, oracle.rate_to_thresh(0.01), oracle.rate_to_thresh(0.001), c, n_chunks, 0, n, d)
+        got = np.empty(n * (L + 1), dtype=np.uint8)
+        e.memcpy_d2h(got, d, got.size)
+        e.device_free(d)
+        # chunk-local read i is global read ((i//1000)*n_chunks + c)*1000 + i%1000
+        want = np.empty_like(got)
+        for b in range((n + 999) // 1000):
+            cnt = min(1000, n - b * 1000)
+            first = (b * n_chunks + c) * 1000
+            want[b * 1000 * (L + 1):(b * 1000 + cnt) * (L + 1)] = oracle.synth_reads(9, 1_000_000, L, 0.01, 0.001, first, cnt)
+        assert (got == want).all(), c
+
+
+# ---- (6) properties at larger size --------------------------------------------------------------------
+
+def test_chunk_invariance_and_digest_1m_reads(skm, oracle):
+    """tests/spcr_18s.rs:437-528 (final histogram independent of --chunks), on
+    device-generated reads, plus the oracle's digest on the same input."""
+    L, n = 150, 300_000
+    G, seed = 2_000_000, 21
+    st, nt = oracle.rate_to_thresh(0.01), oracle.rate_to_thresh(0.001)
+    finals, digests = [], []
+    for chunks, mode in ((1, 1), (20, 1), (7, 2)):
+        e = skm.Engine(21, chunks, 1000, capacity_hint=30_000_000, insert_mode=mode)
+        per = [0] * chunks
+        for b in range(n // 1000):
+            per[b % chunks] += 1000
+        for c in range(chunks):
+            d = e.device_alloc(per[c] * (L + 1))
+            e.synth_device(seed, G, L, st, nt, c, chunks, 0, per[c], d)
+            e.ingest_device(c, d, per[c] * (L + 1))
+            e.sync()
+            e.device_free(d)
+        e.finalize()
+        finals.append(e.histogram(chunks - 1))
+        digests.append(e.digest())
+        t = e.totals()
+        assert t.n_reads == n
+    assert (finals[0] == finals[1]).all() and (finals[0] == finals[2]).all()
+    assert digests[0] == digests[1] == digests[2]
+    run = oracle.Run(21, 1, 1000)
+    run.push_lines(oracle.synth_reads(seed, G, L, 0.01, 0.001, 0, n))
+    run.finish()
+    assert run.table().digest() == digests[0]
+    assert (run.histogram(0) == finals[0]).all()
+
+
+def test_reset_reuses_ctx(skm, oracle):
+    L = 100
+    e = skm.Engine(21, 2, 100)
+    for seed in (1, 2):
+        reads = oracle.synth_reads(seed, 50_000, L, 0.01, 0.0, 0, 4000)
+        e.reset()
+        for b in range(4):
+            e.ingest_batch(b % 2, reads[b * 1000 * (L + 1):(b + 1) * 1000 * (L + 1)])
+        e.finalize()
+        run = run_oracle(oracle, reads, 21, 2, 100)
+        compare(e, run, 2)
