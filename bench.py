@@ -370,7 +370,8 @@ def run_ours(args):
         }
         if args.gups:
             g = {}
-            for name, var in (("load+red", 0), ("red_only", 1), ("load_only", 2)):
+            for name, var in (("load+red", 0), ("red_only", 1), ("load_only", 2), ("local_load+red", 3),
+                              ("local_red_only", 4), ("local_load_only", 5), ("local_load+red32", 6)):
                 ms = eng.bench_gups(int(np.log2(stt.table_capacity)), 1 << 28, 3, var)
                 g[name] = (1 << 28) / (ms * 1e-3)
             out["gups"] = g

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -70,7 +71,10 @@ struct skm_ctx {
 
     ChunkCounters *d_cc = nullptr;  // n_chunks
     GlobalCounters *d_gc = nullptr;
-    unsigned long long *d_bins = nullptr;   // histo_max + 2
+    unsigned long long *d_hist = nullptr;   // running histogram, histo_max + 2 (chunks > 0)
+    bool track_histo = false;
+    int pipe_depth = 4;         // probes in flight per thread (SKM_PIPE_DEPTH: 1, 2, 4, 8)
+    unsigned long long *d_bins = nullptr;   // histo_max + 2 (scan histogram)
     HistoTotals *d_tot = nullptr;
     uint64_t *h_pinned = nullptr;           // small pinned scratch for read-backs
     size_t h_pinned_words = 0;
@@ -268,9 +272,18 @@ int32_t insert_segment_direct(skm_ctx *c, const Segment &sg, uint32_t chunk) {
         tile_units = std::min(tile_units, sg.n_units - u);
         {
             Span sp(c, ST_INSERT, c->stream);
-            extract_insert_kernel<<<grid_for(tile_units, 256), 256, 0, c->stream>>>(
-                sg.codes, sg.breaks, u, u + tile_units, c->p.k, c->table, c->log2cap, &c->d_cc[chunk],
-                c->d_gc);
+#define SKM_LAUNCH_EI(D, H)                                                                              \
+    extract_insert_kernel<D, H><<<grid_for(tile_units, 256), 256, 0, c->stream>>>(                      \
+        sg.codes, sg.breaks, u, u + tile_units, c->p.k, c->table, c->log2cap, &c->d_cc[chunk], c->d_gc, \
+        c->d_hist, c->p.histo_max)
+            const bool h = c->track_histo;
+            switch (c->pipe_depth) {
+            case 1: if (h) SKM_LAUNCH_EI(1, true); else SKM_LAUNCH_EI(1, false); break;
+            case 2: if (h) SKM_LAUNCH_EI(2, true); else SKM_LAUNCH_EI(2, false); break;
+            case 8: if (h) SKM_LAUNCH_EI(8, true); else SKM_LAUNCH_EI(8, false); break;
+            default: if (h) SKM_LAUNCH_EI(4, true); else SKM_LAUNCH_EI(4, false); break;
+            }
+#undef SKM_LAUNCH_EI
             c->launches++;
             c->stage_launches[ST_INSERT]++;
             c->insert_bases += std::min(tile_units * 32, sg.n_bytes - u * 32);
@@ -340,7 +353,7 @@ int32_t bucket_segments(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, Bucket
     return SKM_OK;
 }
 
-int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, uint64_t n, bool sorted) {
+int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_t *d_counts, uint64_t n) {
     uint64_t i = 0;
     while (i < n) {
         uint64_t granted = 0;
@@ -349,12 +362,19 @@ int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, uint64_t n, b
         granted = std::max<uint64_t>(std::min(granted, n - i), 1);
         {
             Span sp(c, ST_INSERT, c->stream);
-            if (sorted)
-                insert_sorted_list_kernel<<<grid_for(granted, 256), 256, 0, c->stream>>>(
-                    d_kmers + i, granted, c->table, c->log2cap, c->d_gc);
-            else
-                insert_list_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_kmers + i, granted, c->table,
-                                                                           c->log2cap, c->d_gc);
+            const uint32_t grid = grid_for(granted, kListTile);
+#define SKM_LAUNCH_IL(D, H)                                                                          \
+    insert_list_kernel<D, H><<<grid, 256, 0, c->stream>>>(d_kmers + i, d_counts ? d_counts + i : nullptr, \
+                                                          granted, c->table, c->log2cap, c->d_gc, c->d_hist, \
+                                                          c->p.histo_max)
+            const bool h = c->track_histo;
+            switch (c->pipe_depth) {
+            case 1: if (h) SKM_LAUNCH_IL(1, true); else SKM_LAUNCH_IL(1, false); break;
+            case 2: if (h) SKM_LAUNCH_IL(2, true); else SKM_LAUNCH_IL(2, false); break;
+            case 8: if (h) SKM_LAUNCH_IL(8, true); else SKM_LAUNCH_IL(8, false); break;
+            default: if (h) SKM_LAUNCH_IL(4, true); else SKM_LAUNCH_IL(4, false); break;
+            }
+#undef SKM_LAUNCH_IL
             c->launches++;
             c->stage_launches[ST_INSERT]++;
             c->insert_kmers += granted;
@@ -378,23 +398,8 @@ int32_t insert_chunk_partitioned(skm_ctx *c, uint32_t chunk) {
             bytes += cs.segs[s1].n_bytes;
             s1++;
         }
-        // the table must not grow between bucketing and inserting (buckets are table regions)
-        uint64_t granted = 0;
-        int32_t rc = reserve_headroom(c, bytes, &granted);
-        if (rc) return rc;
-        if (granted < bytes) {
-            // not enough guaranteed headroom for the whole group: tighten or grow until it fits
-            uint64_t d = 0;
-            rc = read_distinct(c, &d);
-            if (rc) return rc;
-            c->distinct_ub = d;
-            uint32_t nl = c->log2cap;
-            while ((uint64_t)(kMaxLoad * (double)(1ull << nl)) < d + bytes) nl++;
-            if (nl != c->log2cap) {
-                rc = grow_table(c, nl);
-                if (rc) return rc;
-            }
-        }
+        // (the list is ordered by the top hash bits, so it stays region-ordered even if the table grows)
+        int32_t rc;
         BucketFn fn;
         fn.mode = 1;
         fn.n_ranks = 1;
@@ -404,14 +409,15 @@ int32_t insert_chunk_partitioned(skm_ctx *c, uint32_t chunk) {
         uint64_t total = 0;
         rc = bucket_segments(c, chunk, s0, s1, fn, n_buckets, &total, nullptr);
         if (rc) return rc;
-        rc = insert_list(c, c->d_list, total, true);
+        rc = insert_list(c, c->d_list, nullptr, total);
         if (rc) return rc;
         s0 = s1;
     }
     return SKM_OK;
 }
 
-int32_t snapshot_histogram(skm_ctx *c, uint32_t chunk_i, bool want_digest) {
+// One streaming pass over the table: histogram + totals (+ digest).  Synchronous.
+int32_t scan_table(skm_ctx *c, bool want_digest, std::vector<uint64_t> *bins_out) {
     const uint64_t nb = c->p.histo_max + 2;
     CU(cudaMemsetAsync(c->d_bins, 0, nb * sizeof(uint64_t), c->stream));
     CU(cudaMemsetAsync(c->d_tot, 0, sizeof(HistoTotals), c->stream));
@@ -426,15 +432,30 @@ int32_t snapshot_histogram(skm_ctx *c, uint32_t chunk_i, bool want_digest) {
         c->stage_launches[ST_HISTO]++;
     }
     CU(cudaGetLastError());
-    if (chunk_i < c->n_chunks) {
-        c->histos[chunk_i].assign(nb, 0);
-        CU(cudaMemcpyAsync(c->histos[chunk_i].data(), c->d_bins, nb * sizeof(uint64_t),
-                           cudaMemcpyDeviceToHost, c->stream));
-        c->have_histo[chunk_i] = true;
+    if (bins_out) {
+        bins_out->assign(nb, 0);
+        CU(cudaMemcpyAsync(bins_out->data(), c->d_bins, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaMemcpyAsync(&c->last_tot, c->d_tot, sizeof(HistoTotals), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->have_tot = true;
+    return SKM_OK;
+}
+
+// Column `chunk_i` of the incremental histogram: the running histogram kept by the
+// insert kernels (a stream-ordered copy), or a table scan when tracking is off.
+int32_t snapshot_histogram(skm_ctx *c, uint32_t chunk_i) {
+    const uint64_t nb = c->p.histo_max + 2;
+    if (chunk_i >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
+    if (!c->track_histo) {
+        int32_t rc = scan_table(c, false, &c->histos[chunk_i]);
+        if (rc) return rc;
+    } else {
+        c->histos[chunk_i].assign(nb, 0);
+        CU(cudaMemcpyAsync(c->histos[chunk_i].data(), c->d_hist, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                           c->stream));
+    }
+    c->have_histo[chunk_i] = true;
     return SKM_OK;
 }
 
@@ -560,6 +581,15 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     gc.first_bad = ~0ull;
     CU(cudaMemcpy(c->d_gc, &gc, sizeof gc, cudaMemcpyHostToDevice));
     CU(cudaMalloc((void **)&c->d_bins, (c->p.histo_max + 2) * sizeof(uint64_t)));
+    CU(cudaMalloc((void **)&c->d_hist, (c->p.histo_max + 2) * sizeof(uint64_t)));
+    CU(cudaMemset(c->d_hist, 0, (c->p.histo_max + 2) * sizeof(uint64_t)));
+    // chunks == 0: the reference keeps no histogram (src/io.rs:1133-1158), so the cheaper RED path is used.
+    // SKM_HISTO_SCAN=1 (diagnostic) falls back to one table scan per chunk.
+    c->track_histo = c->p.chunks > 0 && !getenv("SKM_HISTO_SCAN");
+    if (const char *g = getenv("SKM_PIPE_DEPTH")) c->pipe_depth = atoi(g);
+    if (const char *g = getenv("SKM_L2_FETCH")) {  // diagnostic: 32 / 64 / 128
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+    }
     CU(cudaMalloc((void **)&c->d_tot, sizeof(HistoTotals)));
     c->h_pinned_words = kMaxBuckets + 16;
     CU(cudaMallocHost((void **)&c->h_pinned, c->h_pinned_words * sizeof(uint64_t)));
@@ -599,6 +629,7 @@ void skm_destroy(skm_ctx *c) {
         cudaFree(c->d_cc);
         cudaFree(c->d_gc);
         cudaFree(c->d_bins);
+        cudaFree(c->d_hist);
         cudaFree(c->d_tot);
         cudaFree(c->d_bucket_counts);
         cudaFree(c->d_bucket_offsets);
@@ -772,15 +803,15 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
         }
         cs.counted = true;
         if (c->p.chunks > 0) {
-            rc = snapshot_histogram(c, ch, false);
+            rc = snapshot_histogram(c, ch);
             if (rc) return rc;
         }
     }
-    if (c->p.chunks == 0) {
-        // totals for the conservation check (no histogram is kept, as in the reference)
-        rc = snapshot_histogram(c, c->n_chunks /* no column */, false);
-        if (rc) return rc;
-    }
+    // One scan of the finished table: totals for the conservation checks and an
+    // independent recount of the final histogram.
+    std::vector<uint64_t> rescan;
+    rc = scan_table(c, false, &rescan);
+    if (rc) return rc;
     cudaEventRecord(e1, c->stream);
     CU(cudaStreamSynchronize(c->stream));
     float ms = 0;
@@ -809,6 +840,8 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
                     (unsigned long long)c->last_tot.n_distinct, (unsigned long long)d);
     if (c->p.chunks > 0) {
         const std::vector<uint64_t> &h = c->histos[c->n_chunks - 1];
+        if (h != rescan)
+            return fail(c, SKM_ERR_CONSERVATION, "The incremental histogram does not match a recount of the table");
         uint64_t uniq = 0;
         for (size_t i = 1; i < h.size(); i++) uniq += h[i];
         if (uniq != d)
@@ -841,6 +874,7 @@ int32_t skm_reset(skm_ctx *c) {
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(c->d_cc, 0, c->n_chunks * sizeof(ChunkCounters), c->stream));
+    CU(cudaMemsetAsync(c->d_hist, 0, (c->p.histo_max + 2) * sizeof(uint64_t), c->stream));
     GlobalCounters gc{};
     gc.first_bad = ~0ull;
     CU(cudaMemcpyAsync(c->d_gc, &gc, sizeof gc, cudaMemcpyHostToDevice, c->stream));
@@ -884,7 +918,7 @@ int32_t skm_histogram(skm_ctx *c, uint32_t chunk_i, uint64_t *out, uint64_t out_
 static int32_t refresh_totals(skm_ctx *c) {
     // table-wide totals come from a histogram pass; refresh if the table changed since
     int32_t rc = SKM_OK;
-    if (!c->have_tot) rc = snapshot_histogram(c, c->n_chunks, false);
+    if (!c->have_tot) rc = scan_table(c, false, nullptr);
     return rc;
 }
 
@@ -1009,7 +1043,7 @@ int32_t skm_table_digest(skm_ctx *c, uint64_t *out) {
     if (!c || !out) return SKM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    int32_t rc = snapshot_histogram(c, c->n_chunks, true);
+    int32_t rc = scan_table(c, true, nullptr);
     if (rc) return rc;
     *out = c->last_tot.digest;
     return SKM_OK;
@@ -1054,19 +1088,8 @@ int32_t skm_insert_counts(skm_ctx *c, const uint64_t *keys, const uint32_t *coun
     CU(cudaMallocAsync((void **)&d_c, n * sizeof(uint32_t), c->stream));
     CU(cudaMemcpyAsync(d_k, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_c, counts, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    uint64_t i = 0;
-    while (i < n) {
-        uint64_t granted = 0;
-        int32_t rc = reserve_headroom(c, n - i, &granted);
-        if (rc) return rc;
-        granted = std::max<uint64_t>(std::min(granted, n - i), 1);
-        insert_pairs_kernel<<<std::min<uint32_t>(grid_for(granted, 256), c->sm_count * 8), 256, 0, c->stream>>>(
-            d_k + i, d_c + i, granted, c->table, c->log2cap, c->d_gc);
-        c->launches++;
-        CU(cudaGetLastError());
-        c->distinct_ub += granted;
-        i += granted;
-    }
+    int32_t rc = insert_list(c, d_k, d_c, n);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaFreeAsync(d_k, c->stream));
     CU(cudaFreeAsync(d_c, c->stream));
@@ -1108,7 +1131,7 @@ int32_t skm_insert_kmers_device(skm_ctx *c, const uint64_t *d_kmers, uint64_t n)
     if (n == 0) return SKM_OK;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    int32_t rc = insert_list(c, (const unsigned long long *)d_kmers, n, false);
+    int32_t rc = insert_list(c, (const unsigned long long *)d_kmers, nullptr, n);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     c->have_tot = false;
@@ -1120,7 +1143,10 @@ int32_t skm_snapshot_histogram(skm_ctx *c, uint32_t chunk_i) {
     if (chunk_i >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    return snapshot_histogram(c, chunk_i, false);
+    int32_t rc = snapshot_histogram(c, chunk_i);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return SKM_OK;
 }
 
 // ---- diagnostics -----------------------------------------------------------------
@@ -1233,11 +1259,13 @@ int32_t skm_bench_gups(skm_ctx *c, uint32_t log2_slots, uint64_t n_updates, uint
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
-    const uint32_t grid = c->sm_count * 8;
-    gups_kernel<<<grid, 256, 0, c->stream>>>(t, log2_slots, n_updates, 1, variant, d_sink);  // warm-up
+    const uint32_t region_log2 = std::min<uint32_t>(17, log2_slots);
+    const uint32_t grid = variant >= 3 ? grid_for(n_updates, 256) : c->sm_count * 8;
+    gups_kernel<<<grid, 256, 0, c->stream>>>(t, log2_slots, n_updates, 1, variant, region_log2, d_sink);  // warm-up
     cudaEventRecord(a, c->stream);
     for (uint32_t i = 0; i < iters; i++)
-        gups_kernel<<<grid, 256, 0, c->stream>>>(t, log2_slots, n_updates, 1000003ull * (i + 2), variant, d_sink);
+        gups_kernel<<<grid, 256, 0, c->stream>>>(t, log2_slots, n_updates, 1000003ull * (i + 2), variant,
+                                                 region_log2, d_sink);
     cudaEventRecord(b, c->stream);
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());

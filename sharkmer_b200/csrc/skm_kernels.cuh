@@ -103,11 +103,12 @@ __device__ __forceinline__ uint64_t rc64(uint64_t x) {
 
 __device__ __forceinline__ void pack_word(uint32_t w, uint32_t &code8, uint32_t &valid4,
                                           uint32_t &n_nl, uint32_t &bad) {
-    uint32_t x = (w >> 1) & 0x03030303u;  // A0 C1 G3 T2
-    x ^= (x >> 1) & 0x01010101u;          // A0 C1 G2 T3 (encoding.rs:341-345)
-    code8 = (x * 0x40100401u) >> 24;      // c0<<6 | c1<<4 | c2<<2 | c3
     const uint32_t acgt = zero_bytes(w ^ 0x41414141u) | zero_bytes(w ^ 0x43434343u) |
                           zero_bytes(w ^ 0x47474747u) | zero_bytes(w ^ 0x54545454u);
+    uint32_t x = (w >> 1) & 0x03030303u;  // A0 C1 G3 T2
+    x ^= (x >> 1) & 0x01010101u;          // A0 C1 G2 T3 (encoding.rs:341-345)
+    x &= (acgt >> 7) * 3u;                // breaks pack as 00, like the padding of Read::from_str
+    code8 = (x * 0x40100401u) >> 24;      // c0<<6 | c1<<4 | c2<<2 | c3
     const uint32_t is_n = zero_bytes(w ^ 0x4E4E4E4Eu);
     const uint32_t is_nl = zero_bytes(w ^ 0x0A0A0A0Au);
     valid4 = (((acgt >> 7) & 0x01010101u) * 0x08040201u) >> 24 & 0xFu;  // byte0 -> bit 3
@@ -274,55 +275,162 @@ extract_positions_kernel(const uint64_t *__restrict__ codes, const uint32_t *__r
 }
 
 // ---------------------------------------------------------------------------
-// (3) insert: open-addressing upsert.  One probe = one key load (ld.cg: L2,
-//     the point of coherence); a hit costs one RED.ADD.64 on the same sector;
-//     a miss on EMPTY costs one atomicCAS.  Keys only ever change EMPTY -> key,
-//     so a plain load can never see a stale "other key".
-//     Returns true when this call claimed a new slot.
+// (3) insert: open-addressing upsert, software-pipelined.
+//     One probe = one key load (ld.cg: L2 is the point of coherence); a hit
+//     costs one atomic add on the same sector; a miss on EMPTY one atomicCAS.
+//     Keys only ever change EMPTY -> key, so a key loaded early can never be a
+//     stale "other key": a stale EMPTY is resolved by the CAS.
+//
+//     The kernels are bound by DRAM latency on random sectors (ncu: >90 % of
+//     stalls are long_scoreboard), so every thread keeps D probes in flight:
+//     the key load for k-mer j+D is issued before k-mer j is resolved
+//     (InsertPipe).  When the running histogram is on, the count update is an
+//     atomicAdd that returns the old count, and that result is consumed one
+//     step later, so its round trip is hidden as well.
+//
+//     Running histogram (replaces a full table scan per chunk): moving a k-mer
+//     from count `old` to `old+add` moves one unit of histogram mass — exactly
+//     Histogram::move_count (src/kmer/histogram.rs:51-85).  Concurrent adds to
+//     one k-mer get distinct `old` values from the atomic, and the moves
+//     telescope, so the result is exact in any interleaving.  Deltas for counts
+//     < kLowBins are privatised in shared memory (one signed copy per lane: no
+//     bank conflicts, no same-address serialisation on the singleton bin) and
+//     flushed once per CTA; higher bins go to global memory directly.
 // ---------------------------------------------------------------------------
 
-__device__ __forceinline__ bool table_upsert(Slot *__restrict__ table, uint32_t log2cap,
-                                             uint64_t kmer, unsigned long long add) {
-    const uint64_t capmask = (1ull << log2cap) - 1;
-    uint64_t s = skm_home_slot(skm_hash_kmer(kmer), log2cap);
-    for (;;) {
-        unsigned long long key = ld_cg_u64(&table[s].key);
-        if (key == SKM_EMPTY_KEY) {
-            key = atomicCAS(&table[s].key, (unsigned long long)SKM_EMPTY_KEY,
-                            (unsigned long long)kmer);
-            if (key == SKM_EMPTY_KEY) {
-                red_add_u64(&table[s].count, add);
-                return true;
-            }
-        }
-        if (key == kmer) {
-            red_add_u64(&table[s].count, add);
-            return false;
-        }
-        s = (s + 1) & capmask;
+static constexpr int kLowBins = 64;
+
+struct HistoSink {
+    int *low;                      // shared: kLowBins * 32 signed deltas
+    unsigned long long *g_hist;    // global: histo_max + 2 bins, wrapping u64 adds
+    unsigned long long histo_max;
+    uint32_t lane;
+    __device__ __forceinline__ void bump(unsigned long long bin, int d) const {
+        if (bin < (unsigned long long)kLowBins)
+            atomicAdd(&low[(uint32_t)bin * 32 + lane], d);
+        else
+            atomicAdd(&g_hist[bin], (unsigned long long)(long long)d);
+    }
+    __device__ __forceinline__ void move(unsigned long long old, unsigned long long add) const {
+        const unsigned long long top = histo_max + 1;
+        const unsigned long long nw = old + add;
+        const unsigned long long ob = old > histo_max ? top : old;
+        const unsigned long long nb = nw > histo_max ? top : nw;
+        if (ob == nb) return;
+        if (old) bump(ob, -1);
+        bump(nb, 1);
+    }
+};
+
+__device__ __forceinline__ void histo_smem_init(int *low) {
+    for (uint32_t i = threadIdx.x; i < kLowBins * 32; i += blockDim.x) low[i] = 0;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void histo_smem_flush(const int *low, unsigned long long *g_hist) {
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < (uint32_t)kLowBins; b += blockDim.x) {
+        long long sum = 0;
+        for (int l = 0; l < 32; l++) sum += low[b * 32 + ((l + b) & 31)];
+        if (sum) atomicAdd(&g_hist[b], (unsigned long long)sum);
     }
 }
 
+template <int D, bool kHisto>
+struct InsertPipe {
+    Slot *table;
+    uint64_t capmask;
+    uint32_t log2cap;
+    HistoSink hs;
+    unsigned long long rk[D], rs[D], rkey[D];
+    uint32_t radd[D];
+    uint32_t valid = 0;
+    unsigned long long o_old = 0;
+    uint32_t o_add = 0;
+    bool o_valid = false;
+    unsigned long long n_new = 0;
+
+    __device__ __forceinline__ InsertPipe(Slot *t, uint32_t l2c, const HistoSink &h)
+        : table(t), capmask((1ull << l2c) - 1), log2cap(l2c), hs(h) {}
+
+    // resolve the oldest probe: find/claim the slot, add the count
+    __device__ __forceinline__ void finish(unsigned long long kmer, unsigned long long s,
+                                           unsigned long long key, uint32_t add) {
+        for (;;) {
+            if (key == SKM_EMPTY_KEY) {
+                key = atomicCAS(&table[s].key, (unsigned long long)SKM_EMPTY_KEY, kmer);
+                if (key == SKM_EMPTY_KEY) {
+                    n_new++;
+                    break;
+                }
+            }
+            if (key == kmer) break;
+            s = (s + 1) & capmask;
+            key = ld_cg_u64(&table[s].key);
+        }
+        if (kHisto) {
+            if (o_valid) hs.move(o_old, o_add);  // previous atomic's result: long since back
+            o_old = atomicAdd(&table[s].count, (unsigned long long)add);
+            o_add = add;
+            o_valid = true;
+        } else {
+            red_add_u64(&table[s].count, (unsigned long long)add);
+        }
+    }
+
+    __device__ __forceinline__ void step(bool have, unsigned long long kmer, uint32_t add) {
+        if (valid & 1u) finish(rk[0], rs[0], rkey[0], radd[0]);
+#pragma unroll
+        for (int i = 0; i + 1 < D; i++) {
+            rk[i] = rk[i + 1];
+            rs[i] = rs[i + 1];
+            rkey[i] = rkey[i + 1];
+            radd[i] = radd[i + 1];
+        }
+        valid >>= 1;
+        if (have) {
+            const unsigned long long s = skm_home_slot(skm_hash_kmer(kmer), log2cap);
+            rk[D - 1] = kmer;
+            rs[D - 1] = s;
+            radd[D - 1] = add;
+            rkey[D - 1] = ld_cg_u64(&table[s].key);  // in flight until this entry reaches the front
+            valid |= 1u << (D - 1);
+        }
+    }
+    __device__ __forceinline__ void push(unsigned long long kmer, uint32_t add = 1) { step(true, kmer, add); }
+    __device__ __forceinline__ void drain() {
+#pragma unroll
+        for (int i = 0; i < D; i++) step(false, 0, 0);
+        if (kHisto && o_valid) hs.move(o_old, o_add);
+        o_valid = false;
+    }
+};
+
 // Fused extract + insert ("direct" mode): k-mers never touch HBM.
+template <int D, bool kHisto>
 __global__ void __launch_bounds__(256)
 extract_insert_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
                       uint64_t u_begin, uint64_t u_end, uint32_t k, Slot *__restrict__ table, uint32_t log2cap,
-                      ChunkCounters *__restrict__ cc, GlobalCounters *__restrict__ gc) {
+                      ChunkCounters *__restrict__ cc, GlobalCounters *__restrict__ gc,
+                      unsigned long long *__restrict__ g_hist, unsigned long long histo_max) {
+    __shared__ int s_low[kHisto ? kLowBins * 32 : 1];
+    if (kHisto) histo_smem_init(s_low);
     const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const UnitInput in = load_unit(codes, breaks, u, u_end);
-    unsigned long long n_new = 0;
-    unsigned long long n_win =
-        extract_unit(in, k, [&](uint64_t kmer, int) { n_new += table_upsert(table, log2cap, kmer, 1ull); });
-    n_new = warp_sum(n_new);
+    HistoSink hs{s_low, g_hist, histo_max, threadIdx.x & 31};
+    InsertPipe<D, kHisto> pipe(table, log2cap, hs);
+    unsigned long long n_win = extract_unit(in, k, [&](uint64_t kmer, int) { pipe.push(kmer); });
+    pipe.drain();
+    unsigned long long n_new = warp_sum(pipe.n_new);
     n_win = warp_sum(n_win);
     if ((threadIdx.x & 31) == 0) {
         if (n_new) atomicAdd(&gc->n_distinct, n_new);
         if (n_win) atomicAdd(&cc->n_windows, n_win);
     }
+    if (kHisto) histo_smem_flush(s_low, g_hist);
 }
 
-// Extract to a flat k-mer list (multi-GPU routing with one rank, tests).
-// Two passes over the packed reads: count windows per unit block, then write.
+// Count the windows of a unit range (conservation checks, list sizing).
 __global__ void __launch_bounds__(256)
 count_windows_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
                      uint64_t u_begin, uint64_t u_end, uint32_t k, ChunkCounters *__restrict__ cc) {
@@ -333,29 +441,32 @@ count_windows_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restr
     if ((threadIdx.x & 31) == 0 && n_win) atomicAdd(&cc->n_windows, n_win);
 }
 
-// Insert a flat list of k-mers (received from other ranks, or a bucket list).
-__global__ void __launch_bounds__(256)
-insert_list_kernel(const unsigned long long *__restrict__ kmers, uint64_t n,
-                   Slot *__restrict__ table, uint32_t log2cap, GlobalCounters *__restrict__ gc) {
-    unsigned long long n_new = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (uint64_t)gridDim.x * blockDim.x)
-        n_new += table_upsert(table, log2cap, kmers[i], 1ull);
-    n_new = warp_sum(n_new);
-    if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(&gc->n_distinct, n_new);
-}
+// Insert a flat list of k-mers (received from other ranks, or a region-sorted
+// bucket list).  CTA b owns the contiguous slice [b*kListTile, (b+1)*kListTile):
+// CTAs walk a region-sorted list in order, so at any moment the chip works on a
+// few neighbouring table regions that stay resident in L2.
+static constexpr uint32_t kListPerThread = 16;
+static constexpr uint32_t kListTile = 256 * kListPerThread;
 
-// KmerCounts::insert / extend (src/kmer/counting.rs:152-166): pre-counted pairs.
+template <int D, bool kHisto>
 __global__ void __launch_bounds__(256)
-insert_pairs_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ counts,
-                    uint64_t n, Slot *__restrict__ table, uint32_t log2cap,
-                    GlobalCounters *__restrict__ gc) {
-    unsigned long long n_new = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (uint64_t)gridDim.x * blockDim.x)
-        n_new += table_upsert(table, log2cap, keys[i], (unsigned long long)counts[i]);
-    n_new = warp_sum(n_new);
+insert_list_kernel(const unsigned long long *__restrict__ kmers, const uint32_t *__restrict__ counts,
+                   uint64_t n, Slot *__restrict__ table, uint32_t log2cap, GlobalCounters *__restrict__ gc,
+                   unsigned long long *__restrict__ g_hist, unsigned long long histo_max) {
+    __shared__ int s_low[kHisto ? kLowBins * 32 : 1];
+    if (kHisto) histo_smem_init(s_low);
+    HistoSink hs{s_low, g_hist, histo_max, threadIdx.x & 31};
+    InsertPipe<D, kHisto> pipe(table, log2cap, hs);
+    const uint64_t base = (uint64_t)blockIdx.x * kListTile + threadIdx.x;
+#pragma unroll 4
+    for (uint32_t j = 0; j < kListPerThread; j++) {
+        const uint64_t i = base + (uint64_t)j * 256;
+        if (i < n) pipe.push(kmers[i], counts ? counts[i] : 1u);
+    }
+    pipe.drain();
+    const unsigned long long n_new = warp_sum(pipe.n_new);
     if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(&gc->n_distinct, n_new);
+    if (kHisto) histo_smem_flush(s_low, g_hist);
 }
 
 __global__ void __launch_bounds__(256) table_clear_kernel(Slot *__restrict__ table, uint64_t n) {
@@ -378,7 +489,15 @@ rehash_kernel(const Slot *__restrict__ old_table, uint64_t old_cap, Slot *__rest
         const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
         if (key == SKM_EMPTY_KEY) continue;
         const unsigned long long cnt = ((unsigned long long)v.w << 32) | v.z;
-        table_upsert(table, log2cap, key, cnt);
+        // keys are unique in the old table: claim the first EMPTY slot of the probe sequence
+        uint64_t sl = skm_home_slot(skm_hash_kmer(key), log2cap);
+        for (;;) {
+            if (ld_cg_u64(&table[sl].key) == SKM_EMPTY_KEY &&
+                atomicCAS(&table[sl].key, (unsigned long long)SKM_EMPTY_KEY, key) == SKM_EMPTY_KEY)
+                break;
+            sl = (sl + 1) & ((1ull << log2cap) - 1);
+        }
+        table[sl].count = cnt;
     }
 }
 
@@ -390,8 +509,6 @@ rehash_kernel(const Slot *__restrict__ old_table, uint64_t old_cap, Slot *__rest
 //     shared copy; the rest (rare) straight to global.  Bin histo_max+1 collects
 //     every count > histo_max (src/kmer/histogram.rs:80-84,125-134).
 // ---------------------------------------------------------------------------
-
-static constexpr int kLowBins = 64;
 
 __global__ void __launch_bounds__(512)
 histogram_kernel(const Slot *__restrict__ table, uint64_t capacity, uint64_t histo_max,
@@ -638,20 +755,6 @@ bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__rest
     });
 }
 
-// Partitioned insert: the k-mer list is grouped by table region; CTAs walk it
-// in order, so at any moment the chip works on a few neighbouring regions that
-// stay resident in L2.
-__global__ void __launch_bounds__(256)
-insert_sorted_list_kernel(const unsigned long long *__restrict__ kmers, uint64_t n,
-                          Slot *__restrict__ table, uint32_t log2cap,
-                          GlobalCounters *__restrict__ gc) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long n_new = 0;
-    if (i < n) n_new = table_upsert(table, log2cap, kmers[i], 1ull);
-    n_new = warp_sum(n_new);
-    if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(&gc->n_distinct, n_new);
-}
-
 // ---------------------------------------------------------------------------
 // synthetic reads on the device (bench / tests)
 // ---------------------------------------------------------------------------
@@ -674,16 +777,40 @@ synth_kernel(skm_synth_params p, uint32_t chunk_index, uint32_t n_chunks, uint64
 // random-access roofline probe
 // ---------------------------------------------------------------------------
 
-// variant 0: key load + RED.ADD.64 (what an insert hit does); 1: RED only; 2: load only
+// variant 0: key load + RED.ADD.64 (what an insert hit does); 1: RED only; 2: load only.
+// variants 3..5: the same three, but update i goes to a random slot of region
+// i / per_region (regions of 2^region_log2 slots visited in order) — the access
+// pattern of the partitioned insert, whose working set stays in L2.
+// variant 6: region-local key load + 32-bit RED.
 __global__ void __launch_bounds__(256)
 gups_kernel(Slot *__restrict__ table, uint32_t log2cap, uint64_t n, uint64_t salt, int variant,
-            unsigned long long *__restrict__ sink) {
+            uint32_t region_log2, unsigned long long *__restrict__ sink) {
     unsigned long long acc = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t s = skm_home_slot(skm_mix64(i + salt), log2cap);
-        if (variant != 1) acc += ld_cg_u64(&table[s].key);
-        if (variant != 2) red_add_u64(&table[s].count, 1ull);
+    const bool local = variant >= 3;
+    const int op = variant == 6 ? 0 : (local ? variant - 3 : variant);
+    const uint64_t n_regions = 1ull << (log2cap - region_log2);
+    const uint64_t per_region = (n + n_regions - 1) / n_regions;
+    if (!local) {
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+             i += (uint64_t)gridDim.x * blockDim.x) {
+            const uint64_t s = skm_home_slot(skm_mix64(i + salt), log2cap);
+            if (op != 1) acc += ld_cg_u64(&table[s].key);
+            if (op != 2) red_add_u64(&table[s].count, 1ull);
+        }
+    } else {
+        // one update per thread, in list order (like insert_sorted_list_kernel)
+        const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < n) {
+            const uint64_t region = i / per_region;
+            const uint64_t s = (region << region_log2) | (skm_mix64(i + salt) >> (64 - region_log2));
+            if (op != 1) acc += ld_cg_u64(&table[s].key);
+            if (op != 2) {
+                if (variant == 6)
+                    atomicAdd(reinterpret_cast<unsigned int *>(&table[s].count), 1u);
+                else
+                    red_add_u64(&table[s].count, 1ull);
+            }
+        }
     }
     if (acc == 0x123456789ull) *sink = acc;
 }

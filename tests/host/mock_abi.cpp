@@ -1,0 +1,102 @@
+// TEST-ONLY mock of the C ABI subset that sharkmer_b200/host/ingest.hpp uses, so
+// that the host-side FASTQ framing / batching / chunk routing can be checked on a
+// machine without a GPU.  It records what the host hands to skm_ingest_batch.
+// Never linked into the product.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sharkmer_b200.h"
+
+struct skm_ctx {
+    skm_params p;
+    std::vector<std::string> chunk_data;
+    std::string err;
+};
+
+extern "C" {
+uint32_t skm_abi_version(void) { return SKM_ABI_VERSION; }
+int32_t skm_create(const skm_params *p, skm_ctx **out) {
+    skm_ctx *c = new skm_ctx();
+    c->p = *p;
+    *out = c;
+    if (p->k < 1 || p->k >= 32) { c->err = "k must be less than 32 (and at least 1), got " + std::to_string(p->k); return SKM_ERR_INVALID_ARG; }
+    if (p->k % 2 == 0) { c->err = "k must be odd, got " + std::to_string(p->k); return SKM_ERR_INVALID_ARG; }
+    c->chunk_data.resize(p->chunks ? p->chunks : 1);
+    return SKM_OK;
+}
+void skm_destroy(skm_ctx *c) { delete c; }
+const char *skm_last_error(const skm_ctx *c) { return c->err.c_str(); }
+int32_t skm_pinned_alloc(skm_ctx *, size_t n, void **out) { *out = std::malloc(n ? n : 1); return *out ? SKM_OK : SKM_ERR_OOM; }
+int32_t skm_pinned_free(skm_ctx *, void *p) { std::free(p); return SKM_OK; }
+int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64_t n, uint32_t) {
+    if (chunk >= c->chunk_data.size()) { c->err = "chunk out of range"; return SKM_ERR_INVALID_ARG; }
+    if (n && seqs[n - 1] != '\n') { c->err = "batch must end with newline"; return SKM_ERR_INVALID_ARG; }
+    c->chunk_data[chunk].append(reinterpret_cast<const char *>(seqs), n);
+    return SKM_OK;
+}
+int32_t skm_finalize(skm_ctx *) { return SKM_OK; }
+int32_t skm_histogram(skm_ctx *, uint32_t, uint64_t *, uint64_t) { return SKM_ERR_STATE; }
+int32_t skm_totals_get(skm_ctx *, skm_totals *t) { std::memset(t, 0, sizeof *t); return SKM_OK; }
+int32_t skm_chunk_totals(skm_ctx *, uint32_t, skm_totals *t) { std::memset(t, 0, sizeof *t); return SKM_OK; }
+int32_t skm_stage_times(skm_ctx *, skm_stage_ms *t) { std::memset(t, 0, sizeof *t); return SKM_OK; }
+int32_t skm_table_len(skm_ctx *, uint64_t *n) { *n = 0; return SKM_OK; }
+int32_t skm_export(skm_ctx *, uint64_t *, uint32_t *, uint64_t, int32_t, uint64_t *n) { *n = 0; return SKM_OK; }
+int32_t skm_lookup_batch(skm_ctx *, const uint64_t *, uint64_t, uint32_t, int32_t, uint32_t *, uint8_t *) { return SKM_ERR_STATE; }
+int32_t skm_insert_counts(skm_ctx *, const uint64_t *, const uint32_t *, uint64_t) { return SKM_ERR_STATE; }
+}
+
+// harness: same flags as the CLI; dumps chunk_<c>.txt + counts.txt into --dump DIR
+#include "../../sharkmer_b200/host/ingest.hpp"
+
+int main(int argc, char **argv) {
+    uint32_t k = 21, chunks = 0;
+    uint64_t max_reads = 0, validate_every = 0;
+    size_t buffer_bytes = 0;
+    bool paired = false;
+    std::string dump = ".";
+    std::vector<std::string> inputs;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "-k") k = std::atoi(argv[++i]);
+        else if (a == "--chunks") chunks = std::atoi(argv[++i]);
+        else if (a == "-m") max_reads = std::strtoull(argv[++i], nullptr, 10);
+        else if (a == "--validate-every") validate_every = std::strtoull(argv[++i], nullptr, 10);
+        else if (a == "--buffer-bytes") buffer_bytes = std::strtoull(argv[++i], nullptr, 10);
+        else if (a == "--paired") paired = true;
+        else if (a == "--dump") dump = argv[++i];
+        else inputs.push_back(a);
+    }
+    try {
+        skm::Engine eng(k, chunks);
+        {
+            skm::Batcher st(eng, buffer_bytes);
+            if (paired) {
+                if (max_reads > 0 && max_reads % 2 != 0) max_reads += 1;
+                skm::LineReader r1(inputs[0]), r2(inputs[1]);
+                skm::read_fastq_paired(r1, r2, st, max_reads, validate_every);
+            } else {
+                for (auto &p : inputs) {
+                    skm::LineReader r(p);
+                    if (skm::read_fastq(r, st, max_reads, validate_every)) break;
+                }
+            }
+            st.finish();
+            FILE *f = std::fopen((dump + "/counts.txt").c_str(), "w");
+            std::fprintf(f, "%llu %llu\n", (unsigned long long)st.n_reads_read, (unsigned long long)st.n_bases_read);
+            std::fclose(f);
+        }
+        skm_ctx *c = eng.raw();
+        for (size_t i = 0; i < c->chunk_data.size(); i++) {
+            FILE *f = std::fopen((dump + "/chunk_" + std::to_string(i) + ".txt").c_str(), "w");
+            std::fwrite(c->chunk_data[i].data(), 1, c->chunk_data[i].size(), f);
+            std::fclose(f);
+        }
+    } catch (const skm::Error &e) {
+        std::fprintf(stderr, "Error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

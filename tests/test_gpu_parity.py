@@ -52,8 +52,7 @@ def test_pack_layout_kats(skm):
             want = (want << 2) | ("ACGT".index(s[p]) if p < len(s) else 0)
         got = int(codes[u])
         nb = min(32, max(0, len(s) - u * 32))
-        if nb:
-            assert got >> (64 - 2 * nb) == want >> (64 - 2 * nb), u
+        assert got == want, u  # breaks and padding pack as 00
         valid_mask = ((1 << nb) - 1) << (32 - nb)
         assert int(breaks[u]) == (~valid_mask) & 0xFFFFFFFF, u
 
@@ -204,7 +203,7 @@ def test_table_growth_from_tiny(skm, oracle):
     for mode in (1, 2):
         e = run_gpu(skm, reads, 31, 2, 100, L, mode=mode, capacity_hint=0)
         run = run_oracle(oracle, reads, 31, 2, 100)
-        assert e.stage_times().n_grows >= 3
+        assert e.stage_times().n_grows >= 2
         compare(e, run, 2)
 
 
