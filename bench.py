@@ -234,21 +234,10 @@ def run_ours(args):
     in_bytes = sum(t.numel() for t in d_bufs)
 
     # ---- one step -------------------------------------------------------------------------------
-    def exchange_and_insert(c):
-        d_ptr, counts = eng.route_chunk(c, world)
-        send = torch.as_tensor(counts.astype(np.int64), device=dev)
-        recv = torch.empty_like(send)
-        dist.all_to_all_single(recv, send)
-        rc = recv.cpu().numpy()
-        n_send, n_recv = int(counts.sum()), int(rc.sum())
-        src = _as_tensor(d_ptr, n_send, dev)
-        dst = torch.empty(max(n_recv, 1), dtype=torch.int64, device=dev)
-        with torch.cuda.stream(stream):
-            dist.all_to_all_single(dst[:n_recv], src, output_split_sizes=rc.tolist(),
-                                   input_split_sizes=counts.astype(np.int64).tolist())
-        stream.synchronize()
-        eng.insert_kmers_device(dst.data_ptr(), n_recv)
-        eng.snapshot_histogram(c)
+    sharded = None
+    if world > 1:
+        from sharkmer_b200.multigpu import ShardedCounter
+        sharded = ShardedCounter(eng, CHUNKS, CHUNKS, HISTO_MAX, dev, stream=stream)
 
     def step(host_buffers: bool):
         eng.reset()
@@ -259,14 +248,9 @@ def run_ours(args):
                 eng.ingest_device(c, d_bufs[c].data_ptr(), d_bufs[c].numel())
         if world == 1:
             eng.finalize()
-            return eng.histogram(CHUNKS - 1)
-        eng.finalize_external()
-        for c in range(CHUNKS):
-            exchange_and_insert(c)
-        cols = np.stack([eng.histogram(c) for c in range(CHUNKS)]).astype(np.int64)
-        tcols = torch.as_tensor(cols, device=dev)
-        dist.all_reduce(tcols)
-        return tcols[-1].cpu().numpy().astype(np.uint64)
+            return eng.histogram(CHUNKS - 1) if CHUNKS else None
+        cols = sharded.finalize()
+        return cols[-1] if cols is not None else None
 
     def timed(host_buffers: bool, steps: int, warmup: int):
         for _ in range(warmup):
@@ -298,7 +282,7 @@ def run_ours(args):
             chk.ingest_batch(b % CHUNKS, reads[b * 1000 * line:(b + 1) * 1000 * line])
         chk.finalize()
         ok = chk.digest() == run.table().digest() and all(
-            (chk.histogram(c) == run.histogram(c)).all() for c in range(CHUNKS))
+            (chk.histogram(c) == run.histogram(c)).all() for c in range(CHUNKS if args.chunks != 0 else 0))
         if not ok:
             raise SystemExit("PARITY FAILURE: GPU table/histograms differ from the oracle on the CPU sample")
         chk.close()
@@ -317,7 +301,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         ms_e2e, ms_e2e_wall, hist_e2e = timed(True, args.steps, args.warmup)
-        if not (hist_e2e == hist_dev).all():
+        if hist_dev is not None and not (hist_e2e == hist_dev).all():
             raise SystemExit("PARITY FAILURE: host-buffer run and device-buffer run disagree")
         if world == 1 and eng.digest() != digest_dev:
             raise SystemExit("PARITY FAILURE: table digest differs between runs")
@@ -366,6 +350,7 @@ def run_ours(args):
                          "algorithmic_bytes": "64 B per k-mer occurrence (sector in + sector out) + 0.375 B per packed base read",
                          "kmers_per_sec_in_kernel": n_kmers_local / (stt.insert * 1e-3)},
             "gpu_launches": int(stt.kernel_launches) * args.steps,
+            "nvlink_bytes_sent_per_step_rank0": (sharded.bytes_sent // max(1, (args.steps + args.warmup) * (1 if args.no_e2e else 2))) if sharded else 0,
             "clocks": clocks,
         }
         if args.gups:
@@ -416,7 +401,14 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--gups", action="store_true", help="also measure the random-access roofline probe")
+    ap.add_argument("--chunks", type=int, default=None, help="EXPERIMENT ONLY: override the workload's chunk count")
+    ap.add_argument("--k", type=int, default=None, help="EXPERIMENT ONLY: override k")
     args = ap.parse_args()
+    global CHUNKS, K
+    if args.chunks is not None:
+        CHUNKS = args.chunks
+    if args.k is not None:
+        K = args.k
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)
     if args.impl == "reference":

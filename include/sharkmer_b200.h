@@ -161,13 +161,16 @@ int32_t skm_insert_counts(skm_ctx *ctx, const uint64_t *keys, const uint32_t *co
 /* ---- multi-GPU building blocks (one ctx per GPU; the collective between the
  * two calls is the caller's: torch.distributed / NCCL all-to-all) ----------- */
 
-/* Extract the canonical k-mers of chunk `chunk_index`'s staged reads on this
- * GPU and bucket them by owner rank.  On return *d_kmers is a device buffer
- * (ctx-owned, valid until the next route call) holding the k-mers grouped by
- * destination rank; send_counts[r] = how many go to rank r. */
-int32_t skm_route_chunk(skm_ctx *ctx, uint32_t chunk_index, uint64_t **d_kmers,
-                        uint64_t *send_counts /* n_ranks */);
-/* Insert `n` k-mers (device memory) that this rank owns. */
+/* Routing of chunk `chunk_index`'s staged reads on this GPU, in two calls so the caller can
+ * size (and double-buffer) the send buffer:
+ *   skm_route_count   extracts the canonical k-mers and counts them per owner rank
+ *                     (send_counts[r], r < n_ranks); synchronous.
+ *   skm_route_scatter writes them into d_out (device memory, sum(send_counts) entries)
+ *                     grouped by destination rank, and drops the chunk's staged reads;
+ *                     asynchronous on the ctx's stream. */
+int32_t skm_route_count(skm_ctx *ctx, uint32_t chunk_index, uint64_t *send_counts /* n_ranks */);
+int32_t skm_route_scatter(skm_ctx *ctx, uint32_t chunk_index, uint64_t *d_out);
+/* Insert `n` k-mers (device memory) that this rank owns; asynchronous on the ctx's stream. */
 int32_t skm_insert_kmers_device(skm_ctx *ctx, const uint64_t *d_kmers, uint64_t n);
 /* Snapshot this rank's partial histogram of its table partition as column
  * `chunk_i` (the caller sums columns over ranks). */

@@ -73,7 +73,8 @@ struct skm_ctx {
     GlobalCounters *d_gc = nullptr;
     unsigned long long *d_hist = nullptr;   // running histogram, histo_max + 2 (chunks > 0)
     bool track_histo = false;
-    int pipe_depth = 4;         // probes in flight per thread (SKM_PIPE_DEPTH: 1, 2, 4, 8)
+    int region_log2 = 17;       // partitioned mode: slots per table region (SKM_REGION_LOG2)
+    int pipe_depth = 1;         // probes in flight per thread (SKM_PIPE_DEPTH: 1, 2, 4, 8); measured best: 1
     unsigned long long *d_bins = nullptr;   // histo_max + 2 (scan histogram)
     HistoTotals *d_tot = nullptr;
     uint64_t *h_pinned = nullptr;           // small pinned scratch for read-backs
@@ -296,17 +297,17 @@ int32_t insert_segment_direct(skm_ctx *c, const Segment &sg, uint32_t chunk) {
 }
 
 uint32_t partition_log2_buckets(const skm_ctx *c) {
-    // regions of <= 2 MiB (2^17 slots), at most kMaxBuckets
-    int l = (int)c->log2cap - 17;
+    // regions of <= 2^region_log2 slots (default 2^17 = 2 MiB), at most kMaxBuckets
+    int l = (int)c->log2cap - c->region_log2;
     if (l < 0) l = 0;
     uint32_t maxl = ceil_log2(kMaxBuckets);
     return std::min<uint32_t>((uint32_t)l, maxl);
 }
 
-// Bucket the k-mers of segments [s0, s1) of a chunk.  On return d_list holds them
-// grouped by bucket; h_counts (optional) receives the per-bucket counts.
-int32_t bucket_segments(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn fn,
-                        uint32_t n_buckets, uint64_t *total_out, uint64_t *h_counts) {
+// Pass 1 of bucketing segments [s0, s1) of a chunk: per-bucket counts + offsets/cursors on the
+// device; the total (and optionally the counts) on the host.
+int32_t bucket_count(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn fn, uint32_t n_buckets,
+                     uint64_t *total_out, uint64_t *h_counts) {
     const ChunkState &cs = c->chunks[chunk];
     CU(cudaMemsetAsync(c->d_bucket_counts, 0, (n_buckets + 1) * sizeof(uint64_t), c->stream));
     {
@@ -314,7 +315,7 @@ int32_t bucket_segments(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, Bucket
         for (size_t s = s0; s < s1; s++) {
             const Segment &sg = cs.segs[s];
             if (!sg.n_units) continue;
-            bucket_count_kernel<<<grid_for(sg.n_units, 256), 256, n_buckets * sizeof(uint32_t), c->stream>>>(
+            bucket_count_kernel<<<grid_for(sg.n_units, 256 * kBucketUnits), 256, n_buckets * sizeof(uint32_t), c->stream>>>(
                 sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_counts,
                 &c->d_cc[chunk]);
             c->launches++;
@@ -325,32 +326,42 @@ int32_t bucket_segments(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, Bucket
         c->launches++;
     }
     CU(cudaGetLastError());
-    // total (and optionally the counts) back to the host
     CU(cudaMemcpyAsync(c->h_pinned, c->d_bucket_offsets + n_buckets, sizeof(uint64_t),
                        cudaMemcpyDeviceToHost, c->stream));
     if (h_counts)
         CU(cudaMemcpyAsync(c->h_pinned + 1, c->d_bucket_counts, n_buckets * sizeof(uint64_t),
                            cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    const uint64_t total = c->h_pinned[0];
+    *total_out = c->h_pinned[0];
     if (h_counts) memcpy(h_counts, c->h_pinned + 1, n_buckets * sizeof(uint64_t));
-    int32_t rc = ensure_list(c, total);
-    if (rc) return rc;
-    {
-        Span sp(c, ST_PART, c->stream);
-        const size_t smem = ((n_buckets + 1) & ~1u) * sizeof(uint32_t) + n_buckets * sizeof(uint64_t);
-        for (size_t s = s0; s < s1; s++) {
-            const Segment &sg = cs.segs[s];
-            if (!sg.n_units) continue;
-            bucket_scatter_kernel<<<grid_for(sg.n_units, 256), 256, smem, c->stream>>>(
-                sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, c->d_list);
-            c->launches++;
-            c->stage_launches[ST_PART]++;
-        }
+    return SKM_OK;
+}
+
+// Pass 2: scatter the k-mers into `d_out`, grouped by bucket (uses the cursors of pass 1).
+int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn fn, uint32_t n_buckets,
+                       unsigned long long *d_out) {
+    const ChunkState &cs = c->chunks[chunk];
+    Span sp(c, ST_PART, c->stream);
+    const size_t smem = ((n_buckets + 1) & ~1u) * sizeof(uint32_t) + n_buckets * sizeof(uint64_t);
+    for (size_t s = s0; s < s1; s++) {
+        const Segment &sg = cs.segs[s];
+        if (!sg.n_units) continue;
+        bucket_scatter_kernel<<<grid_for(sg.n_units, 256 * kBucketUnits), 256, smem, c->stream>>>(
+            sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, d_out);
+        c->launches++;
+        c->stage_launches[ST_PART]++;
     }
     CU(cudaGetLastError());
-    *total_out = total;
     return SKM_OK;
+}
+
+int32_t bucket_segments(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn fn,
+                        uint32_t n_buckets, uint64_t *total_out, uint64_t *h_counts) {
+    int32_t rc = bucket_count(c, chunk, s0, s1, fn, n_buckets, total_out, h_counts);
+    if (rc) return rc;
+    rc = ensure_list(c, *total_out);
+    if (rc) return rc;
+    return bucket_scatter(c, chunk, s0, s1, fn, n_buckets, c->d_list);
 }
 
 int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_t *d_counts, uint64_t n) {
@@ -587,6 +598,7 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     // SKM_HISTO_SCAN=1 (diagnostic) falls back to one table scan per chunk.
     c->track_histo = c->p.chunks > 0 && !getenv("SKM_HISTO_SCAN");
     if (const char *g = getenv("SKM_PIPE_DEPTH")) c->pipe_depth = atoi(g);
+    if (const char *g = getenv("SKM_REGION_LOG2")) c->region_log2 = std::max(10, std::min(30, atoi(g)));
     if (const char *g = getenv("SKM_L2_FETCH")) {  // diagnostic: 32 / 64 / 128
         cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     }
@@ -1099,20 +1111,34 @@ int32_t skm_insert_counts(skm_ctx *c, const uint64_t *keys, const uint32_t *coun
 
 // ---- multi-GPU building blocks -------------------------------------------------
 
-int32_t skm_route_chunk(skm_ctx *c, uint32_t chunk, uint64_t **d_kmers, uint64_t *send_counts) {
-    if (!c || !d_kmers || !send_counts) return SKM_ERR_INVALID_ARG;
-    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
-    if (c->chunks[chunk].counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
+static BucketFn owner_fn(const skm_ctx *c) {
     BucketFn fn;
     fn.mode = 0;
     fn.n_ranks = c->n_ranks;
     fn.log2cap = c->log2cap;
     fn.log2buckets = 0;
-    uint64_t total = 0;
+    return fn;
+}
+
+int32_t skm_route_count(skm_ctx *c, uint32_t chunk, uint64_t *send_counts) {
+    if (!c || !send_counts) return SKM_ERR_INVALID_ARG;
+    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
     ChunkState &cs = c->chunks[chunk];
-    int32_t rc = bucket_segments(c, chunk, 0, cs.segs.size(), fn, c->n_ranks, &total, send_counts);
+    if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
+    uint64_t total = 0;
+    return bucket_count(c, chunk, 0, cs.segs.size(), owner_fn(c), c->n_ranks, &total, send_counts);
+}
+
+int32_t skm_route_scatter(skm_ctx *c, uint32_t chunk, uint64_t *d_out) {
+    if (!c) return SKM_ERR_INVALID_ARG;
+    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    ChunkState &cs = c->chunks[chunk];
+    if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
+    int32_t rc = bucket_scatter(c, chunk, 0, cs.segs.size(), owner_fn(c), c->n_ranks, (unsigned long long *)d_out);
     if (rc) return rc;
     for (auto &sg : cs.segs) {
         CU(cudaFreeAsync(sg.codes, c->stream));
@@ -1121,9 +1147,7 @@ int32_t skm_route_chunk(skm_ctx *c, uint32_t chunk, uint64_t **d_kmers, uint64_t
         sg.breaks = nullptr;
     }
     cs.counted = true;
-    CU(cudaStreamSynchronize(c->stream));
-    *d_kmers = (uint64_t *)c->d_list;
-    return SKM_OK;
+    return SKM_OK;  // asynchronous: ordered on the ctx's stream
 }
 
 int32_t skm_insert_kmers_device(skm_ctx *c, const uint64_t *d_kmers, uint64_t n) {
@@ -1133,9 +1157,8 @@ int32_t skm_insert_kmers_device(skm_ctx *c, const uint64_t *d_kmers, uint64_t n)
     DeviceGuard g(c->device);
     int32_t rc = insert_list(c, (const unsigned long long *)d_kmers, nullptr, n);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(c->stream));
     c->have_tot = false;
-    return SKM_OK;
+    return SKM_OK;  // asynchronous: ordered on the ctx's stream
 }
 
 int32_t skm_snapshot_histogram(skm_ctx *c, uint32_t chunk_i) {

@@ -676,6 +676,10 @@ struct BucketFn {
     }
 };
 
+// Each CTA covers kBucketUnits * 256 units (= kBucketUnits * 8192 bases), so that it owns
+// several k-mers per bucket and the per-bucket global reservations amortise.
+static constexpr uint32_t kBucketUnits = 4;
+
 __global__ void __launch_bounds__(256)
 bucket_count_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
                     uint64_t u_begin, uint64_t u_end, uint32_t k, BucketFn fn, uint32_t n_buckets,
@@ -683,10 +687,13 @@ bucket_count_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restri
     extern __shared__ uint32_t s_cnt[];
     for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
-    const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const UnitInput in = load_unit(codes, breaks, u, u_end);
-    unsigned long long n_win =
-        extract_unit(in, k, [&](uint64_t kmer, int) { atomicAdd(&s_cnt[fn(kmer)], 1u); });
+    unsigned long long n_win = 0;
+#pragma unroll 1
+    for (uint32_t r = 0; r < kBucketUnits; r++) {
+        const uint64_t u = u_begin + ((uint64_t)blockIdx.x * kBucketUnits + r) * blockDim.x + threadIdx.x;
+        const UnitInput in = load_unit(codes, breaks, u, u_end);
+        n_win += extract_unit(in, k, [&](uint64_t kmer, int) { atomicAdd(&s_cnt[fn(kmer)], 1u); });
+    }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) {
         const uint32_t c = s_cnt[i];
@@ -735,24 +742,46 @@ bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__rest
         reinterpret_cast<unsigned long long *>(s_mem + ((n_buckets + 1) & ~1u));  // n_buckets
     for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
-    const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const UnitInput in = load_unit(codes, breaks, u, u_end);
     // round 1: this CTA's count per bucket
-    extract_unit(in, k, [&](uint64_t kmer, int) { atomicAdd(&s_cnt[fn(kmer)], 1u); });
-    __syncthreads();
-    // reserve this CTA's slice of every non-empty bucket
-    for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) {
-        const uint32_t c = s_cnt[i];
-        s_base[i] = c ? atomicAdd(&cursors[i], (unsigned long long)c) : 0ull;
-        s_cnt[i] = 0;
+#pragma unroll 1
+    for (uint32_t r = 0; r < kBucketUnits; r++) {
+        const uint64_t u = u_begin + ((uint64_t)blockIdx.x * kBucketUnits + r) * blockDim.x + threadIdx.x;
+        const UnitInput in = load_unit(codes, breaks, u, u_end);
+        extract_unit(in, k, [&](uint64_t kmer, int) { atomicAdd(&s_cnt[fn(kmer)], 1u); });
     }
     __syncthreads();
-    // round 2: re-extract (ALU is free here) and scatter
-    extract_unit(in, k, [&](uint64_t kmer, int) {
-        const uint32_t b = fn(kmer);
-        const uint32_t r = atomicAdd(&s_cnt[b], 1u);
-        out[s_base[b] + r] = kmer;
-    });
+    // reserve this CTA's slice of every non-empty bucket; the atomics of one thread are
+    // independent, so they are issued back to back and their latencies overlap
+    for (uint32_t i0 = threadIdx.x; i0 < n_buckets; i0 += 4 * blockDim.x) {
+        unsigned long long base[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = i0 + q * blockDim.x;
+            const uint32_t c = i < n_buckets ? s_cnt[i] : 0u;
+            base[q] = c ? atomicAdd(&cursors[i], (unsigned long long)c) : 0ull;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = i0 + q * blockDim.x;
+            if (i < n_buckets) {
+                s_base[i] = base[q];
+                s_cnt[i] = 0;
+            }
+        }
+    }
+    __syncthreads();
+    // round 2: re-extract (ALU is free here) and scatter; neighbouring CTAs fill neighbouring
+    // cells of a bucket, so L2 merges the 8-byte stores into full sectors before DRAM
+#pragma unroll 1
+    for (uint32_t r = 0; r < kBucketUnits; r++) {
+        const uint64_t u = u_begin + ((uint64_t)blockIdx.x * kBucketUnits + r) * blockDim.x + threadIdx.x;
+        const UnitInput in = load_unit(codes, breaks, u, u_end);
+        extract_unit(in, k, [&](uint64_t kmer, int) {
+            const uint32_t b = fn(kmer);
+            const uint32_t rk = atomicAdd(&s_cnt[b], 1u);
+            out[s_base[b] + rk] = kmer;
+        });
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -150,11 +150,13 @@ class Engine:
         self._ck(self.L.skm_insert_counts(self._h, k.ctypes.data, c.ctypes.data, k.size))
 
     # ---- multi-GPU building blocks --------------------------------------
-    def route_chunk(self, chunk_index: int, n_ranks: int):
+    def route_count(self, chunk_index: int, n_ranks: int) -> np.ndarray:
         counts = np.zeros(n_ranks, dtype=np.uint64)
-        d = C.c_void_p()
-        self._ck(self.L.skm_route_chunk(self._h, chunk_index, C.byref(d), counts.ctypes.data))
-        return (d.value or 0), counts
+        self._ck(self.L.skm_route_count(self._h, chunk_index, counts.ctypes.data))
+        return counts
+
+    def route_scatter(self, chunk_index: int, d_out: int):
+        self._ck(self.L.skm_route_scatter(self._h, chunk_index, d_out))
 
     def insert_kmers_device(self, d_ptr: int, n: int):
         self._ck(self.L.skm_insert_kmers_device(self._h, d_ptr, n))

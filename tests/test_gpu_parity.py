@@ -203,7 +203,7 @@ def test_table_growth_from_tiny(skm, oracle):
     for mode in (1, 2):
         e = run_gpu(skm, reads, 31, 2, 100, L, mode=mode, capacity_hint=0)
         run = run_oracle(oracle, reads, 31, 2, 100)
-        assert e.stage_times().n_grows >= 2
+        assert e.stage_times().n_grows >= 1
         compare(e, run, 2)
 
 
@@ -393,3 +393,53 @@ def test_reset_reuses_ctx(skm, oracle):
         e.finalize()
         run = run_oracle(oracle, reads, 21, 2, 100)
         compare(e, run, 2)
+
+
+# ---- (7) hash-sharded path, two table partitions on one GPU ----------------------------------------
+
+def test_sharded_two_partitions_single_process(skm, oracle):
+    """The multi-GPU building blocks (route_count / route_scatter / insert_kmers_device /
+    snapshot_histogram) with two ctx's (ranks 0 and 1 of 2) on the same device; the
+    all-to-all is done by slicing device tensors.  Result must equal the oracle's and be
+    split exactly by owner rank."""
+    import torch
+    from sharkmer_b200 import common
+    L, n, k, chunks, hmax, world = 120, 12_000, 25, 3, 100, 2
+    reads = oracle.synth_reads(31, 40_000, L, 0.01, 0.001, 0, n)
+    run = run_oracle(oracle, reads, k, chunks, hmax)
+    line = L + 1
+    engs = [skm.Engine(k, chunks, hmax, n_ranks=world, rank=r) for r in range(world)]
+    # rank r ingests every other 1000-read batch of each chunk
+    nb = n // 1000
+    for b in range(nb):
+        c = b % chunks
+        r = (b // chunks) % world
+        engs[r].ingest_batch(c, reads[b * 1000 * line:(b + 1) * 1000 * line])
+    for e in engs:
+        e.finalize_external()
+    for c in range(chunks):
+        counts = [e.route_count(c, world) for e in engs]
+        sends = []
+        for e, cnt in zip(engs, counts):
+            t = torch.empty(max(int(cnt.sum()), 1), dtype=torch.int64, device="cuda")
+            e.route_scatter(c, t.data_ptr())
+            e.sync()
+            sends.append(t)
+        for dst in range(world):
+            parts = []
+            for src in range(world):
+                off = int(counts[src][:dst].sum())
+                parts.append(sends[src][off:off + int(counts[src][dst])])
+            recv = torch.cat(parts).contiguous()
+            engs[dst].insert_kmers_device(recv.data_ptr(), recv.numel())
+            engs[dst].snapshot_histogram(c)
+        col = sum(e.histogram(c).astype(np.int64) for e in engs)
+        assert (col == run.histogram(c).astype(np.int64)).all(), c
+    merged = {}
+    for r, e in enumerate(engs):
+        keys, cnts = e.export(sorted=True)
+        assert all(common.owner_rank(common.hash_kmer(int(x)), world) == r for x in keys[:2000])
+        merged.update(zip(keys.tolist(), cnts.tolist()))
+    okeys, ocounts = run.table().export_sorted()
+    assert merged == dict(zip(okeys.tolist(), ocounts.tolist()))
+    assert sum(e.chunk_totals(c).n_kmers for e in engs for c in range(chunks)) == run.n_kmers_ingested

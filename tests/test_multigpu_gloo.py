@@ -1,0 +1,130 @@
+"""The N>1 path on CPU: world_size-2 `gloo` run of sharkmer_b200.multigpu.ShardedCounter
+(the driver code the GPU bench uses) with a TEST-ONLY stand-in for the per-GPU engine that
+gets its k-mers from the oracle.  Checks the routing rule (owner = low 32 hash bits mod N),
+the split sizes, the per-chunk barrier order and the histogram all-reduce: the merged result
+must equal the single-process oracle, independent of N."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+K, CHUNKS, HMAX, L, NREADS = 21, 4, 50, 100, 9000
+
+
+class FakeEngine:
+    """Routing interface of kmer.Engine over host memory; counting by a dict."""
+
+    def __init__(self, oracle, common, reads_by_chunk, world):
+        self.o, self.common, self.world = oracle, common, world
+        self.reads = reads_by_chunk
+        self.table = {}
+        self.cols = {}
+        self.routed = {}
+        self.keep = []
+
+    def finalize_external(self): pass
+    def sync(self): pass
+
+    def _kmers(self, c):
+        out = []
+        for s in self.reads[c]:
+            out.extend(self.o.kmers_from_ascii(s, K))
+        return np.array(out, dtype=np.uint64)
+
+    def route_count(self, c, world):
+        km = self._kmers(c)
+        owners = np.array([self.common.owner_rank(self.common.hash_kmer(int(x)), world) for x in km], dtype=np.int64)
+        order = np.argsort(owners, kind="stable")
+        self.routed[c] = km[order]
+        return np.bincount(owners, minlength=world).astype(np.uint64)
+
+    def route_scatter(self, c, ptr):
+        km = self.routed.pop(c)
+        dst = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_int64 * max(len(km), 1)).from_address(ptr))
+        dst[:len(km)] = km.view(np.int64)
+
+    def insert_kmers_device(self, ptr, n):
+        if n == 0:
+            return
+        a = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_int64 * n).from_address(ptr)).view(np.uint64)
+        for x in a.tolist():
+            self.table[x] = self.table.get(x, 0) + 1
+
+    def snapshot_histogram(self, c):
+        v = np.zeros(HMAX + 2, dtype=np.uint64)
+        for n in self.table.values():
+            v[n if n <= HMAX else HMAX + 1] += 1
+        self.cols[c] = v
+
+    def histogram(self, c):
+        return self.cols[c]
+
+
+def worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as o
+    from sharkmer_b200 import common
+    from sharkmer_b200.multigpu import ShardedCounter
+    reads = o.synth_reads(5, 20_000, L, 0.01, 0.002, 0, NREADS).tobytes().decode().split("\n")[:-1]
+    # chunk c = batches b = c (mod CHUNKS); rank r takes the r-th slice of each chunk's batches
+    by_chunk = []
+    for c in range(CHUNKS):
+        batches = list(range(c, (NREADS + 999) // 1000, CHUNKS))
+        lo, hi = len(batches) * rank // world, len(batches) * (rank + 1) // world
+        mine = []
+        for b in batches[lo:hi]:
+            mine.extend(reads[b * 1000:(b + 1) * 1000])
+        by_chunk.append(mine)
+    eng = FakeEngine(o, common, by_chunk, world)
+    sc = ShardedCounter(eng, CHUNKS, CHUNKS, HMAX, torch.device("cpu"))
+    cols = sc.finalize()
+    # every key this rank holds must be one it owns
+    assert all(common.owner_rank(common.hash_kmer(x), world) == rank for x in eng.table)
+    tot = sc.global_totals({"n_unique": len(eng.table), "n_kmers": sum(eng.table.values())})
+    gathered = [None] * world
+    dist.all_gather_object(gathered, eng.table)
+    if rank == 0:
+        merged = {}
+        for t in gathered:
+            assert not (set(t) & set(merged))  # partitions are disjoint
+            merged.update(t)
+        q.put((cols, tot, merged))
+    dist.destroy_process_group()
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_counter_matches_oracle(oracle, world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    cols, tot, merged = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    run = oracle.Run(K, CHUNKS, HMAX)
+    run.push_lines(oracle.synth_reads(5, 20_000, L, 0.01, 0.002, 0, NREADS))
+    run.finish()
+    keys, counts = run.table().export_sorted()
+    assert merged == dict(zip(keys.tolist(), counts.tolist()))
+    assert tot == {"n_unique": keys.size, "n_kmers": int(run.n_kmers_ingested)}
+    for c in range(CHUNKS):
+        assert (cols[c] == run.histogram(c)).all(), c
