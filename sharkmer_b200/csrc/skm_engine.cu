@@ -29,7 +29,7 @@ constexpr double kMaxLoad = 0.70;       // grow before the table is fuller than 
 constexpr double kTargetLoad = 0.60;    // load at capacity_hint
 constexpr uint64_t kMinTile = 1ull << 22;  // k-mers; smallest tile worth a launch near the limit
 constexpr uint32_t kMinLog2Cap = 16;
-constexpr uint32_t kMaxBuckets = 4096;
+constexpr uint32_t kMaxBuckets = 1024;  // scatter stages a CTA's k-mers in bucket order: runs stay >= 12 k-mers
 constexpr uint64_t kMaxListKmers = 1ull << 30;  // k-mer list budget per partition pass (8 GiB)
 
 enum Stage { ST_H2D, ST_PACK, ST_COUNT, ST_PART, ST_INSERT, ST_HISTO, ST_GROW, ST_FINALIZE, ST_N };
@@ -73,7 +73,7 @@ struct skm_ctx {
     GlobalCounters *d_gc = nullptr;
     unsigned long long *d_hist = nullptr;   // running histogram, histo_max + 2 (chunks > 0)
     bool track_histo = false;
-    int region_log2 = 17;       // partitioned mode: slots per table region (SKM_REGION_LOG2)
+    int region_log2 = 19;       // partitioned mode: slots per table region, 2^19 = 8 MiB (SKM_REGION_LOG2)
     int pipe_depth = 1;         // probes in flight per thread (SKM_PIPE_DEPTH: 1, 2, 4, 8); measured best: 1
     unsigned long long *d_bins = nullptr;   // histo_max + 2 (scan histogram)
     HistoTotals *d_tot = nullptr;
@@ -326,6 +326,7 @@ int32_t bucket_count(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn 
         c->launches++;
     }
     CU(cudaGetLastError());
+    if (!total_out) return SKM_OK;  // caller does not need the numbers on the host: stay asynchronous
     CU(cudaMemcpyAsync(c->h_pinned, c->d_bucket_offsets + n_buckets, sizeof(uint64_t),
                        cudaMemcpyDeviceToHost, c->stream));
     if (h_counts)
@@ -342,11 +343,11 @@ int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketF
                        unsigned long long *d_out) {
     const ChunkState &cs = c->chunks[chunk];
     Span sp(c, ST_PART, c->stream);
-    const size_t smem = ((n_buckets + 1) & ~1u) * sizeof(uint32_t) + n_buckets * sizeof(uint64_t);
+    const size_t smem = scatter_smem_bytes(n_buckets);
     for (size_t s = s0; s < s1; s++) {
         const Segment &sg = cs.segs[s];
         if (!sg.n_units) continue;
-        bucket_scatter_kernel<<<grid_for(sg.n_units, 256 * kBucketUnits), 256, smem, c->stream>>>(
+        bucket_scatter_kernel<<<grid_for(sg.n_units, kScatterThreads), kScatterThreads, smem, c->stream>>>(
             sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, d_out);
         c->launches++;
         c->stage_launches[ST_PART]++;
@@ -355,16 +356,8 @@ int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketF
     return SKM_OK;
 }
 
-int32_t bucket_segments(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn fn,
-                        uint32_t n_buckets, uint64_t *total_out, uint64_t *h_counts) {
-    int32_t rc = bucket_count(c, chunk, s0, s1, fn, n_buckets, total_out, h_counts);
-    if (rc) return rc;
-    rc = ensure_list(c, *total_out);
-    if (rc) return rc;
-    return bucket_scatter(c, chunk, s0, s1, fn, n_buckets, c->d_list);
-}
-
-int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_t *d_counts, uint64_t n) {
+int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_t *d_counts, uint64_t n,
+                    const unsigned long long *n_dev = nullptr) {
     uint64_t i = 0;
     while (i < n) {
         uint64_t granted = 0;
@@ -376,7 +369,8 @@ int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_
             const uint32_t grid = grid_for(granted, kListTile);
 #define SKM_LAUNCH_IL(D, H)                                                                          \
     insert_list_kernel<D, H><<<grid, 256, 0, c->stream>>>(d_kmers + i, d_counts ? d_counts + i : nullptr, \
-                                                          granted, c->table, c->log2cap, c->d_gc, c->d_hist, \
+                                                          granted, (i == 0 && granted == n) ? n_dev : nullptr,   \
+                                                          c->table, c->log2cap, c->d_gc, c->d_hist,           \
                                                           c->p.histo_max)
             const bool h = c->track_histo;
             switch (c->pipe_depth) {
@@ -417,11 +411,34 @@ int32_t insert_chunk_partitioned(skm_ctx *c, uint32_t chunk) {
         fn.log2cap = c->log2cap;
         fn.log2buckets = partition_log2_buckets(c);
         const uint32_t n_buckets = 1u << fn.log2buckets;
-        uint64_t total = 0;
-        rc = bucket_segments(c, chunk, s0, s1, fn, n_buckets, &total, nullptr);
+        // `bytes` bounds the number of k-mers of the group, so the list can be sized and the insert
+        // queued without waiting for the exact count (it stays on the device, offsets[n_buckets]).
+        rc = ensure_list(c, bytes);
         if (rc) return rc;
-        rc = insert_list(c, c->d_list, nullptr, total);
+        uint64_t granted = 0;
+        rc = reserve_headroom(c, bytes, &granted);
         if (rc) return rc;
+        fn.log2cap = c->log2cap;  // reserve_headroom may have grown the table
+        fn.log2buckets = partition_log2_buckets(c);
+        const uint32_t nb2 = 1u << fn.log2buckets;
+        (void)n_buckets;
+        if (granted >= bytes) {
+            rc = bucket_count(c, chunk, s0, s1, fn, nb2, nullptr, nullptr);
+            if (rc) return rc;
+            rc = bucket_scatter(c, chunk, s0, s1, fn, nb2, c->d_list);
+            if (rc) return rc;
+            rc = insert_list(c, c->d_list, nullptr, bytes, c->d_bucket_offsets + nb2);
+            if (rc) return rc;
+        } else {
+            // close to the load limit: get the exact count and let insert_list tile / grow
+            uint64_t total = 0;
+            rc = bucket_count(c, chunk, s0, s1, fn, nb2, &total, nullptr);
+            if (rc) return rc;
+            rc = bucket_scatter(c, chunk, s0, s1, fn, nb2, c->d_list);
+            if (rc) return rc;
+            rc = insert_list(c, c->d_list, nullptr, total);
+            if (rc) return rc;
+        }
         s0 = s1;
     }
     return SKM_OK;
@@ -506,7 +523,7 @@ int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t
     CU(cudaMallocAsync((void **)&sg.breaks, sg.n_units * sizeof(uint32_t), c->stream));
     {
         Span sp(c, ST_PACK, c->stream);
-        pack_kernel<<<grid_for(sg.n_units, 256), 256, 0, c->stream>>>(d_seqs, n_bytes, c->pos_base, sg.codes,
+        pack_kernel<<<grid_for(sg.n_units, 256 * kPackUnits), 256, 0, c->stream>>>(d_seqs, n_bytes, c->pos_base, sg.codes,
                                                                       sg.breaks, sg.n_units, &c->d_cc[chunk],
                                                                       c->d_gc);
         c->launches++;
@@ -583,7 +600,8 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     CU(cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CU(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CU(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)scatter_smem_bytes(kMaxBuckets)));
 
     CU(cudaMalloc((void **)&c->d_cc, c->n_chunks * sizeof(ChunkCounters)));
     CU(cudaMemset(c->d_cc, 0, c->n_chunks * sizeof(ChunkCounters)));
@@ -797,7 +815,12 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
     for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
         ChunkState &cs = c->chunks[ch];
         uint32_t mode = c->p.insert_mode;
-        if (mode == SKM_INSERT_AUTO) mode = SKM_INSERT_DIRECT;
+        if (mode == SKM_INSERT_AUTO) {
+            // Partitioned wins once the table no longer fits in L2 and the chunk is big enough to
+            // amortise the two bucketing passes (measured crossover); else direct.
+            const bool big_table = c->capacity * sizeof(Slot) >= (96ull << 20);
+            mode = (big_table && cs.n_bytes >= (1ull << 23)) ? SKM_INSERT_PARTITIONED : SKM_INSERT_DIRECT;
+        }
         if (mode == SKM_INSERT_PARTITIONED) {
             rc = insert_chunk_partitioned(c, ch);
             if (rc) return rc;
@@ -1188,7 +1211,7 @@ static int32_t pack_host_input(skm_ctx *c, const uint8_t *seqs, uint64_t n_bytes
     CU(cudaMallocAsync((void **)&d_gc, sizeof(GlobalCounters), c->stream));
     CU(cudaMemsetAsync(d_cc, 0, sizeof(ChunkCounters), c->stream));
     CU(cudaMemsetAsync(d_gc, 0xFF, sizeof(GlobalCounters), c->stream));
-    pack_kernel<<<grid_for(sg->n_units, 256), 256, 0, c->stream>>>(d_raw, n_bytes, 0, sg->codes, sg->breaks,
+    pack_kernel<<<grid_for(sg->n_units, 256 * kPackUnits), 256, 0, c->stream>>>(d_raw, n_bytes, 0, sg->codes, sg->breaks,
                                                                   sg->n_units, d_cc, d_gc);
     c->launches++;
     CU(cudaGetLastError());

@@ -80,6 +80,23 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     return v;
 }
 
+// Add a per-thread value into a global counter with ONE atomic per CTA.  Same-address global
+// atomics retire at roughly one per nanosecond chip-wide, so a per-warp atomicAdd on a counter
+// (hundreds of thousands per launch) costs more than the kernel's real work.
+__device__ __forceinline__ void block_add(unsigned long long *counter, unsigned long long v) {
+    __shared__ unsigned long long s_part[32];
+    v = warp_sum(v);
+    const uint32_t w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();  // s_part may still be in use by a previous block_add
+    if ((threadIdx.x & 31) == 0) s_part[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (uint32_t i = 0; i < nw; i++) t += s_part[i];
+        if (t) atomicAdd(counter, t);
+    }
+}
+
 // 0x80 in every byte of v that is zero (exact, no borrow artefacts)
 __device__ __forceinline__ uint32_t zero_bytes(uint32_t v) {
     return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
@@ -116,17 +133,22 @@ __device__ __forceinline__ void pack_word(uint32_t w, uint32_t &code8, uint32_t 
     bad = ~(acgt | is_n | is_nl) & 0x80808080u;
 }
 
+static constexpr uint32_t kPackUnits = 4;  // units per thread: one CTA packs 32 KiB of input
+
 __global__ void __launch_bounds__(256)
 pack_kernel(const uint8_t *__restrict__ in, uint64_t n_bytes, uint64_t pos_base,
             uint64_t *__restrict__ codes, uint32_t *__restrict__ breaks, uint64_t n_units,
             ChunkCounters *__restrict__ cc, GlobalCounters *__restrict__ gc) {
-    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long my_reads = 0, my_bases = 0;
-    if (u < n_units) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+#pragma unroll 1
+    for (uint32_t r = 0; r < kPackUnits; r++) {
+        const uint64_t u = ((uint64_t)blockIdx.x * kPackUnits + r) * blockDim.x + threadIdx.x;
+        if (u >= n_units) break;
         const uint64_t off = u * 32;
         uint32_t w[8];
         const bool full = off + 32 <= n_bytes;
-        if (full && ((reinterpret_cast<uintptr_t>(in) & 15) == 0)) {
+        if (full && aligned) {
             const uint4 a = ld_nc_v4(reinterpret_cast<const uint4 *>(in + off));
             const uint4 b = ld_nc_v4(reinterpret_cast<const uint4 *>(in + off) + 1);
             w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
@@ -169,16 +191,12 @@ pack_kernel(const uint8_t *__restrict__ in, uint64_t n_bytes, uint64_t pos_base,
                 atomicMin(&gc->first_bad, (p << 8) | ((w[i] >> (8 * j)) & 0xFFu));
             }
         }
-        my_bases = __popc(valid);
+        my_bases += __popc(valid);
         codes[u] = code;
         breaks[u] = ~valid;
     }
-    my_reads = warp_sum(my_reads);
-    my_bases = warp_sum(my_bases);
-    if ((threadIdx.x & 31) == 0) {
-        if (my_reads) atomicAdd(&cc->n_reads, my_reads);
-        if (my_bases) atomicAdd(&cc->n_bases, my_bases);
-    }
+    block_add(&cc->n_reads, my_reads);
+    block_add(&cc->n_bases, my_bases);
 }
 
 // Concatenated bases + offsets -> newline-terminated lines (skm_ingest_reads).
@@ -421,12 +439,8 @@ extract_insert_kernel(const uint64_t *__restrict__ codes, const uint32_t *__rest
     InsertPipe<D, kHisto> pipe(table, log2cap, hs);
     unsigned long long n_win = extract_unit(in, k, [&](uint64_t kmer, int) { pipe.push(kmer); });
     pipe.drain();
-    unsigned long long n_new = warp_sum(pipe.n_new);
-    n_win = warp_sum(n_win);
-    if ((threadIdx.x & 31) == 0) {
-        if (n_new) atomicAdd(&gc->n_distinct, n_new);
-        if (n_win) atomicAdd(&cc->n_windows, n_win);
-    }
+    block_add(&gc->n_distinct, pipe.n_new);
+    block_add(&cc->n_windows, n_win);
     if (kHisto) histo_smem_flush(s_low, g_hist);
 }
 
@@ -437,8 +451,7 @@ count_windows_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restr
     const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const UnitInput in = load_unit(codes, breaks, u, u_end);
     unsigned long long n_win = extract_unit(in, k, [&](uint64_t, int) {});
-    n_win = warp_sum(n_win);
-    if ((threadIdx.x & 31) == 0 && n_win) atomicAdd(&cc->n_windows, n_win);
+    block_add(&cc->n_windows, n_win);
 }
 
 // Insert a flat list of k-mers (received from other ranks, or a region-sorted
@@ -451,8 +464,13 @@ static constexpr uint32_t kListTile = 256 * kListPerThread;
 template <int D, bool kHisto>
 __global__ void __launch_bounds__(256)
 insert_list_kernel(const unsigned long long *__restrict__ kmers, const uint32_t *__restrict__ counts,
-                   uint64_t n, Slot *__restrict__ table, uint32_t log2cap, GlobalCounters *__restrict__ gc,
+                   uint64_t n, const unsigned long long *__restrict__ n_dev, Slot *__restrict__ table,
+                   uint32_t log2cap, GlobalCounters *__restrict__ gc,
                    unsigned long long *__restrict__ g_hist, unsigned long long histo_max) {
+    // n_dev (optional): the list length lives in device memory (written by the bucketing scan),
+    // so the host can queue this launch without waiting for it; the grid covers the upper bound n.
+    if (n_dev) n = *n_dev < n ? *n_dev : n;
+    if ((uint64_t)blockIdx.x * kListTile >= n) return;
     __shared__ int s_low[kHisto ? kLowBins * 32 : 1];
     if (kHisto) histo_smem_init(s_low);
     HistoSink hs{s_low, g_hist, histo_max, threadIdx.x & 31};
@@ -464,8 +482,7 @@ insert_list_kernel(const unsigned long long *__restrict__ kmers, const uint32_t 
         if (i < n) pipe.push(kmers[i], counts ? counts[i] : 1u);
     }
     pipe.drain();
-    const unsigned long long n_new = warp_sum(pipe.n_new);
-    if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(&gc->n_distinct, n_new);
+    block_add(&gc->n_distinct, pipe.n_new);
     if (kHisto) histo_smem_flush(s_low, g_hist);
 }
 
@@ -699,8 +716,7 @@ bucket_count_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restri
         const uint32_t c = s_cnt[i];
         if (c) atomicAdd(&g_counts[i], (unsigned long long)c);
     }
-    n_win = warp_sum(n_win);
-    if ((threadIdx.x & 31) == 0 && n_win) atomicAdd(&cc->n_windows, n_win);
+    block_add(&cc->n_windows, n_win);
 }
 
 // offsets[b] = sum of counts[0..b); cursors[b] = offsets[b]; offsets[n] = total
@@ -732,55 +748,75 @@ bucket_scan_kernel(const unsigned long long *__restrict__ counts, uint32_t n_buc
     }
 }
 
-__global__ void __launch_bounds__(256)
+// Scatter with shared-memory staging: the CTA's k-mers are first laid out in bucket order in
+// shared memory, then copied out so that consecutive threads write consecutive cells of a
+// bucket run (whole 32-byte sectors / 128-byte lines instead of lone 8-byte stores, which cost
+// one L2 request each).  One CTA = kScatterThreads units = kScatterThreads*32 bases.
+static constexpr uint32_t kScatterThreads = 384;                    // 12288 positions per CTA
+static constexpr uint32_t kScatterStage = kScatterThreads * 32;     // max k-mers per CTA
+
+__host__ __device__ inline size_t scatter_smem_bytes(uint32_t n_buckets) {
+    // staging (u64) | s_gbase (u64) | s_cnt (u32) | s_start (u32, n_buckets + 1)
+    return (size_t)kScatterStage * 8 + (size_t)n_buckets * 8 + (size_t)n_buckets * 4 + ((size_t)n_buckets + 2) * 4;
+}
+
+__global__ void __launch_bounds__(kScatterThreads)
 bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
                       uint64_t u_begin, uint64_t u_end, uint32_t k, BucketFn fn, uint32_t n_buckets,
                       unsigned long long *__restrict__ cursors, unsigned long long *__restrict__ out) {
-    extern __shared__ uint32_t s_mem[];
-    uint32_t *s_cnt = s_mem;                                   // n_buckets: counts, then local ranks
-    unsigned long long *s_base =
-        reinterpret_cast<unsigned long long *>(s_mem + ((n_buckets + 1) & ~1u));  // n_buckets
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long *stage = reinterpret_cast<unsigned long long *>(s_raw);
+    unsigned long long *s_gbase = stage + kScatterStage;
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_gbase + n_buckets);
+    uint32_t *s_start = s_cnt + n_buckets;  // n_buckets + 1
+    __shared__ uint32_t s_warp_tot[kScatterThreads / 32];
+
     for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
+    const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const UnitInput in = load_unit(codes, breaks, u, u_end);
     // round 1: this CTA's count per bucket
-#pragma unroll 1
-    for (uint32_t r = 0; r < kBucketUnits; r++) {
-        const uint64_t u = u_begin + ((uint64_t)blockIdx.x * kBucketUnits + r) * blockDim.x + threadIdx.x;
-        const UnitInput in = load_unit(codes, breaks, u, u_end);
-        extract_unit(in, k, [&](uint64_t kmer, int) { atomicAdd(&s_cnt[fn(kmer)], 1u); });
-    }
+    extract_unit(in, k, [&](uint64_t kmer, int) { atomicAdd(&s_cnt[fn(kmer)], 1u); });
     __syncthreads();
-    // reserve this CTA's slice of every non-empty bucket; the atomics of one thread are
-    // independent, so they are issued back to back and their latencies overlap
-    for (uint32_t i0 = threadIdx.x; i0 < n_buckets; i0 += 4 * blockDim.x) {
-        unsigned long long base[4];
+    // exclusive scan of the counts (bucket starts inside the stage) + global reservation
+    const uint32_t per = (n_buckets + blockDim.x - 1) / blockDim.x;
+    const uint32_t b0 = threadIdx.x * per;
+    uint32_t mine = 0;
+    for (uint32_t i = b0; i < b0 + per && i < n_buckets; i++) mine += s_cnt[i];
+    uint32_t incl = mine;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t i = i0 + q * blockDim.x;
-            const uint32_t c = i < n_buckets ? s_cnt[i] : 0u;
-            base[q] = c ? atomicAdd(&cursors[i], (unsigned long long)c) : 0ull;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t i = i0 + q * blockDim.x;
-            if (i < n_buckets) {
-                s_base[i] = base[q];
-                s_cnt[i] = 0;
-            }
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= (uint32_t)o) incl += t;
     }
+    if ((threadIdx.x & 31) == 31) s_warp_tot[threadIdx.x >> 5] = incl;
     __syncthreads();
-    // round 2: re-extract (ALU is free here) and scatter; neighbouring CTAs fill neighbouring
-    // cells of a bucket, so L2 merges the 8-byte stores into full sectors before DRAM
-#pragma unroll 1
-    for (uint32_t r = 0; r < kBucketUnits; r++) {
-        const uint64_t u = u_begin + ((uint64_t)blockIdx.x * kBucketUnits + r) * blockDim.x + threadIdx.x;
-        const UnitInput in = load_unit(codes, breaks, u, u_end);
-        extract_unit(in, k, [&](uint64_t kmer, int) {
-            const uint32_t b = fn(kmer);
-            const uint32_t rk = atomicAdd(&s_cnt[b], 1u);
-            out[s_base[b] + rk] = kmer;
-        });
+    uint32_t warp_off = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) warp_off += s_warp_tot[w];
+    uint32_t run = warp_off + incl - mine;
+    for (uint32_t i = b0; i < b0 + per && i < n_buckets; i++) {
+        const uint32_t c = s_cnt[i];
+        s_start[i] = run;
+        s_gbase[i] = c ? atomicAdd(&cursors[i], (unsigned long long)c) : 0ull;
+        s_cnt[i] = 0;
+        run += c;
+    }
+    if (threadIdx.x == blockDim.x - 1) s_start[n_buckets] = run;  // (only used for the total)
+    __syncthreads();
+    uint32_t total = 0;
+    for (uint32_t w = 0; w < kScatterThreads / 32; w++) total += s_warp_tot[w];
+    // round 2: re-extract (ALU is free here) and place every k-mer at its bucket-ordered stage slot
+    extract_unit(in, k, [&](uint64_t kmer, int) {
+        const uint32_t b = fn(kmer);
+        const uint32_t rk = atomicAdd(&s_cnt[b], 1u);
+        stage[s_start[b] + rk] = kmer;
+    });
+    __syncthreads();
+    // copy-out: stage position p belongs to bucket fn(kmer); its cell is gbase[b] + (p - start[b])
+    for (uint32_t p = threadIdx.x; p < total; p += blockDim.x) {
+        const unsigned long long kmer = stage[p];
+        const uint32_t b = fn(kmer);
+        out[s_gbase[b] + (p - s_start[b])] = kmer;
     }
 }
 
