@@ -161,7 +161,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -370,7 +370,7 @@ def run_ours(args):
                           "api": "skm_ingest_batch(pinned host buffers) x10 -> skm_finalize -> skm_histogram"}
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        emit(out)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -389,7 +389,26 @@ def _as_tensor(ptr, n, dev):
     return torch.as_tensor(_CudaArray(ptr, n), device=dev)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries (NCCL's version banner, torchrun notices) print to stdout; keep fd 1 clean for the
+    # single JSON line by pointing it at stderr until the result is ready.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

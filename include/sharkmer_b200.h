@@ -58,7 +58,7 @@ typedef struct skm_params {
     uint64_t capacity_hint;  /* expected distinct k-mers owned by this ctx; 0 => grow on demand */
     int32_t device;          /* CUDA ordinal; -1 => current device */
     uint32_t n_ranks;        /* table partitions (GPUs); 0/1 => single GPU */
-    uint32_t rank;           /* this ctx owns k-mers with skm_owner_rank(hash, n_ranks) == rank */
+    uint32_t rank;           /* this ctx owns k-mers with skm_owner_rank(hash, n_ranks) == rank (a contiguous hash range) */
     uint32_t reserved;
     uint64_t stream;         /* cudaStream_t to run on (e.g. a torch stream's handle); 0 => ctx creates one */
 } skm_params;
@@ -161,15 +161,23 @@ int32_t skm_insert_counts(skm_ctx *ctx, const uint64_t *keys, const uint32_t *co
 /* ---- multi-GPU building blocks (one ctx per GPU; the collective between the
  * two calls is the caller's: torch.distributed / NCCL all-to-all) ----------- */
 
-/* Routing of chunk `chunk_index`'s staged reads on this GPU, in two calls so the caller can
- * size (and double-buffer) the send buffer:
- *   skm_route_count   extracts the canonical k-mers and counts them per owner rank
- *                     (send_counts[r], r < n_ranks); synchronous.
- *   skm_route_scatter writes them into d_out (device memory, sum(send_counts) entries)
- *                     grouped by destination rank, and drops the chunk's staged reads;
- *                     asynchronous on the ctx's stream. */
-int32_t skm_route_count(skm_ctx *ctx, uint32_t chunk_index, uint64_t *send_counts /* n_ranks */);
+/* Routing of chunk `chunk_index`'s staged reads on this GPU.  K-mers are bucketed by
+ * (owner rank, table region of that owner): bucket b = owner * R + region, R = regions per rank
+ * (skm_route_regions), owner = floor(hash * n_ranks / 2^64) (skm_common.h).  Buckets of one owner
+ * are contiguous, so the all-to-all sends contiguous ranges, and every received run is already
+ * ordered by the receiver's table regions.
+ *   skm_route_count   extracts the canonical k-mers and counts them per bucket
+ *                     (bucket_counts[n_ranks * R]); synchronous.
+ *   skm_route_scatter writes them into d_out (device memory, sum(bucket_counts) entries) in bucket
+ *                     order and drops the chunk's staged reads; asynchronous on the ctx's stream. */
+int32_t skm_route_regions(skm_ctx *ctx, uint32_t *regions_per_rank);
+int32_t skm_route_count(skm_ctx *ctx, uint32_t chunk_index, uint64_t *bucket_counts /* n_ranks * R */);
 int32_t skm_route_scatter(skm_ctx *ctx, uint32_t chunk_index, uint64_t *d_out);
+/* Insert what the all-to-all delivered: d_kmers holds n_src blocks (one per source rank, in rank
+ * order), block s = `regions` runs with lengths run_counts[s * regions + r].  Runs are inserted
+ * region by region across all sources (L2-resident table regions); asynchronous on the stream. */
+int32_t skm_insert_runs_device(skm_ctx *ctx, const uint64_t *d_kmers, const uint64_t *run_counts,
+                               uint32_t n_src, uint32_t regions);
 /* Insert `n` k-mers (device memory) that this rank owns; asynchronous on the ctx's stream. */
 int32_t skm_insert_kmers_device(skm_ctx *ctx, const uint64_t *d_kmers, uint64_t n);
 /* Snapshot this rank's partial histogram of its table partition as column

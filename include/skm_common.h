@@ -33,16 +33,32 @@ SKM_HD uint64_t skm_mix64(uint64_t x) {
     return x;
 }
 
-/* The table hash.  Home slot = top log2(capacity) bits; owner rank (multi-GPU)
- * = low 32 bits mod n_ranks, so the two are independent. */
+/* The table hash. */
 SKM_HD uint64_t skm_hash_kmer(uint64_t kmer) { return skm_mix64(kmer); }
 
-SKM_HD uint64_t skm_home_slot(uint64_t h, uint32_t log2_capacity) {
-    return log2_capacity ? (h >> (64u - log2_capacity)) : 0ull;
+SKM_HD uint64_t skm_mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
+#endif
 }
 
+/* Multi-GPU: the hash space [0, 2^64) is cut into n_ranks contiguous ranges.
+ *   owner rank  = floor(h * n_ranks / 2^64)
+ *   local hash  = position inside the owner's range rescaled to 64 bits
+ *               = low 64 bits of h * n_ranks
+ * so a list ordered by hash is ordered by (owner, local hash): one bucketing
+ * pass on the sender yields, for every owner, runs already sorted by that
+ * owner's table regions.  With n_ranks == 1: owner 0, local hash == h. */
 SKM_HD uint32_t skm_owner_rank(uint64_t h, uint32_t n_ranks) {
-    return (uint32_t)(h & 0xFFFFFFFFull) % n_ranks;
+    return (uint32_t)skm_mulhi64(h, (uint64_t)n_ranks);
+}
+SKM_HD uint64_t skm_local_hash(uint64_t h, uint32_t n_ranks) { return h * (uint64_t)n_ranks; }
+
+/* Home slot in a table of 2^log2_capacity slots = top bits of the local hash. */
+SKM_HD uint64_t skm_home_slot(uint64_t local_hash, uint32_t log2_capacity) {
+    return log2_capacity ? (local_hash >> (64u - log2_capacity)) : 0ull;
 }
 
 /* Order-independent digest of one (kmer, count) pair; a table digest is the

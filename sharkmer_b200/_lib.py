@@ -65,9 +65,11 @@ SYMBOLS = {
     "skm_table_digest": (_i32, [_vp, C.POINTER(_u64)]),
     "skm_lookup_batch": (_i32, [_vp, _vp, _u64, _u32, _i32, _vp, _vp]),
     "skm_insert_counts": (_i32, [_vp, _vp, _vp, _u64]),
+    "skm_route_regions": (_i32, [_vp, C.POINTER(_u32)]),
     "skm_route_count": (_i32, [_vp, _u32, _vp]),
     "skm_route_scatter": (_i32, [_vp, _u32, _vp]),
     "skm_insert_kmers_device": (_i32, [_vp, _vp, _u64]),
+    "skm_insert_runs_device": (_i32, [_vp, _vp, _vp, _u32, _u32]),
     "skm_snapshot_histogram": (_i32, [_vp, _u32]),
     "skm_finalize_external": (_i32, [_vp]),
     "skm_extract_kmers": (_i32, [_vp, _u8p, _u64, _vp]),

@@ -18,12 +18,24 @@ def hash_kmer(kmer: int) -> int:
     return mix64(kmer)
 
 
-def home_slot(h: int, log2_capacity: int) -> int:
-    return (h >> (64 - log2_capacity)) if log2_capacity else 0
-
-
 def owner_rank(h: int, n_ranks: int) -> int:
-    return (h & 0xFFFFFFFF) % n_ranks
+    """floor(h * n_ranks / 2^64): contiguous hash ranges per rank."""
+    return (h * n_ranks) >> 64
+
+
+def local_hash(h: int, n_ranks: int) -> int:
+    return (h * n_ranks) & M64
+
+
+def home_slot(local_h: int, log2_capacity: int) -> int:
+    return (local_h >> (64 - log2_capacity)) if log2_capacity else 0
+
+
+def route_bucket(kmer: int, n_ranks: int, log2_regions: int) -> int:
+    """Bucket of the routing / partition pass: owner rank, then the top bits of the local hash."""
+    h = hash_kmer(kmer)
+    o, lh = owner_rank(h, n_ranks), local_hash(h, n_ranks)
+    return (o << log2_regions) | (lh >> (64 - log2_regions) if log2_regions else 0)
 
 
 def pair_digest(kmer: int, count: int) -> int:

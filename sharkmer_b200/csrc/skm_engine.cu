@@ -30,6 +30,8 @@ constexpr double kTargetLoad = 0.60;    // load at capacity_hint
 constexpr uint64_t kMinTile = 1ull << 22;  // k-mers; smallest tile worth a launch near the limit
 constexpr uint32_t kMinLog2Cap = 16;
 constexpr uint32_t kMaxBuckets = 1024;  // scatter stages a CTA's k-mers in bucket order: runs stay >= 12 k-mers
+constexpr uint32_t kMaxRuns = 4096;     // runs per insert launch
+constexpr uint32_t kDescRing = 4;
 constexpr uint64_t kMaxListKmers = 1ull << 30;  // k-mer list budget per partition pass (8 GiB)
 
 enum Stage { ST_H2D, ST_PACK, ST_COUNT, ST_PART, ST_INSERT, ST_HISTO, ST_GROW, ST_FINALIZE, ST_N };
@@ -39,6 +41,10 @@ struct Segment {
     uint32_t *breaks = nullptr;
     uint64_t n_units = 0;
     uint64_t n_bytes = 0;
+    // eager partition (single GPU): the segment's k-mers, already ordered by table region
+    unsigned long long *list = nullptr;
+    uint64_t *h_offsets = nullptr;  // pinned, n_buckets + 1 entries (valid after a stream sync)
+    uint32_t n_buckets = 0;
 };
 
 struct ChunkState {
@@ -91,6 +97,18 @@ struct skm_ctx {
     uint64_t pos_base = 0;  // running byte position for error reports
     bool finalized = false;
     bool sticky_error = false;
+
+    // pinned arena for the per-segment bucket offsets
+    std::vector<uint64_t *> off_blocks;
+    size_t off_used = 0;  // entries used in the last block
+    bool eager = true;    // SKM_EAGER=0 disables partitioning at ingest time
+    size_t mem_budget = 0, list_bytes = 0;
+    cudaEvent_t ev_alloc = nullptr, ev_copy = nullptr;
+
+    // run descriptors (pinned ring + device copy)
+    RunDesc *h_desc = nullptr, *d_desc = nullptr;
+    cudaEvent_t desc_event[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t desc_next = 0;
 
     // routing / partition scratch
     unsigned long long *d_bucket_counts = nullptr, *d_bucket_offsets = nullptr, *d_bucket_cursors = nullptr;
@@ -183,6 +201,8 @@ void collect_spans(skm_ctx *c) {
     c->spans.clear();
 }
 
+TableRef tref(const skm_ctx *c) { return TableRef{c->table, c->log2cap, c->n_ranks}; }
+
 uint32_t ceil_log2(uint64_t v) {
     uint32_t l = 0;
     while ((1ull << l) < v) l++;
@@ -215,7 +235,8 @@ int32_t grow_table(skm_ctx *c, uint32_t new_log2cap) {
     Slot *nt = nullptr;
     int32_t rc = alloc_table(c, new_log2cap, &nt);
     if (rc) return rc;
-    rehash_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity, nt, new_log2cap);
+    rehash_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity,
+                                                          TableRef{nt, new_log2cap, c->n_ranks});
     c->launches++;
     c->stage_launches[ST_GROW]++;
     CU(cudaGetLastError());
@@ -275,7 +296,7 @@ int32_t insert_segment_direct(skm_ctx *c, const Segment &sg, uint32_t chunk) {
             Span sp(c, ST_INSERT, c->stream);
 #define SKM_LAUNCH_EI(D, H)                                                                              \
     extract_insert_kernel<D, H><<<grid_for(tile_units, 256), 256, 0, c->stream>>>(                      \
-        sg.codes, sg.breaks, u, u + tile_units, c->p.k, c->table, c->log2cap, &c->d_cc[chunk], c->d_gc, \
+        sg.codes, sg.breaks, u, u + tile_units, c->p.k, tref(c), &c->d_cc[chunk], c->d_gc,              \
         c->d_hist, c->p.histo_max)
             const bool h = c->track_histo;
             switch (c->pipe_depth) {
@@ -296,12 +317,18 @@ int32_t insert_segment_direct(skm_ctx *c, const Segment &sg, uint32_t chunk) {
     return SKM_OK;
 }
 
+// regions per owner used by the router: the largest power of two with n_ranks * regions <= kMaxBuckets
+uint32_t route_log2_regions(const skm_ctx *c) {
+    uint32_t l = 0;
+    while (((uint64_t)c->n_ranks << (l + 1)) <= kMaxBuckets) l++;
+    return l;
+}
+
 uint32_t partition_log2_buckets(const skm_ctx *c) {
     // regions of <= 2^region_log2 slots (default 2^17 = 2 MiB), at most kMaxBuckets
     int l = (int)c->log2cap - c->region_log2;
     if (l < 0) l = 0;
-    uint32_t maxl = ceil_log2(kMaxBuckets);
-    return std::min<uint32_t>((uint32_t)l, maxl);
+    return std::min<uint32_t>((uint32_t)l, route_log2_regions(c));
 }
 
 // Pass 1 of bucketing segments [s0, s1) of a chunk: per-bucket counts + offsets/cursors on the
@@ -314,7 +341,7 @@ int32_t bucket_count(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn 
         Span sp(c, ST_COUNT, c->stream);
         for (size_t s = s0; s < s1; s++) {
             const Segment &sg = cs.segs[s];
-            if (!sg.n_units) continue;
+            if (!sg.n_units || !sg.codes) continue;
             bucket_count_kernel<<<grid_for(sg.n_units, 256 * kBucketUnits), 256, n_buckets * sizeof(uint32_t), c->stream>>>(
                 sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_counts,
                 &c->d_cc[chunk]);
@@ -346,7 +373,7 @@ int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketF
     const size_t smem = scatter_smem_bytes(n_buckets);
     for (size_t s = s0; s < s1; s++) {
         const Segment &sg = cs.segs[s];
-        if (!sg.n_units) continue;
+        if (!sg.n_units || !sg.codes) continue;
         bucket_scatter_kernel<<<grid_for(sg.n_units, kScatterThreads), kScatterThreads, smem, c->stream>>>(
             sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, d_out);
         c->launches++;
@@ -356,6 +383,25 @@ int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketF
     return SKM_OK;
 }
 
+#define SKM_LAUNCH_RUNS(D, H)                                                                     \
+    insert_runs_kernel<D, H><<<grid, 256, 0, c->stream>>>(descs, n_desc, single, n_dev, tref(c), c->d_gc, \
+                                                          c->d_hist, c->p.histo_max)
+void launch_insert_runs(skm_ctx *c, uint32_t grid, const RunDesc *descs, uint32_t n_desc, RunDesc single,
+                        const unsigned long long *n_dev) {
+    const bool h = c->track_histo;
+    switch (c->pipe_depth) {
+    case 2: if (h) SKM_LAUNCH_RUNS(2, true); else SKM_LAUNCH_RUNS(2, false); break;
+    case 4: if (h) SKM_LAUNCH_RUNS(4, true); else SKM_LAUNCH_RUNS(4, false); break;
+    case 8: if (h) SKM_LAUNCH_RUNS(8, true); else SKM_LAUNCH_RUNS(8, false); break;
+    default: if (h) SKM_LAUNCH_RUNS(1, true); else SKM_LAUNCH_RUNS(1, false); break;
+    }
+    c->launches++;
+    c->stage_launches[ST_INSERT]++;
+}
+#undef SKM_LAUNCH_RUNS
+
+// Insert one flat list (optionally with counts).  n_dev: exact length in device memory (then n
+// is an upper bound and the whole list goes in one launch).
 int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_t *d_counts, uint64_t n,
                     const unsigned long long *n_dev = nullptr) {
     uint64_t i = 0;
@@ -366,27 +412,74 @@ int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_
         granted = std::max<uint64_t>(std::min(granted, n - i), 1);
         {
             Span sp(c, ST_INSERT, c->stream);
-            const uint32_t grid = grid_for(granted, kListTile);
-#define SKM_LAUNCH_IL(D, H)                                                                          \
-    insert_list_kernel<D, H><<<grid, 256, 0, c->stream>>>(d_kmers + i, d_counts ? d_counts + i : nullptr, \
-                                                          granted, (i == 0 && granted == n) ? n_dev : nullptr,   \
-                                                          c->table, c->log2cap, c->d_gc, c->d_hist,           \
-                                                          c->p.histo_max)
-            const bool h = c->track_histo;
-            switch (c->pipe_depth) {
-            case 1: if (h) SKM_LAUNCH_IL(1, true); else SKM_LAUNCH_IL(1, false); break;
-            case 2: if (h) SKM_LAUNCH_IL(2, true); else SKM_LAUNCH_IL(2, false); break;
-            case 8: if (h) SKM_LAUNCH_IL(8, true); else SKM_LAUNCH_IL(8, false); break;
-            default: if (h) SKM_LAUNCH_IL(4, true); else SKM_LAUNCH_IL(4, false); break;
-            }
-#undef SKM_LAUNCH_IL
-            c->launches++;
-            c->stage_launches[ST_INSERT]++;
+            RunDesc single{d_kmers + i, d_counts ? d_counts + i : nullptr, granted, 0};
+            launch_insert_runs(c, grid_for(granted, kListTile), nullptr, 0, single,
+                               (i == 0 && granted == n) ? n_dev : nullptr);
             c->insert_kmers += granted;
         }
         CU(cudaGetLastError());
         c->distinct_ub += granted;
         i += granted;
+    }
+    return SKM_OK;
+}
+
+// Launch one kernel over runs [i, j) (tile_begin is filled in here).
+int32_t launch_run_range(skm_ctx *c, std::vector<RunDesc> &runs, size_t i, size_t j, uint64_t total) {
+    uint64_t tiles = 0;
+    for (size_t q = i; q < j; q++) {
+        runs[q].tile_begin = tiles;
+        tiles += (runs[q].n + kListTile - 1) / kListTile;
+    }
+    if (tiles > 0x7FFFFFFFull) return fail(c, SKM_ERR_INVALID_ARG, "too many k-mers for one launch");
+    // descriptors go through a small ring of pinned buffers (the copy is asynchronous)
+    const size_t n = j - i, bytes = n * sizeof(RunDesc);
+    const uint32_t slot = c->desc_next++ % kDescRing;
+    if (c->desc_event[slot]) CU(cudaEventSynchronize(c->desc_event[slot]));
+    else CU(cudaEventCreateWithFlags(&c->desc_event[slot], cudaEventDisableTiming));
+    memcpy(c->h_desc + (size_t)slot * kMaxRuns, runs.data() + i, bytes);
+    RunDesc *d_descs = c->d_desc + (size_t)slot * kMaxRuns;
+    CU(cudaMemcpyAsync(d_descs, c->h_desc + (size_t)slot * kMaxRuns, bytes, cudaMemcpyHostToDevice, c->stream));
+    {
+        Span sp(c, ST_INSERT, c->stream);
+        launch_insert_runs(c, (uint32_t)tiles, d_descs, (uint32_t)n, RunDesc{}, nullptr);
+        c->insert_kmers += total;
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->desc_event[slot], c->stream));
+    c->distinct_ub += total;
+    return SKM_OK;
+}
+
+// Insert a sequence of runs (host-side lengths known) in the given order, in as few launches as
+// the load-factor headroom allows (normally one).
+int32_t insert_runs(skm_ctx *c, const std::vector<RunDesc> &runs_in) {
+    std::vector<RunDesc> runs;
+    uint64_t remaining = 0;
+    for (auto r : runs_in)
+        if (r.n) {
+            runs.push_back(r);
+            remaining += r.n;
+        }
+    size_t i = 0;
+    while (i < runs.size()) {
+        uint64_t granted = 0;
+        int32_t rc = reserve_headroom(c, remaining, &granted);  // may read the exact count or grow
+        if (rc) return rc;
+        size_t j = i;
+        uint64_t sum = 0;
+        while (j < runs.size() && j - i < kMaxRuns && sum + runs[j].n <= granted) sum += runs[j++].n;
+        if (j == i) {  // the next run alone exceeds the headroom: tile it
+            rc = insert_list(c, runs[i].kmers, runs[i].counts, runs[i].n);
+            if (rc) return rc;
+            remaining -= runs[i].n;
+            i++;
+            continue;
+        }
+        rc = launch_run_range(c, runs, i, j, sum);
+        if (rc) return rc;
+        remaining -= sum;
+        i = j;
     }
     return SKM_OK;
 }
@@ -400,17 +493,18 @@ int32_t insert_chunk_partitioned(skm_ctx *c, uint32_t chunk) {
         size_t s1 = s0;
         uint64_t bytes = 0;
         while (s1 < cs.segs.size() && (s1 == s0 || bytes + cs.segs[s1].n_bytes <= kMaxListKmers)) {
-            bytes += cs.segs[s1].n_bytes;
+            if (cs.segs[s1].codes) bytes += cs.segs[s1].n_bytes;
             s1++;
+        }
+        if (!bytes) {
+            s0 = s1;
+            continue;
         }
         // (the list is ordered by the top hash bits, so it stays region-ordered even if the table grows)
         int32_t rc;
         BucketFn fn;
-        fn.mode = 1;
-        fn.n_ranks = 1;
-        fn.log2cap = c->log2cap;
-        fn.log2buckets = partition_log2_buckets(c);
-        const uint32_t n_buckets = 1u << fn.log2buckets;
+        fn.n_ranks = c->n_ranks;  // (k-mers of other owners, if any, simply form their own buckets)
+        fn.log2_regions = partition_log2_buckets(c);
         // `bytes` bounds the number of k-mers of the group, so the list can be sized and the insert
         // queued without waiting for the exact count (it stays on the device, offsets[n_buckets]).
         rc = ensure_list(c, bytes);
@@ -418,10 +512,8 @@ int32_t insert_chunk_partitioned(skm_ctx *c, uint32_t chunk) {
         uint64_t granted = 0;
         rc = reserve_headroom(c, bytes, &granted);
         if (rc) return rc;
-        fn.log2cap = c->log2cap;  // reserve_headroom may have grown the table
-        fn.log2buckets = partition_log2_buckets(c);
-        const uint32_t nb2 = 1u << fn.log2buckets;
-        (void)n_buckets;
+        fn.log2_regions = partition_log2_buckets(c);  // reserve_headroom may have grown the table
+        const uint32_t nb2 = c->n_ranks << fn.log2_regions;
         if (granted >= bytes) {
             rc = bucket_count(c, chunk, s0, s1, fn, nb2, nullptr, nullptr);
             if (rc) return rc;
@@ -513,6 +605,65 @@ int32_t refresh_chunk_counters(skm_ctx *c) {
     return SKM_OK;
 }
 
+constexpr size_t kOffBlockEntries = 64 * (kMaxBuckets + 1);
+
+uint64_t *alloc_offsets(skm_ctx *c, uint32_t n) {
+    if (c->off_blocks.empty() || c->off_used + n > kOffBlockEntries) {
+        uint64_t *b = nullptr;
+        if (cudaMallocHost((void **)&b, kOffBlockEntries * sizeof(uint64_t)) != cudaSuccess) return nullptr;
+        c->off_blocks.push_back(b);
+        c->off_used = 0;
+    }
+    uint64_t *p = c->off_blocks.back() + c->off_used;
+    c->off_used += n;
+    return p;
+}
+
+bool want_partitioned(const skm_ctx *c, uint64_t n_bytes) {
+    if (c->p.insert_mode == SKM_INSERT_DIRECT) return false;
+    if (c->p.insert_mode == SKM_INSERT_PARTITIONED) return true;
+    // AUTO: partitioned wins once the table no longer fits in L2 and there is enough work to
+    // amortise the two bucketing passes (measured crossover); else direct.
+    return c->capacity * sizeof(Slot) >= (96ull << 20) && n_bytes >= (1ull << 23);
+}
+
+// Bucket a freshly packed segment by table region right away (single GPU).  The work is queued
+// behind the pack kernel on the ctx's stream, so it overlaps the next batch's host-to-device copy,
+// and skm_finalize only has the inserts left.  Costs 8 B per position of HBM instead of 0.375 B;
+// skipped when memory is short (the segment then stays packed and is bucketed at finalize).
+int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index) {
+    Segment &sg = c->chunks[chunk].segs[seg_index];
+    if (!c->eager || c->n_ranks != 1 || !want_partitioned(c, sg.n_bytes)) return SKM_OK;
+    const size_t need = sg.n_bytes * sizeof(uint64_t);
+    // budget = device memory that was free when the ctx was created; keep room for a table twice
+    // the current size plus slack (no cudaMemGetInfo here: it would serialise the ingest path)
+    if (c->list_bytes + need + 3 * c->capacity * sizeof(Slot) + (4ull << 30) > c->mem_budget) return SKM_OK;
+    BucketFn fn;
+    fn.n_ranks = 1;
+    fn.log2_regions = route_log2_regions(c);
+    const uint32_t nb = 1u << fn.log2_regions;
+    uint64_t *h_off = alloc_offsets(c, nb + 1);
+    if (!h_off) return SKM_OK;
+    if (cudaMallocAsync((void **)&sg.list, need, c->stream) != cudaSuccess) {
+        cudaGetLastError();
+        sg.list = nullptr;
+        return SKM_OK;
+    }
+    int32_t rc = bucket_count(c, chunk, seg_index, seg_index + 1, fn, nb, nullptr, nullptr);
+    if (rc) return rc;
+    rc = bucket_scatter(c, chunk, seg_index, seg_index + 1, fn, nb, sg.list);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_off, c->d_bucket_offsets, (nb + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaFreeAsync(sg.codes, c->stream));
+    CU(cudaFreeAsync(sg.breaks, c->stream));
+    sg.codes = nullptr;
+    sg.breaks = nullptr;
+    sg.h_offsets = h_off;
+    sg.n_buckets = nb;
+    c->list_bytes += need;
+    return SKM_OK;
+}
+
 // Stage one batch that is already in device memory.
 int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t n_bytes) {
     if (n_bytes == 0) return SKM_OK;
@@ -533,7 +684,7 @@ int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t
     c->pos_base += n_bytes;
     c->chunks[chunk].segs.push_back(sg);
     c->chunks[chunk].n_bytes += n_bytes;
-    return SKM_OK;
+    return eager_partition(c, chunk, c->chunks[chunk].segs.size() - 1);
 }
 
 int32_t check_ingest_args(skm_ctx *c, uint32_t chunk, const void *p, uint64_t n) {
@@ -616,6 +767,14 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     // SKM_HISTO_SCAN=1 (diagnostic) falls back to one table scan per chunk.
     c->track_histo = c->p.chunks > 0 && !getenv("SKM_HISTO_SCAN");
     if (const char *g = getenv("SKM_PIPE_DEPTH")) c->pipe_depth = atoi(g);
+    if (const char *g = getenv("SKM_EAGER")) c->eager = atoi(g) != 0;
+    {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        c->mem_budget = free_b;
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_alloc, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
     if (const char *g = getenv("SKM_REGION_LOG2")) c->region_log2 = std::max(10, std::min(30, atoi(g)));
     if (const char *g = getenv("SKM_L2_FETCH")) {  // diagnostic: 32 / 64 / 128
         cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
@@ -623,6 +782,8 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     CU(cudaMalloc((void **)&c->d_tot, sizeof(HistoTotals)));
     c->h_pinned_words = kMaxBuckets + 16;
     CU(cudaMallocHost((void **)&c->h_pinned, c->h_pinned_words * sizeof(uint64_t)));
+    CU(cudaMallocHost((void **)&c->h_desc, (size_t)kDescRing * kMaxRuns * sizeof(RunDesc)));
+    CU(cudaMalloc((void **)&c->d_desc, (size_t)kDescRing * kMaxRuns * sizeof(RunDesc)));
     CU(cudaMalloc((void **)&c->d_bucket_counts, (kMaxBuckets + 1) * sizeof(uint64_t)));
     CU(cudaMalloc((void **)&c->d_bucket_offsets, (kMaxBuckets + 1) * sizeof(uint64_t)));
     CU(cudaMalloc((void **)&c->d_bucket_cursors, (kMaxBuckets + 1) * sizeof(uint64_t)));
@@ -654,6 +815,7 @@ void skm_destroy(skm_ctx *c) {
             for (auto &sg : cs.segs) {
                 cudaFree(sg.codes);
                 cudaFree(sg.breaks);
+                cudaFree(sg.list);
             }
         cudaFree(c->table);
         cudaFree(c->d_cc);
@@ -661,6 +823,12 @@ void skm_destroy(skm_ctx *c) {
         cudaFree(c->d_bins);
         cudaFree(c->d_hist);
         cudaFree(c->d_tot);
+        for (auto b : c->off_blocks) cudaFreeHost(b);
+        if (c->ev_alloc) cudaEventDestroy(c->ev_alloc);
+        if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+        cudaFree(c->d_desc);
+        cudaFreeHost(c->h_desc);
+        for (auto e : c->desc_event) if (e) cudaEventDestroy(e);
         cudaFree(c->d_bucket_counts);
         cudaFree(c->d_bucket_offsets);
         cudaFree(c->d_bucket_cursors);
@@ -731,13 +899,18 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
         return fail(c, SKM_ERR_INVALID_ARG, "batch must end with a newline-terminated sequence line");
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
+    // The copy runs on its own stream so that it overlaps the kernels of earlier batches:
+    //   copy: alloc -> H2D -> [ev_copy]              (runs ahead of the kernels)
+    //   main:          wait [ev_copy] -> pack -> (bucket) -> free
     uint8_t *d_raw = nullptr;
-    CU(cudaMallocAsync((void **)&d_raw, n_bytes, c->stream));
+    CU(cudaMallocAsync((void **)&d_raw, n_bytes, c->copy_stream));
     {
-        Span sp(c, ST_H2D, c->stream);
-        CU(cudaMemcpyAsync(d_raw, seqs, n_bytes, cudaMemcpyHostToDevice, c->stream));
+        Span sp(c, ST_H2D, c->copy_stream);
+        CU(cudaMemcpyAsync(d_raw, seqs, n_bytes, cudaMemcpyHostToDevice, c->copy_stream));
     }
-    if (!(flags & SKM_INGEST_ASYNC)) CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventRecord(c->ev_copy, c->copy_stream));
+    if (!(flags & SKM_INGEST_ASYNC)) CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
     rc = stage_device(c, chunk, d_raw, n_bytes);
     CU(cudaFreeAsync(d_raw, c->stream));
     return rc;
@@ -814,27 +987,47 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
     cudaEventRecord(e0, c->stream);
     for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
         ChunkState &cs = c->chunks[ch];
-        uint32_t mode = c->p.insert_mode;
-        if (mode == SKM_INSERT_AUTO) {
-            // Partitioned wins once the table no longer fits in L2 and the chunk is big enough to
-            // amortise the two bucketing passes (measured crossover); else direct.
-            const bool big_table = c->capacity * sizeof(Slot) >= (96ull << 20);
-            mode = (big_table && cs.n_bytes >= (1ull << 23)) ? SKM_INSERT_PARTITIONED : SKM_INSERT_DIRECT;
+        // (1) segments bucketed at ingest time: one launch walks their runs region by region
+        {
+            uint32_t nb = 0;
+            for (auto &sg : cs.segs)
+                if (sg.list) nb = sg.n_buckets;
+            if (nb) {
+                CU(cudaStreamSynchronize(c->stream));  // the offsets were copied long ago; make them visible
+                std::vector<RunDesc> runs;
+                for (uint32_t r = 0; r < nb; r++)
+                    for (auto &sg : cs.segs)
+                        if (sg.list && sg.h_offsets[r + 1] > sg.h_offsets[r])
+                            runs.push_back(RunDesc{sg.list + sg.h_offsets[r], nullptr,
+                                                   sg.h_offsets[r + 1] - sg.h_offsets[r], 0});
+                rc = insert_runs(c, runs);
+                if (rc) return rc;
+            }
         }
-        if (mode == SKM_INSERT_PARTITIONED) {
+        // (2) segments still packed: bucket now (partitioned) or extract+insert directly
+        uint64_t packed_bytes = 0;
+        for (auto &sg : cs.segs)
+            if (sg.codes) packed_bytes += sg.n_bytes;
+        if (packed_bytes && want_partitioned(c, packed_bytes)) {
             rc = insert_chunk_partitioned(c, ch);
             if (rc) return rc;
-        } else {
+        } else if (packed_bytes) {
             for (auto &sg : cs.segs) {
+                if (!sg.codes) continue;
                 rc = insert_segment_direct(c, sg, ch);
                 if (rc) return rc;
             }
         }
         for (auto &sg : cs.segs) {  // drop(chunk), src/io.rs:1025
-            CU(cudaFreeAsync(sg.codes, c->stream));
-            CU(cudaFreeAsync(sg.breaks, c->stream));
+            if (sg.codes) CU(cudaFreeAsync(sg.codes, c->stream));
+            if (sg.breaks) CU(cudaFreeAsync(sg.breaks, c->stream));
+            if (sg.list) {
+                CU(cudaFreeAsync(sg.list, c->stream));
+                c->list_bytes -= std::min<size_t>(c->list_bytes, sg.n_bytes * sizeof(uint64_t));
+            }
             sg.codes = nullptr;
             sg.breaks = nullptr;
+            sg.list = nullptr;
         }
         cs.counted = true;
         if (c->p.chunks > 0) {
@@ -902,6 +1095,7 @@ int32_t skm_reset(skm_ctx *c) {
         for (auto &sg : cs.segs) {
             if (sg.codes) CU(cudaFreeAsync(sg.codes, c->stream));
             if (sg.breaks) CU(cudaFreeAsync(sg.breaks, c->stream));
+            if (sg.list) CU(cudaFreeAsync(sg.list, c->stream));
         }
         cs = ChunkState{};
     }
@@ -920,6 +1114,12 @@ int32_t skm_reset(skm_ctx *c) {
         c->stage_launches[i] = 0;
     }
     c->insert_kmers = c->insert_bases = 0;
+    while (c->off_blocks.size() > 1) {
+        cudaFreeHost(c->off_blocks.back());
+        c->off_blocks.pop_back();
+    }
+    c->off_used = 0;
+    c->list_bytes = 0;
     c->launches = 0;
     c->n_grows = 0;
     c->distinct_ub = 0;
@@ -1098,7 +1298,7 @@ int32_t skm_lookup_batch(skm_ctx *c, const uint64_t *kmers, uint64_t n, uint32_t
     CU(cudaMallocAsync((void **)&d_f, n, c->stream));
     CU(cudaMemcpyAsync(d_q, kmers, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     lookup_kernel<<<std::min<uint32_t>(grid_for(n, 256), c->sm_count * 8), 256, 0, c->stream>>>(
-        c->table, c->log2cap, c->p.k, d_q, n, min_count, mode, d_c, d_f);
+        tref(c), c->p.k, d_q, n, min_count, mode, d_c, d_f);
     c->launches++;
     CU(cudaGetLastError());
     if (counts) CU(cudaMemcpyAsync(counts, d_c, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -1134,24 +1334,29 @@ int32_t skm_insert_counts(skm_ctx *c, const uint64_t *keys, const uint32_t *coun
 
 // ---- multi-GPU building blocks -------------------------------------------------
 
-static BucketFn owner_fn(const skm_ctx *c) {
+static BucketFn route_fn(const skm_ctx *c) {
     BucketFn fn;
-    fn.mode = 0;
     fn.n_ranks = c->n_ranks;
-    fn.log2cap = c->log2cap;
-    fn.log2buckets = 0;
+    fn.log2_regions = route_log2_regions(c);
     return fn;
 }
 
-int32_t skm_route_count(skm_ctx *c, uint32_t chunk, uint64_t *send_counts) {
-    if (!c || !send_counts) return SKM_ERR_INVALID_ARG;
+int32_t skm_route_regions(skm_ctx *c, uint32_t *regions_per_rank) {
+    if (!c || !regions_per_rank) return SKM_ERR_INVALID_ARG;
+    *regions_per_rank = 1u << route_log2_regions(c);
+    return SKM_OK;
+}
+
+int32_t skm_route_count(skm_ctx *c, uint32_t chunk, uint64_t *bucket_counts) {
+    if (!c || !bucket_counts) return SKM_ERR_INVALID_ARG;
     if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     ChunkState &cs = c->chunks[chunk];
     if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
     uint64_t total = 0;
-    return bucket_count(c, chunk, 0, cs.segs.size(), owner_fn(c), c->n_ranks, &total, send_counts);
+    const BucketFn fn = route_fn(c);
+    return bucket_count(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions, &total, bucket_counts);
 }
 
 int32_t skm_route_scatter(skm_ctx *c, uint32_t chunk, uint64_t *d_out) {
@@ -1161,7 +1366,9 @@ int32_t skm_route_scatter(skm_ctx *c, uint32_t chunk, uint64_t *d_out) {
     DeviceGuard g(c->device);
     ChunkState &cs = c->chunks[chunk];
     if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
-    int32_t rc = bucket_scatter(c, chunk, 0, cs.segs.size(), owner_fn(c), c->n_ranks, (unsigned long long *)d_out);
+    const BucketFn fn = route_fn(c);
+    int32_t rc = bucket_scatter(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions,
+                                (unsigned long long *)d_out);
     if (rc) return rc;
     for (auto &sg : cs.segs) {
         CU(cudaFreeAsync(sg.codes, c->stream));
@@ -1171,6 +1378,28 @@ int32_t skm_route_scatter(skm_ctx *c, uint32_t chunk, uint64_t *d_out) {
     }
     cs.counted = true;
     return SKM_OK;  // asynchronous: ordered on the ctx's stream
+}
+
+int32_t skm_insert_runs_device(skm_ctx *c, const uint64_t *d_kmers, const uint64_t *run_counts, uint32_t n_src,
+                               uint32_t regions) {
+    if (!c || !run_counts || n_src == 0 || regions == 0) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    // buffer layout: source-major; insertion order: region-major, so that all sources' k-mers of one
+    // table region are inserted together while that region is L2-resident
+    std::vector<uint64_t> start((size_t)n_src * regions + 1, 0);
+    for (size_t i = 0; i < (size_t)n_src * regions; i++) start[i + 1] = start[i] + run_counts[i];
+    if (start.back() && !d_kmers) return fail(c, SKM_ERR_INVALID_ARG, "null buffer");
+    std::vector<RunDesc> runs;
+    runs.reserve((size_t)n_src * regions);
+    for (uint32_t r = 0; r < regions; r++)
+        for (uint32_t sidx = 0; sidx < n_src; sidx++) {
+            const size_t i = (size_t)sidx * regions + r;
+            if (run_counts[i])
+                runs.push_back(RunDesc{(const unsigned long long *)d_kmers + start[i], nullptr, run_counts[i], 0});
+        }
+    c->have_tot = false;
+    return insert_runs(c, runs);  // asynchronous: ordered on the ctx's stream
 }
 
 int32_t skm_insert_kmers_device(skm_ctx *c, const uint64_t *d_kmers, uint64_t n) {

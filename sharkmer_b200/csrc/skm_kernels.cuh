@@ -30,6 +30,17 @@ struct __align__(16) Slot {
     unsigned long long count;
 };
 
+// A rank's table: 2^log2cap slots addressed by the rank-local hash.
+struct TableRef {
+    Slot *slots;
+    uint32_t log2cap;
+    uint32_t n_ranks;
+    __host__ __device__ __forceinline__ uint64_t mask() const { return (1ull << log2cap) - 1; }
+    __host__ __device__ __forceinline__ uint64_t home(uint64_t kmer) const {
+        return skm_home_slot(skm_local_hash(skm_hash_kmer(kmer), n_ranks), log2cap);
+    }
+};
+
 struct ChunkCounters {          // one per chunk, device memory
     unsigned long long n_reads;   // '\n' seen by the pack kernel
     unsigned long long n_bases;   // A/C/G/T seen by the pack kernel
@@ -356,9 +367,9 @@ __device__ __forceinline__ void histo_smem_flush(const int *low, unsigned long l
 
 template <int D, bool kHisto>
 struct InsertPipe {
+    TableRef tr;
     Slot *table;
     uint64_t capmask;
-    uint32_t log2cap;
     HistoSink hs;
     unsigned long long rk[D], rs[D], rkey[D];
     uint32_t radd[D];
@@ -368,8 +379,8 @@ struct InsertPipe {
     bool o_valid = false;
     unsigned long long n_new = 0;
 
-    __device__ __forceinline__ InsertPipe(Slot *t, uint32_t l2c, const HistoSink &h)
-        : table(t), capmask((1ull << l2c) - 1), log2cap(l2c), hs(h) {}
+    __device__ __forceinline__ InsertPipe(const TableRef &t, const HistoSink &h)
+        : tr(t), table(t.slots), capmask(t.mask()), hs(h) {}
 
     // resolve the oldest probe: find/claim the slot, add the count
     __device__ __forceinline__ void finish(unsigned long long kmer, unsigned long long s,
@@ -407,7 +418,7 @@ struct InsertPipe {
         }
         valid >>= 1;
         if (have) {
-            const unsigned long long s = skm_home_slot(skm_hash_kmer(kmer), log2cap);
+            const unsigned long long s = tr.home(kmer);
             rk[D - 1] = kmer;
             rs[D - 1] = s;
             radd[D - 1] = add;
@@ -428,7 +439,7 @@ struct InsertPipe {
 template <int D, bool kHisto>
 __global__ void __launch_bounds__(256)
 extract_insert_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
-                      uint64_t u_begin, uint64_t u_end, uint32_t k, Slot *__restrict__ table, uint32_t log2cap,
+                      uint64_t u_begin, uint64_t u_end, uint32_t k, TableRef table,
                       ChunkCounters *__restrict__ cc, GlobalCounters *__restrict__ gc,
                       unsigned long long *__restrict__ g_hist, unsigned long long histo_max) {
     __shared__ int s_low[kHisto ? kLowBins * 32 : 1];
@@ -436,7 +447,7 @@ extract_insert_kernel(const uint64_t *__restrict__ codes, const uint32_t *__rest
     const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const UnitInput in = load_unit(codes, breaks, u, u_end);
     HistoSink hs{s_low, g_hist, histo_max, threadIdx.x & 31};
-    InsertPipe<D, kHisto> pipe(table, log2cap, hs);
+    InsertPipe<D, kHisto> pipe(table, hs);
     unsigned long long n_win = extract_unit(in, k, [&](uint64_t kmer, int) { pipe.push(kmer); });
     pipe.drain();
     block_add(&gc->n_distinct, pipe.n_new);
@@ -461,25 +472,48 @@ count_windows_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restr
 static constexpr uint32_t kListPerThread = 16;
 static constexpr uint32_t kListTile = 256 * kListPerThread;
 
+// One run = a contiguous list of k-mers (optionally with counts).  A launch walks a sequence of
+// runs in order; tiles never span runs.
+struct RunDesc {
+    const unsigned long long *kmers;
+    const uint32_t *counts;          // null => every k-mer counts 1
+    unsigned long long n;
+    unsigned long long tile_begin;   // first CTA index of this run
+};
+
 template <int D, bool kHisto>
 __global__ void __launch_bounds__(256)
-insert_list_kernel(const unsigned long long *__restrict__ kmers, const uint32_t *__restrict__ counts,
-                   uint64_t n, const unsigned long long *__restrict__ n_dev, Slot *__restrict__ table,
-                   uint32_t log2cap, GlobalCounters *__restrict__ gc,
-                   unsigned long long *__restrict__ g_hist, unsigned long long histo_max) {
-    // n_dev (optional): the list length lives in device memory (written by the bucketing scan),
-    // so the host can queue this launch without waiting for it; the grid covers the upper bound n.
-    if (n_dev) n = *n_dev < n ? *n_dev : n;
-    if ((uint64_t)blockIdx.x * kListTile >= n) return;
+insert_runs_kernel(const RunDesc *__restrict__ descs, uint32_t n_desc, RunDesc single,
+                   const unsigned long long *__restrict__ n_dev, TableRef table,
+                   GlobalCounters *__restrict__ gc, unsigned long long *__restrict__ g_hist,
+                   unsigned long long histo_max) {
+    RunDesc d;
+    uint64_t tile;
+    if (descs == nullptr) {
+        // single run; n_dev (optional): its length lives in device memory (written by the bucketing
+        // scan) so the host can queue this launch without waiting; the grid covers the bound single.n
+        d = single;
+        if (n_dev && *n_dev < d.n) d.n = *n_dev;
+        tile = blockIdx.x;
+    } else {
+        uint32_t lo = 0, hi = n_desc;  // last run whose tile_begin <= blockIdx.x
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (descs[mid].tile_begin <= blockIdx.x) lo = mid; else hi = mid;
+        }
+        d = descs[lo];
+        tile = blockIdx.x - d.tile_begin;
+    }
+    if (tile * kListTile >= d.n) return;
     __shared__ int s_low[kHisto ? kLowBins * 32 : 1];
     if (kHisto) histo_smem_init(s_low);
     HistoSink hs{s_low, g_hist, histo_max, threadIdx.x & 31};
-    InsertPipe<D, kHisto> pipe(table, log2cap, hs);
-    const uint64_t base = (uint64_t)blockIdx.x * kListTile + threadIdx.x;
+    InsertPipe<D, kHisto> pipe(table, hs);
+    const uint64_t base = tile * kListTile + threadIdx.x;
 #pragma unroll 4
     for (uint32_t j = 0; j < kListPerThread; j++) {
         const uint64_t i = base + (uint64_t)j * 256;
-        if (i < n) pipe.push(kmers[i], counts ? counts[i] : 1u);
+        if (i < d.n) pipe.push(d.kmers[i], d.counts ? d.counts[i] : 1u);
     }
     pipe.drain();
     block_add(&gc->n_distinct, pipe.n_new);
@@ -498,8 +532,8 @@ __global__ void __launch_bounds__(256) table_clear_kernel(Slot *__restrict__ tab
 
 // Grow: re-insert every occupied slot of the old table into the new one.
 __global__ void __launch_bounds__(256)
-rehash_kernel(const Slot *__restrict__ old_table, uint64_t old_cap, Slot *__restrict__ table,
-              uint32_t log2cap) {
+rehash_kernel(const Slot *__restrict__ old_table, uint64_t old_cap, TableRef nt) {
+    Slot *__restrict__ table = nt.slots;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < old_cap;
          i += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 v = ld_nc_v4(reinterpret_cast<const uint4 *>(old_table) + i);
@@ -507,12 +541,12 @@ rehash_kernel(const Slot *__restrict__ old_table, uint64_t old_cap, Slot *__rest
         if (key == SKM_EMPTY_KEY) continue;
         const unsigned long long cnt = ((unsigned long long)v.w << 32) | v.z;
         // keys are unique in the old table: claim the first EMPTY slot of the probe sequence
-        uint64_t sl = skm_home_slot(skm_hash_kmer(key), log2cap);
+        uint64_t sl = nt.home(key);
         for (;;) {
             if (ld_cg_u64(&table[sl].key) == SKM_EMPTY_KEY &&
                 atomicCAS(&table[sl].key, (unsigned long long)SKM_EMPTY_KEY, key) == SKM_EMPTY_KEY)
                 break;
-            sl = (sl + 1) & ((1ull << log2cap) - 1);
+            sl = (sl + 1) & nt.mask();
         }
         table[sl].count = cnt;
     }
@@ -624,11 +658,11 @@ export_kernel(const Slot *__restrict__ table, uint64_t capacity, unsigned long l
 // FilteredKmerCounts::get_canonical_count / KmerCounts::get_count / get_canonical
 // (src/kmer/counting.rs:205-222,328-342).  mode 0: probe min(kmer, revcomp);
 // mode 1: probe the k-mer as given; mode 2: probe as given, else the revcomp.
-__device__ __forceinline__ bool table_find(const Slot *__restrict__ table, uint32_t log2cap, uint64_t q,
-                                           uint32_t &count) {
+__device__ __forceinline__ bool table_find(const TableRef &tr, uint64_t q, uint32_t &count) {
     if (q == SKM_EMPTY_KEY) return false;
-    const uint64_t capmask = (1ull << log2cap) - 1;
-    uint64_t s = skm_home_slot(skm_hash_kmer(q), log2cap);
+    const Slot *__restrict__ table = tr.slots;
+    const uint64_t capmask = tr.mask();
+    uint64_t s = tr.home(q);
     for (;;) {
         const uint4 v = *(reinterpret_cast<const uint4 *>(table) + s);
         const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
@@ -643,7 +677,7 @@ __device__ __forceinline__ bool table_find(const Slot *__restrict__ table, uint3
 }
 
 __global__ void __launch_bounds__(256)
-lookup_kernel(const Slot *__restrict__ table, uint32_t log2cap, uint32_t k,
+lookup_kernel(TableRef table, uint32_t k,
               const unsigned long long *__restrict__ kmers, uint64_t n, uint32_t min_count,
               int mode, uint32_t *__restrict__ counts, uint8_t *__restrict__ found) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -653,11 +687,11 @@ lookup_kernel(const Slot *__restrict__ table, uint32_t log2cap, uint32_t k,
         uint32_t c = 0;
         bool hit;
         if (mode == 0)
-            hit = table_find(table, log2cap, q < rc ? q : rc, c);
+            hit = table_find(table, q < rc ? q : rc, c);
         else if (mode == 1)
-            hit = table_find(table, log2cap, q, c);
+            hit = table_find(table, q, c);
         else
-            hit = table_find(table, log2cap, q, c) || table_find(table, log2cap, rc, c);
+            hit = table_find(table, q, c) || table_find(table, rc, c);
         if (hit && c < min_count) {
             hit = false;
             c = 0;
@@ -669,9 +703,10 @@ lookup_kernel(const Slot *__restrict__ table, uint32_t log2cap, uint32_t k,
 }
 
 // ---------------------------------------------------------------------------
-// bucketing by hash: multi-GPU routing (bucket = owner rank) and the
-// partitioned insert (bucket = top bits of the home slot, so each bucket is a
-// contiguous table region that fits in L2).  Exact two-pass scheme:
+// bucketing by hash, one scheme for both uses: bucket = (owner rank, table region of that
+// owner) = the top bits of (owner, local hash).  On one GPU it orders a chunk's k-mers by
+// table region (partitioned insert); across GPUs the same pass groups them by destination
+// rank AND leaves every destination's run region-sorted.  Exact two-pass scheme:
 //   pass 1  per-bucket counts (shared-memory counters, one global add per
 //           non-empty bucket per CTA)
 //   scan    exclusive prefix sum over buckets (single CTA)
@@ -682,14 +717,13 @@ lookup_kernel(const Slot *__restrict__ table, uint32_t log2cap, uint32_t k,
 // ---------------------------------------------------------------------------
 
 struct BucketFn {
-    uint32_t mode;      // 0: owner rank, 1: table region
-    uint32_t n_ranks;
-    uint32_t log2cap;
-    uint32_t log2buckets;
-    __device__ __forceinline__ uint32_t operator()(uint64_t kmer) const {
+    uint32_t n_ranks;       // owners (1 on a single GPU)
+    uint32_t log2_regions;  // table regions per owner = 2^log2_regions
+    __host__ __device__ __forceinline__ uint32_t operator()(uint64_t kmer) const {
         const uint64_t h = skm_hash_kmer(kmer);
-        if (mode == 0) return skm_owner_rank(h, n_ranks);
-        return (uint32_t)(skm_home_slot(h, log2cap) >> (log2cap - log2buckets));
+        const uint32_t owner = skm_owner_rank(h, n_ranks);
+        if (log2_regions == 0) return owner;
+        return (owner << log2_regions) | (uint32_t)(skm_local_hash(h, n_ranks) >> (64u - log2_regions));
     }
 };
 

@@ -150,10 +150,22 @@ class Engine:
         self._ck(self.L.skm_insert_counts(self._h, k.ctypes.data, c.ctypes.data, k.size))
 
     # ---- multi-GPU building blocks --------------------------------------
+    def route_regions(self) -> int:
+        r = C.c_uint32()
+        self._ck(self.L.skm_route_regions(self._h, C.byref(r)))
+        return r.value
+
     def route_count(self, chunk_index: int, n_ranks: int) -> np.ndarray:
-        counts = np.zeros(n_ranks, dtype=np.uint64)
+        """Per-bucket counts, shape (n_ranks, regions_per_rank)."""
+        regions = self.route_regions()
+        counts = np.zeros((n_ranks, regions), dtype=np.uint64)
         self._ck(self.L.skm_route_count(self._h, chunk_index, counts.ctypes.data))
         return counts
+
+    def insert_runs_device(self, d_ptr: int, run_counts: np.ndarray):
+        """run_counts: shape (n_src, regions) — what each source rank sent, per table region."""
+        rc = np.ascontiguousarray(run_counts, dtype=np.uint64)
+        self._ck(self.L.skm_insert_runs_device(self._h, d_ptr, rc.ctypes.data, rc.shape[0], rc.shape[1]))
 
     def route_scatter(self, chunk_index: int, d_out: int):
         self._ck(self.L.skm_route_scatter(self._h, chunk_index, d_out))

@@ -2,10 +2,11 @@
 for the plumbing (NCCL over NVLink/NVSwitch on GPUs; gloo in the CPU tests).
 
 The path shards by k-mer hash: every rank packs and extracts the
-k-mers of ITS slice of the reads, buckets them by owner rank
-(skm_owner_rank(hash, n_ranks), include/skm_common.h), and an all-to-all delivers
-each bucket to the rank that owns that slice of the table; the owner inserts them
-with no cross-GPU atomics.  With --chunks n > 0 every chunk boundary is a global
+k-mers of ITS slice of the reads and buckets them by (owner rank, table region of that
+owner) — owner = floor(hash * N / 2^64), include/skm_common.h — so one pass both groups
+the k-mers by destination and leaves every destination's run sorted by the receiver's
+table regions.  An all-to-all delivers each rank's range; the owner inserts the runs
+region by region (L2-resident) with no cross-GPU atomics.  With --chunks n > 0 every chunk boundary is a global
 barrier: all ranks finish exchanging and inserting chunk i before histogram column i
 is taken (src/io.rs:1016-1028 merges chunks in index order).  The result is
 independent of N.
@@ -15,7 +16,7 @@ collective's stream) overlaps the insert of chunk c: send/receive buffers are
 double-buffered torch tensors.
 
 `engine` is anything with the routing interface of sharkmer_b200.kmer.Engine
-(route_count / route_scatter / insert_kmers_device / snapshot_histogram / histogram /
+(route_count / route_scatter / insert_runs_device / snapshot_histogram / histogram /
 finalize_external); the CPU tests drive this same code with a recording stand-in.
 """
 from __future__ import annotations
@@ -42,9 +43,11 @@ class ShardedCounter:
 
     # -- small helpers ---------------------------------------------------------
     def _exchange_counts(self, counts: np.ndarray) -> np.ndarray:
-        send = torch.as_tensor(counts.astype(np.int64), device=self.device)
+        """counts[d, r] = k-mers this rank sends to rank d for d's table region r.
+        Returns recv[s, r] = k-mers rank s sends to this rank for our region r."""
+        send = torch.as_tensor(np.ascontiguousarray(counts).astype(np.int64), device=self.device)
         recv = torch.empty_like(send)
-        dist.all_to_all_single(recv, send, group=self.group)
+        dist.all_to_all_single(recv, send, group=self.group)  # row d goes to rank d
         return recv.cpu().numpy()
 
     def _alloc(self, n: int) -> torch.Tensor:
@@ -74,26 +77,27 @@ class ShardedCounter:
         e.finalize_external()  # ingest is complete on every rank; the chunk loop is ours
 
         def launch_exchange(c):
-            counts = e.route_count(c, self.world)            # per-owner counts of this rank's k-mers
-            rcounts = self._exchange_counts(counts)          # how many each rank sends us
-            n_send, n_recv = int(counts.sum()), int(rcounts.sum())
+            counts = e.route_count(c, self.world)            # (world, regions): per destination and region
+            rcounts = self._exchange_counts(counts)          # (world, regions): per source and region
+            per_dst, per_src = counts.sum(axis=1), rcounts.sum(axis=1)
+            n_send, n_recv = int(per_dst.sum()), int(per_src.sum())
             send, recv = self._alloc(n_send), self._alloc(n_recv)
-            e.route_scatter(c, self._ptr(send))              # k-mers grouped by destination (engine stream)
+            e.route_scatter(c, self._ptr(send))              # bucket order = destination-major (engine stream)
             work = dist.all_to_all_single(recv[:n_recv], send[:n_send],
-                                          output_split_sizes=[int(x) for x in rcounts],
-                                          input_split_sizes=[int(x) for x in counts],
+                                          output_split_sizes=[int(x) for x in per_src],
+                                          input_split_sizes=[int(x) for x in per_dst],
                                           group=self.group, async_op=True)
-            self.bytes_sent += 8 * (n_send - int(counts[self.rank]))
+            self.bytes_sent += 8 * (n_send - int(per_dst[self.rank]))
             self.kmers_received += n_recv
-            return work, send, recv, n_recv, c
+            return work, send, recv, rcounts, c
 
         pending = launch_exchange(0)
         for c in range(self.n_chunks):
-            work, send, recv, n_recv, cc = pending
+            work, send, recv, rcounts, cc = pending
             # start routing the next chunk while this chunk's k-mers are in flight
             nxt = launch_exchange(c + 1) if c + 1 < self.n_chunks else None
             work.wait()                                       # engine stream waits for the collective
-            e.insert_kmers_device(self._ptr(recv), n_recv)
+            e.insert_runs_device(self._ptr(recv), rcounts)   # region-major over all sources' runs
             if self.chunks_arg > 0:
                 e.snapshot_histogram(cc)                      # this rank's partial column (syncs the stream)
             else:

@@ -417,8 +417,9 @@ def test_sharded_two_partitions_single_process(skm, oracle):
         engs[r].ingest_batch(c, reads[b * 1000 * line:(b + 1) * 1000 * line])
     for e in engs:
         e.finalize_external()
+    regions = engs[0].route_regions()
     for c in range(chunks):
-        counts = [e.route_count(c, world) for e in engs]
+        counts = [e.route_count(c, world) for e in engs]          # each (world, regions)
         sends = []
         for e, cnt in zip(engs, counts):
             t = torch.empty(max(int(cnt.sum()), 1), dtype=torch.int64, device="cuda")
@@ -426,12 +427,14 @@ def test_sharded_two_partitions_single_process(skm, oracle):
             e.sync()
             sends.append(t)
         for dst in range(world):
-            parts = []
+            parts, rc = [], np.zeros((world, regions), dtype=np.uint64)
             for src in range(world):
                 off = int(counts[src][:dst].sum())
-                parts.append(sends[src][off:off + int(counts[src][dst])])
+                n = int(counts[src][dst].sum())
+                parts.append(sends[src][off:off + n])
+                rc[src] = counts[src][dst]
             recv = torch.cat(parts).contiguous()
-            engs[dst].insert_kmers_device(recv.data_ptr(), recv.numel())
+            engs[dst].insert_runs_device(recv.data_ptr(), rc)
             engs[dst].snapshot_histogram(c)
         col = sum(e.histogram(c).astype(np.int64) for e in engs)
         assert (col == run.histogram(c).astype(np.int64)).all(), c

@@ -1,7 +1,7 @@
 """The N>1 path on CPU: world_size-2 `gloo` run of sharkmer_b200.multigpu.ShardedCounter
 (the driver code the GPU bench uses) with a TEST-ONLY stand-in for the per-GPU engine that
-gets its k-mers from the oracle.  Checks the routing rule (owner = low 32 hash bits mod N),
-the split sizes, the per-chunk barrier order and the histogram all-reduce: the merged result
+gets its k-mers from the oracle.  Checks the routing rule (owner = floor(hash * N / 2^64),
+buckets = (owner, region)), the split sizes, the per-chunk barrier order and the histogram all-reduce: the merged result
 must equal the single-process oracle, independent of N."""
 import os
 import socket
@@ -20,8 +20,8 @@ K, CHUNKS, HMAX, L, NREADS = 21, 4, 50, 100, 9000
 class FakeEngine:
     """Routing interface of kmer.Engine over host memory; counting by a dict."""
 
-    def __init__(self, oracle, common, reads_by_chunk, world):
-        self.o, self.common, self.world = oracle, common, world
+    def __init__(self, oracle, common, reads_by_chunk, world, rank):
+        self.o, self.common, self.world, self.rank = oracle, common, world, rank
         self.reads = reads_by_chunk
         self.table = {}
         self.cols = {}
@@ -37,24 +37,39 @@ class FakeEngine:
             out.extend(self.o.kmers_from_ascii(s, K))
         return np.array(out, dtype=np.uint64)
 
+    REGIONS = 4
+
+    def route_regions(self):
+        return self.REGIONS
+
     def route_count(self, c, world):
         km = self._kmers(c)
-        owners = np.array([self.common.owner_rank(self.common.hash_kmer(int(x)), world) for x in km], dtype=np.int64)
-        order = np.argsort(owners, kind="stable")
+        log2r = self.REGIONS.bit_length() - 1
+        buckets = np.array([self.common.route_bucket(int(x), world, log2r) for x in km], dtype=np.int64)
+        order = np.argsort(buckets, kind="stable")
         self.routed[c] = km[order]
-        return np.bincount(owners, minlength=world).astype(np.uint64)
+        return np.bincount(buckets, minlength=world * self.REGIONS).astype(np.uint64).reshape(world, self.REGIONS)
 
     def route_scatter(self, c, ptr):
         km = self.routed.pop(c)
         dst = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_int64 * max(len(km), 1)).from_address(ptr))
         dst[:len(km)] = km.view(np.int64)
 
-    def insert_kmers_device(self, ptr, n):
+    def insert_runs_device(self, ptr, run_counts):
+        n = int(run_counts.sum())
+        assert run_counts.shape == (self.world, self.REGIONS)
         if n == 0:
             return
         a = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_int64 * n).from_address(ptr)).view(np.uint64)
-        for x in a.tolist():
-            self.table[x] = self.table.get(x, 0) + 1
+        # every run must hold k-mers of exactly that (this rank, region) bucket
+        log2r = self.REGIONS.bit_length() - 1
+        pos = 0
+        for s in range(self.world):
+            for r in range(self.REGIONS):
+                for x in a[pos:pos + int(run_counts[s, r])].tolist():
+                    assert self.common.route_bucket(x, self.world, log2r) == self.rank * self.REGIONS + r
+                    self.table[x] = self.table.get(x, 0) + 1
+                pos += int(run_counts[s, r])
 
     def snapshot_histogram(self, c):
         v = np.zeros(HMAX + 2, dtype=np.uint64)
@@ -83,7 +98,7 @@ def worker(rank, world, port, q):
         for b in batches[lo:hi]:
             mine.extend(reads[b * 1000:(b + 1) * 1000])
         by_chunk.append(mine)
-    eng = FakeEngine(o, common, by_chunk, world)
+    eng = FakeEngine(o, common, by_chunk, world, rank)
     sc = ShardedCounter(eng, CHUNKS, CHUNKS, HMAX, torch.device("cpu"))
     cols = sc.finalize()
     # every key this rank holds must be one it owns
