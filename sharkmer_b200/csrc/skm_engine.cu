@@ -104,6 +104,11 @@ struct skm_ctx {
     bool eager = true;    // SKM_EAGER=0 disables partitioning at ingest time
     size_t mem_budget = 0, list_bytes = 0;
     cudaEvent_t ev_alloc = nullptr, ev_copy = nullptr;
+    // ring of raw (ASCII) device buffers for host batches: the copy stream may run kRawRing-1 batches ahead
+    uint8_t *raw_buf[3] = {nullptr, nullptr, nullptr};
+    size_t raw_cap[3] = {0, 0, 0};
+    cudaEvent_t raw_copied[3] = {nullptr, nullptr, nullptr}, raw_packed[3] = {nullptr, nullptr, nullptr};
+    uint32_t raw_next = 0;
 
     // run descriptors (pinned ring + device copy)
     RunDesc *h_desc = nullptr, *d_desc = nullptr;
@@ -665,7 +670,8 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index) {
 }
 
 // Stage one batch that is already in device memory.
-int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t n_bytes) {
+int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t n_bytes,
+                     cudaEvent_t packed_event = nullptr) {
     if (n_bytes == 0) return SKM_OK;
     Segment sg;
     sg.n_bytes = n_bytes;
@@ -681,6 +687,7 @@ int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t
         c->stage_launches[ST_PACK]++;
     }
     CU(cudaGetLastError());
+    if (packed_event) CU(cudaEventRecord(packed_event, c->stream));  // the raw buffer may be overwritten now
     c->pos_base += n_bytes;
     c->chunks[chunk].segs.push_back(sg);
     c->chunks[chunk].n_bytes += n_bytes;
@@ -823,6 +830,11 @@ void skm_destroy(skm_ctx *c) {
         cudaFree(c->d_bins);
         cudaFree(c->d_hist);
         cudaFree(c->d_tot);
+        for (int i = 0; i < 3; i++) {
+            cudaFree(c->raw_buf[i]);
+            if (c->raw_copied[i]) cudaEventDestroy(c->raw_copied[i]);
+            if (c->raw_packed[i]) cudaEventDestroy(c->raw_packed[i]);
+        }
         for (auto b : c->off_blocks) cudaFreeHost(b);
         if (c->ev_alloc) cudaEventDestroy(c->ev_alloc);
         if (c->ev_copy) cudaEventDestroy(c->ev_copy);
@@ -899,20 +911,36 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
         return fail(c, SKM_ERR_INVALID_ARG, "batch must end with a newline-terminated sequence line");
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    // The copy runs on its own stream so that it overlaps the kernels of earlier batches:
-    //   copy: alloc -> H2D -> [ev_copy]              (runs ahead of the kernels)
-    //   main:          wait [ev_copy] -> pack -> (bucket) -> free
-    uint8_t *d_raw = nullptr;
-    CU(cudaMallocAsync((void **)&d_raw, n_bytes, c->copy_stream));
+    // The copy runs on its own stream, into a ring of persistent raw buffers, so that it overlaps
+    // the kernels of earlier batches (a buffer is reused once its pack kernel has finished):
+    //   copy: wait [packed(b)] -> H2D -> [copied(b)]
+    //   main:                    wait [copied(b)] -> pack -> [packed(b)] -> (bucket)
+    const uint32_t b = c->raw_next++ % 3;
+    if (!c->raw_copied[b]) {
+        CU(cudaEventCreateWithFlags(&c->raw_copied[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->raw_packed[b], cudaEventDisableTiming));
+    }
+    if (c->raw_cap[b] < n_bytes) {
+        if (c->raw_buf[b]) {
+            CU(cudaEventSynchronize(c->raw_packed[b]));
+            CU(cudaFree(c->raw_buf[b]));
+            c->raw_buf[b] = nullptr;
+            c->raw_cap[b] = 0;
+        }
+        const size_t cap = std::max<size_t>(n_bytes, 1 << 20);
+        CU(cudaMalloc((void **)&c->raw_buf[b], cap));
+        c->raw_cap[b] = cap;
+    } else {
+        CU(cudaStreamWaitEvent(c->copy_stream, c->raw_packed[b], 0));
+    }
     {
         Span sp(c, ST_H2D, c->copy_stream);
-        CU(cudaMemcpyAsync(d_raw, seqs, n_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaMemcpyAsync(c->raw_buf[b], seqs, n_bytes, cudaMemcpyHostToDevice, c->copy_stream));
     }
-    CU(cudaEventRecord(c->ev_copy, c->copy_stream));
+    CU(cudaEventRecord(c->raw_copied[b], c->copy_stream));
     if (!(flags & SKM_INGEST_ASYNC)) CU(cudaStreamSynchronize(c->copy_stream));
-    CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
-    rc = stage_device(c, chunk, d_raw, n_bytes);
-    CU(cudaFreeAsync(d_raw, c->stream));
+    CU(cudaStreamWaitEvent(c->stream, c->raw_copied[b], 0));
+    rc = stage_device(c, chunk, c->raw_buf[b], n_bytes, c->raw_packed[b]);
     return rc;
 }
 
