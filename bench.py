@@ -171,7 +171,8 @@ def workload_config(n_gpus):
             "k": K, "chunks": CHUNKS, "reads": READS_PER_GPU * n_gpus, "read_len": READ_LEN,
             "genome_len": GENOME_PER_GPU * n_gpus, "histo_max": HISTO_MAX,
             "l2": "inputs (1.5 GB/GPU) and table (8.6 GB/GPU) exceed L2; no flush needed",
-            "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs: reads split, table sharded by k-mer hash, NCCL all-to-all"}
+            "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs: reads split, table sharded by k-mer hash range, "
+                           "k-mers routed over NVLink (fused peer-store scatter, or NCCL all-to-all with --exchange nccl)"}
 
 
 # ----------------------------------------------------------------------------
@@ -237,7 +238,10 @@ def run_ours(args):
     sharded = None
     if world > 1:
         from sharkmer_b200.multigpu import ShardedCounter
-        sharded = ShardedCounter(eng, CHUNKS, CHUNKS, HISTO_MAX, dev, stream=stream)
+        # receive arena per slot: this rank's share of a chunk's k-mers (+30 % for imbalance)
+        arena = int(1.3 * max(t.numel() for t in d_bufs)) + (1 << 20)
+        sharded = ShardedCounter(eng, CHUNKS, CHUNKS, HISTO_MAX, dev, stream=stream,
+                                 exchange=args.exchange, arena_entries=arena)
 
     def step(host_buffers: bool):
         eng.reset()
@@ -343,7 +347,7 @@ def run_ours(args):
                          "histogram": stt.histogram, "grow": stt.grow, "finalize": stt.total_finalize},
             "table": {"slots": int(stt.table_capacity), "bytes": int(stt.table_bytes),
                       "load": float(tot.n_unique) / float(stt.table_capacity), "grows": int(stt.n_grows)},
-            "roofline": {"bound": "hbm", "kernel": "extract_insert_kernel" if stt.insert_bases else "insert_sorted_list_kernel",
+            "roofline": {"bound": "hbm", "kernel": "extract_insert_kernel" if stt.insert_bases else "insert_runs_kernel",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "launches_per_step": int(n_ins), "ms_per_launch": ins_ms_per_launch,
@@ -420,6 +424,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--gups", action="store_true", help="also measure the random-access roofline probe")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange: fused peer-store scatter over NVLink (p2p) or NCCL all-to-all")
     ap.add_argument("--chunks", type=int, default=None, help="EXPERIMENT ONLY: override the workload's chunk count")
     ap.add_argument("--k", type=int, default=None, help="EXPERIMENT ONLY: override k")
     args = ap.parse_args()

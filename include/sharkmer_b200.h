@@ -154,6 +154,15 @@ enum { SKM_LOOKUP_CANONICAL = 0, SKM_LOOKUP_EXACT = 1, SKM_LOOKUP_EITHER = 2 };
 int32_t skm_lookup_batch(skm_ctx *ctx, const uint64_t *kmers, uint64_t n, uint32_t min_count,
                          int32_t mode, uint32_t *counts, uint8_t *found);
 
+/* find_oligos_in_kmers (src/pcr/primers.rs:163-226), sPCR's full-table scan, as one streaming
+ * pass on the device.  `oligos`: unshifted 2-bit oligos of `oligo_length` bases (0 < len < k).
+ * A table k-mer with count >= min_count matches if it STARTS with an oligo (reported as is),
+ * else if it ENDS with the reverse complement of one (its reverse complement is reported).
+ * Output in ascending k-mer order; *n_out = number of matches (call with keys = NULL to size). */
+int32_t skm_scan_oligos(skm_ctx *ctx, const uint64_t *oligos, uint64_t n_oligos, uint32_t oligo_length,
+                        uint32_t min_count, uint64_t *keys, uint32_t *counts, uint64_t cap,
+                        uint64_t *n_out);
+
 /* KmerCounts::insert / extend (src/kmer/counting.rs:152-166): saturating add of
  * pre-counted (k-mer, count) pairs.  Allowed before or after finalize. */
 int32_t skm_insert_counts(skm_ctx *ctx, const uint64_t *keys, const uint32_t *counts, uint64_t n);
@@ -178,6 +187,27 @@ int32_t skm_route_scatter(skm_ctx *ctx, uint32_t chunk_index, uint64_t *d_out);
  * region by region across all sources (L2-resident table regions); asynchronous on the stream. */
 int32_t skm_insert_runs_device(skm_ctx *ctx, const uint64_t *d_kmers, const uint64_t *run_counts,
                                uint32_t n_src, uint32_t regions);
+/* Fused route + exchange over NVLink (n_ranks <= 16): instead of writing the bucketed k-mers to
+ * a local list that a collective then copies, the scatter kernel stores every destination's runs
+ * straight into that rank's receive arena through a CUDA-IPC mapping (peer stores, no staging).
+ *   skm_p2p_arena_create   allocates this rank's two receive arenas (double buffering)
+ *   skm_p2p_arena_handle   64-byte CUDA IPC handle of arena `slot`, to be sent to every peer
+ *   skm_p2p_open_peer      maps a peer's arena from its handle (other process, same node)
+ *   skm_p2p_set_peer       same, from a raw device pointer (peer ctx in the same process)
+ *   skm_route_scatter_p2p  after skm_route_count(chunk): writes rank d's buckets at element
+ *                          offset dst_offsets[d] of rank d's arena `slot`; asynchronous.
+ * The caller orders the steps with a stream-ordered barrier (a 1-element all-reduce): all ranks
+ * scatter(c) -> barrier -> insert(c) from their own arena (skm_insert_runs_device on
+ * skm_p2p_arena_ptr).  With two slots, a slot is rewritten only after the barrier that follows the
+ * owner's insert of its previous content. */
+int32_t skm_p2p_arena_create(skm_ctx *ctx, uint64_t entries_per_slot);
+int32_t skm_p2p_arena_handle(skm_ctx *ctx, uint32_t slot, uint8_t *handle64);
+int32_t skm_p2p_arena_ptr(skm_ctx *ctx, uint32_t slot, uint64_t **out);
+int32_t skm_p2p_open_peer(skm_ctx *ctx, uint32_t peer_rank, uint32_t slot, const uint8_t *handle64);
+int32_t skm_p2p_set_peer(skm_ctx *ctx, uint32_t peer_rank, uint32_t slot, uint64_t *d_ptr);
+int32_t skm_route_scatter_p2p(skm_ctx *ctx, uint32_t chunk_index, uint32_t slot,
+                              const uint64_t *dst_offsets /* n_ranks */);
+
 /* Insert `n` k-mers (device memory) that this rank owns; asynchronous on the ctx's stream. */
 int32_t skm_insert_kmers_device(skm_ctx *ctx, const uint64_t *d_kmers, uint64_t n);
 /* Snapshot this rank's partial histogram of its table partition as column

@@ -73,6 +73,7 @@ def lib():
         "orc_counts_remove_low": (None, [vp, u32]),
         "orc_counts_export_sorted": (u64, [vp, vp, vp, u64]),
         "orc_counts_digest": (u64, [vp]),
+        "orc_find_oligos": (u64, [vp, vp, u64, u32, u32, vp, vp, u64]),
         "orc_histo_new": (vp, [u64]),
         "orc_histo_free": (None, [vp]),
         "orc_histo_move_count": (None, [vp, u64, u64]),
@@ -244,6 +245,15 @@ class KmerCounts:
         keys = np.empty(n, dtype=np.uint64)
         counts = np.empty(n, dtype=np.uint32)
         lib().orc_counts_export_sorted(self._h, keys.ctypes.data, counts.ctypes.data, n)
+        return keys, counts
+    def find_oligos(self, oligos, oligo_length, min_count):
+        """find_oligos_in_kmers (src/pcr/primers.rs:163-226); sorted (kmers, counts)."""
+        o = np.ascontiguousarray(oligos, dtype=np.uint64)
+        n = lib().orc_find_oligos(self._h, o.ctypes.data, o.size, oligo_length, min_count, None, None, 0)
+        keys = np.empty(n, dtype=np.uint64)
+        counts = np.empty(n, dtype=np.uint32)
+        lib().orc_find_oligos(self._h, o.ctypes.data, o.size, oligo_length, min_count,
+                              keys.ctypes.data, counts.ctypes.data, n)
         return keys, counts
     def filtered_view(self, min_count): return FilteredKmerCounts(self, min_count)
 

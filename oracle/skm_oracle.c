@@ -341,6 +341,14 @@ void orc_counts_free(orc_counts *c) {
 }
 uint32_t orc_counts_k(const orc_counts *c) { return c->k; }
 
+typedef struct {
+    uint64_t key;
+    uint32_t count;
+} kc_pair;
+static int cmp_pair(const void *a, const void *b) {
+    uint64_t x = ((const kc_pair *)a)->key, y = ((const kc_pair *)b)->key;
+    return x < y ? -1 : x > y;
+}
 static inline uint32_t sat_add_u32(uint32_t a, uint32_t b) {
     uint64_t s = (uint64_t)a + b;
     return s > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s;
@@ -451,14 +459,6 @@ void orc_counts_remove_low(orc_counts *c, uint32_t min_count) {
     free(dead);
 }
 
-typedef struct {
-    uint64_t key;
-    uint32_t count;
-} kc_pair;
-static int cmp_pair(const void *a, const void *b) {
-    uint64_t x = ((const kc_pair *)a)->key, y = ((const kc_pair *)b)->key;
-    return x < y ? -1 : x > y;
-}
 uint64_t orc_counts_export_sorted(const orc_counts *c, uint64_t *keys, uint32_t *counts,
                                   uint64_t cap) {
     uint64_t n = c->map.len;
@@ -484,6 +484,55 @@ uint64_t orc_counts_digest(const orc_counts *c) {
     for (uint64_t i = 0; i < c->map.cap; i++)
         if (c->map.cells[i].key != SKM_EMPTY_KEY) d += skm_pair_digest(c->map.cells[i].key, (uint32_t)c->map.cells[i].val);
     return d;
+}
+
+/* src/pcr/primers.rs:163-226 */
+uint64_t orc_find_oligos(const orc_counts *c, const uint64_t *oligos, uint64_t n_oligos,
+                         uint32_t oligo_length, uint32_t min_count, uint64_t *keys, uint32_t *counts,
+                         uint64_t cap) {
+    const uint32_t k = c->k;
+    if (!n_oligos || oligo_length == 0 || oligo_length >= k) return 0;
+    const uint64_t mask = ((1ull << (2 * oligo_length)) - 1) << (2 * k - 2 * oligo_length);
+    const uint64_t rc_mask = (1ull << (2 * oligo_length)) - 1;
+    u64map fwd, rc;
+    map_init(&fwd, n_oligos);
+    map_init(&rc, n_oligos);
+    for (uint64_t i = 0; i < n_oligos; i++) {
+        *map_entry(&fwd, oligos[i] << (2 * (k - oligo_length))) = 1;
+        *map_entry(&rc, orc_revcomp_kmer(oligos[i], oligo_length)) = 1;
+    }
+    uint64_t n = 0, mcap = 1024;
+    kc_pair *m = (kc_pair *)malloc(mcap * sizeof(kc_pair));
+    for (uint64_t i = 0; i < c->map.cap; i++) {
+        const uint64_t kmer = c->map.cells[i].key;
+        if (kmer == SKM_EMPTY_KEY) continue;
+        const uint32_t count = (uint32_t)c->map.cells[i].val;
+        if (count < min_count) continue;
+        uint64_t out;
+        if (map_get(&fwd, kmer & mask))
+            out = kmer;
+        else if (map_get(&rc, kmer & rc_mask))
+            out = orc_revcomp_kmer(kmer, k);
+        else
+            continue;
+        if (n == mcap) {
+            mcap *= 2;
+            m = (kc_pair *)realloc(m, mcap * sizeof(kc_pair));
+        }
+        m[n].key = out;
+        m[n].count = count;
+        n++;
+    }
+    qsort(m, n, sizeof(kc_pair), cmp_pair);
+    if (keys && counts && cap >= n)
+        for (uint64_t i = 0; i < n; i++) {
+            keys[i] = m[i].key;
+            counts[i] = m[i].count;
+        }
+    free(m);
+    map_free(&fwd);
+    map_free(&rc);
+    return n;
 }
 
 /* ======================================================================= */

@@ -108,6 +108,16 @@ uint64_t orc_counts_export_sorted(const orc_counts *, uint64_t *keys, uint32_t *
 /* wrapping sum of skm_pair_digest over all entries. */
 uint64_t orc_counts_digest(const orc_counts *);
 
+/* find_oligos_in_kmers (src/pcr/primers.rs:163-226): the full-table scan sPCR runs per primer
+ * direction and mismatch level.  `oligos` are unshifted 2-bit oligos of `oligo_length` bases
+ * (0 < oligo_length < k).  A table k-mer with count >= min_count matches if its first
+ * oligo_length bases equal an oligo (kept as is), else if its last oligo_length bases equal the
+ * reverse complement of an oligo (then its reverse complement is reported).  Output sorted by
+ * k-mer; returns the number of matches (keys/counts may be NULL to size). */
+uint64_t orc_find_oligos(const orc_counts *, const uint64_t *oligos, uint64_t n_oligos,
+                         uint32_t oligo_length, uint32_t min_count, uint64_t *keys, uint32_t *counts,
+                         uint64_t cap);
+
 /* ---- histogram.rs ------------------------------------------------------ */
 
 typedef struct orc_histo orc_histo;

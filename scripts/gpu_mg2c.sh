@@ -1,0 +1,18 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+timeout 900 $T bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu --exchange p2p > gpurun_out/mg2_p2p.json 2> gpurun_out/mg2_p2p.err; echo "p2p rc=$?"; tail -4 gpurun_out/mg2_p2p.err
+timeout 900 $T bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu --exchange nccl > gpurun_out/mg2_nccl.json 2> gpurun_out/mg2_nccl.err; echo "nccl rc=$?"; tail -2 gpurun_out/mg2_nccl.err
+timeout 600 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu > gpurun_out/mg1_full.json 2> gpurun_out/mg1_full.err; echo "n1 rc=$?"
+python - <<'PY'
+import json,os
+for f in ('mg1_full','mg2_p2p','mg2_nccl'):
+    if not os.path.exists(f'gpurun_out/{f}.json') or os.path.getsize(f'gpurun_out/{f}.json')==0: continue
+    d=json.load(open(f'gpurun_out/{f}.json')); s=d['stage_ms']
+    print(f, 'value %.2f G/s step %.2f ms | e2e %.2f G/s %.2f ms | ins %.2f cnt %.2f part %.2f pack %.2f nvlink/step %.2f GB' % (d['value']/1e9, d['ms_per_step'], d['e2e']['value']/1e9, d['e2e']['ms_per_step'], s['insert'], s['count'], s['partition'], s['pack'], d.get('nvlink_bytes_sent_per_step_rank0',0)/1e9))
+PY
+# capture the insert kernel (N=1 default bench)
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e"
+$CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"insert_runs" -s 50 -c 3 -o gpurun_out/prof_r01_insert $CMD > gpurun_out/ncu_insert.log 2>&1
+echo "insert capture rc=$?"

@@ -110,6 +110,15 @@ struct skm_ctx {
     cudaEvent_t raw_copied[3] = {nullptr, nullptr, nullptr}, raw_packed[3] = {nullptr, nullptr, nullptr};
     uint32_t raw_next = 0;
 
+    // peer-to-peer routing: receive arenas of this rank and the peers' mapped pointers
+    static constexpr uint32_t kP2PSlots = 2;
+    unsigned long long *arena[kP2PSlots] = {nullptr, nullptr};
+    uint64_t arena_entries = 0;
+    unsigned long long *peer_arena[16][kP2PSlots] = {};
+    bool peer_ipc[16][kP2PSlots] = {};
+    std::vector<uint64_t> route_counts;  // bucket counts of the chunk last passed to skm_route_count
+    uint32_t route_counts_chunk = 0xFFFFFFFFu;
+
     // run descriptors (pinned ring + device copy)
     RunDesc *h_desc = nullptr, *d_desc = nullptr;
     cudaEvent_t desc_event[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -372,15 +381,23 @@ int32_t bucket_count(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn 
 
 // Pass 2: scatter the k-mers into `d_out`, grouped by bucket (uses the cursors of pass 1).
 int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn fn, uint32_t n_buckets,
-                       unsigned long long *d_out) {
+                       unsigned long long *d_out, const OwnerBases *p2p = nullptr) {
     const ChunkState &cs = c->chunks[chunk];
     Span sp(c, ST_PART, c->stream);
     const size_t smem = scatter_smem_bytes(n_buckets);
+    OwnerBases bases{};
+    if (p2p) {
+        bases = *p2p;
+    } else {
+        bases.dst[0] = d_out;
+        bases.uniform = 1;
+        bases.log2_regions = fn.log2_regions;
+    }
     for (size_t s = s0; s < s1; s++) {
         const Segment &sg = cs.segs[s];
         if (!sg.n_units || !sg.codes) continue;
         bucket_scatter_kernel<<<grid_for(sg.n_units, kScatterThreads), kScatterThreads, smem, c->stream>>>(
-            sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, d_out);
+            sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, bases);
         c->launches++;
         c->stage_launches[ST_PART]++;
     }
@@ -389,11 +406,17 @@ int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketF
 }
 
 #define SKM_LAUNCH_RUNS(D, H)                                                                     \
-    insert_runs_kernel<D, H><<<grid, 256, 0, c->stream>>>(descs, n_desc, single, n_dev, tref(c), c->d_gc, \
-                                                          c->d_hist, c->p.histo_max)
-void launch_insert_runs(skm_ctx *c, uint32_t grid, const RunDesc *descs, uint32_t n_desc, RunDesc single,
+    insert_runs_kernel<D, H><<<grid, 256, 0, c->stream>>>(descs, n_desc, single, n_dev, n_tiles, counter, \
+                                                          tref(c), c->d_gc, c->d_hist, c->p.histo_max)
+// n_tiles: number of warp tiles (ignored for a single run, where the kernel derives it from the length)
+void launch_insert_runs(skm_ctx *c, uint64_t n_tiles, const RunDesc *descs, uint32_t n_desc, RunDesc single,
                         const unsigned long long *n_dev) {
     const bool h = c->track_histo;
+    // persistent grid: enough CTAs to fill the chip, never more than there are tiles
+    uint64_t want = (n_tiles + 7) / 8;
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->sm_count * 6));
+    unsigned long long *counter = &c->d_gc->scratch[0];
+    cudaMemsetAsync(counter, 0, sizeof(unsigned long long), c->stream);
     switch (c->pipe_depth) {
     case 2: if (h) SKM_LAUNCH_RUNS(2, true); else SKM_LAUNCH_RUNS(2, false); break;
     case 4: if (h) SKM_LAUNCH_RUNS(4, true); else SKM_LAUNCH_RUNS(4, false); break;
@@ -418,7 +441,7 @@ int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_
         {
             Span sp(c, ST_INSERT, c->stream);
             RunDesc single{d_kmers + i, d_counts ? d_counts + i : nullptr, granted, 0};
-            launch_insert_runs(c, grid_for(granted, kListTile), nullptr, 0, single,
+            launch_insert_runs(c, (granted + kWarpTile - 1) / kWarpTile, nullptr, 0, single,
                                (i == 0 && granted == n) ? n_dev : nullptr);
             c->insert_kmers += granted;
         }
@@ -434,9 +457,8 @@ int32_t launch_run_range(skm_ctx *c, std::vector<RunDesc> &runs, size_t i, size_
     uint64_t tiles = 0;
     for (size_t q = i; q < j; q++) {
         runs[q].tile_begin = tiles;
-        tiles += (runs[q].n + kListTile - 1) / kListTile;
+        tiles += (runs[q].n + kWarpTile - 1) / kWarpTile;
     }
-    if (tiles > 0x7FFFFFFFull) return fail(c, SKM_ERR_INVALID_ARG, "too many k-mers for one launch");
     // descriptors go through a small ring of pinned buffers (the copy is asynchronous)
     const size_t n = j - i, bytes = n * sizeof(RunDesc);
     const uint32_t slot = c->desc_next++ % kDescRing;
@@ -447,7 +469,7 @@ int32_t launch_run_range(skm_ctx *c, std::vector<RunDesc> &runs, size_t i, size_
     CU(cudaMemcpyAsync(d_descs, c->h_desc + (size_t)slot * kMaxRuns, bytes, cudaMemcpyHostToDevice, c->stream));
     {
         Span sp(c, ST_INSERT, c->stream);
-        launch_insert_runs(c, (uint32_t)tiles, d_descs, (uint32_t)n, RunDesc{}, nullptr);
+        launch_insert_runs(c, tiles, d_descs, (uint32_t)n, RunDesc{}, nullptr);
         c->insert_kmers += total;
     }
     CU(cudaGetLastError());
@@ -830,6 +852,10 @@ void skm_destroy(skm_ctx *c) {
         cudaFree(c->d_bins);
         cudaFree(c->d_hist);
         cudaFree(c->d_tot);
+        for (uint32_t r = 0; r < 16; r++)
+            for (uint32_t sl = 0; sl < skm_ctx::kP2PSlots; sl++)
+                if (c->peer_ipc[r][sl]) cudaIpcCloseMemHandle(c->peer_arena[r][sl]);
+        for (uint32_t sl = 0; sl < skm_ctx::kP2PSlots; sl++) cudaFree(c->arena[sl]);
         for (int i = 0; i < 3; i++) {
             cudaFree(c->raw_buf[i]);
             if (c->raw_copied[i]) cudaEventDestroy(c->raw_copied[i]);
@@ -1338,6 +1364,74 @@ int32_t skm_lookup_batch(skm_ctx *c, const uint64_t *kmers, uint64_t n, uint32_t
     return SKM_OK;
 }
 
+int32_t skm_scan_oligos(skm_ctx *c, const uint64_t *oligos, uint64_t n_oligos, uint32_t oligo_length,
+                        uint32_t min_count, uint64_t *keys, uint32_t *counts, uint64_t cap, uint64_t *n_out) {
+    if (!c || !n_out || (n_oligos && !oligos)) return SKM_ERR_INVALID_ARG;
+    *n_out = 0;
+    const uint32_t k = c->p.k;
+    // src/pcr/primers.rs:168-187
+    if (n_oligos == 0) return fail(c, SKM_ERR_INVALID_ARG, "find_oligos_in_kmers called with no oligos");
+    if (oligo_length == 0 || oligo_length >= k)
+        return fail(c, SKM_ERR_INVALID_ARG, "oligo length %u out of range for k=%u (must be 1..k-1); trim must be < k",
+                    oligo_length, k);
+    if (n_oligos > (1u << 24)) return fail(c, SKM_ERR_INVALID_ARG, "too many oligos");
+    std::vector<uint64_t> fwd(n_oligos), rc(n_oligos);
+    for (uint64_t i = 0; i < n_oligos; i++) {
+        fwd[i] = oligos[i] << (2 * (k - oligo_length));
+        rc[i] = skm_revcomp_kmer(oligos[i], oligo_length);
+    }
+    std::sort(fwd.begin(), fwd.end());
+    std::sort(rc.begin(), rc.end());
+    const unsigned long long mask = ((1ull << (2 * oligo_length)) - 1) << (2 * k - 2 * oligo_length);
+    const unsigned long long rc_mask = (1ull << (2 * oligo_length)) - 1;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    unsigned long long *d_sets = nullptr, *d_keys = nullptr, *d_cursor = nullptr;
+    uint32_t *d_counts = nullptr;
+    const uint64_t out_cap = cap;
+    CU(cudaMallocAsync((void **)&d_sets, 2 * n_oligos * sizeof(uint64_t), c->stream));
+    CU(cudaMallocAsync((void **)&d_keys, std::max<uint64_t>(out_cap, 1) * sizeof(uint64_t), c->stream));
+    CU(cudaMallocAsync((void **)&d_counts, std::max<uint64_t>(out_cap, 1) * sizeof(uint32_t), c->stream));
+    CU(cudaMallocAsync((void **)&d_cursor, sizeof(uint64_t), c->stream));
+    CU(cudaMemcpyAsync(d_sets, fwd.data(), n_oligos * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_sets + n_oligos, rc.data(), n_oligos * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // fwd/rc are pageable host vectors
+    scan_oligos_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity, k, d_sets, d_sets + n_oligos,
+                                                               (uint32_t)n_oligos, mask, rc_mask, min_count, d_keys,
+                                                               d_counts, out_cap, d_cursor);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_pinned, d_cursor, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const uint64_t n = c->h_pinned[0];
+    *n_out = n;
+    int32_t rc_code = SKM_OK;
+    if (keys && counts && cap >= n && n) {
+        CU(cudaMemcpy(keys, d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(counts, d_counts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        // presentation order (host): ascending k-mer, like skm_export(sorted)
+        std::vector<uint64_t> idx(n);
+        for (uint64_t i = 0; i < n; i++) idx[i] = i;
+        std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return keys[a] < keys[b]; });
+        std::vector<uint64_t> k2(n);
+        std::vector<uint32_t> c2(n);
+        for (uint64_t i = 0; i < n; i++) {
+            k2[i] = keys[idx[i]];
+            c2[i] = counts[idx[i]];
+        }
+        memcpy(keys, k2.data(), n * sizeof(uint64_t));
+        memcpy(counts, c2.data(), n * sizeof(uint32_t));
+    } else if (n && (keys || counts)) {
+        rc_code = fail(c, SKM_ERR_INVALID_ARG, "scan buffers too small: need %llu", (unsigned long long)n);
+    }
+    CU(cudaFreeAsync(d_sets, c->stream));
+    CU(cudaFreeAsync(d_keys, c->stream));
+    CU(cudaFreeAsync(d_counts, c->stream));
+    CU(cudaFreeAsync(d_cursor, c->stream));
+    return rc_code;
+}
+
 int32_t skm_insert_counts(skm_ctx *c, const uint64_t *keys, const uint32_t *counts, uint64_t n) {
     if (!c || (n && (!keys || !counts))) return SKM_ERR_INVALID_ARG;
     if (n == 0) return SKM_OK;
@@ -1384,7 +1478,12 @@ int32_t skm_route_count(skm_ctx *c, uint32_t chunk, uint64_t *bucket_counts) {
     if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
     uint64_t total = 0;
     const BucketFn fn = route_fn(c);
-    return bucket_count(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions, &total, bucket_counts);
+    const uint32_t nb = c->n_ranks << fn.log2_regions;
+    int32_t rc = bucket_count(c, chunk, 0, cs.segs.size(), fn, nb, &total, bucket_counts);
+    if (rc) return rc;
+    c->route_counts.assign(bucket_counts, bucket_counts + nb);
+    c->route_counts_chunk = chunk;
+    return SKM_OK;
 }
 
 int32_t skm_route_scatter(skm_ctx *c, uint32_t chunk, uint64_t *d_out) {
@@ -1397,6 +1496,98 @@ int32_t skm_route_scatter(skm_ctx *c, uint32_t chunk, uint64_t *d_out) {
     const BucketFn fn = route_fn(c);
     int32_t rc = bucket_scatter(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions,
                                 (unsigned long long *)d_out);
+    if (rc) return rc;
+    for (auto &sg : cs.segs) {
+        CU(cudaFreeAsync(sg.codes, c->stream));
+        CU(cudaFreeAsync(sg.breaks, c->stream));
+        sg.codes = nullptr;
+        sg.breaks = nullptr;
+    }
+    cs.counted = true;
+    return SKM_OK;  // asynchronous: ordered on the ctx's stream
+}
+
+int32_t skm_p2p_arena_create(skm_ctx *c, uint64_t entries_per_slot) {
+    if (!c || entries_per_slot == 0) return SKM_ERR_INVALID_ARG;
+    if (c->n_ranks > kMaxP2PRanks) return fail(c, SKM_ERR_INVALID_ARG, "peer-to-peer routing supports at most %u ranks", kMaxP2PRanks);
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    for (uint32_t sl = 0; sl < skm_ctx::kP2PSlots; sl++) {
+        if (c->arena[sl]) CU(cudaFree(c->arena[sl]));
+        c->arena[sl] = nullptr;
+        // cudaMalloc, not the stream-ordered pool: the block must be exportable through CUDA IPC
+        CU(cudaMalloc((void **)&c->arena[sl], entries_per_slot * sizeof(uint64_t)));
+        c->peer_arena[c->p.rank][sl] = c->arena[sl];
+    }
+    c->arena_entries = entries_per_slot;
+    return SKM_OK;
+}
+
+int32_t skm_p2p_arena_handle(skm_ctx *c, uint32_t slot, uint8_t *handle64) {
+    if (!c || !handle64 || slot >= skm_ctx::kP2PSlots) return SKM_ERR_INVALID_ARG;
+    if (!c->arena[slot]) return fail(c, SKM_ERR_STATE, "no arena: call skm_p2p_arena_create first");
+    DeviceGuard g(c->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->arena[slot]));
+    memcpy(handle64, &h, 64);
+    return SKM_OK;
+}
+
+int32_t skm_p2p_arena_ptr(skm_ctx *c, uint32_t slot, uint64_t **out) {
+    if (!c || !out || slot >= skm_ctx::kP2PSlots) return SKM_ERR_INVALID_ARG;
+    *out = (uint64_t *)c->arena[slot];
+    return SKM_OK;
+}
+
+int32_t skm_p2p_open_peer(skm_ctx *c, uint32_t peer_rank, uint32_t slot, const uint8_t *handle64) {
+    if (!c || !handle64 || slot >= skm_ctx::kP2PSlots || peer_rank >= c->n_ranks || peer_rank >= kMaxP2PRanks)
+        return SKM_ERR_INVALID_ARG;
+    if (peer_rank == c->p.rank) return SKM_OK;  // own arena is already set
+    DeviceGuard g(c->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_arena[peer_rank][slot] = (unsigned long long *)p;
+    c->peer_ipc[peer_rank][slot] = true;
+    return SKM_OK;
+}
+
+int32_t skm_p2p_set_peer(skm_ctx *c, uint32_t peer_rank, uint32_t slot, uint64_t *d_ptr) {
+    if (!c || slot >= skm_ctx::kP2PSlots || peer_rank >= c->n_ranks || peer_rank >= kMaxP2PRanks)
+        return SKM_ERR_INVALID_ARG;
+    c->peer_arena[peer_rank][slot] = (unsigned long long *)d_ptr;
+    c->peer_ipc[peer_rank][slot] = false;
+    return SKM_OK;
+}
+
+int32_t skm_route_scatter_p2p(skm_ctx *c, uint32_t chunk, uint32_t slot, const uint64_t *dst_offsets) {
+    if (!c || !dst_offsets || slot >= skm_ctx::kP2PSlots) return SKM_ERR_INVALID_ARG;
+    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    ChunkState &cs = c->chunks[chunk];
+    if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
+    if (c->route_counts_chunk != chunk) return fail(c, SKM_ERR_STATE, "call skm_route_count for chunk %u first", chunk);
+    const BucketFn fn = route_fn(c);
+    const uint32_t regions = 1u << fn.log2_regions;
+    OwnerBases bases{};
+    bases.log2_regions = fn.log2_regions;
+    bases.uniform = 0;
+    uint64_t start = 0;  // first cell of owner o's buckets in the global cursor numbering
+    for (uint32_t o = 0; o < c->n_ranks; o++) {
+        uint64_t n_o = 0;
+        for (uint32_t r = 0; r < regions; r++) n_o += c->route_counts[(size_t)o * regions + r];
+        if (!c->peer_arena[o][slot]) return fail(c, SKM_ERR_STATE, "peer %u arena %u not mapped", o, slot);
+        if (dst_offsets[o] + n_o > c->arena_entries)
+            return fail(c, SKM_ERR_INVALID_ARG, "receive arena of rank %u too small (%llu + %llu > %llu entries)", o,
+                        (unsigned long long)dst_offsets[o], (unsigned long long)n_o, (unsigned long long)c->arena_entries);
+        bases.dst[o] = c->peer_arena[o][slot] + dst_offsets[o] - start;
+        start += n_o;
+    }
+    int32_t rc = bucket_scatter(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions, nullptr, &bases);
     if (rc) return rc;
     for (auto &sg : cs.segs) {
         CU(cudaFreeAsync(sg.codes, c->stream));

@@ -478,42 +478,56 @@ struct RunDesc {
     const unsigned long long *kmers;
     const uint32_t *counts;          // null => every k-mer counts 1
     unsigned long long n;
-    unsigned long long tile_begin;   // first CTA index of this run
+    unsigned long long tile_begin;   // index of this run's first warp tile
 };
+
+// Persistent kernel: every WARP pulls the next 512-k-mer tile from a global counter, so there is
+// no CTA-wide barrier inside the loop (ncu on the one-tile-per-CTA version: 25-30 % of issue
+// slots stalled on barriers because probe latencies differ between warps) and tiles are still
+// handed out in list order, which keeps the chip on a few neighbouring table regions.
+static constexpr uint32_t kWarpTile = 32 * kListPerThread;  // k-mers per warp tile
 
 template <int D, bool kHisto>
 __global__ void __launch_bounds__(256)
 insert_runs_kernel(const RunDesc *__restrict__ descs, uint32_t n_desc, RunDesc single,
-                   const unsigned long long *__restrict__ n_dev, TableRef table,
+                   const unsigned long long *__restrict__ n_dev, unsigned long long n_tiles,
+                   unsigned long long *__restrict__ tile_counter, TableRef table,
                    GlobalCounters *__restrict__ gc, unsigned long long *__restrict__ g_hist,
                    unsigned long long histo_max) {
-    RunDesc d;
-    uint64_t tile;
-    if (descs == nullptr) {
-        // single run; n_dev (optional): its length lives in device memory (written by the bucketing
-        // scan) so the host can queue this launch without waiting; the grid covers the bound single.n
-        d = single;
-        if (n_dev && *n_dev < d.n) d.n = *n_dev;
-        tile = blockIdx.x;
-    } else {
-        uint32_t lo = 0, hi = n_desc;  // last run whose tile_begin <= blockIdx.x
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (descs[mid].tile_begin <= blockIdx.x) lo = mid; else hi = mid;
-        }
-        d = descs[lo];
-        tile = blockIdx.x - d.tile_begin;
-    }
-    if (tile * kListTile >= d.n) return;
     __shared__ int s_low[kHisto ? kLowBins * 32 : 1];
     if (kHisto) histo_smem_init(s_low);
-    HistoSink hs{s_low, g_hist, histo_max, threadIdx.x & 31};
+    const uint32_t lane = threadIdx.x & 31;
+    if (descs == nullptr) {
+        // single run; n_dev (optional): its length lives in device memory (written by the bucketing
+        // scan) so the host can queue this launch without waiting for it
+        if (n_dev && *n_dev < single.n) single.n = *n_dev;
+        n_tiles = (single.n + kWarpTile - 1) / kWarpTile;
+    }
+    HistoSink hs{s_low, g_hist, histo_max, lane};
     InsertPipe<D, kHisto> pipe(table, hs);
-    const uint64_t base = tile * kListTile + threadIdx.x;
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tiles) break;
+        RunDesc d;
+        if (descs == nullptr) {
+            d = single;
+        } else {
+            uint32_t lo = 0, hi = n_desc;  // last run whose tile_begin <= t
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (descs[mid].tile_begin <= t) lo = mid; else hi = mid;
+            }
+            d = descs[lo];
+            t -= d.tile_begin;
+        }
+        const uint64_t base = t * kWarpTile + lane;
 #pragma unroll 4
-    for (uint32_t j = 0; j < kListPerThread; j++) {
-        const uint64_t i = base + (uint64_t)j * 256;
-        if (i < d.n) pipe.push(d.kmers[i], d.counts ? d.counts[i] : 1u);
+        for (uint32_t j = 0; j < kListPerThread; j++) {
+            const uint64_t i = base + (uint64_t)j * 32;
+            if (i < d.n) pipe.push(d.kmers[i], d.counts ? d.counts[i] : 1u);
+        }
     }
     pipe.drain();
     block_add(&gc->n_distinct, pipe.n_new);
@@ -702,6 +716,68 @@ lookup_kernel(TableRef table, uint32_t k,
     }
 }
 
+// find_oligos_in_kmers (src/pcr/primers.rs:163-226) as one streaming pass over the table:
+// a k-mer with count >= min_count matches if its first oligo_length bases are in `fwd_set`
+// (oligos shifted to the top of the k-mer; reported as is), else if its last oligo_length bases
+// are in `rc_set` (reverse complements of the oligos; its reverse complement is reported).
+// Both sets are sorted arrays searched by bisection (a few hundred entries, L1-resident).
+__device__ __forceinline__ bool sorted_contains(const unsigned long long *__restrict__ a, uint32_t n,
+                                                unsigned long long x) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const unsigned long long v = __ldg(&a[mid]);
+        if (v == x) return true;
+        if (v < x) lo = mid + 1; else hi = mid;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(256)
+scan_oligos_kernel(const Slot *__restrict__ table, uint64_t capacity, uint32_t k,
+                   const unsigned long long *__restrict__ fwd_set, const unsigned long long *__restrict__ rc_set,
+                   uint32_t n_set, unsigned long long mask, unsigned long long rc_mask, uint32_t min_count,
+                   unsigned long long *__restrict__ out_keys, uint32_t *__restrict__ out_counts,
+                   uint64_t out_cap, unsigned long long *__restrict__ cursor) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t n_iter = (capacity + stride - 1) / stride;
+    for (uint64_t it = 0; it < n_iter; it++) {
+        const uint64_t i = first + it * stride;
+        unsigned long long key = SKM_EMPTY_KEY, out = 0;
+        uint32_t c = 0;
+        bool hit = false;
+        if (i < capacity) {
+            const uint4 v = ld_nc_v4(reinterpret_cast<const uint4 *>(table) + i);
+            key = ((unsigned long long)v.y << 32) | v.x;
+            const unsigned long long cnt = ((unsigned long long)v.w << 32) | v.z;
+            c = cnt >= kU32Max ? kU32Max : (uint32_t)cnt;
+        }
+        if (key != SKM_EMPTY_KEY && c >= min_count) {
+            if (sorted_contains(fwd_set, n_set, key & mask)) {
+                hit = true;
+                out = key;
+            } else if (sorted_contains(rc_set, n_set, key & rc_mask)) {
+                hit = true;
+                out = skm_revcomp_kmer(key, k);
+            }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) {
+            const unsigned long long o = base + __popc(m & ((1u << lane) - 1));
+            if (o < out_cap) {
+                out_keys[o] = out;
+                out_counts[o] = c;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // bucketing by hash, one scheme for both uses: bucket = (owner rank, table region of that
 // owner) = the top bits of (owner, local hash).  On one GPU it orders a chunk's k-mers by
@@ -794,10 +870,22 @@ __host__ __device__ inline size_t scatter_smem_bytes(uint32_t n_buckets) {
     return (size_t)kScatterStage * 8 + (size_t)n_buckets * 8 + (size_t)n_buckets * 4 + ((size_t)n_buckets + 2) * 4;
 }
 
+// Where each owner's buckets go.  dst[o] is biased so that `dst[o] + global cursor value` is the
+// right cell: on one GPU every entry is the local list; in the fused multi-GPU route entry o is
+// rank o's receive arena mapped through CUDA IPC, and the copy-out loop below becomes the
+// NVLink transfer (contiguous runs of a bucket => full-width peer stores), overlapped tile by
+// tile with the extraction of the other CTAs.
+static constexpr uint32_t kMaxP2PRanks = 16;
+struct OwnerBases {
+    unsigned long long *dst[kMaxP2PRanks];
+    uint32_t log2_regions;  // bucket >> log2_regions = owner
+    uint32_t uniform;       // 1 => all owners share dst[0]
+};
+
 __global__ void __launch_bounds__(kScatterThreads)
 bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
                       uint64_t u_begin, uint64_t u_end, uint32_t k, BucketFn fn, uint32_t n_buckets,
-                      unsigned long long *__restrict__ cursors, unsigned long long *__restrict__ out) {
+                      unsigned long long *__restrict__ cursors, OwnerBases bases) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long *stage = reinterpret_cast<unsigned long long *>(s_raw);
     unsigned long long *s_gbase = stage + kScatterStage;
@@ -850,6 +938,7 @@ bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__rest
     for (uint32_t p = threadIdx.x; p < total; p += blockDim.x) {
         const unsigned long long kmer = stage[p];
         const uint32_t b = fn(kmer);
+        unsigned long long *out = bases.dst[bases.uniform ? 0u : (b >> bases.log2_regions)];
         out[s_gbase[b] + (p - s_start[b])] = kmer;
     }
 }

@@ -143,6 +143,18 @@ class Engine:
                                          counts.ctypes.data, found.ctypes.data))
         return counts, found.astype(bool)
 
+    def scan_oligos(self, oligos, oligo_length: int, min_count: int):
+        """find_oligos_in_kmers (src/pcr/primers.rs:163-226): sorted (kmers, counts)."""
+        o = np.ascontiguousarray(oligos, dtype=np.uint64)
+        n = C.c_uint64()
+        self._ck(self.L.skm_scan_oligos(self._h, o.ctypes.data, o.size, oligo_length, min_count, None, None, 0, C.byref(n)))
+        keys = np.empty(n.value, dtype=np.uint64)
+        counts = np.empty(n.value, dtype=np.uint32)
+        if n.value:
+            self._ck(self.L.skm_scan_oligos(self._h, o.ctypes.data, o.size, oligo_length, min_count,
+                                            keys.ctypes.data, counts.ctypes.data, n.value, C.byref(n)))
+        return keys[:n.value], counts[:n.value]
+
     def insert_counts(self, keys, counts):
         k = np.ascontiguousarray(keys, dtype=np.uint64)
         c = np.ascontiguousarray(counts, dtype=np.uint32)
@@ -169,6 +181,31 @@ class Engine:
 
     def route_scatter(self, chunk_index: int, d_out: int):
         self._ck(self.L.skm_route_scatter(self._h, chunk_index, d_out))
+
+    # fused route + exchange (peer stores over NVLink)
+    def p2p_arena_create(self, entries_per_slot: int):
+        self._ck(self.L.skm_p2p_arena_create(self._h, entries_per_slot))
+
+    def p2p_arena_handle(self, slot: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._ck(self.L.skm_p2p_arena_handle(self._h, slot, buf))
+        return bytes(buf)
+
+    def p2p_arena_ptr(self, slot: int) -> int:
+        p = C.c_void_p()
+        self._ck(self.L.skm_p2p_arena_ptr(self._h, slot, C.byref(p)))
+        return p.value or 0
+
+    def p2p_open_peer(self, peer_rank: int, slot: int, handle: bytes):
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        self._ck(self.L.skm_p2p_open_peer(self._h, peer_rank, slot, buf))
+
+    def p2p_set_peer(self, peer_rank: int, slot: int, d_ptr: int):
+        self._ck(self.L.skm_p2p_set_peer(self._h, peer_rank, slot, d_ptr))
+
+    def route_scatter_p2p(self, chunk_index: int, slot: int, dst_offsets):
+        off = np.ascontiguousarray(dst_offsets, dtype=np.uint64)
+        self._ck(self.L.skm_route_scatter_p2p(self._h, chunk_index, slot, off.ctypes.data))
 
     def insert_kmers_device(self, d_ptr: int, n: int):
         self._ck(self.L.skm_insert_kmers_device(self._h, d_ptr, n))

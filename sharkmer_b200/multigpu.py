@@ -11,9 +11,14 @@ barrier: all ranks finish exchanging and inserting chunk i before histogram colu
 is taken (src/io.rs:1016-1028 merges chunks in index order).  The result is
 independent of N.
 
-The exchange of chunk c+1 (route on the compute stream, all-to-all on the
-collective's stream) overlaps the insert of chunk c: send/receive buffers are
-double-buffered torch tensors.
+Two exchange paths:
+  * "p2p" (default on GPUs, N <= 16): fused route + exchange.  The scatter kernel stores every
+    destination's runs straight into that rank's receive arena through a CUDA-IPC mapping (peer
+    stores over NVLink/NVSwitch) — no local list, no collective copy; the transfer overlaps the
+    extraction tile by tile inside one kernel.  Steps are ordered by a 1-element all-reduce used
+    as a stream-ordered barrier; two arenas per rank give double buffering.
+  * "nccl": route to a local list, then all_to_all_single; the exchange of chunk c+1 overlaps
+    the insert of chunk c (double-buffered torch tensors).  Also the path of the CPU tests (gloo).
 
 `engine` is anything with the routing interface of sharkmer_b200.kmer.Engine
 (route_count / route_scatter / insert_runs_device / snapshot_histogram / histogram /
@@ -28,7 +33,7 @@ import torch.distributed as dist
 
 class ShardedCounter:
     def __init__(self, engine, n_chunks: int, chunks_arg: int, histo_max: int, device: torch.device,
-                 group=None, stream=None):
+                 group=None, stream=None, exchange: str = "nccl", arena_entries: int = 0):
         self.e = engine
         self.n_chunks = n_chunks
         self.chunks_arg = chunks_arg
@@ -40,6 +45,22 @@ class ShardedCounter:
         self.stream = stream  # torch.cuda.Stream the engine launches on (None on CPU)
         self.bytes_sent = 0
         self.kmers_received = 0
+        self.exchange = exchange
+        if exchange == "p2p":
+            self._setup_p2p(arena_entries)
+
+    def _setup_p2p(self, arena_entries: int):
+        """Allocate this rank's receive arenas and map every peer's through CUDA IPC."""
+        e = self.e
+        e.p2p_arena_create(int(arena_entries))
+        mine = [e.p2p_arena_handle(slot) for slot in range(2)]
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine, group=self.group)
+        for r in range(self.world):
+            if r != self.rank:
+                for slot in range(2):
+                    e.p2p_open_peer(r, slot, allh[r][slot])
+        self._tick = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     # -- small helpers ---------------------------------------------------------
     def _exchange_counts(self, counts: np.ndarray) -> np.ndarray:
@@ -73,6 +94,41 @@ class ShardedCounter:
             return self._finalize()
 
     def _finalize(self):
+        if self.exchange == "p2p":
+            return self._finalize_p2p()
+        return self._finalize_nccl()
+
+    def _finalize_p2p(self):
+        e = self.e
+        e.finalize_external()
+        for c in range(self.n_chunks):
+            slot = c & 1
+            counts = e.route_count(c, self.world)            # (world, regions)
+            rcounts = self._exchange_counts(counts)          # (world, regions): per source and region
+            per_dst = counts.sum(axis=1).astype(np.int64)
+            # where this rank's block starts in every destination's arena: after the blocks of lower ranks
+            allt = torch.empty(self.world * self.world, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(allt, torch.as_tensor(per_dst, device=self.device), group=self.group)
+            m = allt.cpu().numpy().reshape(self.world, self.world)   # m[s, d] = k-mers s sends to d
+            dst_offsets = m[:self.rank, :].sum(axis=0)
+            need = int(m[:, self.rank].sum())
+            e.route_scatter_p2p(c, slot, dst_offsets)        # fused: extract + bucket + peer stores
+            dist.all_reduce(self._tick, group=self.group)    # stream-ordered barrier: every rank's stores landed
+            e.insert_runs_device(e.p2p_arena_ptr(slot), rcounts)
+            self.bytes_sent += 8 * (int(per_dst.sum()) - int(per_dst[self.rank]))
+            self.kmers_received += need
+            if self.chunks_arg > 0:
+                e.snapshot_histogram(c)
+            else:
+                e.sync()
+        if self.chunks_arg == 0:
+            return None
+        cols = np.stack([e.histogram(c) for c in range(self.n_chunks)]).astype(np.int64)
+        t = torch.as_tensor(cols, device=self.device)
+        dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy().astype(np.uint64)
+
+    def _finalize_nccl(self):
         e = self.e
         e.finalize_external()  # ingest is complete on every rank; the chunk loop is ours
 

@@ -328,6 +328,27 @@ def test_lookup_batch_vs_oracle(skm, oracle):
         assert (found2 == wantf).all()
 
 
+def test_scan_oligos_vs_oracle(skm, oracle):  # src/pcr/primers.rs:163-226
+    L, k = 120, 25
+    reads = oracle.synth_reads(seed=8, genome_len=30_000, read_len=L, sub_rate=0.01, n_rate=0.0, first=0, n=8_000)
+    run = run_oracle(oracle, reads, k, 0, 100)
+    e = run_gpu(skm, reads, k, 0, 100, L)
+    keys, _ = run.table().export_sorted()
+    rng = np.random.default_rng(1)
+    for olen, min_count in ((12, 2), (8, 1), (20, 5), (24, 0)):
+        # oligos taken from real k-mers (prefixes and reverse-complemented suffixes) plus random ones
+        pick = keys[rng.integers(0, keys.size, 40)]
+        oligos = [int(x) >> (2 * (k - olen)) for x in pick[:20]]
+        oligos += [skm.revcomp_kmer(int(x) & ((1 << (2 * olen)) - 1), olen) for x in pick[20:]]
+        oligos += [int(x) for x in rng.integers(0, 1 << (2 * olen), 20, dtype=np.uint64)]
+        gk, gc = e.scan_oligos(oligos, olen, min_count)
+        ok, oc = run.table().find_oligos(oligos, olen, min_count)
+        assert gk.size == ok.size and gk.size > 0
+        assert (gk == ok).all() and (gc == oc).all()
+    with pytest.raises(skm.SkmError):
+        e.scan_oligos([1], k, 0)  # oligo length must be < k
+
+
 # ---- (5) synthetic generator: device == host, bit for bit ------------------------------------------
 
 def test_device_synth_matches_host(skm, oracle):
@@ -446,3 +467,45 @@ def test_sharded_two_partitions_single_process(skm, oracle):
     okeys, ocounts = run.table().export_sorted()
     assert merged == dict(zip(okeys.tolist(), ocounts.tolist()))
     assert sum(e.chunk_totals(c).n_kmers for e in engs for c in range(chunks)) == run.n_kmers_ingested
+
+
+def test_sharded_p2p_scatter_single_process(skm, oracle):
+    """Fused route + exchange: each ctx's scatter kernel stores straight into the destination
+    ctx's receive arena (peer pointers set directly: both partitions live in this process)."""
+    L, n, k, chunks, hmax, world = 100, 9_000, 21, 3, 100, 2
+    reads = oracle.synth_reads(33, 30_000, L, 0.01, 0.001, 0, n)
+    run = run_oracle(oracle, reads, k, chunks, hmax)
+    line = L + 1
+    engs = [skm.Engine(k, chunks, hmax, n_ranks=world, rank=r) for r in range(world)]
+    for e in engs:
+        e.p2p_arena_create(n * L)
+    for e in engs:
+        for r in range(world):
+            for slot in range(2):
+                e.p2p_set_peer(r, slot, engs[r].p2p_arena_ptr(slot))
+    for b in range(n // 1000):
+        engs[(b // chunks) % world].ingest_batch(b % chunks, reads[b * 1000 * line:(b + 1) * 1000 * line])
+    for e in engs:
+        e.finalize_external()
+    regions = engs[0].route_regions()
+    for c in range(chunks):
+        slot = c & 1
+        counts = [e.route_count(c, world) for e in engs]
+        m = np.array([[int(counts[s][d].sum()) for d in range(world)] for s in range(world)])
+        for s, e in enumerate(engs):
+            e.route_scatter_p2p(c, slot, m[:s, :].sum(axis=0))
+        for e in engs:
+            e.sync()  # (single process: a sync stands in for the stream-ordered barrier)
+        for d, e in enumerate(engs):
+            rc = np.stack([counts[s][d] for s in range(world)])
+            assert rc.shape == (world, regions)
+            e.insert_runs_device(e.p2p_arena_ptr(slot), rc)
+            e.snapshot_histogram(c)
+        col = sum(e.histogram(c).astype(np.int64) for e in engs)
+        assert (col == run.histogram(c).astype(np.int64)).all(), c
+    merged = {}
+    for e in engs:
+        keys, cnts = e.export(sorted=True)
+        merged.update(zip(keys.tolist(), cnts.tolist()))
+    okeys, ocounts = run.table().export_sorted()
+    assert merged == dict(zip(okeys.tolist(), ocounts.tolist()))
