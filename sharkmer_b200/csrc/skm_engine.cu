@@ -43,7 +43,8 @@ struct Segment {
     uint64_t n_bytes = 0;
     // eager partition (single GPU): the segment's k-mers, already ordered by table region
     unsigned long long *list = nullptr;
-    uint64_t *h_offsets = nullptr;  // pinned, n_buckets + 1 entries (valid after a stream sync)
+    uint64_t *h_offsets = nullptr;  // pinned, n_buckets + 1 entries (valid once `ready` has fired)
+    cudaEvent_t ready = nullptr;    // fires when the segment's pack (+ bucketing) has finished
     uint32_t n_buckets = 0;
 };
 
@@ -68,6 +69,10 @@ struct skm_ctx {
     uint32_t n_ranks = 1;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t part_stream = nullptr;  // pack + bucketing of incoming batches (overlaps inserts on `stream`)
+    cudaStream_t work = nullptr;         // stream the bucketing helpers currently launch on
+    cudaEvent_t ev_main = nullptr;
+    uint32_t insert_ctas_per_sm = 6;      // persistent insert grid (SKM_INSERT_CTAS); measured best: 6
     int sm_count = 148;
 
     Slot *table = nullptr;
@@ -345,35 +350,49 @@ uint32_t partition_log2_buckets(const skm_ctx *c) {
     return std::min<uint32_t>((uint32_t)l, route_log2_regions(c));
 }
 
+struct WorkStream {  // selects the stream the bucketing helpers launch on, for the current scope
+    skm_ctx *c;
+    cudaStream_t prev;
+    WorkStream(skm_ctx *c_, cudaStream_t s) : c(c_), prev(c_->work) { c->work = s; }
+    ~WorkStream() { c->work = prev; }
+};
+
+int32_t sync_all(skm_ctx *c) {
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->part_stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SKM_OK;
+}
+
 // Pass 1 of bucketing segments [s0, s1) of a chunk: per-bucket counts + offsets/cursors on the
 // device; the total (and optionally the counts) on the host.
 int32_t bucket_count(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn fn, uint32_t n_buckets,
                      uint64_t *total_out, uint64_t *h_counts) {
     const ChunkState &cs = c->chunks[chunk];
-    CU(cudaMemsetAsync(c->d_bucket_counts, 0, (n_buckets + 1) * sizeof(uint64_t), c->stream));
+    CU(cudaMemsetAsync(c->d_bucket_counts, 0, (n_buckets + 1) * sizeof(uint64_t), c->work));
     {
-        Span sp(c, ST_COUNT, c->stream);
+        Span sp(c, ST_COUNT, c->work);
         for (size_t s = s0; s < s1; s++) {
             const Segment &sg = cs.segs[s];
             if (!sg.n_units || !sg.codes) continue;
-            bucket_count_kernel<<<grid_for(sg.n_units, 256 * kBucketUnits), 256, n_buckets * sizeof(uint32_t), c->stream>>>(
+            bucket_count_kernel<<<grid_for(sg.n_units, 256 * kBucketUnits), 256, n_buckets * sizeof(uint32_t), c->work>>>(
                 sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_counts,
                 &c->d_cc[chunk]);
             c->launches++;
             c->stage_launches[ST_COUNT]++;
         }
-        bucket_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_bucket_counts, n_buckets, c->d_bucket_offsets,
+        bucket_scan_kernel<<<1, 1024, 0, c->work>>>(c->d_bucket_counts, n_buckets, c->d_bucket_offsets,
                                                        c->d_bucket_cursors);
         c->launches++;
     }
     CU(cudaGetLastError());
     if (!total_out) return SKM_OK;  // caller does not need the numbers on the host: stay asynchronous
     CU(cudaMemcpyAsync(c->h_pinned, c->d_bucket_offsets + n_buckets, sizeof(uint64_t),
-                       cudaMemcpyDeviceToHost, c->stream));
+                       cudaMemcpyDeviceToHost, c->work));
     if (h_counts)
         CU(cudaMemcpyAsync(c->h_pinned + 1, c->d_bucket_counts, n_buckets * sizeof(uint64_t),
-                           cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+                           cudaMemcpyDeviceToHost, c->work));
+    CU(cudaStreamSynchronize(c->work));
     *total_out = c->h_pinned[0];
     if (h_counts) memcpy(h_counts, c->h_pinned + 1, n_buckets * sizeof(uint64_t));
     return SKM_OK;
@@ -383,7 +402,7 @@ int32_t bucket_count(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn 
 int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn fn, uint32_t n_buckets,
                        unsigned long long *d_out, const OwnerBases *p2p = nullptr) {
     const ChunkState &cs = c->chunks[chunk];
-    Span sp(c, ST_PART, c->stream);
+    Span sp(c, ST_PART, c->work);
     const size_t smem = scatter_smem_bytes(n_buckets);
     OwnerBases bases{};
     if (p2p) {
@@ -396,7 +415,7 @@ int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketF
     for (size_t s = s0; s < s1; s++) {
         const Segment &sg = cs.segs[s];
         if (!sg.n_units || !sg.codes) continue;
-        bucket_scatter_kernel<<<grid_for(sg.n_units, kScatterThreads), kScatterThreads, smem, c->stream>>>(
+        bucket_scatter_kernel<<<grid_for(sg.n_units, kScatterThreads), kScatterThreads, smem, c->work>>>(
             sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, bases);
         c->launches++;
         c->stage_launches[ST_PART]++;
@@ -414,7 +433,7 @@ void launch_insert_runs(skm_ctx *c, uint64_t n_tiles, const RunDesc *descs, uint
     const bool h = c->track_histo;
     // persistent grid: enough CTAs to fill the chip, never more than there are tiles
     uint64_t want = (n_tiles + 7) / 8;
-    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->sm_count * 6));
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->sm_count * c->insert_ctas_per_sm));
     unsigned long long *counter = &c->d_gc->scratch[0];
     cudaMemsetAsync(counter, 0, sizeof(unsigned long long), c->stream);
     switch (c->pipe_depth) {
@@ -466,7 +485,11 @@ int32_t launch_run_range(skm_ctx *c, std::vector<RunDesc> &runs, size_t i, size_
     else CU(cudaEventCreateWithFlags(&c->desc_event[slot], cudaEventDisableTiming));
     memcpy(c->h_desc + (size_t)slot * kMaxRuns, runs.data() + i, bytes);
     RunDesc *d_descs = c->d_desc + (size_t)slot * kMaxRuns;
-    CU(cudaMemcpyAsync(d_descs, c->h_desc + (size_t)slot * kMaxRuns, bytes, cudaMemcpyHostToDevice, c->stream));
+    RunDesc *h_dev = nullptr;  // device-visible alias of the pinned descriptor ring
+    CU(cudaHostGetDevicePointer((void **)&h_dev, c->h_desc, 0));
+    copy_descs_kernel<<<4, 256, 0, c->stream>>>(h_dev + (size_t)slot * kMaxRuns, d_descs, (uint32_t)n);
+    c->launches++;
+    (void)bytes;
     {
         Span sp(c, ST_INSERT, c->stream);
         launch_insert_runs(c, tiles, d_descs, (uint32_t)n, RunDesc{}, nullptr);
@@ -671,7 +694,7 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index) {
     const uint32_t nb = 1u << fn.log2_regions;
     uint64_t *h_off = alloc_offsets(c, nb + 1);
     if (!h_off) return SKM_OK;
-    if (cudaMallocAsync((void **)&sg.list, need, c->stream) != cudaSuccess) {
+    if (cudaMallocAsync((void **)&sg.list, need, c->work) != cudaSuccess) {
         cudaGetLastError();
         sg.list = nullptr;
         return SKM_OK;
@@ -680,9 +703,9 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index) {
     if (rc) return rc;
     rc = bucket_scatter(c, chunk, seg_index, seg_index + 1, fn, nb, sg.list);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(h_off, c->d_bucket_offsets, (nb + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaFreeAsync(sg.codes, c->stream));
-    CU(cudaFreeAsync(sg.breaks, c->stream));
+    CU(cudaMemcpyAsync(h_off, c->d_bucket_offsets, (nb + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->work));
+    CU(cudaFreeAsync(sg.codes, c->work));
+    CU(cudaFreeAsync(sg.breaks, c->work));
     sg.codes = nullptr;
     sg.breaks = nullptr;
     sg.h_offsets = h_off;
@@ -698,22 +721,27 @@ int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t
     Segment sg;
     sg.n_bytes = n_bytes;
     sg.n_units = (n_bytes + 31) / 32;
-    CU(cudaMallocAsync((void **)&sg.codes, sg.n_units * sizeof(uint64_t), c->stream));
-    CU(cudaMallocAsync((void **)&sg.breaks, sg.n_units * sizeof(uint32_t), c->stream));
+    CU(cudaMallocAsync((void **)&sg.codes, sg.n_units * sizeof(uint64_t), c->work));
+    CU(cudaMallocAsync((void **)&sg.breaks, sg.n_units * sizeof(uint32_t), c->work));
     {
-        Span sp(c, ST_PACK, c->stream);
-        pack_kernel<<<grid_for(sg.n_units, 256 * kPackUnits), 256, 0, c->stream>>>(d_seqs, n_bytes, c->pos_base, sg.codes,
+        Span sp(c, ST_PACK, c->work);
+        pack_kernel<<<grid_for(sg.n_units, 256 * kPackUnits), 256, 0, c->work>>>(d_seqs, n_bytes, c->pos_base, sg.codes,
                                                                       sg.breaks, sg.n_units, &c->d_cc[chunk],
                                                                       c->d_gc);
         c->launches++;
         c->stage_launches[ST_PACK]++;
     }
     CU(cudaGetLastError());
-    if (packed_event) CU(cudaEventRecord(packed_event, c->stream));  // the raw buffer may be overwritten now
+    if (packed_event) CU(cudaEventRecord(packed_event, c->work));  // the raw buffer may be overwritten now
     c->pos_base += n_bytes;
     c->chunks[chunk].segs.push_back(sg);
     c->chunks[chunk].n_bytes += n_bytes;
-    return eager_partition(c, chunk, c->chunks[chunk].segs.size() - 1);
+    int32_t rc = eager_partition(c, chunk, c->chunks[chunk].segs.size() - 1);
+    if (rc) return rc;
+    Segment &seg = c->chunks[chunk].segs.back();
+    seg.ready = get_event(c);
+    CU(cudaEventRecord(seg.ready, c->work));
+    return SKM_OK;
 }
 
 int32_t check_ingest_args(skm_ctx *c, uint32_t chunk, const void *p, uint64_t n) {
@@ -773,6 +801,10 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     }
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->part_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    c->work = c->stream;
+    if (const char *g = getenv("SKM_INSERT_CTAS")) c->insert_ctas_per_sm = std::max(1, atoi(g));
     // keep freed blocks in the stream-ordered pool (staging buffers are recycled every batch)
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -840,6 +872,7 @@ void skm_destroy(skm_ctx *c) {
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->part_stream);
         for (auto &cs : c->chunks)
             for (auto &sg : cs.segs) {
                 cudaFree(sg.codes);
@@ -879,6 +912,8 @@ void skm_destroy(skm_ctx *c) {
         for (auto e : c->event_pool) cudaEventDestroy(e);
         if (c->own_stream) cudaStreamDestroy(c->stream);
         cudaStreamDestroy(c->copy_stream);
+        cudaStreamDestroy(c->part_stream);
+        if (c->ev_main) cudaEventDestroy(c->ev_main);
     }
     delete c;
 }
@@ -965,7 +1000,8 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
     }
     CU(cudaEventRecord(c->raw_copied[b], c->copy_stream));
     if (!(flags & SKM_INGEST_ASYNC)) CU(cudaStreamSynchronize(c->copy_stream));
-    CU(cudaStreamWaitEvent(c->stream, c->raw_copied[b], 0));
+    CU(cudaStreamWaitEvent(c->part_stream, c->raw_copied[b], 0));
+    WorkStream ws(c, c->part_stream);
     rc = stage_device(c, chunk, c->raw_buf[b], n_bytes, c->raw_packed[b]);
     return rc;
 }
@@ -1010,6 +1046,10 @@ int32_t skm_ingest_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uin
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
+    // d_seqs was produced on the ctx's main stream (or is already complete): order the pack after it
+    CU(cudaEventRecord(c->ev_main, c->stream));
+    CU(cudaStreamWaitEvent(c->part_stream, c->ev_main, 0));
+    WorkStream ws(c, c->part_stream);
     return stage_device(c, chunk, d_seqs, n_bytes);
 }
 
@@ -1017,25 +1057,34 @@ int32_t skm_sync(skm_ctx *c) {
     if (!c) return SKM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaStreamSynchronize(c->copy_stream));
+    int32_t rc = sync_all(c);
+    if (rc) return rc;
     collect_spans(c);
     return check_sticky(c);
 }
 
 static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
     if (c->finalized) return fail(c, SKM_ERR_STATE, "finalize called twice");
-    CU(cudaStreamSynchronize(c->stream));
-    int32_t rc = check_sticky(c);  // an invalid base aborts the run before anything is counted
-    if (rc) return rc;
-    rc = refresh_chunk_counters(c);
-    if (rc) return rc;
-    uint64_t n_reads = 0;
-    for (auto &cc : c->h_cc) n_reads += cc.n_reads;
-    if (n_reads == 0 && run_chunk_loop)  // src/io.rs:578-580
-        return fail(c, SKM_ERR_NO_READS, "No reads were ingested. Check that input files contain valid FASTQ records.");
+    bool any = false;
+    for (auto &cs : c->chunks) any = any || !cs.segs.empty();
+    int32_t rc;
+    if (!any || !run_chunk_loop) {
+        // nothing to overlap: wait for the ingest streams, then report errors / hand over
+        rc = sync_all(c);
+        if (rc) return rc;
+        rc = check_sticky(c);  // an invalid base aborts the run
+        if (rc) return rc;
+        rc = refresh_chunk_counters(c);
+        if (rc) return rc;
+        if (!any && run_chunk_loop)  // src/io.rs:578-580 (every non-empty batch holds at least one read)
+            return fail(c, SKM_ERR_NO_READS, "No reads were ingested. Check that input files contain valid FASTQ records.");
+        c->finalized = true;
+        return SKM_OK;
+    }
     c->finalized = true;
-    if (!run_chunk_loop) return SKM_OK;
+    // The chunk loop starts while later batches may still be packing / bucketing on part_stream:
+    // the inserts of chunk c (main stream) overlap the bucketing of chunks > c.  An invalid base
+    // found by a late pack kernel is reported at the end (the run is aborted either way).
 
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     cudaEventRecord(e0, c->stream);
@@ -1046,8 +1095,12 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
             uint32_t nb = 0;
             for (auto &sg : cs.segs)
                 if (sg.list) nb = sg.n_buckets;
+            for (auto &sg : cs.segs) {
+                if (!sg.ready) continue;
+                if (sg.list) CU(cudaEventSynchronize(sg.ready));   // host needs the bucket offsets
+                else CU(cudaStreamWaitEvent(c->stream, sg.ready, 0));  // packed data is consumed on the main stream
+            }
             if (nb) {
-                CU(cudaStreamSynchronize(c->stream));  // the offsets were copied long ago; make them visible
                 std::vector<RunDesc> runs;
                 for (uint32_t r = 0; r < nb; r++)
                     for (auto &sg : cs.segs)
@@ -1063,6 +1116,7 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
         for (auto &sg : cs.segs)
             if (sg.codes) packed_bytes += sg.n_bytes;
         if (packed_bytes && want_partitioned(c, packed_bytes)) {
+            CU(cudaStreamSynchronize(c->part_stream));  // the bucketing scratch is shared with the ingest path
             rc = insert_chunk_partitioned(c, ch);
             if (rc) return rc;
         } else if (packed_bytes) {
@@ -1082,6 +1136,8 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
             sg.codes = nullptr;
             sg.breaks = nullptr;
             sg.list = nullptr;
+            if (sg.ready) c->event_pool.push_back(sg.ready);
+            sg.ready = nullptr;
         }
         cs.counted = true;
         if (c->p.chunks > 0) {
@@ -1095,7 +1151,10 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
     rc = scan_table(c, false, &rescan);
     if (rc) return rc;
     cudaEventRecord(e1, c->stream);
-    CU(cudaStreamSynchronize(c->stream));
+    rc = sync_all(c);
+    if (rc) return rc;
+    rc = check_sticky(c);
+    if (rc) return rc;
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     c->stage_ms[ST_FINALIZE] += ms;
@@ -1145,8 +1204,13 @@ int32_t skm_reset(skm_ctx *c) {
     if (!c) return SKM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
+    {
+        int32_t rc0 = sync_all(c);
+        if (rc0) return rc0;
+    }
     for (auto &cs : c->chunks) {
         for (auto &sg : cs.segs) {
+            if (sg.ready) c->event_pool.push_back(sg.ready);
             if (sg.codes) CU(cudaFreeAsync(sg.codes, c->stream));
             if (sg.breaks) CU(cudaFreeAsync(sg.breaks, c->stream));
             if (sg.list) CU(cudaFreeAsync(sg.list, c->stream));
@@ -1215,8 +1279,9 @@ int32_t skm_totals_get(skm_ctx *c, skm_totals *out) {
     if (!c || !out) return SKM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    CU(cudaStreamSynchronize(c->stream));
-    int32_t rc = refresh_chunk_counters(c);
+    int32_t rc = sync_all(c);
+    if (rc) return rc;
+    rc = refresh_chunk_counters(c);
     if (rc) return rc;
     rc = refresh_totals(c);
     if (rc) return rc;
@@ -1238,8 +1303,9 @@ int32_t skm_chunk_totals(skm_ctx *c, uint32_t chunk, skm_totals *out) {
     if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    CU(cudaStreamSynchronize(c->stream));
-    int32_t rc = refresh_chunk_counters(c);
+    int32_t rc = sync_all(c);
+    if (rc) return rc;
+    rc = refresh_chunk_counters(c);
     if (rc) return rc;
     memset(out, 0, sizeof *out);
     out->n_reads = c->h_cc[chunk].n_reads;
@@ -1253,7 +1319,8 @@ int32_t skm_stage_times(skm_ctx *c, skm_stage_ms *out) {
     if (!c || !out) return SKM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    CU(cudaStreamSynchronize(c->stream));
+    int32_t rc0 = sync_all(c);
+    if (rc0) return rc0;
     collect_spans(c);
     out->h2d = c->stage_ms[ST_H2D];
     out->pack = c->stage_ms[ST_PACK];

@@ -481,6 +481,13 @@ struct RunDesc {
     unsigned long long tile_begin;   // index of this run's first warp tile
 };
 
+// Run descriptors reach the device through a kernel that reads them from pinned host memory:
+// a cudaMemcpy would queue on the host-to-device copy engine BEHIND the read batches still in
+// flight, and the first insert could not start until every batch had arrived.
+__global__ void copy_descs_kernel(const RunDesc *__restrict__ src, RunDesc *__restrict__ dst, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 // Persistent kernel: every WARP pulls the next 512-k-mer tile from a global counter, so there is
 // no CTA-wide barrier inside the loop (ncu on the one-tile-per-CTA version: 25-30 % of issue
 // slots stalled on barriers because probe latencies differ between warps) and tiles are still
