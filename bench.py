@@ -49,6 +49,10 @@ DISTINCT_HINT_PER_GPU = 320_000_000
 CPU_SAMPLE_READS = 300_000
 B_ALG_PER_KMER = 64.0      # 32 B sector in + 32 B sector out per k-mer occurrence
 B_ALG_PER_BASE = 0.375     # packed stream read by the extract kernels: 2-bit code + 1-bit break mask
+# DRAM bytes per k-mer of the dominant kernel from the committed `ncu --set full` captures
+# (profiles/r01_insert_kernel_full.csv: 6.62 GB read + 2.31 GB written for 1.24e8 k-mers;
+#  profiles/r01_direct_kernel_full.csv: 12.2 + 3.0 GB for 1.27e8 k-mers)
+NCU_DRAM_BYTES_PER_KMER = {"insert_runs_kernel": 70.4, "extract_insert_kernel": 119.7}
 
 
 def load_peaks():
@@ -334,6 +338,7 @@ def run_ours(args):
         if stt.insert_bases == 0:  # partitioned: the insert kernel reads the 8-byte k-mer list instead
             alg_bytes_per_launch = n_kmers_local * (B_ALG_PER_KMER + 8.0) / n_ins
         achieved = alg_bytes_per_launch / (ins_ms_per_launch * 1e-3) / 1e9
+        kernel_name = "extract_insert_kernel" if stt.insert_bases else "insert_runs_kernel"
         out = {
             "metric": "kmers_counted_per_sec", "value": value, "unit": "kmers/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
@@ -347,11 +352,15 @@ def run_ours(args):
                          "histogram": stt.histogram, "grow": stt.grow, "finalize": stt.total_finalize},
             "table": {"slots": int(stt.table_capacity), "bytes": int(stt.table_bytes),
                       "load": float(tot.n_unique) / float(stt.table_capacity), "grows": int(stt.n_grows)},
-            "roofline": {"bound": "hbm", "kernel": "extract_insert_kernel" if stt.insert_bases else "insert_runs_kernel",
+            "roofline": {"bound": "hbm", "kernel": kernel_name,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": NCU_DRAM_BYTES_PER_KMER[kernel_name] * n_kmers_local / n_ins,
+                         "traffic_note": "bytes per launch = DRAM read+write per k-mer from the committed ncu --set full "
+                                         "capture of this kernel (profiles/) x k-mers per launch in this run",
+                         "peak_source": peak_src,
                          "launches_per_step": int(n_ins), "ms_per_launch": ins_ms_per_launch,
-                         "algorithmic_bytes": "64 B per k-mer occurrence (sector in + sector out) + 0.375 B per packed base read",
+                         "algorithmic_bytes": "64 B per k-mer occurrence (32 B sector in + 32 B sector out) + 8 B list read "
+                                              "(partitioned) or + 0.375 B per packed base (direct)",
                          "kmers_per_sec_in_kernel": n_kmers_local / (stt.insert * 1e-3)},
             "gpu_launches": int(stt.kernel_launches) * args.steps,
             "nvlink_bytes_sent_per_step_rank0": (sharded.bytes_sent // max(1, (args.steps + args.warmup) * (1 if args.no_e2e else 2))) if sharded else 0,

@@ -176,12 +176,22 @@ int32_t skm_insert_counts(skm_ctx *ctx, const uint64_t *keys, const uint32_t *co
  * are contiguous, so the all-to-all sends contiguous ranges, and every received run is already
  * ordered by the receiver's table regions.
  *   skm_route_count   extracts the canonical k-mers and counts them per bucket
- *                     (bucket_counts[n_ranks * R]); synchronous.
+ *                     (bucket_counts[n_ranks * R]); synchronous; runs on the routing stream.
  *   skm_route_scatter writes them into d_out (device memory, sum(bucket_counts) entries) in bucket
- *                     order and drops the chunk's staged reads; asynchronous on the ctx's stream. */
+ *                     order and drops the chunk's staged reads; asynchronous on the routing stream. */
 int32_t skm_route_regions(skm_ctx *ctx, uint32_t *regions_per_rank);
+/* The ctx's CUDA streams as cudaStream_t handles: which = 0 main (inserts, histograms; the stream
+ * given in skm_params if any), 1 = routing stream (pack, bucketing, skm_route_*).  A multi-GPU
+ * driver issues its collectives on the routing stream and orders the insert of chunk c after the
+ * exchange of chunk c with an event, so that routing chunk c+1 overlaps inserting chunk c. */
+int32_t skm_stream_handle(skm_ctx *ctx, uint32_t which, uint64_t *out);
 int32_t skm_route_count(skm_ctx *ctx, uint32_t chunk_index, uint64_t *bucket_counts /* n_ranks * R */);
 int32_t skm_route_scatter(skm_ctx *ctx, uint32_t chunk_index, uint64_t *d_out);
+/* Asynchronous form of skm_route_count: the counts stay in device memory (*d_counts, n_ranks * R
+ * u64, valid until the next route count) so that the driver can all-gather them without a host
+ * round trip; skm_route_set_counts then hands the host copy back before skm_route_scatter_p2p. */
+int32_t skm_route_count_device(skm_ctx *ctx, uint32_t chunk_index, uint64_t **d_counts);
+int32_t skm_route_set_counts(skm_ctx *ctx, uint32_t chunk_index, const uint64_t *bucket_counts);
 /* Insert what the all-to-all delivered: d_kmers holds n_src blocks (one per source rank, in rank
  * order), block s = `regions` runs with lengths run_counts[s * regions + r].  Runs are inserted
  * region by region across all sources (L2-resident table regions); asynchronous on the stream. */
@@ -195,7 +205,7 @@ int32_t skm_insert_runs_device(skm_ctx *ctx, const uint64_t *d_kmers, const uint
  *   skm_p2p_open_peer      maps a peer's arena from its handle (other process, same node)
  *   skm_p2p_set_peer       same, from a raw device pointer (peer ctx in the same process)
  *   skm_route_scatter_p2p  after skm_route_count(chunk): writes rank d's buckets at element
- *                          offset dst_offsets[d] of rank d's arena `slot`; asynchronous.
+ *                          offset dst_offsets[d] of rank d's arena `slot`; asynchronous (routing stream).
  * The caller orders the steps with a stream-ordered barrier (a 1-element all-reduce): all ranks
  * scatter(c) -> barrier -> insert(c) from their own arena (skm_insert_runs_device on
  * skm_p2p_arena_ptr).  With two slots, a slot is rewritten only after the barrier that follows the

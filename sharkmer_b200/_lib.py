@@ -66,9 +66,12 @@ SYMBOLS = {
     "skm_lookup_batch": (_i32, [_vp, _vp, _u64, _u32, _i32, _vp, _vp]),
     "skm_scan_oligos": (_i32, [_vp, _vp, _u64, _u32, _u32, _vp, _vp, _u64, C.POINTER(_u64)]),
     "skm_insert_counts": (_i32, [_vp, _vp, _vp, _u64]),
+    "skm_stream_handle": (_i32, [_vp, _u32, C.POINTER(_u64)]),
     "skm_route_regions": (_i32, [_vp, C.POINTER(_u32)]),
     "skm_route_count": (_i32, [_vp, _u32, _vp]),
     "skm_route_scatter": (_i32, [_vp, _u32, _vp]),
+    "skm_route_count_device": (_i32, [_vp, _u32, C.POINTER(_vp)]),
+    "skm_route_set_counts": (_i32, [_vp, _u32, _vp]),
     "skm_p2p_arena_create": (_i32, [_vp, _u64]),
     "skm_p2p_arena_handle": (_i32, [_vp, _u32, _vp]),
     "skm_p2p_arena_ptr": (_i32, [_vp, _u32, C.POINTER(_vp)]),

@@ -220,6 +220,14 @@ void collect_spans(skm_ctx *c) {
     c->spans.clear();
 }
 
+// zero `bytes` (a multiple of 8) of device memory with a kernel, never a copy engine
+void zero_async(skm_ctx *c, void *p, size_t bytes, cudaStream_t st) {
+    const uint64_t words = bytes / 8;
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((words + 255) / 256, 1024));
+    zero_kernel<<<grid, 256, 0, st>>>((unsigned long long *)p, words);
+    c->launches++;
+}
+
 TableRef tref(const skm_ctx *c) { return TableRef{c->table, c->log2cap, c->n_ranks}; }
 
 uint32_t ceil_log2(uint64_t v) {
@@ -369,7 +377,7 @@ int32_t sync_all(skm_ctx *c) {
 int32_t bucket_count(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn fn, uint32_t n_buckets,
                      uint64_t *total_out, uint64_t *h_counts) {
     const ChunkState &cs = c->chunks[chunk];
-    CU(cudaMemsetAsync(c->d_bucket_counts, 0, (n_buckets + 1) * sizeof(uint64_t), c->work));
+    zero_async(c, c->d_bucket_counts, (n_buckets + 1) * sizeof(uint64_t), c->work);
     {
         Span sp(c, ST_COUNT, c->work);
         for (size_t s = s0; s < s1; s++) {
@@ -435,7 +443,7 @@ void launch_insert_runs(skm_ctx *c, uint64_t n_tiles, const RunDesc *descs, uint
     uint64_t want = (n_tiles + 7) / 8;
     const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->sm_count * c->insert_ctas_per_sm));
     unsigned long long *counter = &c->d_gc->scratch[0];
-    cudaMemsetAsync(counter, 0, sizeof(unsigned long long), c->stream);
+    zero_async(c, counter, sizeof(unsigned long long), c->stream);
     switch (c->pipe_depth) {
     case 2: if (h) SKM_LAUNCH_RUNS(2, true); else SKM_LAUNCH_RUNS(2, false); break;
     case 4: if (h) SKM_LAUNCH_RUNS(4, true); else SKM_LAUNCH_RUNS(4, false); break;
@@ -589,8 +597,8 @@ int32_t insert_chunk_partitioned(skm_ctx *c, uint32_t chunk) {
 // One streaming pass over the table: histogram + totals (+ digest).  Synchronous.
 int32_t scan_table(skm_ctx *c, bool want_digest, std::vector<uint64_t> *bins_out) {
     const uint64_t nb = c->p.histo_max + 2;
-    CU(cudaMemsetAsync(c->d_bins, 0, nb * sizeof(uint64_t), c->stream));
-    CU(cudaMemsetAsync(c->d_tot, 0, sizeof(HistoTotals), c->stream));
+    zero_async(c, c->d_bins, nb * sizeof(uint64_t), c->stream);
+    zero_async(c, c->d_tot, sizeof(HistoTotals), c->stream);
     const uint32_t n_smem_bins = (uint32_t)std::min<uint64_t>(nb, 12288);
     const size_t smem = (kLowBins * 32 + n_smem_bins) * sizeof(uint32_t);
     {
@@ -694,6 +702,10 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index) {
     const uint32_t nb = 1u << fn.log2_regions;
     uint64_t *h_off = alloc_offsets(c, nb + 1);
     if (!h_off) return SKM_OK;
+    // the pack kernel ran on another stream (the copy stream): order the bucketing after it.  Only
+    // here — a wait queued for a batch that is NOT bucketed now would make everything later on this
+    // stream (e.g. the routing of chunk 0) wait for the arrival of the LAST batch.
+    CU(cudaStreamWaitEvent(c->work, sg.ready, 0));
     if (cudaMallocAsync((void **)&sg.list, need, c->work) != cudaSuccess) {
         cudaGetLastError();
         sg.list = nullptr;
@@ -715,32 +727,35 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index) {
 }
 
 // Stage one batch that is already in device memory.
+// Pack one batch that is in device memory, on `pack_stream` (the copy stream for host batches, so
+// the pack follows its own copy and nothing else), then bucket it eagerly on c->work.
 int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t n_bytes,
-                     cudaEvent_t packed_event = nullptr) {
+                     cudaStream_t pack_stream = nullptr) {
     if (n_bytes == 0) return SKM_OK;
+    if (!pack_stream) pack_stream = c->work;
     Segment sg;
     sg.n_bytes = n_bytes;
     sg.n_units = (n_bytes + 31) / 32;
-    CU(cudaMallocAsync((void **)&sg.codes, sg.n_units * sizeof(uint64_t), c->work));
-    CU(cudaMallocAsync((void **)&sg.breaks, sg.n_units * sizeof(uint32_t), c->work));
+    CU(cudaMallocAsync((void **)&sg.codes, sg.n_units * sizeof(uint64_t), pack_stream));
+    CU(cudaMallocAsync((void **)&sg.breaks, sg.n_units * sizeof(uint32_t), pack_stream));
     {
-        Span sp(c, ST_PACK, c->work);
-        pack_kernel<<<grid_for(sg.n_units, 256 * kPackUnits), 256, 0, c->work>>>(d_seqs, n_bytes, c->pos_base, sg.codes,
-                                                                      sg.breaks, sg.n_units, &c->d_cc[chunk],
-                                                                      c->d_gc);
+        Span sp(c, ST_PACK, pack_stream);
+        pack_kernel<<<grid_for(sg.n_units, 256 * kPackUnits), 256, 0, pack_stream>>>(
+            d_seqs, n_bytes, c->pos_base, sg.codes, sg.breaks, sg.n_units, &c->d_cc[chunk], c->d_gc);
         c->launches++;
         c->stage_launches[ST_PACK]++;
     }
     CU(cudaGetLastError());
-    if (packed_event) CU(cudaEventRecord(packed_event, c->work));  // the raw buffer may be overwritten now
+    sg.ready = get_event(c);
+    CU(cudaEventRecord(sg.ready, pack_stream));  // packed: the raw buffer may be overwritten, the codes read
     c->pos_base += n_bytes;
     c->chunks[chunk].segs.push_back(sg);
     c->chunks[chunk].n_bytes += n_bytes;
-    int32_t rc = eager_partition(c, chunk, c->chunks[chunk].segs.size() - 1);
+    const size_t idx = c->chunks[chunk].segs.size() - 1;
+    int32_t rc = eager_partition(c, chunk, idx);
     if (rc) return rc;
-    Segment &seg = c->chunks[chunk].segs.back();
-    seg.ready = get_event(c);
-    CU(cudaEventRecord(seg.ready, c->work));
+    Segment &seg = c->chunks[chunk].segs[idx];
+    if (seg.list) CU(cudaEventRecord(seg.ready, c->work));  // bucketed: `ready` now also covers the list + offsets
     return SKM_OK;
 }
 
@@ -974,8 +989,9 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
     DeviceGuard g(c->device);
     // The copy runs on its own stream, into a ring of persistent raw buffers, so that it overlaps
     // the kernels of earlier batches (a buffer is reused once its pack kernel has finished):
-    //   copy: wait [packed(b)] -> H2D -> [copied(b)]
-    //   main:                    wait [copied(b)] -> pack -> [packed(b)] -> (bucket)
+    //   copy stream   : H2D(b) -> pack(b) -> [ready]  -> H2D(b+1) -> ...
+    //   routing stream:                      wait [ready] -> bucket(b)
+    //   main stream   : inserts (skm_finalize)
     const uint32_t b = c->raw_next++ % 3;
     if (!c->raw_copied[b]) {
         CU(cudaEventCreateWithFlags(&c->raw_copied[b], cudaEventDisableTiming));
@@ -983,7 +999,7 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
     }
     if (c->raw_cap[b] < n_bytes) {
         if (c->raw_buf[b]) {
-            CU(cudaEventSynchronize(c->raw_packed[b]));
+            CU(cudaStreamSynchronize(c->copy_stream));
             CU(cudaFree(c->raw_buf[b]));
             c->raw_buf[b] = nullptr;
             c->raw_cap[b] = 0;
@@ -991,18 +1007,17 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
         const size_t cap = std::max<size_t>(n_bytes, 1 << 20);
         CU(cudaMalloc((void **)&c->raw_buf[b], cap));
         c->raw_cap[b] = cap;
-    } else {
-        CU(cudaStreamWaitEvent(c->copy_stream, c->raw_packed[b], 0));
     }
     {
         Span sp(c, ST_H2D, c->copy_stream);
         CU(cudaMemcpyAsync(c->raw_buf[b], seqs, n_bytes, cudaMemcpyHostToDevice, c->copy_stream));
     }
     CU(cudaEventRecord(c->raw_copied[b], c->copy_stream));
-    if (!(flags & SKM_INGEST_ASYNC)) CU(cudaStreamSynchronize(c->copy_stream));
-    CU(cudaStreamWaitEvent(c->part_stream, c->raw_copied[b], 0));
+    if (!(flags & SKM_INGEST_ASYNC)) CU(cudaEventSynchronize(c->raw_copied[b]));
+    // the pack kernel follows its copy on the copy stream (so the ring buffer is reused in stream
+    // order); bucketing runs on the routing stream once the pack has fired
     WorkStream ws(c, c->part_stream);
-    rc = stage_device(c, chunk, c->raw_buf[b], n_bytes, c->raw_packed[b]);
+    rc = stage_device(c, chunk, c->raw_buf[b], n_bytes, c->copy_stream);
     return rc;
 }
 
@@ -1068,6 +1083,12 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
     bool any = false;
     for (auto &cs : c->chunks) any = any || !cs.segs.empty();
     int32_t rc;
+    if (any && !run_chunk_loop) {
+        // multi-GPU driver takes over: routing runs on the same stream as the pack kernels, so it
+        // is ordered after them without waiting here; errors surface at the driver's final skm_sync
+        c->finalized = true;
+        return SKM_OK;
+    }
     if (!any || !run_chunk_loop) {
         // nothing to overlap: wait for the ingest streams, then report errors / hand over
         rc = sync_all(c);
@@ -1530,6 +1551,12 @@ static BucketFn route_fn(const skm_ctx *c) {
     return fn;
 }
 
+int32_t skm_stream_handle(skm_ctx *c, uint32_t which, uint64_t *out) {
+    if (!c || !out || which > 1) return SKM_ERR_INVALID_ARG;
+    *out = (uint64_t)(uintptr_t)(which == 0 ? c->stream : c->part_stream);
+    return SKM_OK;
+}
+
 int32_t skm_route_regions(skm_ctx *c, uint32_t *regions_per_rank) {
     if (!c || !regions_per_rank) return SKM_ERR_INVALID_ARG;
     *regions_per_rank = 1u << route_log2_regions(c);
@@ -1541,8 +1568,11 @@ int32_t skm_route_count(skm_ctx *c, uint32_t chunk, uint64_t *bucket_counts) {
     if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
+    WorkStream ws(c, c->part_stream);  // routing overlaps the inserts of the previous chunk (main stream)
     ChunkState &cs = c->chunks[chunk];
     if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
+    for (auto &sg : cs.segs)  // this chunk's pack kernels (copy stream) must have fired; later chunks may still be arriving
+        if (sg.ready) CU(cudaStreamWaitEvent(c->part_stream, sg.ready, 0));
     uint64_t total = 0;
     const BucketFn fn = route_fn(c);
     const uint32_t nb = c->n_ranks << fn.log2_regions;
@@ -1553,11 +1583,39 @@ int32_t skm_route_count(skm_ctx *c, uint32_t chunk, uint64_t *bucket_counts) {
     return SKM_OK;
 }
 
+int32_t skm_route_count_device(skm_ctx *c, uint32_t chunk, uint64_t **d_counts) {
+    if (!c || !d_counts) return SKM_ERR_INVALID_ARG;
+    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    WorkStream ws(c, c->part_stream);
+    ChunkState &cs = c->chunks[chunk];
+    if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
+    for (auto &sg : cs.segs)  // this chunk's pack kernels (copy stream) must have fired; later chunks may still be arriving
+        if (sg.ready) CU(cudaStreamWaitEvent(c->part_stream, sg.ready, 0));
+    const BucketFn fn = route_fn(c);
+    int32_t rc = bucket_count(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions, nullptr, nullptr);
+    if (rc) return rc;
+    *d_counts = (uint64_t *)c->d_bucket_counts;  // valid until the next route count on this ctx
+    c->route_counts_chunk = 0xFFFFFFFFu;
+    return SKM_OK;  // asynchronous (routing stream)
+}
+
+int32_t skm_route_set_counts(skm_ctx *c, uint32_t chunk, const uint64_t *bucket_counts) {
+    if (!c || !bucket_counts) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const uint32_t nb = c->n_ranks << route_log2_regions(c);
+    c->route_counts.assign(bucket_counts, bucket_counts + nb);
+    c->route_counts_chunk = chunk;
+    return SKM_OK;
+}
+
 int32_t skm_route_scatter(skm_ctx *c, uint32_t chunk, uint64_t *d_out) {
     if (!c) return SKM_ERR_INVALID_ARG;
     if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
+    WorkStream ws(c, c->part_stream);  // routing overlaps the inserts of the previous chunk (main stream)
     ChunkState &cs = c->chunks[chunk];
     if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
     const BucketFn fn = route_fn(c);
@@ -1565,8 +1623,8 @@ int32_t skm_route_scatter(skm_ctx *c, uint32_t chunk, uint64_t *d_out) {
                                 (unsigned long long *)d_out);
     if (rc) return rc;
     for (auto &sg : cs.segs) {
-        CU(cudaFreeAsync(sg.codes, c->stream));
-        CU(cudaFreeAsync(sg.breaks, c->stream));
+        CU(cudaFreeAsync(sg.codes, c->work));
+        CU(cudaFreeAsync(sg.breaks, c->work));
         sg.codes = nullptr;
         sg.breaks = nullptr;
     }
@@ -1635,6 +1693,7 @@ int32_t skm_route_scatter_p2p(skm_ctx *c, uint32_t chunk, uint32_t slot, const u
     if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
+    WorkStream ws(c, c->part_stream);  // routing overlaps the inserts of the previous chunk (main stream)
     ChunkState &cs = c->chunks[chunk];
     if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
     if (c->route_counts_chunk != chunk) return fail(c, SKM_ERR_STATE, "call skm_route_count for chunk %u first", chunk);
@@ -1657,8 +1716,8 @@ int32_t skm_route_scatter_p2p(skm_ctx *c, uint32_t chunk, uint32_t slot, const u
     int32_t rc = bucket_scatter(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions, nullptr, &bases);
     if (rc) return rc;
     for (auto &sg : cs.segs) {
-        CU(cudaFreeAsync(sg.codes, c->stream));
-        CU(cudaFreeAsync(sg.breaks, c->stream));
+        CU(cudaFreeAsync(sg.codes, c->work));
+        CU(cudaFreeAsync(sg.breaks, c->work));
         sg.codes = nullptr;
         sg.breaks = nullptr;
     }

@@ -481,6 +481,15 @@ struct RunDesc {
     unsigned long long tile_begin;   // index of this run's first warp tile
 };
 
+// Zero-fill by kernel.  cudaMemsetAsync may be serviced by a copy engine, where it queues behind
+// host-to-device batches already submitted (measured: a routing pass submitted after ten 151 MB
+// copies did not start until the last copy had finished).
+__global__ void zero_kernel(unsigned long long *__restrict__ p, uint64_t n_words) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = 0ull;
+}
+
 // Run descriptors reach the device through a kernel that reads them from pinned host memory:
 // a cudaMemcpy would queue on the host-to-device copy engine BEHIND the read batches still in
 // flight, and the first insert could not start until every batch had arrived.

@@ -162,6 +162,12 @@ class Engine:
         self._ck(self.L.skm_insert_counts(self._h, k.ctypes.data, c.ctypes.data, k.size))
 
     # ---- multi-GPU building blocks --------------------------------------
+    def stream_handle(self, which: int) -> int:
+        """cudaStream_t of the main (0) or routing (1) stream."""
+        h = C.c_uint64()
+        self._ck(self.L.skm_stream_handle(self._h, which, C.byref(h)))
+        return h.value
+
     def route_regions(self) -> int:
         r = C.c_uint32()
         self._ck(self.L.skm_route_regions(self._h, C.byref(r)))
@@ -173,6 +179,15 @@ class Engine:
         counts = np.zeros((n_ranks, regions), dtype=np.uint64)
         self._ck(self.L.skm_route_count(self._h, chunk_index, counts.ctypes.data))
         return counts
+
+    def route_count_device(self, chunk_index: int) -> int:
+        p = C.c_void_p()
+        self._ck(self.L.skm_route_count_device(self._h, chunk_index, C.byref(p)))
+        return p.value
+
+    def route_set_counts(self, chunk_index: int, counts: np.ndarray):
+        cc = np.ascontiguousarray(counts, dtype=np.uint64)
+        self._ck(self.L.skm_route_set_counts(self._h, chunk_index, cc.ctypes.data))
 
     def insert_runs_device(self, d_ptr: int, run_counts: np.ndarray):
         """run_counts: shape (n_src, regions) — what each source rank sent, per table region."""

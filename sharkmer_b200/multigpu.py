@@ -31,6 +31,16 @@ import torch
 import torch.distributed as dist
 
 
+class _CudaArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+
+def _device_i64(ptr: int, n: int, device) -> torch.Tensor:
+    """Zero-copy int64 view of n u64 values at a raw device pointer."""
+    return torch.as_tensor(_CudaArray(ptr, n), device=device)
+
+
 class ShardedCounter:
     def __init__(self, engine, n_chunks: int, chunks_arg: int, histo_max: int, device: torch.device,
                  group=None, stream=None, exchange: str = "nccl", arena_entries: int = 0):
@@ -61,6 +71,7 @@ class ShardedCounter:
                 for slot in range(2):
                     e.p2p_open_peer(r, slot, allh[r][slot])
         self._tick = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._regions = e.route_regions()
 
     # -- small helpers ---------------------------------------------------------
     def _exchange_counts(self, counts: np.ndarray) -> np.ndarray:
@@ -87,38 +98,73 @@ class ShardedCounter:
     def finalize(self) -> np.ndarray | None:
         """Counts every chunk in order.  Returns the (n_chunks, histo_max+2) cumulative
         histogram columns summed over ranks (None when chunks == 0)."""
-        # Everything below is issued with the engine's stream current: tensors are allocated on
-        # it, collectives are ordered after the kernels already queued on it, and work.wait()
-        # makes it (not the default stream) wait for the collective.
+        # Issued with the engine's main stream current: tensors are allocated on it and the final
+        # all-reduce is ordered after the inserts.
         with self._on_stream():
-            return self._finalize()
+            out = self._finalize()
+        self.e.sync()  # waits for every stream; raises if a pack kernel met an invalid base
+        return out
 
     def _finalize(self):
         if self.exchange == "p2p":
             return self._finalize_p2p()
         return self._finalize_nccl()
 
+    def _streams(self):
+        """(main, routing) torch streams wrapping the engine's CUDA streams; None on CPU."""
+        if self.stream is None:
+            return None, None
+        main = torch.cuda.ExternalStream(self.e.stream_handle(0), device=self.device)
+        part = torch.cuda.ExternalStream(self.e.stream_handle(1), device=self.device)
+        return main, part
+
     def _finalize_p2p(self):
+        """Software pipeline: chunk c+1 is routed (extract + bucket + peer stores + barrier, routing
+        stream) while chunk c is inserted (main stream)."""
         e = self.e
         e.finalize_external()
-        for c in range(self.n_chunks):
+        main, part = self._streams()
+
+        def route(c, prev_insert_done):
             slot = c & 1
-            counts = e.route_count(c, self.world)            # (world, regions)
-            rcounts = self._exchange_counts(counts)          # (world, regions): per source and region
-            per_dst = counts.sum(axis=1).astype(np.int64)
-            # where this rank's block starts in every destination's arena: after the blocks of lower ranks
-            allt = torch.empty(self.world * self.world, dtype=torch.int64, device=self.device)
-            dist.all_gather_into_tensor(allt, torch.as_tensor(per_dst, device=self.device), group=self.group)
-            m = allt.cpu().numpy().reshape(self.world, self.world)   # m[s, d] = k-mers s sends to d
-            dst_offsets = m[:self.rank, :].sum(axis=0)
-            need = int(m[:, self.rank].sum())
-            e.route_scatter_p2p(c, slot, dst_offsets)        # fused: extract + bucket + peer stores
-            dist.all_reduce(self._tick, group=self.group)    # stream-ordered barrier: every rank's stores landed
-            e.insert_runs_device(e.p2p_arena_ptr(slot), rcounts)
+            with torch.cuda.stream(part):
+                # per-(destination, region) counts of this rank's k-mers, left on the device and
+                # all-gathered from there: one collective and one host sync per chunk
+                d_counts = e.route_count_device(c)
+                mine = _device_i64(d_counts, self.world * self._regions, self.device)
+                allt = torch.empty(self.world * self.world * self._regions, dtype=torch.int64, device=self.device)
+                dist.all_gather_into_tensor(allt, mine, group=self.group)
+                allc = allt.cpu().numpy().reshape(self.world, self.world, self._regions)  # [src, dst, region]
+                counts = allc[self.rank].astype(np.uint64)
+                rcounts = np.ascontiguousarray(allc[:, self.rank, :]).astype(np.uint64)
+                m = allc.sum(axis=2)                              # m[s, d] = k-mers s sends to d
+                per_dst = m[self.rank]
+                e.route_set_counts(c, counts)
+                # this rank's block in every destination's arena starts after the lower ranks' blocks
+                e.route_scatter_p2p(c, slot, m[:self.rank, :].sum(axis=0))  # fused: extract + bucket + peer stores
+                # Barrier c tells the peers two things: (1) my stores of chunk c have landed, and
+                # (2) my insert of chunk c-1 is finished, so after this barrier they may overwrite
+                # the other arena slot (their scatter of chunk c+1).
+                if prev_insert_done is not None:
+                    part.wait_event(prev_insert_done)
+                dist.all_reduce(self._tick, group=self.group)    # stream-ordered barrier
+                done = torch.cuda.Event()
+                done.record(part)
             self.bytes_sent += 8 * (int(per_dst.sum()) - int(per_dst[self.rank]))
-            self.kmers_received += need
+            self.kmers_received += int(m[:, self.rank].sum())
+            return slot, rcounts, done
+
+        nxt = route(0, None)
+        for c in range(self.n_chunks):
+            slot, rcounts, done = nxt
+            main.wait_event(done)
+            e.insert_runs_device(e.p2p_arena_ptr(slot), rcounts)     # asynchronous, main stream
+            inserted = torch.cuda.Event()
+            inserted.record(main)
+            if c + 1 < self.n_chunks:
+                nxt = route(c + 1, inserted)                      # overlaps the insert just queued
             if self.chunks_arg > 0:
-                e.snapshot_histogram(c)
+                e.snapshot_histogram(c)                          # syncs the main stream
             else:
                 e.sync()
         if self.chunks_arg == 0:
@@ -129,37 +175,47 @@ class ShardedCounter:
         return t.cpu().numpy().astype(np.uint64)
 
     def _finalize_nccl(self):
+        """Route to a local list, all_to_all_single, insert.  On GPUs the routing + collective of
+        chunk c+1 run on the routing stream while chunk c is inserted on the main stream."""
+        import contextlib
         e = self.e
         e.finalize_external()  # ingest is complete on every rank; the chunk loop is ours
+        main, part = self._streams()
+        on_part = (lambda: torch.cuda.stream(part)) if part is not None else contextlib.nullcontext
 
-        def launch_exchange(c):
-            counts = e.route_count(c, self.world)            # (world, regions): per destination and region
-            rcounts = self._exchange_counts(counts)          # (world, regions): per source and region
-            per_dst, per_src = counts.sum(axis=1), rcounts.sum(axis=1)
-            n_send, n_recv = int(per_dst.sum()), int(per_src.sum())
-            send, recv = self._alloc(n_send), self._alloc(n_recv)
-            e.route_scatter(c, self._ptr(send))              # bucket order = destination-major (engine stream)
-            work = dist.all_to_all_single(recv[:n_recv], send[:n_send],
-                                          output_split_sizes=[int(x) for x in per_src],
-                                          input_split_sizes=[int(x) for x in per_dst],
-                                          group=self.group, async_op=True)
+        def route(c):
+            with on_part():
+                counts = e.route_count(c, self.world)            # (world, regions): per destination and region
+                rcounts = self._exchange_counts(counts)          # (world, regions): per source and region
+                per_dst, per_src = counts.sum(axis=1), rcounts.sum(axis=1)
+                n_send, n_recv = int(per_dst.sum()), int(per_src.sum())
+                send, recv = self._alloc(n_send), self._alloc(n_recv)
+                e.route_scatter(c, self._ptr(send))              # bucket order = destination-major
+                dist.all_to_all_single(recv[:n_recv], send[:n_send],
+                                       output_split_sizes=[int(x) for x in per_src],
+                                       input_split_sizes=[int(x) for x in per_dst], group=self.group)
+                done = None
+                if part is not None:
+                    done = torch.cuda.Event()
+                    done.record(part)
+                    recv.record_stream(main)                     # consumed by the insert on the main stream
             self.bytes_sent += 8 * (n_send - int(per_dst[self.rank]))
             self.kmers_received += n_recv
-            return work, send, recv, rcounts, c
+            return recv, rcounts, done
 
-        pending = launch_exchange(0)
+        nxt = route(0)
         for c in range(self.n_chunks):
-            work, send, recv, rcounts, cc = pending
-            # start routing the next chunk while this chunk's k-mers are in flight
-            nxt = launch_exchange(c + 1) if c + 1 < self.n_chunks else None
-            work.wait()                                       # engine stream waits for the collective
-            e.insert_runs_device(self._ptr(recv), rcounts)   # region-major over all sources' runs
+            recv, rcounts, done = nxt
+            if done is not None:
+                main.wait_event(done)
+            e.insert_runs_device(self._ptr(recv), rcounts)       # region-major over all sources' runs
+            if c + 1 < self.n_chunks:
+                nxt = route(c + 1)                                # overlaps the insert just queued
             if self.chunks_arg > 0:
-                e.snapshot_histogram(cc)                      # this rank's partial column (syncs the stream)
+                e.snapshot_histogram(c)                          # this rank's partial column (syncs main)
             else:
                 e.sync()
-            del send, recv
-            pending = nxt
+            del recv
         if self.chunks_arg == 0:
             return None
         cols = np.stack([e.histogram(c) for c in range(self.n_chunks)]).astype(np.int64)

@@ -85,3 +85,46 @@ def test_product_never_imports_oracle():
                     if re.search(r"liboracle|skm_oracle|from oracle|import oracle|orc_", txt):
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_python_mirror_of_skm_common_matches_the_header(tmp_path):
+    """sharkmer_b200/common.py must stay bit-identical to include/skm_common.h (hash, owner rank,
+    local hash, home slot, digest, revcomp, routing bucket)."""
+    import random
+    import subprocess
+    from sharkmer_b200 import common
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include "skm_common.h"
+int main(int argc, char **argv) {
+    unsigned long long x; unsigned n, k, l2;
+    while (scanf("%llu %u %u %u", &x, &n, &k, &l2) == 4) {
+        uint64_t h = skm_hash_kmer(x);
+        uint64_t lh = skm_local_hash(h, n);
+        uint32_t owner = skm_owner_rank(h, n);
+        uint32_t bucket = (owner << l2) | (l2 ? (uint32_t)(lh >> (64 - l2)) : 0);
+        printf("%llu %u %llu %llu %llu %llu %u\n", (unsigned long long)h, owner, (unsigned long long)lh,
+               (unsigned long long)skm_home_slot(lh, 29), (unsigned long long)skm_pair_digest(x, k),
+               (unsigned long long)skm_revcomp_kmer(x & ((1ull << (2 * k)) - 1), k), bucket);
+    }
+    return 0;
+}
+''')
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-O1", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    rng = random.Random(3)
+    cases = [(rng.getrandbits(62), rng.choice([1, 2, 3, 7, 8, 16]), rng.randint(1, 31), rng.choice([0, 3, 7, 10]))
+             for _ in range(500)]
+    out = subprocess.run([str(exe)], input="".join(f"{x} {n} {k} {l2}\n" for x, n, k, l2 in cases),
+                         capture_output=True, text=True, check=True).stdout.split("\n")
+    for (x, n, k, l2), line in zip(cases, out):
+        h, owner, lh, home, dig, rc, bucket = map(int, line.split())
+        assert common.hash_kmer(x) == h
+        assert common.owner_rank(h, n) == owner and owner < n
+        assert common.local_hash(h, n) == lh
+        assert common.home_slot(lh, 29) == home
+        assert common.pair_digest(x, k) == dig
+        assert common.revcomp_kmer(x & ((1 << (2 * k)) - 1), k) == rc
+        assert common.route_bucket(x, n, l2) == bucket
