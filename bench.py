@@ -433,7 +433,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--gups", action="store_true", help="also measure the random-access roofline probe")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "dma", "nccl"],
                     help="multi-GPU exchange: fused peer-store scatter over NVLink (p2p) or NCCL all-to-all")
     ap.add_argument("--chunks", type=int, default=None, help="EXPERIMENT ONLY: override the workload's chunk count")
     ap.add_argument("--k", type=int, default=None, help="EXPERIMENT ONLY: override k")

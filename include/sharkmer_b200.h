@@ -217,6 +217,11 @@ int32_t skm_p2p_open_peer(skm_ctx *ctx, uint32_t peer_rank, uint32_t slot, const
 int32_t skm_p2p_set_peer(skm_ctx *ctx, uint32_t peer_rank, uint32_t slot, uint64_t *d_ptr);
 int32_t skm_route_scatter_p2p(skm_ctx *ctx, uint32_t chunk_index, uint32_t slot,
                               const uint64_t *dst_offsets /* n_ranks */);
+/* Same contract, but the k-mers are bucketed into a local list and pushed to the peers' arenas by
+ * the copy engines (one peer copy per destination): the NVLink transfer costs no SM time and
+ * overlaps the inserts of the previous chunk. */
+int32_t skm_route_scatter_dma(skm_ctx *ctx, uint32_t chunk_index, uint32_t slot,
+                              const uint64_t *dst_offsets /* n_ranks */);
 
 /* Insert `n` k-mers (device memory) that this rank owns; asynchronous on the ctx's stream. */
 int32_t skm_insert_kmers_device(skm_ctx *ctx, const uint64_t *d_kmers, uint64_t n);

@@ -78,6 +78,7 @@ SYMBOLS = {
     "skm_p2p_open_peer": (_i32, [_vp, _u32, _u32, _vp]),
     "skm_p2p_set_peer": (_i32, [_vp, _u32, _u32, _vp]),
     "skm_route_scatter_p2p": (_i32, [_vp, _u32, _u32, _vp]),
+    "skm_route_scatter_dma": (_i32, [_vp, _u32, _u32, _vp]),
     "skm_insert_kmers_device": (_i32, [_vp, _vp, _u64]),
     "skm_insert_runs_device": (_i32, [_vp, _vp, _vp, _u32, _u32]),
     "skm_snapshot_histogram": (_i32, [_vp, _u32]),

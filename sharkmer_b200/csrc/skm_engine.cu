@@ -25,7 +25,8 @@ using namespace skm;
 
 namespace {
 
-constexpr double kMaxLoad = 0.70;       // grow before the table is fuller than this
+constexpr double kMaxLoad = 0.70;       // grow once the exact load passes this
+constexpr double kHardLoad = 0.90;      // the host's upper bound on the load never passes this
 constexpr double kTargetLoad = 0.60;    // load at capacity_hint
 constexpr uint64_t kMinTile = 1ull << 22;  // k-mers; smallest tile worth a launch near the limit
 constexpr uint32_t kMinLog2Cap = 16;
@@ -69,6 +70,8 @@ struct skm_ctx {
     uint32_t n_ranks = 1;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t dma_stream = nullptr;   // peer copies of routed k-mers (copy engines)
+    cudaEvent_t ev_dma = nullptr;
     cudaStream_t part_stream = nullptr;  // pack + bucketing of incoming batches (overlaps inserts on `stream`)
     cudaStream_t work = nullptr;         // stream the bucketing helpers currently launch on
     cudaEvent_t ev_main = nullptr;
@@ -123,6 +126,15 @@ struct skm_ctx {
     bool peer_ipc[16][kP2PSlots] = {};
     std::vector<uint64_t> route_counts;  // bucket counts of the chunk last passed to skm_route_count
     uint32_t route_counts_chunk = 0xFFFFFFFFu;
+
+    // asynchronous snapshots of the device's occupied-slot counter
+    static constexpr uint32_t kSnapRing = 8;
+    uint64_t *h_snap = nullptr;  // pinned, kSnapRing entries
+    cudaEvent_t snap_event[kSnapRing] = {};
+    uint64_t snap_launched[kSnapRing] = {};
+    bool snap_pending[kSnapRing] = {};
+    uint32_t snap_next = 0;
+    uint64_t launched_total = 0;
 
     // run descriptors (pinned ring + device copy)
     RunDesc *h_desc = nullptr, *d_desc = nullptr;
@@ -275,28 +287,69 @@ int32_t grow_table(skm_ctx *c, uint32_t new_log2cap) {
     return SKM_OK;
 }
 
-// Make room for `want` more k-mers if possible; returns how many may be
-// inserted now without risking load > kMaxLoad (>= min(want, kMinTile)).
+// Occupancy bookkeeping without stalling the host.  The exact number of occupied slots lives on
+// the device; the host keeps an UPPER BOUND: the last count it has seen plus every k-mer launched
+// since.  After each insert launch a copy of the device counter is queued into a small pinned ring
+// (note_inserted); reserve_headroom picks up whichever copies have completed (event query, no
+// wait) before it falls back to a blocking read.
+void note_inserted(skm_ctx *c, uint64_t n) {
+    c->distinct_ub += n;
+    const uint32_t slot = c->snap_next++ % skm_ctx::kSnapRing;
+    if (!c->snap_event[slot]) cudaEventCreateWithFlags(&c->snap_event[slot], cudaEventDisableTiming);
+    cudaMemcpyAsync(&c->h_snap[slot], &c->d_gc->n_distinct, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
+    cudaEventRecord(c->snap_event[slot], c->stream);
+    c->snap_launched[slot] = c->launched_total += n;
+    c->snap_pending[slot] = true;
+}
+
+void absorb_snapshots(skm_ctx *c) {
+    for (uint32_t i = 0; i < skm_ctx::kSnapRing; i++) {
+        if (!c->snap_pending[i] || cudaEventQuery(c->snap_event[i]) != cudaSuccess) continue;
+        c->snap_pending[i] = false;
+        // occupied <= (count when this snapshot was taken) + (k-mers launched after it)
+        const uint64_t ub = c->h_snap[i] + (c->launched_total - c->snap_launched[i]);
+        if (ub < c->distinct_ub) c->distinct_ub = ub;
+    }
+}
+
+// Make room for `want` more k-mers; returns how many may be inserted now.  The table is sized for
+// load <= kTargetLoad and grown when the EXACT count passes kMaxLoad; the upper bound only has to
+// stay below kHardLoad (linear probing needs free slots to terminate).
 int32_t reserve_headroom(skm_ctx *c, uint64_t want, uint64_t *granted) {
-    auto headroom = [&]() -> uint64_t {
-        const uint64_t limit = (uint64_t)(kMaxLoad * (double)c->capacity);
+    auto headroom = [&](double load) -> uint64_t {
+        const uint64_t limit = (uint64_t)(load * (double)c->capacity);
         return limit > c->distinct_ub ? limit - c->distinct_ub : 0;
     };
     const uint64_t need = std::min(want, kMinTile);
-    if (headroom() < need) {
-        // the bound counts every inserted k-mer as new; tighten it with the real count
+    if (headroom(kHardLoad) < want) absorb_snapshots(c);
+    if (headroom(kHardLoad) < want) {
+        // the bound is too loose: get the real count (blocks until the queued inserts have finished)
         uint64_t d = 0;
         int32_t rc = read_distinct(c, &d);
         if (rc) return rc;
         c->distinct_ub = d;
-        if (headroom() < need) {
+        for (auto &p : c->snap_pending) p = false;
+        if (headroom(kMaxLoad) < need) {
             uint32_t nl = c->log2cap + 1;
             while ((uint64_t)(kTargetLoad * (double)(1ull << nl)) < d + need * 4) nl++;
             rc = grow_table(c, nl);
             if (rc) return rc;
         }
+        *granted = std::min(want, std::max(headroom(kMaxLoad), std::min(need, headroom(kHardLoad))));
+        return SKM_OK;
     }
-    *granted = std::min(want, headroom());
+    *granted = want;
+    return SKM_OK;
+}
+
+int32_t ensure_list_on(skm_ctx *c, uint64_t n, cudaStream_t st) {
+    if (n <= c->list_cap) return SKM_OK;
+    if (c->d_list) CU(cudaFreeAsync(c->d_list, st));
+    c->d_list = nullptr;
+    c->list_cap = 0;
+    const uint64_t cap = std::max<uint64_t>(n + n / 8, 1024);
+    CU(cudaMallocAsync((void **)&c->d_list, cap * sizeof(uint64_t), st));
+    c->list_cap = cap;
     return SKM_OK;
 }
 
@@ -338,7 +391,7 @@ int32_t insert_segment_direct(skm_ctx *c, const Segment &sg, uint32_t chunk) {
             c->insert_bases += std::min(tile_units * 32, sg.n_bytes - u * 32);
         }
         CU(cudaGetLastError());
-        c->distinct_ub += tile_units * 32;
+        note_inserted(c, tile_units * 32);
         u += tile_units;
     }
     return SKM_OK;
@@ -368,6 +421,7 @@ struct WorkStream {  // selects the stream the bucketing helpers launch on, for 
 int32_t sync_all(skm_ctx *c) {
     CU(cudaStreamSynchronize(c->copy_stream));
     CU(cudaStreamSynchronize(c->part_stream));
+    CU(cudaStreamSynchronize(c->dma_stream));
     CU(cudaStreamSynchronize(c->stream));
     return SKM_OK;
 }
@@ -473,7 +527,7 @@ int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_
             c->insert_kmers += granted;
         }
         CU(cudaGetLastError());
-        c->distinct_ub += granted;
+        note_inserted(c, granted);
         i += granted;
     }
     return SKM_OK;
@@ -505,7 +559,7 @@ int32_t launch_run_range(skm_ctx *c, std::vector<RunDesc> &runs, size_t i, size_
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->desc_event[slot], c->stream));
-    c->distinct_ub += total;
+    note_inserted(c, total);
     return SKM_OK;
 }
 
@@ -817,6 +871,9 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     }
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->part_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->dma_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_dma, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->ev_dma, c->dma_stream));
     CU(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     c->work = c->stream;
     if (const char *g = getenv("SKM_INSERT_CTAS")) c->insert_ctas_per_sm = std::max(1, atoi(g));
@@ -858,6 +915,7 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     CU(cudaMalloc((void **)&c->d_tot, sizeof(HistoTotals)));
     c->h_pinned_words = kMaxBuckets + 16;
     CU(cudaMallocHost((void **)&c->h_pinned, c->h_pinned_words * sizeof(uint64_t)));
+    CU(cudaMallocHost((void **)&c->h_snap, skm_ctx::kSnapRing * sizeof(uint64_t)));
     CU(cudaMallocHost((void **)&c->h_desc, (size_t)kDescRing * kMaxRuns * sizeof(RunDesc)));
     CU(cudaMalloc((void **)&c->d_desc, (size_t)kDescRing * kMaxRuns * sizeof(RunDesc)));
     CU(cudaMalloc((void **)&c->d_bucket_counts, (kMaxBuckets + 1) * sizeof(uint64_t)));
@@ -912,6 +970,8 @@ void skm_destroy(skm_ctx *c) {
         for (auto b : c->off_blocks) cudaFreeHost(b);
         if (c->ev_alloc) cudaEventDestroy(c->ev_alloc);
         if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+        cudaFreeHost(c->h_snap);
+        for (auto e : c->snap_event) if (e) cudaEventDestroy(e);
         cudaFree(c->d_desc);
         cudaFreeHost(c->h_desc);
         for (auto e : c->desc_event) if (e) cudaEventDestroy(e);
@@ -928,6 +988,8 @@ void skm_destroy(skm_ctx *c) {
         if (c->own_stream) cudaStreamDestroy(c->stream);
         cudaStreamDestroy(c->copy_stream);
         cudaStreamDestroy(c->part_stream);
+        cudaStreamDestroy(c->dma_stream);
+        if (c->ev_dma) cudaEventDestroy(c->ev_dma);
         if (c->ev_main) cudaEventDestroy(c->ev_main);
     }
     delete c;
@@ -1262,6 +1324,8 @@ int32_t skm_reset(skm_ctx *c) {
     c->launches = 0;
     c->n_grows = 0;
     c->distinct_ub = 0;
+    c->launched_total = 0;
+    for (auto &p : c->snap_pending) p = false;
     c->pos_base = 0;
     c->have_tot = false;
     c->finalized = false;
@@ -1723,6 +1787,58 @@ int32_t skm_route_scatter_p2p(skm_ctx *c, uint32_t chunk, uint32_t slot, const u
     }
     cs.counted = true;
     return SKM_OK;  // asynchronous: ordered on the ctx's stream
+}
+
+// Exchange by copy engines: bucket into the local list (SM work, routing stream), then one peer
+// copy per destination on the copy stream — the NVLink transfer costs no SM time and overlaps the
+// inserts.  Same arenas, offsets and barrier protocol as skm_route_scatter_p2p.
+int32_t skm_route_scatter_dma(skm_ctx *c, uint32_t chunk, uint32_t slot, const uint64_t *dst_offsets) {
+    if (!c || !dst_offsets || slot >= skm_ctx::kP2PSlots) return SKM_ERR_INVALID_ARG;
+    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    WorkStream ws(c, c->part_stream);
+    ChunkState &cs = c->chunks[chunk];
+    if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
+    if (c->route_counts_chunk != chunk) return fail(c, SKM_ERR_STATE, "call skm_route_count for chunk %u first", chunk);
+    const BucketFn fn = route_fn(c);
+    const uint32_t regions = 1u << fn.log2_regions;
+    std::vector<uint64_t> n_to(c->n_ranks, 0);
+    uint64_t total = 0;
+    for (uint32_t o = 0; o < c->n_ranks; o++) {
+        for (uint32_t r = 0; r < regions; r++) n_to[o] += c->route_counts[(size_t)o * regions + r];
+        if (!c->peer_arena[o][slot]) return fail(c, SKM_ERR_STATE, "peer %u arena %u not mapped", o, slot);
+        if (dst_offsets[o] + n_to[o] > c->arena_entries)
+            return fail(c, SKM_ERR_INVALID_ARG, "receive arena of rank %u too small", o);
+        total += n_to[o];
+    }
+    // the previous chunk's peer copies read the list: they must be done before it is rewritten
+    CU(cudaStreamWaitEvent(c->part_stream, c->ev_dma, 0));
+    int32_t rc = ensure_list_on(c, total, c->part_stream);
+    if (rc) return rc;
+    rc = bucket_scatter(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions, c->d_list);
+    if (rc) return rc;
+    for (auto &sg : cs.segs) {
+        CU(cudaFreeAsync(sg.codes, c->work));
+        CU(cudaFreeAsync(sg.breaks, c->work));
+        sg.codes = nullptr;
+        sg.breaks = nullptr;
+    }
+    cs.counted = true;
+    // copies: dma stream waits for the scatter, then the routing stream waits for the copies
+    CU(cudaEventRecord(c->ev_main, c->part_stream));
+    CU(cudaStreamWaitEvent(c->dma_stream, c->ev_main, 0));
+    for (uint32_t i = 0; i < c->n_ranks; i++) {
+        const uint32_t o = (c->p.rank + 1 + i) % c->n_ranks;  // stagger destinations across ranks
+        uint64_t off = 0;
+        for (uint32_t q = 0; q < o; q++) off += n_to[q];
+        if (n_to[o])
+            CU(cudaMemcpyAsync(c->peer_arena[o][slot] + dst_offsets[o], c->d_list + off, n_to[o] * sizeof(uint64_t),
+                               cudaMemcpyDefault, c->dma_stream));
+    }
+    CU(cudaEventRecord(c->ev_dma, c->dma_stream));
+    CU(cudaStreamWaitEvent(c->part_stream, c->ev_dma, 0));  // what follows on the routing stream (the barrier) sees the copies done
+    return SKM_OK;
 }
 
 int32_t skm_insert_runs_device(skm_ctx *c, const uint64_t *d_kmers, const uint64_t *run_counts, uint32_t n_src,

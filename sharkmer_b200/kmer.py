@@ -222,6 +222,10 @@ class Engine:
         off = np.ascontiguousarray(dst_offsets, dtype=np.uint64)
         self._ck(self.L.skm_route_scatter_p2p(self._h, chunk_index, slot, off.ctypes.data))
 
+    def route_scatter_dma(self, chunk_index: int, slot: int, dst_offsets):
+        off = np.ascontiguousarray(dst_offsets, dtype=np.uint64)
+        self._ck(self.L.skm_route_scatter_dma(self._h, chunk_index, slot, off.ctypes.data))
+
     def insert_kmers_device(self, d_ptr: int, n: int):
         self._ck(self.L.skm_insert_kmers_device(self._h, d_ptr, n))
 

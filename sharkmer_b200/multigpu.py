@@ -17,6 +17,8 @@ Two exchange paths:
     stores over NVLink/NVSwitch) — no local list, no collective copy; the transfer overlaps the
     extraction tile by tile inside one kernel.  Steps are ordered by a 1-element all-reduce used
     as a stream-ordered barrier; two arenas per rank give double buffering.
+  * "dma": bucket into a local list (SM work), then one peer copy per destination on the copy
+    engines into the same arenas: the NVLink transfer costs no SM time.
   * "nccl": route to a local list, then all_to_all_single; the exchange of chunk c+1 overlaps
     the insert of chunk c (double-buffered torch tensors).  Also the path of the CPU tests (gloo).
 
@@ -56,7 +58,7 @@ class ShardedCounter:
         self.bytes_sent = 0
         self.kmers_received = 0
         self.exchange = exchange
-        if exchange == "p2p":
+        if exchange in ("p2p", "dma"):
             self._setup_p2p(arena_entries)
 
     def _setup_p2p(self, arena_entries: int):
@@ -106,7 +108,7 @@ class ShardedCounter:
         return out
 
     def _finalize(self):
-        if self.exchange == "p2p":
+        if self.exchange in ("p2p", "dma"):
             return self._finalize_p2p()
         return self._finalize_nccl()
 
@@ -141,7 +143,10 @@ class ShardedCounter:
                 per_dst = m[self.rank]
                 e.route_set_counts(c, counts)
                 # this rank's block in every destination's arena starts after the lower ranks' blocks
-                e.route_scatter_p2p(c, slot, m[:self.rank, :].sum(axis=0))  # fused: extract + bucket + peer stores
+                if self.exchange == "dma":   # bucket locally, copy engines push the runs to the peers
+                    e.route_scatter_dma(c, slot, m[:self.rank, :].sum(axis=0))
+                else:                          # fused: extract + bucket + peer stores in one kernel
+                    e.route_scatter_p2p(c, slot, m[:self.rank, :].sum(axis=0))
                 # Barrier c tells the peers two things: (1) my stores of chunk c have landed, and
                 # (2) my insert of chunk c-1 is finished, so after this barrier they may overwrite
                 # the other arena slot (their scatter of chunk c+1).
