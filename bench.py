@@ -211,6 +211,10 @@ def run_ours(args):
     mode = {"auto": _lib.INSERT_AUTO, "direct": _lib.INSERT_DIRECT, "partitioned": _lib.INSERT_PARTITIONED}[args.mode]
     hint = int(DISTINCT_HINT_PER_GPU * args.reads_per_gpu / READS_PER_GPU)
 
+    if world > 1 and args.exchange in ("p2p", "nccl"):
+        # these two paths bucket at routing time (p2p: scatter kernel fused with the peer stores);
+        # the "dma" path buckets at ingest time and lets the copy engines move the runs
+        os.environ["SKM_EAGER"] = "0"
     stream = torch.cuda.Stream(device=dev)
     eng = kmer.Engine(K, CHUNKS, HISTO_MAX, capacity_hint=hint, device=local_rank, insert_mode=mode,
                       n_ranks=world, rank=rank, stream=stream.cuda_stream)
@@ -242,7 +246,8 @@ def run_ours(args):
     sharded = None
     if world > 1:
         from sharkmer_b200.multigpu import ShardedCounter
-        # receive arena per slot: this rank's share of a chunk's k-mers (+30 % for imbalance)
+        # receive arena per slot: this rank's share of a chunk's k-mers (+30 % for imbalance);
+        # the dma exchange keeps one slot per chunk (13 GB per rank here)
         arena = int(1.3 * max(t.numel() for t in d_bufs)) + (1 << 20)
         sharded = ShardedCounter(eng, CHUNKS, CHUNKS, HISTO_MAX, dev, stream=stream,
                                  exchange=args.exchange, arena_entries=arena)
@@ -433,8 +438,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--gups", action="store_true", help="also measure the random-access roofline probe")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "dma", "nccl"],
-                    help="multi-GPU exchange: fused peer-store scatter over NVLink (p2p) or NCCL all-to-all")
+    ap.add_argument("--exchange", default="dma", choices=["dma", "p2p", "nccl"],
+                    help="multi-GPU exchange: copy engines over NVLink with a CPU control plane (dma), scatter kernel fused "
+                         "with peer stores (p2p), or NCCL all-to-all (nccl)")
     ap.add_argument("--chunks", type=int, default=None, help="EXPERIMENT ONLY: override the workload's chunk count")
     ap.add_argument("--k", type=int, default=None, help="EXPERIMENT ONLY: override k")
     args = ap.parse_args()

@@ -200,7 +200,8 @@ int32_t skm_insert_runs_device(skm_ctx *ctx, const uint64_t *d_kmers, const uint
 /* Fused route + exchange over NVLink (n_ranks <= 16): instead of writing the bucketed k-mers to
  * a local list that a collective then copies, the scatter kernel stores every destination's runs
  * straight into that rank's receive arena through a CUDA-IPC mapping (peer stores, no staging).
- *   skm_p2p_arena_create   allocates this rank's two receive arenas (double buffering)
+ *   skm_p2p_arena_create   allocates this rank's receive arenas (n_slots of them: 2 = double
+ *                          buffering; one per chunk lets every chunk be exchanged ahead of its insert)
  *   skm_p2p_arena_handle   64-byte CUDA IPC handle of arena `slot`, to be sent to every peer
  *   skm_p2p_open_peer      maps a peer's arena from its handle (other process, same node)
  *   skm_p2p_set_peer       same, from a raw device pointer (peer ctx in the same process)
@@ -210,7 +211,7 @@ int32_t skm_insert_runs_device(skm_ctx *ctx, const uint64_t *d_kmers, const uint
  * scatter(c) -> barrier -> insert(c) from their own arena (skm_insert_runs_device on
  * skm_p2p_arena_ptr).  With two slots, a slot is rewritten only after the barrier that follows the
  * owner's insert of its previous content. */
-int32_t skm_p2p_arena_create(skm_ctx *ctx, uint64_t entries_per_slot);
+int32_t skm_p2p_arena_create(skm_ctx *ctx, uint64_t entries_per_slot, uint32_t n_slots /* 1..16 */);
 int32_t skm_p2p_arena_handle(skm_ctx *ctx, uint32_t slot, uint8_t *handle64);
 int32_t skm_p2p_arena_ptr(skm_ctx *ctx, uint32_t slot, uint64_t **out);
 int32_t skm_p2p_open_peer(skm_ctx *ctx, uint32_t peer_rank, uint32_t slot, const uint8_t *handle64);
@@ -222,6 +223,15 @@ int32_t skm_route_scatter_p2p(skm_ctx *ctx, uint32_t chunk_index, uint32_t slot,
  * overlaps the inserts of the previous chunk. */
 int32_t skm_route_scatter_dma(skm_ctx *ctx, uint32_t chunk_index, uint32_t slot,
                               const uint64_t *dst_offsets /* n_ranks */);
+/* Number of leading chunks (0 .. n-1) whose staged batches have all been packed / bucketed on the
+ * device already (non-blocking; meaningful once ingest is closed). */
+int32_t skm_chunks_ready(skm_ctx *ctx, uint32_t *n_ready);
+/* Block the calling host thread until the peer copies queued by skm_route_scatter_dma into
+ * arena `slot` (at every destination) have landed. */
+int32_t skm_dma_wait(skm_ctx *ctx, uint32_t slot);
+/* skm_snapshot_histogram without the host wait: the column is copied in stream order (pinned
+ * landing area) and skm_histogram waits for it. */
+int32_t skm_snapshot_histogram_async(skm_ctx *ctx, uint32_t chunk_i);
 
 /* Insert `n` k-mers (device memory) that this rank owns; asynchronous on the ctx's stream. */
 int32_t skm_insert_kmers_device(skm_ctx *ctx, const uint64_t *d_kmers, uint64_t n);

@@ -23,52 +23,30 @@ for c in range(CH):
     h = torch.empty(t.numel(), dtype=torch.uint8, pin_memory=True); h.copy_(t); h_bufs.append(h)
 torch.cuda.synchronize()
 arena = int(1.3 * max(t.numel() for t in d_bufs)) + (1 << 20)
-sc = multigpu.ShardedCounter(eng, CH, CH, HM, dev, stream=stream, exchange="p2p", arena_entries=arena)
+sc = multigpu.ShardedCounter(eng, CH, CH, HM, dev, stream=stream, exchange="dma", arena_entries=arena)
 
-orig_snap = eng.snapshot_histogram
 marks = []
-def snap(c):
-    orig_snap(c); marks.append((f"snap{c}", time.perf_counter()))
-eng.snapshot_histogram = snap
-orig_rcd = eng.route_count_device
-def rcd(c):
-    marks.append((f"route{c}_begin", time.perf_counter()))
-    r = orig_rcd(c)
-    if c == 0:
-        marks.append(("r0_count_queued", time.perf_counter()))
-        torch.cuda.current_stream().synchronize()
-        marks.append(("r0_count_done", time.perf_counter()))
-    return r
-eng.route_count_device = rcd
-orig_ag = dist.all_gather_into_tensor
-def ag(*a, **k):
-    r = orig_ag(*a, **k)
-    marks.append(("ag_queued", time.perf_counter()))
-    torch.cuda.current_stream().synchronize()
-    marks.append(("ag_done", time.perf_counter()))
-    return r
-dist.all_gather_into_tensor = ag
-orig_sc = eng.route_scatter_p2p
-def scp(c, slot, off):
-    r = orig_sc(c, slot, off)
-    if c == 0:
-        marks.append(("r0_scatter_queued", time.perf_counter()))
-        torch.cuda.current_stream().synchronize()
-        marks.append(("r0_scatter_done", time.perf_counter()))
-    return r
-eng.route_scatter_p2p = scp
-
+def wrap(obj, name, label):
+    orig = getattr(obj, name)
+    def f(*a, **k):
+        t = time.perf_counter(); r = orig(*a, **k); marks.append((label, t, time.perf_counter())); return r
+    setattr(obj, name, f)
+wrap(eng, "route_count", "cnt"); wrap(eng, "route_scatter_dma", "dma"); wrap(eng, "dma_wait", "wait")
+wrap(eng, "insert_runs_device", "ins"); wrap(dist, "barrier", "bar"); wrap(dist, "all_gather_into_tensor", "ag")
+MODE = os.environ.get("DBG_MODE", "value")
 for it in range(4):
     marks.clear()
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     eng.reset()
-    marks.append(("reset", time.perf_counter()))
     for c in range(CH):
-        eng.ingest_ptr(c, h_bufs[c].data_ptr(), h_bufs[c].numel(), _lib.INGEST_ASYNC)
-    marks.append(("ingest_queued", time.perf_counter()))
+        if MODE == "e2e":
+            eng.ingest_ptr(c, h_bufs[c].data_ptr(), h_bufs[c].numel(), _lib.INGEST_ASYNC)
+        else:
+            eng.ingest_device(c, d_bufs[c].data_ptr(), d_bufs[c].numel())
+    marks.clear()
     sc.finalize()
-    marks.append(("done", time.perf_counter()))
+    t1 = time.perf_counter()
     if rank == 0 and it >= 2:
-        print(" ".join(f"{n}={1e3*(t-t0):.1f}" for n, t in marks), flush=True)
+        print(f"total={1e3*(t1-t0):.1f} " + " ".join(f"{n}@{1e3*(a-t0):.1f}+{1e3*(b-a):.2f}" for n, a, b in marks), flush=True)
 dist.destroy_process_group()

@@ -72,13 +72,16 @@ SYMBOLS = {
     "skm_route_scatter": (_i32, [_vp, _u32, _vp]),
     "skm_route_count_device": (_i32, [_vp, _u32, C.POINTER(_vp)]),
     "skm_route_set_counts": (_i32, [_vp, _u32, _vp]),
-    "skm_p2p_arena_create": (_i32, [_vp, _u64]),
+    "skm_p2p_arena_create": (_i32, [_vp, _u64, _u32]),
     "skm_p2p_arena_handle": (_i32, [_vp, _u32, _vp]),
     "skm_p2p_arena_ptr": (_i32, [_vp, _u32, C.POINTER(_vp)]),
     "skm_p2p_open_peer": (_i32, [_vp, _u32, _u32, _vp]),
     "skm_p2p_set_peer": (_i32, [_vp, _u32, _u32, _vp]),
     "skm_route_scatter_p2p": (_i32, [_vp, _u32, _u32, _vp]),
     "skm_route_scatter_dma": (_i32, [_vp, _u32, _u32, _vp]),
+    "skm_dma_wait": (_i32, [_vp, _u32]),
+    "skm_chunks_ready": (_i32, [_vp, C.POINTER(_u32)]),
+    "skm_snapshot_histogram_async": (_i32, [_vp, _u32]),
     "skm_insert_kmers_device": (_i32, [_vp, _vp, _u64]),
     "skm_insert_runs_device": (_i32, [_vp, _vp, _vp, _u32, _u32]),
     "skm_snapshot_histogram": (_i32, [_vp, _u32]),

@@ -47,6 +47,7 @@ struct Segment {
     uint64_t *h_offsets = nullptr;  // pinned, n_buckets + 1 entries (valid once `ready` has fired)
     cudaEvent_t ready = nullptr;    // fires when the segment's pack (+ bucketing) has finished
     uint32_t n_buckets = 0;
+    unsigned long long *d_counts = nullptr;  // per-bucket counts on the device (multi-GPU routing)
 };
 
 struct ChunkState {
@@ -96,6 +97,8 @@ struct skm_ctx {
 
     std::vector<ChunkState> chunks;
     std::vector<std::vector<uint64_t>> histos;  // per chunk snapshot
+    uint64_t *h_cols = nullptr;                 // pinned landing area for asynchronous column snapshots
+    std::vector<bool> col_pending;
     std::vector<bool> have_histo;
     std::vector<ChunkCounters> h_cc;
     HistoTotals last_tot{};
@@ -119,8 +122,10 @@ struct skm_ctx {
     uint32_t raw_next = 0;
 
     // peer-to-peer routing: receive arenas of this rank and the peers' mapped pointers
-    static constexpr uint32_t kP2PSlots = 2;
-    unsigned long long *arena[kP2PSlots] = {nullptr, nullptr};
+    static constexpr uint32_t kP2PSlots = 16;
+    uint32_t n_slots = 0;                     // arenas actually allocated
+    unsigned long long *arena[kP2PSlots] = {};
+    cudaEvent_t ev_slot[kP2PSlots] = {};      // fires when the peer copies into slot s (all destinations) are done
     uint64_t arena_entries = 0;
     unsigned long long *peer_arena[16][kP2PSlots] = {};
     bool peer_ipc[16][kP2PSlots] = {};
@@ -682,6 +687,12 @@ int32_t snapshot_histogram(skm_ctx *c, uint32_t chunk_i) {
     if (!c->track_histo) {
         int32_t rc = scan_table(c, false, &c->histos[chunk_i]);
         if (rc) return rc;
+    } else if (c->h_cols) {
+        // pinned landing area: the copy is truly asynchronous (a pageable destination would block the
+        // host until the inserts queued before it have finished)
+        CU(cudaMemcpyAsync(c->h_cols + (size_t)chunk_i * nb, c->d_hist, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                           c->stream));
+        c->col_pending[chunk_i] = true;
     } else {
         c->histos[chunk_i].assign(nb, 0);
         CU(cudaMemcpyAsync(c->histos[chunk_i].data(), c->d_hist, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost,
@@ -689,6 +700,16 @@ int32_t snapshot_histogram(skm_ctx *c, uint32_t chunk_i) {
     }
     c->have_histo[chunk_i] = true;
     return SKM_OK;
+}
+
+// After the main stream has been synchronised: move landed columns into c->histos.
+void materialize_cols(skm_ctx *c) {
+    const uint64_t nb = c->p.histo_max + 2;
+    for (uint32_t i = 0; i < c->n_chunks; i++)
+        if (c->col_pending[i]) {
+            c->histos[i].assign(c->h_cols + (size_t)i * nb, c->h_cols + (size_t)(i + 1) * nb);
+            c->col_pending[i] = false;
+        }
 }
 
 int32_t check_sticky(skm_ctx *c) {
@@ -717,6 +738,12 @@ int32_t refresh_chunk_counters(skm_ctx *c) {
     return SKM_OK;
 }
 
+BucketFn route_fn(const skm_ctx *c) {
+    BucketFn fn;
+    fn.n_ranks = c->n_ranks;
+    fn.log2_regions = route_log2_regions(c);
+    return fn;
+}
 constexpr size_t kOffBlockEntries = 64 * (kMaxBuckets + 1);
 
 uint64_t *alloc_offsets(skm_ctx *c, uint32_t n) {
@@ -743,19 +770,21 @@ bool want_partitioned(const skm_ctx *c, uint64_t n_bytes) {
 // behind the pack kernel on the ctx's stream, so it overlaps the next batch's host-to-device copy,
 // and skm_finalize only has the inserts left.  Costs 8 B per position of HBM instead of 0.375 B;
 // skipped when memory is short (the segment then stays packed and is bucketed at finalize).
-int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index) {
+int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force = false) {
     Segment &sg = c->chunks[chunk].segs[seg_index];
-    if (!c->eager || c->n_ranks != 1 || !want_partitioned(c, sg.n_bytes)) return SKM_OK;
+    if (!sg.codes || sg.list) return SKM_OK;
     const size_t need = sg.n_bytes * sizeof(uint64_t);
-    // budget = device memory that was free when the ctx was created; keep room for a table twice
-    // the current size plus slack (no cudaMemGetInfo here: it would serialise the ingest path)
-    if (c->list_bytes + need + 3 * c->capacity * sizeof(Slot) + (4ull << 30) > c->mem_budget) return SKM_OK;
-    BucketFn fn;
-    fn.n_ranks = 1;
-    fn.log2_regions = route_log2_regions(c);
-    const uint32_t nb = 1u << fn.log2_regions;
+    if (!force) {
+        // multi-GPU: routing needs the buckets anyway; single GPU: only when partitioned insert pays off
+        if (!c->eager || (c->n_ranks == 1 && !want_partitioned(c, sg.n_bytes))) return SKM_OK;
+        // budget = device memory that was free when the ctx was created; keep room for a table twice
+        // the current size plus slack (no cudaMemGetInfo here: it would serialise the ingest path)
+        if (c->list_bytes + need + 3 * c->capacity * sizeof(Slot) + (4ull << 30) > c->mem_budget) return SKM_OK;
+    }
+    const BucketFn fn = route_fn(c);  // (owner, region); a single GPU is the n_ranks == 1 case
+    const uint32_t nb = c->n_ranks << fn.log2_regions;
     uint64_t *h_off = alloc_offsets(c, nb + 1);
-    if (!h_off) return SKM_OK;
+    if (!h_off) return force ? fail(c, SKM_ERR_OOM, "pinned allocation failed") : SKM_OK;
     // the pack kernel ran on another stream (the copy stream): order the bucketing after it.  Only
     // here — a wait queued for a batch that is NOT bucketed now would make everything later on this
     // stream (e.g. the routing of chunk 0) wait for the arrival of the LAST batch.
@@ -763,13 +792,17 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index) {
     if (cudaMallocAsync((void **)&sg.list, need, c->work) != cudaSuccess) {
         cudaGetLastError();
         sg.list = nullptr;
-        return SKM_OK;
+        return force ? fail(c, SKM_ERR_OOM, "device allocation failed") : SKM_OK;
     }
     int32_t rc = bucket_count(c, chunk, seg_index, seg_index + 1, fn, nb, nullptr, nullptr);
     if (rc) return rc;
     rc = bucket_scatter(c, chunk, seg_index, seg_index + 1, fn, nb, sg.list);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h_off, c->d_bucket_offsets, (nb + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->work));
+    if (c->n_ranks > 1) {
+        CU(cudaMallocAsync((void **)&sg.d_counts, nb * sizeof(uint64_t), c->work));
+        CU(cudaMemcpyAsync(sg.d_counts, c->d_bucket_counts, nb * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->work));
+    }
     CU(cudaFreeAsync(sg.codes, c->work));
     CU(cudaFreeAsync(sg.breaks, c->work));
     sg.codes = nullptr;
@@ -777,6 +810,7 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index) {
     sg.h_offsets = h_off;
     sg.n_buckets = nb;
     c->list_bytes += need;
+    CU(cudaEventRecord(sg.ready, c->work));  // `ready` now also covers the list + offsets
     return SKM_OK;
 }
 
@@ -808,8 +842,6 @@ int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t
     const size_t idx = c->chunks[chunk].segs.size() - 1;
     int32_t rc = eager_partition(c, chunk, idx);
     if (rc) return rc;
-    Segment &seg = c->chunks[chunk].segs[idx];
-    if (seg.list) CU(cudaEventRecord(seg.ready, c->work));  // bucketed: `ready` now also covers the list + offsets
     return SKM_OK;
 }
 
@@ -924,7 +956,11 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
 
     c->chunks.resize(c->n_chunks);
     c->histos.resize(c->n_chunks);
+    c->col_pending.assign(c->n_chunks, false);
+    if ((uint64_t)c->n_chunks * (c->p.histo_max + 2) * sizeof(uint64_t) <= (256ull << 20))
+        CU(cudaMallocHost((void **)&c->h_cols, (size_t)c->n_chunks * (c->p.histo_max + 2) * sizeof(uint64_t)));
     c->have_histo.assign(c->n_chunks, false);
+    c->col_pending.assign(c->n_chunks, false);
     c->h_cc.assign(c->n_chunks, ChunkCounters{});
     c->chunk_bases_read.assign(c->n_chunks, 0);
 
@@ -951,6 +987,7 @@ void skm_destroy(skm_ctx *c) {
                 cudaFree(sg.codes);
                 cudaFree(sg.breaks);
                 cudaFree(sg.list);
+                cudaFree(sg.d_counts);
             }
         cudaFree(c->table);
         cudaFree(c->d_cc);
@@ -961,7 +998,10 @@ void skm_destroy(skm_ctx *c) {
         for (uint32_t r = 0; r < 16; r++)
             for (uint32_t sl = 0; sl < skm_ctx::kP2PSlots; sl++)
                 if (c->peer_ipc[r][sl]) cudaIpcCloseMemHandle(c->peer_arena[r][sl]);
-        for (uint32_t sl = 0; sl < skm_ctx::kP2PSlots; sl++) cudaFree(c->arena[sl]);
+        for (uint32_t sl = 0; sl < skm_ctx::kP2PSlots; sl++) {
+            cudaFree(c->arena[sl]);
+            if (c->ev_slot[sl]) cudaEventDestroy(c->ev_slot[sl]);
+        }
         for (int i = 0; i < 3; i++) {
             cudaFree(c->raw_buf[i]);
             if (c->raw_copied[i]) cudaEventDestroy(c->raw_copied[i]);
@@ -970,6 +1010,7 @@ void skm_destroy(skm_ctx *c) {
         for (auto b : c->off_blocks) cudaFreeHost(b);
         if (c->ev_alloc) cudaEventDestroy(c->ev_alloc);
         if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+        cudaFreeHost(c->h_cols);
         cudaFreeHost(c->h_snap);
         for (auto e : c->snap_event) if (e) cudaEventDestroy(e);
         cudaFree(c->d_desc);
@@ -1236,6 +1277,7 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
     cudaEventRecord(e1, c->stream);
     rc = sync_all(c);
     if (rc) return rc;
+    materialize_cols(c);
     rc = check_sticky(c);
     if (rc) return rc;
     float ms = 0;
@@ -1297,6 +1339,7 @@ int32_t skm_reset(skm_ctx *c) {
             if (sg.codes) CU(cudaFreeAsync(sg.codes, c->stream));
             if (sg.breaks) CU(cudaFreeAsync(sg.breaks, c->stream));
             if (sg.list) CU(cudaFreeAsync(sg.list, c->stream));
+            if (sg.d_counts) CU(cudaFreeAsync(sg.d_counts, c->stream));
         }
         cs = ChunkState{};
     }
@@ -1331,8 +1374,43 @@ int32_t skm_reset(skm_ctx *c) {
     c->finalized = false;
     c->sticky_error = false;
     c->have_histo.assign(c->n_chunks, false);
+    c->col_pending.assign(c->n_chunks, false);
     c->h_cc.assign(c->n_chunks, ChunkCounters{});
     c->err.clear();
+    return SKM_OK;
+}
+
+int32_t skm_snapshot_histogram_async(skm_ctx *c, uint32_t chunk_i) {
+    if (!c) return SKM_ERR_INVALID_ARG;
+    if (chunk_i >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    return snapshot_histogram(c, chunk_i);  // stream-ordered; skm_histogram waits for it
+}
+
+int32_t skm_chunks_ready(skm_ctx *c, uint32_t *n_ready) {
+    if (!c || !n_ready) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    uint32_t n = 0;
+    for (; n < c->n_chunks; n++) {
+        bool ok = true;
+        for (auto &sg : c->chunks[n].segs)
+            if (sg.ready && cudaEventQuery(sg.ready) != cudaSuccess) {
+                ok = false;
+                break;
+            }
+        if (!ok) break;
+    }
+    cudaGetLastError();  // cudaErrorNotReady is not an error
+    *n_ready = n;
+    return SKM_OK;
+}
+
+int32_t skm_dma_wait(skm_ctx *c, uint32_t slot) {
+    if (!c || slot >= skm_ctx::kP2PSlots || !c->ev_slot[slot]) return SKM_ERR_INVALID_ARG;
+    DeviceGuard g(c->device);
+    CU(cudaEventSynchronize(c->ev_slot[slot]));
     return SKM_OK;
 }
 
@@ -1346,6 +1424,11 @@ int32_t skm_finalize_external(skm_ctx *c) {
 int32_t skm_histogram(skm_ctx *c, uint32_t chunk_i, uint64_t *out, uint64_t out_len) {
     if (!c || !out) return SKM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
+    if (chunk_i < c->n_chunks && c->col_pending[chunk_i]) {
+        DeviceGuard g(c->device);
+        CU(cudaStreamSynchronize(c->stream));
+        materialize_cols(c);
+    }
     if (chunk_i >= c->n_chunks || !c->have_histo[chunk_i])
         return fail(c, SKM_ERR_STATE, "no histogram snapshot for chunk %u (chunks=%u, finalized=%d)", chunk_i, c->p.chunks, (int)c->finalized);
     if (out_len < c->p.histo_max + 2) return fail(c, SKM_ERR_INVALID_ARG, "histogram buffer too small");
@@ -1366,6 +1449,7 @@ int32_t skm_totals_get(skm_ctx *c, skm_totals *out) {
     DeviceGuard g(c->device);
     int32_t rc = sync_all(c);
     if (rc) return rc;
+    materialize_cols(c);
     rc = refresh_chunk_counters(c);
     if (rc) return rc;
     rc = refresh_totals(c);
@@ -1608,13 +1692,6 @@ int32_t skm_insert_counts(skm_ctx *c, const uint64_t *keys, const uint32_t *coun
 
 // ---- multi-GPU building blocks -------------------------------------------------
 
-static BucketFn route_fn(const skm_ctx *c) {
-    BucketFn fn;
-    fn.n_ranks = c->n_ranks;
-    fn.log2_regions = route_log2_regions(c);
-    return fn;
-}
-
 int32_t skm_stream_handle(skm_ctx *c, uint32_t which, uint64_t *out) {
     if (!c || !out || which > 1) return SKM_ERR_INVALID_ARG;
     *out = (uint64_t)(uintptr_t)(which == 0 ? c->stream : c->part_stream);
@@ -1626,6 +1703,114 @@ int32_t skm_route_regions(skm_ctx *c, uint32_t *regions_per_rank) {
     *regions_per_rank = 1u << route_log2_regions(c);
     return SKM_OK;
 }
+
+
+}  // extern "C" (helpers below are internal)
+
+namespace {
+
+// Make sure every segment of the chunk is in bucketed form (list + offsets + device counts).
+int32_t bucketed_chunk(skm_ctx *c, uint32_t chunk) {
+    ChunkState &cs = c->chunks[chunk];
+    for (size_t i = 0; i < cs.segs.size(); i++) {
+        if (cs.segs[i].list) continue;
+        int32_t rc = eager_partition(c, chunk, i, true);
+        if (rc) return rc;
+    }
+    return SKM_OK;
+}
+
+// Host copy of the chunk's per-bucket counts (waits for the bucketing of its segments).
+int32_t chunk_counts_host(skm_ctx *c, uint32_t chunk, std::vector<uint64_t> &counts) {
+    ChunkState &cs = c->chunks[chunk];
+    const uint32_t nb = c->n_ranks << route_log2_regions(c);
+    counts.assign(nb, 0);
+    for (auto &sg : cs.segs) {
+        if (!sg.list) continue;
+        CU(cudaEventSynchronize(sg.ready));
+        for (uint32_t b = 0; b < nb; b++) counts[b] += sg.h_offsets[b + 1] - sg.h_offsets[b];
+    }
+    return SKM_OK;
+}
+
+// Copy pieces with the descriptor-driven copy kernel on `st`.
+int32_t launch_copy(skm_ctx *c, std::vector<CopyDesc> &pieces, cudaStream_t st) {
+    size_t i = 0;
+    while (i < pieces.size()) {
+        const size_t j = std::min(pieces.size(), i + kMaxRuns);
+        uint64_t tiles = 0;
+        for (size_t q = i; q < j; q++) {
+            pieces[q].tile_begin = tiles;
+            tiles += (pieces[q].n + kCopyTile - 1) / kCopyTile;
+        }
+        static_assert(sizeof(CopyDesc) == sizeof(RunDesc), "descriptor rings are shared");
+        const uint32_t slot = c->desc_next++ % kDescRing;
+        if (c->desc_event[slot]) CU(cudaEventSynchronize(c->desc_event[slot]));
+        else CU(cudaEventCreateWithFlags(&c->desc_event[slot], cudaEventDisableTiming));
+        memcpy(c->h_desc + (size_t)slot * kMaxRuns, pieces.data() + i, (j - i) * sizeof(CopyDesc));
+        RunDesc *h_dev = nullptr;
+        CU(cudaHostGetDevicePointer((void **)&h_dev, c->h_desc, 0));
+        RunDesc *d_descs = c->d_desc + (size_t)slot * kMaxRuns;
+        copy_descs_kernel<<<4, 256, 0, st>>>(h_dev + (size_t)slot * kMaxRuns, d_descs, (uint32_t)(j - i));
+        unsigned long long *counter = &c->d_gc->scratch[1];
+        zero_async(c, counter, sizeof(unsigned long long), st);
+        const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((tiles + 7) / 8, (uint64_t)c->sm_count * 4));
+        {
+            Span sp(c, ST_PART, st);
+            copy_runs_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const CopyDesc *>(d_descs), (uint32_t)(j - i), tiles, counter);
+            c->launches += 2;
+            c->stage_launches[ST_PART]++;
+        }
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->desc_event[slot], st));
+        i = j;
+    }
+    return SKM_OK;
+}
+
+// Pieces that move a bucketed chunk to its destinations: for every owner o, region-major over the
+// chunk's segments, into dst_base[o] (contiguous).  Adjacent pieces that are contiguous on both
+// sides are merged (one segment => one piece per destination).
+void build_pieces(skm_ctx *c, uint32_t chunk, unsigned long long *const *dst_base, std::vector<CopyDesc> &out) {
+    ChunkState &cs = c->chunks[chunk];
+    const uint32_t regions = 1u << route_log2_regions(c);
+    for (uint32_t o = 0; o < c->n_ranks; o++) {
+        uint64_t at = 0;
+        for (uint32_t r = 0; r < regions; r++)
+            for (auto &sg : cs.segs) {
+                if (!sg.list) continue;
+                const uint32_t b = o * regions + r;
+                const uint64_t n = sg.h_offsets[b + 1] - sg.h_offsets[b];
+                if (!n) continue;
+                const unsigned long long *src = sg.list + sg.h_offsets[b];
+                unsigned long long *dst = dst_base[o] + at;
+                if (!out.empty() && out.back().src + out.back().n == src && out.back().dst + out.back().n == dst)
+                    out.back().n += n;
+                else
+                    out.push_back(CopyDesc{src, dst, n, 0});
+                at += n;
+            }
+    }
+}
+
+int32_t drop_chunk_lists(skm_ctx *c, uint32_t chunk, cudaStream_t st) {
+    ChunkState &cs = c->chunks[chunk];
+    for (auto &sg : cs.segs) {
+        if (sg.list) {
+            CU(cudaFreeAsync(sg.list, st));
+            c->list_bytes -= std::min<size_t>(c->list_bytes, sg.n_bytes * sizeof(uint64_t));
+        }
+        if (sg.d_counts) CU(cudaFreeAsync(sg.d_counts, st));
+        sg.list = nullptr;
+        sg.d_counts = nullptr;
+    }
+    cs.counted = true;
+    return SKM_OK;
+}
+
+}  // namespace
+
+extern "C" {
 
 int32_t skm_route_count(skm_ctx *c, uint32_t chunk, uint64_t *bucket_counts) {
     if (!c || !bucket_counts) return SKM_ERR_INVALID_ARG;
@@ -1640,6 +1825,15 @@ int32_t skm_route_count(skm_ctx *c, uint32_t chunk, uint64_t *bucket_counts) {
     uint64_t total = 0;
     const BucketFn fn = route_fn(c);
     const uint32_t nb = c->n_ranks << fn.log2_regions;
+    if (c->eager) {  // batches are bucketed at ingest time: the counts are the list offsets
+        int32_t rc = bucketed_chunk(c, chunk);
+        if (rc) return rc;
+        rc = chunk_counts_host(c, chunk, c->route_counts);
+        if (rc) return rc;
+        memcpy(bucket_counts, c->route_counts.data(), nb * sizeof(uint64_t));
+        c->route_counts_chunk = chunk;
+        return SKM_OK;
+    }
     int32_t rc = bucket_count(c, chunk, 0, cs.segs.size(), fn, nb, &total, bucket_counts);
     if (rc) return rc;
     c->route_counts.assign(bucket_counts, bucket_counts + nb);
@@ -1658,8 +1852,23 @@ int32_t skm_route_count_device(skm_ctx *c, uint32_t chunk, uint64_t **d_counts) 
     for (auto &sg : cs.segs)  // this chunk's pack kernels (copy stream) must have fired; later chunks may still be arriving
         if (sg.ready) CU(cudaStreamWaitEvent(c->part_stream, sg.ready, 0));
     const BucketFn fn = route_fn(c);
-    int32_t rc = bucket_count(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions, nullptr, nullptr);
-    if (rc) return rc;
+    const uint32_t nb = c->n_ranks << fn.log2_regions;
+    int32_t rc;
+    if (c->eager) {  // sum the per-segment counts left on the device by the ingest-time bucketing
+        rc = bucketed_chunk(c, chunk);
+        if (rc) return rc;
+        zero_async(c, c->d_bucket_counts, nb * sizeof(uint64_t), c->work);
+        for (auto &sg : cs.segs) {
+            if (!sg.d_counts) continue;
+            CU(cudaStreamWaitEvent(c->work, sg.ready, 0));
+            add_counts_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_counts, sg.d_counts, nb);
+            c->launches++;
+        }
+        CU(cudaGetLastError());
+    } else {
+        rc = bucket_count(c, chunk, 0, cs.segs.size(), fn, nb, nullptr, nullptr);
+        if (rc) return rc;
+    }
     *d_counts = (uint64_t *)c->d_bucket_counts;  // valid until the next route count on this ctx
     c->route_counts_chunk = 0xFFFFFFFFu;
     return SKM_OK;  // asynchronous (routing stream)
@@ -1683,8 +1892,28 @@ int32_t skm_route_scatter(skm_ctx *c, uint32_t chunk, uint64_t *d_out) {
     ChunkState &cs = c->chunks[chunk];
     if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
     const BucketFn fn = route_fn(c);
-    int32_t rc = bucket_scatter(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions,
-                                (unsigned long long *)d_out);
+    int32_t rc;
+    if (c->eager) {  // already bucketed: gather the segments' runs into d_out, bucket-major
+        rc = bucketed_chunk(c, chunk);
+        if (rc) return rc;
+        std::vector<uint64_t> counts;
+        rc = chunk_counts_host(c, chunk, counts);
+        if (rc) return rc;
+        const uint32_t regions = 1u << fn.log2_regions;
+        std::vector<unsigned long long *> base(c->n_ranks);
+        uint64_t at = 0;
+        for (uint32_t o = 0; o < c->n_ranks; o++) {
+            base[o] = (unsigned long long *)d_out + at;
+            for (uint32_t r = 0; r < regions; r++) at += counts[(size_t)o * regions + r];
+        }
+        std::vector<CopyDesc> pieces;
+        build_pieces(c, chunk, base.data(), pieces);
+        rc = launch_copy(c, pieces, c->work);
+        if (rc) return rc;
+        return drop_chunk_lists(c, chunk, c->work);
+    }
+    rc = bucket_scatter(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions,
+                        (unsigned long long *)d_out);
     if (rc) return rc;
     for (auto &sg : cs.segs) {
         CU(cudaFreeAsync(sg.codes, c->work));
@@ -1696,8 +1925,8 @@ int32_t skm_route_scatter(skm_ctx *c, uint32_t chunk, uint64_t *d_out) {
     return SKM_OK;  // asynchronous: ordered on the ctx's stream
 }
 
-int32_t skm_p2p_arena_create(skm_ctx *c, uint64_t entries_per_slot) {
-    if (!c || entries_per_slot == 0) return SKM_ERR_INVALID_ARG;
+int32_t skm_p2p_arena_create(skm_ctx *c, uint64_t entries_per_slot, uint32_t n_slots) {
+    if (!c || entries_per_slot == 0 || n_slots == 0 || n_slots > skm_ctx::kP2PSlots) return SKM_ERR_INVALID_ARG;
     if (c->n_ranks > kMaxP2PRanks) return fail(c, SKM_ERR_INVALID_ARG, "peer-to-peer routing supports at most %u ranks", kMaxP2PRanks);
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
@@ -1705,10 +1934,13 @@ int32_t skm_p2p_arena_create(skm_ctx *c, uint64_t entries_per_slot) {
     for (uint32_t sl = 0; sl < skm_ctx::kP2PSlots; sl++) {
         if (c->arena[sl]) CU(cudaFree(c->arena[sl]));
         c->arena[sl] = nullptr;
+        if (sl >= n_slots) continue;
         // cudaMalloc, not the stream-ordered pool: the block must be exportable through CUDA IPC
         CU(cudaMalloc((void **)&c->arena[sl], entries_per_slot * sizeof(uint64_t)));
         c->peer_arena[c->p.rank][sl] = c->arena[sl];
+        if (!c->ev_slot[sl]) CU(cudaEventCreateWithFlags(&c->ev_slot[sl], cudaEventDisableTiming));
     }
+    c->n_slots = n_slots;
     c->arena_entries = entries_per_slot;
     return SKM_OK;
 }
@@ -1777,6 +2009,19 @@ int32_t skm_route_scatter_p2p(skm_ctx *c, uint32_t chunk, uint32_t slot, const u
         bases.dst[o] = c->peer_arena[o][slot] + dst_offsets[o] - start;
         start += n_o;
     }
+    if (c->eager) {  // already bucketed at ingest time: a copy kernel pushes the runs (peer stores)
+        int32_t rc2 = bucketed_chunk(c, chunk);
+        if (rc2) return rc2;
+        for (auto &sg : cs.segs)
+            if (sg.list) CU(cudaEventSynchronize(sg.ready));
+        std::vector<unsigned long long *> base(c->n_ranks);
+        for (uint32_t o = 0; o < c->n_ranks; o++) base[o] = c->peer_arena[o][slot] + dst_offsets[o];
+        std::vector<CopyDesc> pieces;
+        build_pieces(c, chunk, base.data(), pieces);
+        rc2 = launch_copy(c, pieces, c->work);
+        if (rc2) return rc2;
+        return drop_chunk_lists(c, chunk, c->work);
+    }
     int32_t rc = bucket_scatter(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions, nullptr, &bases);
     if (rc) return rc;
     for (auto &sg : cs.segs) {
@@ -1812,6 +2057,35 @@ int32_t skm_route_scatter_dma(skm_ctx *c, uint32_t chunk, uint32_t slot, const u
             return fail(c, SKM_ERR_INVALID_ARG, "receive arena of rank %u too small", o);
         total += n_to[o];
     }
+    if (c->eager) {  // already bucketed: copy engines push each destination's block (one segment),
+                     // or the copy kernel merges several segments region-major
+        int32_t rc2 = bucketed_chunk(c, chunk);
+        if (rc2) return rc2;
+        size_t n_seg = 0;
+        for (auto &sg : cs.segs)
+            if (sg.list) {
+                CU(cudaEventSynchronize(sg.ready));
+                n_seg++;
+            }
+        std::vector<unsigned long long *> base(c->n_ranks);
+        for (uint32_t o = 0; o < c->n_ranks; o++) base[o] = c->peer_arena[o][slot] + dst_offsets[o];
+        std::vector<CopyDesc> pieces;
+        build_pieces(c, chunk, base.data(), pieces);
+        if (n_seg <= 1) {
+            // (the segment was bucketed on the routing stream and `ready` has fired: the lists are complete)
+            for (size_t i = 0; i < pieces.size(); i++) {
+                const CopyDesc &d = pieces[(i + c->p.rank + 1) % pieces.size()];  // stagger destinations
+                CU(cudaMemcpyAsync(d.dst, d.src, d.n * sizeof(uint64_t), cudaMemcpyDefault, c->dma_stream));
+            }
+            CU(cudaEventRecord(c->ev_slot[slot], c->dma_stream));
+            CU(cudaEventRecord(c->ev_dma, c->dma_stream));
+            return drop_chunk_lists(c, chunk, c->dma_stream);  // freed once the copies have read them
+        }
+        rc2 = launch_copy(c, pieces, c->work);
+        if (rc2) return rc2;
+        CU(cudaEventRecord(c->ev_slot[slot], c->work));
+        return drop_chunk_lists(c, chunk, c->work);
+    }
     // the previous chunk's peer copies read the list: they must be done before it is rewritten
     CU(cudaStreamWaitEvent(c->part_stream, c->ev_dma, 0));
     int32_t rc = ensure_list_on(c, total, c->part_stream);
@@ -1836,6 +2110,7 @@ int32_t skm_route_scatter_dma(skm_ctx *c, uint32_t chunk, uint32_t slot, const u
             CU(cudaMemcpyAsync(c->peer_arena[o][slot] + dst_offsets[o], c->d_list + off, n_to[o] * sizeof(uint64_t),
                                cudaMemcpyDefault, c->dma_stream));
     }
+    CU(cudaEventRecord(c->ev_slot[slot], c->dma_stream));
     CU(cudaEventRecord(c->ev_dma, c->dma_stream));
     CU(cudaStreamWaitEvent(c->part_stream, c->ev_dma, 0));  // what follows on the routing stream (the barrier) sees the copies done
     return SKM_OK;

@@ -481,6 +481,46 @@ struct RunDesc {
     unsigned long long tile_begin;   // index of this run's first warp tile
 };
 
+// Descriptor-driven copy: every warp pulls the next 2048-word tile of a sequence of (src, dst, n)
+// pieces.  Used to push already-bucketed runs into the peers' receive arenas (peer stores over
+// NVLink) and to merge the runs of several segments region-major on the way.
+struct CopyDesc {
+    const unsigned long long *src;
+    unsigned long long *dst;
+    unsigned long long n;
+    unsigned long long tile_begin;
+};
+static constexpr uint32_t kCopyTile = 2048;
+
+__global__ void __launch_bounds__(256)
+copy_runs_kernel(const CopyDesc *__restrict__ descs, uint32_t n_desc, unsigned long long n_tiles,
+                 unsigned long long *__restrict__ tile_counter) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tiles) break;
+        uint32_t lo = 0, hi = n_desc;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (descs[mid].tile_begin <= t) lo = mid; else hi = mid;
+        }
+        const CopyDesc d = descs[lo];
+        const uint64_t base = (t - d.tile_begin) * kCopyTile;
+#pragma unroll 4
+        for (uint32_t j = lane; j < kCopyTile; j += 32) {
+            const uint64_t i = base + j;
+            if (i < d.n) d.dst[i] = d.src[i];
+        }
+    }
+}
+
+__global__ void add_counts_kernel(unsigned long long *__restrict__ dst, const unsigned long long *__restrict__ src,
+                                  uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
 // Zero-fill by kernel.  cudaMemsetAsync may be serviced by a copy engine, where it queues behind
 // host-to-device batches already submitted (measured: a routing pass submitted after ten 151 MB
 // copies did not start until the last copy had finished).

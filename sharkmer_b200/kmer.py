@@ -198,8 +198,8 @@ class Engine:
         self._ck(self.L.skm_route_scatter(self._h, chunk_index, d_out))
 
     # fused route + exchange (peer stores over NVLink)
-    def p2p_arena_create(self, entries_per_slot: int):
-        self._ck(self.L.skm_p2p_arena_create(self._h, entries_per_slot))
+    def p2p_arena_create(self, entries_per_slot: int, n_slots: int = 2):
+        self._ck(self.L.skm_p2p_arena_create(self._h, entries_per_slot, n_slots))
 
     def p2p_arena_handle(self, slot: int) -> bytes:
         buf = (C.c_uint8 * 64)()
@@ -228,6 +228,14 @@ class Engine:
 
     def insert_kmers_device(self, d_ptr: int, n: int):
         self._ck(self.L.skm_insert_kmers_device(self._h, d_ptr, n))
+
+    def chunks_ready(self) -> int:
+        n = C.c_uint32()
+        self._ck(self.L.skm_chunks_ready(self._h, C.byref(n)))
+        return n.value
+
+    def dma_wait(self, slot: int): self._ck(self.L.skm_dma_wait(self._h, slot))
+    def snapshot_histogram_async(self, chunk_i: int): self._ck(self.L.skm_snapshot_histogram_async(self._h, chunk_i))
 
     def snapshot_histogram(self, chunk_i: int):
         self._ck(self.L.skm_snapshot_histogram(self._h, chunk_i))

@@ -17,8 +17,9 @@ Two exchange paths:
     stores over NVLink/NVSwitch) — no local list, no collective copy; the transfer overlaps the
     extraction tile by tile inside one kernel.  Steps are ordered by a 1-element all-reduce used
     as a stream-ordered barrier; two arenas per rank give double buffering.
-  * "dma": bucket into a local list (SM work), then one peer copy per destination on the copy
-    engines into the same arenas: the NVLink transfer costs no SM time.
+  * "dma": batches are bucketed at ingest time; per chunk the copy engines push each
+    destination's block into its arena over NVLink while a CPU (gloo) group carries the counts
+    and the two barriers: the exchange needs no SM at all and hides behind the inserts.
   * "nccl": route to a local list, then all_to_all_single; the exchange of chunk c+1 overlaps
     the insert of chunk c (double-buffered torch tensors).  Also the path of the CPU tests (gloo).
 
@@ -64,16 +65,22 @@ class ShardedCounter:
     def _setup_p2p(self, arena_entries: int):
         """Allocate this rank's receive arenas and map every peer's through CUDA IPC."""
         e = self.e
-        e.p2p_arena_create(int(arena_entries))
-        mine = [e.p2p_arena_handle(slot) for slot in range(2)]
+        # "dma": one arena per chunk (up to 16), so that every chunk can be exchanged ahead of its
+        # insert while the chip is busy; "p2p": two (double buffering)
+        self._n_slots = min(16, self.n_chunks) if self.exchange == "dma" else 2
+        e.p2p_arena_create(int(arena_entries), self._n_slots)
+        mine = [e.p2p_arena_handle(slot) for slot in range(self._n_slots)]
         allh = [None] * self.world
         dist.all_gather_object(allh, mine, group=self.group)
         for r in range(self.world):
             if r != self.rank:
-                for slot in range(2):
+                for slot in range(self._n_slots):
                     e.p2p_open_peer(r, slot, allh[r][slot])
         self._tick = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._regions = e.route_regions()
+        # control plane of the "dma" exchange: a CPU group, so that metadata and barriers never
+        # need an SM (created collectively by every rank)
+        self._cpu_group = dist.new_group(backend="gloo") if self.exchange == "dma" else None
 
     # -- small helpers ---------------------------------------------------------
     def _exchange_counts(self, counts: np.ndarray) -> np.ndarray:
@@ -108,7 +115,9 @@ class ShardedCounter:
         return out
 
     def _finalize(self):
-        if self.exchange in ("p2p", "dma"):
+        if self.exchange == "dma":
+            return self._finalize_dma()
+        if self.exchange == "p2p":
             return self._finalize_p2p()
         return self._finalize_nccl()
 
@@ -173,6 +182,71 @@ class ShardedCounter:
             else:
                 e.sync()
         if self.chunks_arg == 0:
+            return None
+        cols = np.stack([e.histogram(c) for c in range(self.n_chunks)]).astype(np.int64)
+        t = torch.as_tensor(cols, device=self.device)
+        dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy().astype(np.uint64)
+
+    def _finalize_dma(self):
+        """Exchange with zero SM time: batches were bucketed by (owner, region) at ingest time; per
+        chunk the HOST gathers the counts and runs the two barriers over a CPU (gloo) group, and
+        the copy engines push every destination's block into its arena over NVLink.  Nothing here
+        needs a free SM, so it all proceeds while the persistent insert kernel of the previous
+        chunk owns the chip (a small NCCL kernel would have to wait for it to finish).
+
+            host, chunk c:  wait own insert(c-2) -> all-gather counts (= slot free everywhere)
+                            -> peer copies(c) -> wait for them -> BARRIER (all blocks landed)
+                            -> queue insert(c), queue histogram column c
+        """
+        e = self.e
+        e.finalize_external()
+        main, _ = self._streams()
+        cpu = self._cpu_group
+        regions = self._regions
+        n_slots = self._n_slots
+        inserted, pending = {}, {}
+
+        def exchange(c):
+            """Queue the peer copies of chunk c into arena slot c % n_slots (asynchronous)."""
+            slot = c % n_slots
+            counts = e.route_count(c, self.world)                 # host: waits for chunk c's bucketing only
+            if c >= n_slots:
+                inserted[c - n_slots].synchronize()               # my reads of this arena slot are over ...
+            mine = torch.from_numpy(counts.astype(np.int64).reshape(-1))
+            allt = torch.empty(self.world * mine.numel(), dtype=torch.int64)
+            dist.all_gather_into_tensor(allt, mine, group=cpu)    # ... and, once this returns, everybody's
+            allc = allt.numpy().reshape(self.world, self.world, regions)   # [src, dst, region]
+            m = allc.sum(axis=2)                                  # m[s, d] = k-mers s sends to d
+            e.route_scatter_dma(c, slot, m[:self.rank, :].sum(axis=0))
+            pending[c] = np.ascontiguousarray(allc[:, self.rank, :]).astype(np.uint64)
+            self.bytes_sent += 8 * (int(m[self.rank].sum()) - int(m[self.rank, self.rank]))
+            self.kmers_received += int(m[:, self.rank].sum())
+
+        nxt = 0
+        for c in range(self.n_chunks):
+            # keep the exchange as far ahead of the inserts as there are arena slots: the copies then
+            # run while the chip is bucketing (SM-bound) instead of inserting (memory-bound), which
+            # slows the copy engines down 3-4x
+            # ... but only as far as every rank has its batches on the device already: a chunk that
+            # is still arriving from the host must not hold up the inserts of the earlier ones
+            mine = torch.tensor([e.chunks_ready()], dtype=torch.int64)
+            allr = torch.empty(self.world, dtype=torch.int64)
+            dist.all_gather_into_tensor(allr, mine, group=cpu)
+            ahead = max(int(allr.min()), c + 1)
+            while nxt < self.n_chunks and nxt < min(ahead, c + n_slots):
+                exchange(nxt)
+                nxt += 1
+            e.dma_wait(c % n_slots)                               # my blocks of chunk c have landed at the peers
+            dist.barrier(group=cpu)                               # ... and everybody's at mine
+            e.insert_runs_device(e.p2p_arena_ptr(c % n_slots), pending.pop(c))  # asynchronous, main stream
+            ev = torch.cuda.Event()
+            ev.record(main)
+            inserted[c] = ev
+            if self.chunks_arg > 0:
+                e.snapshot_histogram_async(c)
+        if self.chunks_arg == 0:
+            e.sync()
             return None
         cols = np.stack([e.histogram(c) for c in range(self.n_chunks)]).astype(np.int64)
         t = torch.as_tensor(cols, device=self.device)

@@ -478,7 +478,7 @@ def test_sharded_p2p_scatter_single_process(skm, oracle):
     line = L + 1
     engs = [skm.Engine(k, chunks, hmax, n_ranks=world, rank=r) for r in range(world)]
     for e in engs:
-        e.p2p_arena_create(n * L)
+        e.p2p_arena_create(n * L, 2)
     for e in engs:
         for r in range(world):
             for slot in range(2):
