@@ -195,6 +195,13 @@ def run_ours(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun for --gpus > 1")
+    if world > 1 and os.environ.get("SKM_NUMA_BIND", "1") != "0":
+        # before the CUDA context and every pinned allocation: keep this rank's host buffers on the
+        # NUMA node of its GPU
+        from sharkmer_b200.multigpu import bind_to_gpu_numa
+        cpus = bind_to_gpu_numa(local_rank)
+        print(f"[rank {rank}] bound to {len(cpus) if cpus else 0} CPUs local to GPU {local_rank}"
+              + (f" ({cpus[0]}..{cpus[-1]})" if cpus else ""), file=sys.stderr)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -319,6 +326,8 @@ def run_ours(args):
         if world == 1 and eng.digest() != digest_dev:
             raise SystemExit("PARITY FAILURE: table digest differs between runs")
         st2 = eng.stage_times()
+        if world > 1:
+            print(f"[rank {rank}] e2e h2d {st2.h2d:.1f} ms, step {ms_e2e:.1f} ms", file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- totals over ranks ------------------------------------------------------------------------

@@ -1,0 +1,14 @@
+#!/bin/bash
+N=${1:-8}
+mkdir -p gpurun_out
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+timeout 900 $T bench.py --gpus $N --steps 3 --warmup 3 --no-cpu > gpurun_out/mg${N}_dma.json 2> gpurun_out/mg${N}_dma.err; echo "dma rc=$?"; tail -4 gpurun_out/mg${N}_dma.err
+python - $N <<'PY'
+import json,os,sys
+N=sys.argv[1]
+f=f'mg{N}_dma'
+if os.path.exists(f'gpurun_out/{f}.json') and os.path.getsize(f'gpurun_out/{f}.json'):
+    d=json.load(open(f'gpurun_out/{f}.json')); s=d['stage_ms']
+    print(f, 'value %.2f G/s step %.2f ms | e2e %.2f G/s %.2f ms | ins %.2f cnt %.2f part %.2f nvlink/step %.2f GB' % (d['value']/1e9, d['ms_per_step'], d['e2e']['value']/1e9, d['e2e']['ms_per_step'], s['insert'], s['count'], s['partition'], d.get('nvlink_bytes_sent_per_step_rank0',0)/1e9))
+else: print(f,'FAILED')
+PY

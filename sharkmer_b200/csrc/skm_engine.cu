@@ -70,7 +70,9 @@ struct skm_ctx {
     uint32_t n_chunks = 1;
     uint32_t n_ranks = 1;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host->device copies of raw batches, nothing else: the copy
+                                          // engine never queues behind a kernel that waits for an SM
+    cudaStream_t pack_stream = nullptr;   // pack kernels of host batches (event-chained to their copies)
     cudaStream_t dma_stream = nullptr;   // peer copies of routed k-mers (copy engines)
     cudaEvent_t ev_dma = nullptr;
     cudaStream_t part_stream = nullptr;  // pack + bucketing of incoming batches (overlaps inserts on `stream`)
@@ -115,10 +117,13 @@ struct skm_ctx {
     bool eager = true;    // SKM_EAGER=0 disables partitioning at ingest time
     size_t mem_budget = 0, list_bytes = 0;
     cudaEvent_t ev_alloc = nullptr, ev_copy = nullptr;
-    // ring of raw (ASCII) device buffers for host batches: the copy stream may run kRawRing-1 batches ahead
-    uint8_t *raw_buf[3] = {nullptr, nullptr, nullptr};
-    size_t raw_cap[3] = {0, 0, 0};
-    cudaEvent_t raw_copied[3] = {nullptr, nullptr, nullptr}, raw_packed[3] = {nullptr, nullptr, nullptr};
+    // ring of raw (ASCII) device buffers for host batches: the copy stream may run kRawRing-1 batches
+    // ahead of the pack kernels (which may be waiting for the insert kernel to release the SMs)
+    static constexpr uint32_t kRawRing = 4;
+    uint8_t *raw_buf[kRawRing] = {};
+    size_t raw_cap[kRawRing] = {};
+    cudaEvent_t raw_copied[kRawRing] = {}, raw_packed[kRawRing] = {};
+    bool raw_in_use[kRawRing] = {};
     uint32_t raw_next = 0;
 
     // peer-to-peer routing: receive arenas of this rank and the peers' mapped pointers
@@ -425,6 +430,7 @@ struct WorkStream {  // selects the stream the bucketing helpers launch on, for 
 
 int32_t sync_all(skm_ctx *c) {
     CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->pack_stream));
     CU(cudaStreamSynchronize(c->part_stream));
     CU(cudaStreamSynchronize(c->dma_stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -814,9 +820,9 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force
     return SKM_OK;
 }
 
-// Stage one batch that is already in device memory.
-// Pack one batch that is in device memory, on `pack_stream` (the copy stream for host batches, so
-// the pack follows its own copy and nothing else), then bucket it eagerly on c->work.
+// Stage one batch that is already in device memory: pack it on `pack_stream` (for host batches the
+// ctx's pack stream, which waits for the batch's copy and nothing else), then bucket it eagerly on
+// c->work.
 int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t n_bytes,
                      cudaStream_t pack_stream = nullptr) {
     if (n_bytes == 0) return SKM_OK;
@@ -902,6 +908,7 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     }
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->part_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->dma_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_dma, cudaEventDisableTiming));
@@ -981,6 +988,7 @@ void skm_destroy(skm_ctx *c) {
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->pack_stream);
         cudaStreamSynchronize(c->part_stream);
         for (auto &cs : c->chunks)
             for (auto &sg : cs.segs) {
@@ -1002,7 +1010,7 @@ void skm_destroy(skm_ctx *c) {
             cudaFree(c->arena[sl]);
             if (c->ev_slot[sl]) cudaEventDestroy(c->ev_slot[sl]);
         }
-        for (int i = 0; i < 3; i++) {
+        for (uint32_t i = 0; i < skm_ctx::kRawRing; i++) {
             cudaFree(c->raw_buf[i]);
             if (c->raw_copied[i]) cudaEventDestroy(c->raw_copied[i]);
             if (c->raw_packed[i]) cudaEventDestroy(c->raw_packed[i]);
@@ -1028,6 +1036,7 @@ void skm_destroy(skm_ctx *c) {
         for (auto e : c->event_pool) cudaEventDestroy(e);
         if (c->own_stream) cudaStreamDestroy(c->stream);
         cudaStreamDestroy(c->copy_stream);
+        cudaStreamDestroy(c->pack_stream);
         cudaStreamDestroy(c->part_stream);
         cudaStreamDestroy(c->dma_stream);
         if (c->ev_dma) cudaEventDestroy(c->ev_dma);
@@ -1092,10 +1101,13 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
     DeviceGuard g(c->device);
     // The copy runs on its own stream, into a ring of persistent raw buffers, so that it overlaps
     // the kernels of earlier batches (a buffer is reused once its pack kernel has finished):
-    //   copy stream   : H2D(b) -> pack(b) -> [ready]  -> H2D(b+1) -> ...
-    //   routing stream:                      wait [ready] -> bucket(b)
+    //   copy stream   : wait [packed(b-R)] -> H2D(b) -> [copied(b)] -> H2D(b+1) -> ...
+    //   pack stream   : wait [copied(b)] -> pack(b) -> [packed(b) = ready]
+    //   routing stream: wait [ready] -> bucket(b)
     //   main stream   : inserts (skm_finalize)
-    const uint32_t b = c->raw_next++ % 3;
+    // The copies have a stream of their own: a pack kernel that is waiting for the (persistent)
+    // insert kernel to release the SMs must not hold back the next batch's copy.
+    const uint32_t b = c->raw_next++ % skm_ctx::kRawRing;
     if (!c->raw_copied[b]) {
         CU(cudaEventCreateWithFlags(&c->raw_copied[b], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->raw_packed[b], cudaEventDisableTiming));
@@ -1103,6 +1115,7 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
     if (c->raw_cap[b] < n_bytes) {
         if (c->raw_buf[b]) {
             CU(cudaStreamSynchronize(c->copy_stream));
+            CU(cudaStreamSynchronize(c->pack_stream));
             CU(cudaFree(c->raw_buf[b]));
             c->raw_buf[b] = nullptr;
             c->raw_cap[b] = 0;
@@ -1111,16 +1124,20 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
         CU(cudaMalloc((void **)&c->raw_buf[b], cap));
         c->raw_cap[b] = cap;
     }
+    if (c->raw_in_use[b]) CU(cudaStreamWaitEvent(c->copy_stream, c->raw_packed[b], 0));  // buffer free again
     {
         Span sp(c, ST_H2D, c->copy_stream);
         CU(cudaMemcpyAsync(c->raw_buf[b], seqs, n_bytes, cudaMemcpyHostToDevice, c->copy_stream));
     }
     CU(cudaEventRecord(c->raw_copied[b], c->copy_stream));
     if (!(flags & SKM_INGEST_ASYNC)) CU(cudaEventSynchronize(c->raw_copied[b]));
-    // the pack kernel follows its copy on the copy stream (so the ring buffer is reused in stream
-    // order); bucketing runs on the routing stream once the pack has fired
+    // the pack kernel waits for its copy on the pack stream; bucketing runs on the routing stream
+    // once the pack has fired
+    CU(cudaStreamWaitEvent(c->pack_stream, c->raw_copied[b], 0));
     WorkStream ws(c, c->part_stream);
-    rc = stage_device(c, chunk, c->raw_buf[b], n_bytes, c->copy_stream);
+    rc = stage_device(c, chunk, c->raw_buf[b], n_bytes, c->pack_stream);
+    CU(cudaEventRecord(c->raw_packed[b], c->pack_stream));
+    c->raw_in_use[b] = true;
     return rc;
 }
 

@@ -34,6 +34,37 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index: int) -> list[int] | None:
+    """Pin the calling thread (and the threads it spawns later) to the CPUs NVML reports as local to
+    GPU `device_index`, so that pinned staging buffers allocated afterwards land on that GPU's NUMA
+    node. With one process per GPU and no binding, half the ranks of an 8-GPU box read their FASTQ
+    bytes across the socket interconnect and host->device bandwidth drops by 2x (profiles/
+    experiments_r01.md #24). Call before the first pinned allocation; returns the CPU list, or None
+    when NVML is unavailable (binding is an optimisation, never a requirement)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        if not uuid.startswith("GPU-"):
+            uuid = "GPU-" + uuid
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except TypeError:
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 class _CudaArray:
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
