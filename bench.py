@@ -222,7 +222,8 @@ def run_ours(args):
         # these two paths bucket at routing time (p2p: scatter kernel fused with the peer stores);
         # the "dma" path buckets at ingest time and lets the copy engines move the runs
         os.environ["SKM_EAGER"] = "0"
-    stream = torch.cuda.Stream(device=dev)
+    # high priority: the inserts (this stream) outrank the engine's bucketing streams
+    stream = torch.cuda.Stream(device=dev, priority=-1 if os.environ.get("SKM_PRIO", "1") != "0" else 0)
     eng = kmer.Engine(K, CHUNKS, HISTO_MAX, capacity_hint=hint, device=local_rank, insert_mode=mode,
                       n_ranks=world, rank=rank, stream=stream.cuda_stream)
     st, nt = o.rate_to_thresh(SUB_RATE), o.rate_to_thresh(N_RATE)

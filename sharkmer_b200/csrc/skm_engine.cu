@@ -78,7 +78,8 @@ struct skm_ctx {
     cudaStream_t part_stream = nullptr;  // pack + bucketing of incoming batches (overlaps inserts on `stream`)
     cudaStream_t work = nullptr;         // stream the bucketing helpers currently launch on
     cudaEvent_t ev_main = nullptr;
-    uint32_t insert_ctas_per_sm = 6;      // persistent insert grid (SKM_INSERT_CTAS); measured best: 6
+    uint32_t insert_ctas_per_sm = 5;      // persistent insert grid (SKM_INSERT_CTAS): 5 of the 6 CTAs that fit,
+                                          // the rest of the SM is for the bucketing of the next chunk
     int sm_count = 148;
 
     Slot *table = nullptr;
@@ -905,7 +906,11 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
         c->stream = (cudaStream_t)(uintptr_t)c->p.stream;
         c->own_stream = false;
     } else {
-        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        // the inserts outrank the bucketing of later batches (routing / pack streams, default = lowest
+        // priority): CTAs of the bucketing kernels only fill what the insert kernel leaves free
+        int prio_least = 0, prio_greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
     }
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));

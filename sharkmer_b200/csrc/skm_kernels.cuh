@@ -543,8 +543,15 @@ __global__ void copy_descs_kernel(const RunDesc *__restrict__ src, RunDesc *__re
 // handed out in list order, which keeps the chip on a few neighbouring table regions.
 static constexpr uint32_t kWarpTile = 32 * kListPerThread;  // k-mers per warp tile
 
+// 6 CTAs per SM caps the kernel at 40 registers (no spills): 5 resident CTAs then leave 14 K registers
+// per SM, enough for one CTA of a bucketing kernel of the next chunk to run beside the inserts
+// (profiles/experiments_r01.md #25: 43 registers, 5 resident, nothing beside them: 62.0 ms per step;
+// 40 registers, 6 resident: 58.3 ms; 40 registers, 5 resident + bucketing beside them: 54.0 ms).
+#ifndef SKM_INSERT_MIN_CTAS
+#define SKM_INSERT_MIN_CTAS 6
+#endif
 template <int D, bool kHisto>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, D == 1 ? SKM_INSERT_MIN_CTAS : 1)
 insert_runs_kernel(const RunDesc *__restrict__ descs, uint32_t n_desc, RunDesc single,
                    const unsigned long long *__restrict__ n_dev, unsigned long long n_tiles,
                    unsigned long long *__restrict__ tile_counter, TableRef table,

@@ -10,6 +10,7 @@
 
 #include "../../include/sharkmer_b200.h"
 
+static bool g_discard = false;  // --bench: time the framing only, keep nothing
 struct skm_ctx {
     skm_params p;
     std::vector<std::string> chunk_data;
@@ -34,9 +35,10 @@ int32_t skm_pinned_free(skm_ctx *, void *p) { std::free(p); return SKM_OK; }
 int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64_t n, uint32_t) {
     if (chunk >= c->chunk_data.size()) { c->err = "chunk out of range"; return SKM_ERR_INVALID_ARG; }
     if (n && seqs[n - 1] != '\n') { c->err = "batch must end with newline"; return SKM_ERR_INVALID_ARG; }
-    c->chunk_data[chunk].append(reinterpret_cast<const char *>(seqs), n);
+    if (!g_discard) c->chunk_data[chunk].append(reinterpret_cast<const char *>(seqs), n);
     return SKM_OK;
 }
+int32_t skm_sync(skm_ctx *) { return SKM_OK; }
 int32_t skm_finalize(skm_ctx *) { return SKM_OK; }
 int32_t skm_histogram(skm_ctx *, uint32_t, uint64_t *, uint64_t) { return SKM_ERR_STATE; }
 int32_t skm_totals_get(skm_ctx *, skm_totals *t) { std::memset(t, 0, sizeof *t); return SKM_OK; }
@@ -49,13 +51,14 @@ int32_t skm_insert_counts(skm_ctx *, const uint64_t *, const uint32_t *, uint64_
 }
 
 // harness: same flags as the CLI; dumps chunk_<c>.txt + counts.txt into --dump DIR
-#include "../../sharkmer_b200/host/ingest.hpp"
+#include "../../sharkmer_b200/host/fastq_parallel.hpp"
 
 int main(int argc, char **argv) {
     uint32_t k = 21, chunks = 0;
     uint64_t max_reads = 0, validate_every = 0;
-    size_t buffer_bytes = 0;
-    bool paired = false;
+    size_t buffer_bytes = 0, window_bytes = size_t(128) << 20;
+    unsigned threads = 0;
+    bool paired = false, serial = false;
     std::string dump = ".";
     std::vector<std::string> inputs;
     for (int i = 1; i < argc; i++) {
@@ -66,12 +69,29 @@ int main(int argc, char **argv) {
         else if (a == "--validate-every") validate_every = std::strtoull(argv[++i], nullptr, 10);
         else if (a == "--buffer-bytes") buffer_bytes = std::strtoull(argv[++i], nullptr, 10);
         else if (a == "--paired") paired = true;
+        else if (a == "--serial") serial = true;
+        else if (a == "--bench") g_discard = true;
+        else if (a == "--threads" || a == "-t") threads = (unsigned)std::atoi(argv[++i]);
+        else if (a == "--window-bytes") window_bytes = std::strtoull(argv[++i], nullptr, 10);
         else if (a == "--dump") dump = argv[++i];
         else inputs.push_back(a);
     }
     try {
         skm::Engine eng(k, chunks);
-        {
+        if (!serial) {
+            skm::ParallelIngest st(eng, threads, window_bytes);
+            if (paired) {
+                if (max_reads > 0 && max_reads % 2 != 0) max_reads += 1;
+                st.read_fastq_paired(inputs[0], inputs[1], max_reads, validate_every);
+            } else {
+                for (auto &p : inputs)
+                    if (st.read_fastq(p, max_reads, validate_every)) break;
+            }
+            st.finish();
+            FILE *f = std::fopen((dump + "/counts.txt").c_str(), "w");
+            std::fprintf(f, "%llu %llu\n", (unsigned long long)st.n_reads_read, (unsigned long long)st.n_bases_read);
+            std::fclose(f);
+        } else {
             skm::Batcher st(eng, buffer_bytes);
             if (paired) {
                 if (max_reads > 0 && max_reads % 2 != 0) max_reads += 1;
