@@ -30,7 +30,6 @@ constexpr double kHardLoad = 0.90;      // the host's upper bound on the load ne
 constexpr double kTargetLoad = 0.60;    // load at capacity_hint
 constexpr uint64_t kMinTile = 1ull << 22;  // k-mers; smallest tile worth a launch near the limit
 constexpr uint32_t kMinLog2Cap = 16;
-constexpr uint32_t kMaxBuckets = 1024;  // scatter stages a CTA's k-mers in bucket order: runs stay >= 12 k-mers
 constexpr uint32_t kMaxRuns = 4096;     // runs per insert launch
 constexpr uint32_t kDescRing = 4;
 constexpr uint64_t kMaxListKmers = 1ull << 30;  // k-mer list budget per partition pass (8 GiB)
@@ -48,6 +47,10 @@ struct Segment {
     cudaEvent_t ready = nullptr;    // fires when the segment's pack (+ bucketing) has finished
     uint32_t n_buckets = 0;
     unsigned long long *d_counts = nullptr;  // per-bucket counts on the device (multi-GPU routing)
+    // capped layout (CapLayout; single GPU): h_offsets then holds the n_buckets bucket totals + the
+    // overflow total instead of offsets, and codes/breaks stay alive until the totals were checked
+    uint64_t cap = 0, ovf_cap = 0;
+    size_t list_cells = 0;  // cells allocated for `list`
 };
 
 struct ChunkState {
@@ -72,7 +75,6 @@ struct skm_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host->device copies of raw batches, nothing else: the copy
                                           // engine never queues behind a kernel that waits for an SM
-    cudaStream_t pack_stream = nullptr;   // pack kernels of host batches (event-chained to their copies)
     cudaStream_t dma_stream = nullptr;   // peer copies of routed k-mers (copy engines)
     cudaEvent_t ev_dma = nullptr;
     cudaStream_t part_stream = nullptr;  // pack + bucketing of incoming batches (overlaps inserts on `stream`)
@@ -116,6 +118,8 @@ struct skm_ctx {
     std::vector<uint64_t *> off_blocks;
     size_t off_used = 0;  // entries used in the last block
     bool eager = true;    // SKM_EAGER=0 disables partitioning at ingest time
+    bool capped = true;   // SKM_CAPPED=0: single-GPU eager bucketing uses the exact two-pass layout
+    uint32_t n_capped_fallbacks = 0;
     size_t mem_budget = 0, list_bytes = 0;
     cudaEvent_t ev_alloc = nullptr, ev_copy = nullptr;
     // ring of raw (ASCII) device buffers for host batches: the copy stream may run kRawRing-1 batches
@@ -232,8 +236,25 @@ struct Span {
     }
 };
 
-// Call only after the streams are synchronised.
+// Call only after the streams are synchronised.  SKM_TRACE=<file>: also append one line per span
+// ("batch stage start_ms end_ms", times relative to the first span recorded since the last
+// collection) — a poor man's timeline of the copy / pack / bucketing / insert streams.
 void collect_spans(skm_ctx *c) {
+    static const char *trace_path = getenv("SKM_TRACE");
+    if (trace_path && !c->spans.empty()) {
+        static const char *names[] = {"h2d", "pack", "count", "partition", "insert", "histogram", "grow", "other"};
+        static int batch = 0;
+        if (FILE *f = std::fopen(trace_path, "a")) {
+            for (auto &t : c->spans) {
+                float a = 0, b = 0;
+                if (cudaEventElapsedTime(&a, c->spans[0].a, t.a) == cudaSuccess &&
+                    cudaEventElapsedTime(&b, c->spans[0].a, t.b) == cudaSuccess)
+                    std::fprintf(f, "%d %s %.3f %.3f\n", batch, names[t.stage < 8 ? t.stage : 7], a, b);
+            }
+            std::fclose(f);
+        }
+        batch++;
+    }
     for (auto &t : c->spans) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) c->stage_ms[t.stage] += ms;
@@ -431,7 +452,6 @@ struct WorkStream {  // selects the stream the bucketing helpers launch on, for 
 
 int32_t sync_all(skm_ctx *c) {
     CU(cudaStreamSynchronize(c->copy_stream));
-    CU(cudaStreamSynchronize(c->pack_stream));
     CU(cudaStreamSynchronize(c->part_stream));
     CU(cudaStreamSynchronize(c->dma_stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -489,11 +509,45 @@ int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketF
     for (size_t s = s0; s < s1; s++) {
         const Segment &sg = cs.segs[s];
         if (!sg.n_units || !sg.codes) continue;
-        bucket_scatter_kernel<<<grid_for(sg.n_units, kScatterThreads), kScatterThreads, smem, c->work>>>(
-            sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, bases);
+        bucket_scatter_kernel<false><<<grid_for(sg.n_units, kScatterThreads), kScatterThreads, smem, c->work>>>(
+            sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, bases, CapLayout{},
+            nullptr);
         c->launches++;
         c->stage_launches[ST_PART]++;
     }
+    CU(cudaGetLastError());
+    return SKM_OK;
+}
+
+// Forget a capped list (waits for its bucketing): frees it on `st` and takes back the windows its
+// scatter added to the chunk's counter, so that the exact path can count them again.
+int32_t drop_capped_list(skm_ctx *c, uint32_t chunk, Segment &sg, cudaStream_t st) {
+    CU(cudaEventSynchronize(sg.ready));
+    uint64_t counted = 0;
+    for (uint32_t r = 0; r < sg.n_buckets; r++) counted += sg.h_offsets[r];
+    adjust_counter_kernel<<<1, 1, 0, st>>>(&c->d_cc[chunk].n_windows, 0ull - counted);
+    c->launches++;
+    CU(cudaFreeAsync(sg.list, st));
+    c->list_bytes -= std::min<size_t>(c->list_bytes, sg.list_cells * sizeof(uint64_t));
+    sg.list = nullptr;
+    sg.cap = 0;
+    return SKM_OK;
+}
+
+// One-pass bucketing of one segment into the capped layout (no counting pass): see CapLayout.
+int32_t bucket_scatter_capped(skm_ctx *c, uint32_t chunk, const Segment &sg, BucketFn fn, uint32_t n_buckets,
+                              unsigned long long *d_out, CapLayout lay) {
+    zero_async(c, c->d_bucket_cursors, (n_buckets + 1) * sizeof(uint64_t), c->work);
+    Span sp(c, ST_PART, c->work);
+    OwnerBases bases{};
+    bases.dst[0] = d_out;
+    bases.uniform = 1;
+    bases.log2_regions = fn.log2_regions;
+    bucket_scatter_kernel<true><<<grid_for(sg.n_units, kScatterThreads), kScatterThreads,
+                                  scatter_smem_bytes(n_buckets, true), c->work>>>(
+        sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, bases, lay, &c->d_cc[chunk]);
+    c->launches++;
+    c->stage_launches[ST_PART]++;
     CU(cudaGetLastError());
     return SKM_OK;
 }
@@ -792,6 +846,34 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force
     const uint32_t nb = c->n_ranks << fn.log2_regions;
     uint64_t *h_off = alloc_offsets(c, nb + 1);
     if (!h_off) return force ? fail(c, SKM_ERR_OOM, "pinned allocation failed") : SKM_OK;
+    if (c->n_ranks == 1 && c->capped && !force && sg.n_bytes < (3ull << 30)) {
+        // single GPU: one pass, no counting (the routing of the multi-GPU paths needs exact,
+        // contiguous per-owner blocks and keeps the two-pass version below)
+        CapLayout lay;
+        lay.cap = ((sg.n_bytes / nb + sg.n_bytes / (16ull * nb) + 1024) + 15) & ~15ull;
+        lay.ovf_base = lay.cap * nb;
+        lay.ovf_cap = sg.n_bytes / 8 + 4096;
+        const size_t cells = (size_t)(lay.ovf_base + lay.ovf_cap);
+        if (c->list_bytes + cells * 8 + 3 * c->capacity * sizeof(Slot) + (4ull << 30) > c->mem_budget) return SKM_OK;
+        CU(cudaStreamWaitEvent(c->work, sg.ready, 0));
+        if (cudaMallocAsync((void **)&sg.list, cells * sizeof(uint64_t), c->work) != cudaSuccess) {
+            cudaGetLastError();
+            sg.list = nullptr;
+            return SKM_OK;
+        }
+        int32_t rc = bucket_scatter_capped(c, chunk, sg, fn, nb, sg.list, lay);
+        if (rc) return rc;
+        copy_words_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_cursors, (unsigned long long *)h_off, nb + 1);
+        c->launches++;
+        sg.h_offsets = h_off;
+        sg.n_buckets = nb;
+        sg.cap = lay.cap;
+        sg.ovf_cap = lay.ovf_cap;
+        sg.list_cells = cells;
+        c->list_bytes += cells * 8;
+        CU(cudaEventRecord(sg.ready, c->work));  // `ready` now also covers the list + totals
+        return SKM_OK;
+    }
     // the pack kernel ran on another stream (the copy stream): order the bucketing after it.  Only
     // here — a wait queued for a batch that is NOT bucketed now would make everything later on this
     // stream (e.g. the routing of chunk 0) wait for the arrival of the LAST batch.
@@ -805,7 +887,8 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force
     if (rc) return rc;
     rc = bucket_scatter(c, chunk, seg_index, seg_index + 1, fn, nb, sg.list);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(h_off, c->d_bucket_offsets, (nb + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->work));
+    copy_words_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_offsets, (unsigned long long *)h_off, nb + 1);
+    c->launches++;
     if (c->n_ranks > 1) {
         CU(cudaMallocAsync((void **)&sg.d_counts, nb * sizeof(uint64_t), c->work));
         CU(cudaMemcpyAsync(sg.d_counts, c->d_bucket_counts, nb * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->work));
@@ -816,16 +899,16 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force
     sg.breaks = nullptr;
     sg.h_offsets = h_off;
     sg.n_buckets = nb;
+    sg.list_cells = sg.n_bytes;
     c->list_bytes += need;
     CU(cudaEventRecord(sg.ready, c->work));  // `ready` now also covers the list + offsets
     return SKM_OK;
 }
 
-// Stage one batch that is already in device memory: pack it on `pack_stream` (for host batches the
-// ctx's pack stream, which waits for the batch's copy and nothing else), then bucket it eagerly on
-// c->work.
+// Stage one batch that is already in device memory: pack it on `pack_stream` (default c->work;
+// `packed` fires once the raw bytes are no longer needed), then bucket it eagerly on c->work.
 int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t n_bytes,
-                     cudaStream_t pack_stream = nullptr) {
+                     cudaStream_t pack_stream = nullptr, cudaEvent_t packed = nullptr) {
     if (n_bytes == 0) return SKM_OK;
     if (!pack_stream) pack_stream = c->work;
     Segment sg;
@@ -843,6 +926,7 @@ int32_t stage_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uint64_t
     CU(cudaGetLastError());
     sg.ready = get_event(c);
     CU(cudaEventRecord(sg.ready, pack_stream));  // packed: the raw buffer may be overwritten, the codes read
+    if (packed) CU(cudaEventRecord(packed, pack_stream));
     c->pos_base += n_bytes;
     c->chunks[chunk].segs.push_back(sg);
     c->chunks[chunk].n_bytes += n_bytes;
@@ -913,7 +997,6 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
         CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
     }
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->part_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->dma_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_dma, cudaEventDisableTiming));
@@ -928,8 +1011,10 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     CU(cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CU(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(bucket_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)scatter_smem_bytes(kMaxBuckets)));
+    CU(cudaFuncSetAttribute(bucket_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)scatter_smem_bytes(kMaxBuckets, true)));
 
     CU(cudaMalloc((void **)&c->d_cc, c->n_chunks * sizeof(ChunkCounters)));
     CU(cudaMemset(c->d_cc, 0, c->n_chunks * sizeof(ChunkCounters)));
@@ -945,6 +1030,7 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     c->track_histo = c->p.chunks > 0 && !getenv("SKM_HISTO_SCAN");
     if (const char *g = getenv("SKM_PIPE_DEPTH")) c->pipe_depth = atoi(g);
     if (const char *g = getenv("SKM_EAGER")) c->eager = atoi(g) != 0;
+    if (const char *g = getenv("SKM_CAPPED")) c->capped = atoi(g) != 0;
     {
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
@@ -993,7 +1079,6 @@ void skm_destroy(skm_ctx *c) {
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copy_stream);
-        cudaStreamSynchronize(c->pack_stream);
         cudaStreamSynchronize(c->part_stream);
         for (auto &cs : c->chunks)
             for (auto &sg : cs.segs) {
@@ -1041,7 +1126,6 @@ void skm_destroy(skm_ctx *c) {
         for (auto e : c->event_pool) cudaEventDestroy(e);
         if (c->own_stream) cudaStreamDestroy(c->stream);
         cudaStreamDestroy(c->copy_stream);
-        cudaStreamDestroy(c->pack_stream);
         cudaStreamDestroy(c->part_stream);
         cudaStreamDestroy(c->dma_stream);
         if (c->ev_dma) cudaEventDestroy(c->ev_dma);
@@ -1107,11 +1191,13 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
     // The copy runs on its own stream, into a ring of persistent raw buffers, so that it overlaps
     // the kernels of earlier batches (a buffer is reused once its pack kernel has finished):
     //   copy stream   : wait [packed(b-R)] -> H2D(b) -> [copied(b)] -> H2D(b+1) -> ...
-    //   pack stream   : wait [copied(b)] -> pack(b) -> [packed(b) = ready]
-    //   routing stream: wait [ready] -> bucket(b)
+    //   routing stream: wait [copied(b)] -> pack(b) -> [packed(b)] -> bucket(b) -> [ready] -> pack(b+1) ...
     //   main stream   : inserts (skm_finalize)
     // The copies have a stream of their own: a pack kernel that is waiting for the (persistent)
-    // insert kernel to release the SMs must not hold back the next batch's copy.
+    // insert kernel to leave it room must not hold back the next batch's copy.  Pack and bucketing
+    // share ONE stream on purpose: beside the insert kernel there is room for one of their CTAs per
+    // SM, and two kernels fighting for it (pack of batch b+1 against bucketing of batch b) slowed
+    // both them and the inserts down (profiles/experiments_r01.md #26).
     const uint32_t b = c->raw_next++ % skm_ctx::kRawRing;
     if (!c->raw_copied[b]) {
         CU(cudaEventCreateWithFlags(&c->raw_copied[b], cudaEventDisableTiming));
@@ -1120,8 +1206,7 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
     if (c->raw_cap[b] < n_bytes) {
         if (c->raw_buf[b]) {
             CU(cudaStreamSynchronize(c->copy_stream));
-            CU(cudaStreamSynchronize(c->pack_stream));
-            CU(cudaFree(c->raw_buf[b]));
+                    CU(cudaFree(c->raw_buf[b]));
             c->raw_buf[b] = nullptr;
             c->raw_cap[b] = 0;
         }
@@ -1136,14 +1221,10 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
     }
     CU(cudaEventRecord(c->raw_copied[b], c->copy_stream));
     if (!(flags & SKM_INGEST_ASYNC)) CU(cudaEventSynchronize(c->raw_copied[b]));
-    // the pack kernel waits for its copy on the pack stream; bucketing runs on the routing stream
-    // once the pack has fired
-    CU(cudaStreamWaitEvent(c->pack_stream, c->raw_copied[b], 0));
+    CU(cudaStreamWaitEvent(c->part_stream, c->raw_copied[b], 0));
     WorkStream ws(c, c->part_stream);
-    rc = stage_device(c, chunk, c->raw_buf[b], n_bytes, c->pack_stream);
-    CU(cudaEventRecord(c->raw_packed[b], c->pack_stream));
     c->raw_in_use[b] = true;
-    return rc;
+    return stage_device(c, chunk, c->raw_buf[b], n_bytes, c->part_stream, c->raw_packed[b]);
 }
 
 int32_t skm_ingest_reads(skm_ctx *c, uint32_t chunk, const uint8_t *bases, const uint64_t *offsets,
@@ -1246,15 +1327,43 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
                 if (sg.list) CU(cudaEventSynchronize(sg.ready));   // host needs the bucket offsets
                 else CU(cudaStreamWaitEvent(c->stream, sg.ready, 0));  // packed data is consumed on the main stream
             }
+            for (auto &sg : cs.segs) {
+                if (!sg.list || !sg.cap) continue;
+                if (sg.h_offsets[sg.n_buckets] > sg.ovf_cap) {
+                    // capped layout overflowed even its overflow run (heavily repeated k-mers): drop
+                    // the list and let (2) below bucket the segment exactly (its packed form is still here)
+                    rc = drop_capped_list(c, ch, sg, c->stream);
+                    if (rc) return rc;
+                    c->n_capped_fallbacks++;
+                } else {  // the packed form is no longer needed
+                    CU(cudaFreeAsync(sg.codes, c->stream));
+                    CU(cudaFreeAsync(sg.breaks, c->stream));
+                    sg.codes = nullptr;
+                    sg.breaks = nullptr;
+                }
+            }
             if (nb) {
                 std::vector<RunDesc> runs;
                 for (uint32_t r = 0; r < nb; r++)
-                    for (auto &sg : cs.segs)
-                        if (sg.list && sg.h_offsets[r + 1] > sg.h_offsets[r])
+                    for (auto &sg : cs.segs) {
+                        if (!sg.list) continue;
+                        if (r >= sg.n_buckets) continue;
+                        if (sg.cap) {
+                            const uint64_t n = std::min<uint64_t>(sg.h_offsets[r], sg.cap);
+                            if (n) runs.push_back(RunDesc{sg.list + r * sg.cap, nullptr, n, 0});
+                        } else if (sg.h_offsets[r + 1] > sg.h_offsets[r]) {
                             runs.push_back(RunDesc{sg.list + sg.h_offsets[r], nullptr,
                                                    sg.h_offsets[r + 1] - sg.h_offsets[r], 0});
-                rc = insert_runs(c, runs);
-                if (rc) return rc;
+                        }
+                    }
+                for (auto &sg : cs.segs)  // overflow runs: any region, inserted last
+                    if (sg.list && sg.cap && sg.h_offsets[sg.n_buckets])
+                        runs.push_back(RunDesc{sg.list + (uint64_t)sg.n_buckets * sg.cap, nullptr,
+                                               sg.h_offsets[sg.n_buckets], 0});
+                if (!runs.empty()) {
+                    rc = insert_runs(c, runs);
+                    if (rc) return rc;
+                }
             }
         }
         // (2) segments still packed: bucket now (partitioned) or extract+insert directly
@@ -1277,7 +1386,7 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
             if (sg.breaks) CU(cudaFreeAsync(sg.breaks, c->stream));
             if (sg.list) {
                 CU(cudaFreeAsync(sg.list, c->stream));
-                c->list_bytes -= std::min<size_t>(c->list_bytes, sg.n_bytes * sizeof(uint64_t));
+                c->list_bytes -= std::min<size_t>(c->list_bytes, sg.list_cells * sizeof(uint64_t));
             }
             sg.codes = nullptr;
             sg.breaks = nullptr;
@@ -1735,7 +1844,14 @@ namespace {
 int32_t bucketed_chunk(skm_ctx *c, uint32_t chunk) {
     ChunkState &cs = c->chunks[chunk];
     for (size_t i = 0; i < cs.segs.size(); i++) {
-        if (cs.segs[i].list) continue;
+        Segment &sg = cs.segs[i];
+        if (sg.list && sg.cap) {
+            // capped single-GPU layout, but the routing API wants exact contiguous blocks (a sharded
+            // driver with one rank): undo it — the packed form is still there — and bucket exactly
+            int32_t rc = drop_capped_list(c, chunk, sg, c->work);
+            if (rc) return rc;
+        }
+        if (sg.list) continue;
         int32_t rc = eager_partition(c, chunk, i, true);
         if (rc) return rc;
     }

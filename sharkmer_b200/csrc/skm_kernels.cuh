@@ -537,6 +537,13 @@ __global__ void copy_descs_kernel(const RunDesc *__restrict__ src, RunDesc *__re
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// Same reason, other direction: small results the host waits for (bucket totals) are stored to
+// pinned host memory by a kernel instead of a device-to-host copy.
+__global__ void copy_words_kernel(const unsigned long long *__restrict__ src, unsigned long long *__restrict__ dst,
+                                  uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 // Persistent kernel: every WARP pulls the next 512-k-mer tile from a global counter, so there is
 // no CTA-wide barrier inside the loop (ncu on the one-tile-per-CTA version: 25-30 % of issue
 // slots stalled on barriers because probe latencies differ between warps) and tiles are still
@@ -925,13 +932,23 @@ bucket_scan_kernel(const unsigned long long *__restrict__ counts, uint32_t n_buc
 // shared memory, then copied out so that consecutive threads write consecutive cells of a
 // bucket run (whole 32-byte sectors / 128-byte lines instead of lone 8-byte stores, which cost
 // one L2 request each).  One CTA = kScatterThreads units = kScatterThreads*32 bases.
+static constexpr uint32_t kMaxBuckets = 1024;  // scatter stages a CTA's k-mers in bucket order: runs stay >= 12 k-mers
 static constexpr uint32_t kScatterThreads = 384;                    // 12288 positions per CTA
 static constexpr uint32_t kScatterStage = kScatterThreads * 32;     // max k-mers per CTA
 
-__host__ __device__ inline size_t scatter_smem_bytes(uint32_t n_buckets) {
-    // staging (u64) | s_gbase (u64) | s_cnt (u32) | s_start (u32, n_buckets + 1)
-    return (size_t)kScatterStage * 8 + (size_t)n_buckets * 8 + (size_t)n_buckets * 4 + ((size_t)n_buckets + 2) * 4;
+__host__ __device__ inline size_t scatter_smem_bytes(uint32_t n_buckets, bool capped = false) {
+    // staging (u64) | exact: s_gbase (u64) + s_cs (u32) | capped: s_cs, s_g, s_room, s_obase (u32 each)
+    return (size_t)kScatterStage * 8 + (size_t)n_buckets * (capped ? 16 : 12);
 }
+
+// Capped layout (single GPU, no counting pass): bucket b owns cells [b * cap, (b + 1) * cap) of the
+// list; what does not fit goes to one overflow run of `ovf_cap` cells at `ovf_base`.  With a
+// uniform hash the buckets of a batch differ by a few sigma, so `cap` = mean + 6 % and the overflow
+// run stays empty; skewed inputs (one k-mer repeated millions of times) spill into it, and if even
+// that is too small the host sees cursors[n_buckets] > ovf_cap and re-buckets the batch exactly.
+struct CapLayout {
+    unsigned long long cap, ovf_base, ovf_cap;
+};
 
 // Where each owner's buckets go.  dst[o] is biased so that `dst[o] + global cursor value` is the
 // right cell: on one GPU every entry is the local list; in the fused multi-GPU route entry o is
@@ -945,29 +962,50 @@ struct OwnerBases {
     uint32_t uniform;       // 1 => all owners share dst[0]
 };
 
-__global__ void __launch_bounds__(kScatterThreads)
+// kCapped = false: cursors[] start at the exact bucket offsets of the counting pass.
+// kCapped = true : cursors[] start at 0 and end as the bucket totals (cursors[n_buckets] = overflow
+//                  total); the CTA also adds its windows to cc->n_windows (no counting pass did).
+static constexpr uint32_t kScatterPer = (kMaxBuckets + kScatterThreads - 1) / kScatterThreads;  // buckets per thread
+static_assert(kScatterStage < (1u << 16), "stage offsets and ranks share one 32-bit word");
+
+template <bool kCapped>
+__global__ void __launch_bounds__(kScatterThreads, 5)  // <= 32 registers: one CTA fits beside the inserts
 bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
                       uint64_t u_begin, uint64_t u_end, uint32_t k, BucketFn fn, uint32_t n_buckets,
-                      unsigned long long *__restrict__ cursors, OwnerBases bases) {
+                      unsigned long long *__restrict__ cursors, OwnerBases bases, CapLayout lay,
+                      ChunkCounters *__restrict__ cc) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long *stage = reinterpret_cast<unsigned long long *>(s_raw);
-    unsigned long long *s_gbase = stage + kScatterStage;
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_gbase + n_buckets);
-    uint32_t *s_start = s_cnt + n_buckets;  // n_buckets + 1
+    unsigned long long *s_gbase = stage + kScatterStage;  // exact: first list cell of this CTA's run
+    // s_cs[b]: round 1 = this CTA's count of bucket b; afterwards (start in the stage << 16) | rank
+    uint32_t *s_cs = reinterpret_cast<uint32_t *>(s_gbase + (kCapped ? 0 : n_buckets));
+    uint32_t *s_g = s_cs + n_buckets;       // capped: the run's first cell inside the bucket's region
+    uint32_t *s_room = s_g + n_buckets;     // capped: how many of the run's k-mers fit the region
+    uint32_t *s_obase = s_room + n_buckets; // capped: first overflow cell of the others
     __shared__ uint32_t s_warp_tot[kScatterThreads / 32];
 
-    for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) s_cnt[i] = 0;
+    for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) s_cs[i] = 0;
     __syncthreads();
     const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const UnitInput in = load_unit(codes, breaks, u, u_end);
     // round 1: this CTA's count per bucket
-    extract_unit(in, k, [&](uint64_t kmer, int) { atomicAdd(&s_cnt[fn(kmer)], 1u); });
+    extract_unit(in, k, [&](uint64_t kmer, int) { atomicAdd(&s_cs[fn(kmer)], 1u); });
     __syncthreads();
-    // exclusive scan of the counts (bucket starts inside the stage) + global reservation
-    const uint32_t per = (n_buckets + blockDim.x - 1) / blockDim.x;
+    // exclusive scan of the counts (bucket starts inside the stage) + global reservation; the
+    // reservations of a thread's buckets are all issued before any result is used
+    const uint32_t per = (n_buckets + blockDim.x - 1) / blockDim.x;  // <= kScatterPer
     const uint32_t b0 = threadIdx.x * per;
+    uint32_t cnt[kScatterPer];
+    unsigned long long g[kScatterPer];
     uint32_t mine = 0;
-    for (uint32_t i = b0; i < b0 + per && i < n_buckets; i++) mine += s_cnt[i];
+#pragma unroll
+    for (uint32_t j = 0; j < kScatterPer; j++) {
+        cnt[j] = (j < per && b0 + j < n_buckets) ? s_cs[b0 + j] : 0u;
+        mine += cnt[j];
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < kScatterPer; j++)
+        g[j] = cnt[j] ? atomicAdd(&cursors[b0 + j], (unsigned long long)cnt[j]) : 0ull;
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -979,32 +1017,55 @@ bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__rest
     uint32_t warp_off = 0;
     for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) warp_off += s_warp_tot[w];
     uint32_t run = warp_off + incl - mine;
-    for (uint32_t i = b0; i < b0 + per && i < n_buckets; i++) {
-        const uint32_t c = s_cnt[i];
-        s_start[i] = run;
-        s_gbase[i] = c ? atomicAdd(&cursors[i], (unsigned long long)c) : 0ull;
-        s_cnt[i] = 0;
-        run += c;
+#pragma unroll
+    for (uint32_t j = 0; j < kScatterPer; j++) {
+        const uint32_t i = b0 + j;
+        if (j < per && i < n_buckets) {
+            if (kCapped) {
+                const uint32_t room = g[j] >= lay.cap ? 0u : (uint32_t)min((unsigned long long)cnt[j], lay.cap - g[j]);
+                s_g[i] = (uint32_t)min(g[j], lay.cap);
+                s_room[i] = room;
+                s_obase[i] = cnt[j] > room
+                                 ? (uint32_t)min(atomicAdd(&cursors[n_buckets], (unsigned long long)(cnt[j] - room)),
+                                                 0xffff0000ull)
+                                 : 0u;
+            } else {
+                s_gbase[i] = g[j];
+            }
+            s_cs[i] = run << 16;
+            run += cnt[j];
+        }
     }
-    if (threadIdx.x == blockDim.x - 1) s_start[n_buckets] = run;  // (only used for the total)
     __syncthreads();
     uint32_t total = 0;
     for (uint32_t w = 0; w < kScatterThreads / 32; w++) total += s_warp_tot[w];
     // round 2: re-extract (ALU is free here) and place every k-mer at its bucket-ordered stage slot
     extract_unit(in, k, [&](uint64_t kmer, int) {
-        const uint32_t b = fn(kmer);
-        const uint32_t rk = atomicAdd(&s_cnt[b], 1u);
-        stage[s_start[b] + rk] = kmer;
+        const uint32_t cs = atomicAdd(&s_cs[fn(kmer)], 1u);
+        stage[(cs >> 16) + (cs & 0xffffu)] = kmer;
     });
     __syncthreads();
-    // copy-out: stage position p belongs to bucket fn(kmer); its cell is gbase[b] + (p - start[b])
+    // copy-out: stage position p belongs to bucket fn(kmer); consecutive threads write consecutive
+    // cells of a bucket run
     for (uint32_t p = threadIdx.x; p < total; p += blockDim.x) {
         const unsigned long long kmer = stage[p];
         const uint32_t b = fn(kmer);
+        const uint32_t rel = p - (s_cs[b] >> 16);
         unsigned long long *out = bases.dst[bases.uniform ? 0u : (b >> bases.log2_regions)];
-        out[s_gbase[b] + (p - s_start[b])] = kmer;
+        if (!kCapped) {
+            out[s_gbase[b] + rel] = kmer;
+        } else if (rel < s_room[b]) {
+            out[(unsigned long long)b * lay.cap + s_g[b] + rel] = kmer;
+        } else {
+            const unsigned long long o = (unsigned long long)s_obase[b] + (rel - s_room[b]);
+            if (o < lay.ovf_cap) out[lay.ovf_base + o] = kmer;  // else: dropped, the host re-buckets the batch
+        }
     }
+    if (kCapped && threadIdx.x == 0 && total) atomicAdd(&cc->n_windows, (unsigned long long)total);
 }
+
+// *p += delta (delta may be "negative" in two's complement)
+__global__ void adjust_counter_kernel(unsigned long long *p, unsigned long long delta) { *p += delta; }
 
 // ---------------------------------------------------------------------------
 // synthetic reads on the device (bench / tests)

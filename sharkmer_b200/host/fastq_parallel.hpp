@@ -8,9 +8,9 @@
 //                                                            longer file contributes ONE extra record
 //   open_fastq_reader                   :598-625             gzip by suffix or magic, one member only
 // but built for throughput rather than after the reference's control flow:
-//   * the text is handled in WINDOWS (default 128 MiB) that start on a record boundary; a window of
-//     a plain file is read by all workers at once (pread), a window of a gzip file is inflated by a
-//     producer thread while the previous window is being framed;
+//   * the text is handled in WINDOWS (default 128 MiB) that start on a record boundary; a plain file
+//     is mapped, so a window is just a span of the page cache (no read() copy: framing is memory
+//     bound); a gzip file is inflated by a producer thread while the previous window is being framed;
 //   * every worker finds the newlines of its 1 MiB block with SSE2 compares; since a record is four
 //     lines, the line table IS the record table (no per-line strings, no state machine);
 //   * 1000-read batches are sized in parallel, given their place in the chunk-major staging buffer
@@ -20,6 +20,7 @@
 #pragma once
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -211,6 +212,13 @@ class TextSource {
         struct stat st;
         regular_ = ::fstat(fd_, &st) == 0 && S_ISREG(st.st_mode);
         file_size_ = regular_ ? (size_t)st.st_size : 0;
+        if (!gz_ && regular_ && file_size_ > 0) {
+            void *m = ::mmap(nullptr, file_size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+            if (m != MAP_FAILED) {
+                map_ = static_cast<const char *>(m);
+                ::madvise(m, file_size_, MADV_SEQUENTIAL);
+            }
+        }
         if (gz_) producer_ = std::thread([this] { inflate_loop(); });
     }
     ~TextSource() {
@@ -222,6 +230,7 @@ class TextSource {
             cv_.notify_all();
             producer_.join();
         }
+        if (map_) ::munmap(const_cast<char *>(map_), file_size_);
         if (fd_ >= 0) ::close(fd_);
     }
     TextSource(const TextSource &) = delete;
@@ -231,6 +240,17 @@ class TextSource {
     // Returns false when there is no text left at all.  `grow`: the last window held no complete
     // record, so read further instead of starting over.
     bool next(size_t keep_from) {
+        if (map_) {
+            // keep_from == 0 on a later call: the window held no complete record, so widen it
+            span_ = (started_ && keep_from == 0 && !eof_) ? std::min(span_ * 2, kMaxWindow) : window_;
+            started_ = true;
+            file_pos_ += keep_from;
+            const size_t left = file_size_ - file_pos_;
+            data_ = map_ + file_pos_;
+            size_ = std::min(span_, left);
+            eof_ = size_ == left;
+            return size_ > 0;
+        }
         const size_t carry = size_ - keep_from;
         if (eof_ && carry == 0) {
             size_ = 0;
@@ -239,6 +259,7 @@ class TextSource {
         if (eof_) {  // only the carried bytes remain (a truncated record)
             std::memmove(buf_.data(), buf_.data() + keep_from, carry);
             size_ = carry;
+            data_ = buf_.data();
             return true;
         }
         size_t want = window_;
@@ -253,9 +274,10 @@ class TextSource {
         }
         size_t got = gz_ ? take_inflated(buf_.data() + carry, want) : read_plain(buf_.data() + carry, want);
         size_ = carry + got;
+        data_ = buf_.data();
         return size_ > 0 || !eof_;
     }
-    const char *data() const { return buf_.data(); }
+    const char *data() const { return data_; }
     size_t size() const { return size_; }
     bool eof() const { return eof_; }
     const std::string &name() const { return path_; }
@@ -263,30 +285,8 @@ class TextSource {
   private:
     static constexpr size_t kMaxWindow = size_t(3) << 30;  // line offsets are 32-bit
 
-    size_t read_plain(char *dst, size_t want) {
-        if (regular_) {
-            const size_t left = file_size_ > file_pos_ ? file_size_ - file_pos_ : 0;
-            const size_t n = std::min(want, left);
-            const size_t blk = size_t(4) << 20, nb = (n + blk - 1) / blk;
-            std::atomic<bool> bad{false};
-            pool_.parallel_for(nb, [&](size_t b) {
-                size_t off = b * blk, len = std::min(blk, n - off);
-                while (len) {
-                    ssize_t r = ::pread(fd_, dst + off, len, (off_t)(file_pos_ + off));
-                    if (r <= 0) {
-                        bad = true;
-                        return;
-                    }
-                    off += (size_t)r;
-                    len -= (size_t)r;
-                }
-            });
-            if (bad) throw Error(SKM_ERR_INVALID_ARG, "Failed to read " + path_);
-            file_pos_ += n;
-            if (file_pos_ >= file_size_) eof_ = true;
-            return n;
-        }
-        size_t n = 0;  // a pipe or device: plain sequential reads
+    size_t read_plain(char *dst, size_t want) {  // a pipe, a device or an unmappable file
+        size_t n = 0;
         while (n < want) {
             ssize_t r = ::read(fd_, dst + n, want - n);
             if (r < 0) throw Error(SKM_ERR_INVALID_ARG, "Failed to read " + path_);
@@ -395,7 +395,11 @@ class TextSource {
     int fd_ = -1;
     bool gz_ = false, regular_ = false, eof_ = false;
     size_t file_size_ = 0, file_pos_ = 0;
-    std::vector<char> buf_;
+    const char *map_ = nullptr;  // plain regular file: the whole file, mapped read-only
+    size_t span_ = 0;
+    bool started_ = false;
+    std::vector<char> buf_;      // otherwise: carried partial record + freshly read / inflated text
+    const char *data_ = nullptr;
     size_t size_ = 0;
     std::thread producer_;
     std::mutex mu_;

@@ -290,8 +290,8 @@ inline void write_histo_files(Engine &e, const std::string &directory, const std
 }
 
 // main.rs:182-197 / stats.rs:26-45 (scalar fields)
-inline void write_stats_file(Engine &e, const Batcher &st, const std::string &directory, const std::string &sample,
-                             const std::string &command) {
+inline void write_stats_file(Engine &e, uint64_t n_reads_read, uint64_t n_bases_read, const std::string &directory,
+                             const std::string &sample, const std::string &command) {
     skm_totals t = e.totals();
     std::string path = directory + sample + ".stats.yaml";
     FILE *f = std::fopen(path.c_str(), "w");
@@ -301,8 +301,8 @@ inline void write_stats_file(Engine &e, const Batcher &st, const std::string &di
     std::fprintf(f, "sample: %s\n", sample.c_str());
     std::fprintf(f, "kmer_length: %u\n", e.k());
     std::fprintf(f, "chunks: %u\n", e.chunks());
-    std::fprintf(f, "n_reads_read: %llu\n", (unsigned long long)st.n_reads_read);
-    std::fprintf(f, "n_bases_read: %llu\n", (unsigned long long)st.n_bases_read);
+    std::fprintf(f, "n_reads_read: %llu\n", (unsigned long long)n_reads_read);
+    std::fprintf(f, "n_bases_read: %llu\n", (unsigned long long)n_bases_read);
     std::fprintf(f, "n_subreads_ingested: %llu\n", (unsigned long long)t.n_reads);
     std::fprintf(f, "n_bases_ingested: %llu\n", (unsigned long long)t.n_bases);
     std::fprintf(f, "n_kmers: %llu\n", (unsigned long long)t.n_kmers);

@@ -24,23 +24,25 @@ def stats_fields(path):
     return d
 
 
-def run_both(tmp_path, args, inputs):
+def run_both(tmp_path, args, inputs, gpu_flags=()):
     outs = []
-    for name, cli in (("gpu", GPU_CLI), ("orc", ORC_CLI)):
+    for name, cli, extra in (("gpu", GPU_CLI, list(gpu_flags)), ("orc", ORC_CLI, [])):
         d = tmp_path / name
         d.mkdir(exist_ok=True)
-        r = subprocess.run([cli, *map(str, args), "-s", "smp", "-o", str(d) + "/", *map(str, inputs)],
+        r = subprocess.run([cli, *map(str, args), *extra, "-s", "smp", "-o", str(d) + "/", *map(str, inputs)],
                            capture_output=True, text=True)
         outs.append((r, d))
     return outs
 
 
+# the multi-threaded reader (default) and the reference-shaped serial reader feed the same batches
+@pytest.mark.parametrize("reader", [(), ("--serial",), ("-t", "3")])
 @pytest.mark.parametrize("k,chunks,gz,n", [(21, 10, False, 25_500), (31, 1, True, 12_000), (25, 3, True, 7_777)])
-def test_histo_files_byte_identical(oracle, tmp_path, k, chunks, gz, n):
+def test_histo_files_byte_identical(oracle, tmp_path, k, chunks, gz, n, reader):
     assert os.path.exists(GPU_CLI) and os.path.exists(ORC_CLI)
     fq = tmp_path / ("reads.fastq.gz" if gz else "reads.fastq")
     oracle.synth_fastq(fq, seed=k, genome_len=80_000, read_len=150, sub_rate=0.01, n_rate=0.001, first=0, n=n, gzip=gz)
-    (rg, dg), (ro, do) = run_both(tmp_path, ["-k", k, "--chunks", chunks, "--histo-max", 500], [fq])
+    (rg, dg), (ro, do) = run_both(tmp_path, ["-k", k, "--chunks", chunks, "--histo-max", 500], [fq], reader)
     assert rg.returncode == 0, rg.stderr
     assert ro.returncode == 0, ro.stderr
     for f in ("smp.histo", "smp.final.histo"):

@@ -196,6 +196,25 @@ def test_18s_golden(skm):  # src/pcr/mod.rs:1236-1247,1336-1342
     assert e.digest() == gold["digest"] and e.histogram(0)[10] == 1812
 
 
+@pytest.mark.parametrize("poly_frac", [0.04, 0.10, 0.7, 1.0])
+def test_skewed_buckets_overflow_and_fallback(skm, oracle, poly_frac):
+    """Single-GPU bucketing is one pass into fixed-capacity regions (CapLayout): a k-mer repeated
+    many times overfills its region.  4 % poly-A reads spill into the overflow run, 10 % nearly
+    fill it, 70 % / 100 % overflow that too and the engine re-buckets the batch exactly."""
+    L = 150
+    n = 30_000
+    reads = oracle.synth_reads(seed=11, genome_len=200_000, read_len=L, sub_rate=0.01, n_rate=0.001, first=0, n=n).copy()
+    lines = reads.reshape(n, L + 1)
+    rng = np.random.default_rng(5)
+    poly = rng.random(n) < poly_frac
+    lines[poly, :L] = ord("A")
+    reads = lines.reshape(-1)
+    for chunks in (0, 3):
+        run = run_oracle(oracle, reads, 21, chunks, 300)
+        e = run_gpu(skm, reads, 21, chunks, 300, L, mode=2)
+        compare(e, run, chunks)
+
+
 def test_table_growth_from_tiny(skm, oracle):
     """capacity_hint = 0: the table starts at 2^16 slots and must grow several times."""
     L = 100

@@ -15,11 +15,22 @@ ROOT = os.path.dirname(HERE)
 
 
 @pytest.fixture(scope="module")
-def harness(tmp_path_factory):
+def harness_bin(tmp_path_factory):
     out = tmp_path_factory.mktemp("host") / "host_harness"
-    subprocess.run(["g++", "-O1", "-std=c++17", "-o", str(out), os.path.join(HERE, "host", "mock_abi.cpp"), "-lz"],
-                   check=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-o", str(out), os.path.join(HERE, "host", "mock_abi.cpp"),
+                    "-lz"], check=True)
     return str(out)
+
+
+# every test runs against the reference-shaped serial reader (ingest.hpp) and the multi-threaded one
+# (fastq_parallel.hpp); "tiny" forces many windows, carried partial records and window growth
+READERS = {"serial": ["--serial"], "parallel": ["--threads", "4"],
+           "tiny": ["--threads", "3", "--window-bytes", "700"]}
+
+
+@pytest.fixture(scope="module", params=list(READERS))
+def harness(request, harness_bin):
+    return [harness_bin] + READERS[request.param]
 
 
 def write_fastq(path, seqs, gz=False, crlf=False, trailing_newline=True):
@@ -53,7 +64,7 @@ def route(seqs, n_chunks):
 def run(harness, tmp, args):
     d = tmp / "dump"
     d.mkdir(exist_ok=True)
-    r = subprocess.run([harness, "--dump", str(d)] + [str(a) for a in args], capture_output=True, text=True)
+    r = subprocess.run(harness + ["--dump", str(d)] + [str(a) for a in args], capture_output=True, text=True)
     return r, d
 
 
@@ -176,3 +187,28 @@ def test_only_first_record_validated_by_default(harness, tmp_path):  # io.rs:321
     assert r.returncode == 0 and read_chunks(d, 1) == [["ACGT", "GGCC"]]
     r, _ = run(harness, tmp_path, ["--validate-every", 1, fq])
     assert r.returncode == 1 and "FASTQ record 2 has invalid header" in r.stderr
+
+
+def test_record_longer_than_a_window_and_empty_lines(harness, tmp_path):
+    # a read far longer than the "tiny" reader's 700-byte window (the window must grow, then shrink
+    # back), an empty sequence line (a read of length 0 is still a read) and an empty header line
+    seqs = ["ACGT" * 3, "G" * 5000, "", "TTAGC", "C" * 1500, "A"]
+    fq = tmp_path / "long.fastq"
+    txt = "".join(f"@r{i}\n{s}\n+\n{'I' * len(s)}\n" for i, s in enumerate(seqs))
+    txt += "\nACGTAC\n+\nIIIIII\n"  # record 7: empty header; only record 1 is validated by default
+    fq.write_text(txt)
+    r, d = run(harness, tmp_path, ["--chunks", 2, fq])
+    assert r.returncode == 0, r.stderr
+    assert read_chunks(d, 2) == route(seqs + ["ACGTAC"], 2)
+    n_reads, n_bases = map(int, open(d / "counts.txt").read().split())
+    assert (n_reads, n_bases) == (7, sum(map(len, seqs)) + 6)
+
+
+def test_empty_and_newline_only_files(harness, tmp_path):
+    fq = tmp_path / "empty.fastq"
+    fq.write_bytes(b"")
+    r, d = run(harness, tmp_path, [fq])
+    assert r.returncode == 0 and open(d / "counts.txt").read().split() == ["0", "0"]
+    fq.write_bytes(b"\n")  # one empty line: a header without its record
+    r, _ = run(harness, tmp_path, [fq])
+    assert r.returncode == 1 and "Truncated FASTQ record at record 1" in r.stderr and "missing sequence line" in r.stderr
