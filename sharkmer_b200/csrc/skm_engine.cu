@@ -118,6 +118,7 @@ struct skm_ctx {
     std::vector<uint64_t *> off_blocks;
     size_t off_used = 0;  // entries used in the last block
     bool eager = true;    // SKM_EAGER=0 disables partitioning at ingest time
+    uint32_t max_buckets = kMaxBuckets;  // SKM_MAX_BUCKETS (power of two <= kMaxBuckets; same on every rank)
     bool capped = true;   // SKM_CAPPED=0: single-GPU eager bucketing uses the exact two-pass layout
     uint32_t n_capped_fallbacks = 0;
     size_t mem_budget = 0, list_bytes = 0;
@@ -432,7 +433,7 @@ int32_t insert_segment_direct(skm_ctx *c, const Segment &sg, uint32_t chunk) {
 // regions per owner used by the router: the largest power of two with n_ranks * regions <= kMaxBuckets
 uint32_t route_log2_regions(const skm_ctx *c) {
     uint32_t l = 0;
-    while (((uint64_t)c->n_ranks << (l + 1)) <= kMaxBuckets) l++;
+    while (((uint64_t)c->n_ranks << (l + 1)) <= c->max_buckets) l++;
     return l;
 }
 
@@ -1031,6 +1032,7 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     if (const char *g = getenv("SKM_PIPE_DEPTH")) c->pipe_depth = atoi(g);
     if (const char *g = getenv("SKM_EAGER")) c->eager = atoi(g) != 0;
     if (const char *g = getenv("SKM_CAPPED")) c->capped = atoi(g) != 0;
+    if (const char *g = getenv("SKM_MAX_BUCKETS")) c->max_buckets = std::min<uint32_t>(kMaxBuckets, std::max(1, atoi(g)));
     {
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));

@@ -867,6 +867,9 @@ struct BucketFn {
     uint32_t log2_regions;  // table regions per owner = 2^log2_regions
     __host__ __device__ __forceinline__ uint32_t operator()(uint64_t kmer) const {
         const uint64_t h = skm_hash_kmer(kmer);
+        // one owner: owner = 0 and the local hash is h itself (skips two 64-bit multiplies per call;
+        // the bucketing kernels are instruction bound and hash every k-mer three times)
+        if (n_ranks == 1) return log2_regions ? (uint32_t)(h >> (64u - log2_regions)) : 0u;
         const uint32_t owner = skm_owner_rank(h, n_ranks);
         if (log2_regions == 0) return owner;
         return (owner << log2_regions) | (uint32_t)(skm_local_hash(h, n_ranks) >> (64u - log2_regions));
