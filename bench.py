@@ -50,9 +50,10 @@ CPU_SAMPLE_READS = 300_000
 B_ALG_PER_KMER = 64.0      # 32 B sector in + 32 B sector out per k-mer occurrence
 B_ALG_PER_BASE = 0.375     # packed stream read by the extract kernels: 2-bit code + 1-bit break mask
 # DRAM bytes per k-mer of the dominant kernel from the committed `ncu --set full` captures
-# (profiles/r01_insert_kernel_full.csv: 7.69 GB read + 2.70 GB written for 1.275e8 k-mers;
+# (profiles/r01_insert_kernel_full.csv: 7.58 GB read + 2.72 GB written per launch of 1.273e8 k-mers,
+#  mean of the three captured launches;
 #  profiles/r01_direct_kernel_full.csv: 12.2 + 3.0 GB for 1.27e8 k-mers)
-NCU_DRAM_BYTES_PER_KMER = {"insert_runs_kernel": 81.5, "extract_insert_kernel": 119.7}
+NCU_DRAM_BYTES_PER_KMER = {"insert_runs_kernel": 80.9, "extract_insert_kernel": 119.7}
 
 
 def load_peaks():
