@@ -219,6 +219,8 @@ def run_ours(args):
     mode = {"auto": _lib.INSERT_AUTO, "direct": _lib.INSERT_DIRECT, "partitioned": _lib.INSERT_PARTITIONED}[args.mode]
     hint = int(DISTINCT_HINT_PER_GPU * args.reads_per_gpu / READS_PER_GPU)
 
+    if world > 1 and os.environ.get("SKM_TRACE"):
+        os.environ["SKM_TRACE"] += f".rank{rank}"   # one timeline file per rank
     if world > 1 and args.exchange in ("p2p", "nccl"):
         # these two paths bucket at routing time (p2p: scatter kernel fused with the peer stores);
         # the "dma" path buckets at ingest time and lets the copy engines move the runs

@@ -476,7 +476,7 @@ int32_t bucket_count(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn 
             c->launches++;
             c->stage_launches[ST_COUNT]++;
         }
-        bucket_scan_kernel<<<1, 1024, 0, c->work>>>(c->d_bucket_counts, n_buckets, c->d_bucket_offsets,
+        bucket_scan_kernel<<<1, kScanThreads, 0, c->work>>>(c->d_bucket_counts, n_buckets, c->d_bucket_offsets,
                                                        c->d_bucket_cursors);
         c->launches++;
     }
@@ -1012,6 +1012,9 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     CU(cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    // (Asking for the largest shared-memory carve-out on the insert kernels, so that the 108-112 KB
+    // scatter CTAs of the next chunk can always move in beside them, DOUBLES the insert time: the
+    // insert kernel needs its L1 — profiles/experiments_r01.md #30.  Left at the default.)
     CU(cudaFuncSetAttribute(bucket_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)scatter_smem_bytes(kMaxBuckets)));
     CU(cudaFuncSetAttribute(bucket_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -903,10 +903,14 @@ bucket_count_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restri
 }
 
 // offsets[b] = sum of counts[0..b); cursors[b] = offsets[b]; offsets[n] = total
-__global__ void __launch_bounds__(1024)
+// One CTA of 256 threads, not 1024: beside the persistent insert kernel (5 x 256 threads per SM)
+// a 1024-thread CTA fits on no SM and the whole bucketing of the next chunk waited for the inserts
+// to finish (profiles/experiments_r01.md #30).
+static constexpr uint32_t kScanThreads = 256;
+__global__ void __launch_bounds__(kScanThreads)
 bucket_scan_kernel(const unsigned long long *__restrict__ counts, uint32_t n_buckets,
                    unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ cursors) {
-    __shared__ unsigned long long part[1024];
+    __shared__ unsigned long long part[kScanThreads];
     const uint32_t per = (n_buckets + blockDim.x - 1) / blockDim.x;
     const uint32_t a = threadIdx.x * per;
     unsigned long long s = 0;
