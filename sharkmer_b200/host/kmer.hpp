@@ -148,6 +148,21 @@ class KmerCounts {
         e_.check(skm_lookup_batch(e_.raw(), kmers.data(), kmers.size(), min_count, mode, c.data(), nullptr));
         return c;
     }
+    // find_oligos_in_kmers (src/pcr/primers.rs:163-226) as one table pass on the device: table
+    // k-mers with count >= min_count that start with one of the (unshifted, 2-bit) oligos, or whose
+    // reverse complement does (then the reverse complement is reported); ascending k-mer order
+    std::pair<std::vector<uint64_t>, std::vector<uint32_t>> scan_oligos(const std::vector<uint64_t> &oligos,
+                                                                        uint32_t oligo_length, uint32_t min_count) {
+        uint64_t n = 0;
+        e_.check(skm_scan_oligos(e_.raw(), oligos.data(), oligos.size(), oligo_length, min_count, nullptr, nullptr, 0, &n));
+        std::vector<uint64_t> keys(n);
+        std::vector<uint32_t> counts(n);
+        if (n) e_.check(skm_scan_oligos(e_.raw(), oligos.data(), oligos.size(), oligo_length, min_count, keys.data(),
+                                        counts.data(), n, &n));
+        keys.resize(n);
+        counts.resize(n);
+        return {std::move(keys), std::move(counts)};
+    }
     FilteredKmerCounts filtered_view(uint32_t min_count);
     Engine &engine() { return e_; }
 

@@ -5,15 +5,18 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
 #include "../../include/sharkmer_b200.h"
+#include "../../include/skm_common.h"
 
 static bool g_discard = false;  // --bench: time the framing only, keep nothing
 struct skm_ctx {
     skm_params p;
     std::vector<std::string> chunk_data;
+    std::map<uint64_t, uint32_t> table;  // --primers mode: filled through skm_insert_counts
     std::string err;
 };
 
@@ -47,11 +50,46 @@ int32_t skm_stage_times(skm_ctx *, skm_stage_ms *t) { std::memset(t, 0, sizeof *
 int32_t skm_table_len(skm_ctx *, uint64_t *n) { *n = 0; return SKM_OK; }
 int32_t skm_export(skm_ctx *, uint64_t *, uint32_t *, uint64_t, int32_t, uint64_t *n) { *n = 0; return SKM_OK; }
 int32_t skm_lookup_batch(skm_ctx *, const uint64_t *, uint64_t, uint32_t, int32_t, uint32_t *, uint8_t *) { return SKM_ERR_STATE; }
-int32_t skm_insert_counts(skm_ctx *, const uint64_t *, const uint32_t *, uint64_t) { return SKM_ERR_STATE; }
+int32_t skm_insert_counts(skm_ctx *c, const uint64_t *keys, const uint32_t *counts, uint64_t n) {
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t v = (uint64_t)c->table[keys[i]] + counts[i];
+        c->table[keys[i]] = v > 0xffffffffull ? 0xffffffffu : (uint32_t)v;
+    }
+    return SKM_OK;
+}
+// brute-force statement of the scan's contract (include/sharkmer_b200.h), over the mock's std::map
+int32_t skm_scan_oligos(skm_ctx *c, const uint64_t *oligos, uint64_t n_oligos, uint32_t len, uint32_t min_count,
+                        uint64_t *keys, uint32_t *counts, uint64_t cap, uint64_t *n_out) {
+    const uint32_t k = c->p.k;
+    if (len == 0 || len >= k || n_oligos == 0) { c->err = "bad oligo length"; return SKM_ERR_INVALID_ARG; }
+    std::map<uint64_t, uint32_t> out;
+    for (auto &kv : c->table) {
+        if (kv.second < min_count) continue;
+        bool fwd = false, rev = false;
+        for (uint64_t i = 0; i < n_oligos && !fwd; i++) fwd = (kv.first >> (2 * (k - len))) == oligos[i];
+        if (!fwd) {
+            const uint64_t rc = skm_revcomp_kmer(kv.first, k);
+            for (uint64_t i = 0; i < n_oligos && !rev; i++) rev = (rc >> (2 * (k - len))) == oligos[i];
+            if (rev) out[rc] = kv.second;
+        } else {
+            out[kv.first] = kv.second;
+        }
+    }
+    *n_out = out.size();
+    if (!keys) return SKM_OK;
+    uint64_t i = 0;
+    for (auto &kv : out) {
+        if (i >= cap) break;
+        keys[i] = kv.first;
+        counts[i++] = kv.second;
+    }
+    return SKM_OK;
+}
 }
 
 // harness: same flags as the CLI; dumps chunk_<c>.txt + counts.txt into --dump DIR
 #include "../../sharkmer_b200/host/fastq_parallel.hpp"
+#include "../../sharkmer_b200/host/primers.hpp"
 
 int main(int argc, char **argv) {
     uint32_t k = 21, chunks = 0;
@@ -59,6 +97,9 @@ int main(int argc, char **argv) {
     size_t buffer_bytes = 0, window_bytes = size_t(128) << 20;
     unsigned threads = 0;
     bool paired = false, serial = false;
+    skm::PCRParams pcr;
+    std::string table_path;
+    uint32_t view_min = 0;
     std::string dump = ".";
     std::vector<std::string> inputs;
     for (int i = 1; i < argc; i++) {
@@ -74,10 +115,30 @@ int main(int argc, char **argv) {
         else if (a == "--threads" || a == "-t") threads = (unsigned)std::atoi(argv[++i]);
         else if (a == "--window-bytes") window_bytes = std::strtoull(argv[++i], nullptr, 10);
         else if (a == "--dump") dump = argv[++i];
+        else if (a == "--table") table_path = argv[++i];
+        else if (a == "--forward") pcr.forward_seq = argv[++i];
+        else if (a == "--reverse") pcr.reverse_seq = argv[++i];
+        else if (a == "--mismatches") pcr.mismatches = std::strtoull(argv[++i], nullptr, 10);
+        else if (a == "--trim") pcr.trim = std::strtoull(argv[++i], nullptr, 10);
+        else if (a == "--min-count") pcr.min_count = (uint32_t)std::strtoul(argv[++i], nullptr, 10);
+        else if (a == "--cap") pcr.max_primer_kmers = std::strtoull(argv[++i], nullptr, 10);
+        else if (a == "--view-min") view_min = (uint32_t)std::strtoul(argv[++i], nullptr, 10);
         else inputs.push_back(a);
     }
     try {
         skm::Engine eng(k, chunks);
+        if (!table_path.empty()) {
+            // --primers mode: load "kmer count" lines, run get_primer_kmers, print "F|R kmer count"
+            FILE *f = std::fopen(table_path.c_str(), "r");
+            unsigned long long km, ct;
+            skm::KmerCounts table(eng);
+            while (f && std::fscanf(f, "%llu %llu", &km, &ct) == 2) table.insert((uint64_t)km, (uint32_t)ct);
+            if (f) std::fclose(f);
+            auto res = skm::get_primer_kmers(table, pcr, view_min);
+            for (auto &e : res.first) std::printf("F %llu %u\n", (unsigned long long)e.first, e.second);
+            for (auto &e : res.second) std::printf("R %llu %u\n", (unsigned long long)e.first, e.second);
+            return 0;
+        }
         if (!serial) {
             skm::ParallelIngest st(eng, threads, window_bytes);
             if (paired) {

@@ -370,6 +370,62 @@ def test_scan_oligos_vs_oracle(skm, oracle):  # src/pcr/primers.rs:163-226
 
 # ---- (5) synthetic generator: device == host, bit for bit ------------------------------------------
 
+def test_get_primer_kmers_vs_oracle(skm, oracle):  # src/pcr/primers.rs:376-478, pcr/mod.rs:1344-1350
+    """sPCR's primer k-mer discovery (one device scan per primer direction and mismatch level)
+    against the oracle restatement: the 18S case of the reference's own test, then a synthetic
+    genome with planted primer sites."""
+    from oracle import primers_oracle as po
+    from sharkmer_b200 import primers as pp
+    read = open(os.path.join(os.path.dirname(__file__), "golden", "pcr_18s_read.txt")).read().strip()
+    e = skm.Engine(21, chunks=0)
+    t = oracle.KmerCounts(21)
+    for _ in range(10):
+        e.ingest_batch(0, np.frombuffer((read + "\n").encode(), dtype=np.uint8))
+        t.ingest_seq(read)
+    e.finalize()
+    args = dict(forward_seq="AACCTGGTTGATCCTGCCAGT", reverse_seq="TGATCCTTCTGCAGGTTCACCTAC", min_count=3, mismatches=2,
+                trim=15, max_primer_kmers=40)
+    (fk, fc), (rk, rc) = pp.get_primer_kmers(pp.PCRParams(**args), e, 21, view_min_count=1)
+    want_f, want_r = po.get_primer_kmers(po.PCRParams(**args), t, view_min_count=1)
+    assert dict(zip(fk.tolist(), fc.tolist())) == want_f and dict(zip(rk.tolist(), rc.tolist())) == want_r
+    assert fk.size == 1 and rk.size == 1 and fc[0] == 10 and rc[0] == 10
+
+    rng = random.Random(9)
+    L = 150
+    fwd, rev = "ACGGTCATTGCAGGTCAAGT", "TTGACCGTAGGCATCCAGTA"
+    def rcs(s):
+        return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    lines = []
+    for i in range(3000):
+        s = [rng.choice("ACGT") for _ in range(L)]
+        if i % 3 == 0:   # plant a (possibly mutated, possibly reverse-complemented) primer site
+            site = list(fwd if i % 2 else rev)
+            for p in rng.sample(range(len(site)), rng.randint(0, 3)):
+                site[p] = rng.choice("ACGT")
+            site = "".join(site)
+            if rng.random() < 0.5:
+                site = rcs(site)
+            at = rng.randint(0, L - len(site))
+            s[at:at + len(site)] = site
+        lines.append("".join(s))
+    lines = lines + lines[:1500]   # some k-mers twice
+    buf = np.frombuffer(("\n".join(lines) + "\n").encode(), dtype=np.uint8)
+    for k, cap, mm in ((21, 40, 2), (31, 3, 1), (15, 5, 2)):
+        e = skm.Engine(k, chunks=0)
+        e.ingest_batch(0, buf)
+        e.finalize()
+        t = oracle.KmerCounts(k)
+        for s in lines:
+            t.ingest_seq(s)
+        args = dict(forward_seq=fwd[:-2] + "R" + fwd[-1], reverse_seq=rev, min_count=1, mismatches=mm, trim=15,
+                    max_primer_kmers=cap)
+        (fk, fc), (rk, rc) = pp.get_primer_kmers(pp.PCRParams(**args), e, k)
+        want_f, want_r = po.get_primer_kmers(po.PCRParams(**args), t)
+        assert dict(zip(fk.tolist(), fc.tolist())) == want_f, k
+        assert dict(zip(rk.tolist(), rc.tolist())) == want_r, k
+        assert len(want_f) > 0 and len(want_r) > 0
+
+
 def test_device_synth_matches_host(skm, oracle):
     e = skm.Engine(21)
     L, n, n_chunks = 150, 2345, 3
