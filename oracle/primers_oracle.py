@@ -141,13 +141,13 @@ def discover_primer_kmers_by_round(levels, table, min_count: int, cap: int) -> d
     return result
 
 
-def get_primer_kmers(params: PCRParams, table, view_min_count: int = 0):  # primers.rs:448-478
-    """`table`: oracle KmerCounts; `view_min_count`: threshold of the FilteredKmerCounts view the
-    reference iterates (its iter() hides counts below it, counting.rs:343-349)."""
+def get_primer_kmers(params: PCRParams, table):  # primers.rs:448-478
+    """`table`: oracle KmerCounts.  The FilteredKmerCounts view the reference passes in does not
+    matter here: its iter() yields every entry (counting.rs:343-349) and find_oligos_in_kmers
+    filters by params.min_count alone."""
     k = table.get_k()
-    mc = max(params.min_count, view_min_count)
-    fwd = discover_primer_kmers_by_round(preprocess_primer_by_mismatch(params, False, k), table, mc,
+    fwd = discover_primer_kmers_by_round(preprocess_primer_by_mismatch(params, False, k), table, params.min_count,
                                          params.max_primer_kmers)
-    rev = discover_primer_kmers_by_round(preprocess_primer_by_mismatch(params, True, k), table, mc,
+    rev = discover_primer_kmers_by_round(preprocess_primer_by_mismatch(params, True, k), table, params.min_count,
                                          params.max_primer_kmers)
     return fwd, rev

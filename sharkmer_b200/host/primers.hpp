@@ -175,14 +175,12 @@ inline PrimerKmers discover_primer_kmers(KmerCounts &table, const PrimerLevels &
     return result;
 }
 
-// get_primer_kmers, primers.rs:448-478.  view_min_count: threshold of the FilteredKmerCounts view
-// the reference iterates (its iter() hides lower counts, counting.rs:343-349).
-inline std::pair<PrimerKmers, PrimerKmers> get_primer_kmers(KmerCounts &table, const PCRParams &p,
-                                                            uint32_t view_min_count = 0) {
-    const uint32_t mc = std::max(p.min_count, view_min_count);
+// get_primer_kmers, primers.rs:448-478.  The scan threshold is params.min_count alone: the reference's
+// FilteredKmerCounts::iter() yields every entry whatever the view's threshold (counting.rs:343-349).
+inline std::pair<PrimerKmers, PrimerKmers> get_primer_kmers(KmerCounts &table, const PCRParams &p) {
     const size_t k = table.get_k();
-    PrimerKmers fwd = discover_primer_kmers(table, preprocess_primer_by_mismatch(p, false, k), mc, p.max_primer_kmers);
-    PrimerKmers rev = discover_primer_kmers(table, preprocess_primer_by_mismatch(p, true, k), mc, p.max_primer_kmers);
+    PrimerKmers fwd = discover_primer_kmers(table, preprocess_primer_by_mismatch(p, false, k), p.min_count, p.max_primer_kmers);
+    PrimerKmers rev = discover_primer_kmers(table, preprocess_primer_by_mismatch(p, true, k), p.min_count, p.max_primer_kmers);
     return {std::move(fwd), std::move(rev)};
 }
 

@@ -136,12 +136,12 @@ def discover_primer_kmers(engine, length: int, levels, min_count: int, cap: int)
     return keys[order], counts[order]
 
 
-def get_primer_kmers(params: PCRParams, engine, k: int, view_min_count: int = 0):
+def get_primer_kmers(params: PCRParams, engine, k: int):
     """((fwd_kmers, fwd_counts), (rev_kmers, rev_counts)) — get_primer_kmers, primers.rs:448-478.
-    `view_min_count`: threshold of the FilteredKmerCounts view the reference would iterate."""
-    mc = max(params.min_count, view_min_count)
+    The scan threshold is params.min_count alone: the reference's FilteredKmerCounts::iter() yields
+    every entry whatever the view's threshold (counting.rs:343-349)."""
     out = []
     for reverse in (False, True):
         length, levels = preprocess_primer_by_mismatch(params, reverse, k)  # length <= k-1 by the trim clamp
-        out.append(discover_primer_kmers(engine, length, levels, mc, params.max_primer_kmers))
+        out.append(discover_primer_kmers(engine, length, levels, params.min_count, params.max_primer_kmers))
     return out[0], out[1]

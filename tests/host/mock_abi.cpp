@@ -99,7 +99,6 @@ int main(int argc, char **argv) {
     bool paired = false, serial = false;
     skm::PCRParams pcr;
     std::string table_path;
-    uint32_t view_min = 0;
     std::string dump = ".";
     std::vector<std::string> inputs;
     for (int i = 1; i < argc; i++) {
@@ -122,7 +121,6 @@ int main(int argc, char **argv) {
         else if (a == "--trim") pcr.trim = std::strtoull(argv[++i], nullptr, 10);
         else if (a == "--min-count") pcr.min_count = (uint32_t)std::strtoul(argv[++i], nullptr, 10);
         else if (a == "--cap") pcr.max_primer_kmers = std::strtoull(argv[++i], nullptr, 10);
-        else if (a == "--view-min") view_min = (uint32_t)std::strtoul(argv[++i], nullptr, 10);
         else inputs.push_back(a);
     }
     try {
@@ -134,7 +132,7 @@ int main(int argc, char **argv) {
             skm::KmerCounts table(eng);
             while (f && std::fscanf(f, "%llu %llu", &km, &ct) == 2) table.insert((uint64_t)km, (uint32_t)ct);
             if (f) std::fclose(f);
-            auto res = skm::get_primer_kmers(table, pcr, view_min);
+            auto res = skm::get_primer_kmers(table, pcr);
             for (auto &e : res.first) std::printf("F %llu %u\n", (unsigned long long)e.first, e.second);
             for (auto &e : res.second) std::printf("R %llu %u\n", (unsigned long long)e.first, e.second);
             return 0;

@@ -385,8 +385,8 @@ def test_get_primer_kmers_vs_oracle(skm, oracle):  # src/pcr/primers.rs:376-478,
     e.finalize()
     args = dict(forward_seq="AACCTGGTTGATCCTGCCAGT", reverse_seq="TGATCCTTCTGCAGGTTCACCTAC", min_count=3, mismatches=2,
                 trim=15, max_primer_kmers=40)
-    (fk, fc), (rk, rc) = pp.get_primer_kmers(pp.PCRParams(**args), e, 21, view_min_count=1)
-    want_f, want_r = po.get_primer_kmers(po.PCRParams(**args), t, view_min_count=1)
+    (fk, fc), (rk, rc) = pp.get_primer_kmers(pp.PCRParams(**args), e, 21)
+    want_f, want_r = po.get_primer_kmers(po.PCRParams(**args), t)
     assert dict(zip(fk.tolist(), fc.tolist())) == want_f and dict(zip(rk.tolist(), rc.tolist())) == want_r
     assert fk.size == 1 and rk.size == 1 and fc[0] == 10 and rc[0] == 10
 

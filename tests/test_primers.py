@@ -156,9 +156,9 @@ def test_18s_primer_kmers_kat(oracle):  # pcr/mod.rs:1303-1311, 1344-1350
     prm = params_18s(po.PCRParams)
     rev_variants = po.preprocess_primer(prm, True, 21)
     assert len(po.get_kmers_from_primers(rev_variants, t, prm.min_count)) == 1
-    fwd, rev = po.get_primer_kmers(prm, t, view_min_count=1)
+    fwd, rev = po.get_primer_kmers(prm, t)
     assert len(fwd) == 1 and len(rev) == 1
-    (fk, fc), (rk, rc) = pp.get_primer_kmers(params_18s(pp.PCRParams), OracleScan(t), 21, view_min_count=1)
+    (fk, fc), (rk, rc) = pp.get_primer_kmers(params_18s(pp.PCRParams), OracleScan(t), 21)
     assert dict(zip(fk.tolist(), fc.tolist())) == fwd and dict(zip(rk.tolist(), rc.tolist())) == rev
     assert list(fc) == [10] and list(rc) == [10]
     # the forward primer k-mer starts with the trimmed primer; the reverse primer binds with one
@@ -213,7 +213,7 @@ def harness(tmp_path_factory):
     return str(out)
 
 
-def run_cpp(harness, tmp_path, table, k, args, view_min=0):
+def run_cpp(harness, tmp_path, table, k, args):
     keys, counts = table.export_sorted()
     tf = tmp_path / "table.txt"
     with open(tf, "w") as f:
@@ -221,7 +221,7 @@ def run_cpp(harness, tmp_path, table, k, args, view_min=0):
             f.write(f"{a} {b}\n")
     cmd = [harness, "-k", str(k), "--table", str(tf), "--forward", args["forward_seq"], "--reverse", args["reverse_seq"],
            "--mismatches", str(args["mismatches"]), "--trim", str(args["trim"]), "--min-count", str(args["min_count"]),
-           "--cap", str(args["max_primer_kmers"]), "--view-min", str(view_min)]
+           "--cap", str(args["max_primer_kmers"])]
     r = subprocess.run(cmd, capture_output=True, text=True)
     fwd, rev = {}, {}
     for line in r.stdout.split("\n"):
@@ -235,9 +235,9 @@ def test_cpp_18s_primer_kmers(harness, oracle, tmp_path):
     t = table_from(oracle, READ_18S, 21, replicates=10)
     args = dict(forward_seq="AACCTGGTTGATCCTGCCAGT", reverse_seq="TGATCCTTCTGCAGGTTCACCTAC", min_count=3, mismatches=2,
                 trim=15, max_primer_kmers=40)
-    r, fwd, rev = run_cpp(harness, tmp_path, t, 21, args, view_min=1)
+    r, fwd, rev = run_cpp(harness, tmp_path, t, 21, args)
     assert r.returncode == 0, r.stderr
-    want_f, want_r = po.get_primer_kmers(po.PCRParams(**args), t, view_min_count=1)
+    want_f, want_r = po.get_primer_kmers(po.PCRParams(**args), t)
     assert (fwd, rev) == (want_f, want_r) and len(fwd) == 1 and len(rev) == 1
 
 
