@@ -40,6 +40,8 @@ class PrimerError(ValueError):
 
 @dataclass
 class PCRParams:
+    """The fields of PCRParams (src/pcr/mod.rs:148-247) the pipeline reads, with the defaults of
+    cli.rs:20-27 and pcr/mod.rs:54,278-283."""
     forward_seq: str
     reverse_seq: str
     gene_name: str = "gene"
@@ -47,6 +49,14 @@ class PCRParams:
     mismatches: int = 2
     trim: int = 15
     max_primer_kmers: int = DEFAULT_MAX_NUM_PRIMER_KMERS
+    min_length: int = 0
+    max_length: int = 10000
+    dedup_edit_threshold: int = 10
+    max_dfs_states: int = 100_000
+    max_paths_per_pair: int = 20
+    max_node_visits: int = 2
+    high_coverage_ratio: float = 10.0
+    tip_coverage_fraction: float = 0.1
 
 
 def string_to_oligo(seq: str):
