@@ -322,3 +322,108 @@ def test_threshold_sweep_and_multiple_products(oracle):
         t1.ingest_seq(g[at:at + L])
     out = pcr.do_pcr(OracleTable(t1), k, "syn", PCRParams(fwd, rev, gene_name="g", min_count=2, max_length=1500))
     assert [r.seq for r in out.records] == [fwd[-15:] + ins + rc(rev)[:15]]
+
+
+# ---- the batched / speculative extension against a literal node-at-a-time restatement ------------
+
+def sequential_extend(graph, node_lookup, table, view_min, min_count, params, max_num_nodes, k):
+    """Test-only: extend_graph exactly as graph.rs:322-527 reads — one node at a time, four
+    get_canonical probes per node, no batching — to pin the product's wave machinery."""
+    from collections import deque
+    mask = pcr.get_suffix_mask(k)
+    shift = 2 * (k - 1)
+    found_path = False
+    m = pcr.median_f64(graph.edge_counts())
+    median = float(min_count) if m is None else m
+    last_median_check = 0
+    frontier = deque()
+    for n in graph.node_indices():
+        if graph.nodes[n][1]:
+            frontier.append((n, 0))
+        if graph.nodes[n][2]:
+            frontier.append((n, 1))
+    processed = (set(), set())
+    added = (set(n for n in graph.node_indices() if graph.nodes[n][1]), set(n for n in graph.node_indices() if graph.nodes[n][2]))
+    def get_canonical(kmer):
+        c = table.t.get_canonical(kmer)
+        return c if c is not None and c >= view_min else None
+    while frontier:
+        node, d = frontier.popleft()
+        if node in processed[d]:
+            continue
+        processed[d].add(node)
+        n_nodes = graph.n_nodes
+        if n_nodes > max_num_nodes:
+            break
+        if n_nodes > last_median_check and n_nodes - last_median_check > 1000:
+            m = pcr.median_f64(graph.edge_counts())
+            median = float(min_count) if m is None else m
+            last_median_check = n_nodes - n_nodes % 1000
+        sub = graph.nodes[node][0]
+        cands = []
+        for base in range(4):
+            kmer = (sub << 2) | base if d == 0 else (base << shift) | sub
+            c = get_canonical(kmer)
+            if c is not None and c >= min_count:
+                cands.append(kmer)
+        for kmer in cands:
+            new_sub = kmer & mask if d == 0 else kmer >> 2
+            if new_sub == sub:
+                continue
+            count = table.t.get_canonical_count(kmer)
+            count = count if count >= view_min else 0
+            ex = node_lookup.get(new_sub)
+            if ex is not None:
+                a, b = (node, ex) if d == 0 else (ex, node)
+                if graph.find_edge(a, b) is None:
+                    graph.add_edge(a, b, count)
+                    if ex in added[1 - d]:
+                        found_path = True
+            else:
+                if float(count) > median * params.high_coverage_ratio:
+                    continue
+                new = graph.add_node(new_sub)
+                node_lookup[new_sub] = new
+                added[d].add(new)
+                if d == 0:
+                    graph.add_edge(node, new, count)
+                else:
+                    graph.add_edge(new, node, count)
+                frontier.append((new, d))
+    return graph, found_path
+
+
+@pytest.mark.parametrize("seed,budget", [(1, 500_000), (2, 500_000), (3, 1500), (4, 500_000)])
+def test_wave_extension_equals_sequential(oracle, seed, budget):
+    """Branchy, repeat-rich input (shared repeats at several copy numbers, sequencing errors, more
+    than 1000 nodes so the median refresh and the high-coverage skip fire; one case runs into the
+    node budget): the graphs must be identical node for node and edge for edge."""
+    from sharkmer_b200.primers import get_primer_kmers
+    rng = random.Random(seed)
+    rnd = lambda n: "".join(rng.choice("ACGT") for _ in range(n))
+    k = 21
+    fwd, rev = rnd(21), rnd(21)
+    repeat = rnd(150)
+    body = rnd(500) + repeat + rnd(300) + repeat + rnd(400)
+    genome = rnd(600) + fwd + body + rc(rev) + rnd(600)
+    extra = "".join(rnd(200) + repeat for _ in range(6))          # the repeat is also elsewhere, deeper
+    t = oracle.KmerCounts(k)
+    reads = make_reads(rng, genome, 2500, 100, err=0.01) + make_reads(rng, extra, 1500, 100, err=0.01)
+    for s in reads:
+        t.ingest_seq(s)
+    tab = OracleTable(t)
+    prm = PCRParams(fwd, rev, gene_name="g", min_count=2, max_length=5000)
+    (fk, _), (rk, _) = get_primer_kmers(prm, tab, k)
+    assert fk.size and rk.size
+    # (the median starts at min_count, so edges above 10 x min_count are "repeats" until the first
+    #  refresh at 1001 nodes: thresholds as low as 2 would stop at the seeds, as in the reference)
+    for min_count in (8, 20):
+        seed_g, lk = pcr.create_seed_graph(fk, rk, k)
+        g1, _, f1, calls = pcr.extend_graph(seed_g.copy(), dict(lk), tab, 2, min_count, prm, budget, k)
+        g2, f2 = sequential_extend(seed_g.copy(), dict(lk), tab, 2, min_count, prm, budget, k)
+        assert g1.nodes == g2.nodes and g1.edges == g2.edges and f1 == f2
+        assert calls <= max(2, g1.n_nodes // 4)
+        if seed == 1:
+            assert g1.n_nodes > 1000    # far enough for the median refresh to fire
+    if budget < 10_000 and g1.n_nodes > budget:
+        assert g1.n_nodes <= budget + 8  # the check fires when a node is taken from the frontier
