@@ -4,6 +4,9 @@
 //   -k <odd 1..31> (19)  --chunks <n> (0)  --histo-max <1..1e6> (10000)  -m/--max-reads <n>
 //   -s/--sample <name> (sample)  -o/--outdir <dir> (./)  --paired  --validate-every <n>
 //   --capacity-hint <distinct k-mers>  --insert-mode auto|direct|partitioned  --device <n>
+//   --pcr-primers "forward=..,reverse=..,name=..[,max-length=..,min-length=..,min-count=..,mismatches=..,trim=..]"
+//   (repeatable; src/cli.rs:12-140)  --min-kmer-count <n> (2)  --node-budget-global <n>: in silico PCR on the
+//   device table (pcr.hpp; no read threading) -> {outdir}{sample}_{gene}.fasta
 //   -t/--threads <n> (all cores): FASTQ framing threads (fastq_parallel.hpp); --serial: the
 //   reference-shaped one-thread reader (ingest.hpp).  Both give the same batches, bit for bit.
 #include <cstdio>
@@ -13,6 +16,7 @@
 #include <vector>
 
 #include "fastq_parallel.hpp"
+#include "pcr.hpp"
 
 int main(int argc, char **argv) {
     uint32_t k = 19, chunks = 0, insert_mode = SKM_INSERT_AUTO;
@@ -20,6 +24,9 @@ int main(int argc, char **argv) {
     int device = -1;
     unsigned threads = 0;
     bool paired = false, serial = false;
+    std::vector<std::string> pcr_specs;
+    uint32_t min_kmer_count = 2;
+    size_t node_budget = 0;
     std::string sample = "sample", outdir = "./", command;
     std::vector<std::string> inputs;
     for (int i = 0; i < argc; i++) command += (i ? " " : "") + std::string(argv[i]);
@@ -43,6 +50,9 @@ int main(int argc, char **argv) {
         else if (a == "--device") device = std::atoi(val());
         else if (a == "--paired") paired = true;
         else if (a == "--serial") serial = true;
+        else if (a == "--pcr-primers") pcr_specs.push_back(val());
+        else if (a == "--min-kmer-count") min_kmer_count = (uint32_t)std::strtoul(val(), nullptr, 10);
+        else if (a == "--node-budget-global") node_budget = std::strtoull(val(), nullptr, 10);
         else if (a == "-t" || a == "--threads") threads = (unsigned)std::strtoul(val(), nullptr, 10);
         else if (a == "--insert-mode") {
             std::string m = val();
@@ -56,6 +66,12 @@ int main(int argc, char **argv) {
     std::string dir = outdir;
     if (!dir.empty() && dir.back() != '/') dir += '/';
     try {
+        std::vector<skm::pcr::Params> pcr_runs;   // parsed and validated before any read is touched (cli.rs:491-570)
+        for (auto &spec : pcr_specs) {
+            pcr_runs.push_back(skm::pcr::parse_pcr_primers_string(spec));
+            auto errs = skm::pcr::validate_pcr_params(pcr_runs.back());
+            if (!errs.empty()) throw skm::Error(SKM_ERR_INVALID_ARG, errs[0].first + " (" + errs[0].second + ")");
+        }
         skm::Engine eng(k, chunks, histo_max, capacity_hint, device, insert_mode);  // validates k, histo_max
         if (paired && max_reads > 0 && max_reads % 2 != 0) max_reads += 1;  // src/io.rs:483-485
         uint64_t n_reads_read = 0, n_bases_read = 0;
@@ -87,8 +103,40 @@ int main(int argc, char **argv) {
         }
         eng.finalize();
         skm::write_histo_files(eng, dir, sample);
-        skm::write_stats_file(eng, n_reads_read, n_bases_read, dir, sample, command);
         skm_totals t = eng.totals();
+        std::vector<skm::pcr::GeneResult> pcr_results;
+        if (!pcr_runs.empty()) {   // main.rs:146-177
+            skm::KmerCounts table(eng);
+            const size_t budget = node_budget ? node_budget : skm::pcr::compute_node_budget(t.n_bases);
+            pcr_results = skm::pcr::run_pcr(table, pcr_runs, sample, dir, min_kmer_count, budget);
+            for (auto &r : pcr_results) {
+                if (r.status == "success") {
+                    std::string lens;
+                    for (size_t l : r.product_lengths) lens += (lens.empty() ? "" : ", ") + std::to_string(l);
+                    std::fprintf(stderr, "  + %s (%zu product%s, %s bp)\n", r.gene_name.c_str(), r.product_lengths.size(),
+                                 r.product_lengths.size() == 1 ? "" : "s", lens.c_str());
+                } else {
+                    std::fprintf(stderr, "  - %s (no products, %s)\n", r.gene_name.c_str(), r.failure_reason.c_str());
+                }
+            }
+        }
+        skm::write_stats_file(eng, n_reads_read, n_bases_read, dir, sample, command);
+        if (!pcr_results.empty()) {   // stats.rs:12-45: the pcr_results list of the stats file
+            FILE *f = std::fopen((dir + sample + ".stats.yaml").c_str(), "a");
+            if (f) {
+                std::fprintf(f, "pcr_results:\n");
+                for (auto &r : pcr_results) {
+                    std::fprintf(f, "- gene_name: %s\n  status: %s\n  n_products: %zu\n", r.gene_name.c_str(), r.status.c_str(),
+                                 r.product_lengths.size());
+                    if (!r.product_lengths.empty()) {
+                        std::fprintf(f, "  product_lengths:\n");
+                        for (size_t l : r.product_lengths) std::fprintf(f, "  - %zu\n", l);
+                    }
+                    if (!r.failure_reason.empty()) std::fprintf(f, "  failure_reason: %s\n", r.failure_reason.c_str());
+                }
+                std::fclose(f);
+            }
+        }
         skm_stage_ms ms = eng.stage_times();
         std::fprintf(stderr, "reads %llu bases %llu kmers %llu unique %llu | device ms: h2d %.2f pack %.2f insert %.2f histogram %.2f\n",
                      (unsigned long long)n_reads_read, (unsigned long long)n_bases_read,

@@ -49,7 +49,25 @@ int32_t skm_chunk_totals(skm_ctx *, uint32_t, skm_totals *t) { std::memset(t, 0,
 int32_t skm_stage_times(skm_ctx *, skm_stage_ms *t) { std::memset(t, 0, sizeof *t); return SKM_OK; }
 int32_t skm_table_len(skm_ctx *, uint64_t *n) { *n = 0; return SKM_OK; }
 int32_t skm_export(skm_ctx *, uint64_t *, uint32_t *, uint64_t, int32_t, uint64_t *n) { *n = 0; return SKM_OK; }
-int32_t skm_lookup_batch(skm_ctx *, const uint64_t *, uint64_t, uint32_t, int32_t, uint32_t *, uint8_t *) { return SKM_ERR_STATE; }
+// the lookup contract of include/sharkmer_b200.h over the mock's std::map
+int32_t skm_lookup_batch(skm_ctx *c, const uint64_t *kmers, uint64_t n, uint32_t min_count, int32_t mode,
+                         uint32_t *counts, uint8_t *found) {
+    const uint32_t k = c->p.k;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t rc = skm_revcomp_kmer(kmers[i], k);
+        auto it = c->table.end();
+        if (mode == SKM_LOOKUP_CANONICAL) it = c->table.find(kmers[i] < rc ? kmers[i] : rc);
+        else if (mode == SKM_LOOKUP_EXACT) it = c->table.find(kmers[i]);
+        else {
+            it = c->table.find(kmers[i]);
+            if (it == c->table.end()) it = c->table.find(rc);
+        }
+        const bool ok = it != c->table.end() && it->second >= min_count;
+        counts[i] = ok ? it->second : 0;
+        if (found) found[i] = ok ? 1 : 0;
+    }
+    return SKM_OK;
+}
 int32_t skm_insert_counts(skm_ctx *c, const uint64_t *keys, const uint32_t *counts, uint64_t n) {
     for (uint64_t i = 0; i < n; i++) {
         uint64_t v = (uint64_t)c->table[keys[i]] + counts[i];
@@ -90,6 +108,7 @@ int32_t skm_scan_oligos(skm_ctx *c, const uint64_t *oligos, uint64_t n_oligos, u
 // harness: same flags as the CLI; dumps chunk_<c>.txt + counts.txt into --dump DIR
 #include "../../sharkmer_b200/host/fastq_parallel.hpp"
 #include "../../sharkmer_b200/host/primers.hpp"
+#include "../../sharkmer_b200/host/pcr.hpp"
 
 int main(int argc, char **argv) {
     uint32_t k = 21, chunks = 0;
@@ -98,7 +117,10 @@ int main(int argc, char **argv) {
     unsigned threads = 0;
     bool paired = false, serial = false;
     skm::PCRParams pcr;
-    std::string table_path;
+    std::string table_path, sample = "sample", outdir = "./";
+    std::vector<std::string> pcr_specs;
+    uint32_t min_kmer_count = 2;
+    size_t max_nodes = skm::pcr::DEFAULT_MAX_NUM_NODES;
     std::string dump = ".";
     std::vector<std::string> inputs;
     for (int i = 1; i < argc; i++) {
@@ -115,6 +137,15 @@ int main(int argc, char **argv) {
         else if (a == "--window-bytes") window_bytes = std::strtoull(argv[++i], nullptr, 10);
         else if (a == "--dump") dump = argv[++i];
         else if (a == "--table") table_path = argv[++i];
+        else if (a == "--pcr-primers") pcr_specs.push_back(argv[++i]);
+        else if (a == "--sample") sample = argv[++i];
+        else if (a == "--outdir") outdir = argv[++i];
+        else if (a == "--min-kmer-count") min_kmer_count = (uint32_t)std::strtoul(argv[++i], nullptr, 10);
+        else if (a == "--max-nodes") max_nodes = std::strtoull(argv[++i], nullptr, 10);
+        else if (a == "--lev") {   // bounded_levenshtein a b k
+            std::printf("%ld\n", skm::pcr::bounded_levenshtein(argv[i + 1], argv[i + 2], std::strtoull(argv[i + 3], nullptr, 10)));
+            return 0;
+        }
         else if (a == "--forward") pcr.forward_seq = argv[++i];
         else if (a == "--reverse") pcr.reverse_seq = argv[++i];
         else if (a == "--mismatches") pcr.mismatches = std::strtoull(argv[++i], nullptr, 10);
@@ -132,6 +163,21 @@ int main(int argc, char **argv) {
             skm::KmerCounts table(eng);
             while (f && std::fscanf(f, "%llu %llu", &km, &ct) == 2) table.insert((uint64_t)km, (uint32_t)ct);
             if (f) std::fclose(f);
+            if (!pcr_specs.empty()) {
+                // sPCR mode: one "gene status n_products lengths... | reason" line per primer pair
+                std::vector<skm::pcr::Params> runs;
+                for (auto &spec : pcr_specs) {
+                    runs.push_back(skm::pcr::parse_pcr_primers_string(spec));
+                    for (auto &e : skm::pcr::validate_pcr_params(runs.back()))
+                        throw skm::Error(SKM_ERR_INVALID_ARG, e.first + " (" + e.second + ")");
+                }
+                for (auto &r : skm::pcr::run_pcr(table, runs, sample, outdir, min_kmer_count, max_nodes)) {
+                    std::printf("%s %s %zu", r.gene_name.c_str(), r.status.c_str(), r.product_lengths.size());
+                    for (size_t l : r.product_lengths) std::printf(" %zu", l);
+                    std::printf(" | %s\n", r.failure_reason.c_str());
+                }
+                return 0;
+            }
             auto res = skm::get_primer_kmers(table, pcr);
             for (auto &e : res.first) std::printf("F %llu %u\n", (unsigned long long)e.first, e.second);
             for (auto &e : res.second) std::printf("R %llu %u\n", (unsigned long long)e.first, e.second);

@@ -427,3 +427,128 @@ def test_wave_extension_equals_sequential(oracle, seed, budget):
             assert g1.n_nodes > 1000    # far enough for the median refresh to fire
     if budget < 10_000 and g1.n_nodes > budget:
         assert g1.n_nodes <= budget + 8  # the check fires when a node is taken from the frontier
+
+
+# ---- the C++ twin (sharkmer_b200/host/pcr.hpp) through the test-only mock ABI ----------------------
+
+import subprocess
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    out = tmp_path_factory.mktemp("pcr") / "host_harness"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-o", str(out), os.path.join(HERE, "host", "mock_abi.cpp"),
+                    "-lz"], check=True)
+    return str(out)
+
+
+def run_cpp_pcr(harness, tmp_path, table, k, specs, sample="syn", extra=()):
+    keys, counts = table.export_sorted()
+    tf = tmp_path / "table.txt"
+    with open(tf, "w") as f:
+        for a, b in zip(keys.tolist(), counts.tolist()):
+            f.write(f"{a} {b}\n")
+    out = tmp_path / "cpp"
+    out.mkdir(exist_ok=True)
+    for f in out.iterdir():
+        f.unlink()
+    cmd = [harness, "-k", str(k), "--table", str(tf), "--sample", sample, "--outdir", str(out) + "/", *extra]
+    for s in specs:
+        cmd += ["--pcr-primers", s]
+    return subprocess.run(cmd, capture_output=True, text=True), out
+
+
+def spec_of(p):
+    return (f"forward={p.forward_seq},reverse={p.reverse_seq},name={p.gene_name},max-length={p.max_length},"
+            f"min-length={p.min_length},min-count={p.min_count},mismatches={p.mismatches},trim={p.trim}")
+
+
+def compare_with_python(harness, tmp_path, oracle_table, k, params_list, sample="syn", min_kmer_count=2, max_nodes=None):
+    extra = ["--min-kmer-count", str(min_kmer_count)] + (["--max-nodes", str(max_nodes)] if max_nodes else [])
+    r, out = run_cpp_pcr(harness, tmp_path, oracle_table, k, [spec_of(p) for p in params_list], sample, extra)
+    assert r.returncode == 0, r.stderr
+    py = tmp_path / "py"
+    py.mkdir(exist_ok=True)
+    for f in py.iterdir():
+        f.unlink()
+    res = pcr.run_pcr(OracleTable(oracle_table), k, params_list, sample, str(py) + "/", min_kmer_count,
+                      max_nodes or pcr.DEFAULT_MAX_NUM_NODES)
+    lines = [l for l in r.stdout.split("\n") if l]
+    assert len(lines) == len(res)
+    for line, want in zip(lines, res):
+        head, _, reason = line.partition(" | ")
+        gene, status, n, *lengths = head.split()
+        assert (gene, status, int(n), [int(x) for x in lengths]) == (want["gene_name"], want["status"], want["n_products"],
+                                                                    want["product_lengths"])
+        assert reason == (want["failure_reason"] or "")
+        fa = f"{sample}_{gene}.fasta"
+        if status == "success":
+            assert open(out / fa).read() == open(py / fa).read()     # byte-identical FASTA
+        else:
+            assert not os.path.exists(out / fa)
+    return res
+
+
+def test_cpp_18s_and_failures(harness, oracle, tmp_path):
+    t = table_18s(oracle)
+    absent = PCRParams("ACGTTTGACCATGACCA", "GGGTTTGACCATGACAA", gene_name="absent", min_count=3)
+    short = params_18s()
+    short.gene_name, short.max_length = "short", 300
+    res = compare_with_python(harness, tmp_path, t, 21, [params_18s(), absent, short], sample="smp", min_kmer_count=1)
+    assert [r["status"] for r in res] == ["success", "fail", "fail"]
+    assert res[1]["failure_reason"] == "forward and reverse primers not found" and res[2]["failure_reason"] == "no path found"
+    res = compare_with_python(harness, tmp_path, t, 21, [params_18s()], sample="smp", min_kmer_count=1, max_nodes=50)
+    assert res[0]["failure_reason"] == "node budget exceeded"
+
+
+@pytest.mark.parametrize("seed,k", [(1, 21), (5, 31)])
+def test_cpp_matches_python_on_branchy_input(harness, oracle, tmp_path, seed, k):
+    """Two loci, sequencing errors, a repeat shared with deeper sequence elsewhere, two alleles at
+    one locus: every FASTA byte and every failure reason must agree between the two hosts."""
+    rng = random.Random(seed)
+    rnd = lambda n: "".join(rng.choice("ACGT") for _ in range(n))
+    f1, r1, f2, r2 = rnd(22), rnd(22), rnd(20), rnd(24)
+    repeat = rnd(120)
+    ins = rnd(350)
+    ins_b = list(ins)
+    for p in range(30, 330, 14):
+        ins_b[p] = {"A": "C", "C": "G", "G": "T", "T": "A"}[ins_b[p]]
+    ins_b = "".join(ins_b)
+    g_a = rnd(500) + f1 + ins + rc(r1) + rnd(400) + f2 + rnd(200) + repeat + rnd(250) + rc(r2) + rnd(500)
+    g_b = g_a.replace(ins, ins_b)
+    other = "".join(rnd(150) + repeat for _ in range(5))
+    t = oracle.KmerCounts(k)
+    for s in make_reads(rng, g_a, 2600, 110, err=0.006) + make_reads(rng, g_b, 2200, 110, err=0.006) + make_reads(rng, other, 900, 110, err=0.006):
+        t.ingest_seq(s)
+    runs = [PCRParams(f1, r1, gene_name="locus1", min_count=2, max_length=1200),
+            PCRParams(f2, r2, gene_name="locus2", min_count=2, max_length=1500, min_length=100),
+            PCRParams(f1, r2, gene_name="span", min_count=3, max_length=400)]
+    res = compare_with_python(harness, tmp_path, t, k, runs)
+    assert res[0]["status"] == "success"
+
+
+def test_cpp_levenshtein_and_primer_spec_errors(harness, tmp_path):
+    rng = random.Random(3)
+    for _ in range(60):
+        a = "".join(rng.choice("ACG") for _ in range(rng.randint(1, 25)))
+        b = "".join(rng.choice("ACG") for _ in range(rng.randint(1, 25)))
+        for kk in (0, 2, 10):
+            got = int(subprocess.run([harness, "--lev", a, b, str(kk)], capture_output=True, text=True).stdout)
+            want = pcr.bounded_levenshtein(a, b, kk)
+            assert got == (-1 if want is None else want), (a, b, kk)
+    tf = tmp_path / "t.txt"
+    tf.write_text("5 3\n")
+    def spec(s):
+        return subprocess.run([harness, "-k", "5", "--table", str(tf), "--pcr-primers", s], capture_output=True, text=True)
+    r = spec("forward=ACGT,reverse=TTGA,name=x,forward=AAAA")
+    assert r.returncode == 1 and "Duplicate parameter 'forward' in primer specification" in r.stderr
+    r = spec("forward=ACGT,reverse=TTGA,bogus=1")
+    assert r.returncode == 1 and "Unexpected parameter: bogus" in r.stderr
+    r = spec("forward=ACGT,reverse")
+    assert r.returncode == 1 and "Invalid parameter (should be key=value): 'reverse'" in r.stderr
+    r = spec("forward=ACGT,reverse=TTGA,name=x,trim=abc")
+    assert r.returncode == 1 and "Invalid value for trim: abc" in r.stderr
+    r = spec("forward=acgt,reverse=ttga,name=x,min-count=1")
+    assert r.returncode == 1 and "min-count is 1, must be at least 2" in r.stderr
+    r = spec("forward=ACGT,reverse=TTGA")
+    assert r.returncode == 1 and "Gene name is empty" in r.stderr
