@@ -333,6 +333,37 @@ class ShardedCounter:
         dist.all_reduce(t, group=self.group)                  # histogram = sum of the partitions' histograms
         return t.cpu().numpy().astype(np.uint64)
 
+    # -- table services over the sharded table (what sPCR needs; collective: every rank calls them
+    #    with the same arguments and gets the same answer) ----------------------------------------
+    def lookup(self, kmers, min_count: int = 0, mode: int = 0):
+        """skm_lookup_batch over all shards: a k-mer lives on exactly one rank (ownership is by the
+        hash of the canonical k-mer), so the answer is the maximum over the ranks' local answers."""
+        counts, _ = self.e.lookup(kmers, min_count, mode)
+        t = torch.as_tensor(np.ascontiguousarray(counts).astype(np.int64), device=self.device)
+        if t.numel():
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        c = t.cpu().numpy().astype(np.uint32)
+        return c, c > 0
+
+    def scan_oligos(self, oligos, oligo_length: int, min_count: int):
+        """skm_scan_oligos over all shards: every rank scans its own part of the table, the matches
+        are gathered and merged in ascending k-mer order."""
+        keys, counts = self.e.scan_oligos(oligos, oligo_length, min_count)
+        n = torch.tensor([keys.size], dtype=torch.int64, device=self.device)
+        sizes = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.world)]
+        dist.all_gather(sizes, n, group=self.group)
+        sizes = [int(x.item()) for x in sizes]
+        width = max(max(sizes), 1)
+        mine = torch.zeros(2 * width, dtype=torch.int64, device=self.device)
+        mine[:keys.size] = torch.as_tensor(keys.astype(np.int64), device=self.device)
+        mine[width:width + keys.size] = torch.as_tensor(counts.astype(np.int64), device=self.device)
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        all_k = np.concatenate([p[:sizes[r]].cpu().numpy().astype(np.uint64) for r, p in enumerate(parts)])
+        all_c = np.concatenate([p[width:width + sizes[r]].cpu().numpy().astype(np.uint32) for r, p in enumerate(parts)])
+        order = np.argsort(all_k, kind="stable")
+        return all_k[order], all_c[order]
+
     def global_totals(self, local: dict) -> dict:
         keys = sorted(local)
         t = torch.as_tensor([int(local[k]) for k in keys], dtype=torch.int64, device=self.device)

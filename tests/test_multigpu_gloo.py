@@ -80,6 +80,33 @@ class FakeEngine:
     def histogram(self, c):
         return self.cols[c]
 
+    # table services over this rank's shard (what Engine.lookup / Engine.scan_oligos do on the device)
+    def lookup(self, kmers, min_count, mode):
+        rc = self.common.revcomp_kmer
+        counts = np.zeros(len(kmers), dtype=np.uint32)
+        for i, x in enumerate(np.asarray(kmers, dtype=np.uint64).tolist()):
+            r = rc(x, K)
+            c = self.table.get(min(x, r) if mode == 0 else x, 0)
+            if mode == 2 and not c:
+                c = self.table.get(r, 0)
+            counts[i] = c if c >= min_count else 0
+        return counts, counts > 0
+
+    def scan_oligos(self, oligos, length, min_count):
+        want = set(int(x) for x in oligos)
+        out = {}
+        for x, c in self.table.items():
+            if c < min_count:
+                continue
+            if (x >> (2 * (K - length))) in want:
+                out[x] = c
+            else:
+                r = self.common.revcomp_kmer(x, K)
+                if (r >> (2 * (K - length))) in want:
+                    out[r] = c
+        keys = np.array(sorted(out), dtype=np.uint64)
+        return keys, np.array([out[int(x)] for x in keys], dtype=np.uint32)
+
 
 def worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
@@ -115,6 +142,54 @@ def worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def planted_reads():
+    import random
+    rng = random.Random(17)
+    rnd = lambda n: "".join(rng.choice("ACGT") for _ in range(n))
+    rcs = lambda x: x[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    fwd, rev, insert = rnd(22), rnd(22), rnd(300)
+    genome = rnd(700) + fwd + insert + rcs(rev) + rnd(700)
+    reads = []
+    for _ in range(4000):
+        at = rng.randint(0, len(genome) - L)
+        seq = "".join(c if rng.random() > 0.003 else rng.choice("ACGT") for c in genome[at:at + L])
+        reads.append(seq if rng.random() < 0.5 else rcs(seq))
+    return fwd, rev, fwd[-15:] + insert + rcs(rev)[:15], reads
+
+
+def worker_pcr(rank, world, port, q):
+    """Count planted-amplicon reads on a sharded (fake) table, then run sPCR on it through
+    ShardedCounter.lookup / scan_oligos: every rank must recover the same amplicon."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as o
+    from sharkmer_b200 import common, pcr
+    from sharkmer_b200.multigpu import ShardedCounter
+    from sharkmer_b200.primers import PCRParams
+    fwd, rev, want, reads = planted_reads()
+    by_chunk = []
+    for c in range(CHUNKS):
+        batches = list(range(c, (len(reads) + 999) // 1000, CHUNKS))
+        lo, hi = len(batches) * rank // world, len(batches) * (rank + 1) // world
+        mine = []
+        for b in batches[lo:hi]:
+            mine.extend(reads[b * 1000:(b + 1) * 1000])
+        by_chunk.append(mine)
+    eng = FakeEngine(o, common, by_chunk, world, rank)
+    sc = ShardedCounter(eng, CHUNKS, CHUNKS, HMAX, torch.device("cpu"))
+    sc.finalize()
+    out = pcr.do_pcr(sc, K, "smp", PCRParams(fwd, rev, gene_name="locus", max_length=1000))
+    probe = np.array(list(eng.table)[:50] + [12345], dtype=np.uint64)   # this rank's keys, asked of everybody
+    everybody = [None] * world
+    dist.all_gather_object(everybody, probe.tolist())
+    probe = np.array(everybody[0], dtype=np.uint64)                       # same query on every rank
+    counts, found = sc.lookup(probe, 0, 2)
+    if rank == 0:
+        q.put(([(r.id, r.seq) for r in out.records], out.failure_reason, want, counts.tolist(), found.tolist(), probe.tolist()))
+    dist.destroy_process_group()
+
+
 def free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -143,3 +218,25 @@ def test_sharded_counter_matches_oracle(oracle, world):
     assert tot == {"n_unique": keys.size, "n_kmers": int(run.n_kmers_ingested)}
     for c in range(CHUNKS):
         assert (cols[c] == run.histogram(c)).all(), c
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_spcr_on_sharded_table(oracle, world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=worker_pcr, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    records, failure, want, counts, found, probe = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert failure is None and records == [("smp_locus_0", want)]
+    # the collective lookup answers like one table holding everything
+    t = oracle.KmerCounts(K)
+    for s in planted_reads()[3]:
+        t.ingest_seq(s)
+    for x, c, f in zip(probe, counts, found):
+        ref = t.get_canonical(x)
+        assert (c, f) == ((ref, True) if ref is not None else (0, False))
