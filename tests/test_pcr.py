@@ -15,11 +15,24 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 READ_18S = open(os.path.join(HERE, "golden", "pcr_18s_read.txt")).read().strip()
 
 
+def revcomp_np(x, k):
+    """Vectorised reverse complement of 2-bit packed k-mers (same bit tricks as skm_revcomp_kmer)."""
+    x = ~np.asarray(x, dtype=np.uint64)
+    for sh, m in ((2, 0x3333333333333333), (4, 0x0F0F0F0F0F0F0F0F), (8, 0x00FF00FF00FF00FF), (16, 0x0000FFFF0000FFFF)):
+        m = np.uint64(m)
+        x = ((x >> np.uint64(sh)) & m) | ((x & m) << np.uint64(sh))
+    x = (x >> np.uint64(32)) | (x << np.uint64(32))
+    return x >> np.uint64(64 - 2 * k)
+
+
 class OracleTable:
-    """Engine stand-in over an oracle KmerCounts (tests only): lookup (EITHER mode) + scan_oligos."""
+    """Engine stand-in over an oracle KmerCounts (tests only): lookup (EITHER mode) + scan_oligos.
+    The oracle's tables hold canonical k-mers only, so "the k-mer as given, else its reverse
+    complement" is a search for min(kmer, revcomp) in the sorted export."""
     def __init__(self, table):
         self.t = table
         self.k = table.get_k()
+        self.keys, self.counts = table.export_sorted()
         self.lookup_calls = 0
         self.lookups = 0
     def scan_oligos(self, oligos, length, min_count):
@@ -28,13 +41,13 @@ class OracleTable:
         assert mode == _lib.LOOKUP_EITHER
         self.lookup_calls += 1
         self.lookups += len(kmers)
-        counts = np.zeros(len(kmers), dtype=np.uint32)
-        found = np.zeros(len(kmers), dtype=bool)
-        for i, km in enumerate(np.asarray(kmers, dtype=np.uint64).tolist()):
-            c = self.t.get_canonical(km)
-            if c is not None and c >= min_count:
-                counts[i], found[i] = c, True
-        return counts, found
+        q = np.asarray(kmers, dtype=np.uint64)
+        canon = np.minimum(q, revcomp_np(q, self.k))
+        pos = np.minimum(np.searchsorted(self.keys, canon), max(self.keys.size - 1, 0))
+        hit = (self.keys[pos] == canon) if self.keys.size else np.zeros(q.size, dtype=bool)
+        counts = np.where(hit, self.counts[pos] if self.keys.size else 0, 0).astype(np.uint32)
+        found = hit & (counts >= min_count)
+        return np.where(found, counts, 0).astype(np.uint32), found
 
 
 def rc(s):
