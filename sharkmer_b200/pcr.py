@@ -218,50 +218,71 @@ class _WaveLookups:
     is narrow (a linear stretch has two entries, one per direction) the call also asks, blindly, for
     the candidates of the candidates, several levels deep, up to `budget` k-mers: what a node needs
     depends only on its sub-k-mer and direction, so answers are cached under that key and a level
-    of the graph that was guessed right costs no round trip at all."""
+    of the graph that was guessed right costs no round trip at all.  The guesses are enumerated
+    with array arithmetic, not per k-mer."""
 
     def __init__(self, table, view_min_count: int, k: int, budget: int = 4096):
         self.table, self.view_min, self.k, self.budget = table, view_min_count, k, budget
-        self.shift = 2 * (k - 1)
-        self.mask = get_suffix_mask(k)
-        self.ready = {}       # (sub_kmer, dir) -> (kmers[4], counts[4], found[4])
+        self.shift = np.uint64(2 * (k - 1))
+        self.mask = np.uint64(get_suffix_mask(k))
+        self.row = {}         # (sub_kmer << 1 | dir) -> (wave, row) of the cached answer
+        self.waves = {}       # wave id -> (kmers[n,4], counts[n,4], found[n,4], rows still cached)
+        self.next_wave = 0
         self.calls = 0
         self.kmers_asked = 0
 
-    def candidates(self, sub_kmer: int, direction: int):
-        if direction == FORWARD:
-            return [(sub_kmer << 2) | b for b in range(4)]
-        return [(b << self.shift) | sub_kmer for b in range(4)]
+    def _candidates(self, keys):
+        """keys: packed (sub_kmer << 1 | dir) -> candidate k-mers [n, 4] and the children's keys [n, 4]."""
+        sub, d = keys >> np.uint64(1), keys & np.uint64(1)
+        base = np.arange(4, dtype=np.uint64)[None, :]
+        fwd = (sub[:, None] << np.uint64(2)) | base
+        rev = (base << self.shift) | sub[:, None]
+        is_fwd = (d == 0)[:, None]
+        cands = np.where(is_fwd, fwd, rev)
+        child = np.where(is_fwd, cands & self.mask, cands >> np.uint64(2))
+        return cands, (child << np.uint64(1)) | d[:, None]
 
     def get(self, graph: DiGraph, frontier, node: int, direction: int):
-        key = (graph.nodes[node][0], direction)
-        if key not in self.ready:
-            level = list(dict.fromkeys([key] + [(graph.nodes[n][0], d) for (n, d) in frontier]))
-            level = [e for e in level if e not in self.ready]
-            todo, seen = [], set()
-            while level and 4 * (len(todo) + len(level)) <= max(self.budget, 4 * len(level) if not todo else 0):
-                todo += level
-                seen.update(level)
-                nxt = []
-                for sub, d in level:
-                    for c in self.candidates(sub, d):
-                        child = ((c & self.mask) if d == FORWARD else (c >> 2), d)
-                        if child not in seen and child not in self.ready:
-                            seen.add(child)
-                            nxt.append(child)
+        key = (graph.nodes[node][0] << 1) | direction
+        if key not in self.row:
+            first = [key] + [(graph.nodes[n][0] << 1) | d for (n, d) in frontier]
+            first = [q for q in dict.fromkeys(first) if q not in self.row]
+            level = np.array(first, dtype=np.uint64)
+            todo, cands_all = [], []
+            n_todo = 0
+            while level.size and (not todo or 4 * (n_todo + level.size) <= self.budget):
+                cands, child = self._candidates(level)
+                todo.append(level)
+                cands_all.append(cands)
+                n_todo += level.size
+                nxt = np.unique(child.reshape(-1))
+                known = np.concatenate(todo)
+                nxt = nxt[~np.isin(nxt, known)]
+                if self.row and nxt.size:
+                    nxt = np.array([q for q in nxt.tolist() if q not in self.row], dtype=np.uint64)
                 level = nxt
-            kmers = np.array([c for (sub, d) in todo for c in self.candidates(sub, d)], dtype=np.uint64)
-            counts, found = self.table.lookup(kmers, self.view_min, _lib.LOOKUP_EITHER)
+            keys = np.concatenate(todo)
+            kmers = np.concatenate(cands_all)
+            counts, found = self.table.lookup(kmers.reshape(-1), self.view_min, _lib.LOOKUP_EITHER)
             self.calls += 1
             self.kmers_asked += int(kmers.size)
-            kl, cl, fl = kmers.tolist(), counts.tolist(), found.tolist()
-            for i, e in enumerate(todo):
-                self.ready[e] = (kl[4 * i:4 * i + 4], cl[4 * i:4 * i + 4], fl[4 * i:4 * i + 4])
-            if len(self.ready) > 1_000_000:   # guesses that were never needed
-                keep = {(graph.nodes[n][0], d) for (n, d) in frontier}
+            w = self.next_wave
+            self.next_wave += 1
+            self.waves[w] = [kmers, np.asarray(counts).reshape(-1, 4), np.asarray(found).reshape(-1, 4), keys.size]
+            self.row.update(zip(keys.tolist(), ((w, i) for i in range(keys.size))))
+            if len(self.row) > 1_000_000:   # guesses that were never needed
+                keep = {(graph.nodes[n][0] << 1) | d for (n, d) in frontier}
                 keep.add(key)
-                self.ready = {e: v for e, v in self.ready.items() if e in keep}
-        return self.ready.pop(key)
+                self.row = {q: v for q, v in self.row.items() if q in keep}
+                alive = {v[0] for v in self.row.values()}
+                self.waves = {i: x for i, x in self.waves.items() if i in alive}
+        w, i = self.row.pop(key)
+        wave = self.waves[w]
+        out = (wave[0][i].tolist(), wave[1][i].tolist(), wave[2][i].tolist())
+        wave[3] -= 1
+        if wave[3] == 0:
+            del self.waves[w]
+        return out
 
 
 def extend_graph(graph: DiGraph, node_lookup: dict, table, view_min_count: int, min_count: int,
