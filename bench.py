@@ -47,13 +47,15 @@ N_RATE = 0.001
 SEED = 2
 DISTINCT_HINT_PER_GPU = 320_000_000
 CPU_SAMPLE_READS = 300_000
-B_ALG_PER_KMER = 64.0      # 32 B sector in + 32 B sector out per k-mer occurrence
-B_ALG_PER_BASE = 0.375     # packed stream read by the extract kernels: 2-bit code + 1-bit break mask
-# DRAM bytes per k-mer of the dominant kernel from the committed `ncu --set full` captures
-# (profiles/r01_insert_kernel_full.csv: 7.58 GB read + 2.72 GB written per launch of 1.273e8 k-mers,
-#  mean of the three captured launches;
-#  profiles/r01_direct_kernel_full.csv: 12.2 + 3.0 GB for 1.27e8 k-mers)
-NCU_DRAM_BYTES_PER_KMER = {"insert_runs_kernel": 80.9, "extract_insert_kernel": 119.7}
+B_SURVEY_PER_KMER = 64.0   # 32 B sector in + 32 B sector out per k-mer occurrence (random-sector model)
+B_SURVEY_PER_BASE = 1.5    # 1 B ASCII read + 0.25 B packed write + 0.25 B packed read
+# Algorithmic bytes of each kernel of the tiled path, per unit of work:
+#   bucket_scatter_kernel : 0.375 B per position read (2-bit code + break bit) + 8 B per k-mer written
+#   tile_sort_kernel      : 8 B per k-mer read + 8 B per k-mer written (in place, tile by tile)
+#   tile_insert_kernel    : 8 B per k-mer read + 16 B per slot written (+ 16 B per slot read unless the table is new)
+#   extract_insert_kernel : 64 B per k-mer (one random 32-byte sector in and out) + 0.375 B per position (direct mode)
+# DRAM bytes per launch measured by `ncu --set full` (profiles/README.md), per unit, for `traffic`:
+NCU_TRAFFIC = {}  # filled from profiles/r02_traffic.json when present
 
 
 def load_peaks():
@@ -126,8 +128,14 @@ class ClockSampler:
 # reference arm: the reference's CPU algorithm (oracle port), bounded sample
 # ----------------------------------------------------------------------------
 
+def sample_genome(n_reads):
+    """Genome length for a bounded sample at the SAME depth as the full workload (30x): a sample
+    taken from the full-size genome would be almost all first-time inserts, a different regime."""
+    return max(1000, GENOME_PER_GPU * n_reads // READS_PER_GPU)
+
+
 def cpu_sample(n_reads, genome_len):
-    """One bounded CPU pass: the first n_reads reads of the workload, k=21, 10 chunks."""
+    """One bounded CPU pass over n_reads reads of the workload's generator, k=21, 10 chunks."""
     from oracle import oracle as o
     reads = o.synth_reads(SEED, genome_len, READ_LEN, SUB_RATE, N_RATE, 0, n_reads)
     t0 = time.perf_counter()
@@ -143,7 +151,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     n = args.cpu_sample_reads
-    genome = GENOME_PER_GPU * args.gpus
+    genome = sample_genome(n)
     times, kmers = [], 0
     for i in range(args.warmup + args.steps):
         run, _, dt = cpu_sample(n, genome)
@@ -153,18 +161,22 @@ def run_reference(args):
         del run
     t = float(np.mean(times))
     v = kmers / t
-    sample = (f"first {n} reads of the workload (k={K}, chunks={CHUNKS}); full algorithm: per-chunk tables, "
-              f"ordered merge, incremental histogram; one pass per step")
+    sample = (f"{n} reads of the workload's generator at the workload's depth ({genome} bp genome = 30x, same error "
+              f"rates and seed; k={K}, chunks={CHUNKS}); full algorithm: per-chunk tables, ordered merge, incremental "
+              f"histogram; one pass per step")
+    cfg = workload_config(args.gpus)   # the repo arm's config (contract); what was actually run is `sample` below
     line = {
         "impl": "reference", "metric": "kmers_counted_per_sec", "value": v, "unit": "kmers/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": v, "unit": "kmers/s", "cores": 1, "kind": "port", "sample": sample,
                          "note": "C oracle port of sharkmer src/kmer + src/io.rs (Rust reference cannot be "
                                  "built here: no cargo); the reference counts on 1 thread regardless of -t"},
         "e2e": {"value": v, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "sample": {"what": "each step runs a BOUNDED SAMPLE of config.workload, not the whole workload",
+                   "reads": n, "genome_len": genome, "depth": "30x, as in the workload", "kmers_per_step": int(kmers)},
     }
     emit(line)
     return 0
@@ -188,7 +200,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from sharkmer_b200 import _lib, kmer
-    from oracle import oracle as o  # thresholds + cpu_baseline leg only
+    from sharkmer_b200.common import rate_to_thresh
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -229,7 +241,7 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev, priority=-1 if os.environ.get("SKM_PRIO", "1") != "0" else 0)
     eng = kmer.Engine(K, CHUNKS, HISTO_MAX, capacity_hint=hint, device=local_rank, insert_mode=mode,
                       n_ranks=world, rank=rank, stream=stream.cuda_stream)
-    st, nt = o.rate_to_thresh(SUB_RATE), o.rate_to_thresh(N_RATE)
+    st, nt = rate_to_thresh(SUB_RATE), rate_to_thresh(N_RATE)
     line = READ_LEN + 1
 
     # ---- inputs: chunk c holds the reads of batches b = c (mod CHUNKS) (src/io.rs:355-361);

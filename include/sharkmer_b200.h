@@ -41,7 +41,8 @@ enum {
     SKM_ERR_STATE = 5,         /* call not valid in this state (e.g. ingest after finalize) */
     SKM_ERR_CONSERVATION = 6,  /* a conservation identity failed (src/io.rs:1042-1047,1120-1132) */
     SKM_ERR_K_MISMATCH = 7,    /* merge of tables with different k (src/kmer/counting.rs:158-160) */
-    SKM_ERR_NO_READS = 8       /* nothing was ingested (src/io.rs:578-580) */
+    SKM_ERR_NO_READS = 8,      /* nothing was ingested (src/io.rs:578-580) */
+    SKM_ERR_CAPACITY = 9       /* the table could not be grown far enough (device memory), or a table partition filled up */
 };
 
 typedef struct skm_ctx skm_ctx;
@@ -86,6 +87,11 @@ typedef struct skm_stage_ms {
     uint64_t table_bytes;
     uint64_t insert_kmers;   /* k-mers handed to the insert kernels */
     uint64_t insert_bases;   /* packed bases read by the fused extract+insert kernel */
+    float sort;              /* tile_sort_kernel (pass B of the tiled insert) */
+    float scan;              /* skm_scan_oligos table passes */
+    uint32_t sort_launches, scan_launches;
+    uint32_t tiled_launches; /* tile_insert_kernel launches ... */
+    uint32_t tiled_retries;  /* ... of which retries after growing the table */
 } skm_stage_ms;
 
 uint32_t skm_abi_version(void);

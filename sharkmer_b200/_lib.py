@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsharkmer_b200.so")
 
 OK = 0
-ERR_INVALID_ARG, ERR_INVALID_BASE, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_CONSERVATION, ERR_K_MISMATCH, ERR_NO_READS = range(1, 9)
+ERR_INVALID_ARG, ERR_INVALID_BASE, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_CONSERVATION, ERR_K_MISMATCH, ERR_NO_READS, ERR_CAPACITY = range(1, 10)
 INSERT_AUTO, INSERT_DIRECT, INSERT_PARTITIONED = 0, 1, 2
 LOOKUP_CANONICAL, LOOKUP_EXACT, LOOKUP_EITHER = 0, 1, 2
 INGEST_ASYNC = 1
@@ -38,7 +38,9 @@ class SkmStageMs(C.Structure):
         ("launches", C.c_uint32 * 8),
         ("kernel_launches", C.c_uint32), ("n_grows", C.c_uint32),
         ("table_capacity", C.c_uint64), ("table_bytes", C.c_uint64),
-        ("insert_kmers", C.c_uint64), ("insert_bases", C.c_uint64)]
+        ("insert_kmers", C.c_uint64), ("insert_bases", C.c_uint64),
+        ("sort", C.c_float), ("scan", C.c_float), ("sort_launches", C.c_uint32), ("scan_launches", C.c_uint32),
+        ("tiled_launches", C.c_uint32), ("tiled_retries", C.c_uint32)]
 
 
 # every symbol include/sharkmer_b200.h declares: name -> (restype, argtypes)

@@ -49,3 +49,8 @@ def revcomp_kmer(kmer: int, k: int) -> int:
         x = ((x >> sh) & m) | ((x & m) << sh)
     x = ((x >> 32) | (x << 32)) & M64
     return x >> (64 - 2 * k)
+
+
+def rate_to_thresh(rate: float) -> int:
+    """A probability as the 32-bit threshold skm_synth_params takes (include/skm_common.h)."""
+    return min(0xFFFFFFFF, int(round(rate * 4294967296.0)))

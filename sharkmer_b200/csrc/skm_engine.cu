@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../include/sharkmer_b200.h"
 #include "skm_kernels.cuh"
 
@@ -34,7 +36,7 @@ constexpr uint32_t kMaxRuns = 4096;     // runs per insert launch
 constexpr uint32_t kDescRing = 4;
 constexpr uint64_t kMaxListKmers = 1ull << 30;  // k-mer list budget per partition pass (8 GiB)
 
-enum Stage { ST_H2D, ST_PACK, ST_COUNT, ST_PART, ST_INSERT, ST_HISTO, ST_GROW, ST_FINALIZE, ST_N };
+enum Stage { ST_H2D, ST_PACK, ST_COUNT, ST_PART, ST_INSERT, ST_HISTO, ST_GROW, ST_FINALIZE, ST_SCAN, ST_SORT, ST_N };
 
 struct Segment {
     uint64_t *codes = nullptr;
@@ -51,6 +53,11 @@ struct Segment {
     // overflow total instead of offsets, and codes/breaks stay alive until the totals were checked
     uint64_t cap = 0, ovf_cap = 0;
     size_t list_cells = 0;  // cells allocated for `list`
+    // tile-sorted form (tiled insert): where the buckets' tiles are + the sub-bucket offsets of every tile
+    unsigned long long *meta = nullptr;   // ListMeta arrays (list_meta_words(n_buckets) words)
+    uint16_t *tile_off = nullptr;         // max_tiles * (2^g2 + 1)
+    uint32_t max_tiles = 0;
+    bool tiled = false;
 };
 
 struct ChunkState {
@@ -171,6 +178,24 @@ struct skm_ctx {
     uint32_t launches = 0;
     uint32_t n_grows = 0;
 
+    std::vector<cudaStream_t> read_streams;  // idle private streams of the read-side calls
+
+    // tiled insert (tile_insert_kernel)
+    uint32_t g2 = 7;                         // sub-bucket bits of the lists built by this ctx
+    bool table_fresh = true;                 // logically empty: no key was ever inserted since create / reset
+    bool table_zombie = false;               // logically empty but NOT physically cleared (skm_reset defers the clear:
+                                             // the tiled insert starts every partition empty and rewrites the whole table)
+    unsigned long long *d_delta = nullptr;   // per-chunk histogram moves of one launch
+    size_t delta_words = 0;
+    unsigned long long *d_recount = nullptr; // histogram of the written-back partitions (histo_max + 2)
+    uint32_t *d_fail = nullptr;              // failed partitions of the last launch
+    uint32_t *d_part_ids = nullptr;          // partitions to retry
+    static constexpr uint32_t kFailCap = 1u << 20;
+    void *h_segs = nullptr, *d_segs = nullptr;   // SegDesc[] + chunk_first_seg[] of one launch (pinned / device)
+    size_t segs_bytes = 0;
+    uint32_t n_tiled_launches = 0, n_tiled_retries = 0;
+    bool recount_valid = false;              // d_recount / last_tot describe the whole table as it is now
+
     std::string err;
     std::mutex mu;
 };
@@ -243,14 +268,14 @@ struct Span {
 void collect_spans(skm_ctx *c) {
     static const char *trace_path = getenv("SKM_TRACE");
     if (trace_path && !c->spans.empty()) {
-        static const char *names[] = {"h2d", "pack", "count", "partition", "insert", "histogram", "grow", "other"};
+        static const char *names[] = {"h2d", "pack", "count", "partition", "insert", "histogram", "grow", "other", "scan", "sort"};
         static int batch = 0;
         if (FILE *f = std::fopen(trace_path, "a")) {
             for (auto &t : c->spans) {
                 float a = 0, b = 0;
                 if (cudaEventElapsedTime(&a, c->spans[0].a, t.a) == cudaSuccess &&
                     cudaEventElapsedTime(&b, c->spans[0].a, t.b) == cudaSuccess)
-                    std::fprintf(f, "%d %s %.3f %.3f\n", batch, names[t.stage < 8 ? t.stage : 7], a, b);
+                    std::fprintf(f, "%d %s %.3f %.3f\n", batch, names[t.stage < 10 ? t.stage : 7], a, b);
             }
             std::fclose(f);
         }
@@ -283,14 +308,28 @@ uint32_t ceil_log2(uint64_t v) {
 
 inline uint32_t grid_for(uint64_t n, uint32_t block) { return (uint32_t)((n + block - 1) / block); }
 
-int32_t alloc_table(skm_ctx *c, uint32_t log2cap, Slot **out) {
+int32_t alloc_table(skm_ctx *c, uint32_t log2cap, Slot **out, bool clear = true) {
     Slot *t = nullptr;
     const uint64_t cap = 1ull << log2cap;
     CU(cudaMallocAsync((void **)&t, cap * sizeof(Slot), c->stream));
-    table_clear_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(t, cap);
+    if (clear) {
+        table_clear_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(t, cap);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    *out = t;
+    return SKM_OK;
+}
+
+// skm_reset (and a re-sized empty table) leave the table "zombie": logically empty, physically
+// stale.  The tiled insert never reads it (every partition starts empty in shared memory and the
+// whole table is rewritten); anything else that touches the table clears it first.
+int32_t ensure_physical(skm_ctx *c) {
+    if (!c->table_zombie) return SKM_OK;
+    table_clear_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity);
     c->launches++;
     CU(cudaGetLastError());
-    *out = t;
+    c->table_zombie = false;
     return SKM_OK;
 }
 
@@ -305,10 +344,22 @@ int32_t read_distinct(skm_ctx *c, uint64_t *out) {
 int32_t grow_table(skm_ctx *c, uint32_t new_log2cap) {
     Span sp(c, ST_GROW, c->stream);
     Slot *nt = nullptr;
+    if (c->table_fresh) {  // nothing to move; the new table is cleared lazily (ensure_physical)
+        CU(cudaFreeAsync(c->table, c->stream));
+        c->table = nullptr;
+        int32_t rc0 = alloc_table(c, new_log2cap, &nt, false);
+        if (rc0) return rc0;
+        c->table_zombie = true;
+        c->table = nt;
+        c->log2cap = new_log2cap;
+        c->capacity = 1ull << new_log2cap;
+        c->n_grows++;
+        return SKM_OK;
+    }
     int32_t rc = alloc_table(c, new_log2cap, &nt);
     if (rc) return rc;
     rehash_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity,
-                                                          TableRef{nt, new_log2cap, c->n_ranks});
+                                                          TableRef{nt, new_log2cap, c->n_ranks}, c->d_gc);
     c->launches++;
     c->stage_launches[ST_GROW]++;
     CU(cudaGetLastError());
@@ -398,10 +449,13 @@ int32_t ensure_list(skm_ctx *c, uint64_t n) {
 
 // ---- direct mode: fused extract + insert over one segment -------------------
 int32_t insert_segment_direct(skm_ctx *c, const Segment &sg, uint32_t chunk) {
+    c->recount_valid = false;
     uint64_t u = 0;
     while (u < sg.n_units) {
         uint64_t granted = 0;
         int32_t rc = reserve_headroom(c, (sg.n_units - u) * 32, &granted);
+        if (rc) return rc;
+        rc = ensure_physical(c);  // (after the headroom check: an empty table may just have been re-sized)
         if (rc) return rc;
         uint64_t tile_units = std::max<uint64_t>(granted / 32, 1);
         tile_units = std::min(tile_units, sg.n_units - u);
@@ -424,6 +478,7 @@ int32_t insert_segment_direct(skm_ctx *c, const Segment &sg, uint32_t chunk) {
             c->insert_bases += std::min(tile_units * 32, sg.n_bytes - u * 32);
         }
         CU(cudaGetLastError());
+        c->table_fresh = false;
         note_inserted(c, tile_units * 32);
         u += tile_units;
     }
@@ -522,16 +577,14 @@ int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketF
 
 // Forget a capped list (waits for its bucketing): frees it on `st` and takes back the windows its
 // scatter added to the chunk's counter, so that the exact path can count them again.
+void release_list(skm_ctx *c, Segment &sg, cudaStream_t st);
 int32_t drop_capped_list(skm_ctx *c, uint32_t chunk, Segment &sg, cudaStream_t st) {
     CU(cudaEventSynchronize(sg.ready));
     uint64_t counted = 0;
     for (uint32_t r = 0; r < sg.n_buckets; r++) counted += sg.h_offsets[r];
     adjust_counter_kernel<<<1, 1, 0, st>>>(&c->d_cc[chunk].n_windows, 0ull - counted);
     c->launches++;
-    CU(cudaFreeAsync(sg.list, st));
-    c->list_bytes -= std::min<size_t>(c->list_bytes, sg.list_cells * sizeof(uint64_t));
-    sg.list = nullptr;
-    sg.cap = 0;
+    release_list(c, sg, st);
     return SKM_OK;
 }
 
@@ -580,10 +633,13 @@ void launch_insert_runs(skm_ctx *c, uint64_t n_tiles, const RunDesc *descs, uint
 // is an upper bound and the whole list goes in one launch).
 int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_t *d_counts, uint64_t n,
                     const unsigned long long *n_dev = nullptr) {
+    c->recount_valid = false;
     uint64_t i = 0;
     while (i < n) {
         uint64_t granted = 0;
         int32_t rc = reserve_headroom(c, n - i, &granted);
+        if (rc) return rc;
+        rc = ensure_physical(c);  // (after the headroom check: an empty table may just have been re-sized)
         if (rc) return rc;
         granted = std::max<uint64_t>(std::min(granted, n - i), 1);
         {
@@ -594,6 +650,7 @@ int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_
             c->insert_kmers += granted;
         }
         CU(cudaGetLastError());
+        c->table_fresh = false;
         note_inserted(c, granted);
         i += granted;
     }
@@ -602,6 +659,10 @@ int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_
 
 // Launch one kernel over runs [i, j) (tile_begin is filled in here).
 int32_t launch_run_range(skm_ctx *c, std::vector<RunDesc> &runs, size_t i, size_t j, uint64_t total) {
+    int32_t rc0 = ensure_physical(c);
+    if (rc0) return rc0;
+    c->recount_valid = false;
+    c->table_fresh = false;
     uint64_t tiles = 0;
     for (size_t q = i; q < j; q++) {
         runs[q].tile_begin = tiles;
@@ -663,61 +724,13 @@ int32_t insert_runs(skm_ctx *c, const std::vector<RunDesc> &runs_in) {
     return SKM_OK;
 }
 
-// ---- partitioned mode: bucket by table region, then insert region by region --
-int32_t insert_chunk_partitioned(skm_ctx *c, uint32_t chunk) {
-    const ChunkState &cs = c->chunks[chunk];
-    size_t s0 = 0;
-    while (s0 < cs.segs.size()) {
-        // group segments up to the list budget
-        size_t s1 = s0;
-        uint64_t bytes = 0;
-        while (s1 < cs.segs.size() && (s1 == s0 || bytes + cs.segs[s1].n_bytes <= kMaxListKmers)) {
-            if (cs.segs[s1].codes) bytes += cs.segs[s1].n_bytes;
-            s1++;
-        }
-        if (!bytes) {
-            s0 = s1;
-            continue;
-        }
-        // (the list is ordered by the top hash bits, so it stays region-ordered even if the table grows)
-        int32_t rc;
-        BucketFn fn;
-        fn.n_ranks = c->n_ranks;  // (k-mers of other owners, if any, simply form their own buckets)
-        fn.log2_regions = partition_log2_buckets(c);
-        // `bytes` bounds the number of k-mers of the group, so the list can be sized and the insert
-        // queued without waiting for the exact count (it stays on the device, offsets[n_buckets]).
-        rc = ensure_list(c, bytes);
-        if (rc) return rc;
-        uint64_t granted = 0;
-        rc = reserve_headroom(c, bytes, &granted);
-        if (rc) return rc;
-        fn.log2_regions = partition_log2_buckets(c);  // reserve_headroom may have grown the table
-        const uint32_t nb2 = c->n_ranks << fn.log2_regions;
-        if (granted >= bytes) {
-            rc = bucket_count(c, chunk, s0, s1, fn, nb2, nullptr, nullptr);
-            if (rc) return rc;
-            rc = bucket_scatter(c, chunk, s0, s1, fn, nb2, c->d_list);
-            if (rc) return rc;
-            rc = insert_list(c, c->d_list, nullptr, bytes, c->d_bucket_offsets + nb2);
-            if (rc) return rc;
-        } else {
-            // close to the load limit: get the exact count and let insert_list tile / grow
-            uint64_t total = 0;
-            rc = bucket_count(c, chunk, s0, s1, fn, nb2, &total, nullptr);
-            if (rc) return rc;
-            rc = bucket_scatter(c, chunk, s0, s1, fn, nb2, c->d_list);
-            if (rc) return rc;
-            rc = insert_list(c, c->d_list, nullptr, total);
-            if (rc) return rc;
-        }
-        s0 = s1;
-    }
-    return SKM_OK;
-}
-
 // One streaming pass over the table: histogram + totals (+ digest).  Synchronous.
 int32_t scan_table(skm_ctx *c, bool want_digest, std::vector<uint64_t> *bins_out) {
     const uint64_t nb = c->p.histo_max + 2;
+    {
+        int32_t rc0 = ensure_physical(c);
+        if (rc0) return rc0;
+    }
     zero_async(c, c->d_bins, nb * sizeof(uint64_t), c->stream);
     zero_async(c, c->d_tot, sizeof(HistoTotals), c->stream);
     const uint32_t n_smem_bins = (uint32_t)std::min<uint64_t>(nb, 12288);
@@ -778,6 +791,10 @@ int32_t check_sticky(skm_ctx *c) {
     // requires stream sync done by the caller
     GlobalCounters gc;
     CU(cudaMemcpy(&gc, c->d_gc, sizeof gc, cudaMemcpyDeviceToHost));
+    if (gc.part_full) {
+        c->sticky_error = true;
+        return fail(c, SKM_ERR_CAPACITY, "a table partition (%u slots) filled up: keys were dropped; raise capacity_hint", kPartSlots);
+    }
     if (gc.first_bad != ~0ull) {
         c->sticky_error = true;
         const unsigned ch = (unsigned)(gc.first_bad & 0xFF);
@@ -820,12 +837,320 @@ uint64_t *alloc_offsets(skm_ctx *c, uint32_t n) {
     return p;
 }
 
+bool want_partitioned_cap(const skm_ctx *c, uint64_t n_bytes, uint64_t capacity) {
+    if (c->p.insert_mode == SKM_INSERT_DIRECT) return false;
+    if (c->p.insert_mode == SKM_INSERT_PARTITIONED) return true;
+    return capacity * sizeof(Slot) >= (96ull << 20) && n_bytes >= (1ull << 23);
+}
+
 bool want_partitioned(const skm_ctx *c, uint64_t n_bytes) {
     if (c->p.insert_mode == SKM_INSERT_DIRECT) return false;
     if (c->p.insert_mode == SKM_INSERT_PARTITIONED) return true;
     // AUTO: partitioned wins once the table no longer fits in L2 and there is enough work to
     // amortise the two bucketing passes (measured crossover); else direct.
     return c->capacity * sizeof(Slot) >= (96ull << 20) && n_bytes >= (1ull << 23);
+}
+
+void release_list(skm_ctx *c, Segment &sg, cudaStream_t st) {
+    if (sg.list) {
+        cudaFreeAsync(sg.list, st);
+        c->list_bytes -= std::min<size_t>(c->list_bytes, sg.list_cells * sizeof(uint64_t));
+    }
+    if (sg.meta) cudaFreeAsync(sg.meta, st);
+    if (sg.tile_off) {
+        cudaFreeAsync(sg.tile_off, st);
+        c->list_bytes -= std::min<size_t>(c->list_bytes, (size_t)sg.max_tiles * ((1u << c->g2) + 1) * sizeof(uint16_t));
+    }
+    if (sg.d_counts) cudaFreeAsync(sg.d_counts, st);
+    sg.list = nullptr;
+    sg.meta = nullptr;
+    sg.tile_off = nullptr;
+    sg.d_counts = nullptr;
+    sg.tiled = false;
+    sg.cap = 0;
+}
+
+ListGeom list_geom(const skm_ctx *c) { return ListGeom{c->n_ranks, route_log2_regions(c), c->g2}; }
+
+// Passes A and B for one packed segment, on c->work: bucket its k-mers by (owner, table region)
+// into a list — capped one-pass layout, or exact two-pass layout — then sort every tile of every
+// bucket by sub-bucket in place (tile_sort_kernel).  `must`: fail instead of skipping when memory
+// is short.  Leaves sg.list == nullptr when skipped.
+int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off, bool exact, bool must) {
+    Segment &sg = c->chunks[chunk].segs[seg_index];
+    const BucketFn fn = route_fn(c);
+    const uint32_t nb = c->n_ranks << fn.log2_regions;
+    const uint32_t F = 1u << c->g2;
+    CapLayout lay{};
+    size_t cells;
+    uint32_t tpb = 0, max_tiles;
+    if (!exact) {
+        lay.cap = ((sg.n_bytes / nb + sg.n_bytes / (16ull * nb) + 1024) + 15) & ~15ull;
+        lay.ovf_base = lay.cap * nb;
+        lay.ovf_cap = 4096;  // any k-mer that lands here sends the segment to the exact path
+        cells = (size_t)(lay.ovf_base + lay.ovf_cap);
+        tpb = (uint32_t)((lay.cap + kTile - 1) / kTile);
+        max_tiles = nb * tpb;
+    } else {
+        cells = sg.n_bytes;
+        max_tiles = (uint32_t)(sg.n_bytes / kTile) + nb + 1;
+    }
+    const size_t off_bytes = (size_t)max_tiles * (F + 1) * sizeof(uint16_t);
+    const size_t need = cells * 8 + off_bytes;
+    if (!must && c->list_bytes + need + 3 * c->capacity * sizeof(Slot) + (4ull << 30) > c->mem_budget) return SKM_OK;
+    CU(cudaStreamWaitEvent(c->work, sg.ready, 0));
+    unsigned long long *list = nullptr, *meta = nullptr;
+    uint16_t *tile_off = nullptr;
+    if (cudaMallocAsync((void **)&list, cells * sizeof(uint64_t), c->work) != cudaSuccess ||
+        cudaMallocAsync((void **)&tile_off, off_bytes, c->work) != cudaSuccess ||
+        cudaMallocAsync((void **)&meta, list_meta_words(nb) * sizeof(uint64_t), c->work) != cudaSuccess) {
+        cudaGetLastError();
+        if (list) cudaFreeAsync(list, c->work);
+        if (tile_off) cudaFreeAsync(tile_off, c->work);
+        return must ? fail(c, SKM_ERR_OOM, "device allocation failed (k-mer list of %llu cells)", (unsigned long long)cells) : SKM_OK;
+    }
+    sg.list = list;
+    sg.meta = meta;
+    sg.tile_off = tile_off;
+    sg.max_tiles = max_tiles;
+    sg.n_buckets = nb;
+    sg.h_offsets = h_off;
+    sg.list_cells = cells;
+    c->list_bytes += need;
+    const ListMeta m = list_meta_at(meta, nb);
+    int32_t rc;
+    if (!exact) {
+        rc = bucket_scatter_capped(c, chunk, sg, fn, nb, sg.list, lay);
+        if (rc) return rc;
+        copy_words_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_cursors, (unsigned long long *)h_off, nb + 1);
+        tile_plan_kernel<<<1, 1024, 0, c->work>>>(c->d_bucket_cursors, nb, lay.cap, tpb, m);
+        c->launches += 2;
+        sg.cap = lay.cap;
+        sg.ovf_cap = 0;  // capped lists have no usable overflow run: h_offsets[nb] > 0 => rebuild exactly
+    } else {
+        rc = bucket_count(c, chunk, seg_index, seg_index + 1, fn, nb, nullptr, nullptr);
+        if (rc) return rc;
+        rc = bucket_scatter(c, chunk, seg_index, seg_index + 1, fn, nb, sg.list);
+        if (rc) return rc;
+        copy_words_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_offsets, (unsigned long long *)h_off, nb + 1);
+        tile_plan_kernel<<<1, 1024, 0, c->work>>>(c->d_bucket_offsets, nb, 0ull, 0u, m);
+        c->launches += 2;
+        sg.cap = 0;
+        CU(cudaFreeAsync(sg.codes, c->work));
+        CU(cudaFreeAsync(sg.breaks, c->work));
+        sg.codes = nullptr;
+        sg.breaks = nullptr;
+    }
+    {
+        Span sp(c, ST_SORT, c->work);
+        tile_sort_kernel<<<max_tiles, kSortThreads, tile_sort_smem_bytes(c->g2), c->work>>>(sg.list, m, nb, list_geom(c), sg.tile_off);
+        c->launches++;
+        c->stage_launches[ST_SORT]++;
+    }
+    CU(cudaGetLastError());
+    sg.tiled = true;
+    CU(cudaEventRecord(sg.ready, c->work));  // `ready` now also covers the list, the tile offsets and the totals
+    return SKM_OK;
+}
+
+// ---- tiled insert ---------------------------------------------------------------------------------
+struct TiledSeg {
+    const Segment *sg;
+    uint32_t chunk;   // relative to the launch's first chunk
+};
+
+uint32_t tiled_k_low(const skm_ctx *c, uint32_t n_chunks_l, bool histo) {
+    // as many low bins in shared memory as fit beside the partition with 3 CTAs per SM
+    uint32_t k = 1024;
+    while (k > 16 && tile_insert_smem_bytes(n_chunks_l, k, histo) > 74 * 1024) k >>= 1;
+    const uint64_t want = c->p.histo_max + 2;   // no point in more bins than the histogram has
+    while (k > 16 && (k >> 1) >= want) k >>= 1;
+    return k;
+}
+constexpr uint32_t kMaxChunksPerLaunch = 64;
+
+int32_t ensure_tiled_buffers(skm_ctx *c, uint32_t n_chunks_l, size_t seg_bytes) {
+    const size_t nbins = c->p.histo_max + 2;
+    if (c->delta_words < (size_t)n_chunks_l * nbins) {
+        if (c->d_delta) CU(cudaFreeAsync(c->d_delta, c->stream));
+        c->d_delta = nullptr;
+        CU(cudaMallocAsync((void **)&c->d_delta, (size_t)n_chunks_l * nbins * sizeof(uint64_t), c->stream));
+        c->delta_words = (size_t)n_chunks_l * nbins;
+    }
+    if (!c->d_recount) CU(cudaMalloc((void **)&c->d_recount, nbins * sizeof(uint64_t)));
+    if (!c->d_fail) CU(cudaMalloc((void **)&c->d_fail, (size_t)skm_ctx::kFailCap * sizeof(uint32_t)));
+    if (c->segs_bytes < seg_bytes) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->h_segs) CU(cudaFreeHost(c->h_segs));
+        if (c->d_segs) CU(cudaFree(c->d_segs));
+        c->h_segs = c->d_segs = nullptr;
+        const size_t cap = std::max<size_t>(seg_bytes * 2, 64 * 1024);
+        CU(cudaMallocHost(&c->h_segs, cap));
+        CU(cudaMalloc(&c->d_segs, cap));
+        c->segs_bytes = cap;
+    }
+    return SKM_OK;
+}
+
+// One launch (plus retries after growth) of tile_insert_kernel over the given lists, which hold
+// chunks [chunk0, chunk0 + n_chunks_l) in chunk order.  Histogram columns of those chunks are
+// produced when the ctx tracks the histogram.  Synchronises the main stream.
+int32_t launch_tiled(skm_ctx *c, const std::vector<TiledSeg> &segs, uint32_t chunk0, uint32_t n_chunks_l) {
+    const bool histo = c->track_histo;
+    const size_t nbins = c->p.histo_max + 2;
+    const uint32_t n = (uint32_t)segs.size();
+    const size_t seg_bytes = (size_t)n * sizeof(SegDesc) + ((size_t)n_chunks_l + 2) * sizeof(uint32_t) + 16;
+    int32_t rc = ensure_tiled_buffers(c, n_chunks_l, seg_bytes);
+    if (rc) return rc;
+    // descriptors -> pinned -> device (by a kernel: never behind the read batches on a copy engine)
+    SegDesc *hd = (SegDesc *)c->h_segs;
+    uint32_t *hfirst = (uint32_t *)(hd + n);
+    const ListGeom geom = list_geom(c);
+    uint32_t at = 0;
+    for (uint32_t ch = 0; ch <= n_chunks_l; ch++) {
+        while (at < n && segs[at].chunk < ch) at++;
+        hfirst[ch] = at;
+    }
+    hfirst[n_chunks_l] = n;
+    for (uint32_t i = 0; i < n; i++) {
+        const Segment &sg = *segs[i].sg;
+        const ListMeta m = list_meta_at(sg.meta, sg.n_buckets);
+        hd[i] = SegDesc{sg.list, sg.tile_off, m.tile_begin, m.cell_begin, c->p.rank << geom.g1, segs[i].chunk};
+    }
+    {
+        unsigned long long *h_dev = nullptr;
+        CU(cudaHostGetDevicePointer((void **)&h_dev, c->h_segs, 0));
+        const uint32_t words = (uint32_t)((seg_bytes + 7) / 8);
+        copy_words_kernel<<<8, 256, 0, c->stream>>>(h_dev, (unsigned long long *)c->d_segs, words);
+        c->launches++;
+    }
+    InsertLaunch L{};
+    L.n_ranks = c->n_ranks;
+    L.g1 = geom.g1;
+    L.g2 = geom.g2;
+    L.segs = (const SegDesc *)c->d_segs;
+    L.chunk_first_seg = (const uint32_t *)((const SegDesc *)c->d_segs + n);
+    L.n_segs = n;
+    L.n_chunks = n_chunks_l;
+    L.k_low = tiled_k_low(c, n_chunks_l, histo);
+    L.max_occupied = (uint32_t)(kHardLoad * kPartSlots);
+    L.g_delta = c->d_delta;
+    L.g_recount = c->d_recount;
+    L.histo_max = c->p.histo_max;
+    L.gc = c->d_gc;
+    L.tot = c->d_tot;
+    L.part_counter = &c->d_gc->scratch[0];
+    L.fail_list = c->d_fail;
+    L.fail_cap = skm_ctx::kFailCap;
+    const size_t smem = tile_insert_smem_bytes(n_chunks_l, L.k_low, histo);
+    if (histo) zero_async(c, c->d_delta, (size_t)n_chunks_l * nbins * sizeof(uint64_t), c->stream);
+    zero_async(c, c->d_recount, nbins * sizeof(uint64_t), c->stream);
+    zero_async(c, c->d_tot, sizeof(HistoTotals), c->stream);
+    std::vector<uint32_t> part_ids;  // empty: all partitions
+    for (uint32_t attempt = 0;; attempt++) {
+        L.table = c->table;
+        L.log2cap = c->log2cap;
+        L.fresh = c->table_fresh ? 1 : 0;
+        const uint64_t n_parts_all = c->capacity >> kPartLog2;
+        if (part_ids.empty()) {
+            L.part_ids = nullptr;
+            L.n_parts = n_parts_all;
+        } else {
+            if (c->d_part_ids) CU(cudaFreeAsync(c->d_part_ids, c->stream));
+            CU(cudaMallocAsync((void **)&c->d_part_ids, part_ids.size() * sizeof(uint32_t), c->stream));
+            CU(cudaMemcpyAsync(c->d_part_ids, part_ids.data(), part_ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+            L.part_ids = c->d_part_ids;
+            L.n_parts = part_ids.size();
+        }
+        // how many (list, bucket) pairs one partition reads: the kernel stages them in shared memory
+        const uint32_t pbits = c->log2cap - kPartLog2;
+        const uint64_t nbr = pbits >= geom.g1 ? 1ull : (1ull << (geom.g1 - pbits));
+        if ((uint64_t)n * nbr > kMaxVseg)
+            return fail(c, SKM_ERR_STATE, "internal: %u lists x %llu buckets per partition exceed one launch", n, (unsigned long long)nbr);
+        zero_async(c, L.part_counter, sizeof(unsigned long long), c->stream);
+        zero_async(c, &c->d_gc->n_failed, 2 * sizeof(unsigned long long), c->stream);  // n_failed, fatal
+        int occ = 0;
+        if (histo) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_insert_kernel<true>, kInsThreads, smem));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_insert_kernel<false>, kInsThreads, smem));
+        const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(L.n_parts, (uint64_t)c->sm_count * std::max(occ, 1)));
+        if (getenv("SKM_DEBUG"))
+            std::fprintf(stderr, "[skm] tile_insert: grid %u (occ %d) smem %zu k_low %u chunks %u lists %u parts %llu g1 %u g2 %u log2cap %u fresh %d attempt %u\n",
+                         grid, occ, smem, L.k_low, n_chunks_l, n, (unsigned long long)L.n_parts, L.g1, L.g2, L.log2cap, L.fresh, attempt);
+        {
+            Span sp(c, ST_INSERT, c->stream);
+            if (histo) tile_insert_kernel<true><<<grid, kInsThreads, smem, c->stream>>>(L);
+            else tile_insert_kernel<false><<<grid, kInsThreads, smem, c->stream>>>(L);
+            c->launches++;
+            c->stage_launches[ST_INSERT]++;
+            c->n_tiled_launches++;
+        }
+        CU(cudaGetLastError());
+        const bool was_fresh = c->table_fresh;
+        c->table_fresh = false;
+        c->table_zombie = false;  // every partition was written (failed ones: written empty)
+        GlobalCounters *hgc = (GlobalCounters *)c->h_pinned;
+        CU(cudaMemcpyAsync(hgc, c->d_gc, sizeof(GlobalCounters), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->distinct_ub = hgc->n_distinct;
+        for (auto &pnd : c->snap_pending) pnd = false;
+        const uint64_t n_failed = hgc->n_failed;
+        if (n_failed == 0) break;
+        if (hgc->fatal)
+            return fail(c, SKM_ERR_CAPACITY,
+                        "a table partition filled up after publishing histogram moves (capacity_hint %llu far too small for this input)",
+                        (unsigned long long)c->p.capacity_hint);
+        if (attempt >= 24) return fail(c, SKM_ERR_CAPACITY, "table growth did not converge");
+        // grow (the partitions that succeeded keep their keys: rehash), then retry the children of the failed ones
+        std::vector<uint32_t> failed(std::min<uint64_t>(n_failed, skm_ctx::kFailCap));
+        const bool all = n_failed > skm_ctx::kFailCap;
+        if (!all) CU(cudaMemcpy(failed.data(), c->d_fail, failed.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        // size the new table from what was seen: failed partitions hold > 0.9 * kPartSlots keys each
+        uint32_t nl = c->log2cap + 1;
+        if (n_failed * 2 > n_parts_all && was_fresh) nl = c->log2cap + 2;
+        {
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            if (((size_t)sizeof(Slot) << nl) + (1ull << 30) > free_b) nl = c->log2cap + 1;
+            if (((size_t)sizeof(Slot) << nl) + (1ull << 30) > free_b)
+                return fail(c, SKM_ERR_CAPACITY, "out of device memory growing the table to 2^%u slots", nl);
+        }
+        const uint32_t shift = nl - c->log2cap;
+        rc = grow_table(c, nl);
+        if (rc) return rc;
+        c->n_tiled_retries++;
+        std::vector<uint32_t> next;
+        if (all) {
+            // too many to list: every partition that is still empty of this launch's k-mers is unknown
+            return fail(c, SKM_ERR_CAPACITY, "more than %u table partitions overflowed; raise capacity_hint", skm_ctx::kFailCap);
+        }
+        next.reserve(failed.size() << shift);
+        for (uint32_t q : failed)
+            for (uint32_t j = 0; j < (1u << shift); j++) next.push_back((q << shift) | j);
+        part_ids.swap(next);
+    }
+    if (c->d_part_ids) {
+        CU(cudaFreeAsync(c->d_part_ids, c->stream));
+        c->d_part_ids = nullptr;
+    }
+    if (histo) {
+        // columns of chunks chunk0 .. chunk0 + n_chunks_l - 1 (in place over the moves), running histogram updated
+        hist_columns_kernel<<<std::min<uint32_t>(grid_for(nbins, 256), 1024), 256, 0, c->stream>>>(c->d_delta, n_chunks_l, nbins, c->d_hist, c->d_delta);
+        c->launches++;
+        CU(cudaGetLastError());
+        for (uint32_t i = 0; i < n_chunks_l; i++) {
+            const uint32_t ch = chunk0 + i;
+            if (c->h_cols) {
+                CU(cudaMemcpyAsync(c->h_cols + (size_t)ch * nbins, c->d_delta + (size_t)i * nbins, nbins * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+                c->col_pending[ch] = true;
+            } else {
+                c->histos[ch].assign(nbins, 0);
+                CU(cudaMemcpyAsync(c->histos[ch].data(), c->d_delta + (size_t)i * nbins, nbins * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+            }
+            c->have_histo[ch] = true;
+        }
+    }
+    c->recount_valid = true;
+    return SKM_OK;
 }
 
 // Bucket a freshly packed segment by table region right away (single GPU).  The work is queued
@@ -847,33 +1172,10 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force
     const uint32_t nb = c->n_ranks << fn.log2_regions;
     uint64_t *h_off = alloc_offsets(c, nb + 1);
     if (!h_off) return force ? fail(c, SKM_ERR_OOM, "pinned allocation failed") : SKM_OK;
-    if (c->n_ranks == 1 && c->capped && !force && sg.n_bytes < (3ull << 30)) {
-        // single GPU: one pass, no counting (the routing of the multi-GPU paths needs exact,
-        // contiguous per-owner blocks and keeps the two-pass version below)
-        CapLayout lay;
-        lay.cap = ((sg.n_bytes / nb + sg.n_bytes / (16ull * nb) + 1024) + 15) & ~15ull;
-        lay.ovf_base = lay.cap * nb;
-        lay.ovf_cap = sg.n_bytes / 8 + 4096;
-        const size_t cells = (size_t)(lay.ovf_base + lay.ovf_cap);
-        if (c->list_bytes + cells * 8 + 3 * c->capacity * sizeof(Slot) + (4ull << 30) > c->mem_budget) return SKM_OK;
-        CU(cudaStreamWaitEvent(c->work, sg.ready, 0));
-        if (cudaMallocAsync((void **)&sg.list, cells * sizeof(uint64_t), c->work) != cudaSuccess) {
-            cudaGetLastError();
-            sg.list = nullptr;
-            return SKM_OK;
-        }
-        int32_t rc = bucket_scatter_capped(c, chunk, sg, fn, nb, sg.list, lay);
-        if (rc) return rc;
-        copy_words_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_cursors, (unsigned long long *)h_off, nb + 1);
-        c->launches++;
-        sg.h_offsets = h_off;
-        sg.n_buckets = nb;
-        sg.cap = lay.cap;
-        sg.ovf_cap = lay.ovf_cap;
-        sg.list_cells = cells;
-        c->list_bytes += cells * 8;
-        CU(cudaEventRecord(sg.ready, c->work));  // `ready` now also covers the list + totals
-        return SKM_OK;
+    if (c->n_ranks == 1) {
+        // single GPU: bucket by table region and tile-sort the buckets (tiled insert).  One pass
+        // (capped layout) unless the caller needs the exact layout: `force` = a capped list overflowed.
+        return build_list(c, chunk, seg_index, h_off, /*exact=*/force || !c->capped || sg.n_bytes >= (3ull << 30), force);
     }
     // the pack kernel ran on another stream (the copy stream): order the bucketing after it.  Only
     // here — a wait queued for a batch that is NOT bucketed now would make everything later on this
@@ -942,6 +1244,70 @@ int32_t check_ingest_args(skm_ctx *c, uint32_t chunk, const void *p, uint64_t n)
     if (c->finalized) return fail(c, SKM_ERR_STATE, "ingest after finalize");
     if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index %u out of range (n_chunks %u)", chunk, c->n_chunks);
     if (n && !p) return fail(c, SKM_ERR_INVALID_ARG, "null buffer");
+    return SKM_OK;
+}
+
+// Ascending-key order for exported (k-mer, count) pairs: a device radix sort over the 2k significant
+// bits (CUB, a library call: presentation order of the read side, not the counting path).
+int32_t sort_pairs_device(skm_ctx *c, unsigned long long *d_keys, uint32_t *d_counts, uint64_t n) {
+    if (n < 2) return SKM_OK;
+    if (n > (uint64_t)INT32_MAX * 2) return fail(c, SKM_ERR_INVALID_ARG, "sorted export limited to 2^32 entries per call");
+    unsigned long long *k2 = nullptr;
+    uint32_t *c2 = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const int end_bit = std::min<int>(64, 2 * (int)c->p.k);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, k2, d_counts, c2, n, 0, end_bit, c->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&k2, n * sizeof(uint64_t), c->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&c2, n * sizeof(uint32_t), c->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 1), c->stream);
+    if (e == cudaSuccess)
+        e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d_keys, k2, d_counts, c2, n, 0, end_bit, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_keys, k2, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_counts, c2, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream);
+    if (k2) cudaFreeAsync(k2, c->stream);
+    if (c2) cudaFreeAsync(c2, c->stream);
+    if (tmp) cudaFreeAsync(tmp, c->stream);
+    c->launches += 4;
+    if (e != cudaSuccess)
+        return fail(c, e == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA, "device sort failed: %s", cudaGetErrorString(e));
+    return SKM_OK;
+}
+
+// A private stream for one read-side call (returned to the pool by the caller); call with c->mu held.
+cudaStream_t take_read_stream(skm_ctx *c) {
+    if (!c->read_streams.empty()) {
+        cudaStream_t s = c->read_streams.back();
+        c->read_streams.pop_back();
+        return s;
+    }
+    cudaStream_t s = nullptr;
+    cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    return s;
+}
+
+// Stream-ordered temporary: freed on every exit path (the CU() macro returns early on errors).
+template <class T>
+struct DevTmp {
+    T *p = nullptr;
+    cudaStream_t st;
+    explicit DevTmp(cudaStream_t s) : st(s) {}
+    DevTmp(const DevTmp &) = delete;
+    DevTmp &operator=(const DevTmp &) = delete;
+    ~DevTmp() {
+        if (p) cudaFreeAsync(p, st);
+    }
+    cudaError_t alloc(size_t n) { return cudaMallocAsync((void **)&p, std::max<size_t>(n, 1) * sizeof(T), st); }
+};
+
+// The read side (lookups, scans, export, totals of the table) describes the COUNTED table: batches
+// that were ingested but not yet counted (inserts are deferred to skm_finalize) would silently be
+// missing from the answer, so those calls fail instead.
+int32_t check_counted(skm_ctx *c, const char *what) {
+    if (c->finalized) return SKM_OK;
+    for (auto &cs : c->chunks)
+        if (!cs.segs.empty())
+            return fail(c, SKM_ERR_STATE, "%s before skm_finalize: ingested batches are not counted yet", what);
     return SKM_OK;
 }
 
@@ -1074,6 +1440,19 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     if (rc) return rc;
     c->log2cap = l2;
     c->capacity = 1ull << l2;
+    // sub-bucket bits of the k-mer lists: with a capacity_hint, exactly as fine as the table's
+    // partitions (one sub-bucket per partition); without one, 2^7 sub-buckets per region — a
+    // partition then covers several adjacent sub-buckets, or filters a shared one
+    {
+        const int g1 = (int)route_log2_regions(c);
+        int g2 = c->p.capacity_hint ? (int)l2 - (int)kPartLog2 - g1 : 7;
+        if (const char *g = getenv("SKM_G2")) g2 = atoi(g);
+        c->g2 = (uint32_t)std::max(0, std::min<int>(g2, (int)kMaxSubLog2));
+    }
+    CU(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)tile_sort_smem_bytes(kMaxSubLog2)));
+    CU(cudaFuncSetAttribute(tile_insert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(tile_insert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaStreamSynchronize(c->stream));
     return SKM_OK;
 }
@@ -1091,7 +1470,15 @@ void skm_destroy(skm_ctx *c) {
                 cudaFree(sg.breaks);
                 cudaFree(sg.list);
                 cudaFree(sg.d_counts);
+                cudaFree(sg.meta);
+                cudaFree(sg.tile_off);
             }
+        cudaFree(c->d_delta);
+        cudaFree(c->d_recount);
+        cudaFree(c->d_fail);
+        cudaFree(c->d_part_ids);
+        cudaFree(c->d_segs);
+        cudaFreeHost(c->h_segs);
         cudaFree(c->table);
         cudaFree(c->d_cc);
         cudaFree(c->d_gc);
@@ -1129,6 +1516,7 @@ void skm_destroy(skm_ctx *c) {
             cudaEventDestroy(t.b);
         }
         for (auto e : c->event_pool) cudaEventDestroy(e);
+        for (auto rs : c->read_streams) cudaStreamDestroy(rs);
         if (c->own_stream) cudaStreamDestroy(c->stream);
         cudaStreamDestroy(c->copy_stream);
         cudaStreamDestroy(c->part_stream);
@@ -1243,27 +1631,32 @@ int32_t skm_ingest_reads(skm_ctx *c, uint32_t chunk, const uint8_t *bases, const
         if (offsets[i + 1] < offsets[i]) return fail(c, SKM_ERR_INVALID_ARG, "offsets must be non-decreasing");
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
+    // Everything runs on the routing stream, like skm_ingest_batch / skm_ingest_device: the bucketing
+    // scratch (d_bucket_counts / offsets / cursors) belongs to that stream, so mixing the three entry
+    // points in one run cannot race on it.
+    cudaStream_t st = c->part_stream;
+    WorkStream ws(c, st);
     uint8_t *d_bases = nullptr, *d_lines = nullptr;
     uint64_t *d_off = nullptr;
     const uint64_t n_out = offsets[n_reads] + n_reads;  // dst offset of read r = offsets[r] + r
-    CU(cudaMallocAsync((void **)&d_bases, offsets[n_reads] + 1, c->stream));
-    CU(cudaMallocAsync((void **)&d_off, (n_reads + 1) * sizeof(uint64_t), c->stream));
-    CU(cudaMallocAsync((void **)&d_lines, n_out, c->stream));
+    CU(cudaMallocAsync((void **)&d_bases, offsets[n_reads] + 1, st));
+    CU(cudaMallocAsync((void **)&d_off, (n_reads + 1) * sizeof(uint64_t), st));
+    CU(cudaMallocAsync((void **)&d_lines, n_out, st));
     {
-        Span sp(c, ST_H2D, c->stream);
+        Span sp(c, ST_H2D, st);
         if (offsets[n_reads])
-            CU(cudaMemcpyAsync(d_bases, bases, offsets[n_reads], cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(d_off, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(d_bases, bases, offsets[n_reads], cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_off, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     }
-    CU(cudaStreamSynchronize(c->stream));
-    add_separators_kernel<<<grid_for(n_reads * 32, 256), 256, 0, c->stream>>>(d_bases, d_off, n_reads, d_lines);
+    CU(cudaStreamSynchronize(st));  // the caller's (pageable) buffers may be reused on return
+    add_separators_kernel<<<grid_for(n_reads * 32, 256), 256, 0, st>>>(d_bases, d_off, n_reads, d_lines);
     c->launches++;
     CU(cudaGetLastError());
     // bytes before offsets[0] are not part of any read: skip them
     rc = stage_device(c, chunk, d_lines + offsets[0], n_out - offsets[0]);
-    CU(cudaFreeAsync(d_bases, c->stream));
-    CU(cudaFreeAsync(d_off, c->stream));
-    CU(cudaFreeAsync(d_lines, c->stream));
+    CU(cudaFreeAsync(d_bases, st));
+    CU(cudaFreeAsync(d_off, st));
+    CU(cudaFreeAsync(d_lines, st));
     return rc;
 }
 
@@ -1320,96 +1713,185 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
 
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     cudaEventRecord(e0, c->stream);
-    for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
-        ChunkState &cs = c->chunks[ch];
-        // (1) segments bucketed at ingest time: one launch walks their runs region by region
-        {
-            uint32_t nb = 0;
-            for (auto &sg : cs.segs)
-                if (sg.list) nb = sg.n_buckets;
-            for (auto &sg : cs.segs) {
-                if (!sg.ready) continue;
-                if (sg.list) CU(cudaEventSynchronize(sg.ready));   // host needs the bucket offsets
-                else CU(cudaStreamWaitEvent(c->stream, sg.ready, 0));  // packed data is consumed on the main stream
-            }
-            for (auto &sg : cs.segs) {
-                if (!sg.list || !sg.cap) continue;
-                if (sg.h_offsets[sg.n_buckets] > sg.ovf_cap) {
-                    // capped layout overflowed even its overflow run (heavily repeated k-mers): drop
-                    // the list and let (2) below bucket the segment exactly (its packed form is still here)
-                    rc = drop_capped_list(c, ch, sg, c->stream);
-                    if (rc) return rc;
-                    c->n_capped_fallbacks++;
-                } else {  // the packed form is no longer needed
-                    CU(cudaFreeAsync(sg.codes, c->stream));
-                    CU(cudaFreeAsync(sg.breaks, c->stream));
-                    sg.codes = nullptr;
-                    sg.breaks = nullptr;
-                }
-            }
-            if (nb) {
-                std::vector<RunDesc> runs;
-                for (uint32_t r = 0; r < nb; r++)
-                    for (auto &sg : cs.segs) {
-                        if (!sg.list) continue;
-                        if (r >= sg.n_buckets) continue;
-                        if (sg.cap) {
-                            const uint64_t n = std::min<uint64_t>(sg.h_offsets[r], sg.cap);
-                            if (n) runs.push_back(RunDesc{sg.list + r * sg.cap, nullptr, n, 0});
-                        } else if (sg.h_offsets[r + 1] > sg.h_offsets[r]) {
-                            runs.push_back(RunDesc{sg.list + sg.h_offsets[r], nullptr,
-                                                   sg.h_offsets[r + 1] - sg.h_offsets[r], 0});
-                        }
-                    }
-                for (auto &sg : cs.segs)  // overflow runs: any region, inserted last
-                    if (sg.list && sg.cap && sg.h_offsets[sg.n_buckets])
-                        runs.push_back(RunDesc{sg.list + (uint64_t)sg.n_buckets * sg.cap, nullptr,
-                                               sg.h_offsets[sg.n_buckets], 0});
-                if (!runs.empty()) {
-                    rc = insert_runs(c, runs);
-                    if (rc) return rc;
-                }
-            }
-        }
-        // (2) segments still packed: bucket now (partitioned) or extract+insert directly
-        uint64_t packed_bytes = 0;
-        for (auto &sg : cs.segs)
-            if (sg.codes) packed_bytes += sg.n_bytes;
-        if (packed_bytes && want_partitioned(c, packed_bytes)) {
-            CU(cudaStreamSynchronize(c->part_stream));  // the bucketing scratch is shared with the ingest path
-            rc = insert_chunk_partitioned(c, ch);
-            if (rc) return rc;
-        } else if (packed_bytes) {
-            for (auto &sg : cs.segs) {
-                if (!sg.codes) continue;
-                rc = insert_segment_direct(c, sg, ch);
+    c->recount_valid = false;
+    // A fresh table is sized once, for the whole input: the tiled insert counts all chunks in one
+    // launch and cannot grow in the middle of it without a retry.  With a capacity_hint the table
+    // already has its size; without one, the number of ingested positions bounds the distinct k-mers.
+    if (c->table_fresh && c->n_ranks == 1) {
+        uint64_t positions = 0;
+        for (auto &cs : c->chunks) positions += cs.n_bytes;
+        uint64_t bound = positions;
+        if (c->p.k < 31) bound = std::min<uint64_t>(bound, (1ull << (2 * c->p.k)) / 2 + (1ull << c->p.k));  // canonical k-mers
+        if (want_partitioned(c, positions) || c->capacity * sizeof(Slot) < (96ull << 20)) {
+            uint32_t want = c->log2cap;
+            if (!c->p.capacity_hint) want = std::max(want, ceil_log2((uint64_t)((double)bound / kTargetLoad) + 1));
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            while (want > c->log2cap && ((size_t)sizeof(Slot) << want) > (free_b + c->capacity * sizeof(Slot)) / 2) want--;
+            if (want > c->log2cap && want_partitioned_cap(c, positions, 1ull << want)) {
+                rc = grow_table(c, want);
                 if (rc) return rc;
             }
         }
-        for (auto &sg : cs.segs) {  // drop(chunk), src/io.rs:1025
+    }
+    std::vector<TiledSeg> group;      // lists of consecutive chunks, to be counted by one tiled launch
+    uint32_t group_chunk0 = 0;
+    auto flush_group = [&](uint32_t end_chunk) -> int32_t {
+        if (group.empty()) {
+            group_chunk0 = end_chunk;
+            return SKM_OK;
+        }
+        const uint32_t n_l = end_chunk - group_chunk0;
+        int32_t r = launch_tiled(c, group, group_chunk0, n_l);
+        if (r) return r;
+        for (auto &ts : group) {
+            Segment &sg = *const_cast<Segment *>(ts.sg);
+            uint64_t nk = 0;
+            if (sg.cap) for (uint32_t b = 0; b < sg.n_buckets; b++) nk += sg.h_offsets[b];
+            else nk = sg.h_offsets[sg.n_buckets];
+            c->insert_kmers += nk;
+            release_list(c, sg, c->stream);
+        }
+        group.clear();
+        group_chunk0 = end_chunk;
+        return SKM_OK;
+    };
+    const uint32_t pbits_now = c->log2cap - kPartLog2, g1_now = route_log2_regions(c);
+    const uint64_t nbr_now = pbits_now >= g1_now ? 1ull : (1ull << (g1_now - pbits_now));
+    for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
+        ChunkState &cs = c->chunks[ch];
+        for (auto &sg : cs.segs) {
+            if (!sg.ready) continue;
+            if (sg.list) CU(cudaEventSynchronize(sg.ready));      // host needs the bucket totals
+            else CU(cudaStreamWaitEvent(c->stream, sg.ready, 0));  // packed data is consumed on the main stream
+        }
+        // (1) lists built at ingest time; a capped list that overflowed (heavily repeated k-mers) is
+        //     rebuilt with the exact two-pass layout from the packed form, which was kept for this
+        for (size_t si = 0; si < cs.segs.size(); si++) {
+            Segment &sg = cs.segs[si];
+            if (!sg.list || !sg.tiled) continue;
+            if (sg.cap && sg.h_offsets[sg.n_buckets] > 0) {
+                WorkStream ws(c, c->part_stream);
+                rc = drop_capped_list(c, ch, sg, c->part_stream);
+                if (rc) return rc;
+                c->n_capped_fallbacks++;
+                uint64_t *h_off = alloc_offsets(c, sg.n_buckets + 1);
+                if (!h_off) return fail(c, SKM_ERR_OOM, "pinned allocation failed");
+                rc = build_list(c, ch, si, h_off, /*exact=*/true, /*must=*/true);
+                if (rc) return rc;
+                CU(cudaEventSynchronize(sg.ready));
+            } else if (sg.codes) {  // the packed form is no longer needed
+                CU(cudaFreeAsync(sg.codes, c->stream));
+                CU(cudaFreeAsync(sg.breaks, c->stream));
+                sg.codes = nullptr;
+                sg.breaks = nullptr;
+            }
+        }
+        // (2) segments still packed: build their lists now when the chunk is worth it and memory allows
+        uint64_t packed_bytes = 0;
+        for (auto &sg : cs.segs)
+            if (sg.codes && !sg.list) packed_bytes += sg.n_bytes;
+        if (packed_bytes && c->n_ranks == 1 && want_partitioned(c, packed_bytes)) {
+            WorkStream ws(c, c->part_stream);
+            for (size_t si = 0; si < cs.segs.size(); si++) {
+                Segment &sg = cs.segs[si];
+                if (!sg.codes || sg.list) continue;
+                for (int attempt = 0; attempt < 2 && !sg.list; attempt++) {
+                    uint64_t *h_off = alloc_offsets(c, (c->n_ranks << route_log2_regions(c)) + 1);
+                    if (!h_off) return fail(c, SKM_ERR_OOM, "pinned allocation failed");
+                    rc = build_list(c, ch, si, h_off, /*exact=*/true, /*must=*/false);
+                    if (rc) return rc;
+                    if (!sg.list && attempt == 0) {  // memory is short: count what is already listed, then retry
+                        rc = flush_group(ch);
+                        if (rc) return rc;
+                    }
+                }
+                if (sg.list) CU(cudaEventSynchronize(sg.ready));
+            }
+        }
+        // (3) this chunk's lists join the group
+        size_t n_listed = 0;
+        for (auto &sg : cs.segs) n_listed += (sg.list && sg.tiled) ? 1 : 0;
+        if ((group.size() + n_listed) * nbr_now > kMaxVseg || ch - group_chunk0 >= kMaxChunksPerLaunch) {
+            rc = flush_group(ch);
+            if (rc) return rc;
+        }
+        if (n_listed * nbr_now > kMaxVseg) {
+            // more lists in one chunk than a launch can read: count them in several launches of this
+            // chunk alone (the order inside a chunk does not matter)
+            std::vector<TiledSeg> part;
+            for (auto &sg : cs.segs) {
+                if (!(sg.list && sg.tiled)) continue;
+                part.push_back(TiledSeg{&sg, 0});
+                if ((part.size() + 1) * nbr_now > kMaxVseg) {
+                    group.swap(part);
+                    group_chunk0 = ch;
+                    // (columns of chunk ch are rewritten by every partial launch; the last one is complete)
+                    rc = flush_group(ch + 1);
+                    if (rc) return rc;
+                    part.clear();
+                }
+            }
+            group.swap(part);
+            group_chunk0 = ch;
+        } else {
+            for (auto &sg : cs.segs)
+                if (sg.list && sg.tiled) group.push_back(TiledSeg{&sg, ch - group_chunk0});
+        }
+        // (4) what is still packed goes through the direct kernel (small inputs, or no memory for a list);
+        //     a chunk's lists are counted first, so that the chunk's column is complete afterwards
+        bool direct = false;
+        for (auto &sg : cs.segs) direct = direct || (sg.codes && !sg.list);
+        if (direct) {
+            rc = flush_group(ch + 1);
+            if (rc) return rc;
+            for (auto &sg : cs.segs) {
+                if (!sg.codes || sg.list) continue;
+                rc = insert_segment_direct(c, sg, ch);
+                if (rc) return rc;
+            }
+            if (c->p.chunks > 0) {
+                rc = snapshot_histogram(c, ch);
+                if (rc) return rc;
+            }
+        } else if (group.empty() && c->p.chunks > 0) {
+            // an empty chunk between launches: its column is the running histogram
+            rc = flush_group(ch);
+            if (rc) return rc;
+            rc = snapshot_histogram(c, ch);
+            if (rc) return rc;
+            group_chunk0 = ch + 1;
+        }
+        for (auto &sg : cs.segs) {  // drop(chunk), src/io.rs:1025 (lists are released after their launch)
+            if (sg.list && sg.tiled) continue;
             if (sg.codes) CU(cudaFreeAsync(sg.codes, c->stream));
             if (sg.breaks) CU(cudaFreeAsync(sg.breaks, c->stream));
-            if (sg.list) {
-                CU(cudaFreeAsync(sg.list, c->stream));
-                c->list_bytes -= std::min<size_t>(c->list_bytes, sg.list_cells * sizeof(uint64_t));
-            }
             sg.codes = nullptr;
             sg.breaks = nullptr;
-            sg.list = nullptr;
+            release_list(c, sg, c->stream);
+        }
+        cs.counted = true;
+    }
+    rc = flush_group(c->n_chunks);
+    if (rc) return rc;
+    for (auto &cs : c->chunks)
+        for (auto &sg : cs.segs) {
             if (sg.ready) c->event_pool.push_back(sg.ready);
             sg.ready = nullptr;
         }
-        cs.counted = true;
-        if (c->p.chunks > 0) {
-            rc = snapshot_histogram(c, ch);
-            if (rc) return rc;
-        }
-    }
-    // One scan of the finished table: totals for the conservation checks and an
-    // independent recount of the final histogram.
+    // Totals for the conservation checks and an independent recount of the final histogram: the
+    // tiled insert histograms every partition as it writes it back; otherwise one scan of the table.
     std::vector<uint64_t> rescan;
-    rc = scan_table(c, false, &rescan);
-    if (rc) return rc;
+    if (c->recount_valid) {
+        rescan.assign(c->p.histo_max + 2, 0);
+        CU(cudaMemcpyAsync(rescan.data(), c->d_recount, rescan.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&c->last_tot, c->d_tot, sizeof(HistoTotals), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->have_tot = true;
+    } else {
+        rc = scan_table(c, false, &rescan);
+        if (rc) return rc;
+    }
     cudaEventRecord(e1, c->stream);
     rc = sync_all(c);
     if (rc) return rc;
@@ -1474,14 +1956,15 @@ int32_t skm_reset(skm_ctx *c) {
             if (sg.ready) c->event_pool.push_back(sg.ready);
             if (sg.codes) CU(cudaFreeAsync(sg.codes, c->stream));
             if (sg.breaks) CU(cudaFreeAsync(sg.breaks, c->stream));
-            if (sg.list) CU(cudaFreeAsync(sg.list, c->stream));
-            if (sg.d_counts) CU(cudaFreeAsync(sg.d_counts, c->stream));
+            release_list(c, sg, c->stream);
         }
         cs = ChunkState{};
     }
-    table_clear_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity);
-    c->launches++;
-    CU(cudaGetLastError());
+    // the clear is deferred (ensure_physical): a tiled insert never needs it
+    c->table_fresh = true;
+    c->table_zombie = true;
+    c->recount_valid = false;
+    c->n_tiled_launches = c->n_tiled_retries = 0;
     CU(cudaMemsetAsync(c->d_cc, 0, c->n_chunks * sizeof(ChunkCounters), c->stream));
     CU(cudaMemsetAsync(c->d_hist, 0, (c->p.histo_max + 2) * sizeof(uint64_t), c->stream));
     GlobalCounters gc{};
@@ -1642,6 +2125,12 @@ int32_t skm_stage_times(skm_ctx *c, skm_stage_ms *out) {
     out->n_grows = c->n_grows;
     out->table_capacity = c->capacity;
     out->table_bytes = c->capacity * sizeof(Slot);
+    out->sort = c->stage_ms[ST_SORT];
+    out->scan = c->stage_ms[ST_SCAN];
+    out->sort_launches = c->stage_launches[ST_SORT];
+    out->scan_launches = c->stage_launches[ST_SCAN];
+    out->tiled_launches = c->n_tiled_launches;
+    out->tiled_retries = c->n_tiled_retries;
     return SKM_OK;
 }
 
@@ -1656,47 +2145,39 @@ int32_t skm_export(skm_ctx *c, uint64_t *keys, uint32_t *counts, uint64_t cap, i
     if (!c || !n_out) return SKM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
+    int32_t rc = check_counted(c, "skm_export");
+    if (rc) return rc;
+    rc = ensure_physical(c);
+    if (rc) return rc;
     uint64_t n = 0;
-    int32_t rc = read_distinct(c, &n);
+    rc = read_distinct(c, &n);
     if (rc) return rc;
     *n_out = n;
     if (!keys && !counts) return SKM_OK;  // size query
     if (!keys || !counts || cap < n)
         return fail(c, SKM_ERR_INVALID_ARG, "export buffers too small: need %llu", (unsigned long long)n);
     if (n == 0) return SKM_OK;
-    unsigned long long *d_keys = nullptr, *d_cursor = nullptr;
-    uint32_t *d_counts = nullptr;
-    CU(cudaMallocAsync((void **)&d_keys, n * sizeof(uint64_t), c->stream));
-    CU(cudaMallocAsync((void **)&d_counts, n * sizeof(uint32_t), c->stream));
-    CU(cudaMallocAsync((void **)&d_cursor, sizeof(uint64_t), c->stream));
-    CU(cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), c->stream));
-    export_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity, d_keys, d_counts, n, d_cursor);
+    DevTmp<unsigned long long> d_keys(c->stream), d_cursor(c->stream);
+    DevTmp<uint32_t> d_counts(c->stream);
+    CU(d_keys.alloc(n));
+    CU(d_counts.alloc(n));
+    CU(d_cursor.alloc(1));
+    CU(cudaMemsetAsync(d_cursor.p, 0, sizeof(uint64_t), c->stream));
+    export_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity, d_keys.p, d_counts.p, n, d_cursor.p);
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(keys, d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(counts, d_counts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(c->h_pinned, d_cursor, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (sorted) {
+        // presentation order (the table itself has none): ascending k-mer, sorted on the device
+        rc = sort_pairs_device(c, d_keys.p, d_counts.p, n);
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(keys, d_keys.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(counts, d_counts.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_pinned, d_cursor.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaFreeAsync(d_keys, c->stream));
-    CU(cudaFreeAsync(d_counts, c->stream));
-    CU(cudaFreeAsync(d_cursor, c->stream));
     if (c->h_pinned[0] != n)
         return fail(c, SKM_ERR_CONSERVATION, "export found %llu occupied slots, expected %llu",
                     (unsigned long long)c->h_pinned[0], (unsigned long long)n);
-    if (sorted) {
-        // presentation order only (host): the table itself has no order
-        std::vector<uint64_t> idx(n);
-        for (uint64_t i = 0; i < n; i++) idx[i] = i;
-        std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return keys[a] < keys[b]; });
-        std::vector<uint64_t> k2(n);
-        std::vector<uint32_t> c2(n);
-        for (uint64_t i = 0; i < n; i++) {
-            k2[i] = keys[idx[i]];
-            c2[i] = counts[idx[i]];
-        }
-        memcpy(keys, k2.data(), n * sizeof(uint64_t));
-        memcpy(counts, c2.data(), n * sizeof(uint32_t));
-    }
     return SKM_OK;
 }
 
@@ -1704,7 +2185,9 @@ int32_t skm_table_digest(skm_ctx *c, uint64_t *out) {
     if (!c || !out) return SKM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    int32_t rc = scan_table(c, true, nullptr);
+    int32_t rc = check_counted(c, "skm_table_digest");
+    if (rc) return rc;
+    rc = scan_table(c, true, nullptr);
     if (rc) return rc;
     *out = c->last_tot.digest;
     return SKM_OK;
@@ -1714,26 +2197,53 @@ int32_t skm_lookup_batch(skm_ctx *c, const uint64_t *kmers, uint64_t n, uint32_t
                          uint32_t *counts, uint8_t *found) {
     if (!c || (n && !kmers) || mode < 0 || mode > SKM_LOOKUP_EITHER) return SKM_ERR_INVALID_ARG;
     if (n == 0) return SKM_OK;
-    std::lock_guard<std::mutex> lk(c->mu);
+    // Readers share the table like the reference's rayon workers do (src/stats.rs:84-98): the ctx
+    // lock is held only to take a private stream, never across the kernel or the copies.
+    cudaStream_t st = nullptr;
+    TableRef tr;
+    uint32_t k;
+    int sm_count;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        int32_t rc = check_counted(c, "skm_lookup_batch");
+        if (rc) return rc;
+        DeviceGuard g(c->device);
+        rc = ensure_physical(c);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(c->stream));  // inserts queued before this call are visible
+        st = take_read_stream(c);
+        tr = tref(c);
+        k = c->p.k;
+        sm_count = c->sm_count;
+        c->launches++;
+    }
     DeviceGuard g(c->device);
-    unsigned long long *d_q = nullptr;
-    uint32_t *d_c = nullptr;
-    uint8_t *d_f = nullptr;
-    CU(cudaMallocAsync((void **)&d_q, n * sizeof(uint64_t), c->stream));
-    CU(cudaMallocAsync((void **)&d_c, n * sizeof(uint32_t), c->stream));
-    CU(cudaMallocAsync((void **)&d_f, n, c->stream));
-    CU(cudaMemcpyAsync(d_q, kmers, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-    lookup_kernel<<<std::min<uint32_t>(grid_for(n, 256), c->sm_count * 8), 256, 0, c->stream>>>(
-        tref(c), c->p.k, d_q, n, min_count, mode, d_c, d_f);
-    c->launches++;
-    CU(cudaGetLastError());
-    if (counts) CU(cudaMemcpyAsync(counts, d_c, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    if (found) CU(cudaMemcpyAsync(found, d_f, n, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaFreeAsync(d_q, c->stream));
-    CU(cudaFreeAsync(d_c, c->stream));
-    CU(cudaFreeAsync(d_f, c->stream));
-    return SKM_OK;
+    int32_t rc = SKM_OK;
+    {
+        DevTmp<unsigned long long> d_q(st);
+        DevTmp<uint32_t> d_c(st);
+        DevTmp<uint8_t> d_f(st);
+        cudaError_t e = d_q.alloc(n);
+        if (e == cudaSuccess) e = d_c.alloc(n);
+        if (e == cudaSuccess) e = d_f.alloc(n);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_q.p, kmers, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            lookup_kernel<<<std::min<uint32_t>(grid_for(n, 256), sm_count * 8), 256, 0, st>>>(tr, k, d_q.p, n, min_count,
+                                                                                             mode, d_c.p, d_f.p);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && counts) e = cudaMemcpyAsync(counts, d_c.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && found) e = cudaMemcpyAsync(found, d_f.p, n, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            std::lock_guard<std::mutex> lk(c->mu);
+            rc = fail(c, e == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA, "skm_lookup_batch: %s",
+                      cudaGetErrorString(e));
+        }
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->read_streams.push_back(st);
+    return rc;
 }
 
 int32_t skm_scan_oligos(skm_ctx *c, const uint64_t *oligos, uint64_t n_oligos, uint32_t oligo_length,
@@ -1747,68 +2257,65 @@ int32_t skm_scan_oligos(skm_ctx *c, const uint64_t *oligos, uint64_t n_oligos, u
         return fail(c, SKM_ERR_INVALID_ARG, "oligo length %u out of range for k=%u (must be 1..k-1); trim must be < k",
                     oligo_length, k);
     if (n_oligos > (1u << 24)) return fail(c, SKM_ERR_INVALID_ARG, "too many oligos");
-    std::vector<uint64_t> fwd(n_oligos), rc(n_oligos);
+    std::vector<uint64_t> sets(2 * n_oligos);  // [sorted forward prefixes | sorted reverse-complement suffixes]
     for (uint64_t i = 0; i < n_oligos; i++) {
-        fwd[i] = oligos[i] << (2 * (k - oligo_length));
-        rc[i] = skm_revcomp_kmer(oligos[i], oligo_length);
+        sets[i] = oligos[i] << (2 * (k - oligo_length));
+        sets[n_oligos + i] = skm_revcomp_kmer(oligos[i], oligo_length);
     }
-    std::sort(fwd.begin(), fwd.end());
-    std::sort(rc.begin(), rc.end());
+    std::sort(sets.begin(), sets.begin() + n_oligos);
+    std::sort(sets.begin() + n_oligos, sets.end());
     const unsigned long long mask = ((1ull << (2 * oligo_length)) - 1) << (2 * k - 2 * oligo_length);
     const unsigned long long rc_mask = (1ull << (2 * oligo_length)) - 1;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    unsigned long long *d_sets = nullptr, *d_keys = nullptr, *d_cursor = nullptr;
-    uint32_t *d_counts = nullptr;
-    const uint64_t out_cap = cap;
-    CU(cudaMallocAsync((void **)&d_sets, 2 * n_oligos * sizeof(uint64_t), c->stream));
-    CU(cudaMallocAsync((void **)&d_keys, std::max<uint64_t>(out_cap, 1) * sizeof(uint64_t), c->stream));
-    CU(cudaMallocAsync((void **)&d_counts, std::max<uint64_t>(out_cap, 1) * sizeof(uint32_t), c->stream));
-    CU(cudaMallocAsync((void **)&d_cursor, sizeof(uint64_t), c->stream));
-    CU(cudaMemcpyAsync(d_sets, fwd.data(), n_oligos * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(d_sets + n_oligos, rc.data(), n_oligos * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), c->stream));
-    CU(cudaStreamSynchronize(c->stream));  // fwd/rc are pageable host vectors
-    scan_oligos_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity, k, d_sets, d_sets + n_oligos,
-                                                               (uint32_t)n_oligos, mask, rc_mask, min_count, d_keys,
-                                                               d_counts, out_cap, d_cursor);
-    c->launches++;
+    int32_t rc_code = check_counted(c, "skm_scan_oligos");
+    if (rc_code) return rc_code;
+    rc_code = ensure_physical(c);
+    if (rc_code) return rc_code;
+    DevTmp<unsigned long long> d_sets(c->stream), d_keys(c->stream), d_cursor(c->stream);
+    DevTmp<uint32_t> d_counts(c->stream);
+    const uint64_t out_cap = (keys && counts) ? cap : 0;
+    CU(d_sets.alloc(2 * n_oligos));
+    CU(d_keys.alloc(out_cap));
+    CU(d_counts.alloc(out_cap));
+    CU(d_cursor.alloc(1));
+    CU(cudaMemcpyAsync(d_sets.p, sets.data(), 2 * n_oligos * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(d_cursor.p, 0, sizeof(uint64_t), c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // `sets` is a pageable host vector
+    {
+        Span sp(c, ST_SCAN, c->stream);
+        scan_oligos_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity, k, d_sets.p, d_sets.p + n_oligos,
+                                                                   (uint32_t)n_oligos, mask, rc_mask, min_count, d_keys.p,
+                                                                   d_counts.p, out_cap, d_cursor.p);
+        c->launches++;
+        c->stage_launches[ST_SCAN]++;
+    }
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(c->h_pinned, d_cursor, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_pinned, d_cursor.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const uint64_t n = c->h_pinned[0];
     *n_out = n;
-    int32_t rc_code = SKM_OK;
-    if (keys && counts && cap >= n && n) {
-        CU(cudaMemcpy(keys, d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(counts, d_counts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        // presentation order (host): ascending k-mer, like skm_export(sorted)
-        std::vector<uint64_t> idx(n);
-        for (uint64_t i = 0; i < n; i++) idx[i] = i;
-        std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return keys[a] < keys[b]; });
-        std::vector<uint64_t> k2(n);
-        std::vector<uint32_t> c2(n);
-        for (uint64_t i = 0; i < n; i++) {
-            k2[i] = keys[idx[i]];
-            c2[i] = counts[idx[i]];
-        }
-        memcpy(keys, k2.data(), n * sizeof(uint64_t));
-        memcpy(counts, c2.data(), n * sizeof(uint32_t));
-    } else if (n && (keys || counts)) {
-        rc_code = fail(c, SKM_ERR_INVALID_ARG, "scan buffers too small: need %llu", (unsigned long long)n);
-    }
-    CU(cudaFreeAsync(d_sets, c->stream));
-    CU(cudaFreeAsync(d_keys, c->stream));
-    CU(cudaFreeAsync(d_counts, c->stream));
-    CU(cudaFreeAsync(d_cursor, c->stream));
-    return rc_code;
+    if (n == 0 || (!keys && !counts)) return SKM_OK;  // nothing found, or a size query
+    if (!keys || !counts || cap < n)
+        return fail(c, SKM_ERR_INVALID_ARG, "scan buffers too small: need %llu", (unsigned long long)n);
+    // presentation order: ascending k-mer, like skm_export(sorted)
+    rc_code = sort_pairs_device(c, d_keys.p, d_counts.p, n);
+    if (rc_code) return rc_code;
+    CU(cudaMemcpyAsync(keys, d_keys.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(counts, d_counts.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SKM_OK;
 }
 
 int32_t skm_insert_counts(skm_ctx *c, const uint64_t *keys, const uint32_t *counts, uint64_t n) {
     if (!c || (n && (!keys || !counts))) return SKM_ERR_INVALID_ARG;
     if (n == 0) return SKM_OK;
-    for (uint64_t i = 0; i < n; i++)
+    for (uint64_t i = 0; i < n; i++) {
         if (keys[i] == SKM_EMPTY_KEY) return fail(c, SKM_ERR_INVALID_ARG, "key %llu is the EMPTY sentinel (k <= 31 keys never are)", (unsigned long long)i);
+        // a zero count would claim a slot without histogram mass (KmerCounts never holds one:
+        // src/kmer/counting.rs:82-85 inserts 1 or adds to an existing count)
+        if (counts[i] == 0) return fail(c, SKM_ERR_INVALID_ARG, "count %llu is zero", (unsigned long long)i);
+    }
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     unsigned long long *d_k = nullptr;

@@ -30,14 +30,32 @@ struct __align__(16) Slot {
     unsigned long long count;
 };
 
+// The table is cut into partitions of 2^kPartLog2 consecutive slots (64 KiB).  A probe sequence
+// never leaves the partition of its home slot (it wraps inside it), so a partition is a
+// self-contained open-addressing table: the bulk insert kernel (tile_insert_kernel) loads one into
+// shared memory, counts every k-mer that hashes there with shared-memory atomics, and writes it
+// back — the table streams through the SMs once per launch instead of taking one random DRAM
+// sector per k-mer.  Every other kernel (direct insert, lookup, rehash) follows the same rule.
+// Capacity is always >= 2^16 slots, i.e. a whole number of partitions.
+static constexpr uint32_t kPartLog2 = 12;
+static constexpr uint32_t kPartSlots = 1u << kPartLog2;
+
 // A rank's table: 2^log2cap slots addressed by the rank-local hash.
 struct TableRef {
     Slot *slots;
     uint32_t log2cap;
     uint32_t n_ranks;
     __host__ __device__ __forceinline__ uint64_t mask() const { return (1ull << log2cap) - 1; }
+    __host__ __device__ __forceinline__ uint64_t local_hash(uint64_t kmer) const {
+        const uint64_t h = skm_hash_kmer(kmer);
+        return n_ranks == 1 ? h : skm_local_hash(h, n_ranks);
+    }
     __host__ __device__ __forceinline__ uint64_t home(uint64_t kmer) const {
-        return skm_home_slot(skm_local_hash(skm_hash_kmer(kmer), n_ranks), log2cap);
+        return skm_home_slot(local_hash(kmer), log2cap);
+    }
+    // next slot of a probe sequence: wraps inside the partition
+    __host__ __device__ __forceinline__ static uint64_t next(uint64_t s) {
+        return (s & ~(uint64_t)(kPartSlots - 1)) | ((s + 1) & (uint64_t)(kPartSlots - 1));
     }
 };
 
@@ -51,7 +69,11 @@ struct ChunkCounters {          // one per chunk, device memory
 struct GlobalCounters {         // one per ctx, device memory
     unsigned long long first_bad;   // min over (byte position << 8 | byte) of invalid bytes; ~0 = none
     unsigned long long n_distinct;  // keys claimed so far
-    unsigned long long scratch[6];
+    unsigned long long scratch[2];  // tile counters of the persistent kernels
+    unsigned long long part_full;   // != 0: a probe sequence found its whole partition occupied by other keys
+    unsigned long long n_failed;    // tile_insert_kernel: partitions that ran out of room in this launch
+    unsigned long long fatal;       // tile_insert_kernel: a failed partition had already published histogram moves
+    unsigned long long pad;
 };
 
 struct HistoTotals {
@@ -377,6 +399,7 @@ struct InsertPipe {
     unsigned long long o_old = 0;
     uint32_t o_add = 0;
     bool o_valid = false;
+    bool part_full = false;
     unsigned long long n_new = 0;
 
     __device__ __forceinline__ InsertPipe(const TableRef &t, const HistoSink &h)
@@ -385,6 +408,7 @@ struct InsertPipe {
     // resolve the oldest probe: find/claim the slot, add the count
     __device__ __forceinline__ void finish(unsigned long long kmer, unsigned long long s,
                                            unsigned long long key, uint32_t add) {
+        uint32_t probes = 0;
         for (;;) {
             if (key == SKM_EMPTY_KEY) {
                 key = atomicCAS(&table[s].key, (unsigned long long)SKM_EMPTY_KEY, kmer);
@@ -394,7 +418,11 @@ struct InsertPipe {
                 }
             }
             if (key == kmer) break;
-            s = (s + 1) & capmask;
+            if (++probes >= kPartSlots) {  // the whole partition holds other keys: report, never spin
+                part_full = true;
+                return;
+            }
+            s = TableRef::next(s);
             key = ld_cg_u64(&table[s].key);
         }
         if (kHisto) {
@@ -450,6 +478,7 @@ extract_insert_kernel(const uint64_t *__restrict__ codes, const uint32_t *__rest
     InsertPipe<D, kHisto> pipe(table, hs);
     unsigned long long n_win = extract_unit(in, k, [&](uint64_t kmer, int) { pipe.push(kmer); });
     pipe.drain();
+    if (pipe.part_full) gc->part_full = 1ull;
     block_add(&gc->n_distinct, pipe.n_new);
     block_add(&cc->n_windows, n_win);
     if (kHisto) histo_smem_flush(s_low, g_hist);
@@ -600,6 +629,7 @@ insert_runs_kernel(const RunDesc *__restrict__ descs, uint32_t n_desc, RunDesc s
         }
     }
     pipe.drain();
+    if (pipe.part_full) gc->part_full = 1ull;
     block_add(&gc->n_distinct, pipe.n_new);
     if (kHisto) histo_smem_flush(s_low, g_hist);
 }
@@ -616,7 +646,7 @@ __global__ void __launch_bounds__(256) table_clear_kernel(Slot *__restrict__ tab
 
 // Grow: re-insert every occupied slot of the old table into the new one.
 __global__ void __launch_bounds__(256)
-rehash_kernel(const Slot *__restrict__ old_table, uint64_t old_cap, TableRef nt) {
+rehash_kernel(const Slot *__restrict__ old_table, uint64_t old_cap, TableRef nt, GlobalCounters *__restrict__ gc) {
     Slot *__restrict__ table = nt.slots;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < old_cap;
          i += (uint64_t)gridDim.x * blockDim.x) {
@@ -626,11 +656,17 @@ rehash_kernel(const Slot *__restrict__ old_table, uint64_t old_cap, TableRef nt)
         const unsigned long long cnt = ((unsigned long long)v.w << 32) | v.z;
         // keys are unique in the old table: claim the first EMPTY slot of the probe sequence
         uint64_t sl = nt.home(key);
+        uint32_t probes = 0;
         for (;;) {
             if (ld_cg_u64(&table[sl].key) == SKM_EMPTY_KEY &&
                 atomicCAS(&table[sl].key, (unsigned long long)SKM_EMPTY_KEY, key) == SKM_EMPTY_KEY)
                 break;
-            sl = (sl + 1) & nt.mask();
+            if (++probes >= kPartSlots) break;
+            sl = TableRef::next(sl);
+        }
+        if (probes >= kPartSlots) {
+            gc->part_full = 1ull;
+            continue;
         }
         table[sl].count = cnt;
     }
@@ -745,9 +781,8 @@ export_kernel(const Slot *__restrict__ table, uint64_t capacity, unsigned long l
 __device__ __forceinline__ bool table_find(const TableRef &tr, uint64_t q, uint32_t &count) {
     if (q == SKM_EMPTY_KEY) return false;
     const Slot *__restrict__ table = tr.slots;
-    const uint64_t capmask = tr.mask();
     uint64_t s = tr.home(q);
-    for (;;) {
+    for (uint32_t probes = 0; probes < kPartSlots; probes++) {
         const uint4 v = *(reinterpret_cast<const uint4 *>(table) + s);
         const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
         if (key == q) {
@@ -756,8 +791,9 @@ __device__ __forceinline__ bool table_find(const TableRef &tr, uint64_t q, uint3
             return true;
         }
         if (key == SKM_EMPTY_KEY) return false;
-        s = (s + 1) & capmask;
+        s = TableRef::next(s);
     }
+    return false;
 }
 
 __global__ void __launch_bounds__(256)
@@ -1069,6 +1105,555 @@ bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__rest
         }
     }
     if (kCapped && threadIdx.x == 0 && total) atomicAdd(&cc->n_windows, (unsigned long long)total);
+}
+
+// ---------------------------------------------------------------------------
+// (5) tile-sorted lists + shared-memory insert ("tiled" mode; the bulk path)
+//
+//   pass A  bucket_scatter_kernel above: k-mers grouped by (owner, table region) — <= 1024 buckets.
+//   pass B  tile_sort_kernel: every bucket's cells are cut into tiles of kTile k-mers; each tile
+//           is sorted IN PLACE by the next g2 hash bits (the "sub-bucket") inside shared memory,
+//           and the tile's F+1 sub-bucket offsets are written beside it.  Reads and writes are whole
+//           64 KiB tiles: pure streaming, 8 B in + 8 B out per k-mer.
+//   insert  tile_insert_kernel: one CTA per table partition (kPartSlots slots = 64 KiB).  The
+//           partition's k-mers are, in every tile of its bucket, one contiguous run (sub-buckets
+//           are ordered by hash).  The CTA loads the partition into shared memory, walks the runs
+//           chunk by chunk (a CTA barrier between chunks makes the per-chunk histogram columns
+//           exact), counts with shared-memory atomics, and writes the partition back.
+//           DRAM traffic: 16 B/slot in + 16 B/slot out + 8 B per k-mer, all sequential.
+//
+//   The list geometry (g1 region bits, g2 sub-bucket bits) is fixed when a list is built and
+//   does not depend on the table size at insert time: a partition of a smaller table covers
+//   several adjacent sub-buckets or whole buckets (still one run per tile), a partition of a
+//   larger table shares a sub-bucket with its neighbours and filters by home slot.
+// ---------------------------------------------------------------------------
+
+static constexpr uint32_t kTile = 8192;                       // k-mers per tile (64 KiB)
+static constexpr uint32_t kSortThreads = 512;
+static constexpr uint32_t kSortPer = kTile / kSortThreads;    // k-mers per thread
+static constexpr uint32_t kMaxSubLog2 = 10;                   // g2 <= 10: sub-bucket and rank share a 32-bit word
+static_assert(kTile <= (1u << 14), "rank must fit 14 bits");
+
+struct ListGeom {
+    uint32_t n_ranks;
+    uint32_t g1;  // log2(table regions per owner): bucket = owner << g1 | region
+    uint32_t g2;  // log2(sub-buckets per region)
+    __host__ __device__ __forceinline__ uint32_t sub(uint64_t kmer) const {
+        const uint64_t h = skm_hash_kmer(kmer);
+        const uint64_t lh = n_ranks == 1 ? h : skm_local_hash(h, n_ranks);
+        return g2 ? (uint32_t)((lh << g1) >> (64u - g2)) : 0u;
+    }
+};
+
+// Where the tiles of a bucketed list are (device arrays, one set per list):
+//   cell_begin[b]  first cell of bucket b          bucket_n[b]  k-mers in bucket b
+//   tile_begin[b]  index of bucket b's first tile; tile_begin[nb] = number of tiles
+// Tile t of bucket b covers cells [cell_begin[b] + j*kTile, +min(kTile, bucket_n[b] - j*kTile)),
+// j = t - tile_begin[b]; a tile past the end of its bucket is empty (capped layout: every bucket
+// owns the same number of tile slots).
+struct ListMeta {
+    unsigned long long *cell_begin;
+    uint32_t *tile_begin;
+    uint32_t *bucket_n;
+};
+__host__ __device__ inline size_t list_meta_words(uint32_t nb) { return (size_t)nb + (2 * (size_t)nb + 2) / 2 + 1; }
+__host__ __device__ inline ListMeta list_meta_at(unsigned long long *base, uint32_t nb) {
+    ListMeta m;
+    m.cell_begin = base;
+    m.tile_begin = reinterpret_cast<uint32_t *>(base + nb);
+    m.bucket_n = m.tile_begin + nb + 1;
+    return m;
+}
+
+// src: capped layout (cap > 0) = the scatter kernel's per-bucket totals; exact layout (cap == 0) =
+// the nb+1 bucket offsets.  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024)
+tile_plan_kernel(const unsigned long long *__restrict__ src, uint32_t nb, unsigned long long cap,
+                 uint32_t tiles_per_bucket, ListMeta m) {
+    __shared__ uint32_t s_warp[32];
+    const uint32_t b = threadIdx.x;
+    uint32_t tiles = 0;
+    unsigned long long n = 0;
+    if (b < nb) {
+        if (cap) {
+            n = src[b] < cap ? src[b] : cap;
+            m.cell_begin[b] = (unsigned long long)b * cap;
+            tiles = tiles_per_bucket;
+        } else {
+            n = src[b + 1] - src[b];
+            m.cell_begin[b] = src[b];
+            tiles = (uint32_t)((n + kTile - 1) / kTile);
+        }
+        m.bucket_n[b] = (uint32_t)n;
+    }
+    uint32_t incl = tiles;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= (uint32_t)o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t off = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) off += s_warp[w];
+    if (b < nb) m.tile_begin[b] = off + incl - tiles;
+    if (b == nb - 1 || (nb == 0 && b == 0)) m.tile_begin[nb] = nb ? off + incl : 0;
+}
+
+// tile_off[t * (F + 1) + f] = first cell (relative to the tile) of sub-bucket f; [.. + F] = tile length
+__global__ void __launch_bounds__(kSortThreads, 2)
+tile_sort_kernel(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb, ListGeom geom,
+                 uint16_t *__restrict__ tile_off) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long *stage = reinterpret_cast<unsigned long long *>(s_raw);   // kTile
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(stage + kTile);                  // F (+1)
+    __shared__ uint32_t s_warp[kSortThreads / 32];
+    const uint32_t F = 1u << geom.g2;
+    const uint32_t t = blockIdx.x;
+    if (t >= m.tile_begin[nb]) return;
+    uint32_t lo = 0, hi = nb;  // last bucket whose tile_begin <= t
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (m.tile_begin[mid] <= t) lo = mid; else hi = mid;
+    }
+    const uint32_t j = t - m.tile_begin[lo];
+    const unsigned long long bn = m.bucket_n[lo];
+    const unsigned long long first = (unsigned long long)j * kTile;
+    const uint32_t n = first >= bn ? 0u : (uint32_t)(bn - first < kTile ? bn - first : kTile);
+    uint16_t *off = tile_off + (size_t)t * (F + 1);
+    if (n == 0) {  // empty tile slot: all offsets zero, so every run read from it has length 0
+        for (uint32_t f = threadIdx.x; f <= F; f += kSortThreads) off[f] = 0;
+        return;
+    }
+    unsigned long long *cells = list + m.cell_begin[lo] + first;
+    for (uint32_t f = threadIdx.x; f < F; f += kSortThreads) cnt[f] = 0;
+    __syncthreads();
+    unsigned long long km[kSortPer];
+    uint32_t fr[kSortPer];  // sub-bucket | rank inside (tile, sub-bucket) << 10
+#pragma unroll
+    for (uint32_t r = 0; r < kSortPer; r++) {
+        const uint32_t i = threadIdx.x + r * kSortThreads;
+        km[r] = i < n ? cells[i] : 0ull;
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < kSortPer; r++) {
+        const uint32_t i = threadIdx.x + r * kSortThreads;
+        if (i < n) {
+            const uint32_t f = geom.sub(km[r]);
+            fr[r] = f | (atomicAdd(&cnt[f], 1u) << kMaxSubLog2);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..F) (F <= 1024 = 2 entries per thread)
+    const uint32_t a = threadIdx.x * 2;
+    const uint32_t c0 = a < F ? cnt[a] : 0u, c1 = a + 1 < F ? cnt[a + 1] : 0u;
+    uint32_t incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= (uint32_t)o) incl += v;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) base += s_warp[w];
+    const uint32_t start0 = base + incl - c0 - c1;
+    if (a < F) {
+        cnt[a] = start0;
+        off[a] = (uint16_t)start0;
+    }
+    if (a + 1 < F) {
+        cnt[a + 1] = start0 + c0;
+        off[a + 1] = (uint16_t)(start0 + c0);
+    }
+    if (threadIdx.x == 0) off[F] = (uint16_t)n;  // kTile = 8192 fits
+    __syncthreads();
+#pragma unroll
+    for (uint32_t r = 0; r < kSortPer; r++) {
+        const uint32_t i = threadIdx.x + r * kSortThreads;
+        if (i < n) stage[cnt[fr[r] & ((1u << kMaxSubLog2) - 1)] + (fr[r] >> kMaxSubLog2)] = km[r];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) cells[i] = stage[i];
+}
+
+__host__ __device__ inline size_t tile_sort_smem_bytes(uint32_t g2) { return (size_t)kTile * 8 + ((size_t)1 << g2) * 4 + 16; }
+
+// One bucketed, tile-sorted list as the insert kernel sees it.  `list` and `tile_off` are biased by
+// the receiver so that the sender's own numbering (cell_begin / tile_begin of bucket0 + region)
+// indexes them directly: on one GPU bucket0 = 0 and nothing is biased; across GPUs the list is the
+// owner's block inside a receive arena.
+struct SegDesc {
+    const unsigned long long *list;
+    const uint16_t *tile_off;
+    const uint32_t *tile_begin;
+    const unsigned long long *cell_begin;
+    uint32_t bucket0;   // first bucket of this table's owner in the list's numbering (rank << g1)
+    uint32_t chunk;     // chunk index relative to the launch's first chunk
+};
+
+static constexpr uint32_t kInsThreads = 256;
+static constexpr uint32_t kMaxVseg = 256;    // (list, bucket) pairs per launch that one partition reads
+static constexpr uint32_t kStagedRuns = 256; // runs staged in shared memory at a time
+static constexpr uint32_t kHlogCap = 512;    // pending moves of histogram bins >= k_low, per partition
+static constexpr uint32_t kBigCount = 0x80000000u;
+
+struct InsertLaunch {
+    Slot *table;
+    uint32_t log2cap, n_ranks;
+    uint32_t g1, g2;
+    const SegDesc *segs;                 // sorted by chunk
+    const uint32_t *chunk_first_seg;     // [n_chunks + 1]
+    uint32_t n_segs, n_chunks;
+    uint32_t k_low;                      // histogram bins kept in shared memory (per chunk)
+    uint32_t max_occupied;               // a partition holding more keys than this fails (grow + retry)
+    const uint32_t *part_ids;            // null: partitions 0 .. n_parts-1
+    unsigned long long n_parts;
+    int fresh;                           // table logically empty: partitions are not loaded
+    unsigned long long *g_delta;         // [n_chunks][histo_max + 2] histogram moves per chunk
+    unsigned long long *g_recount;       // [histo_max + 2] histogram of the partitions written back
+    unsigned long long histo_max;
+    GlobalCounters *gc;
+    HistoTotals *tot;                    // n_distinct / n_kmers / n_saturated of the partitions written back
+    unsigned long long *part_counter;
+    uint32_t *fail_list;
+    uint32_t fail_cap;
+};
+
+__host__ __device__ inline size_t tile_insert_smem_bytes(uint32_t n_chunks, uint32_t k_low, bool histo) {
+    size_t b = (size_t)kPartSlots * 12;                    // keys + counts
+    b += (size_t)kMaxVseg * 16 + 8;                        // vs_cell (u64), vs_tb, vs_first (u32)
+    b += (size_t)kStagedRuns * 12;                            // run_src (u64), run_len (u32)
+    if (histo) b += (size_t)n_chunks * k_low * 8 + (size_t)k_low * 4 + (size_t)kHlogCap * 4;  // chist + phist, fhist, hlog
+    else b += (size_t)k_low * 4;
+    return b + 64;
+}
+
+template <bool kHisto>
+__global__ void __launch_bounds__(kInsThreads, 3)
+tile_insert_kernel(const InsertLaunch L) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(s_raw);
+    unsigned long long *vs_cell = keys + kPartSlots;
+    unsigned long long *run_src = vs_cell + kMaxVseg;
+    uint32_t *counts = reinterpret_cast<uint32_t *>(run_src + kStagedRuns);
+    uint32_t *vs_tb = counts + kPartSlots;
+    uint32_t *vs_first = vs_tb + kMaxVseg;          // kMaxVseg + 1
+    uint32_t *run_len = vs_first + kMaxVseg + 2;
+    int *fhist = reinterpret_cast<int *>(run_len + kStagedRuns);   // k_low: histogram of the written-back partition(s)
+    int *chist = fhist + L.k_low;                   // n_chunks * k_low: moves of committed partitions
+    int *phist = chist + (kHisto ? L.n_chunks * L.k_low : 0);   // n_chunks * k_low: moves of the current partition
+    uint32_t *hlog = reinterpret_cast<uint32_t *>(phist + (kHisto ? L.n_chunks * L.k_low : 0));
+    __shared__ unsigned long long s_q;
+    __shared__ uint32_t s_occ, s_fail, s_big, s_hlog_n, s_dirty;
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = kInsThreads / 32;
+    const uint32_t pbits = L.log2cap - kPartLog2;
+    const uint32_t F = 1u << L.g2;
+    const unsigned long long top = L.histo_max + 1;
+    for (uint32_t i = threadIdx.x; i < L.k_low; i += kInsThreads) fhist[i] = 0;
+    if (kHisto)
+        for (uint32_t i = threadIdx.x; i < 2 * L.n_chunks * L.k_low; i += kInsThreads) chist[i] = 0;
+    unsigned long long n_new_cta = 0, n_kmers_cta = 0, n_dist_cta = 0, n_sat_cta = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long i = atomicAdd(L.part_counter, 1ull);
+            s_q = i < L.n_parts ? (L.part_ids ? (unsigned long long)L.part_ids[i] : i) : ~0ull;
+            s_occ = 0;
+            s_fail = 0;
+            s_big = 0;
+            s_hlog_n = 0;
+            s_dirty = 0;
+        }
+        __syncthreads();
+        const unsigned long long q = s_q;
+        if (q == ~0ull) break;
+        // which buckets / sub-buckets of the lists hold this partition's k-mers
+        uint32_t b_lo, nbr, f0, f1;
+        bool filter = false;
+        if (pbits <= L.g1) {
+            nbr = 1u << (L.g1 - pbits);
+            b_lo = (uint32_t)q << (L.g1 - pbits);
+            f0 = 0;
+            f1 = F;
+        } else if (pbits <= L.g1 + L.g2) {
+            const uint32_t d = pbits - L.g1, e = L.g1 + L.g2 - pbits;
+            nbr = 1;
+            b_lo = (uint32_t)(q >> d);
+            f0 = ((uint32_t)q & ((1u << d) - 1)) << e;
+            f1 = f0 + (1u << e);
+        } else {
+            const uint32_t d = pbits - L.g1;
+            nbr = 1;
+            b_lo = (uint32_t)(q >> d);
+            f0 = (uint32_t)(q >> (d - L.g2)) & (F - 1);
+            f1 = f0 + 1;
+            filter = true;
+        }
+        Slot *tp = L.table + (q << kPartLog2);
+        // ---- load the partition (or start empty) ----
+        {
+            uint32_t occ = 0, big = 0;
+            if (!L.fresh) {
+#pragma unroll 4
+                for (uint32_t i = threadIdx.x; i < kPartSlots; i += kInsThreads) {
+                    const uint4 v = ld_nc_v4(reinterpret_cast<const uint4 *>(tp) + i);
+                    const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
+                    keys[i] = key;
+                    const bool is_big = v.w != 0u || v.z >= kBigCount;
+                    counts[i] = is_big ? kBigCount : v.z;
+                    occ += key != SKM_EMPTY_KEY;
+                    big |= is_big && key != SKM_EMPTY_KEY;
+                }
+            } else {
+                for (uint32_t i = threadIdx.x; i < kPartSlots; i += kInsThreads) {
+                    keys[i] = SKM_EMPTY_KEY;
+                    counts[i] = 0;
+                }
+            }
+            occ = __reduce_add_sync(0xffffffffu, occ);
+            if (lane == 0 && occ) atomicAdd(&s_occ, occ);
+            if (big) s_big = 1;
+        }
+        // ---- which tiles: one "virtual segment" per (list, bucket) ----
+        const uint32_t n_vseg = L.n_segs * nbr;   // <= kMaxVseg (the host splits launches)
+        for (uint32_t v = threadIdx.x; v < n_vseg; v += kInsThreads) {
+            const SegDesc &sg = L.segs[v / nbr];
+            const uint32_t bkt = sg.bucket0 + b_lo + v % nbr;
+            const uint32_t tb = sg.tile_begin[bkt];
+            vs_tb[v] = tb;
+            vs_first[v] = sg.tile_begin[bkt + 1] - tb;   // tiles; scanned below
+            vs_cell[v] = sg.cell_begin[bkt];
+        }
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the tile counts -> first run of each virtual segment
+            uint32_t run = 0;
+            for (uint32_t v0 = 0; v0 < n_vseg; v0 += 32) {
+                const uint32_t v = v0 + lane;
+                const uint32_t x = v < n_vseg ? vs_first[v] : 0u;
+                uint32_t incl = x;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= (uint32_t)o) incl += t;
+                }
+                if (v < n_vseg) vs_first[v] = run + incl - x;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) vs_first[n_vseg] = run;
+        }
+        __syncthreads();
+        const uint32_t total_runs = vs_first[n_vseg];
+        unsigned long long n_new = 0;
+        uint32_t w0 = 0, w1 = 0;  // runs [w0, w1) are staged in run_src / run_len
+        for (uint32_t c = 0; c < L.n_chunks; c++) {
+            const uint32_t cr0 = vs_first[L.chunk_first_seg[c] * nbr], cr1 = vs_first[L.chunk_first_seg[c + 1] * nbr];
+            uint32_t pos = cr0;
+            while (pos < cr1) {
+                if (pos >= w1) {  // stage the next window of runs
+                    __syncthreads();
+                    w0 = pos;
+                    w1 = min(total_runs, w0 + kStagedRuns);
+                    for (uint32_t r = w0 + threadIdx.x; r < w1; r += kInsThreads) {
+                        uint32_t lo = 0, hi = n_vseg;  // last virtual segment whose first run <= r
+                        while (hi - lo > 1) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (vs_first[mid] <= r) lo = mid; else hi = mid;
+                        }
+                        const SegDesc &sg = L.segs[lo / nbr];
+                        const uint32_t jt = r - vs_first[lo];
+                        const uint16_t *off = sg.tile_off + (size_t)(vs_tb[lo] + jt) * (F + 1);
+                        const uint32_t o0 = off[f0], o1 = off[f1];
+                        run_src[r - w0] = reinterpret_cast<unsigned long long>(sg.list + vs_cell[lo] + (unsigned long long)jt * kTile + o0);
+                        run_len[r - w0] = o1 - o0;
+                    }
+                    __syncthreads();
+                }
+                const uint32_t end = min(cr1, w1);
+                if (!s_fail) {
+                    for (uint32_t r = pos + warp; r < end; r += n_warps) {
+                        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(run_src[r - w0]);
+                        const uint32_t n = run_len[r - w0];
+                        for (uint32_t i0 = 0; i0 < n; i0 += 128) {
+                            unsigned long long km[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const uint32_t i = i0 + u * 32 + lane;
+                                km[u] = i < n ? src[i] : SKM_EMPTY_KEY;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const unsigned long long kmer = km[u];
+                                if (kmer == SKM_EMPTY_KEY) continue;
+                                const uint64_t h = skm_hash_kmer(kmer);
+                                const uint64_t home = skm_home_slot(L.n_ranks == 1 ? h : skm_local_hash(h, L.n_ranks), L.log2cap);
+                                if (filter && (home >> kPartLog2) != q) continue;
+                                uint32_t s = (uint32_t)home & (kPartSlots - 1);
+                                uint32_t probes = 0;
+                                bool ok = true;
+                                for (;;) {
+                                    unsigned long long key = keys[s];
+                                    if (key == kmer) break;
+                                    if (key == SKM_EMPTY_KEY) {
+                                        key = atomicCAS(&keys[s], (unsigned long long)SKM_EMPTY_KEY, kmer);
+                                        if (key == SKM_EMPTY_KEY) {
+                                            n_new++;
+                                            if (atomicAdd(&s_occ, 1u) >= L.max_occupied) s_fail = 1;
+                                            break;
+                                        }
+                                        if (key == kmer) break;
+                                    }
+                                    if (++probes >= kPartSlots) {
+                                        ok = false;
+                                        s_fail = 1;
+                                        break;
+                                    }
+                                    s = (s + 1) & (kPartSlots - 1);
+                                }
+                                if (!ok) continue;
+                                if (!kHisto) {
+                                    atomicAdd(&counts[s], 1u);
+                                } else {
+                                    const unsigned long long old = atomicAdd(&counts[s], 1u);
+                                    // Histogram::move_count (src/kmer/histogram.rs:51-85): one unit of mass from bin old to old+1
+                                    const unsigned long long ob = old > L.histo_max ? top : old;
+                                    const unsigned long long nb2 = old + 1 > L.histo_max ? top : old + 1;
+                                    if (ob != nb2) {
+                                        if (old) {
+                                            if (ob < L.k_low) atomicAdd(&phist[c * L.k_low + (uint32_t)ob], -1);
+                                            else {
+                                                const uint32_t e = atomicAdd(&s_hlog_n, 1u);
+                                                if (e < kHlogCap) hlog[e] = (c << 24) | 0x800000u | (uint32_t)ob;   // bit 23: minus
+                                                else {
+                                                    s_dirty = 1;
+                                                    atomicAdd(&L.g_delta[(size_t)c * (L.histo_max + 2) + ob], ~0ull);
+                                                }
+                                            }
+                                        }
+                                        if (nb2 < L.k_low) atomicAdd(&phist[c * L.k_low + (uint32_t)nb2], 1);
+                                        else {
+                                            const uint32_t e = atomicAdd(&s_hlog_n, 1u);
+                                            if (e < kHlogCap) hlog[e] = (c << 24) | (uint32_t)nb2;
+                                            else {
+                                                s_dirty = 1;
+                                                atomicAdd(&L.g_delta[(size_t)c * (L.histo_max + 2) + nb2], 1ull);
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                pos = end;
+            }
+            if (kHisto) __syncthreads();  // chunk c is complete before any k-mer of chunk c+1 is counted
+        }
+        __syncthreads();
+        // ---- commit or roll back ----
+        if (!s_fail) {
+            unsigned long long nk = 0, nd = 0, ns = 0;
+#pragma unroll 4
+            for (uint32_t i = threadIdx.x; i < kPartSlots; i += kInsThreads) {
+                const unsigned long long key = keys[i];
+                unsigned long long cnt = counts[i];
+                if (s_big && counts[i] >= kBigCount && !L.fresh && key != SKM_EMPTY_KEY) {
+                    // the slot may have held a count >= 2^31 before the launch (kept as the marker kBigCount + adds)
+                    const uint4 o = *(reinterpret_cast<const uint4 *>(tp) + i);
+                    const unsigned long long old64 = ((unsigned long long)o.w << 32) | o.z;
+                    const unsigned long long oldkey = ((unsigned long long)o.y << 32) | o.x;
+                    if (oldkey == key && old64 >= kBigCount) cnt = old64 + (cnt - kBigCount);
+                }
+                uint4 v;
+                v.x = (uint32_t)key;
+                v.y = (uint32_t)(key >> 32);
+                v.z = (uint32_t)cnt;
+                v.w = (uint32_t)(cnt >> 32);
+                reinterpret_cast<uint4 *>(tp)[i] = v;
+                if (key != SKM_EMPTY_KEY) {
+                    if (cnt >= kU32Max) {
+                        cnt = kU32Max;
+                        ns++;
+                    }
+                    nd++;
+                    nk += cnt;
+                    const unsigned long long bin = cnt > L.histo_max ? top : cnt;
+                    if (bin < L.k_low) atomicAdd(&fhist[(uint32_t)bin], 1);
+                    else atomicAdd(&L.g_recount[bin], 1ull);
+                }
+            }
+            n_kmers_cta += nk;
+            n_dist_cta += nd;
+            n_sat_cta += ns;
+            n_new_cta += n_new;
+            if (kHisto) {
+                for (uint32_t i = threadIdx.x; i < L.n_chunks * L.k_low; i += kInsThreads) {
+                    const int d = phist[i];
+                    if (d) {
+                        chist[i] += d;
+                        phist[i] = 0;
+                    }
+                }
+                const uint32_t nh = min(s_hlog_n, kHlogCap);
+                for (uint32_t i = threadIdx.x; i < nh; i += kInsThreads) {
+                    const uint32_t e = hlog[i];
+                    atomicAdd(&L.g_delta[(size_t)(e >> 24) * (L.histo_max + 2) + (e & 0x7FFFFFu)],
+                              (e & 0x800000u) ? ~0ull : 1ull);
+                }
+            }
+        } else {
+            // rolled back: nothing of this partition is published.  (A launch on a logically empty
+            // table owns the partition's memory: leave it physically empty for the retry.)
+            if (L.fresh)
+                for (uint32_t i = threadIdx.x; i < kPartSlots; i += kInsThreads) {
+                    uint4 v;
+                    v.x = v.y = 0xFFFFFFFFu;
+                    v.z = v.w = 0u;
+                    reinterpret_cast<uint4 *>(tp)[i] = v;
+                }
+            if (kHisto)
+                for (uint32_t i = threadIdx.x; i < L.n_chunks * L.k_low; i += kInsThreads) phist[i] = 0;
+            if (threadIdx.x == 0) {
+                const unsigned long long e = atomicAdd(&L.gc->n_failed, 1ull);
+                if (e < L.fail_cap) L.fail_list[e] = (uint32_t)q;
+                if (s_dirty) L.gc->fatal = 1ull;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- publish this CTA's accumulators ----
+    for (uint32_t i = threadIdx.x; i < L.k_low; i += kInsThreads)
+        if (fhist[i]) atomicAdd(&L.g_recount[i > L.histo_max ? top : i], (unsigned long long)(long long)fhist[i]);
+    if (kHisto)
+        for (uint32_t i = threadIdx.x; i < L.n_chunks * L.k_low; i += kInsThreads)
+            if (chist[i]) {
+                const unsigned long long bin = i % L.k_low;
+                atomicAdd(&L.g_delta[(size_t)(i / L.k_low) * (L.histo_max + 2) + (bin > L.histo_max ? top : bin)],
+                          (unsigned long long)(long long)chist[i]);
+            }
+    block_add(&L.gc->n_distinct, n_new_cta);
+    block_add(&L.tot->n_kmers, n_kmers_cta);
+    block_add(&L.tot->n_distinct, n_dist_cta);
+    block_add(&L.tot->n_saturated, n_sat_cta);
+}
+
+// Columns of the incremental histogram from the per-chunk moves: column c = base + sum of the
+// moves of chunks <= c (src/io.rs:1023-1028: chunks are merged in index order and the histogram
+// is read after each).  `base` (the running histogram) ends as the last column.
+__global__ void __launch_bounds__(256)
+hist_columns_kernel(const unsigned long long *delta, uint32_t n_chunks, unsigned long long n_bins,
+                    unsigned long long *__restrict__ base, unsigned long long *cols /* may be null or == delta */) {
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < n_bins;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long run = base[b];
+        for (uint32_t c = 0; c < n_chunks; c++) {
+            run += delta[(size_t)c * n_bins + b];
+            if (cols) cols[(size_t)c * n_bins + b] = run;
+        }
+        base[b] = run;
+    }
 }
 
 // *p += delta (delta may be "negative" in two's complement)
