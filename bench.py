@@ -189,7 +189,7 @@ def workload_config(n_gpus):
             "genome_len": GENOME_PER_GPU * n_gpus, "histo_max": HISTO_MAX,
             "l2": "inputs (1.5 GB/GPU) and table (8.6 GB/GPU) exceed L2; no flush needed",
             "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs: reads split, table sharded by k-mer hash range, "
-                           "k-mers routed over NVLink (fused peer-store scatter, or NCCL all-to-all with --exchange nccl)"}
+                           "k-mers routed to their owners over NVLink by the copy engines"}
 
 
 # ----------------------------------------------------------------------------
@@ -233,10 +233,6 @@ def run_ours(args):
 
     if world > 1 and os.environ.get("SKM_TRACE"):
         os.environ["SKM_TRACE"] += f".rank{rank}"   # one timeline file per rank
-    if world > 1 and args.exchange in ("p2p", "nccl"):
-        # these two paths bucket at routing time (p2p: scatter kernel fused with the peer stores);
-        # the "dma" path buckets at ingest time and lets the copy engines move the runs
-        os.environ["SKM_EAGER"] = "0"
     # high priority: the inserts (this stream) outrank the engine's bucketing streams
     stream = torch.cuda.Stream(device=dev, priority=-1 if os.environ.get("SKM_PRIO", "1") != "0" else 0)
     eng = kmer.Engine(K, CHUNKS, HISTO_MAX, capacity_hint=hint, device=local_rank, insert_mode=mode,
@@ -246,17 +242,23 @@ def run_ours(args):
 
     # ---- inputs: chunk c holds the reads of batches b = c (mod CHUNKS) (src/io.rs:355-361);
     #      rank r takes the r-th contiguous slice of every chunk's 1000-read batches ---------------
-    d_bufs, h_bufs, n_local = [], [], []
-    for c in range(CHUNKS):
-        n_batches_c = len(range(c, (n_reads_total + 999) // 1000, CHUNKS))
-        lo, hi = n_batches_c * rank // world, n_batches_c * (rank + 1) // world
-        first, n = lo * 1000, (hi - lo) * 1000
-        # (n_reads_total is a multiple of 1000 * CHUNKS in every configuration used here)
-        t = torch.empty(n * line, dtype=torch.uint8, device=dev)
-        eng.synth_device(SEED, genome, READ_LEN, st, nt, c, CHUNKS, first, n, t.data_ptr())
-        d_bufs.append(t)
-        n_local.append(n)
-    torch.cuda.synchronize()
+    def make_inputs(engine, n_total, genome_len):
+        bufs, counts = [], []
+        for c in range(CHUNKS):
+            n_batches_c = len(range(c, (n_total + 999) // 1000, CHUNKS))
+            lo, hi = n_batches_c * rank // world, n_batches_c * (rank + 1) // world
+            first, n = lo * 1000, (hi - lo) * 1000
+            # (n_total is a multiple of 1000 in every configuration used here)
+            t = torch.empty(max(n * line, 1), dtype=torch.uint8, device=dev)[:n * line]
+            if n:
+                engine.synth_device(SEED, genome_len, READ_LEN, st, nt, c, CHUNKS, first, n, t.data_ptr())
+            bufs.append(t)
+            counts.append(n)
+        torch.cuda.synchronize()
+        return bufs, counts
+
+    d_bufs, n_local = make_inputs(eng, n_reads_total, genome)
+    h_bufs = []
     if not args.no_e2e:
         for t in d_bufs:
             h = torch.empty(t.numel(), dtype=torch.uint8, pin_memory=True)
@@ -267,13 +269,14 @@ def run_ours(args):
 
     # ---- one step -------------------------------------------------------------------------------
     sharded = None
+    cpu_group = None
     if world > 1:
         from sharkmer_b200.multigpu import ShardedCounter
-        # receive arena per slot: this rank's share of a chunk's k-mers (+30 % for imbalance);
-        # the dma exchange keeps one slot per chunk (13 GB per rank here)
-        arena = int(1.3 * max(t.numel() for t in d_bufs)) + (1 << 20)
-        sharded = ShardedCounter(eng, CHUNKS, CHUNKS, HISTO_MAX, dev, stream=stream,
-                                 exchange=args.exchange, arena_entries=arena)
+        cpu_group = dist.new_group(backend="gloo")   # carries the library's all-gathers (host bytes); NCCL: barriers only
+        # receive arena: this rank's share of all ranks' k-mers = ~its own input x 8 B, +6 % capped-region
+        # slack, +3 % tile offsets, + margin for imbalance
+        arena = int(in_bytes * 8 * 1.25) + (256 << 20)
+        sharded = ShardedCounter(eng, dev, cpu_group=cpu_group, arena_bytes=arena)
 
     def step(host_buffers: bool):
         eng.reset()
@@ -307,68 +310,133 @@ def run_ours(args):
             ms, wall = float(tm[0]), float(tm[1]) / 1e3
         return ms / steps, wall * 1e3 / steps, hist
 
-    # ---- parity guard before timing: GPU vs oracle on the bounded CPU sample (rank 0, N=1) ------
+    # ---- parity guard before timing: GPU vs oracle on a bounded sample, through the SAME path as the
+    #      timed region (tiled insert; at N > 1 the sharded path: bucketing by owner, copy-engine exchange,
+    #      collective finalize) ----------------------------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        run, reads, dt = cpu_sample(args.cpu_sample_reads, genome)
-        chk = kmer.Engine(K, CHUNKS, HISTO_MAX, capacity_hint=int(hint * args.cpu_sample_reads / args.reads_per_gpu) + 1000,
-                          device=local_rank, insert_mode=mode)
-        nb = args.cpu_sample_reads // 1000
-        for b in range(nb):
-            chk.ingest_batch(b % CHUNKS, reads[b * 1000 * line:(b + 1) * 1000 * line])
-        chk.finalize()
-        ok = chk.digest() == run.table().digest() and all(
-            (chk.histogram(c) == run.histogram(c)).all() for c in range(CHUNKS if args.chunks != 0 else 0))
-        if not ok:
-            raise SystemExit("PARITY FAILURE: GPU table/histograms differ from the oracle on the CPU sample")
+    parity = None
+    if not args.no_cpu:
+        n_s = max(1000 * CHUNKS * world, args.cpu_sample_reads // (1000 * CHUNKS * world) * (1000 * CHUNKS * world))
+        g_s = sample_genome(n_s)
+        chk = kmer.Engine(K, CHUNKS, HISTO_MAX, capacity_hint=int(hint * n_s / args.reads_per_gpu / world) + 1000,
+                          device=local_rank, insert_mode=_lib.INSERT_PARTITIONED if args.mode == "auto" else mode,
+                          n_ranks=world, rank=rank)
+        s_bufs, _ = make_inputs(chk, n_s, g_s)
+        chk_sh = None
+        if world > 1:
+            chk_sh = ShardedCounter(chk, dev, cpu_group=cpu_group,
+                                    arena_bytes=int(sum(t.numel() for t in s_bufs) * 8 * 1.5) + (64 << 20))
+        for c in range(CHUNKS):
+            if s_bufs[c].numel():
+                chk.ingest_device(c, s_bufs[c].data_ptr(), s_bufs[c].numel())
+        if world == 1:
+            chk.finalize()
+        else:
+            chk_sh.finalize()
+        digest = chk.digest()
+        cols = np.stack([chk.histogram(c) for c in range(CHUNKS)])
+        if world > 1:   # a table digest is a wrapping sum over entries: the global one is the sum of the partitions'
+            dg = torch.tensor([np.uint64(digest).astype(np.int64)], device=dev, dtype=torch.int64)
+            dist.all_reduce(dg)
+            digest = int(np.int64(int(dg[0])).astype(np.uint64))
+        if rank == 0:
+            run, _, dt = cpu_sample(n_s, g_s)   # the oracle: checker + CPU baseline
+            ok_digest = digest == run.table().digest()
+            ok_cols = all((cols[c] == run.histogram(c)).all() for c in range(CHUNKS))
+            parity = {"sample_reads": n_s, "ranks": world, "table_digest_equals_oracle": bool(ok_digest),
+                      "histogram_columns_equal_oracle": bool(ok_cols)}
+            if not (ok_digest and ok_cols):
+                raise SystemExit(f"PARITY FAILURE: GPU table/histograms differ from the oracle on the sample: {parity}")
+            cpu = {"value": run.n_kmers_ingested / dt, "unit": "kmers/s", "cores": 1, "kind": "port",
+                   "sample": f"{n_s} reads of the workload's generator at the workload's depth ({g_s} bp genome), same "
+                             f"k/chunks; {dt:.1f} s; the GPU result on this sample (same path as the timed region, "
+                             f"{world} rank(s)) was checked bit-exact: table digest + {CHUNKS} histogram columns"}
+            del run
         chk.close()
-        cpu = {"value": run.n_kmers_ingested / dt, "unit": "kmers/s", "cores": 1, "kind": "port",
-               "sample": f"first {args.cpu_sample_reads} reads of the workload, same k/chunks; "
-                         f"{dt:.1f} s; GPU result on this sample checked bit-exact (table digest + 10 histograms)"}
-        del run, reads
+        del s_bufs
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    def global_state():
+        """Totals and the table digest of the last run, summed over the partitions."""
+        t = eng.totals()
+        kc = sum(eng.chunk_totals(c).n_kmers for c in range(CHUNKS))
+        v = torch.tensor([int(t.n_kmers), int(t.n_unique), int(kc), int(np.uint64(eng.digest()).astype(np.int64))],
+                         device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(v)
+        return {"table_mass": int(v[0]), "distinct": int(v[1]), "windows_extracted": int(v[2]),
+                "digest": int(np.int64(int(v[3])).astype(np.uint64))}
+
     ms_dev, ms_wall, hist_dev = timed(False, args.steps, args.warmup)
     stt = eng.stage_times()
     tot = eng.totals()
-    digest_dev = eng.digest() if world == 1 else None
-    e2e = None
+    gs_dev = global_state()
+    full = {"table_mass_equals_windows_extracted": gs_dev["table_mass"] == gs_dev["windows_extracted"],   # src/io.rs:1042-1047
+            "histogram_support_equals_distinct": hist_dev is None or int(hist_dev[1:].sum()) == gs_dev["distinct"]}  # :1120-1132
     if not args.no_e2e:
         ms_e2e, ms_e2e_wall, hist_e2e = timed(True, args.steps, args.warmup)
-        if hist_dev is not None and not (hist_e2e == hist_dev).all():
-            raise SystemExit("PARITY FAILURE: host-buffer run and device-buffer run disagree")
-        if world == 1 and eng.digest() != digest_dev:
-            raise SystemExit("PARITY FAILURE: table digest differs between runs")
+        gs_e2e = global_state()
+        full["host_buffer_run_equals_device_run"] = bool((hist_dev is None or (hist_e2e == hist_dev).all())
+                                                         and gs_e2e == gs_dev)
         st2 = eng.stage_times()
         if world > 1:
             print(f"[rank {rank}] e2e h2d {st2.h2d:.1f} ms, step {ms_e2e:.1f} ms", file=sys.stderr)
+    if not all(full.values()):
+        raise SystemExit(f"PARITY FAILURE on the full-size run: {full} {gs_dev}")
+    if parity is None:
+        parity = {}
+    parity["full_size_run"] = dict(full, **{"n_ranks": world, "table_digest": f"{gs_dev['digest']:016x}",
+                                            "note": "conservation identities of src/io.rs:1042-1047,1120-1132 on the "
+                                                    "totals summed over all partitions; the digest is the wrapping sum of "
+                                                    "skm_pair_digest over every (k-mer, count) of every partition"})
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- totals over ranks ------------------------------------------------------------------------
     n_kmers_local = sum(eng.chunk_totals(c).n_kmers for c in range(CHUNKS))
     n_bases_local = in_bytes - sum(n_local)
+    n_kmers = gs_dev["windows_extracted"]
     if world > 1:
-        tt = torch.tensor([n_kmers_local, n_bases_local], device=dev, dtype=torch.int64)
+        tt = torch.tensor([n_bases_local], device=dev, dtype=torch.int64)
         dist.all_reduce(tt)
-        n_kmers, n_bases = int(tt[0]), int(tt[1])
+        n_bases = int(tt[0])
     else:
-        n_kmers, n_bases = n_kmers_local, n_bases_local
-        assert tot.n_kmers == n_kmers  # conservation: table mass == windows extracted
+        n_bases = n_bases_local
 
     if rank == 0:
         peak, peak_src = load_peaks()
         value = n_kmers / (ms_dev / 1e3)
-        # dominant kernel: the insert kernels (fused extract+insert, or list insert in partitioned mode)
-        n_ins = max(1, stt.launches[4])
-        ins_ms_per_launch = stt.insert / n_ins
-        alg_bytes_per_launch = (n_kmers_local * B_ALG_PER_KMER +
-                                (stt.insert_bases if stt.insert_bases else 0) * B_ALG_PER_BASE) / n_ins
-        if stt.insert_bases == 0:  # partitioned: the insert kernel reads the 8-byte k-mer list instead
-            alg_bytes_per_launch = n_kmers_local * (B_ALG_PER_KMER + 8.0) / n_ins
-        achieved = alg_bytes_per_launch / (ins_ms_per_launch * 1e-3) / 1e9
-        kernel_name = "extract_insert_kernel" if stt.insert_bases else "insert_runs_kernel"
+        # per-kernel roofline: algorithmic bytes (DESIGN.md §3) over the CUDA-event time of the kernel's launches
+        slots = int(stt.table_capacity)
+        kernels = {}
+
+        def add_kernel(name, ms, launches, nbytes, what):
+            if launches and ms > 0:
+                kernels[name] = {"ms_per_step": ms, "launches_per_step": int(launches), "ms_per_launch": ms / launches,
+                                 "algorithmic_bytes_per_launch": nbytes / launches, "achieved": nbytes / (ms * 1e-3) / 1e9,
+                                 "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": what}
+        if stt.insert_bases:   # direct mode
+            add_kernel("extract_insert_kernel", stt.insert, stt.launches[4],
+                       n_kmers_local * 64.0 + stt.insert_bases * 0.375,
+                       "64 B per k-mer (one random 32 B sector in and out) + 0.375 B per packed position")
+        else:
+            add_kernel("tile_insert_kernel", stt.insert, stt.launches[4], n_kmers_local * 8.0 + slots * 16.0,
+                       "8 B per k-mer (list read) + 16 B per table slot written (new table: nothing to load)")
+            add_kernel("bucket_scatter_kernel", stt.partition, stt.launches[3], in_bytes * 0.375 + n_kmers_local * 8.0,
+                       "0.375 B per position read (2-bit code + break bit) + 8 B per k-mer written")
+            add_kernel("tile_sort_kernel", stt.sort, stt.sort_launches, n_kmers_local * 16.0,
+                       "8 B per k-mer read + 8 B per k-mer written (in place)")
+        add_kernel("pack_kernel", stt.pack, stt.launches[1], in_bytes * 1.375, "1 B per position read + 0.375 B written")
+        kernel_name = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        dom = kernels[kernel_name]
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            traffic = tr["dram_bytes_per_launch"].get(kernel_name)
+        except Exception:
+            pass
+        survey_bytes = n_kmers * B_SURVEY_PER_KMER + n_bases * B_SURVEY_PER_BASE
         out = {
             "metric": "kmers_counted_per_sec", "value": value, "unit": "kmers/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
@@ -378,33 +446,47 @@ def run_ours(args):
             "ms_per_step_wall": ms_wall,
             "insert_mode": args.mode,
             "n_kmers": n_kmers, "n_distinct_rank0": int(tot.n_unique),
-            "stage_ms": {"pack": stt.pack, "count": stt.count, "partition": stt.partition, "insert": stt.insert,
-                         "histogram": stt.histogram, "grow": stt.grow, "finalize": stt.total_finalize},
-            "table": {"slots": int(stt.table_capacity), "bytes": int(stt.table_bytes),
-                      "load": float(tot.n_unique) / float(stt.table_capacity), "grows": int(stt.n_grows)},
+            "stage_ms": {"pack": stt.pack, "count": stt.count, "partition": stt.partition, "sort": stt.sort,
+                         "insert": stt.insert, "histogram": stt.histogram, "grow": stt.grow,
+                         "finalize": stt.total_finalize},
+            "table": {"slots": slots, "bytes": int(stt.table_bytes),
+                      "load": float(tot.n_unique) / float(stt.table_capacity), "grows": int(stt.n_grows),
+                      "tiled_launches": int(stt.tiled_launches), "tiled_retries": int(stt.tiled_retries)},
             "roofline": {"bound": "hbm", "kernel": kernel_name,
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_KMER[kernel_name] * n_kmers_local / n_ins,
-                         "traffic_note": "bytes per launch = DRAM read+write per k-mer from the committed ncu --set full "
-                                         "capture of this kernel (profiles/) x k-mers per launch in this run",
+                         "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                         "traffic": traffic,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the "
+                                         "committed ncu --set full capture of this workload (profiles/r02_traffic.json)",
                          "peak_source": peak_src,
-                         "launches_per_step": int(n_ins), "ms_per_launch": ins_ms_per_launch,
-                         "algorithmic_bytes": "64 B per k-mer occurrence (32 B sector in + 32 B sector out) + 8 B list read "
-                                              "(partitioned) or + 0.375 B per packed base (direct)",
-                         "kmers_per_sec_in_kernel": n_kmers_local / (stt.insert * 1e-3)},
+                         "launches_per_step": dom["launches_per_step"], "ms_per_launch": dom["ms_per_launch"],
+                         "algorithmic_bytes": dom["algorithmic_bytes"],
+                         "kernels": kernels,
+                         "step_survey_model": {
+                             "what": "whole step on SURVEY.md §8d's figure: 64 B per k-mer occurrence + 1.5 B per input base "
+                                     "(the random-sector model the tiled design replaces with streaming passes)",
+                             "achieved": survey_bytes / (ms_dev * 1e-3) / 1e9 / world,
+                             "frac": survey_bytes / (ms_dev * 1e-3) / 1e9 / world / peak},
+                         "kmers_per_sec_in_kernel": n_kmers_local / (max(stt.insert, 1e-6) * 1e-3)},
             "gpu_launches": int(stt.kernel_launches) * args.steps,
-            "nvlink_bytes_sent_per_step_rank0": (sharded.bytes_sent // max(1, (args.steps + args.warmup) * (1 if args.no_e2e else 2))) if sharded else 0,
+            "nvlink_bytes_sent_per_step_rank0": sharded.bytes_sent if sharded else 0,
+            "exchange": None if world == 1 else "copy-engine peer copies over NVLink into per-source sub-arenas at ingest time "
+                        "(no SM time); NCCL carries only the bench's barriers and all-reduces, gloo the library's all-gathers",
             "clocks": clocks,
         }
-        if args.gups:
+        if not args.no_gups:
             g = {}
             for name, var in (("load+red", 0), ("red_only", 1), ("load_only", 2), ("local_load+red", 3),
                               ("local_red_only", 4), ("local_load_only", 5), ("local_load+red32", 6)):
                 ms = eng.bench_gups(int(np.log2(stt.table_capacity)), 1 << 28, 3, var)
                 g[name] = (1 << 28) / (ms * 1e-3)
             out["gups"] = g
-            out["roofline"]["random_access_frac"] = out["roofline"]["kmers_per_sec_in_kernel"] / g["load+red"]
-        if e2e is None and not args.no_e2e:
+            # north-star ratio: whole-job k-mers/s per GPU over the part's measured random-access update rates
+            out["roofline"]["random_access_frac"] = value / world / g["load+red"]
+            out["roofline"]["random_access_frac_l2_local"] = value / world / g["local_load+red"]
+            out["roofline"]["random_access_note"] = ("k-mers/s per GPU / GUPS probe (key load + RED.ADD on 16 B slots): DRAM-resident "
+                                                      "uniform-random updates, and region-local (L2-resident) updates")
+        out["parity"] = parity
+        if not args.no_e2e:
             out["e2e"] = {"value": n_kmers / (ms_e2e / 1e3), "unit": "kmers/s",
                           "h2d_bytes_per_step": int(in_bytes) * world,
                           "d2h_bytes_per_step": int(CHUNKS * (HISTO_MAX + 2) * 8 + 64) * world,
@@ -462,10 +544,9 @@ def main():
     ap.add_argument("--cpu-sample-reads", type=int, default=CPU_SAMPLE_READS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--gups", action="store_true", help="also measure the random-access roofline probe")
-    ap.add_argument("--exchange", default="dma", choices=["dma", "p2p", "nccl"],
-                    help="multi-GPU exchange: copy engines over NVLink with a CPU control plane (dma), scatter kernel fused "
-                         "with peer stores (p2p), or NCCL all-to-all (nccl)")
+    ap.add_argument("--no-gups", action="store_true", help="skip the random-access roofline probe")
+    ap.add_argument("--gups", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--exchange", default="dma", help="(ignored: the exchange is the copy-engine path; kept for old command lines)")
     ap.add_argument("--chunks", type=int, default=None, help="EXPERIMENT ONLY: override the workload's chunk count")
     ap.add_argument("--k", type=int, default=None, help="EXPERIMENT ONLY: override k")
     args = ap.parse_args()

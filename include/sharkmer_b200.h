@@ -173,79 +173,71 @@ int32_t skm_scan_oligos(skm_ctx *ctx, const uint64_t *oligos, uint64_t n_oligos,
  * pre-counted (k-mer, count) pairs.  Allowed before or after finalize. */
 int32_t skm_insert_counts(skm_ctx *ctx, const uint64_t *keys, const uint32_t *counts, uint64_t n);
 
-/* ---- multi-GPU building blocks (one ctx per GPU; the collective between the
- * two calls is the caller's: torch.distributed / NCCL all-to-all) ----------- */
+/* ---- multi-GPU: the table sharded by k-mer hash over n_ranks GPUs ----------------------------
+ *
+ * The reference has no multi-GPU mode; this is the path BASELINE.json's north star adds (k-mers
+ * routed to the owning GPU over NVLink).  One ctx per GPU (skm_params.n_ranks / rank); every ctx
+ * ingests ITS share of the read batches with the ordinary skm_ingest_* calls and owns the k-mers
+ * whose hash falls in its contiguous hash range (skm_owner_rank, skm_common.h).
+ *
+ * Exchange.  At ingest time a batch is bucketed by (owner, table region of that owner) and
+ * tile-sorted like on one GPU; the slices of the other owners are then pushed into THEIR receive
+ * arenas by the copy engines (peer copies over NVLink/NVSwitch, no SM time, no collective): a
+ * sender owns a fixed sub-arena inside every peer's arena and allocates in it on its own, so the
+ * exchange needs no coordination and overlaps the ingest of the following batches.
+ *   skm_mg_arena_create   allocates this rank's receive arena (bytes: this rank's share of all k-mers
+ *                         x 8 B x ~1.2, plus ~3 %% for the tile offsets)
+ *   skm_mg_arena_handle   64-byte CUDA IPC handle of the arena, for peers in other processes
+ *   skm_mg_arena_ptr      the arena's device pointer, for peers in the same process
+ *   skm_mg_open_peer      maps a peer's arena from its IPC handle
+ *   skm_mg_set_peer       same from a raw device pointer (peer_device: its CUDA ordinal)
+ * Wire the arenas before the first skm_ingest_* call (batches ingested earlier are shipped at
+ * finalize instead).
+ *
+ * skm_mg_finalize is COLLECTIVE: every rank calls it once all of ITS batches are ingested.  The
+ * caller lends it one primitive, an all-gather of host bytes among the ranks (skm_comm; a barrier
+ * is an all-gather of one byte): torch.distributed / MPI / sockets across processes, or the
+ * in-process implementation of skm_group below.  It waits for the exchange, counts every chunk in
+ * order from the local lists and the arena (one tile_insert_kernel launch), runs the conservation
+ * checks of src/io.rs:1042-1047,1120-1132 on the GLOBAL totals and leaves in every ctx the
+ * histogram columns summed over all ranks (skm_histogram), while table, lookups, scans, export
+ * and skm_totals_get describe the ctx's own partition.  Results do not depend on n_ranks.
+ */
+typedef struct skm_comm {
+    void *user;
+    /* every rank contributes `bytes` bytes from `send`; `recv` receives n_ranks * bytes, in rank
+     * order.  Returns 0 on success.  Called from the thread that called skm_mg_finalize. */
+    int32_t (*allgather)(void *user, const void *send, void *recv, uint64_t bytes);
+} skm_comm;
+int32_t skm_mg_arena_create(skm_ctx *ctx, uint64_t bytes);
+int32_t skm_mg_arena_handle(skm_ctx *ctx, uint8_t *handle64);
+int32_t skm_mg_arena_ptr(skm_ctx *ctx, void **out);
+int32_t skm_mg_open_peer(skm_ctx *ctx, uint32_t peer_rank, const uint8_t *handle64);
+int32_t skm_mg_set_peer(skm_ctx *ctx, uint32_t peer_rank, void *d_ptr, int32_t peer_device);
+int32_t skm_mg_finalize(skm_ctx *ctx, const skm_comm *comm);
+/* bytes this rank pushed to its peers since create / reset */
+int32_t skm_mg_bytes_sent(skm_ctx *ctx, uint64_t *out);
 
-/* Routing of chunk `chunk_index`'s staged reads on this GPU.  K-mers are bucketed by
- * (owner rank, table region of that owner): bucket b = owner * R + region, R = regions per rank
- * (skm_route_regions), owner = floor(hash * n_ranks / 2^64) (skm_common.h).  Buckets of one owner
- * are contiguous, so the all-to-all sends contiguous ranges, and every received run is already
- * ordered by the receiver's table regions.
- *   skm_route_count   extracts the canonical k-mers and counts them per bucket
- *                     (bucket_counts[n_ranks * R]); synchronous; runs on the routing stream.
- *   skm_route_scatter writes them into d_out (device memory, sum(bucket_counts) entries) in bucket
- *                     order and drops the chunk's staged reads; asynchronous on the routing stream. */
-int32_t skm_route_regions(skm_ctx *ctx, uint32_t *regions_per_rank);
-/* The ctx's CUDA streams as cudaStream_t handles: which = 0 main (inserts, histograms; the stream
- * given in skm_params if any), 1 = routing stream (pack, bucketing, skm_route_*).  A multi-GPU
- * driver issues its collectives on the routing stream and orders the insert of chunk c after the
- * exchange of chunk c with an event, so that routing chunk c+1 overlaps inserting chunk c. */
-int32_t skm_stream_handle(skm_ctx *ctx, uint32_t which, uint64_t *out);
-int32_t skm_route_count(skm_ctx *ctx, uint32_t chunk_index, uint64_t *bucket_counts /* n_ranks * R */);
-int32_t skm_route_scatter(skm_ctx *ctx, uint32_t chunk_index, uint64_t *d_out);
-/* Asynchronous form of skm_route_count: the counts stay in device memory (*d_counts, n_ranks * R
- * u64, valid until the next route count) so that the driver can all-gather them without a host
- * round trip; skm_route_set_counts then hands the host copy back before skm_route_scatter_p2p. */
-int32_t skm_route_count_device(skm_ctx *ctx, uint32_t chunk_index, uint64_t **d_counts);
-int32_t skm_route_set_counts(skm_ctx *ctx, uint32_t chunk_index, const uint64_t *bucket_counts);
-/* Insert what the all-to-all delivered: d_kmers holds n_src blocks (one per source rank, in rank
- * order), block s = `regions` runs with lengths run_counts[s * regions + r].  Runs are inserted
- * region by region across all sources (L2-resident table regions); asynchronous on the stream. */
-int32_t skm_insert_runs_device(skm_ctx *ctx, const uint64_t *d_kmers, const uint64_t *run_counts,
-                               uint32_t n_src, uint32_t regions);
-/* Fused route + exchange over NVLink (n_ranks <= 16): instead of writing the bucketed k-mers to
- * a local list that a collective then copies, the scatter kernel stores every destination's runs
- * straight into that rank's receive arena through a CUDA-IPC mapping (peer stores, no staging).
- *   skm_p2p_arena_create   allocates this rank's receive arenas (n_slots of them: 2 = double
- *                          buffering; one per chunk lets every chunk be exchanged ahead of its insert)
- *   skm_p2p_arena_handle   64-byte CUDA IPC handle of arena `slot`, to be sent to every peer
- *   skm_p2p_open_peer      maps a peer's arena from its handle (other process, same node)
- *   skm_p2p_set_peer       same, from a raw device pointer (peer ctx in the same process)
- *   skm_route_scatter_p2p  after skm_route_count(chunk): writes rank d's buckets at element
- *                          offset dst_offsets[d] of rank d's arena `slot`; asynchronous (routing stream).
- * The caller orders the steps with a stream-ordered barrier (a 1-element all-reduce): all ranks
- * scatter(c) -> barrier -> insert(c) from their own arena (skm_insert_runs_device on
- * skm_p2p_arena_ptr).  With two slots, a slot is rewritten only after the barrier that follows the
- * owner's insert of its previous content. */
-int32_t skm_p2p_arena_create(skm_ctx *ctx, uint64_t entries_per_slot, uint32_t n_slots /* 1..16 */);
-int32_t skm_p2p_arena_handle(skm_ctx *ctx, uint32_t slot, uint8_t *handle64);
-int32_t skm_p2p_arena_ptr(skm_ctx *ctx, uint32_t slot, uint64_t **out);
-int32_t skm_p2p_open_peer(skm_ctx *ctx, uint32_t peer_rank, uint32_t slot, const uint8_t *handle64);
-int32_t skm_p2p_set_peer(skm_ctx *ctx, uint32_t peer_rank, uint32_t slot, uint64_t *d_ptr);
-int32_t skm_route_scatter_p2p(skm_ctx *ctx, uint32_t chunk_index, uint32_t slot,
-                              const uint64_t *dst_offsets /* n_ranks */);
-/* Same contract, but the k-mers are bucketed into a local list and pushed to the peers' arenas by
- * the copy engines (one peer copy per destination): the NVLink transfer costs no SM time and
- * overlaps the inserts of the previous chunk. */
-int32_t skm_route_scatter_dma(skm_ctx *ctx, uint32_t chunk_index, uint32_t slot,
-                              const uint64_t *dst_offsets /* n_ranks */);
-/* Number of leading chunks (0 .. n-1) whose staged batches have all been packed / bucketed on the
- * device already (non-blocking; meaningful once ingest is closed). */
-int32_t skm_chunks_ready(skm_ctx *ctx, uint32_t *n_ready);
-/* Block the calling host thread until the peer copies queued by skm_route_scatter_dma into
- * arena `slot` (at every destination) have landed. */
-int32_t skm_dma_wait(skm_ctx *ctx, uint32_t slot);
-/* skm_snapshot_histogram without the host wait: the column is copied in stream order (pinned
- * landing area) and skm_histogram waits for it. */
-int32_t skm_snapshot_histogram_async(skm_ctx *ctx, uint32_t chunk_i);
+/* All ranks in ONE process (what sharkmer's single-process main, src/main.rs:112-131, would drive):
+ * n ctx's on the given devices (repeats allowed: several ranks may share a GPU), arenas wired by
+ * device pointers, skm_group_finalize runs skm_mg_finalize on n threads with an in-process
+ * all-gather.  Ingest through skm_group_ctx(g, i) with the ordinary calls (rank i counts what it is
+ * given; any split of the batches over the ranks gives the same result). */
+typedef struct skm_group skm_group;
+int32_t skm_group_create(const skm_params *params /* rank, n_ranks, device are filled in per member */,
+                         uint32_t n_ranks, const int32_t *devices, uint64_t arena_bytes_per_rank,
+                         skm_group **out);
+skm_ctx *skm_group_ctx(skm_group *g, uint32_t rank);
+int32_t skm_group_finalize(skm_group *g);
+int32_t skm_group_reset(skm_group *g);
+const char *skm_group_last_error(skm_group *g);
+void skm_group_destroy(skm_group *g);
 
 /* Insert `n` k-mers (device memory) that this rank owns; asynchronous on the ctx's stream. */
 int32_t skm_insert_kmers_device(skm_ctx *ctx, const uint64_t *d_kmers, uint64_t n);
 /* Snapshot this rank's partial histogram of its table partition as column
  * `chunk_i` (the caller sums columns over ranks). */
 int32_t skm_snapshot_histogram(skm_ctx *ctx, uint32_t chunk_i);
-/* Mark ingest finished without running the chunk loop (multi-GPU driver does it). */
-int32_t skm_finalize_external(skm_ctx *ctx);
 
 /* ---- diagnostics / test entry points (same kernels, small inputs) -------- */
 

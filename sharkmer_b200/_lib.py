@@ -68,26 +68,21 @@ SYMBOLS = {
     "skm_lookup_batch": (_i32, [_vp, _vp, _u64, _u32, _i32, _vp, _vp]),
     "skm_scan_oligos": (_i32, [_vp, _vp, _u64, _u32, _u32, _vp, _vp, _u64, C.POINTER(_u64)]),
     "skm_insert_counts": (_i32, [_vp, _vp, _vp, _u64]),
-    "skm_stream_handle": (_i32, [_vp, _u32, C.POINTER(_u64)]),
-    "skm_route_regions": (_i32, [_vp, C.POINTER(_u32)]),
-    "skm_route_count": (_i32, [_vp, _u32, _vp]),
-    "skm_route_scatter": (_i32, [_vp, _u32, _vp]),
-    "skm_route_count_device": (_i32, [_vp, _u32, C.POINTER(_vp)]),
-    "skm_route_set_counts": (_i32, [_vp, _u32, _vp]),
-    "skm_p2p_arena_create": (_i32, [_vp, _u64, _u32]),
-    "skm_p2p_arena_handle": (_i32, [_vp, _u32, _vp]),
-    "skm_p2p_arena_ptr": (_i32, [_vp, _u32, C.POINTER(_vp)]),
-    "skm_p2p_open_peer": (_i32, [_vp, _u32, _u32, _vp]),
-    "skm_p2p_set_peer": (_i32, [_vp, _u32, _u32, _vp]),
-    "skm_route_scatter_p2p": (_i32, [_vp, _u32, _u32, _vp]),
-    "skm_route_scatter_dma": (_i32, [_vp, _u32, _u32, _vp]),
-    "skm_dma_wait": (_i32, [_vp, _u32]),
-    "skm_chunks_ready": (_i32, [_vp, C.POINTER(_u32)]),
-    "skm_snapshot_histogram_async": (_i32, [_vp, _u32]),
+    "skm_mg_arena_create": (_i32, [_vp, _u64]),
+    "skm_mg_arena_handle": (_i32, [_vp, _vp]),
+    "skm_mg_arena_ptr": (_i32, [_vp, C.POINTER(_vp)]),
+    "skm_mg_open_peer": (_i32, [_vp, _u32, _vp]),
+    "skm_mg_set_peer": (_i32, [_vp, _u32, _vp, _i32]),
+    "skm_mg_finalize": (_i32, [_vp, _vp]),
+    "skm_mg_bytes_sent": (_i32, [_vp, C.POINTER(_u64)]),
+    "skm_group_create": (_i32, [C.POINTER(SkmParams), _u32, _vp, _u64, C.POINTER(_vp)]),
+    "skm_group_ctx": (_vp, [_vp, _u32]),
+    "skm_group_finalize": (_i32, [_vp]),
+    "skm_group_reset": (_i32, [_vp]),
+    "skm_group_last_error": (C.c_char_p, [_vp]),
+    "skm_group_destroy": (None, [_vp]),
     "skm_insert_kmers_device": (_i32, [_vp, _vp, _u64]),
-    "skm_insert_runs_device": (_i32, [_vp, _vp, _vp, _u32, _u32]),
     "skm_snapshot_histogram": (_i32, [_vp, _u32]),
-    "skm_finalize_external": (_i32, [_vp]),
     "skm_extract_kmers": (_i32, [_vp, _u8p, _u64, _vp]),
     "skm_pack": (_i32, [_vp, _u8p, _u64, _vp, _vp]),
     "skm_synth_device": (_i32, [_vp, _u64, _u64, _u32, _u32, _u32, _u32, _u32, _u64, _u64, _vp]),

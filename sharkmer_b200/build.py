@@ -46,7 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libsharkmer_b200.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *sources()]
+    extra = os.environ.get("SKM_NVCC_EXTRA", "").split()   # experiments: e.g. -DSKM_INS_THREADS=256 -DSKM_INS_CTAS=3
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", LIB, *sources()]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:

@@ -32,9 +32,6 @@ constexpr double kHardLoad = 0.90;      // the host's upper bound on the load ne
 constexpr double kTargetLoad = 0.60;    // load at capacity_hint
 constexpr uint64_t kMinTile = 1ull << 22;  // k-mers; smallest tile worth a launch near the limit
 constexpr uint32_t kMinLog2Cap = 16;
-constexpr uint32_t kMaxRuns = 4096;     // runs per insert launch
-constexpr uint32_t kDescRing = 4;
-constexpr uint64_t kMaxListKmers = 1ull << 30;  // k-mer list budget per partition pass (8 GiB)
 
 enum Stage { ST_H2D, ST_PACK, ST_COUNT, ST_PART, ST_INSERT, ST_HISTO, ST_GROW, ST_FINALIZE, ST_SCAN, ST_SORT, ST_N };
 
@@ -58,6 +55,8 @@ struct Segment {
     uint16_t *tile_off = nullptr;         // max_tiles * (2^g2 + 1)
     uint32_t max_tiles = 0;
     bool tiled = false;
+    bool shipped = false;       // multi-GPU: the other owners' slices are on their way (or there)
+    size_t rec_first = 0;       // first of this list's n_ranks - 1 records in skm_ctx::mg_sent
 };
 
 struct ChunkState {
@@ -65,6 +64,16 @@ struct ChunkState {
     uint64_t n_bytes = 0;       // staged bytes incl. separators
     uint64_t n_windows_host = 0;
     bool counted = false;
+};
+
+// One list slice shipped to another rank: where it lies inside the sender's sub-arena at the
+// destination (byte offsets), and what it holds.  Plain data: exchanged by all-gather at finalize.
+struct MgRecord {
+    uint32_t src, dst, chunk, dead;   // dead: superseded (a capped list that overflowed and was rebuilt)
+    uint32_t regions, n_tiles;
+    uint64_t off_cells, n_cells;
+    uint64_t off_tile_off, off_cell_begin, off_tile_begin;
+    uint64_t n_kmers;
 };
 
 struct TimedSpan {
@@ -139,16 +148,16 @@ struct skm_ctx {
     bool raw_in_use[kRawRing] = {};
     uint32_t raw_next = 0;
 
-    // peer-to-peer routing: receive arenas of this rank and the peers' mapped pointers
-    static constexpr uint32_t kP2PSlots = 16;
-    uint32_t n_slots = 0;                     // arenas actually allocated
-    unsigned long long *arena[kP2PSlots] = {};
-    cudaEvent_t ev_slot[kP2PSlots] = {};      // fires when the peer copies into slot s (all destinations) are done
-    uint64_t arena_entries = 0;
-    unsigned long long *peer_arena[16][kP2PSlots] = {};
-    bool peer_ipc[16][kP2PSlots] = {};
-    std::vector<uint64_t> route_counts;  // bucket counts of the chunk last passed to skm_route_count
-    uint32_t route_counts_chunk = 0xFFFFFFFFu;
+    // multi-GPU exchange: this rank's receive arena (cut into one sub-arena per source rank) and
+    // the peers' arenas as mapped here.  A sender bump-allocates inside ITS sub-arena of every peer.
+    static constexpr uint32_t kMaxPeers = 16;
+    uint8_t *mg_arena = nullptr;
+    size_t mg_arena_bytes = 0, mg_sub_bytes = 0;
+    uint8_t *mg_peer[kMaxPeers] = {};
+    bool mg_peer_ipc[kMaxPeers] = {};
+    size_t mg_cursor[kMaxPeers] = {};          // bytes this rank has used of its sub-arena at each peer
+    std::vector<MgRecord> mg_sent;             // what this rank shipped, in order
+    uint64_t mg_bytes_sent = 0;
 
     // asynchronous snapshots of the device's occupied-slot counter
     static constexpr uint32_t kSnapRing = 8;
@@ -158,11 +167,6 @@ struct skm_ctx {
     bool snap_pending[kSnapRing] = {};
     uint32_t snap_next = 0;
     uint64_t launched_total = 0;
-
-    // run descriptors (pinned ring + device copy)
-    RunDesc *h_desc = nullptr, *d_desc = nullptr;
-    cudaEvent_t desc_event[4] = {nullptr, nullptr, nullptr, nullptr};
-    uint32_t desc_next = 0;
 
     // routing / partition scratch
     unsigned long long *d_bucket_counts = nullptr, *d_bucket_offsets = nullptr, *d_bucket_cursors = nullptr;
@@ -426,27 +430,6 @@ int32_t reserve_headroom(skm_ctx *c, uint64_t want, uint64_t *granted) {
     return SKM_OK;
 }
 
-int32_t ensure_list_on(skm_ctx *c, uint64_t n, cudaStream_t st) {
-    if (n <= c->list_cap) return SKM_OK;
-    if (c->d_list) CU(cudaFreeAsync(c->d_list, st));
-    c->d_list = nullptr;
-    c->list_cap = 0;
-    const uint64_t cap = std::max<uint64_t>(n + n / 8, 1024);
-    CU(cudaMallocAsync((void **)&c->d_list, cap * sizeof(uint64_t), st));
-    c->list_cap = cap;
-    return SKM_OK;
-}
-
-int32_t ensure_list(skm_ctx *c, uint64_t n) {
-    if (n <= c->list_cap) return SKM_OK;
-    if (c->d_list) CU(cudaFreeAsync(c->d_list, c->stream));
-    c->d_list = nullptr;
-    c->list_cap = 0;
-    CU(cudaMallocAsync((void **)&c->d_list, std::max<uint64_t>(n, 1024) * sizeof(uint64_t), c->stream));
-    c->list_cap = std::max<uint64_t>(n, 1024);
-    return SKM_OK;
-}
-
 // ---- direct mode: fused extract + insert over one segment -------------------
 int32_t insert_segment_direct(skm_ctx *c, const Segment &sg, uint32_t chunk) {
     c->recount_valid = false;
@@ -490,13 +473,6 @@ uint32_t route_log2_regions(const skm_ctx *c) {
     uint32_t l = 0;
     while (((uint64_t)c->n_ranks << (l + 1)) <= c->max_buckets) l++;
     return l;
-}
-
-uint32_t partition_log2_buckets(const skm_ctx *c) {
-    // regions of <= 2^region_log2 slots (default 2^17 = 2 MiB), at most kMaxBuckets
-    int l = (int)c->log2cap - c->region_log2;
-    if (l < 0) l = 0;
-    return std::min<uint32_t>((uint32_t)l, route_log2_regions(c));
 }
 
 struct WorkStream {  // selects the stream the bucketing helpers launch on, for the current scope
@@ -607,13 +583,11 @@ int32_t bucket_scatter_capped(skm_ctx *c, uint32_t chunk, const Segment &sg, Buc
 }
 
 #define SKM_LAUNCH_RUNS(D, H)                                                                     \
-    insert_runs_kernel<D, H><<<grid, 256, 0, c->stream>>>(descs, n_desc, single, n_dev, n_tiles, counter, \
+    insert_runs_kernel<D, H><<<grid, 256, 0, c->stream>>>(nullptr, 0, single, n_dev, n_tiles, counter, \
                                                           tref(c), c->d_gc, c->d_hist, c->p.histo_max)
-// n_tiles: number of warp tiles (ignored for a single run, where the kernel derives it from the length)
-void launch_insert_runs(skm_ctx *c, uint64_t n_tiles, const RunDesc *descs, uint32_t n_desc, RunDesc single,
-                        const unsigned long long *n_dev) {
+// One flat list (skm_insert_counts, skm_insert_kmers_device): global-memory atomics.
+void launch_insert_runs(skm_ctx *c, uint64_t n_tiles, RunDesc single, const unsigned long long *n_dev) {
     const bool h = c->track_histo;
-    // persistent grid: enough CTAs to fill the chip, never more than there are tiles
     uint64_t want = (n_tiles + 7) / 8;
     const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->sm_count * c->insert_ctas_per_sm));
     unsigned long long *counter = &c->d_gc->scratch[0];
@@ -645,7 +619,7 @@ int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_
         {
             Span sp(c, ST_INSERT, c->stream);
             RunDesc single{d_kmers + i, d_counts ? d_counts + i : nullptr, granted, 0};
-            launch_insert_runs(c, (granted + kWarpTile - 1) / kWarpTile, nullptr, 0, single,
+            launch_insert_runs(c, (granted + kWarpTile - 1) / kWarpTile, single,
                                (i == 0 && granted == n) ? n_dev : nullptr);
             c->insert_kmers += granted;
         }
@@ -653,73 +627,6 @@ int32_t insert_list(skm_ctx *c, const unsigned long long *d_kmers, const uint32_
         c->table_fresh = false;
         note_inserted(c, granted);
         i += granted;
-    }
-    return SKM_OK;
-}
-
-// Launch one kernel over runs [i, j) (tile_begin is filled in here).
-int32_t launch_run_range(skm_ctx *c, std::vector<RunDesc> &runs, size_t i, size_t j, uint64_t total) {
-    int32_t rc0 = ensure_physical(c);
-    if (rc0) return rc0;
-    c->recount_valid = false;
-    c->table_fresh = false;
-    uint64_t tiles = 0;
-    for (size_t q = i; q < j; q++) {
-        runs[q].tile_begin = tiles;
-        tiles += (runs[q].n + kWarpTile - 1) / kWarpTile;
-    }
-    // descriptors go through a small ring of pinned buffers (the copy is asynchronous)
-    const size_t n = j - i, bytes = n * sizeof(RunDesc);
-    const uint32_t slot = c->desc_next++ % kDescRing;
-    if (c->desc_event[slot]) CU(cudaEventSynchronize(c->desc_event[slot]));
-    else CU(cudaEventCreateWithFlags(&c->desc_event[slot], cudaEventDisableTiming));
-    memcpy(c->h_desc + (size_t)slot * kMaxRuns, runs.data() + i, bytes);
-    RunDesc *d_descs = c->d_desc + (size_t)slot * kMaxRuns;
-    RunDesc *h_dev = nullptr;  // device-visible alias of the pinned descriptor ring
-    CU(cudaHostGetDevicePointer((void **)&h_dev, c->h_desc, 0));
-    copy_descs_kernel<<<4, 256, 0, c->stream>>>(h_dev + (size_t)slot * kMaxRuns, d_descs, (uint32_t)n);
-    c->launches++;
-    (void)bytes;
-    {
-        Span sp(c, ST_INSERT, c->stream);
-        launch_insert_runs(c, tiles, d_descs, (uint32_t)n, RunDesc{}, nullptr);
-        c->insert_kmers += total;
-    }
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(c->desc_event[slot], c->stream));
-    note_inserted(c, total);
-    return SKM_OK;
-}
-
-// Insert a sequence of runs (host-side lengths known) in the given order, in as few launches as
-// the load-factor headroom allows (normally one).
-int32_t insert_runs(skm_ctx *c, const std::vector<RunDesc> &runs_in) {
-    std::vector<RunDesc> runs;
-    uint64_t remaining = 0;
-    for (auto r : runs_in)
-        if (r.n) {
-            runs.push_back(r);
-            remaining += r.n;
-        }
-    size_t i = 0;
-    while (i < runs.size()) {
-        uint64_t granted = 0;
-        int32_t rc = reserve_headroom(c, remaining, &granted);  // may read the exact count or grow
-        if (rc) return rc;
-        size_t j = i;
-        uint64_t sum = 0;
-        while (j < runs.size() && j - i < kMaxRuns && sum + runs[j].n <= granted) sum += runs[j++].n;
-        if (j == i) {  // the next run alone exceeds the headroom: tile it
-            rc = insert_list(c, runs[i].kmers, runs[i].counts, runs[i].n);
-            if (rc) return rc;
-            remaining -= runs[i].n;
-            i++;
-            continue;
-        }
-        rc = launch_run_range(c, runs, i, j, sum);
-        if (rc) return rc;
-        remaining -= sum;
-        i = j;
     }
     return SKM_OK;
 }
@@ -954,15 +861,18 @@ int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off
 }
 
 // ---- tiled insert ---------------------------------------------------------------------------------
-struct TiledSeg {
-    const Segment *sg;
-    uint32_t chunk;   // relative to the launch's first chunk
-};
+SegDesc local_desc(const skm_ctx *c, const Segment &sg, uint32_t chunk_rel) {
+    const ListMeta m = list_meta_at(sg.meta, sg.n_buckets);
+    return SegDesc{sg.list, sg.tile_off, m.tile_begin, m.cell_begin, c->p.rank << route_log2_regions(c), chunk_rel, 0u, 0u};
+}
+
+// dynamic shared memory one insert CTA may use so that kInsCtasPerSm of them fit an SM (227 KiB, 1 KiB reserved per CTA)
+constexpr size_t kTileInsertSmemBudget = (227 * 1024 - kInsCtasPerSm * 1024) / kInsCtasPerSm - 1024;
 
 uint32_t tiled_k_low(const skm_ctx *c, uint32_t n_chunks_l, bool histo) {
     // as many low bins in shared memory as fit beside the partition with 3 CTAs per SM
     uint32_t k = 1024;
-    while (k > 16 && tile_insert_smem_bytes(n_chunks_l, k, histo) > 74 * 1024) k >>= 1;
+    while (k > 16 && tile_insert_smem_bytes(n_chunks_l, k, histo) > kTileInsertSmemBudget) k >>= 1;
     const uint64_t want = c->p.histo_max + 2;   // no point in more bins than the histogram has
     while (k > 16 && (k >> 1) >= want) k >>= 1;
     return k;
@@ -995,7 +905,7 @@ int32_t ensure_tiled_buffers(skm_ctx *c, uint32_t n_chunks_l, size_t seg_bytes) 
 // One launch (plus retries after growth) of tile_insert_kernel over the given lists, which hold
 // chunks [chunk0, chunk0 + n_chunks_l) in chunk order.  Histogram columns of those chunks are
 // produced when the ctx tracks the histogram.  Synchronises the main stream.
-int32_t launch_tiled(skm_ctx *c, const std::vector<TiledSeg> &segs, uint32_t chunk0, uint32_t n_chunks_l) {
+int32_t launch_tiled(skm_ctx *c, const std::vector<SegDesc> &segs, uint32_t chunk0, uint32_t n_chunks_l) {
     const bool histo = c->track_histo;
     const size_t nbins = c->p.histo_max + 2;
     const uint32_t n = (uint32_t)segs.size();
@@ -1012,11 +922,7 @@ int32_t launch_tiled(skm_ctx *c, const std::vector<TiledSeg> &segs, uint32_t chu
         hfirst[ch] = at;
     }
     hfirst[n_chunks_l] = n;
-    for (uint32_t i = 0; i < n; i++) {
-        const Segment &sg = *segs[i].sg;
-        const ListMeta m = list_meta_at(sg.meta, sg.n_buckets);
-        hd[i] = SegDesc{sg.list, sg.tile_off, m.tile_begin, m.cell_begin, c->p.rank << geom.g1, segs[i].chunk};
-    }
+    for (uint32_t i = 0; i < n; i++) hd[i] = segs[i];
     {
         unsigned long long *h_dev = nullptr;
         CU(cudaHostGetDevicePointer((void **)&h_dev, c->h_segs, 0));
@@ -1153,6 +1059,8 @@ int32_t launch_tiled(skm_ctx *c, const std::vector<TiledSeg> &segs, uint32_t chu
     return SKM_OK;
 }
 
+int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index);
+
 // Bucket a freshly packed segment by table region right away (single GPU).  The work is queued
 // behind the pack kernel on the ctx's stream, so it overlaps the next batch's host-to-device copy,
 // and skm_finalize only has the inserts left.  Costs 8 B per position of HBM instead of 0.375 B;
@@ -1172,39 +1080,81 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force
     const uint32_t nb = c->n_ranks << fn.log2_regions;
     uint64_t *h_off = alloc_offsets(c, nb + 1);
     if (!h_off) return force ? fail(c, SKM_ERR_OOM, "pinned allocation failed") : SKM_OK;
-    if (c->n_ranks == 1) {
-        // single GPU: bucket by table region and tile-sort the buckets (tiled insert).  One pass
-        // (capped layout) unless the caller needs the exact layout: `force` = a capped list overflowed.
-        return build_list(c, chunk, seg_index, h_off, /*exact=*/force || !c->capped || sg.n_bytes >= (3ull << 30), force);
-    }
-    // the pack kernel ran on another stream (the copy stream): order the bucketing after it.  Only
-    // here — a wait queued for a batch that is NOT bucketed now would make everything later on this
-    // stream (e.g. the routing of chunk 0) wait for the arrival of the LAST batch.
-    CU(cudaStreamWaitEvent(c->work, sg.ready, 0));
-    if (cudaMallocAsync((void **)&sg.list, need, c->work) != cudaSuccess) {
-        cudaGetLastError();
-        sg.list = nullptr;
-        return force ? fail(c, SKM_ERR_OOM, "device allocation failed") : SKM_OK;
-    }
-    int32_t rc = bucket_count(c, chunk, seg_index, seg_index + 1, fn, nb, nullptr, nullptr);
+    // bucket by (owner, table region) and tile-sort the buckets (tiled insert).  One pass (capped
+    // layout) unless the caller needs the exact layout: `force` = a capped list overflowed.
+    // The capped layout pays a fixed slack per bucket (1024 cells): batches too small to amortise it, and
+    // batches whose bucket counts could overflow 32 bits, take the exact two-pass layout.
+    const bool exact = force || !c->capped || sg.n_bytes >= (3ull << 30) || sg.n_bytes / nb < 4096;
+    int32_t rc = build_list(c, chunk, seg_index, h_off, exact, force);
     if (rc) return rc;
-    rc = bucket_scatter(c, chunk, seg_index, seg_index + 1, fn, nb, sg.list);
-    if (rc) return rc;
-    copy_words_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_offsets, (unsigned long long *)h_off, nb + 1);
-    c->launches++;
-    if (c->n_ranks > 1) {
-        CU(cudaMallocAsync((void **)&sg.d_counts, nb * sizeof(uint64_t), c->work));
-        CU(cudaMemcpyAsync(sg.d_counts, c->d_bucket_counts, nb * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->work));
+    if (c->n_ranks > 1 && sg.list && sg.cap) rc = ship_segment(c, chunk, seg_index);  // exchange starts at ingest time
+    return rc;
+}
+
+// Multi-GPU: push the other owners' slices of a tile-sorted list into their receive arenas (peer
+// copies by the copy engines, on the dma stream, ordered after the list's `ready` event).  A capped
+// list has a fixed geometry, so nothing here waits for the device; an exact list (a capped one that
+// overflowed) is shipped from skm_mg_finalize, where its offsets are known on the host.
+int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index) {
+    Segment &sg = c->chunks[chunk].segs[seg_index];
+    if (sg.shipped || !sg.list || !sg.tiled) return SKM_OK;
+    const uint32_t me = c->p.rank, N = c->n_ranks;
+    for (uint32_t o = 0; o < N; o++)
+        if (o != me && !c->mg_peer[o]) return SKM_OK;  // arenas not wired yet: shipped at finalize
+    const uint32_t g1 = route_log2_regions(c), R = 1u << g1, F = 1u << c->g2;
+    const ListMeta m = list_meta_at(sg.meta, sg.n_buckets);
+    std::vector<uint64_t> tile_first;  // exact layout: first tile of every bucket (host copy)
+    if (!sg.cap) {
+        tile_first.assign(sg.n_buckets + 1, 0);
+        for (uint32_t b = 0; b < sg.n_buckets; b++)
+            tile_first[b + 1] = tile_first[b] + (sg.h_offsets[b + 1] - sg.h_offsets[b] + kTile - 1) / kTile;
     }
-    CU(cudaFreeAsync(sg.codes, c->work));
-    CU(cudaFreeAsync(sg.breaks, c->work));
-    sg.codes = nullptr;
-    sg.breaks = nullptr;
-    sg.h_offsets = h_off;
-    sg.n_buckets = nb;
-    sg.list_cells = sg.n_bytes;
-    c->list_bytes += need;
-    CU(cudaEventRecord(sg.ready, c->work));  // `ready` now also covers the list + offsets
+    CU(cudaStreamWaitEvent(c->dma_stream, sg.ready, 0));
+    sg.rec_first = c->mg_sent.size();
+    auto take = [&](uint32_t o, size_t bytes, uint64_t *off) -> bool {
+        const size_t at = (c->mg_cursor[o] + 255) & ~(size_t)255;
+        if (at + bytes > c->mg_sub_bytes) return false;
+        *off = at;
+        c->mg_cursor[o] = at + bytes;
+        return true;
+    };
+    for (uint32_t i = 1; i < N; i++) {
+        const uint32_t o = (me + i) % N;  // stagger the destinations across ranks
+        uint64_t cell0, n_cells, tile0, n_tiles;
+        if (sg.cap) {
+            const uint64_t tpb = (sg.cap + kTile - 1) / kTile;
+            cell0 = (uint64_t)o * R * sg.cap;
+            n_cells = (uint64_t)R * sg.cap;
+            tile0 = (uint64_t)o * R * tpb;
+            n_tiles = (uint64_t)R * tpb;
+        } else {
+            cell0 = sg.h_offsets[(size_t)o * R];
+            n_cells = sg.h_offsets[(size_t)(o + 1) * R] - cell0;
+            tile0 = tile_first[(size_t)o * R];
+            n_tiles = tile_first[(size_t)(o + 1) * R] - tile0;
+        }
+        MgRecord rec{};
+        rec.src = me;
+        rec.dst = o;
+        rec.chunk = chunk;
+        rec.regions = R;
+        rec.n_tiles = (uint32_t)n_tiles;
+        rec.n_cells = n_cells;
+        const size_t b_cells = n_cells * 8, b_off = n_tiles * (F + 1) * sizeof(uint16_t);
+        const size_t b_cb = (size_t)R * 8, b_tb = (size_t)(R + 1) * 4;
+        if (!take(o, b_cells, &rec.off_cells) || !take(o, b_off, &rec.off_tile_off) || !take(o, b_cb, &rec.off_cell_begin) ||
+            !take(o, b_tb, &rec.off_tile_begin))
+            return fail(c, SKM_ERR_OOM, "receive arena of rank %u is too small for rank %u's k-mers (%zu bytes per source): create larger arenas",
+                        o, me, c->mg_sub_bytes);
+        uint8_t *base = c->mg_peer[o] + (size_t)me * c->mg_sub_bytes;
+        if (b_cells) CU(cudaMemcpyAsync(base + rec.off_cells, sg.list + cell0, b_cells, cudaMemcpyDefault, c->dma_stream));
+        if (b_off) CU(cudaMemcpyAsync(base + rec.off_tile_off, sg.tile_off + tile0 * (F + 1), b_off, cudaMemcpyDefault, c->dma_stream));
+        CU(cudaMemcpyAsync(base + rec.off_cell_begin, m.cell_begin + (size_t)o * R, b_cb, cudaMemcpyDefault, c->dma_stream));
+        CU(cudaMemcpyAsync(base + rec.off_tile_begin, m.tile_begin + (size_t)o * R, b_tb, cudaMemcpyDefault, c->dma_stream));
+        c->mg_bytes_sent += b_cells + b_off + b_cb + b_tb;
+        c->mg_sent.push_back(rec);
+    }
+    sg.shipped = true;
     return SKM_OK;
 }
 
@@ -1417,8 +1367,6 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     c->h_pinned_words = kMaxBuckets + 16;
     CU(cudaMallocHost((void **)&c->h_pinned, c->h_pinned_words * sizeof(uint64_t)));
     CU(cudaMallocHost((void **)&c->h_snap, skm_ctx::kSnapRing * sizeof(uint64_t)));
-    CU(cudaMallocHost((void **)&c->h_desc, (size_t)kDescRing * kMaxRuns * sizeof(RunDesc)));
-    CU(cudaMalloc((void **)&c->d_desc, (size_t)kDescRing * kMaxRuns * sizeof(RunDesc)));
     CU(cudaMalloc((void **)&c->d_bucket_counts, (kMaxBuckets + 1) * sizeof(uint64_t)));
     CU(cudaMalloc((void **)&c->d_bucket_offsets, (kMaxBuckets + 1) * sizeof(uint64_t)));
     CU(cudaMalloc((void **)&c->d_bucket_cursors, (kMaxBuckets + 1) * sizeof(uint64_t)));
@@ -1451,8 +1399,8 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     }
     CU(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)tile_sort_smem_bytes(kMaxSubLog2)));
-    CU(cudaFuncSetAttribute(tile_insert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(tile_insert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(tile_insert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileInsertSmemBudget));
+    CU(cudaFuncSetAttribute(tile_insert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileInsertSmemBudget));
     CU(cudaStreamSynchronize(c->stream));
     return SKM_OK;
 }
@@ -1485,13 +1433,9 @@ void skm_destroy(skm_ctx *c) {
         cudaFree(c->d_bins);
         cudaFree(c->d_hist);
         cudaFree(c->d_tot);
-        for (uint32_t r = 0; r < 16; r++)
-            for (uint32_t sl = 0; sl < skm_ctx::kP2PSlots; sl++)
-                if (c->peer_ipc[r][sl]) cudaIpcCloseMemHandle(c->peer_arena[r][sl]);
-        for (uint32_t sl = 0; sl < skm_ctx::kP2PSlots; sl++) {
-            cudaFree(c->arena[sl]);
-            if (c->ev_slot[sl]) cudaEventDestroy(c->ev_slot[sl]);
-        }
+        for (uint32_t r = 0; r < skm_ctx::kMaxPeers; r++)
+            if (c->mg_peer_ipc[r]) cudaIpcCloseMemHandle(c->mg_peer[r]);
+        cudaFree(c->mg_arena);
         for (uint32_t i = 0; i < skm_ctx::kRawRing; i++) {
             cudaFree(c->raw_buf[i]);
             if (c->raw_copied[i]) cudaEventDestroy(c->raw_copied[i]);
@@ -1503,9 +1447,6 @@ void skm_destroy(skm_ctx *c) {
         cudaFreeHost(c->h_cols);
         cudaFreeHost(c->h_snap);
         for (auto e : c->snap_event) if (e) cudaEventDestroy(e);
-        cudaFree(c->d_desc);
-        cudaFreeHost(c->h_desc);
-        for (auto e : c->desc_event) if (e) cudaEventDestroy(e);
         cudaFree(c->d_bucket_counts);
         cudaFree(c->d_bucket_offsets);
         cudaFree(c->d_bucket_cursors);
@@ -1682,29 +1623,19 @@ int32_t skm_sync(skm_ctx *c) {
     return check_sticky(c);
 }
 
-static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
+static int32_t finalize_common(skm_ctx *c) {
     if (c->finalized) return fail(c, SKM_ERR_STATE, "finalize called twice");
+    if (c->n_ranks > 1) return fail(c, SKM_ERR_STATE, "a ctx with n_ranks > 1 is finalized with skm_mg_finalize (collective)");
     bool any = false;
     for (auto &cs : c->chunks) any = any || !cs.segs.empty();
     int32_t rc;
-    if (any && !run_chunk_loop) {
-        // multi-GPU driver takes over: routing runs on the same stream as the pack kernels, so it
-        // is ordered after them without waiting here; errors surface at the driver's final skm_sync
-        c->finalized = true;
-        return SKM_OK;
-    }
-    if (!any || !run_chunk_loop) {
-        // nothing to overlap: wait for the ingest streams, then report errors / hand over
+    if (!any) {
         rc = sync_all(c);
         if (rc) return rc;
-        rc = check_sticky(c);  // an invalid base aborts the run
+        rc = check_sticky(c);
         if (rc) return rc;
-        rc = refresh_chunk_counters(c);
-        if (rc) return rc;
-        if (!any && run_chunk_loop)  // src/io.rs:578-580 (every non-empty batch holds at least one read)
-            return fail(c, SKM_ERR_NO_READS, "No reads were ingested. Check that input files contain valid FASTQ records.");
-        c->finalized = true;
-        return SKM_OK;
+        // src/io.rs:578-580 (every non-empty batch holds at least one read)
+        return fail(c, SKM_ERR_NO_READS, "No reads were ingested. Check that input files contain valid FASTQ records.");
     }
     c->finalized = true;
     // The chunk loop starts while later batches may still be packing / bucketing on part_stream:
@@ -1734,7 +1665,8 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
             }
         }
     }
-    std::vector<TiledSeg> group;      // lists of consecutive chunks, to be counted by one tiled launch
+    std::vector<SegDesc> group;       // lists of consecutive chunks, to be counted by one tiled launch
+    std::vector<Segment *> group_segs;
     uint32_t group_chunk0 = 0;
     auto flush_group = [&](uint32_t end_chunk) -> int32_t {
         if (group.empty()) {
@@ -1744,8 +1676,8 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
         const uint32_t n_l = end_chunk - group_chunk0;
         int32_t r = launch_tiled(c, group, group_chunk0, n_l);
         if (r) return r;
-        for (auto &ts : group) {
-            Segment &sg = *const_cast<Segment *>(ts.sg);
+        for (Segment *psg : group_segs) {
+            Segment &sg = *psg;
             uint64_t nk = 0;
             if (sg.cap) for (uint32_t b = 0; b < sg.n_buckets; b++) nk += sg.h_offsets[b];
             else nk = sg.h_offsets[sg.n_buckets];
@@ -1753,6 +1685,7 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
             release_list(c, sg, c->stream);
         }
         group.clear();
+        group_segs.clear();
         group_chunk0 = end_chunk;
         return SKM_OK;
     };
@@ -1819,24 +1752,23 @@ static int32_t finalize_common(skm_ctx *c, bool run_chunk_loop) {
         if (n_listed * nbr_now > kMaxVseg) {
             // more lists in one chunk than a launch can read: count them in several launches of this
             // chunk alone (the order inside a chunk does not matter)
-            std::vector<TiledSeg> part;
             for (auto &sg : cs.segs) {
                 if (!(sg.list && sg.tiled)) continue;
-                part.push_back(TiledSeg{&sg, 0});
-                if ((part.size() + 1) * nbr_now > kMaxVseg) {
-                    group.swap(part);
-                    group_chunk0 = ch;
+                if ((group.size() + 1) * nbr_now > kMaxVseg) {
                     // (columns of chunk ch are rewritten by every partial launch; the last one is complete)
                     rc = flush_group(ch + 1);
                     if (rc) return rc;
-                    part.clear();
+                    group_chunk0 = ch;
                 }
+                group.push_back(local_desc(c, sg, 0));
+                group_segs.push_back(&sg);
             }
-            group.swap(part);
-            group_chunk0 = ch;
         } else {
             for (auto &sg : cs.segs)
-                if (sg.list && sg.tiled) group.push_back(TiledSeg{&sg, ch - group_chunk0});
+                if (sg.list && sg.tiled) {
+                    group.push_back(local_desc(c, sg, ch - group_chunk0));
+                    group_segs.push_back(&sg);
+                }
         }
         // (4) what is still packed goes through the direct kernel (small inputs, or no memory for a list);
         //     a chunk's lists are counted first, so that the chunk's column is complete afterwards
@@ -1940,7 +1872,7 @@ int32_t skm_finalize(skm_ctx *c) {
     if (!c) return SKM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    return finalize_common(c, true);
+    return finalize_common(c);
 }
 
 int32_t skm_reset(skm_ctx *c) {
@@ -1960,6 +1892,9 @@ int32_t skm_reset(skm_ctx *c) {
         }
         cs = ChunkState{};
     }
+    for (auto &cur : c->mg_cursor) cur = 0;
+    c->mg_sent.clear();
+    c->mg_bytes_sent = 0;
     // the clear is deferred (ensure_physical): a tiled insert never needs it
     c->table_fresh = true;
     c->table_zombie = true;
@@ -1997,47 +1932,6 @@ int32_t skm_reset(skm_ctx *c) {
     c->h_cc.assign(c->n_chunks, ChunkCounters{});
     c->err.clear();
     return SKM_OK;
-}
-
-int32_t skm_snapshot_histogram_async(skm_ctx *c, uint32_t chunk_i) {
-    if (!c) return SKM_ERR_INVALID_ARG;
-    if (chunk_i >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
-    return snapshot_histogram(c, chunk_i);  // stream-ordered; skm_histogram waits for it
-}
-
-int32_t skm_chunks_ready(skm_ctx *c, uint32_t *n_ready) {
-    if (!c || !n_ready) return SKM_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
-    uint32_t n = 0;
-    for (; n < c->n_chunks; n++) {
-        bool ok = true;
-        for (auto &sg : c->chunks[n].segs)
-            if (sg.ready && cudaEventQuery(sg.ready) != cudaSuccess) {
-                ok = false;
-                break;
-            }
-        if (!ok) break;
-    }
-    cudaGetLastError();  // cudaErrorNotReady is not an error
-    *n_ready = n;
-    return SKM_OK;
-}
-
-int32_t skm_dma_wait(skm_ctx *c, uint32_t slot) {
-    if (!c || slot >= skm_ctx::kP2PSlots || !c->ev_slot[slot]) return SKM_ERR_INVALID_ARG;
-    DeviceGuard g(c->device);
-    CU(cudaEventSynchronize(c->ev_slot[slot]));
-    return SKM_OK;
-}
-
-int32_t skm_finalize_external(skm_ctx *c) {
-    if (!c) return SKM_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
-    return finalize_common(c, false);
 }
 
 int32_t skm_histogram(skm_ctx *c, uint32_t chunk_i, uint64_t *out, uint64_t out_len) {
@@ -2333,460 +2227,7 @@ int32_t skm_insert_counts(skm_ctx *c, const uint64_t *keys, const uint32_t *coun
     return SKM_OK;
 }
 
-// ---- multi-GPU building blocks -------------------------------------------------
-
-int32_t skm_stream_handle(skm_ctx *c, uint32_t which, uint64_t *out) {
-    if (!c || !out || which > 1) return SKM_ERR_INVALID_ARG;
-    *out = (uint64_t)(uintptr_t)(which == 0 ? c->stream : c->part_stream);
-    return SKM_OK;
-}
-
-int32_t skm_route_regions(skm_ctx *c, uint32_t *regions_per_rank) {
-    if (!c || !regions_per_rank) return SKM_ERR_INVALID_ARG;
-    *regions_per_rank = 1u << route_log2_regions(c);
-    return SKM_OK;
-}
-
-
-}  // extern "C" (helpers below are internal)
-
-namespace {
-
-// Make sure every segment of the chunk is in bucketed form (list + offsets + device counts).
-int32_t bucketed_chunk(skm_ctx *c, uint32_t chunk) {
-    ChunkState &cs = c->chunks[chunk];
-    for (size_t i = 0; i < cs.segs.size(); i++) {
-        Segment &sg = cs.segs[i];
-        if (sg.list && sg.cap) {
-            // capped single-GPU layout, but the routing API wants exact contiguous blocks (a sharded
-            // driver with one rank): undo it — the packed form is still there — and bucket exactly
-            int32_t rc = drop_capped_list(c, chunk, sg, c->work);
-            if (rc) return rc;
-        }
-        if (sg.list) continue;
-        int32_t rc = eager_partition(c, chunk, i, true);
-        if (rc) return rc;
-    }
-    return SKM_OK;
-}
-
-// Host copy of the chunk's per-bucket counts (waits for the bucketing of its segments).
-int32_t chunk_counts_host(skm_ctx *c, uint32_t chunk, std::vector<uint64_t> &counts) {
-    ChunkState &cs = c->chunks[chunk];
-    const uint32_t nb = c->n_ranks << route_log2_regions(c);
-    counts.assign(nb, 0);
-    for (auto &sg : cs.segs) {
-        if (!sg.list) continue;
-        CU(cudaEventSynchronize(sg.ready));
-        for (uint32_t b = 0; b < nb; b++) counts[b] += sg.h_offsets[b + 1] - sg.h_offsets[b];
-    }
-    return SKM_OK;
-}
-
-// Copy pieces with the descriptor-driven copy kernel on `st`.
-int32_t launch_copy(skm_ctx *c, std::vector<CopyDesc> &pieces, cudaStream_t st) {
-    size_t i = 0;
-    while (i < pieces.size()) {
-        const size_t j = std::min(pieces.size(), i + kMaxRuns);
-        uint64_t tiles = 0;
-        for (size_t q = i; q < j; q++) {
-            pieces[q].tile_begin = tiles;
-            tiles += (pieces[q].n + kCopyTile - 1) / kCopyTile;
-        }
-        static_assert(sizeof(CopyDesc) == sizeof(RunDesc), "descriptor rings are shared");
-        const uint32_t slot = c->desc_next++ % kDescRing;
-        if (c->desc_event[slot]) CU(cudaEventSynchronize(c->desc_event[slot]));
-        else CU(cudaEventCreateWithFlags(&c->desc_event[slot], cudaEventDisableTiming));
-        memcpy(c->h_desc + (size_t)slot * kMaxRuns, pieces.data() + i, (j - i) * sizeof(CopyDesc));
-        RunDesc *h_dev = nullptr;
-        CU(cudaHostGetDevicePointer((void **)&h_dev, c->h_desc, 0));
-        RunDesc *d_descs = c->d_desc + (size_t)slot * kMaxRuns;
-        copy_descs_kernel<<<4, 256, 0, st>>>(h_dev + (size_t)slot * kMaxRuns, d_descs, (uint32_t)(j - i));
-        unsigned long long *counter = &c->d_gc->scratch[1];
-        zero_async(c, counter, sizeof(unsigned long long), st);
-        const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((tiles + 7) / 8, (uint64_t)c->sm_count * 4));
-        {
-            Span sp(c, ST_PART, st);
-            copy_runs_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const CopyDesc *>(d_descs), (uint32_t)(j - i), tiles, counter);
-            c->launches += 2;
-            c->stage_launches[ST_PART]++;
-        }
-        CU(cudaGetLastError());
-        CU(cudaEventRecord(c->desc_event[slot], st));
-        i = j;
-    }
-    return SKM_OK;
-}
-
-// Pieces that move a bucketed chunk to its destinations: for every owner o, region-major over the
-// chunk's segments, into dst_base[o] (contiguous).  Adjacent pieces that are contiguous on both
-// sides are merged (one segment => one piece per destination).
-void build_pieces(skm_ctx *c, uint32_t chunk, unsigned long long *const *dst_base, std::vector<CopyDesc> &out) {
-    ChunkState &cs = c->chunks[chunk];
-    const uint32_t regions = 1u << route_log2_regions(c);
-    for (uint32_t o = 0; o < c->n_ranks; o++) {
-        uint64_t at = 0;
-        for (uint32_t r = 0; r < regions; r++)
-            for (auto &sg : cs.segs) {
-                if (!sg.list) continue;
-                const uint32_t b = o * regions + r;
-                const uint64_t n = sg.h_offsets[b + 1] - sg.h_offsets[b];
-                if (!n) continue;
-                const unsigned long long *src = sg.list + sg.h_offsets[b];
-                unsigned long long *dst = dst_base[o] + at;
-                if (!out.empty() && out.back().src + out.back().n == src && out.back().dst + out.back().n == dst)
-                    out.back().n += n;
-                else
-                    out.push_back(CopyDesc{src, dst, n, 0});
-                at += n;
-            }
-    }
-}
-
-int32_t drop_chunk_lists(skm_ctx *c, uint32_t chunk, cudaStream_t st) {
-    ChunkState &cs = c->chunks[chunk];
-    for (auto &sg : cs.segs) {
-        if (sg.list) {
-            CU(cudaFreeAsync(sg.list, st));
-            c->list_bytes -= std::min<size_t>(c->list_bytes, sg.n_bytes * sizeof(uint64_t));
-        }
-        if (sg.d_counts) CU(cudaFreeAsync(sg.d_counts, st));
-        sg.list = nullptr;
-        sg.d_counts = nullptr;
-    }
-    cs.counted = true;
-    return SKM_OK;
-}
-
-}  // namespace
-
-extern "C" {
-
-int32_t skm_route_count(skm_ctx *c, uint32_t chunk, uint64_t *bucket_counts) {
-    if (!c || !bucket_counts) return SKM_ERR_INVALID_ARG;
-    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
-    WorkStream ws(c, c->part_stream);  // routing overlaps the inserts of the previous chunk (main stream)
-    ChunkState &cs = c->chunks[chunk];
-    if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
-    for (auto &sg : cs.segs)  // this chunk's pack kernels (copy stream) must have fired; later chunks may still be arriving
-        if (sg.ready) CU(cudaStreamWaitEvent(c->part_stream, sg.ready, 0));
-    uint64_t total = 0;
-    const BucketFn fn = route_fn(c);
-    const uint32_t nb = c->n_ranks << fn.log2_regions;
-    if (c->eager) {  // batches are bucketed at ingest time: the counts are the list offsets
-        int32_t rc = bucketed_chunk(c, chunk);
-        if (rc) return rc;
-        rc = chunk_counts_host(c, chunk, c->route_counts);
-        if (rc) return rc;
-        memcpy(bucket_counts, c->route_counts.data(), nb * sizeof(uint64_t));
-        c->route_counts_chunk = chunk;
-        return SKM_OK;
-    }
-    int32_t rc = bucket_count(c, chunk, 0, cs.segs.size(), fn, nb, &total, bucket_counts);
-    if (rc) return rc;
-    c->route_counts.assign(bucket_counts, bucket_counts + nb);
-    c->route_counts_chunk = chunk;
-    return SKM_OK;
-}
-
-int32_t skm_route_count_device(skm_ctx *c, uint32_t chunk, uint64_t **d_counts) {
-    if (!c || !d_counts) return SKM_ERR_INVALID_ARG;
-    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
-    WorkStream ws(c, c->part_stream);
-    ChunkState &cs = c->chunks[chunk];
-    if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
-    for (auto &sg : cs.segs)  // this chunk's pack kernels (copy stream) must have fired; later chunks may still be arriving
-        if (sg.ready) CU(cudaStreamWaitEvent(c->part_stream, sg.ready, 0));
-    const BucketFn fn = route_fn(c);
-    const uint32_t nb = c->n_ranks << fn.log2_regions;
-    int32_t rc;
-    if (c->eager) {  // sum the per-segment counts left on the device by the ingest-time bucketing
-        rc = bucketed_chunk(c, chunk);
-        if (rc) return rc;
-        zero_async(c, c->d_bucket_counts, nb * sizeof(uint64_t), c->work);
-        for (auto &sg : cs.segs) {
-            if (!sg.d_counts) continue;
-            CU(cudaStreamWaitEvent(c->work, sg.ready, 0));
-            add_counts_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_counts, sg.d_counts, nb);
-            c->launches++;
-        }
-        CU(cudaGetLastError());
-    } else {
-        rc = bucket_count(c, chunk, 0, cs.segs.size(), fn, nb, nullptr, nullptr);
-        if (rc) return rc;
-    }
-    *d_counts = (uint64_t *)c->d_bucket_counts;  // valid until the next route count on this ctx
-    c->route_counts_chunk = 0xFFFFFFFFu;
-    return SKM_OK;  // asynchronous (routing stream)
-}
-
-int32_t skm_route_set_counts(skm_ctx *c, uint32_t chunk, const uint64_t *bucket_counts) {
-    if (!c || !bucket_counts) return SKM_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> lk(c->mu);
-    const uint32_t nb = c->n_ranks << route_log2_regions(c);
-    c->route_counts.assign(bucket_counts, bucket_counts + nb);
-    c->route_counts_chunk = chunk;
-    return SKM_OK;
-}
-
-int32_t skm_route_scatter(skm_ctx *c, uint32_t chunk, uint64_t *d_out) {
-    if (!c) return SKM_ERR_INVALID_ARG;
-    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
-    WorkStream ws(c, c->part_stream);  // routing overlaps the inserts of the previous chunk (main stream)
-    ChunkState &cs = c->chunks[chunk];
-    if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
-    const BucketFn fn = route_fn(c);
-    int32_t rc;
-    if (c->eager) {  // already bucketed: gather the segments' runs into d_out, bucket-major
-        rc = bucketed_chunk(c, chunk);
-        if (rc) return rc;
-        std::vector<uint64_t> counts;
-        rc = chunk_counts_host(c, chunk, counts);
-        if (rc) return rc;
-        const uint32_t regions = 1u << fn.log2_regions;
-        std::vector<unsigned long long *> base(c->n_ranks);
-        uint64_t at = 0;
-        for (uint32_t o = 0; o < c->n_ranks; o++) {
-            base[o] = (unsigned long long *)d_out + at;
-            for (uint32_t r = 0; r < regions; r++) at += counts[(size_t)o * regions + r];
-        }
-        std::vector<CopyDesc> pieces;
-        build_pieces(c, chunk, base.data(), pieces);
-        rc = launch_copy(c, pieces, c->work);
-        if (rc) return rc;
-        return drop_chunk_lists(c, chunk, c->work);
-    }
-    rc = bucket_scatter(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions,
-                        (unsigned long long *)d_out);
-    if (rc) return rc;
-    for (auto &sg : cs.segs) {
-        CU(cudaFreeAsync(sg.codes, c->work));
-        CU(cudaFreeAsync(sg.breaks, c->work));
-        sg.codes = nullptr;
-        sg.breaks = nullptr;
-    }
-    cs.counted = true;
-    return SKM_OK;  // asynchronous: ordered on the ctx's stream
-}
-
-int32_t skm_p2p_arena_create(skm_ctx *c, uint64_t entries_per_slot, uint32_t n_slots) {
-    if (!c || entries_per_slot == 0 || n_slots == 0 || n_slots > skm_ctx::kP2PSlots) return SKM_ERR_INVALID_ARG;
-    if (c->n_ranks > kMaxP2PRanks) return fail(c, SKM_ERR_INVALID_ARG, "peer-to-peer routing supports at most %u ranks", kMaxP2PRanks);
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
-    CU(cudaStreamSynchronize(c->stream));
-    for (uint32_t sl = 0; sl < skm_ctx::kP2PSlots; sl++) {
-        if (c->arena[sl]) CU(cudaFree(c->arena[sl]));
-        c->arena[sl] = nullptr;
-        if (sl >= n_slots) continue;
-        // cudaMalloc, not the stream-ordered pool: the block must be exportable through CUDA IPC
-        CU(cudaMalloc((void **)&c->arena[sl], entries_per_slot * sizeof(uint64_t)));
-        c->peer_arena[c->p.rank][sl] = c->arena[sl];
-        if (!c->ev_slot[sl]) CU(cudaEventCreateWithFlags(&c->ev_slot[sl], cudaEventDisableTiming));
-    }
-    c->n_slots = n_slots;
-    c->arena_entries = entries_per_slot;
-    return SKM_OK;
-}
-
-int32_t skm_p2p_arena_handle(skm_ctx *c, uint32_t slot, uint8_t *handle64) {
-    if (!c || !handle64 || slot >= skm_ctx::kP2PSlots) return SKM_ERR_INVALID_ARG;
-    if (!c->arena[slot]) return fail(c, SKM_ERR_STATE, "no arena: call skm_p2p_arena_create first");
-    DeviceGuard g(c->device);
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
-    cudaIpcMemHandle_t h;
-    CU(cudaIpcGetMemHandle(&h, c->arena[slot]));
-    memcpy(handle64, &h, 64);
-    return SKM_OK;
-}
-
-int32_t skm_p2p_arena_ptr(skm_ctx *c, uint32_t slot, uint64_t **out) {
-    if (!c || !out || slot >= skm_ctx::kP2PSlots) return SKM_ERR_INVALID_ARG;
-    *out = (uint64_t *)c->arena[slot];
-    return SKM_OK;
-}
-
-int32_t skm_p2p_open_peer(skm_ctx *c, uint32_t peer_rank, uint32_t slot, const uint8_t *handle64) {
-    if (!c || !handle64 || slot >= skm_ctx::kP2PSlots || peer_rank >= c->n_ranks || peer_rank >= kMaxP2PRanks)
-        return SKM_ERR_INVALID_ARG;
-    if (peer_rank == c->p.rank) return SKM_OK;  // own arena is already set
-    DeviceGuard g(c->device);
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handle64, 64);
-    void *p = nullptr;
-    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-    c->peer_arena[peer_rank][slot] = (unsigned long long *)p;
-    c->peer_ipc[peer_rank][slot] = true;
-    return SKM_OK;
-}
-
-int32_t skm_p2p_set_peer(skm_ctx *c, uint32_t peer_rank, uint32_t slot, uint64_t *d_ptr) {
-    if (!c || slot >= skm_ctx::kP2PSlots || peer_rank >= c->n_ranks || peer_rank >= kMaxP2PRanks)
-        return SKM_ERR_INVALID_ARG;
-    c->peer_arena[peer_rank][slot] = (unsigned long long *)d_ptr;
-    c->peer_ipc[peer_rank][slot] = false;
-    return SKM_OK;
-}
-
-int32_t skm_route_scatter_p2p(skm_ctx *c, uint32_t chunk, uint32_t slot, const uint64_t *dst_offsets) {
-    if (!c || !dst_offsets || slot >= skm_ctx::kP2PSlots) return SKM_ERR_INVALID_ARG;
-    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
-    WorkStream ws(c, c->part_stream);  // routing overlaps the inserts of the previous chunk (main stream)
-    ChunkState &cs = c->chunks[chunk];
-    if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
-    if (c->route_counts_chunk != chunk) return fail(c, SKM_ERR_STATE, "call skm_route_count for chunk %u first", chunk);
-    const BucketFn fn = route_fn(c);
-    const uint32_t regions = 1u << fn.log2_regions;
-    OwnerBases bases{};
-    bases.log2_regions = fn.log2_regions;
-    bases.uniform = 0;
-    uint64_t start = 0;  // first cell of owner o's buckets in the global cursor numbering
-    for (uint32_t o = 0; o < c->n_ranks; o++) {
-        uint64_t n_o = 0;
-        for (uint32_t r = 0; r < regions; r++) n_o += c->route_counts[(size_t)o * regions + r];
-        if (!c->peer_arena[o][slot]) return fail(c, SKM_ERR_STATE, "peer %u arena %u not mapped", o, slot);
-        if (dst_offsets[o] + n_o > c->arena_entries)
-            return fail(c, SKM_ERR_INVALID_ARG, "receive arena of rank %u too small (%llu + %llu > %llu entries)", o,
-                        (unsigned long long)dst_offsets[o], (unsigned long long)n_o, (unsigned long long)c->arena_entries);
-        bases.dst[o] = c->peer_arena[o][slot] + dst_offsets[o] - start;
-        start += n_o;
-    }
-    if (c->eager) {  // already bucketed at ingest time: a copy kernel pushes the runs (peer stores)
-        int32_t rc2 = bucketed_chunk(c, chunk);
-        if (rc2) return rc2;
-        for (auto &sg : cs.segs)
-            if (sg.list) CU(cudaEventSynchronize(sg.ready));
-        std::vector<unsigned long long *> base(c->n_ranks);
-        for (uint32_t o = 0; o < c->n_ranks; o++) base[o] = c->peer_arena[o][slot] + dst_offsets[o];
-        std::vector<CopyDesc> pieces;
-        build_pieces(c, chunk, base.data(), pieces);
-        rc2 = launch_copy(c, pieces, c->work);
-        if (rc2) return rc2;
-        return drop_chunk_lists(c, chunk, c->work);
-    }
-    int32_t rc = bucket_scatter(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions, nullptr, &bases);
-    if (rc) return rc;
-    for (auto &sg : cs.segs) {
-        CU(cudaFreeAsync(sg.codes, c->work));
-        CU(cudaFreeAsync(sg.breaks, c->work));
-        sg.codes = nullptr;
-        sg.breaks = nullptr;
-    }
-    cs.counted = true;
-    return SKM_OK;  // asynchronous: ordered on the ctx's stream
-}
-
-// Exchange by copy engines: bucket into the local list (SM work, routing stream), then one peer
-// copy per destination on the copy stream — the NVLink transfer costs no SM time and overlaps the
-// inserts.  Same arenas, offsets and barrier protocol as skm_route_scatter_p2p.
-int32_t skm_route_scatter_dma(skm_ctx *c, uint32_t chunk, uint32_t slot, const uint64_t *dst_offsets) {
-    if (!c || !dst_offsets || slot >= skm_ctx::kP2PSlots) return SKM_ERR_INVALID_ARG;
-    if (chunk >= c->n_chunks) return fail(c, SKM_ERR_INVALID_ARG, "chunk_index out of range");
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
-    WorkStream ws(c, c->part_stream);
-    ChunkState &cs = c->chunks[chunk];
-    if (cs.counted) return fail(c, SKM_ERR_STATE, "chunk %u already routed", chunk);
-    if (c->route_counts_chunk != chunk) return fail(c, SKM_ERR_STATE, "call skm_route_count for chunk %u first", chunk);
-    const BucketFn fn = route_fn(c);
-    const uint32_t regions = 1u << fn.log2_regions;
-    std::vector<uint64_t> n_to(c->n_ranks, 0);
-    uint64_t total = 0;
-    for (uint32_t o = 0; o < c->n_ranks; o++) {
-        for (uint32_t r = 0; r < regions; r++) n_to[o] += c->route_counts[(size_t)o * regions + r];
-        if (!c->peer_arena[o][slot]) return fail(c, SKM_ERR_STATE, "peer %u arena %u not mapped", o, slot);
-        if (dst_offsets[o] + n_to[o] > c->arena_entries)
-            return fail(c, SKM_ERR_INVALID_ARG, "receive arena of rank %u too small", o);
-        total += n_to[o];
-    }
-    if (c->eager) {  // already bucketed: copy engines push each destination's block (one segment),
-                     // or the copy kernel merges several segments region-major
-        int32_t rc2 = bucketed_chunk(c, chunk);
-        if (rc2) return rc2;
-        size_t n_seg = 0;
-        for (auto &sg : cs.segs)
-            if (sg.list) {
-                CU(cudaEventSynchronize(sg.ready));
-                n_seg++;
-            }
-        std::vector<unsigned long long *> base(c->n_ranks);
-        for (uint32_t o = 0; o < c->n_ranks; o++) base[o] = c->peer_arena[o][slot] + dst_offsets[o];
-        std::vector<CopyDesc> pieces;
-        build_pieces(c, chunk, base.data(), pieces);
-        if (n_seg <= 1) {
-            // (the segment was bucketed on the routing stream and `ready` has fired: the lists are complete)
-            for (size_t i = 0; i < pieces.size(); i++) {
-                const CopyDesc &d = pieces[(i + c->p.rank + 1) % pieces.size()];  // stagger destinations
-                CU(cudaMemcpyAsync(d.dst, d.src, d.n * sizeof(uint64_t), cudaMemcpyDefault, c->dma_stream));
-            }
-            CU(cudaEventRecord(c->ev_slot[slot], c->dma_stream));
-            CU(cudaEventRecord(c->ev_dma, c->dma_stream));
-            return drop_chunk_lists(c, chunk, c->dma_stream);  // freed once the copies have read them
-        }
-        rc2 = launch_copy(c, pieces, c->work);
-        if (rc2) return rc2;
-        CU(cudaEventRecord(c->ev_slot[slot], c->work));
-        return drop_chunk_lists(c, chunk, c->work);
-    }
-    // the previous chunk's peer copies read the list: they must be done before it is rewritten
-    CU(cudaStreamWaitEvent(c->part_stream, c->ev_dma, 0));
-    int32_t rc = ensure_list_on(c, total, c->part_stream);
-    if (rc) return rc;
-    rc = bucket_scatter(c, chunk, 0, cs.segs.size(), fn, c->n_ranks << fn.log2_regions, c->d_list);
-    if (rc) return rc;
-    for (auto &sg : cs.segs) {
-        CU(cudaFreeAsync(sg.codes, c->work));
-        CU(cudaFreeAsync(sg.breaks, c->work));
-        sg.codes = nullptr;
-        sg.breaks = nullptr;
-    }
-    cs.counted = true;
-    // copies: dma stream waits for the scatter, then the routing stream waits for the copies
-    CU(cudaEventRecord(c->ev_main, c->part_stream));
-    CU(cudaStreamWaitEvent(c->dma_stream, c->ev_main, 0));
-    for (uint32_t i = 0; i < c->n_ranks; i++) {
-        const uint32_t o = (c->p.rank + 1 + i) % c->n_ranks;  // stagger destinations across ranks
-        uint64_t off = 0;
-        for (uint32_t q = 0; q < o; q++) off += n_to[q];
-        if (n_to[o])
-            CU(cudaMemcpyAsync(c->peer_arena[o][slot] + dst_offsets[o], c->d_list + off, n_to[o] * sizeof(uint64_t),
-                               cudaMemcpyDefault, c->dma_stream));
-    }
-    CU(cudaEventRecord(c->ev_slot[slot], c->dma_stream));
-    CU(cudaEventRecord(c->ev_dma, c->dma_stream));
-    CU(cudaStreamWaitEvent(c->part_stream, c->ev_dma, 0));  // what follows on the routing stream (the barrier) sees the copies done
-    return SKM_OK;
-}
-
-int32_t skm_insert_runs_device(skm_ctx *c, const uint64_t *d_kmers, const uint64_t *run_counts, uint32_t n_src,
-                               uint32_t regions) {
-    if (!c || !run_counts || n_src == 0 || regions == 0) return SKM_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
-    // buffer layout: source-major; insertion order: region-major, so that all sources' k-mers of one
-    // table region are inserted together while that region is L2-resident
-    std::vector<uint64_t> start((size_t)n_src * regions + 1, 0);
-    for (size_t i = 0; i < (size_t)n_src * regions; i++) start[i + 1] = start[i] + run_counts[i];
-    if (start.back() && !d_kmers) return fail(c, SKM_ERR_INVALID_ARG, "null buffer");
-    std::vector<RunDesc> runs;
-    runs.reserve((size_t)n_src * regions);
-    for (uint32_t r = 0; r < regions; r++)
-        for (uint32_t sidx = 0; sidx < n_src; sidx++) {
-            const size_t i = (size_t)sidx * regions + r;
-            if (run_counts[i])
-                runs.push_back(RunDesc{(const unsigned long long *)d_kmers + start[i], nullptr, run_counts[i], 0});
-        }
-    c->have_tot = false;
-    return insert_runs(c, runs);  // asynchronous: ordered on the ctx's stream
-}
+// ---- multi-GPU: see the skm_mg_* / skm_group_* entry points at the end of this file ----------
 
 int32_t skm_insert_kmers_device(skm_ctx *c, const uint64_t *d_kmers, uint64_t n) {
     if (!c || (n && !d_kmers)) return SKM_ERR_INVALID_ARG;
@@ -2938,6 +2379,513 @@ int32_t skm_bench_gups(skm_ctx *c, uint32_t log2_slots, uint64_t n_updates, uint
     cudaFree(t);
     cudaFree(d_sink);
     return SKM_OK;
+}
+
+}  // extern "C"
+
+// ============================================================================
+// multi-GPU: receive arenas, collective finalize, in-process group
+// ============================================================================
+
+namespace {
+
+int32_t mg_allgather(skm_ctx *c, const skm_comm *comm, const void *send, void *recv, uint64_t bytes) {
+    const int32_t rc = comm->allgather(comm->user, send, recv, bytes);
+    if (rc) return fail(c, SKM_ERR_STATE, "all-gather callback failed (%d)", rc);
+    return SKM_OK;
+}
+
+// Everything this rank has ingested is bucketed, tile-sorted and on its way to the owners.
+int32_t mg_prepare_local(skm_ctx *c) {
+    int32_t rc;
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->part_stream));
+    WorkStream ws(c, c->part_stream);
+    for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
+        ChunkState &cs = c->chunks[ch];
+        for (size_t si = 0; si < cs.segs.size(); si++) {
+            Segment &sg = cs.segs[si];
+            if (!sg.list && sg.codes) {  // skipped at ingest time (memory): build it now
+                uint64_t *h_off = alloc_offsets(c, (c->n_ranks << route_log2_regions(c)) + 1);
+                if (!h_off) return fail(c, SKM_ERR_OOM, "pinned allocation failed");
+                rc = build_list(c, ch, si, h_off, /*exact=*/!c->capped, /*must=*/true);
+                if (rc) return rc;
+                CU(cudaEventSynchronize(sg.ready));
+            }
+            if (!sg.list) continue;
+            if (sg.cap && sg.h_offsets[sg.n_buckets] > 0) {
+                // a capped list that overflowed: what was shipped is void; rebuild exactly and ship that
+                if (sg.shipped)
+                    for (size_t r = sg.rec_first; r < sg.rec_first + c->n_ranks - 1 && r < c->mg_sent.size(); r++)
+                        c->mg_sent[r].dead = 1;
+                sg.shipped = false;
+                CU(cudaStreamSynchronize(c->dma_stream));  // the copies still read the old list
+                rc = drop_capped_list(c, ch, sg, c->part_stream);
+                if (rc) return rc;
+                c->n_capped_fallbacks++;
+                uint64_t *h_off = alloc_offsets(c, sg.n_buckets + 1);
+                if (!h_off) return fail(c, SKM_ERR_OOM, "pinned allocation failed");
+                rc = build_list(c, ch, si, h_off, /*exact=*/true, /*must=*/true);
+                if (rc) return rc;
+                CU(cudaEventSynchronize(sg.ready));
+            }
+            if (!sg.shipped) {
+                rc = ship_segment(c, ch, si);
+                if (rc) return rc;
+                if (!sg.shipped) return fail(c, SKM_ERR_STATE, "receive arenas are not wired (skm_mg_open_peer / skm_mg_set_peer for every peer)");
+            }
+            // k-mers per destination, now that the totals are on the host
+            const uint32_t R = 1u << route_log2_regions(c);
+            for (uint32_t i = 0; i + 1 < c->n_ranks; i++) {
+                MgRecord &rec = c->mg_sent[sg.rec_first + i];
+                uint64_t nk = 0;
+                for (uint32_t b = rec.dst * R; b < (rec.dst + 1) * R; b++)
+                    nk += sg.cap ? std::min<uint64_t>(sg.h_offsets[b], sg.cap) : sg.h_offsets[b + 1] - sg.h_offsets[b];
+                rec.n_kmers = nk;
+            }
+            if (sg.codes) {  // the packed form was kept for the overflow fallback only
+                CU(cudaFreeAsync(sg.codes, c->part_stream));
+                CU(cudaFreeAsync(sg.breaks, c->part_stream));
+                sg.codes = nullptr;
+                sg.breaks = nullptr;
+            }
+        }
+    }
+    CU(cudaStreamSynchronize(c->part_stream));
+    CU(cudaStreamSynchronize(c->dma_stream));  // every slice of mine has landed
+    rc = check_sticky(c);
+    if (rc) return rc;
+    return refresh_chunk_counters(c);
+}
+
+struct MgHeader {
+    int32_t status;
+    uint32_t n_records;
+    uint64_t n_windows, n_reads;
+};
+
+struct MgTotals {
+    int32_t status;
+    uint32_t pad;
+    uint64_t n_kmers, n_distinct_scan, n_distinct, n_saturated, n_windows;
+};
+
+int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm) {
+    const uint32_t N = c->n_ranks, me = c->p.rank;
+    const size_t nbins = c->p.histo_max + 2;
+    // ---- phase 1: local work, then the directory of what everybody shipped (doubles as the
+    //      "all slices have landed" barrier: a rank joins only after its own copies are done) ----
+    MgHeader mine{};
+    mine.status = mg_prepare_local(c);
+    mine.n_records = (uint32_t)c->mg_sent.size();
+    for (auto &cc : c->h_cc) {
+        mine.n_windows += cc.n_windows;
+        mine.n_reads += cc.n_reads;
+    }
+    std::vector<MgHeader> hdrs(N);
+    int32_t rc = mg_allgather(c, comm, &mine, hdrs.data(), sizeof(MgHeader));
+    if (rc) return rc;
+    uint32_t max_rec = 0;
+    uint64_t windows_all = 0, reads_all = 0;
+    for (uint32_t r = 0; r < N; r++) {
+        if (hdrs[r].status != SKM_OK) {
+            if (mine.status != SKM_OK) return mine.status;  // own message is already set
+            return fail(c, hdrs[r].status, "rank %u failed before the exchange (see its skm_last_error)", r);
+        }
+        max_rec = std::max(max_rec, hdrs[r].n_records);
+        windows_all += hdrs[r].n_windows;
+        reads_all += hdrs[r].n_reads;
+    }
+    if (reads_all == 0)  // src/io.rs:578-580
+        return fail(c, SKM_ERR_NO_READS, "No reads were ingested. Check that input files contain valid FASTQ records.");
+    std::vector<MgRecord> all((size_t)N * std::max(max_rec, 1u)), sendbuf(std::max(max_rec, 1u));
+    std::copy(c->mg_sent.begin(), c->mg_sent.end(), sendbuf.begin());
+    rc = mg_allgather(c, comm, sendbuf.data(), all.data(), (uint64_t)sendbuf.size() * sizeof(MgRecord));
+    if (rc) return rc;
+
+    // ---- phase 2: the lists this rank counts, in chunk order: its own + the slices in its arena ----
+    struct Item { SegDesc d; uint32_t chunk; uint64_t n_kmers; };
+    std::vector<Item> items;
+    const uint32_t g1 = route_log2_regions(c), R = 1u << g1;
+    uint64_t kmers_mine = 0;
+    for (uint32_t ch = 0; ch < c->n_chunks; ch++)
+        for (auto &sg : c->chunks[ch].segs) {
+            if (!sg.list || !sg.tiled) continue;
+            uint64_t nk = 0;
+            for (uint32_t b = me * R; b < (me + 1) * R; b++)
+                nk += sg.cap ? std::min<uint64_t>(sg.h_offsets[b], sg.cap) : sg.h_offsets[b + 1] - sg.h_offsets[b];
+            items.push_back(Item{local_desc(c, sg, 0), ch, nk});
+            kmers_mine += nk;
+        }
+    for (uint32_t src = 0; src < N; src++)
+        for (uint32_t i = 0; i < hdrs[src].n_records; i++) {
+            const MgRecord &rec = all[(size_t)src * sendbuf.size() + i];
+            if (rec.dst != me || rec.dead) continue;
+            if (rec.chunk >= c->n_chunks) return fail(c, SKM_ERR_STATE, "rank %u shipped chunk %u (this ctx has %u chunks)", src, rec.chunk, c->n_chunks);
+            uint8_t *base = c->mg_arena + (size_t)src * c->mg_sub_bytes;
+            SegDesc d{};
+            d.list = (const unsigned long long *)(base + rec.off_cells);
+            d.tile_off = (const uint16_t *)(base + rec.off_tile_off);
+            d.tile_begin = (const uint32_t *)(base + rec.off_tile_begin);
+            d.cell_begin = (const unsigned long long *)(base + rec.off_cell_begin);
+            d.bucket0 = 0;
+            d.rel = 1;
+            items.push_back(Item{d, rec.chunk, rec.n_kmers});
+            kmers_mine += rec.n_kmers;
+        }
+    std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.chunk < b.chunk; });
+
+    // ---- phase 3: size the (new) table for this rank's share, then count, chunk group by chunk group ----
+    int32_t status = SKM_OK;
+    c->recount_valid = false;
+    if (c->table_fresh && !c->p.capacity_hint) {
+        uint64_t bound = kmers_mine;
+        if (c->p.k < 31) bound = std::min<uint64_t>(bound, ((1ull << (2 * c->p.k)) / 2 + (1ull << c->p.k)) / N + 1024);
+        uint32_t want = std::max(c->log2cap, ceil_log2((uint64_t)((double)bound / kTargetLoad) + 1));
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+            while (want > c->log2cap && ((size_t)sizeof(Slot) << want) > (free_b + c->capacity * sizeof(Slot)) / 2) want--;
+        if (want > c->log2cap) status = grow_table(c, want);
+    }
+    std::vector<SegDesc> group;
+    uint32_t group_chunk0 = 0;
+    auto flush = [&](uint32_t end_chunk) -> int32_t {
+        if (group.empty()) {
+            // chunks without k-mers for this rank: their columns are the running histogram
+            for (uint32_t ch = group_chunk0; ch < end_chunk && c->p.chunks > 0; ch++) {
+                int32_t r = snapshot_histogram(c, ch);
+                if (r) return r;
+            }
+            group_chunk0 = end_chunk;
+            return SKM_OK;
+        }
+        int32_t r = launch_tiled(c, group, group_chunk0, end_chunk - group_chunk0);
+        group.clear();
+        group_chunk0 = end_chunk;
+        return r;
+    };
+    size_t at = 0;
+    for (uint32_t ch = 0; ch < c->n_chunks && status == SKM_OK; ch++) {
+        size_t end = at;
+        while (end < items.size() && items[end].chunk == ch) end++;
+        const uint32_t pbits = c->log2cap - kPartLog2;
+        const uint64_t nbr = pbits >= g1 ? 1ull : (1ull << (g1 - pbits));
+        if ((group.size() + (end - at)) * nbr > kMaxVseg || ch - group_chunk0 >= kMaxChunksPerLaunch) status = flush(ch);
+        for (; at < end && status == SKM_OK; at++) {
+            if ((group.size() + 1) * nbr > kMaxVseg) {  // one chunk, more lists than a launch reads: several launches
+                status = flush(ch + 1);
+                group_chunk0 = ch;
+                if (status) break;
+            }
+            SegDesc d = items[at].d;
+            d.chunk = ch - group_chunk0;
+            group.push_back(d);
+            c->insert_kmers += items[at].n_kmers;
+        }
+    }
+    if (status == SKM_OK) status = flush(c->n_chunks);
+    if (status == SKM_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) status = fail(c, SKM_ERR_CUDA, "stream synchronisation failed");
+    if (status == SKM_OK) {
+        materialize_cols(c);
+        status = check_sticky(c);
+    }
+
+    // ---- phase 4: totals and histogram columns over all ranks ----
+    MgTotals tm{};
+    tm.status = status;
+    if (status == SKM_OK) {
+        if (c->recount_valid) {
+            if (cudaMemcpy(&c->last_tot, c->d_tot, sizeof(HistoTotals), cudaMemcpyDeviceToHost) != cudaSuccess)
+                tm.status = fail(c, SKM_ERR_CUDA, "read-back of the totals failed");
+            c->have_tot = true;
+        } else {
+            tm.status = scan_table(c, false, nullptr);
+        }
+        uint64_t d = 0;
+        if (tm.status == SKM_OK) tm.status = read_distinct(c, &d);
+        c->distinct_ub = d;
+        tm.n_kmers = c->last_tot.n_kmers;
+        tm.n_distinct_scan = c->last_tot.n_distinct;
+        tm.n_distinct = d;
+        tm.n_saturated = c->last_tot.n_saturated;
+        tm.n_windows = mine.n_windows;
+    }
+    std::vector<MgTotals> tots(N);
+    rc = mg_allgather(c, comm, &tm, tots.data(), sizeof(MgTotals));
+    if (rc) return rc;
+    uint64_t g_kmers = 0, g_scan = 0, g_distinct = 0, g_sat = 0;
+    for (uint32_t r = 0; r < N; r++) {
+        if (tots[r].status != SKM_OK) {
+            if (tm.status != SKM_OK) return tm.status;
+            return fail(c, tots[r].status, "rank %u failed while counting (see its skm_last_error)", r);
+        }
+        g_kmers += tots[r].n_kmers;
+        g_scan += tots[r].n_distinct_scan;
+        g_distinct += tots[r].n_distinct;
+        g_sat += tots[r].n_saturated;
+    }
+    // conservation identities on the global totals (src/io.rs:1042-1047, 1120-1132)
+    if (g_sat == 0 && g_kmers != windows_all)
+        return fail(c, SKM_ERR_CONSERVATION,
+                    "The total count of hashed kmers (%llu) does not equal the number of ingested kmers (%llu)",
+                    (unsigned long long)g_kmers, (unsigned long long)windows_all);
+    if (g_scan != g_distinct)
+        return fail(c, SKM_ERR_CONSERVATION,
+                    "The total count of unique kmers in the histogram (%llu) does not equal the total count of hashed kmers (%llu)",
+                    (unsigned long long)g_scan, (unsigned long long)g_distinct);
+    if (c->p.chunks > 0) {
+        // column i = sum over the partitions' columns (a k-mer lives in exactly one partition)
+        std::vector<uint64_t> mycols((size_t)c->n_chunks * nbins), allcols((size_t)N * c->n_chunks * nbins);
+        for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
+            if (!c->have_histo[ch] || c->histos[ch].size() != nbins) return fail(c, SKM_ERR_STATE, "internal: column %u missing", ch);
+            std::copy(c->histos[ch].begin(), c->histos[ch].end(), mycols.begin() + (size_t)ch * nbins);
+        }
+        rc = mg_allgather(c, comm, mycols.data(), allcols.data(), (uint64_t)mycols.size() * sizeof(uint64_t));
+        if (rc) return rc;
+        for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
+            std::vector<uint64_t> &h = c->histos[ch];
+            std::fill(h.begin(), h.end(), 0);
+            for (uint32_t r = 0; r < N; r++) {
+                const uint64_t *src = allcols.data() + ((size_t)r * c->n_chunks + ch) * nbins;
+                for (size_t b = 0; b < nbins; b++) h[b] += src[b];
+            }
+        }
+        const std::vector<uint64_t> &last = c->histos[c->n_chunks - 1];
+        uint64_t uniq = 0;
+        for (size_t i = 1; i < last.size(); i++) uniq += last[i];
+        if (uniq != g_distinct)
+            return fail(c, SKM_ERR_CONSERVATION,
+                        "The total count of unique kmers in the histogram (%llu) does not equal the total count of hashed kmers (%llu)",
+                        (unsigned long long)uniq, (unsigned long long)g_distinct);
+    }
+    // lists and arena contents are no longer needed; the last all-gather above is also the barrier
+    // after which a peer may write into this rank's arena again (next sample)
+    for (auto &cs : c->chunks)
+        for (auto &sg : cs.segs) {
+            release_list(c, sg, c->stream);
+            if (sg.ready) c->event_pool.push_back(sg.ready);
+            sg.ready = nullptr;
+        }
+    collect_spans(c);
+    return SKM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t skm_mg_arena_create(skm_ctx *c, uint64_t bytes) {
+    if (!c || bytes == 0) return SKM_ERR_INVALID_ARG;
+    if (c->n_ranks > skm_ctx::kMaxPeers) return fail(c, SKM_ERR_INVALID_ARG, "at most %u ranks", skm_ctx::kMaxPeers);
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->mg_arena) CU(cudaFree(c->mg_arena));
+    c->mg_arena = nullptr;
+    const size_t sub = ((size_t)(bytes / c->n_ranks) + 255) & ~(size_t)255;
+    // cudaMalloc, not the stream-ordered pool: the block must be exportable through CUDA IPC
+    CU(cudaMalloc((void **)&c->mg_arena, sub * c->n_ranks));
+    c->mg_arena_bytes = sub * c->n_ranks;
+    c->mg_sub_bytes = sub;
+    c->mg_peer[c->p.rank] = c->mg_arena;
+    return SKM_OK;
+}
+
+int32_t skm_mg_arena_handle(skm_ctx *c, uint8_t *handle64) {
+    if (!c || !handle64) return SKM_ERR_INVALID_ARG;
+    if (!c->mg_arena) return fail(c, SKM_ERR_STATE, "no arena: call skm_mg_arena_create first");
+    DeviceGuard g(c->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->mg_arena));
+    memcpy(handle64, &h, 64);
+    return SKM_OK;
+}
+
+int32_t skm_mg_arena_ptr(skm_ctx *c, void **out) {
+    if (!c || !out) return SKM_ERR_INVALID_ARG;
+    *out = c->mg_arena;
+    return SKM_OK;
+}
+
+int32_t skm_mg_open_peer(skm_ctx *c, uint32_t peer_rank, const uint8_t *handle64) {
+    if (!c || !handle64 || peer_rank >= c->n_ranks || peer_rank >= skm_ctx::kMaxPeers) return SKM_ERR_INVALID_ARG;
+    if (peer_rank == c->p.rank) return SKM_OK;
+    DeviceGuard g(c->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->mg_peer[peer_rank] = (uint8_t *)p;
+    c->mg_peer_ipc[peer_rank] = true;
+    return SKM_OK;
+}
+
+int32_t skm_mg_set_peer(skm_ctx *c, uint32_t peer_rank, void *d_ptr, int32_t peer_device) {
+    if (!c || peer_rank >= c->n_ranks || peer_rank >= skm_ctx::kMaxPeers) return SKM_ERR_INVALID_ARG;
+    if (peer_rank == c->p.rank) return SKM_OK;
+    DeviceGuard g(c->device);
+    if (peer_device >= 0 && peer_device != c->device) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return fail(c, SKM_ERR_CUDA, "no peer access from device %d to device %d: %s", c->device, peer_device, cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    c->mg_peer[peer_rank] = (uint8_t *)d_ptr;
+    c->mg_peer_ipc[peer_rank] = false;
+    return SKM_OK;
+}
+
+int32_t skm_mg_bytes_sent(skm_ctx *c, uint64_t *out) {
+    if (!c || !out) return SKM_ERR_INVALID_ARG;
+    *out = c->mg_bytes_sent;
+    return SKM_OK;
+}
+
+int32_t skm_mg_finalize(skm_ctx *c, const skm_comm *comm) {
+    if (!c || !comm || !comm->allgather) return SKM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    if (c->finalized) return fail(c, SKM_ERR_STATE, "finalize called twice");
+    if (c->n_ranks == 1) return finalize_common(c);
+    if (!c->mg_arena) return fail(c, SKM_ERR_STATE, "no receive arena: call skm_mg_arena_create and wire the peers first");
+    c->finalized = true;
+    cudaEvent_t e0 = get_event(c), e1 = get_event(c);
+    cudaEventRecord(e0, c->stream);
+    const int32_t rc = mg_finalize_impl(c, comm);
+    cudaEventRecord(e1, c->stream);
+    if (cudaStreamSynchronize(c->stream) == cudaSuccess) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) c->stage_ms[ST_FINALIZE] += ms;
+    }
+    c->event_pool.push_back(e0);
+    c->event_pool.push_back(e1);
+    return rc;
+}
+
+}  // extern "C"
+
+// ---- all ranks in one process ------------------------------------------------------------------
+
+#include <condition_variable>
+#include <thread>
+
+struct skm_group {
+    std::vector<skm_ctx *> ctx;
+    std::mutex mu;
+    std::condition_variable cv;
+    uint32_t arrived = 0;
+    uint64_t generation = 0;
+    std::vector<const void *> send;
+    std::string err;
+
+    void barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        const uint64_t gen = generation;
+        if (++arrived == ctx.size()) {
+            arrived = 0;
+            generation++;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return generation != gen; });
+        }
+    }
+};
+
+namespace {
+struct GroupMember {
+    skm_group *g;
+    uint32_t rank;
+};
+int32_t group_allgather(void *user, const void *send, void *recv, uint64_t bytes) {
+    GroupMember *m = (GroupMember *)user;
+    skm_group *g = m->g;
+    g->send[m->rank] = send;
+    g->barrier();
+    for (size_t r = 0; r < g->ctx.size(); r++) memcpy((uint8_t *)recv + r * bytes, g->send[r], bytes);
+    g->barrier();  // nobody's send buffer is reused before everybody has read it
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t skm_group_create(const skm_params *params, uint32_t n_ranks, const int32_t *devices, uint64_t arena_bytes_per_rank,
+                         skm_group **out) {
+    if (!params || !out || n_ranks == 0 || n_ranks > skm_ctx::kMaxPeers) return SKM_ERR_INVALID_ARG;
+    skm_group *g = new (std::nothrow) skm_group();
+    if (!g) return SKM_ERR_OOM;
+    *out = g;
+    g->send.assign(n_ranks, nullptr);
+    for (uint32_t r = 0; r < n_ranks; r++) {
+        skm_params p = *params;
+        p.n_ranks = n_ranks;
+        p.rank = r;
+        p.device = devices ? devices[r] : -1;
+        p.stream = 0;
+        skm_ctx *c = nullptr;
+        int32_t rc = skm_create(&p, &c);
+        if (c) g->ctx.push_back(c);
+        if (rc == SKM_OK && n_ranks > 1) rc = skm_mg_arena_create(c, arena_bytes_per_rank);
+        if (rc) {
+            g->err = c ? c->err : "skm_create failed";
+            return rc;
+        }
+    }
+    for (uint32_t a = 0; a < n_ranks && n_ranks > 1; a++)
+        for (uint32_t b = 0; b < n_ranks; b++) {
+            if (a == b) continue;
+            const int32_t rc = skm_mg_set_peer(g->ctx[a], b, g->ctx[b]->mg_arena, g->ctx[b]->device);
+            if (rc) {
+                g->err = g->ctx[a]->err;
+                return rc;
+            }
+        }
+    return SKM_OK;
+}
+
+skm_ctx *skm_group_ctx(skm_group *g, uint32_t rank) { return g && rank < g->ctx.size() ? g->ctx[rank] : nullptr; }
+
+int32_t skm_group_finalize(skm_group *g) {
+    if (!g || g->ctx.empty()) return SKM_ERR_INVALID_ARG;
+    const size_t n = g->ctx.size();
+    std::vector<int32_t> rcs(n, SKM_OK);
+    std::vector<GroupMember> members(n);
+    std::vector<std::thread> threads;
+    for (size_t r = 0; r < n; r++) {
+        members[r] = GroupMember{g, (uint32_t)r};
+        threads.emplace_back([&, r] {
+            skm_comm comm{&members[r], group_allgather};
+            rcs[r] = skm_mg_finalize(g->ctx[r], &comm);
+        });
+    }
+    for (auto &t : threads) t.join();
+    for (size_t r = 0; r < n; r++)
+        if (rcs[r]) {
+            g->err = "rank " + std::to_string(r) + ": " + g->ctx[r]->err;
+            return rcs[r];
+        }
+    return SKM_OK;
+}
+
+int32_t skm_group_reset(skm_group *g) {
+    if (!g) return SKM_ERR_INVALID_ARG;
+    for (auto c : g->ctx) {
+        const int32_t rc = skm_reset(c);
+        if (rc) {
+            g->err = c->err;
+            return rc;
+        }
+    }
+    return SKM_OK;
+}
+
+const char *skm_group_last_error(skm_group *g) { return g ? g->err.c_str() : "null group"; }
+
+void skm_group_destroy(skm_group *g) {
+    if (!g) return;
+    for (auto c : g->ctx) skm_destroy(c);
+    delete g;
 }
 
 }  // extern "C"

@@ -107,6 +107,17 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4 *p) {
     return r;
 }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS): the data never passes through registers
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -1290,11 +1301,30 @@ struct SegDesc {
     const unsigned long long *cell_begin;
     uint32_t bucket0;   // first bucket of this table's owner in the list's numbering (rank << g1)
     uint32_t chunk;     // chunk index relative to the launch's first chunk
+    uint32_t rel;       // 1: the arrays are an owner's SLICE of the sender's metadata (bucket0 = 0) and the
+                        //    list / tile_off pointers address the slice: subtract the slice's first entries
+    uint32_t pad;
 };
 
-static constexpr uint32_t kInsThreads = 256;
+#ifndef SKM_INS_THREADS
+#define SKM_INS_THREADS 512
+#endif
+#ifndef SKM_INS_CTAS
+#define SKM_INS_CTAS 2
+#endif
+static constexpr uint32_t kInsThreads = SKM_INS_THREADS;
+static constexpr uint32_t kInsCtasPerSm = SKM_INS_CTAS;
 static constexpr uint32_t kMaxVseg = 256;    // (list, bucket) pairs per launch that one partition reads
-static constexpr uint32_t kStagedRuns = 256; // runs staged in shared memory at a time
+static constexpr uint32_t kStagedRuns = 256; // runs whose descriptors are staged in shared memory at a time
+#ifndef SKM_INS_STAGE
+#define SKM_INS_STAGE 1024
+#endif
+#ifndef SKM_INS_DEPTH
+#define SKM_INS_DEPTH 4
+#endif
+static constexpr uint32_t kStageCap = SKM_INS_STAGE;    // k-mers per staged span
+static constexpr uint32_t kStageDepth = SKM_INS_DEPTH;  // spans in flight (being copied or counted), 2..4
+static_assert(kStageDepth >= 2 && kStageDepth <= 4, "cp.async wait depth");
 static constexpr uint32_t kHlogCap = 512;    // pending moves of histogram bins >= k_low, per partition
 static constexpr uint32_t kBigCount = 0x80000000u;
 
@@ -1323,29 +1353,47 @@ struct InsertLaunch {
 __host__ __device__ inline size_t tile_insert_smem_bytes(uint32_t n_chunks, uint32_t k_low, bool histo) {
     size_t b = (size_t)kPartSlots * 12;                    // keys + counts
     b += (size_t)kMaxVseg * 16 + 8;                        // vs_cell (u64), vs_tb, vs_first (u32)
-    b += (size_t)kStagedRuns * 12;                            // run_src (u64), run_len (u32)
+    b += (size_t)kStagedRuns * 16 + 8;                     // run_src (u64), run_len, run_pos (u32)
+    b += (size_t)kStageDepth * kStageCap * 8;              // staged spans of k-mers
     if (histo) b += (size_t)n_chunks * k_low * 8 + (size_t)k_low * 4 + (size_t)kHlogCap * 4;  // chist + phist, fhist, hlog
     else b += (size_t)k_low * 4;
     return b + 64;
 }
 
+// A histogram move of a bin >= k_low: logged per partition (so that a failed partition can be rolled
+// back) and published when the partition commits; a full log publishes at once and marks the
+// partition dirty.
+__device__ __forceinline__ void hlog_push(uint32_t *hlog, uint32_t *n, uint32_t *dirty, const InsertLaunch &L, uint32_t c,
+                                          uint32_t bin, bool minus) {
+    const uint32_t e = atomicAdd(n, 1u);
+    if (e < kHlogCap) {
+        hlog[e] = (c << 24) | (minus ? 0x800000u : 0u) | bin;
+    } else {
+        *dirty = 1;
+        atomicAdd(&L.g_delta[(size_t)c * (L.histo_max + 2) + bin], minus ? ~0ull : 1ull);
+    }
+}
+
 template <bool kHisto>
-__global__ void __launch_bounds__(kInsThreads, 3)
+__global__ void __launch_bounds__(kInsThreads, kInsCtasPerSm)
 tile_insert_kernel(const InsertLaunch L) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(s_raw);
-    unsigned long long *vs_cell = keys + kPartSlots;
+    unsigned long long *stage = keys + kPartSlots;           // kStageDepth * kStageCap
+    unsigned long long *vs_cell = stage + kStageDepth * kStageCap;
     unsigned long long *run_src = vs_cell + kMaxVseg;
     uint32_t *counts = reinterpret_cast<uint32_t *>(run_src + kStagedRuns);
     uint32_t *vs_tb = counts + kPartSlots;
     uint32_t *vs_first = vs_tb + kMaxVseg;          // kMaxVseg + 1
     uint32_t *run_len = vs_first + kMaxVseg + 2;
-    int *fhist = reinterpret_cast<int *>(run_len + kStagedRuns);   // k_low: histogram of the written-back partition(s)
+    uint32_t *run_pos = run_len + kStagedRuns;      // kStagedRuns + 1: first k-mer of each staged run, window-relative
+    int *fhist = reinterpret_cast<int *>(run_pos + kStagedRuns + 2);   // k_low: histogram of the written-back partition(s)
     int *chist = fhist + L.k_low;                   // n_chunks * k_low: moves of committed partitions
     int *phist = chist + (kHisto ? L.n_chunks * L.k_low : 0);   // n_chunks * k_low: moves of the current partition
     uint32_t *hlog = reinterpret_cast<uint32_t *>(phist + (kHisto ? L.n_chunks * L.k_low : 0));
     __shared__ unsigned long long s_q;
     __shared__ uint32_t s_occ, s_fail, s_big, s_hlog_n, s_dirty;
+    __shared__ uint32_t s_span[kStageDepth][2];   // chunk and length of the spans in flight
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = kInsThreads / 32;
     const uint32_t pbits = L.log2cap - kPartLog2;
@@ -1423,9 +1471,9 @@ tile_insert_kernel(const InsertLaunch L) {
             const SegDesc &sg = L.segs[v / nbr];
             const uint32_t bkt = sg.bucket0 + b_lo + v % nbr;
             const uint32_t tb = sg.tile_begin[bkt];
-            vs_tb[v] = tb;
+            vs_tb[v] = tb - (sg.rel ? sg.tile_begin[0] : 0u);
             vs_first[v] = sg.tile_begin[bkt + 1] - tb;   // tiles; scanned below
-            vs_cell[v] = sg.cell_begin[bkt];
+            vs_cell[v] = sg.cell_begin[bkt] - (sg.rel ? sg.cell_begin[0] : 0ull);
         }
         __syncthreads();
         if (warp == 0) {  // exclusive scan of the tile counts -> first run of each virtual segment
@@ -1447,109 +1495,197 @@ tile_insert_kernel(const InsertLaunch L) {
         __syncthreads();
         const uint32_t total_runs = vs_first[n_vseg];
         unsigned long long n_new = 0;
-        uint32_t w0 = 0, w1 = 0;  // runs [w0, w1) are staged in run_src / run_len
-        for (uint32_t c = 0; c < L.n_chunks; c++) {
-            const uint32_t cr0 = vs_first[L.chunk_first_seg[c] * nbr], cr1 = vs_first[L.chunk_first_seg[c + 1] * nbr];
-            uint32_t pos = cr0;
-            while (pos < cr1) {
-                if (pos >= w1) {  // stage the next window of runs
-                    __syncthreads();
-                    w0 = pos;
-                    w1 = min(total_runs, w0 + kStagedRuns);
-                    for (uint32_t r = w0 + threadIdx.x; r < w1; r += kInsThreads) {
-                        uint32_t lo = 0, hi = n_vseg;  // last virtual segment whose first run <= r
-                        while (hi - lo > 1) {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            if (vs_first[mid] <= r) lo = mid; else hi = mid;
-                        }
-                        const SegDesc &sg = L.segs[lo / nbr];
-                        const uint32_t jt = r - vs_first[lo];
-                        const uint16_t *off = sg.tile_off + (size_t)(vs_tb[lo] + jt) * (F + 1);
-                        const uint32_t o0 = off[f0], o1 = off[f1];
-                        run_src[r - w0] = reinterpret_cast<unsigned long long>(sg.list + vs_cell[lo] + (unsigned long long)jt * kTile + o0);
-                        run_len[r - w0] = o1 - o0;
-                    }
-                    __syncthreads();
+        const uint32_t hm = (uint32_t)L.histo_max, top32 = hm + 1;
+        // Runs [w0, w1) have their descriptors staged (run_src / run_len / run_pos).  The k-mers are
+        // walked in SPANS of <= kStageCap consecutive k-mers of one chunk; span i+1 is copied into
+        // shared memory (cp.async, no registers held) while span i is counted.  The barrier after
+        // every span orders the chunks: chunk c is complete before any k-mer of chunk c+1 is counted.
+        uint32_t w0 = 0, w1 = 0;
+        uint32_t sc = 0, spos = vs_first[L.chunk_first_seg[0] * nbr], soff = 0;            // span cursor: chunk, run, k-mers done in the group
+        uint32_t scr1 = vs_first[L.chunk_first_seg[1] * nbr];
+        struct Span { uint32_t c, r0, r1, a, n; };
+        // 0: span produced; 1: descriptors of run `spos` are not staged; 2: no k-mers left
+        auto next_span = [&](Span &sp) -> int {
+            for (;;) {
+                if (sc >= L.n_chunks) return 2;
+                if (spos >= scr1) {
+                    sc++;
+                    if (sc >= L.n_chunks) return 2;
+                    spos = vs_first[L.chunk_first_seg[sc] * nbr];
+                    scr1 = vs_first[L.chunk_first_seg[sc + 1] * nbr];
+                    soff = 0;
+                    continue;
                 }
-                const uint32_t end = min(cr1, w1);
-                if (!s_fail) {
-                    for (uint32_t r = pos + warp; r < end; r += n_warps) {
-                        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(run_src[r - w0]);
-                        const uint32_t n = run_len[r - w0];
-                        for (uint32_t i0 = 0; i0 < n; i0 += 128) {
-                            unsigned long long km[4];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const uint32_t i = i0 + u * 32 + lane;
-                                km[u] = i < n ? src[i] : SKM_EMPTY_KEY;
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const unsigned long long kmer = km[u];
-                                if (kmer == SKM_EMPTY_KEY) continue;
-                                const uint64_t h = skm_hash_kmer(kmer);
-                                const uint64_t home = skm_home_slot(L.n_ranks == 1 ? h : skm_local_hash(h, L.n_ranks), L.log2cap);
-                                if (filter && (home >> kPartLog2) != q) continue;
-                                uint32_t s = (uint32_t)home & (kPartSlots - 1);
-                                uint32_t probes = 0;
-                                bool ok = true;
-                                for (;;) {
-                                    unsigned long long key = keys[s];
-                                    if (key == kmer) break;
-                                    if (key == SKM_EMPTY_KEY) {
-                                        key = atomicCAS(&keys[s], (unsigned long long)SKM_EMPTY_KEY, kmer);
-                                        if (key == SKM_EMPTY_KEY) {
-                                            n_new++;
-                                            if (atomicAdd(&s_occ, 1u) >= L.max_occupied) s_fail = 1;
-                                            break;
-                                        }
-                                        if (key == kmer) break;
-                                    }
-                                    if (++probes >= kPartSlots) {
-                                        ok = false;
-                                        s_fail = 1;
-                                        break;
-                                    }
-                                    s = (s + 1) & (kPartSlots - 1);
-                                }
-                                if (!ok) continue;
-                                if (!kHisto) {
-                                    atomicAdd(&counts[s], 1u);
-                                } else {
-                                    const unsigned long long old = atomicAdd(&counts[s], 1u);
-                                    // Histogram::move_count (src/kmer/histogram.rs:51-85): one unit of mass from bin old to old+1
-                                    const unsigned long long ob = old > L.histo_max ? top : old;
-                                    const unsigned long long nb2 = old + 1 > L.histo_max ? top : old + 1;
-                                    if (ob != nb2) {
-                                        if (old) {
-                                            if (ob < L.k_low) atomicAdd(&phist[c * L.k_low + (uint32_t)ob], -1);
-                                            else {
-                                                const uint32_t e = atomicAdd(&s_hlog_n, 1u);
-                                                if (e < kHlogCap) hlog[e] = (c << 24) | 0x800000u | (uint32_t)ob;   // bit 23: minus
-                                                else {
-                                                    s_dirty = 1;
-                                                    atomicAdd(&L.g_delta[(size_t)c * (L.histo_max + 2) + ob], ~0ull);
-                                                }
-                                            }
-                                        }
-                                        if (nb2 < L.k_low) atomicAdd(&phist[c * L.k_low + (uint32_t)nb2], 1);
-                                        else {
-                                            const uint32_t e = atomicAdd(&s_hlog_n, 1u);
-                                            if (e < kHlogCap) hlog[e] = (c << 24) | (uint32_t)nb2;
-                                            else {
-                                                s_dirty = 1;
-                                                atomicAdd(&L.g_delta[(size_t)c * (L.histo_max + 2) + nb2], 1ull);
-                                            }
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                    }
+                if (spos >= w1 || spos < w0) return 1;
+                const uint32_t gend = min(scr1, w1);
+                const uint32_t gbase = run_pos[spos - w0], glen = run_pos[gend - w0] - gbase;
+                if (soff >= glen) {
+                    spos = gend;
+                    soff = 0;
+                    continue;
                 }
-                pos = end;
+                sp.c = sc;
+                sp.r0 = spos;
+                sp.r1 = gend;
+                sp.a = gbase + soff;
+                sp.n = min(kStageCap, glen - soff);
+                soff += sp.n;
+                return 0;
             }
-            if (kHisto) __syncthreads();  // chunk c is complete before any k-mer of chunk c+1 is counted
+        };
+        auto stage_window = [&](uint32_t from) {
+            __syncthreads();
+            w0 = from;
+            w1 = min(total_runs, w0 + kStagedRuns);
+            for (uint32_t r = w0 + threadIdx.x; r < w1; r += kInsThreads) {
+                uint32_t lo = 0, hi = n_vseg;  // last virtual segment whose first run <= r
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (vs_first[mid] <= r) lo = mid; else hi = mid;
+                }
+                const SegDesc &sg = L.segs[lo / nbr];
+                const uint32_t jt = r - vs_first[lo];
+                const uint16_t *off = sg.tile_off + (size_t)(vs_tb[lo] + jt) * (F + 1);
+                const uint32_t o0 = off[f0], o1 = off[f1];
+                run_src[r - w0] = reinterpret_cast<unsigned long long>(sg.list + vs_cell[lo] + (unsigned long long)jt * kTile + o0);
+                run_len[r - w0] = o1 - o0;
+            }
+            __syncthreads();
+            if (warp == 0) {  // run_pos = exclusive scan of run_len over the window
+                uint32_t run = 0;
+                const uint32_t nw = w1 - w0;
+                for (uint32_t v0 = 0; v0 < nw; v0 += 32) {
+                    const uint32_t v = v0 + lane;
+                    const uint32_t x = v < nw ? run_len[v] : 0u;
+                    uint32_t incl = x;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= (uint32_t)o) incl += t;
+                    }
+                    if (v < nw) run_pos[v] = run + incl - x;
+                    run += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) run_pos[nw] = run;
+            }
+            __syncthreads();
+        };
+        auto issue_copy = [&](const Span &sp, uint32_t buf) {
+            unsigned long long *dst = stage + buf * kStageCap;
+            for (uint32_t r = sp.r0 + warp; r < sp.r1; r += n_warps) {
+                const uint32_t rp = run_pos[r - w0], len = run_len[r - w0];
+                const uint32_t lo = max(rp, sp.a), hi = min(rp + len, sp.a + sp.n);
+                const unsigned long long *src = reinterpret_cast<const unsigned long long *>(run_src[r - w0]);
+                for (uint32_t i = lo + lane; i < hi; i += 32) cp_async8(dst + (i - sp.a), src + (i - rp));
+            }
+            cp_async_commit();
+        };
+        // pipeline: up to kStageDepth spans are in flight (copies issued), the oldest is counted
+        uint32_t q_head = 0, q_n = 0;
+        int more = total_runs ? 0 : 2;   // 0: more spans may follow; 1: the next run's descriptors are not staged; 2: done
+        auto fill = [&]() {
+            while (q_n < kStageDepth && more == 0) {
+                Span sp;
+                more = next_span(sp);
+                if (more == 0) {
+                    const uint32_t b = (q_head + q_n) % kStageDepth;
+                    issue_copy(sp, b);
+                    if (threadIdx.x == 0) {
+                        s_span[b][0] = sp.c;
+                        s_span[b][1] = sp.n;
+                    }
+                    q_n++;
+                }
+            }
+        };
+        fill();
+        if (q_n == 0 && more == 1) {
+            stage_window(spos);
+            more = 0;
+            fill();
+        }
+        while (q_n > 0) {
+            switch (q_n - 1) {  // copy groups issued after the oldest span's
+            case 0: cp_async_wait<0>(); break;
+            case 1: cp_async_wait<1>(); break;
+            case 2: cp_async_wait<2>(); break;
+            default: cp_async_wait<3>(); break;
+            }
+            __syncthreads();
+            const uint32_t c = s_span[q_head][0], span_n = s_span[q_head][1];
+            if (!s_fail) {
+                const unsigned long long *src = stage + q_head * kStageCap;
+                int *ph = phist + c * L.k_low;  // this chunk's histogram moves
+                (void)ph;
+                for (uint32_t i0 = 0; i0 < span_n; i0 += kInsThreads) {
+                    const uint32_t i = i0 + threadIdx.x;
+                    const unsigned long long kmer = i < span_n ? src[i] : SKM_EMPTY_KEY;
+                    bool active = kmer != SKM_EMPTY_KEY;
+                    uint32_t s = 0;
+                    if (active) {
+                        const uint64_t h = skm_hash_kmer(kmer);
+                        const uint64_t home = skm_home_slot(L.n_ranks == 1 ? h : skm_local_hash(h, L.n_ranks), L.log2cap);
+                        if (filter && (home >> kPartLog2) != q) active = false;
+                        s = (uint32_t)home & (kPartSlots - 1);
+                    }
+                    // The probe loop is warp-uniform (lanes that are done idle, predicated off): with
+                    // per-lane `break`s the compiler kept the lanes apart for the rest of the iteration
+                    // and the count update ran with 7 of 32 lanes on average.
+                    bool counted = active;
+                    uint32_t probes = 0;
+                    while (__any_sync(0xffffffffu, active)) {
+                        if (active) {
+                            unsigned long long key = keys[s];
+                            bool hit = key == kmer;
+                            if (!hit && key == SKM_EMPTY_KEY) {
+                                key = atomicCAS(&keys[s], (unsigned long long)SKM_EMPTY_KEY, kmer);
+                                if (key == SKM_EMPTY_KEY) {
+                                    hit = true;
+                                    n_new++;
+                                    if (atomicAdd(&s_occ, 1u) >= L.max_occupied) s_fail = 1;
+                                } else {
+                                    hit = key == kmer;
+                                }
+                            }
+                            if (hit) {
+                                active = false;
+                            } else if (++probes >= kPartSlots) {  // the partition holds only other keys
+                                active = false;
+                                counted = false;
+                                s_fail = 1;
+                            } else {
+                                s = (s + 1) & (kPartSlots - 1);
+                            }
+                        }
+                    }
+                    if (!counted) continue;
+                    if (!kHisto) {
+                        atomicAdd(&counts[s], 1u);
+                    } else {
+                        const uint32_t old = atomicAdd(&counts[s], 1u);
+                        // Histogram::move_count (src/kmer/histogram.rs:51-85): one unit of mass from bin old to old+1
+                        const uint32_t ob = old > hm ? top32 : old;
+                        const uint32_t nb2 = old >= hm ? top32 : old + 1;
+                        if (ob != nb2) {
+                            if (old) {
+                                if (ob < L.k_low) atomicAdd(&ph[ob], -1);
+                                else hlog_push(hlog, &s_hlog_n, &s_dirty, L, c, ob, true);
+                            }
+                            if (nb2 < L.k_low) atomicAdd(&ph[nb2], 1);
+                            else hlog_push(hlog, &s_hlog_n, &s_dirty, L, c, nb2, false);
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // the span is counted: its buffer may be refilled, the next chunk may start
+            q_head = (q_head + 1) % kStageDepth;
+            q_n--;
+            fill();
+            if (q_n == 0 && more == 1) {   // the next run's descriptors are not staged yet
+                stage_window(spos);
+                more = 0;
+                fill();
+            }
         }
         __syncthreads();
         // ---- commit or roll back ----

@@ -93,7 +93,6 @@ class Engine:
 
     def sync(self): self._ck(self.L.skm_sync(self._h))
     def finalize(self): self._ck(self.L.skm_finalize(self._h))
-    def finalize_external(self): self._ck(self.L.skm_finalize_external(self._h))
     def reset(self): self._ck(self.L.skm_reset(self._h))
 
     # ---- results --------------------------------------------------------
@@ -143,17 +142,21 @@ class Engine:
                                          counts.ctypes.data, found.ctypes.data))
         return counts, found.astype(bool)
 
-    def scan_oligos(self, oligos, oligo_length: int, min_count: int):
-        """find_oligos_in_kmers (src/pcr/primers.rs:163-226): sorted (kmers, counts)."""
+    def scan_oligos(self, oligos, oligo_length: int, min_count: int, cap: int = 1 << 16):
+        """find_oligos_in_kmers (src/pcr/primers.rs:163-226): sorted (kmers, counts).  One table pass
+        (the matches of a primer are a handful of k-mers); a second one only if `cap` was too small."""
         o = np.ascontiguousarray(oligos, dtype=np.uint64)
         n = C.c_uint64()
-        self._ck(self.L.skm_scan_oligos(self._h, o.ctypes.data, o.size, oligo_length, min_count, None, None, 0, C.byref(n)))
-        keys = np.empty(n.value, dtype=np.uint64)
-        counts = np.empty(n.value, dtype=np.uint32)
-        if n.value:
-            self._ck(self.L.skm_scan_oligos(self._h, o.ctypes.data, o.size, oligo_length, min_count,
-                                            keys.ctypes.data, counts.ctypes.data, n.value, C.byref(n)))
-        return keys[:n.value], counts[:n.value]
+        while True:
+            keys = np.empty(cap, dtype=np.uint64)
+            counts = np.empty(cap, dtype=np.uint32)
+            rc = self.L.skm_scan_oligos(self._h, o.ctypes.data, o.size, oligo_length, min_count,
+                                        keys.ctypes.data, counts.ctypes.data, cap, C.byref(n))
+            if rc == _lib.ERR_INVALID_ARG and n.value > cap:
+                cap = int(n.value)
+                continue
+            self._ck(rc)
+            return keys[:n.value].copy(), counts[:n.value].copy()
 
     def insert_counts(self, keys, counts):
         k = np.ascontiguousarray(keys, dtype=np.uint64)
@@ -161,81 +164,38 @@ class Engine:
         assert k.size == c.size
         self._ck(self.L.skm_insert_counts(self._h, k.ctypes.data, c.ctypes.data, k.size))
 
-    # ---- multi-GPU building blocks --------------------------------------
-    def stream_handle(self, which: int) -> int:
-        """cudaStream_t of the main (0) or routing (1) stream."""
-        h = C.c_uint64()
-        self._ck(self.L.skm_stream_handle(self._h, which, C.byref(h)))
-        return h.value
+    # ---- multi-GPU (include/sharkmer_b200.h: skm_mg_*) ---------------------
+    def mg_arena_create(self, n_bytes: int):
+        self._ck(self.L.skm_mg_arena_create(self._h, int(n_bytes)))
 
-    def route_regions(self) -> int:
-        r = C.c_uint32()
-        self._ck(self.L.skm_route_regions(self._h, C.byref(r)))
-        return r.value
-
-    def route_count(self, chunk_index: int, n_ranks: int) -> np.ndarray:
-        """Per-bucket counts, shape (n_ranks, regions_per_rank)."""
-        regions = self.route_regions()
-        counts = np.zeros((n_ranks, regions), dtype=np.uint64)
-        self._ck(self.L.skm_route_count(self._h, chunk_index, counts.ctypes.data))
-        return counts
-
-    def route_count_device(self, chunk_index: int) -> int:
-        p = C.c_void_p()
-        self._ck(self.L.skm_route_count_device(self._h, chunk_index, C.byref(p)))
-        return p.value
-
-    def route_set_counts(self, chunk_index: int, counts: np.ndarray):
-        cc = np.ascontiguousarray(counts, dtype=np.uint64)
-        self._ck(self.L.skm_route_set_counts(self._h, chunk_index, cc.ctypes.data))
-
-    def insert_runs_device(self, d_ptr: int, run_counts: np.ndarray):
-        """run_counts: shape (n_src, regions) — what each source rank sent, per table region."""
-        rc = np.ascontiguousarray(run_counts, dtype=np.uint64)
-        self._ck(self.L.skm_insert_runs_device(self._h, d_ptr, rc.ctypes.data, rc.shape[0], rc.shape[1]))
-
-    def route_scatter(self, chunk_index: int, d_out: int):
-        self._ck(self.L.skm_route_scatter(self._h, chunk_index, d_out))
-
-    # fused route + exchange (peer stores over NVLink)
-    def p2p_arena_create(self, entries_per_slot: int, n_slots: int = 2):
-        self._ck(self.L.skm_p2p_arena_create(self._h, entries_per_slot, n_slots))
-
-    def p2p_arena_handle(self, slot: int) -> bytes:
+    def mg_arena_handle(self) -> bytes:
         buf = (C.c_uint8 * 64)()
-        self._ck(self.L.skm_p2p_arena_handle(self._h, slot, buf))
+        self._ck(self.L.skm_mg_arena_handle(self._h, buf))
         return bytes(buf)
 
-    def p2p_arena_ptr(self, slot: int) -> int:
+    def mg_arena_ptr(self) -> int:
         p = C.c_void_p()
-        self._ck(self.L.skm_p2p_arena_ptr(self._h, slot, C.byref(p)))
+        self._ck(self.L.skm_mg_arena_ptr(self._h, C.byref(p)))
         return p.value or 0
 
-    def p2p_open_peer(self, peer_rank: int, slot: int, handle: bytes):
+    def mg_open_peer(self, peer_rank: int, handle: bytes):
         buf = (C.c_uint8 * 64).from_buffer_copy(handle)
-        self._ck(self.L.skm_p2p_open_peer(self._h, peer_rank, slot, buf))
+        self._ck(self.L.skm_mg_open_peer(self._h, peer_rank, buf))
 
-    def p2p_set_peer(self, peer_rank: int, slot: int, d_ptr: int):
-        self._ck(self.L.skm_p2p_set_peer(self._h, peer_rank, slot, d_ptr))
+    def mg_set_peer(self, peer_rank: int, d_ptr: int, peer_device: int = -1):
+        self._ck(self.L.skm_mg_set_peer(self._h, peer_rank, d_ptr, peer_device))
 
-    def route_scatter_p2p(self, chunk_index: int, slot: int, dst_offsets):
-        off = np.ascontiguousarray(dst_offsets, dtype=np.uint64)
-        self._ck(self.L.skm_route_scatter_p2p(self._h, chunk_index, slot, off.ctypes.data))
+    def mg_finalize(self, comm_struct):
+        """Collective.  comm_struct: a ctypes skm_comm (sharkmer_b200.multigpu builds one over torch.distributed)."""
+        self._ck(self.L.skm_mg_finalize(self._h, C.byref(comm_struct)))
 
-    def route_scatter_dma(self, chunk_index: int, slot: int, dst_offsets):
-        off = np.ascontiguousarray(dst_offsets, dtype=np.uint64)
-        self._ck(self.L.skm_route_scatter_dma(self._h, chunk_index, slot, off.ctypes.data))
+    def mg_bytes_sent(self) -> int:
+        n = C.c_uint64()
+        self._ck(self.L.skm_mg_bytes_sent(self._h, C.byref(n)))
+        return n.value
 
     def insert_kmers_device(self, d_ptr: int, n: int):
         self._ck(self.L.skm_insert_kmers_device(self._h, d_ptr, n))
-
-    def chunks_ready(self) -> int:
-        n = C.c_uint32()
-        self._ck(self.L.skm_chunks_ready(self._h, C.byref(n)))
-        return n.value
-
-    def dma_wait(self, slot: int): self._ck(self.L.skm_dma_wait(self._h, slot))
-    def snapshot_histogram_async(self, chunk_i: int): self._ck(self.L.skm_snapshot_histogram_async(self._h, chunk_i))
 
     def snapshot_histogram(self, chunk_i: int):
         self._ck(self.L.skm_snapshot_histogram(self._h, chunk_i))

@@ -1,46 +1,35 @@
-"""Hash-sharded k-mer counting over N GPUs: one process per GPU, torch.distributed
-for the plumbing (NCCL over NVLink/NVSwitch on GPUs; gloo in the CPU tests).
+"""Hash-sharded k-mer counting over N GPUs.
 
-The path shards by k-mer hash: every rank packs and extracts the
-k-mers of ITS slice of the reads and buckets them by (owner rank, table region of that
-owner) — owner = floor(hash * N / 2^64), include/skm_common.h — so one pass both groups
-the k-mers by destination and leaves every destination's run sorted by the receiver's
-table regions.  An all-to-all delivers each rank's range; the owner inserts the runs
-region by region (L2-resident) with no cross-GPU atomics.  With --chunks n > 0 every chunk boundary is a global
-barrier: all ranks finish exchanging and inserting chunk i before histogram column i
-is taken (src/io.rs:1016-1028 merges chunks in index order).  The result is
-independent of N.
+The multi-GPU path lives behind the C ABI (include/sharkmer_b200.h, skm_mg_* / skm_group_*):
+every rank buckets and tile-sorts its batches as on one GPU, the copy engines push the other
+owners' slices into their receive arenas over NVLink at ingest time, and the collective
+skm_mg_finalize counts everything in chunk order and sums the histogram columns.  The library
+only borrows ONE primitive from its host: an all-gather of host bytes among the ranks.
 
-Two exchange paths:
-  * "p2p" (default on GPUs, N <= 16): fused route + exchange.  The scatter kernel stores every
-    destination's runs straight into that rank's receive arena through a CUDA-IPC mapping (peer
-    stores over NVLink/NVSwitch) — no local list, no collective copy; the transfer overlaps the
-    extraction tile by tile inside one kernel.  Steps are ordered by a 1-element all-reduce used
-    as a stream-ordered barrier; two arenas per rank give double buffering.
-  * "dma": batches are bucketed at ingest time; per chunk the copy engines push each
-    destination's block into its arena over NVLink while a CPU (gloo) group carries the counts
-    and the two barriers: the exchange needs no SM at all and hides behind the inserts.
-  * "nccl": route to a local list, then all_to_all_single; the exchange of chunk c+1 overlaps
-    the insert of chunk c (double-buffered torch tensors).  Also the path of the CPU tests (gloo).
-
-`engine` is anything with the routing interface of sharkmer_b200.kmer.Engine
-(route_count / route_scatter / insert_runs_device / snapshot_histogram / histogram /
-finalize_external); the CPU tests drive this same code with a recording stand-in.
+This module supplies that primitive for the two ways of running N ranks:
+  * ShardedCounter — one process per GPU (torchrun): the all-gather is torch.distributed on a
+    CPU (gloo) group; arenas are wired through CUDA IPC handles.
+  * Group          — all ranks in one process (skm_group_*): threads + an in-process all-gather
+    inside the library; arenas are wired by device pointers.  Several ranks may share a GPU,
+    which is how the multi-rank path is tested on a one-GPU box.
+Both also offer the table services sPCR needs over the sharded table (lookup, scan_oligos).
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _lib
+
 
 def bind_to_gpu_numa(device_index: int) -> list[int] | None:
     """Pin the calling thread (and the threads it spawns later) to the CPUs NVML reports as local to
     GPU `device_index`, so that pinned staging buffers allocated afterwards land on that GPU's NUMA
-    node. With one process per GPU and no binding, half the ranks of an 8-GPU box read their FASTQ
-    bytes across the socket interconnect and host->device bandwidth drops by 2x (profiles/
-    experiments_r01.md #24). Call before the first pinned allocation; returns the CPU list, or None
-    when NVML is unavailable (binding is an optimisation, never a requirement)."""
+    node.  Call before the first pinned allocation; returns the CPU list, or None when NVML is
+    unavailable (binding is an optimisation, never a requirement)."""
     import os
     try:
         import pynvml
@@ -65,273 +54,87 @@ def bind_to_gpu_numa(device_index: int) -> list[int] | None:
         return None
 
 
-class _CudaArray:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+# ---- the all-gather the library borrows (skm_comm) ------------------------------------------------
+
+_ALLGATHER = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
 
 
-def _device_i64(ptr: int, n: int, device) -> torch.Tensor:
-    """Zero-copy int64 view of n u64 values at a raw device pointer."""
-    return torch.as_tensor(_CudaArray(ptr, n), device=device)
+class SkmComm(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("allgather", _ALLGATHER)]
+
+
+class TorchComm:
+    """skm_comm over a torch.distributed group of CPU tensors (gloo)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.calls = 0
+        self.bytes = 0
+        self.error = None
+
+        def _allgather(_user, send, recv, n_bytes):
+            try:
+                n = int(n_bytes)
+                src = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), shape=(n,))
+                dst = np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_uint8)), shape=(n * self.world,))
+                dist.all_gather_into_tensor(torch.from_numpy(dst), torch.from_numpy(src.copy()), group=self.group)
+                self.calls += 1
+                self.bytes += n
+                return 0
+            except Exception as e:  # never let an exception cross the C boundary
+                self.error = e
+                return 1
+
+        self._cb = _ALLGATHER(_allgather)       # keep the callback object alive
+        self.struct = SkmComm(None, self._cb)
 
 
 class ShardedCounter:
-    def __init__(self, engine, n_chunks: int, chunks_arg: int, histo_max: int, device: torch.device,
-                 group=None, stream=None, exchange: str = "nccl", arena_entries: int = 0):
+    """One rank of a hash-sharded count (one process per GPU).  `engine` is this rank's
+    sharkmer_b200.kmer.Engine, created with n_ranks / rank; ingest into it as usual, then call
+    finalize() on every rank."""
+
+    def __init__(self, engine, device: torch.device | None = None, group=None, cpu_group=None, arena_bytes: int = 0):
         self.e = engine
-        self.n_chunks = n_chunks
-        self.chunks_arg = chunks_arg
-        self.histo_max = histo_max
         self.device = device
-        self.group = group
+        self.group = group                      # for the table services (device tensors: NCCL on GPUs)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.stream = stream  # torch.cuda.Stream the engine launches on (None on CPU)
-        self.bytes_sent = 0
-        self.kmers_received = 0
-        self.exchange = exchange
-        if exchange in ("p2p", "dma"):
-            self._setup_p2p(arena_entries)
+        # the library's all-gather runs on a CPU group: metadata never needs an SM
+        if cpu_group is None:
+            cpu_group = group if dist.get_backend(group) == "gloo" else dist.new_group(backend="gloo")
+        self.comm = TorchComm(cpu_group)
+        if arena_bytes and self.world > 1:
+            self._wire(arena_bytes, cpu_group)
 
-    def _setup_p2p(self, arena_entries: int):
-        """Allocate this rank's receive arenas and map every peer's through CUDA IPC."""
+    def _wire(self, arena_bytes: int, cpu_group):
+        """Allocate this rank's receive arena and map every peer's through CUDA IPC."""
         e = self.e
-        # "dma": one arena per chunk (up to 16), so that every chunk can be exchanged ahead of its
-        # insert while the chip is busy; "p2p": two (double buffering)
-        self._n_slots = min(16, self.n_chunks) if self.exchange == "dma" else 2
-        e.p2p_arena_create(int(arena_entries), self._n_slots)
-        mine = [e.p2p_arena_handle(slot) for slot in range(self._n_slots)]
-        allh = [None] * self.world
-        dist.all_gather_object(allh, mine, group=self.group)
+        e.mg_arena_create(int(arena_bytes))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, e.mg_arena_handle(), group=cpu_group)
         for r in range(self.world):
             if r != self.rank:
-                for slot in range(self._n_slots):
-                    e.p2p_open_peer(r, slot, allh[r][slot])
-        self._tick = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self._regions = e.route_regions()
-        # control plane of the "dma" exchange: a CPU group, so that metadata and barriers never
-        # need an SM (created collectively by every rank)
-        self._cpu_group = dist.new_group(backend="gloo") if self.exchange == "dma" else None
+                e.mg_open_peer(r, handles[r])
 
-    # -- small helpers ---------------------------------------------------------
-    def _exchange_counts(self, counts: np.ndarray) -> np.ndarray:
-        """counts[d, r] = k-mers this rank sends to rank d for d's table region r.
-        Returns recv[s, r] = k-mers rank s sends to this rank for our region r."""
-        send = torch.as_tensor(np.ascontiguousarray(counts).astype(np.int64), device=self.device)
-        recv = torch.empty_like(send)
-        dist.all_to_all_single(recv, send, group=self.group)  # row d goes to rank d
-        return recv.cpu().numpy()
-
-    def _alloc(self, n: int) -> torch.Tensor:
-        return torch.empty(max(int(n), 1), dtype=torch.int64, device=self.device)
-
-    def _ptr(self, t: torch.Tensor) -> int:
-        return t.data_ptr()
-
-    def _on_stream(self):
-        if self.stream is not None:
-            return torch.cuda.stream(self.stream)
-        import contextlib
-        return contextlib.nullcontext()
-
-    # -- the chunk loop ----------------------------------------------------------
     def finalize(self) -> np.ndarray | None:
-        """Counts every chunk in order.  Returns the (n_chunks, histo_max+2) cumulative
+        """Collective: counts every chunk in order.  Returns the (n_chunks, histo_max+2) cumulative
         histogram columns summed over ranks (None when chunks == 0)."""
-        # Issued with the engine's main stream current: tensors are allocated on it and the final
-        # all-reduce is ordered after the inserts.
-        with self._on_stream():
-            out = self._finalize()
-        self.e.sync()  # waits for every stream; raises if a pack kernel met an invalid base
-        return out
-
-    def _finalize(self):
-        if self.exchange == "dma":
-            return self._finalize_dma()
-        if self.exchange == "p2p":
-            return self._finalize_p2p()
-        return self._finalize_nccl()
-
-    def _streams(self):
-        """(main, routing) torch streams wrapping the engine's CUDA streams; None on CPU."""
-        if self.stream is None:
-            return None, None
-        main = torch.cuda.ExternalStream(self.e.stream_handle(0), device=self.device)
-        part = torch.cuda.ExternalStream(self.e.stream_handle(1), device=self.device)
-        return main, part
-
-    def _finalize_p2p(self):
-        """Software pipeline: chunk c+1 is routed (extract + bucket + peer stores + barrier, routing
-        stream) while chunk c is inserted (main stream)."""
         e = self.e
-        e.finalize_external()
-        main, part = self._streams()
-
-        def route(c, prev_insert_done):
-            slot = c & 1
-            with torch.cuda.stream(part):
-                # per-(destination, region) counts of this rank's k-mers, left on the device and
-                # all-gathered from there: one collective and one host sync per chunk
-                d_counts = e.route_count_device(c)
-                mine = _device_i64(d_counts, self.world * self._regions, self.device)
-                allt = torch.empty(self.world * self.world * self._regions, dtype=torch.int64, device=self.device)
-                dist.all_gather_into_tensor(allt, mine, group=self.group)
-                allc = allt.cpu().numpy().reshape(self.world, self.world, self._regions)  # [src, dst, region]
-                counts = allc[self.rank].astype(np.uint64)
-                rcounts = np.ascontiguousarray(allc[:, self.rank, :]).astype(np.uint64)
-                m = allc.sum(axis=2)                              # m[s, d] = k-mers s sends to d
-                per_dst = m[self.rank]
-                e.route_set_counts(c, counts)
-                # this rank's block in every destination's arena starts after the lower ranks' blocks
-                if self.exchange == "dma":   # bucket locally, copy engines push the runs to the peers
-                    e.route_scatter_dma(c, slot, m[:self.rank, :].sum(axis=0))
-                else:                          # fused: extract + bucket + peer stores in one kernel
-                    e.route_scatter_p2p(c, slot, m[:self.rank, :].sum(axis=0))
-                # Barrier c tells the peers two things: (1) my stores of chunk c have landed, and
-                # (2) my insert of chunk c-1 is finished, so after this barrier they may overwrite
-                # the other arena slot (their scatter of chunk c+1).
-                if prev_insert_done is not None:
-                    part.wait_event(prev_insert_done)
-                dist.all_reduce(self._tick, group=self.group)    # stream-ordered barrier
-                done = torch.cuda.Event()
-                done.record(part)
-            self.bytes_sent += 8 * (int(per_dst.sum()) - int(per_dst[self.rank]))
-            self.kmers_received += int(m[:, self.rank].sum())
-            return slot, rcounts, done
-
-        nxt = route(0, None)
-        for c in range(self.n_chunks):
-            slot, rcounts, done = nxt
-            main.wait_event(done)
-            e.insert_runs_device(e.p2p_arena_ptr(slot), rcounts)     # asynchronous, main stream
-            inserted = torch.cuda.Event()
-            inserted.record(main)
-            if c + 1 < self.n_chunks:
-                nxt = route(c + 1, inserted)                      # overlaps the insert just queued
-            if self.chunks_arg > 0:
-                e.snapshot_histogram(c)                          # syncs the main stream
-            else:
-                e.sync()
-        if self.chunks_arg == 0:
+        try:
+            e.mg_finalize(self.comm.struct)
+        except Exception:
+            if self.comm.error is not None:
+                raise self.comm.error
+            raise
+        if e.chunks == 0:
             return None
-        cols = np.stack([e.histogram(c) for c in range(self.n_chunks)]).astype(np.int64)
-        t = torch.as_tensor(cols, device=self.device)
-        dist.all_reduce(t, group=self.group)
-        return t.cpu().numpy().astype(np.uint64)
+        return np.stack([e.histogram(c) for c in range(e.n_chunks)])
 
-    def _finalize_dma(self):
-        """Exchange with zero SM time: batches were bucketed by (owner, region) at ingest time; per
-        chunk the HOST gathers the counts and runs the two barriers over a CPU (gloo) group, and
-        the copy engines push every destination's block into its arena over NVLink.  Nothing here
-        needs a free SM, so it all proceeds while the persistent insert kernel of the previous
-        chunk owns the chip (a small NCCL kernel would have to wait for it to finish).
-
-            host, chunk c:  wait own insert(c-2) -> all-gather counts (= slot free everywhere)
-                            -> peer copies(c) -> wait for them -> BARRIER (all blocks landed)
-                            -> queue insert(c), queue histogram column c
-        """
-        e = self.e
-        e.finalize_external()
-        main, _ = self._streams()
-        cpu = self._cpu_group
-        regions = self._regions
-        n_slots = self._n_slots
-        inserted, pending = {}, {}
-
-        def exchange(c):
-            """Queue the peer copies of chunk c into arena slot c % n_slots (asynchronous)."""
-            slot = c % n_slots
-            counts = e.route_count(c, self.world)                 # host: waits for chunk c's bucketing only
-            if c >= n_slots:
-                inserted[c - n_slots].synchronize()               # my reads of this arena slot are over ...
-            mine = torch.from_numpy(counts.astype(np.int64).reshape(-1))
-            allt = torch.empty(self.world * mine.numel(), dtype=torch.int64)
-            dist.all_gather_into_tensor(allt, mine, group=cpu)    # ... and, once this returns, everybody's
-            allc = allt.numpy().reshape(self.world, self.world, regions)   # [src, dst, region]
-            m = allc.sum(axis=2)                                  # m[s, d] = k-mers s sends to d
-            e.route_scatter_dma(c, slot, m[:self.rank, :].sum(axis=0))
-            pending[c] = np.ascontiguousarray(allc[:, self.rank, :]).astype(np.uint64)
-            self.bytes_sent += 8 * (int(m[self.rank].sum()) - int(m[self.rank, self.rank]))
-            self.kmers_received += int(m[:, self.rank].sum())
-
-        nxt = 0
-        for c in range(self.n_chunks):
-            # keep the exchange as far ahead of the inserts as there are arena slots: the copies then
-            # run while the chip is bucketing (SM-bound) instead of inserting (memory-bound), which
-            # slows the copy engines down 3-4x
-            # ... but only as far as every rank has its batches on the device already: a chunk that
-            # is still arriving from the host must not hold up the inserts of the earlier ones
-            mine = torch.tensor([e.chunks_ready()], dtype=torch.int64)
-            allr = torch.empty(self.world, dtype=torch.int64)
-            dist.all_gather_into_tensor(allr, mine, group=cpu)
-            ahead = max(int(allr.min()), c + 1)
-            while nxt < self.n_chunks and nxt < min(ahead, c + n_slots):
-                exchange(nxt)
-                nxt += 1
-            e.dma_wait(c % n_slots)                               # my blocks of chunk c have landed at the peers
-            dist.barrier(group=cpu)                               # ... and everybody's at mine
-            e.insert_runs_device(e.p2p_arena_ptr(c % n_slots), pending.pop(c))  # asynchronous, main stream
-            ev = torch.cuda.Event()
-            ev.record(main)
-            inserted[c] = ev
-            if self.chunks_arg > 0:
-                e.snapshot_histogram_async(c)
-        if self.chunks_arg == 0:
-            e.sync()
-            return None
-        cols = np.stack([e.histogram(c) for c in range(self.n_chunks)]).astype(np.int64)
-        t = torch.as_tensor(cols, device=self.device)
-        dist.all_reduce(t, group=self.group)
-        return t.cpu().numpy().astype(np.uint64)
-
-    def _finalize_nccl(self):
-        """Route to a local list, all_to_all_single, insert.  On GPUs the routing + collective of
-        chunk c+1 run on the routing stream while chunk c is inserted on the main stream."""
-        import contextlib
-        e = self.e
-        e.finalize_external()  # ingest is complete on every rank; the chunk loop is ours
-        main, part = self._streams()
-        on_part = (lambda: torch.cuda.stream(part)) if part is not None else contextlib.nullcontext
-
-        def route(c):
-            with on_part():
-                counts = e.route_count(c, self.world)            # (world, regions): per destination and region
-                rcounts = self._exchange_counts(counts)          # (world, regions): per source and region
-                per_dst, per_src = counts.sum(axis=1), rcounts.sum(axis=1)
-                n_send, n_recv = int(per_dst.sum()), int(per_src.sum())
-                send, recv = self._alloc(n_send), self._alloc(n_recv)
-                e.route_scatter(c, self._ptr(send))              # bucket order = destination-major
-                dist.all_to_all_single(recv[:n_recv], send[:n_send],
-                                       output_split_sizes=[int(x) for x in per_src],
-                                       input_split_sizes=[int(x) for x in per_dst], group=self.group)
-                done = None
-                if part is not None:
-                    done = torch.cuda.Event()
-                    done.record(part)
-                    recv.record_stream(main)                     # consumed by the insert on the main stream
-            self.bytes_sent += 8 * (n_send - int(per_dst[self.rank]))
-            self.kmers_received += n_recv
-            return recv, rcounts, done
-
-        nxt = route(0)
-        for c in range(self.n_chunks):
-            recv, rcounts, done = nxt
-            if done is not None:
-                main.wait_event(done)
-            e.insert_runs_device(self._ptr(recv), rcounts)       # region-major over all sources' runs
-            if c + 1 < self.n_chunks:
-                nxt = route(c + 1)                                # overlaps the insert just queued
-            if self.chunks_arg > 0:
-                e.snapshot_histogram(c)                          # this rank's partial column (syncs main)
-            else:
-                e.sync()
-            del recv
-        if self.chunks_arg == 0:
-            return None
-        cols = np.stack([e.histogram(c) for c in range(self.n_chunks)]).astype(np.int64)
-        t = torch.as_tensor(cols, device=self.device)
-        dist.all_reduce(t, group=self.group)                  # histogram = sum of the partitions' histograms
-        return t.cpu().numpy().astype(np.uint64)
+    @property
+    def bytes_sent(self) -> int:
+        return self.e.mg_bytes_sent()
 
     # -- table services over the sharded table (what sPCR needs; collective: every rank calls them
     #    with the same arguments and gets the same answer) ----------------------------------------
@@ -369,3 +172,83 @@ class ShardedCounter:
         t = torch.as_tensor([int(local[k]) for k in keys], dtype=torch.int64, device=self.device)
         dist.all_reduce(t, group=self.group)
         return dict(zip(keys, t.cpu().tolist()))
+
+
+class Group:
+    """All ranks in one process (skm_group_*): n ctx's, possibly several per GPU."""
+
+    def __init__(self, k: int, chunks: int, histo_max: int, devices, arena_bytes_per_rank: int,
+                 capacity_hint: int = 0, insert_mode: int = _lib.INSERT_AUTO):
+        from .kmer import Engine, SkmError
+        self.L = _lib.load()
+        self.n = len(devices)
+        p = _lib.SkmParams(struct_size=C.sizeof(_lib.SkmParams), k=k, chunks=chunks, insert_mode=insert_mode,
+                           histo_max=histo_max, capacity_hint=capacity_hint, device=-1, n_ranks=self.n, rank=0,
+                           reserved=0, stream=0)
+        devs = (C.c_int32 * self.n)(*devices)
+        h = C.c_void_p()
+        rc = self.L.skm_group_create(C.byref(p), self.n, devs, int(arena_bytes_per_rank), C.byref(h))
+        self._h = h
+        if rc:
+            msg = self.L.skm_group_last_error(h).decode() if h else "skm_group_create failed"
+            if h:
+                self.L.skm_group_destroy(h)
+            self._h = None
+            raise SkmError(rc, msg)
+        # borrowed engines over the members' ctx's (the group owns them)
+        self.engines = []
+        for r in range(self.n):
+            e = Engine.__new__(Engine)
+            e.L, e.k, e.chunks, e.histo_max, e.n_chunks = self.L, k, chunks, histo_max, max(1, chunks)
+            e._h = C.c_void_p(self.L.skm_group_ctx(h, r))
+            e.close = lambda: None  # owned by the group
+            self.engines.append(e)
+
+    def _ck(self, rc):
+        from .kmer import SkmError
+        if rc:
+            raise SkmError(rc, self.L.skm_group_last_error(self._h).decode(errors="replace"))
+
+    def finalize(self):
+        self._ck(self.L.skm_group_finalize(self._h))
+
+    def reset(self):
+        self._ck(self.L.skm_group_reset(self._h))
+
+    def histogram(self, chunk_i: int) -> np.ndarray:
+        return self.engines[0].histogram(chunk_i)     # every member holds the global columns
+
+    def export_sorted(self):
+        parts = [e.export(sorted=False) for e in self.engines]
+        keys = np.concatenate([p[0] for p in parts])
+        counts = np.concatenate([p[1] for p in parts])
+        order = np.argsort(keys, kind="stable")
+        return keys[order], counts[order]
+
+    def lookup(self, kmers, min_count: int = 0, mode: int = 0):
+        """A k-mer lives in exactly one partition: the answer is the maximum over the members."""
+        counts = None
+        for e in self.engines:
+            c, _ = e.lookup(kmers, min_count, mode)
+            counts = c if counts is None else np.maximum(counts, c)
+        return counts, counts > 0
+
+    def scan_oligos(self, oligos, oligo_length: int, min_count: int):
+        parts = [e.scan_oligos(oligos, oligo_length, min_count) for e in self.engines]
+        keys = np.concatenate([p[0] for p in parts])
+        counts = np.concatenate([p[1] for p in parts])
+        order = np.argsort(keys, kind="stable")
+        return keys[order], counts[order]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for e in self.engines:
+                e._h = None
+            self.L.skm_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

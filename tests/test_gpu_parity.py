@@ -4,6 +4,7 @@ integer work, so every comparison is equality."""
 import json
 import os
 import random
+import sys
 
 import numpy as np
 import pytest
@@ -11,6 +12,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMPTY = 0xFFFFFFFFFFFFFFFF
 U32_MAX = 0xFFFFFFFF
 
@@ -491,96 +493,141 @@ def test_reset_reuses_ctx(skm, oracle):
         compare(e, run, 2)
 
 
-# ---- (7) hash-sharded path, two table partitions on one GPU ----------------------------------------
+# ---- (7) hash-sharded path: several ranks on one GPU ---------------------------------------------------
 
-def test_sharded_two_partitions_single_process(skm, oracle):
-    """The multi-GPU building blocks (route_count / route_scatter / insert_kmers_device /
-    snapshot_histogram) with two ctx's (ranks 0 and 1 of 2) on the same device; the
-    all-to-all is done by slicing device tensors.  Result must equal the oracle's and be
-    split exactly by owner rank."""
-    import torch
+def _feed_ranks(engines, reads, n_reads, line, chunks, world):
+    """1000-read batches round-robin over chunks (src/io.rs:355-361); the batches of a chunk are
+    dealt to the ranks in turn."""
+    n_chunks = max(1, chunks)
+    for b in range((n_reads + 999) // 1000):
+        c = b % n_chunks
+        r = (b // n_chunks) % world
+        engines[r].ingest_batch(c, reads[b * 1000 * line:min((b + 1) * 1000, n_reads) * line])
+
+
+def _check_sharded(group_like, engines, run, chunks, world):
     from sharkmer_b200 import common
-    L, n, k, chunks, hmax, world = 120, 12_000, 25, 3, 100, 2
-    reads = oracle.synth_reads(31, 40_000, L, 0.01, 0.001, 0, n)
-    run = run_oracle(oracle, reads, k, chunks, hmax)
-    line = L + 1
-    engs = [skm.Engine(k, chunks, hmax, n_ranks=world, rank=r) for r in range(world)]
-    # rank r ingests every other 1000-read batch of each chunk
-    nb = n // 1000
-    for b in range(nb):
-        c = b % chunks
-        r = (b // chunks) % world
-        engs[r].ingest_batch(c, reads[b * 1000 * line:(b + 1) * 1000 * line])
-    for e in engs:
-        e.finalize_external()
-    regions = engs[0].route_regions()
-    for c in range(chunks):
-        counts = [e.route_count(c, world) for e in engs]          # each (world, regions)
-        sends = []
-        for e, cnt in zip(engs, counts):
-            t = torch.empty(max(int(cnt.sum()), 1), dtype=torch.int64, device="cuda")
-            e.route_scatter(c, t.data_ptr())
-            e.sync()
-            sends.append(t)
-        for dst in range(world):
-            parts, rc = [], np.zeros((world, regions), dtype=np.uint64)
-            for src in range(world):
-                off = int(counts[src][:dst].sum())
-                n = int(counts[src][dst].sum())
-                parts.append(sends[src][off:off + n])
-                rc[src] = counts[src][dst]
-            recv = torch.cat(parts).contiguous()
-            engs[dst].insert_runs_device(recv.data_ptr(), rc)
-            engs[dst].snapshot_histogram(c)
-        col = sum(e.histogram(c).astype(np.int64) for e in engs)
-        assert (col == run.histogram(c).astype(np.int64)).all(), c
     merged = {}
-    for r, e in enumerate(engs):
+    for r, e in enumerate(engines):
         keys, cnts = e.export(sorted=True)
-        assert all(common.owner_rank(common.hash_kmer(int(x)), world) == r for x in keys[:2000])
+        assert all(common.owner_rank(common.hash_kmer(int(x)), world) == r for x in keys[:3000])
+        assert not (set(keys[:3000].tolist()) & set(merged))
         merged.update(zip(keys.tolist(), cnts.tolist()))
     okeys, ocounts = run.table().export_sorted()
+    assert len(merged) == okeys.size
     assert merged == dict(zip(okeys.tolist(), ocounts.tolist()))
-    assert sum(e.chunk_totals(c).n_kmers for e in engs for c in range(chunks)) == run.n_kmers_ingested
+    for c in range(chunks):   # every rank holds the columns summed over all ranks
+        for e in engines:
+            assert (e.histogram(c) == run.histogram(c)).all(), c
+    assert sum(int(e.totals().n_kmers) for e in engines) == run.n_kmers_ingested
+    assert sum(int(e.totals().n_unique) for e in engines) == okeys.size
+    assert sum(int(e.totals().n_reads) for e in engines) == run.n_reads_ingested
 
 
-def test_sharded_p2p_scatter_single_process(skm, oracle):
-    """Fused route + exchange: each ctx's scatter kernel stores straight into the destination
-    ctx's receive arena (peer pointers set directly: both partitions live in this process)."""
-    L, n, k, chunks, hmax, world = 100, 9_000, 21, 3, 100, 2
-    reads = oracle.synth_reads(33, 30_000, L, 0.01, 0.001, 0, n)
+@pytest.mark.parametrize("world,k,chunks,mode", [(2, 25, 3, 0), (3, 21, 5, 0), (2, 31, 0, 0), (4, 21, 2, 2)])
+def test_sharded_group_vs_oracle(skm, oracle, world, k, chunks, mode):
+    """skm_group_*: `world` ranks in one process on ONE GPU — bucketing by (owner, region), tile sort,
+    copy-engine exchange into the peers' arenas, collective finalize, column sum.  Sorted table
+    (partition by partition, each key on its owner) and every histogram column vs the oracle."""
+    from sharkmer_b200.multigpu import Group
+    L, n, hmax = 120, 23_000, 100
+    reads = oracle.synth_reads(31 + world, 50_000, L, 0.01, 0.001, 0, n)
     run = run_oracle(oracle, reads, k, chunks, hmax)
-    line = L + 1
-    engs = [skm.Engine(k, chunks, hmax, n_ranks=world, rank=r) for r in range(world)]
-    for e in engs:
-        e.p2p_arena_create(n * L, 2)
-    for e in engs:
-        for r in range(world):
-            for slot in range(2):
-                e.p2p_set_peer(r, slot, engs[r].p2p_arena_ptr(slot))
+    g = Group(k, chunks, hmax, [0] * world, arena_bytes_per_rank=96 << 20, insert_mode=mode)
+    _feed_ranks(g.engines, reads, n, L + 1, chunks, world)
+    g.finalize()
+    _check_sharded(g, g.engines, run, chunks, world)
+    assert all(e.mg_bytes_sent() > 0 for e in g.engines)
+    # sharded table services answer like one table
+    keys, counts = run.table().export_sorted()
+    probe = np.concatenate([keys[::97][:400], np.array([12345, 99999999], dtype=np.uint64)])
+    got, found = g.lookup(probe, 0, 1)
+    want = dict(zip(keys.tolist(), counts.tolist()))
+    assert got.tolist() == [want.get(int(x), 0) for x in probe]
+    # a second sample through the same group (reset is collective)
+    g.reset()
+    reads2 = oracle.synth_reads(77, 30_000, L, 0.01, 0.0, 0, 8000)
+    run2 = run_oracle(oracle, reads2, k, chunks, hmax)
+    _feed_ranks(g.engines, reads2, 8000, L + 1, chunks, world)
+    g.finalize()
+    _check_sharded(g, g.engines, run2, chunks, world)
+    g.close()
+
+
+def test_sharded_group_skewed_and_unbalanced(skm, oracle):
+    """Overflowing capped buckets on a sender (poly-A reads: one k-mer millions of times) take the
+    exact re-bucketing path and are shipped again; one rank gets no reads at all."""
+    from sharkmer_b200.multigpu import Group
+    L, n, k, chunks, hmax, world = 100, 16_000, 21, 2, 1000, 3
+    reads = oracle.synth_reads(5, 40_000, L, 0.01, 0.001, 0, n).copy()
+    lines = reads.reshape(n, L + 1)
+    lines[::3, :L] = ord("A")          # a third of the reads are poly-A
+    run = run_oracle(oracle, reads, k, chunks, hmax)
+    g = Group(k, chunks, hmax, [0] * world, arena_bytes_per_rank=96 << 20, insert_mode=2)
+    # rank 2 ingests nothing
+    n_chunks = max(1, chunks)
     for b in range(n // 1000):
-        engs[(b // chunks) % world].ingest_batch(b % chunks, reads[b * 1000 * line:(b + 1) * 1000 * line])
-    for e in engs:
-        e.finalize_external()
-    regions = engs[0].route_regions()
-    for c in range(chunks):
-        slot = c & 1
-        counts = [e.route_count(c, world) for e in engs]
-        m = np.array([[int(counts[s][d].sum()) for d in range(world)] for s in range(world)])
-        for s, e in enumerate(engs):
-            e.route_scatter_p2p(c, slot, m[:s, :].sum(axis=0))
-        for e in engs:
-            e.sync()  # (single process: a sync stands in for the stream-ordered barrier)
-        for d, e in enumerate(engs):
-            rc = np.stack([counts[s][d] for s in range(world)])
-            assert rc.shape == (world, regions)
-            e.insert_runs_device(e.p2p_arena_ptr(slot), rc)
-            e.snapshot_histogram(c)
-        col = sum(e.histogram(c).astype(np.int64) for e in engs)
-        assert (col == run.histogram(c).astype(np.int64)).all(), c
+        g.engines[(b // n_chunks) % 2].ingest_batch(b % n_chunks, reads[b * 1000 * (L + 1):(b + 1) * 1000 * (L + 1)])
+    g.finalize()
+    _check_sharded(g, g.engines, run, chunks, world)
+    g.close()
+
+
+def _mp_worker(rank, world, port, q, k, chunks, hmax, L, n, seed):
+    import os
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch
+    from oracle import oracle as o
+    from sharkmer_b200 import kmer
+    from sharkmer_b200.multigpu import ShardedCounter
+    torch.cuda.set_device(0)
+    reads = o.synth_reads(seed, 50_000, L, 0.01, 0.001, 0, n)
+    e = kmer.Engine(k, chunks, hmax, device=0, n_ranks=world, rank=rank)
+    sc = ShardedCounter(e, torch.device("cuda", 0), arena_bytes=64 << 20)
+    line = L + 1
+    for b in range(n // 1000):
+        if (b // chunks) % world == rank:
+            e.ingest_batch(b % chunks, reads[b * 1000 * line:(b + 1) * 1000 * line])
+    cols = sc.finalize()
+    keys, cnts = e.export(sorted=True)
+    t = e.totals()
+    q.put((rank, keys, cnts, cols, int(t.n_kmers)))
+    dist.barrier()
+    e.close()
+    dist.destroy_process_group()
+
+
+def test_sharded_two_processes_one_gpu(oracle):
+    """The torchrun shape of the multi-GPU path on a one-GPU box: two PROCESSES (two ranks) share
+    cuda:0, arenas mapped through CUDA IPC, the library's all-gather carried by gloo
+    (sharkmer_b200.multigpu.ShardedCounter, what bench.py uses at --gpus N).  No NCCL and no
+    kernel that waits for another rank: peer copies + host-side collectives only."""
+    import socket
+    import torch.multiprocessing as mp
+    world, k, chunks, hmax, L, n, seed = 2, 21, 4, 100, 100, 16_000, 44
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mp_worker, args=(r, world, port, q, k, chunks, hmax, L, n, seed)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    run = run_oracle(oracle, oracle.synth_reads(seed, 50_000, L, 0.01, 0.001, 0, n), k, chunks, hmax)
     merged = {}
-    for e in engs:
-        keys, cnts = e.export(sorted=True)
+    for _, keys, cnts, cols, _ in got:
+        assert not (set(keys[:2000].tolist()) & set(merged))
         merged.update(zip(keys.tolist(), cnts.tolist()))
+        for c in range(chunks):
+            assert (cols[c] == run.histogram(c)).all(), c
     okeys, ocounts = run.table().export_sorted()
     assert merged == dict(zip(okeys.tolist(), ocounts.tolist()))
+    assert sum(t[4] for t in got) == run.n_kmers_ingested

@@ -1,8 +1,15 @@
-"""The N>1 path on CPU: world_size-2 `gloo` run of sharkmer_b200.multigpu.ShardedCounter
-(the driver code the GPU bench uses) with a TEST-ONLY stand-in for the per-GPU engine that
-gets its k-mers from the oracle.  Checks the routing rule (owner = floor(hash * N / 2^64),
-buckets = (owner, region)), the split sizes, the per-chunk barrier order and the histogram all-reduce: the merged result
-must equal the single-process oracle, independent of N."""
+"""The N>1 path on CPU: world_size-2 and -3 `gloo` runs of sharkmer_b200.multigpu.ShardedCounter
+(the driver the GPU bench uses) with a TEST-ONLY stand-in for the per-GPU engine.
+
+On a GPU, skm_mg_finalize (C, CUDA) does the work and borrows one primitive from the host: an
+all-gather of host bytes (skm_comm).  The stand-in below follows the same protocol in Python and
+reaches the other ranks ONLY through that callback, called through its C function pointer exactly
+as the library calls it: header all-gather, directory all-gather, count in chunk order, totals
+all-gather, histogram-column all-gather + sum.  (Its k-mers travel inside the directory message;
+on GPUs they travel by peer copies.)  Checked: the ownership rule (owner = floor(hash * N / 2^64)),
+the callback marshalling over gloo, the chunk order, the column sum — the merged result must equal
+the single-process oracle, independent of N."""
+import ctypes as C
 import os
 import socket
 import sys
@@ -18,18 +25,15 @@ K, CHUNKS, HMAX, L, NREADS = 21, 4, 50, 100, 9000
 
 
 class FakeEngine:
-    """Routing interface of kmer.Engine over host memory; counting by a dict."""
+    """The multi-GPU interface of kmer.Engine over host memory; counting by a dict."""
 
     def __init__(self, oracle, common, reads_by_chunk, world, rank):
         self.o, self.common, self.world, self.rank = oracle, common, world, rank
         self.reads = reads_by_chunk
         self.table = {}
         self.cols = {}
-        self.routed = {}
-        self.keep = []
-
-    def finalize_external(self): pass
-    def sync(self): pass
+        self.chunks, self.n_chunks = CHUNKS, CHUNKS
+        self.sent = 0
 
     def _kmers(self, c):
         out = []
@@ -37,45 +41,54 @@ class FakeEngine:
             out.extend(self.o.kmers_from_ascii(s, K))
         return np.array(out, dtype=np.uint64)
 
-    REGIONS = 4
+    def _allgather(self, comm, arr: np.ndarray) -> np.ndarray:
+        """One call of the borrowed primitive, through the C function pointer."""
+        send = np.ascontiguousarray(arr)
+        recv = np.empty(self.world * send.size, dtype=send.dtype)
+        rc = comm.allgather(comm.user, send.ctypes.data, recv.ctypes.data, send.nbytes)
+        assert rc == 0
+        return recv.reshape(self.world, -1)
 
-    def route_regions(self):
-        return self.REGIONS
-
-    def route_count(self, c, world):
-        km = self._kmers(c)
-        log2r = self.REGIONS.bit_length() - 1
-        buckets = np.array([self.common.route_bucket(int(x), world, log2r) for x in km], dtype=np.int64)
-        order = np.argsort(buckets, kind="stable")
-        self.routed[c] = km[order]
-        return np.bincount(buckets, minlength=world * self.REGIONS).astype(np.uint64).reshape(world, self.REGIONS)
-
-    def route_scatter(self, c, ptr):
-        km = self.routed.pop(c)
-        dst = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_int64 * max(len(km), 1)).from_address(ptr))
-        dst[:len(km)] = km.view(np.int64)
-
-    def insert_runs_device(self, ptr, run_counts):
-        n = int(run_counts.sum())
-        assert run_counts.shape == (self.world, self.REGIONS)
-        if n == 0:
-            return
-        a = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_int64 * n).from_address(ptr)).view(np.uint64)
-        # every run must hold k-mers of exactly that (this rank, region) bucket
-        log2r = self.REGIONS.bit_length() - 1
-        pos = 0
-        for s in range(self.world):
-            for r in range(self.REGIONS):
-                for x in a[pos:pos + int(run_counts[s, r])].tolist():
-                    assert self.common.route_bucket(x, self.world, log2r) == self.rank * self.REGIONS + r
+    def mg_finalize(self, comm):
+        own = self.common.owner_rank
+        # (1) header: how many k-mers this rank sends to each owner, per chunk
+        per_chunk = [self._kmers(c) for c in range(CHUNKS)]
+        owners = [np.array([own(self.common.hash_kmer(int(x)), self.world) for x in km], dtype=np.int64) for km in per_chunk]
+        counts = np.array([[int((o == d).sum()) for d in range(self.world)] for o in owners], dtype=np.uint64)  # [chunk, dst]
+        allc = self._allgather(comm, counts.reshape(-1)).reshape(self.world, CHUNKS, self.world)              # [src, chunk, dst]
+        # (2) directory + payload, padded to the largest message
+        width = int(allc.sum(axis=(1, 2)).max())
+        msg = np.zeros(max(width, 1), dtype=np.uint64)
+        at = 0
+        for c in range(CHUNKS):
+            for d in range(self.world):
+                sel = per_chunk[c][owners[c] == d]
+                msg[at:at + sel.size] = sel
+                at += sel.size
+        self.sent = 8 * int(counts.sum() - counts[:, self.rank].sum())
+        allm = self._allgather(comm, msg)
+        # (3) count what this rank owns, chunk by chunk, a histogram column after each
+        for c in range(CHUNKS):
+            for s in range(self.world):
+                start = int(allc[s, :c, :].sum() + allc[s, c, :self.rank].sum())
+                for x in allm[s, start:start + int(allc[s, c, self.rank])].tolist():
+                    assert own(self.common.hash_kmer(x), self.world) == self.rank
                     self.table[x] = self.table.get(x, 0) + 1
-                pos += int(run_counts[s, r])
+            v = np.zeros(HMAX + 2, dtype=np.uint64)
+            for n in self.table.values():
+                v[n if n <= HMAX else HMAX + 1] += 1
+            self.cols[c] = v
+        # (4) totals: the conservation identity on the global sums (src/io.rs:1042-1047)
+        tot = self._allgather(comm, np.array([sum(self.table.values()), int(counts.sum())], dtype=np.uint64))
+        assert int(tot[:, 0].sum()) == int(tot[:, 1].sum())
+        # (5) columns summed over the partitions
+        cols = self._allgather(comm, np.stack([self.cols[c] for c in range(CHUNKS)]).reshape(-1))
+        total = cols.reshape(self.world, CHUNKS, HMAX + 2).sum(axis=0)
+        for c in range(CHUNKS):
+            self.cols[c] = total[c]
 
-    def snapshot_histogram(self, c):
-        v = np.zeros(HMAX + 2, dtype=np.uint64)
-        for n in self.table.values():
-            v[n if n <= HMAX else HMAX + 1] += 1
-        self.cols[c] = v
+    def mg_bytes_sent(self):
+        return self.sent
 
     def histogram(self, c):
         return self.cols[c]
@@ -126,8 +139,9 @@ def worker(rank, world, port, q):
             mine.extend(reads[b * 1000:(b + 1) * 1000])
         by_chunk.append(mine)
     eng = FakeEngine(o, common, by_chunk, world, rank)
-    sc = ShardedCounter(eng, CHUNKS, CHUNKS, HMAX, torch.device("cpu"))
+    sc = ShardedCounter(eng, torch.device("cpu"))
     cols = sc.finalize()
+    assert sc.comm.calls == 4 and sc.bytes_sent == eng.sent
     # every key this rank holds must be one it owns
     assert all(common.owner_rank(common.hash_kmer(x), world) == rank for x in eng.table)
     tot = sc.global_totals({"n_unique": len(eng.table), "n_kmers": sum(eng.table.values())})
@@ -177,7 +191,7 @@ def worker_pcr(rank, world, port, q):
             mine.extend(reads[b * 1000:(b + 1) * 1000])
         by_chunk.append(mine)
     eng = FakeEngine(o, common, by_chunk, world, rank)
-    sc = ShardedCounter(eng, CHUNKS, CHUNKS, HMAX, torch.device("cpu"))
+    sc = ShardedCounter(eng, torch.device("cpu"))
     sc.finalize()
     out = pcr.do_pcr(sc, K, "smp", PCRParams(fwd, rev, gene_name="locus", max_length=1000))
     probe = np.array(list(eng.table)[:50] + [12345], dtype=np.uint64)   # this rank's keys, asked of everybody
