@@ -94,6 +94,9 @@ struct skm_ctx {
     cudaStream_t dma_stream = nullptr;   // peer copies of routed k-mers (copy engines)
     cudaEvent_t ev_dma = nullptr;
     cudaStream_t part_stream = nullptr;  // pack + bucketing of incoming batches (overlaps inserts on `stream`)
+    cudaStream_t sort_stream = nullptr;  // tile sort of a bucketed batch (overlaps the bucketing of the next one)
+    cudaEvent_t ev_sort = nullptr;
+    bool sort_overlap = true;            // SKM_SORT_OVERLAP=0: tile sort on the bucketing stream
     cudaStream_t work = nullptr;         // stream the bucketing helpers currently launch on
     cudaEvent_t ev_main = nullptr;
     uint32_t insert_ctas_per_sm = 5;      // persistent insert grid (SKM_INSERT_CTAS): 5 of the 6 CTAs that fit,
@@ -485,6 +488,7 @@ struct WorkStream {  // selects the stream the bucketing helpers launch on, for 
 int32_t sync_all(skm_ctx *c) {
     CU(cudaStreamSynchronize(c->copy_stream));
     CU(cudaStreamSynchronize(c->part_stream));
+    CU(cudaStreamSynchronize(c->sort_stream));
     CU(cudaStreamSynchronize(c->dma_stream));
     CU(cudaStreamSynchronize(c->stream));
     return SKM_OK;
@@ -848,15 +852,22 @@ int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off
         sg.codes = nullptr;
         sg.breaks = nullptr;
     }
+    // The tile sort runs on its own stream: it is bound by HBM bandwidth, the bucketing of the NEXT
+    // batch (same `work` stream otherwise) by instruction issue, so the two share the chip well.
+    cudaStream_t sort_st = c->sort_overlap ? c->sort_stream : c->work;
+    if (sort_st != c->work) {
+        CU(cudaEventRecord(c->ev_sort, c->work));
+        CU(cudaStreamWaitEvent(sort_st, c->ev_sort, 0));
+    }
     {
-        Span sp(c, ST_SORT, c->work);
-        tile_sort_kernel<<<max_tiles, kSortThreads, tile_sort_smem_bytes(c->g2), c->work>>>(sg.list, m, nb, list_geom(c), sg.tile_off);
+        Span sp(c, ST_SORT, sort_st);
+        tile_sort_kernel<<<max_tiles, kSortThreads, tile_sort_smem_bytes(c->g2), sort_st>>>(sg.list, m, nb, list_geom(c), sg.tile_off);
         c->launches++;
         c->stage_launches[ST_SORT]++;
     }
     CU(cudaGetLastError());
     sg.tiled = true;
-    CU(cudaEventRecord(sg.ready, c->work));  // `ready` now also covers the list, the tile offsets and the totals
+    CU(cudaEventRecord(sg.ready, sort_st));  // `ready` now also covers the list, the tile offsets and the totals
     return SKM_OK;
 }
 
@@ -1316,6 +1327,9 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->part_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->dma_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->sort_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_sort, cudaEventDisableTiming));
+    if (const char *g = getenv("SKM_SORT_OVERLAP")) c->sort_overlap = atoi(g) != 0;
     CU(cudaEventCreateWithFlags(&c->ev_dma, cudaEventDisableTiming));
     CU(cudaEventRecord(c->ev_dma, c->dma_stream));
     CU(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
@@ -1412,6 +1426,8 @@ void skm_destroy(skm_ctx *c) {
         cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copy_stream);
         cudaStreamSynchronize(c->part_stream);
+        cudaStreamSynchronize(c->sort_stream);
+        cudaStreamSynchronize(c->dma_stream);
         for (auto &cs : c->chunks)
             for (auto &sg : cs.segs) {
                 cudaFree(sg.codes);
@@ -1462,6 +1478,8 @@ void skm_destroy(skm_ctx *c) {
         cudaStreamDestroy(c->copy_stream);
         cudaStreamDestroy(c->part_stream);
         cudaStreamDestroy(c->dma_stream);
+        cudaStreamDestroy(c->sort_stream);
+        if (c->ev_sort) cudaEventDestroy(c->ev_sort);
         if (c->ev_dma) cudaEventDestroy(c->ev_dma);
         if (c->ev_main) cudaEventDestroy(c->ev_main);
     }
@@ -2400,6 +2418,7 @@ int32_t mg_prepare_local(skm_ctx *c) {
     int32_t rc;
     CU(cudaStreamSynchronize(c->copy_stream));
     CU(cudaStreamSynchronize(c->part_stream));
+    CU(cudaStreamSynchronize(c->sort_stream));
     WorkStream ws(c, c->part_stream);
     for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
         ChunkState &cs = c->chunks[ch];
@@ -2452,6 +2471,7 @@ int32_t mg_prepare_local(skm_ctx *c) {
         }
     }
     CU(cudaStreamSynchronize(c->part_stream));
+    CU(cudaStreamSynchronize(c->sort_stream));
     CU(cudaStreamSynchronize(c->dma_stream));  // every slice of mine has landed
     rc = check_sticky(c);
     if (rc) return rc;

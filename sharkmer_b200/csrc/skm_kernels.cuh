@@ -1325,6 +1325,7 @@ static constexpr uint32_t kStagedRuns = 256; // runs whose descriptors are stage
 static constexpr uint32_t kStageCap = SKM_INS_STAGE;    // k-mers per staged span
 static constexpr uint32_t kStageDepth = SKM_INS_DEPTH;  // spans in flight (being copied or counted), 2..4
 static_assert(kStageDepth >= 2 && kStageDepth <= 4, "cp.async wait depth");
+static constexpr uint32_t kMaxSpans = 48;    // spans planned at a time
 static constexpr uint32_t kHlogCap = 512;    // pending moves of histogram bins >= k_low, per partition
 static constexpr uint32_t kBigCount = 0x80000000u;
 
@@ -1393,7 +1394,8 @@ tile_insert_kernel(const InsertLaunch L) {
     uint32_t *hlog = reinterpret_cast<uint32_t *>(phist + (kHisto ? L.n_chunks * L.k_low : 0));
     __shared__ unsigned long long s_q;
     __shared__ uint32_t s_occ, s_fail, s_big, s_hlog_n, s_dirty;
-    __shared__ uint32_t s_span[kStageDepth][2];   // chunk and length of the spans in flight
+    __shared__ uint32_t s_span[kMaxSpans][5];     // the plan: chunk, first run, end run, first k-mer, k-mers of each span
+    __shared__ uint32_t s_nspans, s_more, s_next_run;
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = kInsThreads / 32;
     const uint32_t pbits = L.log2cap - kPartLog2;
@@ -1496,12 +1498,17 @@ tile_insert_kernel(const InsertLaunch L) {
         const uint32_t total_runs = vs_first[n_vseg];
         unsigned long long n_new = 0;
         const uint32_t hm = (uint32_t)L.histo_max, top32 = hm + 1;
+        const uint32_t fast_lim = min(L.k_low, hm + 1);   // old + 1 < fast_lim: both bins are plain shared-memory bins
         // Runs [w0, w1) have their descriptors staged (run_src / run_len / run_pos).  The k-mers are
-        // walked in SPANS of <= kStageCap consecutive k-mers of one chunk; span i+1 is copied into
-        // shared memory (cp.async, no registers held) while span i is counted.  The barrier after
-        // every span orders the chunks: chunk c is complete before any k-mer of chunk c+1 is counted.
+        // walked in SPANS of <= kStageCap consecutive k-mers of one chunk.  PLAN: warp 0 alone cuts
+        // the staged runs into spans (a table in shared memory) — run by every warp, that control
+        // code was as many instructions as the counting itself.  EXECUTE: all warps walk the table;
+        // the copies of the next kStageDepth-1 spans (cp.async, no registers held) are in flight
+        // while a span is counted, and ONE barrier per span both publishes the next span's copies
+        // and orders the chunks (chunk c is complete before any k-mer of chunk c+1 is counted).
         uint32_t w0 = 0, w1 = 0;
-        uint32_t sc = 0, spos = vs_first[L.chunk_first_seg[0] * nbr], soff = 0;            // span cursor: chunk, run, k-mers done in the group
+        // span cursor (meaningful in warp 0 only): chunk, run, k-mers done in the current group
+        uint32_t sc = 0, spos = vs_first[L.chunk_first_seg[0] * nbr], soff = 0;
         uint32_t scr1 = vs_first[L.chunk_first_seg[1] * nbr];
         struct Span { uint32_t c, r0, r1, a, n; };
         // 0: span produced; 1: descriptors of run `spos` are not staged; 2: no k-mers left
@@ -1534,7 +1541,6 @@ tile_insert_kernel(const InsertLaunch L) {
             }
         };
         auto stage_window = [&](uint32_t from) {
-            __syncthreads();
             w0 = from;
             w1 = min(total_runs, w0 + kStagedRuns);
             for (uint32_t r = w0 + threadIdx.x; r < w1; r += kInsThreads) {
@@ -1551,7 +1557,8 @@ tile_insert_kernel(const InsertLaunch L) {
                 run_len[r - w0] = o1 - o0;
             }
             __syncthreads();
-            if (warp == 0) {  // run_pos = exclusive scan of run_len over the window
+            if (warp == 0) {
+                // run_pos = exclusive scan of run_len over the window
                 uint32_t run = 0;
                 const uint32_t nw = w1 - w0;
                 for (uint32_t v0 = 0; v0 < nw; v0 += 32) {
@@ -1567,125 +1574,166 @@ tile_insert_kernel(const InsertLaunch L) {
                     run += __shfl_sync(0xffffffffu, incl, 31);
                 }
                 if (lane == 0) run_pos[nw] = run;
-            }
-            __syncthreads();
-        };
-        auto issue_copy = [&](const Span &sp, uint32_t buf) {
-            unsigned long long *dst = stage + buf * kStageCap;
-            for (uint32_t r = sp.r0 + warp; r < sp.r1; r += n_warps) {
-                const uint32_t rp = run_pos[r - w0], len = run_len[r - w0];
-                const uint32_t lo = max(rp, sp.a), hi = min(rp + len, sp.a + sp.n);
-                const unsigned long long *src = reinterpret_cast<const unsigned long long *>(run_src[r - w0]);
-                for (uint32_t i = lo + lane; i < hi; i += 32) cp_async8(dst + (i - sp.a), src + (i - rp));
-            }
-            cp_async_commit();
-        };
-        // pipeline: up to kStageDepth spans are in flight (copies issued), the oldest is counted
-        uint32_t q_head = 0, q_n = 0;
-        int more = total_runs ? 0 : 2;   // 0: more spans may follow; 1: the next run's descriptors are not staged; 2: done
-        auto fill = [&]() {
-            while (q_n < kStageDepth && more == 0) {
+                __syncwarp();
+                // the plan: spans of this window, in order
+                uint32_t ns = 0;
+                int st = 0;
                 Span sp;
-                more = next_span(sp);
-                if (more == 0) {
-                    const uint32_t b = (q_head + q_n) % kStageDepth;
-                    issue_copy(sp, b);
-                    if (threadIdx.x == 0) {
-                        s_span[b][0] = sp.c;
-                        s_span[b][1] = sp.n;
+                while (ns < kMaxSpans && (st = next_span(sp)) == 0) {
+                    if (lane == 0) {
+                        s_span[ns][0] = sp.c;
+                        s_span[ns][1] = sp.r0;
+                        s_span[ns][2] = sp.r1;
+                        s_span[ns][3] = sp.a;
+                        s_span[ns][4] = sp.n;
                     }
-                    q_n++;
+                    ns++;
+                }
+                if (lane == 0) {
+                    s_nspans = ns;
+                    s_more = ns == kMaxSpans ? 0 : st;   // 0: this window has more spans; 1: next window; 2: done
+                    s_next_run = spos;
                 }
             }
-        };
-        fill();
-        if (q_n == 0 && more == 1) {
-            stage_window(spos);
-            more = 0;
-            fill();
-        }
-        while (q_n > 0) {
-            switch (q_n - 1) {  // copy groups issued after the oldest span's
-            case 0: cp_async_wait<0>(); break;
-            case 1: cp_async_wait<1>(); break;
-            case 2: cp_async_wait<2>(); break;
-            default: cp_async_wait<3>(); break;
-            }
             __syncthreads();
-            const uint32_t c = s_span[q_head][0], span_n = s_span[q_head][1];
-            if (!s_fail) {
-                const unsigned long long *src = stage + q_head * kStageCap;
-                int *ph = phist + c * L.k_low;  // this chunk's histogram moves
-                (void)ph;
-                for (uint32_t i0 = 0; i0 < span_n; i0 += kInsThreads) {
-                    const uint32_t i = i0 + threadIdx.x;
-                    const unsigned long long kmer = i < span_n ? src[i] : SKM_EMPTY_KEY;
-                    bool active = kmer != SKM_EMPTY_KEY;
-                    uint32_t s = 0;
-                    if (active) {
-                        const uint64_t h = skm_hash_kmer(kmer);
-                        const uint64_t home = skm_home_slot(L.n_ranks == 1 ? h : skm_local_hash(h, L.n_ranks), L.log2cap);
-                        if (filter && (home >> kPartLog2) != q) active = false;
-                        s = (uint32_t)home & (kPartSlots - 1);
+        };
+        auto issue_copy = [&](uint32_t i) {   // span i of the table -> stage buffer i % kStageDepth
+            const uint32_t r0 = s_span[i][1], r1 = s_span[i][2], a = s_span[i][3], n = s_span[i][4];
+            unsigned long long *dst = stage + (i % kStageDepth) * kStageCap;
+            for (uint32_t r = r0 + warp; r < r1; r += n_warps) {
+                const uint32_t rp = run_pos[r - w0], len = run_len[r - w0];
+                const uint32_t lo = max(rp, a), hi = min(rp + len, a + n);
+                const unsigned long long *src = reinterpret_cast<const unsigned long long *>(run_src[r - w0]);
+                for (uint32_t k = lo + lane; k < hi; k += 32) cp_async8(dst + (k - a), src + (k - rp));
+            }
+        };
+        uint32_t from = spos;
+        bool replan_same_window = false;
+        for (;;) {
+            if (!total_runs) break;
+            if (replan_same_window) {
+                // the span table was full: warp 0 continues from its cursor over the same window
+                __syncthreads();
+                if (warp == 0) {
+                    uint32_t ns = 0;
+                    int st = 0;
+                    Span sp;
+                    while (ns < kMaxSpans && (st = next_span(sp)) == 0) {
+                        if (lane == 0) {
+                            s_span[ns][0] = sp.c;
+                            s_span[ns][1] = sp.r0;
+                            s_span[ns][2] = sp.r1;
+                            s_span[ns][3] = sp.a;
+                            s_span[ns][4] = sp.n;
+                        }
+                        ns++;
                     }
-                    // The probe loop is warp-uniform (lanes that are done idle, predicated off): with
-                    // per-lane `break`s the compiler kept the lanes apart for the rest of the iteration
-                    // and the count update ran with 7 of 32 lanes on average.
-                    bool counted = active;
-                    uint32_t probes = 0;
-                    while (__any_sync(0xffffffffu, active)) {
+                    if (lane == 0) {
+                        s_nspans = ns;
+                        s_more = ns == kMaxSpans ? 0 : st;
+                        s_next_run = spos;
+                    }
+                }
+                __syncthreads();
+            } else {
+                __syncthreads();   // the previous table / window is no longer read
+                stage_window(from);
+            }
+            const uint32_t n_spans = s_nspans;
+            // ---- execute ----
+            for (uint32_t i = 0; i < kStageDepth - 1; i++) {
+                if (i < n_spans) issue_copy(i);
+                cp_async_commit();
+            }
+            if (n_spans) {
+                cp_async_wait<kStageDepth - 2>();   // span 0 has landed (this thread's part)
+                __syncthreads();
+            }
+            for (uint32_t i = 0; i < n_spans; i++) {
+                if (i + kStageDepth - 1 < n_spans) issue_copy(i + kStageDepth - 1);   // into the buffer span i-1 used
+                cp_async_commit();
+                const uint32_t c = s_span[i][0], span_n = s_span[i][4];
+                const unsigned long long n_new_before = n_new;
+                if (!s_fail) {
+                    const unsigned long long *src = stage + (i % kStageDepth) * kStageCap;
+                    int *ph = phist + c * L.k_low;  // this chunk's histogram moves
+                    (void)ph;
+                    for (uint32_t i0 = 0; i0 < span_n; i0 += kInsThreads) {
+                        const uint32_t k = i0 + threadIdx.x;
+                        const unsigned long long kmer = k < span_n ? src[k] : SKM_EMPTY_KEY;
+                        uint32_t active = kmer != SKM_EMPTY_KEY;
+                        uint32_t s = 0;
                         if (active) {
-                            unsigned long long key = keys[s];
-                            bool hit = key == kmer;
-                            if (!hit && key == SKM_EMPTY_KEY) {
-                                key = atomicCAS(&keys[s], (unsigned long long)SKM_EMPTY_KEY, kmer);
+                            const uint64_t h = skm_hash_kmer(kmer);
+                            const uint64_t home = skm_home_slot(L.n_ranks == 1 ? h : skm_local_hash(h, L.n_ranks), L.log2cap);
+                            if (filter && (home >> kPartLog2) != q) active = 0;
+                            s = (uint32_t)home & (kPartSlots - 1);
+                        }
+                        // The probe loop is warp-uniform (lanes that are done idle, predicated off): with
+                        // per-lane `break`s the compiler kept the lanes apart for the rest of the iteration
+                        // and the count update ran with 7 of 32 lanes on average.
+                        uint32_t counted = active;
+                        uint32_t probes = 0;
+                        while (__any_sync(0xffffffffu, active)) {
+                            if (active) {
+                                unsigned long long key = keys[s];
                                 if (key == SKM_EMPTY_KEY) {
-                                    hit = true;
-                                    n_new++;
-                                    if (atomicAdd(&s_occ, 1u) >= L.max_occupied) s_fail = 1;
+                                    key = atomicCAS(&keys[s], (unsigned long long)SKM_EMPTY_KEY, kmer);
+                                    if (key == SKM_EMPTY_KEY) {
+                                        key = kmer;
+                                        n_new++;
+                                    }
+                                }
+                                if (key == kmer) {
+                                    active = 0;
+                                } else if (++probes >= kPartSlots) {  // the partition holds only other keys
+                                    active = 0;
+                                    counted = 0;
+                                    s_fail = 1;
                                 } else {
-                                    hit = key == kmer;
+                                    s = (s + 1) & (kPartSlots - 1);
                                 }
                             }
-                            if (hit) {
-                                active = false;
-                            } else if (++probes >= kPartSlots) {  // the partition holds only other keys
-                                active = false;
-                                counted = false;
-                                s_fail = 1;
-                            } else {
-                                s = (s + 1) & (kPartSlots - 1);
-                            }
                         }
-                    }
-                    if (!counted) continue;
-                    if (!kHisto) {
-                        atomicAdd(&counts[s], 1u);
-                    } else {
-                        const uint32_t old = atomicAdd(&counts[s], 1u);
-                        // Histogram::move_count (src/kmer/histogram.rs:51-85): one unit of mass from bin old to old+1
-                        const uint32_t ob = old > hm ? top32 : old;
-                        const uint32_t nb2 = old >= hm ? top32 : old + 1;
-                        if (ob != nb2) {
-                            if (old) {
-                                if (ob < L.k_low) atomicAdd(&ph[ob], -1);
-                                else hlog_push(hlog, &s_hlog_n, &s_dirty, L, c, ob, true);
+                        if (!counted) continue;
+                        if (!kHisto) {
+                            atomicAdd(&counts[s], 1u);
+                        } else {
+                            const uint32_t old = atomicAdd(&counts[s], 1u);
+                            // Histogram::move_count (src/kmer/histogram.rs:51-85): one unit of mass from bin old to old+1
+                            if (old + 1 < fast_lim) {
+                                // both bins are shared-memory bins below the clamp.  Bin 0 is a scratch cell
+                                // (the histogram has no bin 0: it takes the -1 of a new key and is never
+                                // published), so the common case is two unconditional atomics.
+                                atomicAdd(&ph[old], -1);
+                                atomicAdd(&ph[old + 1], 1);
+                            } else {
+                                const uint32_t ob = old > hm ? top32 : old;
+                                const uint32_t nb2 = old >= hm ? top32 : old + 1;
+                                if (ob != nb2) {
+                                    if (old) {
+                                        if (ob < L.k_low) atomicAdd(&ph[ob], -1);
+                                        else hlog_push(hlog, &s_hlog_n, &s_dirty, L, c, ob, true);
+                                    }
+                                    if (nb2 < L.k_low) atomicAdd(&ph[nb2], 1);
+                                    else hlog_push(hlog, &s_hlog_n, &s_dirty, L, c, nb2, false);
+                                }
                             }
-                            if (nb2 < L.k_low) atomicAdd(&ph[nb2], 1);
-                            else hlog_push(hlog, &s_hlog_n, &s_dirty, L, c, nb2, false);
                         }
                     }
                 }
+                {   // occupancy: one shared-memory atomic per warp and span
+                    const uint32_t add = __reduce_add_sync(0xffffffffu, (uint32_t)(n_new - n_new_before));
+                    if (lane == 0 && add) atomicAdd(&s_occ, add);
+                }
+                cp_async_wait<kStageDepth - 2>();   // span i+1 has landed (this thread's part)
+                __syncthreads();   // span i is counted everywhere; span i+1 is visible to everybody
+                if (s_occ > L.max_occupied) s_fail = 1;   // too full to go on: roll the partition back, grow, retry
             }
-            __syncthreads();  // the span is counted: its buffer may be refilled, the next chunk may start
-            q_head = (q_head + 1) % kStageDepth;
-            q_n--;
-            fill();
-            if (q_n == 0 && more == 1) {   // the next run's descriptors are not staged yet
-                stage_window(spos);
-                more = 0;
-                fill();
-            }
+            const uint32_t more = s_more;
+            if (more == 2) break;
+            replan_same_window = more == 0;
+            from = s_next_run;
         }
         __syncthreads();
         // ---- commit or roll back ----
@@ -1728,7 +1776,7 @@ tile_insert_kernel(const InsertLaunch L) {
                 for (uint32_t i = threadIdx.x; i < L.n_chunks * L.k_low; i += kInsThreads) {
                     const int d = phist[i];
                     if (d) {
-                        chist[i] += d;
+                        if (i % L.k_low) chist[i] += d;   // (bin 0 is the scratch cell)
                         phist[i] = 0;
                     }
                 }
