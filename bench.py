@@ -47,6 +47,29 @@ N_RATE = 0.001
 SEED = 2
 DISTINCT_HINT_PER_GPU = 320_000_000
 CPU_SAMPLE_READS = 300_000
+# BASELINE.json configs (SURVEY.md §8d fixes the generators).  `--config`; the default and the driver's runs are C2.
+#   weak: reads / genome / distinct hint are PER GPU; strong: totals, divided over the GPUs
+CONFIGS = {
+    "C2": dict(k=21, chunks=10, scaling="weak", reads=10_000_000, genome=50_000_000, sub=0.01, n=0.001, seed=2,
+               hint=320_000_000, bufs=10, golden="C2",
+               what="k=21 incremental counting, 10 chunks over 10 M synthetic 150 bp reads with 1 % error (per GPU)"),
+    "C1": dict(k=31, chunks=1, scaling="strong", reads=1_000_000, genome=10_000_000, sub=0.01, n=0.001, seed=1,
+               hint=45_000_000, bufs=1, golden="C1_chunks1",
+               what="sharkmer -k 31 --max-reads 1000000 on 1 M synthetic 150 bp reads (golden counts + histogram)"),
+    "C3": dict(k=31, chunks=0, scaling="strong", reads=100_000_000, genome=500_000_000, sub=0.01, n=0.0, seed=3,
+               hint=4_700_000_000, bufs=10, golden=None,
+               what="k=31, 100 M synthetic 150 bp reads (~15 Gbp), hash-sharded table across the GPUs"),
+    "C5": dict(k=31, chunks=0, scaling="strong", reads=1_000_000_000, genome=8_000_000_000, sub=0.0005, n=0.0, seed=5,
+               hint=10_500_000_000, bufs=64, bufs_per_round=8, golden=None,
+               what="high-diversity stress: 1 B synthetic 150 bp reads, ~1e10 distinct k-mers, tables near HBM capacity; "
+                    "the input is counted in rounds (skm_mg_flush) because its k-mer lists do not fit the GPUs at once"),
+}
+CONFIG = "C2"
+N_BUF = CHUNKS          # input buffers per GPU (one per chunk when chunks > 0)
+BUFS_PER_ROUND = 0      # > 0: flush the sharded engine after this many buffers (inputs larger than memory)
+SCALING = "weak"
+GOLDEN = "C2"
+
 B_SURVEY_PER_KMER = 64.0   # 32 B sector in + 32 B sector out per k-mer occurrence (random-sector model)
 B_SURVEY_PER_BASE = 1.5    # 1 B ASCII read + 0.25 B packed write + 0.25 B packed read
 # Algorithmic bytes of each kernel of the tiled path, per unit of work:
@@ -129,7 +152,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------
 
 def sample_genome(n_reads):
-    """Genome length for a bounded sample at the SAME depth as the full workload (30x): a sample
+    """Genome length for a bounded sample at the SAME depth as the full workload: a sample
     taken from the full-size genome would be almost all first-time inserts, a different regime."""
     return max(1000, GENOME_PER_GPU * n_reads // READS_PER_GPU)
 
@@ -168,7 +191,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "kmers_counted_per_sec", "value": v, "unit": "kmers/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": cfg,
         "cpu_baseline": {"value": v, "unit": "kmers/s", "cores": 1, "kind": "port", "sample": sample,
                          "note": "C oracle port of sharkmer src/kmer + src/io.rs (Rust reference cannot be "
@@ -183,11 +206,14 @@ def run_reference(args):
 
 
 def workload_config(n_gpus):
-    return {"workload": f"C2: k={K}, {CHUNKS} chunks, {READS_PER_GPU * n_gpus} synthetic {READ_LEN} bp reads "
-                        f"({GENOME_PER_GPU * n_gpus} bp genome, {SUB_RATE} sub, {N_RATE} N, seed {SEED})",
-            "k": K, "chunks": CHUNKS, "reads": READS_PER_GPU * n_gpus, "read_len": READ_LEN,
-            "genome_len": GENOME_PER_GPU * n_gpus, "histo_max": HISTO_MAX,
-            "l2": "inputs (1.5 GB/GPU) and table (8.6 GB/GPU) exceed L2; no flush needed",
+    per = 1 if SCALING == "strong" else n_gpus
+    reads, genome = READS_PER_GPU * per if SCALING == "weak" else READS_PER_GPU, GENOME_PER_GPU * per if SCALING == "weak" else GENOME_PER_GPU
+    return {"workload": f"{CONFIG}: k={K}, {CHUNKS} chunks, {reads} synthetic {READ_LEN} bp reads "
+                        f"({genome} bp genome, {SUB_RATE} sub, {N_RATE} N, seed {SEED})",
+            "baseline_config": CONFIGS[CONFIG]["what"],
+            "k": K, "chunks": CHUNKS, "reads": reads, "read_len": READ_LEN,
+            "genome_len": genome, "histo_max": HISTO_MAX,
+            "l2": "inputs and table are GBs, far beyond the 126 MB L2; no flush needed",
             "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs: reads split, table sharded by k-mer hash range, "
                            "k-mers routed to their owners over NVLink by the copy engines"}
 
@@ -225,11 +251,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n_reads_total = args.reads_per_gpu * world
-    genome = GENOME_PER_GPU * world * args.reads_per_gpu // READS_PER_GPU
+    scale = args.reads_per_gpu / READS_PER_GPU           # (--reads-per-gpu: experiments at reduced size)
+    if SCALING == "weak":
+        n_reads_total = args.reads_per_gpu * world
+        genome = int(GENOME_PER_GPU * world * scale)
+        hint = int(DISTINCT_HINT_PER_GPU * scale)
+    else:   # strong: the configuration fixes the totals
+        n_reads_total = int(READS_PER_GPU * scale) // (1000 * world) * (1000 * world)
+        genome = int(GENOME_PER_GPU * scale)
+        hint = int(DISTINCT_HINT_PER_GPU * scale / world * 1.03)
     genome = max(genome, 1000)
     mode = {"auto": _lib.INSERT_AUTO, "direct": _lib.INSERT_DIRECT, "partitioned": _lib.INSERT_PARTITIONED}[args.mode]
-    hint = int(DISTINCT_HINT_PER_GPU * args.reads_per_gpu / READS_PER_GPU)
 
     if world > 1 and os.environ.get("SKM_TRACE"):
         os.environ["SKM_TRACE"] += f".rank{rank}"   # one timeline file per rank
@@ -242,18 +274,33 @@ def run_ours(args):
 
     # ---- inputs: chunk c holds the reads of batches b = c (mod CHUNKS) (src/io.rs:355-361);
     #      rank r takes the r-th contiguous slice of every chunk's 1000-read batches ---------------
-    def make_inputs(engine, n_total, genome_len):
+    def make_inputs(engine, n_total, genome_len, n_buf=None):
+        """This rank's input as device buffers.  chunks > 0: buffer c = this rank's slice of chunk c's 1000-read
+        batches; chunks == 0: this rank's contiguous share of the reads, cut into n_buf buffers."""
         bufs, counts = [], []
-        for c in range(CHUNKS):
-            n_batches_c = len(range(c, (n_total + 999) // 1000, CHUNKS))
-            lo, hi = n_batches_c * rank // world, n_batches_c * (rank + 1) // world
-            first, n = lo * 1000, (hi - lo) * 1000
-            # (n_total is a multiple of 1000 in every configuration used here)
-            t = torch.empty(max(n * line, 1), dtype=torch.uint8, device=dev)[:n * line]
-            if n:
-                engine.synth_device(SEED, genome_len, READ_LEN, st, nt, c, CHUNKS, first, n, t.data_ptr())
-            bufs.append(t)
-            counts.append(n)
+        if CHUNKS > 0:
+            for c in range(CHUNKS):
+                n_batches_c = len(range(c, (n_total + 999) // 1000, CHUNKS))
+                lo, hi = n_batches_c * rank // world, n_batches_c * (rank + 1) // world
+                first, n = lo * 1000, (hi - lo) * 1000
+                # (n_total is a multiple of 1000 in every configuration used here)
+                t = torch.empty(max(n * line, 1), dtype=torch.uint8, device=dev)[:n * line]
+                if n:
+                    engine.synth_device(SEED, genome_len, READ_LEN, st, nt, c, CHUNKS, first, n, t.data_ptr())
+                bufs.append(t)
+                counts.append(n)
+        else:
+            n_buf = n_buf or N_BUF
+            n_batches = (n_total + 999) // 1000
+            lo, hi = n_batches * rank // world, n_batches * (rank + 1) // world
+            for b in range(n_buf):
+                b0, b1 = lo + (hi - lo) * b // n_buf, lo + (hi - lo) * (b + 1) // n_buf
+                first, n = b0 * 1000, (b1 - b0) * 1000
+                t = torch.empty(max(n * line, 1), dtype=torch.uint8, device=dev)[:n * line]
+                if n:
+                    engine.synth_device(SEED, genome_len, READ_LEN, st, nt, 0, 1, first, n, t.data_ptr())
+                bufs.append(t)
+                counts.append(n)
         torch.cuda.synchronize()
         return bufs, counts
 
@@ -280,11 +327,16 @@ def run_ours(args):
 
     def step(host_buffers: bool):
         eng.reset()
-        for c in range(CHUNKS):
+        for i in range(len(d_bufs)):
+            c = i if CHUNKS > 0 else 0
+            if d_bufs[i].numel() == 0:
+                continue
             if host_buffers:
-                eng.ingest_ptr(c, h_bufs[c].data_ptr(), h_bufs[c].numel(), _lib.INGEST_ASYNC)
+                eng.ingest_ptr(c, h_bufs[i].data_ptr(), h_bufs[i].numel(), _lib.INGEST_ASYNC)
             else:
-                eng.ingest_device(c, d_bufs[c].data_ptr(), d_bufs[c].numel())
+                eng.ingest_device(c, d_bufs[i].data_ptr(), d_bufs[i].numel())
+            if sharded is not None and BUFS_PER_ROUND and (i + 1) % BUFS_PER_ROUND == 0 and i + 1 < len(d_bufs):
+                sharded.flush()    # collective: count this round, free its lists and the arenas
         if world == 1:
             eng.finalize()
             return eng.histogram(CHUNKS - 1) if CHUNKS else None
@@ -316,25 +368,26 @@ def run_ours(args):
     cpu = None
     parity = None
     if not args.no_cpu:
-        n_s = max(1000 * CHUNKS * world, args.cpu_sample_reads // (1000 * CHUNKS * world) * (1000 * CHUNKS * world))
+        unit = 1000 * max(1, CHUNKS) * world
+        n_s = max(unit, args.cpu_sample_reads // unit * unit)
         g_s = sample_genome(n_s)
-        chk = kmer.Engine(K, CHUNKS, HISTO_MAX, capacity_hint=int(hint * n_s / args.reads_per_gpu / world) + 1000,
+        chk = kmer.Engine(K, CHUNKS, HISTO_MAX, capacity_hint=int(hint * n_s * world / max(n_reads_total, 1)) + 1000,
                           device=local_rank, insert_mode=_lib.INSERT_PARTITIONED if args.mode == "auto" else mode,
                           n_ranks=world, rank=rank)
-        s_bufs, _ = make_inputs(chk, n_s, g_s)
+        s_bufs, _ = make_inputs(chk, n_s, g_s, n_buf=3)
         chk_sh = None
         if world > 1:
             chk_sh = ShardedCounter(chk, dev, cpu_group=cpu_group,
                                     arena_bytes=int(sum(t.numel() for t in s_bufs) * 8 * 1.5) + (64 << 20))
-        for c in range(CHUNKS):
-            if s_bufs[c].numel():
-                chk.ingest_device(c, s_bufs[c].data_ptr(), s_bufs[c].numel())
+        for i, t in enumerate(s_bufs):
+            if t.numel():
+                chk.ingest_device(i if CHUNKS > 0 else 0, t.data_ptr(), t.numel())
         if world == 1:
             chk.finalize()
         else:
             chk_sh.finalize()
         digest = chk.digest()
-        cols = np.stack([chk.histogram(c) for c in range(CHUNKS)])
+        cols = np.stack([chk.histogram(c) for c in range(CHUNKS)]) if CHUNKS else None
         if world > 1:   # a table digest is a wrapping sum over entries: the global one is the sum of the partitions'
             dg = torch.tensor([np.uint64(digest).astype(np.int64)], device=dev, dtype=torch.int64)
             dist.all_reduce(dg)
@@ -342,7 +395,7 @@ def run_ours(args):
         if rank == 0:
             run, _, dt = cpu_sample(n_s, g_s)   # the oracle: checker + CPU baseline
             ok_digest = digest == run.table().digest()
-            ok_cols = all((cols[c] == run.histogram(c)).all() for c in range(CHUNKS))
+            ok_cols = all((cols[c] == run.histogram(c)).all() for c in range(CHUNKS))   # (chunks == 0: no columns)
             parity = {"sample_reads": n_s, "ranks": world, "table_digest_equals_oracle": bool(ok_digest),
                       "histogram_columns_equal_oracle": bool(ok_cols)}
             if not (ok_digest and ok_cols):
@@ -361,7 +414,7 @@ def run_ours(args):
     def global_state():
         """Totals and the table digest of the last run, summed over the partitions."""
         t = eng.totals()
-        kc = sum(eng.chunk_totals(c).n_kmers for c in range(CHUNKS))
+        kc = sum(eng.chunk_totals(c).n_kmers for c in range(max(1, CHUNKS)))
         v = torch.tensor([int(t.n_kmers), int(t.n_unique), int(kc), int(np.uint64(eng.digest()).astype(np.int64))],
                          device=dev, dtype=torch.int64)
         if world > 1:
@@ -383,6 +436,20 @@ def run_ours(args):
         st2 = eng.stage_times()
         if world > 1:
             print(f"[rank {rank}] e2e h2d {st2.h2d:.1f} ms, step {ms_e2e:.1f} ms", file=sys.stderr)
+    if GOLDEN and scale == 1.0 and (SCALING == "strong" or world == 1) and args.k is None and args.chunks is None:
+        # the oracle's result for exactly this configuration, committed as a fixture (tests/golden/make_golden_full.py)
+        try:
+            gold = json.load(open(os.path.join(ROOT, "tests", "golden", "full_cases.json"))).get(GOLDEN)
+        except Exception:
+            gold = None
+        if gold:
+            full["table_digest_equals_oracle_golden"] = gs_dev["digest"] == int(gold["digest"])
+            full["totals_equal_oracle_golden"] = (gs_dev["table_mass"], gs_dev["distinct"]) == (gold["n_kmers"], gold["n_unique"])
+            if CHUNKS and hist_dev is not None:
+                want = np.zeros(HISTO_MAX + 2, dtype=np.uint64)
+                for b, v in gold["histograms"][CHUNKS - 1].items():
+                    want[int(b)] = v
+                full["final_histogram_equals_oracle_golden"] = bool((hist_dev == want).all())
     if not all(full.values()):
         raise SystemExit(f"PARITY FAILURE on the full-size run: {full} {gs_dev}")
     if parity is None:
@@ -394,7 +461,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- totals over ranks ------------------------------------------------------------------------
-    n_kmers_local = sum(eng.chunk_totals(c).n_kmers for c in range(CHUNKS))
+    n_kmers_local = sum(eng.chunk_totals(c).n_kmers for c in range(max(1, CHUNKS)))
     n_bases_local = in_bytes - sum(n_local)
     n_kmers = gs_dev["windows_extracted"]
     if world > 1:
@@ -440,7 +507,7 @@ def run_ours(args):
         out = {
             "metric": "kmers_counted_per_sec", "value": value, "unit": "kmers/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "scaling": SCALING, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(world),
             "bases_per_sec": n_bases / (ms_dev / 1e3),
             "ms_per_step_wall": ms_wall,
@@ -489,7 +556,7 @@ def run_ours(args):
         if not args.no_e2e:
             out["e2e"] = {"value": n_kmers / (ms_e2e / 1e3), "unit": "kmers/s",
                           "h2d_bytes_per_step": int(in_bytes) * world,
-                          "d2h_bytes_per_step": int(CHUNKS * (HISTO_MAX + 2) * 8 + 64) * world,
+                          "d2h_bytes_per_step": int(CHUNKS * (HISTO_MAX + 2) * 8 + 64) * world,   # histogram columns + totals
                           "ms_per_step": ms_e2e, "ms_per_step_wall": ms_e2e_wall,
                           "stage_ms": {"h2d": st2.h2d, "pack": st2.pack, "insert": st2.insert, "histogram": st2.histogram},
                           "api": "skm_ingest_batch(pinned host buffers) x10 -> skm_finalize -> skm_histogram"}
@@ -531,6 +598,8 @@ def main():
     # Libraries (NCCL's version banner, torchrun notices) print to stdout; keep fd 1 clean for the
     # single JSON line by pointing it at stderr until the result is ready.
     global _REAL_STDOUT
+    global CHUNKS, K, CONFIG, READS_PER_GPU, GENOME_PER_GPU, SUB_RATE, N_RATE, SEED, DISTINCT_HINT_PER_GPU, N_BUF
+    global BUFS_PER_ROUND, SCALING, GOLDEN
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
@@ -549,10 +618,19 @@ def main():
     ap.add_argument("--exchange", default="dma", help="(ignored: the exchange is the copy-engine path; kept for old command lines)")
     ap.add_argument("--chunks", type=int, default=None, help="EXPERIMENT ONLY: override the workload's chunk count")
     ap.add_argument("--k", type=int, default=None, help="EXPERIMENT ONLY: override k")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS),
+                    help="BASELINE.json configuration (default C2: the metric's configuration and the driver's runs)")
     args = ap.parse_args()
-    global CHUNKS, K
+    cfg = CONFIGS[args.config]
+    CONFIG, K, CHUNKS, SCALING, GOLDEN = args.config, cfg["k"], cfg["chunks"], cfg["scaling"], cfg["golden"]
+    READS_PER_GPU, GENOME_PER_GPU, DISTINCT_HINT_PER_GPU = cfg["reads"], cfg["genome"], cfg["hint"]
+    SUB_RATE, N_RATE, SEED = cfg["sub"], cfg["n"], cfg["seed"]
+    N_BUF, BUFS_PER_ROUND = cfg["bufs"], cfg.get("bufs_per_round", 0)
+    if args.reads_per_gpu == 10_000_000 and args.config != "C2":
+        args.reads_per_gpu = READS_PER_GPU      # (the option's default is C2's)
     if args.chunks is not None:
         CHUNKS = args.chunks
+        N_BUF = max(N_BUF, CHUNKS)
     if args.k is not None:
         K = args.k
     if args.warmup < 3 and args.impl == "ours":

@@ -215,6 +215,10 @@ int32_t skm_mg_arena_ptr(skm_ctx *ctx, void **out);
 int32_t skm_mg_open_peer(skm_ctx *ctx, uint32_t peer_rank, const uint8_t *handle64);
 int32_t skm_mg_set_peer(skm_ctx *ctx, uint32_t peer_rank, void *d_ptr, int32_t peer_device);
 int32_t skm_mg_finalize(skm_ctx *ctx, const skm_comm *comm);
+/* Inputs larger than the GPUs' memory (BASELINE config 5: 1e9 reads): COLLECTIVE, chunks == 0 only —
+ * counts everything ingested so far into the tables and frees the k-mer lists and the arenas; ingest
+ * goes on afterwards and skm_mg_finalize ends the run as usual. */
+int32_t skm_mg_flush(skm_ctx *ctx, const skm_comm *comm);
 /* bytes this rank pushed to its peers since create / reset */
 int32_t skm_mg_bytes_sent(skm_ctx *ctx, uint64_t *out);
 
@@ -229,6 +233,7 @@ int32_t skm_group_create(const skm_params *params /* rank, n_ranks, device are f
                          skm_group **out);
 skm_ctx *skm_group_ctx(skm_group *g, uint32_t rank);
 int32_t skm_group_finalize(skm_group *g);
+int32_t skm_group_flush(skm_group *g);
 int32_t skm_group_reset(skm_group *g);
 const char *skm_group_last_error(skm_group *g);
 void skm_group_destroy(skm_group *g);

@@ -74,10 +74,12 @@ SYMBOLS = {
     "skm_mg_open_peer": (_i32, [_vp, _u32, _vp]),
     "skm_mg_set_peer": (_i32, [_vp, _u32, _vp, _i32]),
     "skm_mg_finalize": (_i32, [_vp, _vp]),
+    "skm_mg_flush": (_i32, [_vp, _vp]),
     "skm_mg_bytes_sent": (_i32, [_vp, C.POINTER(_u64)]),
     "skm_group_create": (_i32, [C.POINTER(SkmParams), _u32, _vp, _u64, C.POINTER(_vp)]),
     "skm_group_ctx": (_vp, [_vp, _u32]),
     "skm_group_finalize": (_i32, [_vp]),
+    "skm_group_flush": (_i32, [_vp]),
     "skm_group_reset": (_i32, [_vp]),
     "skm_group_last_error": (C.c_char_p, [_vp]),
     "skm_group_destroy": (None, [_vp]),

@@ -787,7 +787,7 @@ ListGeom list_geom(const skm_ctx *c) { return ListGeom{c->n_ranks, route_log2_re
 // into a list — capped one-pass layout, or exact two-pass layout — then sort every tile of every
 // bucket by sub-bucket in place (tile_sort_kernel).  `must`: fail instead of skipping when memory
 // is short.  Leaves sg.list == nullptr when skipped.
-int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off, bool exact, bool must) {
+int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off, bool exact, bool must, int reserve_tables = 3) {
     Segment &sg = c->chunks[chunk].segs[seg_index];
     const BucketFn fn = route_fn(c);
     const uint32_t nb = c->n_ranks << fn.log2_regions;
@@ -808,7 +808,9 @@ int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off
     }
     const size_t off_bytes = (size_t)max_tiles * (F + 1) * sizeof(uint16_t);
     const size_t need = cells * 8 + off_bytes;
-    if (!must && c->list_bytes + need + 3 * c->capacity * sizeof(Slot) + (4ull << 30) > c->mem_budget) return SKM_OK;
+    // budget = device memory that was free when the ctx was created (no cudaMemGetInfo here: it would serialise
+    // the ingest path); room is kept for `reserve_tables` tables of the current size (growth) plus slack
+    if (!must && c->list_bytes + need + (size_t)reserve_tables * c->capacity * sizeof(Slot) + (4ull << 30) > c->mem_budget) return SKM_OK;
     CU(cudaStreamWaitEvent(c->work, sg.ready, 0));
     unsigned long long *list = nullptr, *meta = nullptr;
     uint16_t *tile_off = nullptr;
@@ -1079,13 +1081,9 @@ int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index);
 int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force = false) {
     Segment &sg = c->chunks[chunk].segs[seg_index];
     if (!sg.codes || sg.list) return SKM_OK;
-    const size_t need = sg.n_bytes * sizeof(uint64_t);
     if (!force) {
         // multi-GPU: routing needs the buckets anyway; single GPU: only when partitioned insert pays off
         if (!c->eager || (c->n_ranks == 1 && !want_partitioned(c, sg.n_bytes))) return SKM_OK;
-        // budget = device memory that was free when the ctx was created; keep room for a table twice
-        // the current size plus slack (no cudaMemGetInfo here: it would serialise the ingest path)
-        if (c->list_bytes + need + 3 * c->capacity * sizeof(Slot) + (4ull << 30) > c->mem_budget) return SKM_OK;
     }
     const BucketFn fn = route_fn(c);  // (owner, region); a single GPU is the n_ranks == 1 case
     const uint32_t nb = c->n_ranks << fn.log2_regions;
@@ -1096,7 +1094,8 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force
     // The capped layout pays a fixed slack per bucket (1024 cells): batches too small to amortise it, and
     // batches whose bucket counts could overflow 32 bits, take the exact two-pass layout.
     const bool exact = force || !c->capped || sg.n_bytes >= (3ull << 30) || sg.n_bytes / nb < 4096;
-    int32_t rc = build_list(c, chunk, seg_index, h_off, exact, force);
+    // (a table sized from a capacity_hint is not expected to grow: keep room for it alone)
+    int32_t rc = build_list(c, chunk, seg_index, h_off, exact, force, c->p.capacity_hint ? 1 : 3);
     if (rc) return rc;
     if (c->n_ranks > 1 && sg.list && sg.cap) rc = ship_segment(c, chunk, seg_index);  // exchange starts at ingest time
     return rc;
@@ -1370,6 +1369,8 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
         c->mem_budget = free_b;
+        // SKM_MEM_BUDGET=<MiB>: pretend the device is this small (tests of the memory-bounded paths)
+        if (const char *g = getenv("SKM_MEM_BUDGET")) c->mem_budget = std::min<size_t>(free_b, (size_t)atoll(g) << 20);
     }
     CU(cudaEventCreateWithFlags(&c->ev_alloc, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
@@ -1738,55 +1739,45 @@ static int32_t finalize_common(skm_ctx *c) {
                 sg.breaks = nullptr;
             }
         }
-        // (2) segments still packed: build their lists now when the chunk is worth it and memory allows
+        // (2) this chunk's lists join the group; segments still packed get their lists built now when the
+        //     chunk is worth it.  When memory is short (inputs larger than the GPU: BASELINE config 5) or a
+        //     launch cannot read more lists, what is grouped so far is counted first — if need be in the
+        //     middle of a chunk: the order inside a chunk does not matter, and every launch that touches a
+        //     chunk rewrites its column, so the last one leaves it complete.
+        if (ch - group_chunk0 >= kMaxChunksPerLaunch) {
+            rc = flush_group(ch);
+            if (rc) return rc;
+        }
         uint64_t packed_bytes = 0;
         for (auto &sg : cs.segs)
             if (sg.codes && !sg.list) packed_bytes += sg.n_bytes;
-        if (packed_bytes && c->n_ranks == 1 && want_partitioned(c, packed_bytes)) {
-            WorkStream ws(c, c->part_stream);
-            for (size_t si = 0; si < cs.segs.size(); si++) {
-                Segment &sg = cs.segs[si];
-                if (!sg.codes || sg.list) continue;
+        const bool build_now = packed_bytes && c->n_ranks == 1 && want_partitioned(c, packed_bytes);
+        for (size_t si = 0; si < cs.segs.size(); si++) {
+            Segment &sg = cs.segs[si];
+            if (!sg.list && sg.codes && build_now) {
+                WorkStream ws(c, c->part_stream);
                 for (int attempt = 0; attempt < 2 && !sg.list; attempt++) {
                     uint64_t *h_off = alloc_offsets(c, (c->n_ranks << route_log2_regions(c)) + 1);
                     if (!h_off) return fail(c, SKM_ERR_OOM, "pinned allocation failed");
-                    rc = build_list(c, ch, si, h_off, /*exact=*/true, /*must=*/false);
+                    rc = build_list(c, ch, si, h_off, /*exact=*/true, /*must=*/false, /*reserve_tables=*/1);
                     if (rc) return rc;
-                    if (!sg.list && attempt == 0) {  // memory is short: count what is already listed, then retry
-                        rc = flush_group(ch);
+                    if (!sg.list && attempt == 0) {  // memory is short: count what is listed so far, then retry
+                        if (group.empty()) break;
+                        rc = flush_group(ch + 1);
                         if (rc) return rc;
+                        group_chunk0 = ch;
                     }
                 }
                 if (sg.list) CU(cudaEventSynchronize(sg.ready));
             }
-        }
-        // (3) this chunk's lists join the group
-        size_t n_listed = 0;
-        for (auto &sg : cs.segs) n_listed += (sg.list && sg.tiled) ? 1 : 0;
-        if ((group.size() + n_listed) * nbr_now > kMaxVseg || ch - group_chunk0 >= kMaxChunksPerLaunch) {
-            rc = flush_group(ch);
-            if (rc) return rc;
-        }
-        if (n_listed * nbr_now > kMaxVseg) {
-            // more lists in one chunk than a launch can read: count them in several launches of this
-            // chunk alone (the order inside a chunk does not matter)
-            for (auto &sg : cs.segs) {
-                if (!(sg.list && sg.tiled)) continue;
-                if ((group.size() + 1) * nbr_now > kMaxVseg) {
-                    // (columns of chunk ch are rewritten by every partial launch; the last one is complete)
-                    rc = flush_group(ch + 1);
-                    if (rc) return rc;
-                    group_chunk0 = ch;
-                }
-                group.push_back(local_desc(c, sg, 0));
-                group_segs.push_back(&sg);
+            if (!(sg.list && sg.tiled)) continue;
+            if ((group.size() + 1) * nbr_now > kMaxVseg) {  // more lists than one launch reads
+                rc = flush_group(ch + 1);
+                if (rc) return rc;
+                group_chunk0 = ch;
             }
-        } else {
-            for (auto &sg : cs.segs)
-                if (sg.list && sg.tiled) {
-                    group.push_back(local_desc(c, sg, ch - group_chunk0));
-                    group_segs.push_back(&sg);
-                }
+            group.push_back(local_desc(c, sg, ch - group_chunk0));
+            group_segs.push_back(&sg);
         }
         // (4) what is still packed goes through the direct kernel (small inputs, or no memory for a list);
         //     a chunk's lists are counted first, so that the chunk's column is complete afterwards
@@ -2490,7 +2481,9 @@ struct MgTotals {
     uint64_t n_kmers, n_distinct_scan, n_distinct, n_saturated, n_windows;
 };
 
-int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm) {
+// final = false: skm_mg_flush — count what has been ingested so far and free the lists / arenas
+// (chunks == 0 only: without histogram columns the order of counting does not matter).
+int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm, bool final) {
     const uint32_t N = c->n_ranks, me = c->p.rank;
     const size_t nbins = c->p.histo_max + 2;
     // ---- phase 1: local work, then the directory of what everybody shipped (doubles as the
@@ -2516,7 +2509,7 @@ int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm) {
         windows_all += hdrs[r].n_windows;
         reads_all += hdrs[r].n_reads;
     }
-    if (reads_all == 0)  // src/io.rs:578-580
+    if (reads_all == 0 && final)  // src/io.rs:578-580
         return fail(c, SKM_ERR_NO_READS, "No reads were ingested. Check that input files contain valid FASTQ records.");
     std::vector<MgRecord> all((size_t)N * std::max(max_rec, 1u)), sendbuf(std::max(max_rec, 1u));
     std::copy(c->mg_sent.begin(), c->mg_sent.end(), sendbuf.begin());
@@ -2680,12 +2673,18 @@ int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm) {
     }
     // lists and arena contents are no longer needed; the last all-gather above is also the barrier
     // after which a peer may write into this rank's arena again (next sample)
-    for (auto &cs : c->chunks)
+    for (auto &cs : c->chunks) {
         for (auto &sg : cs.segs) {
             release_list(c, sg, c->stream);
             if (sg.ready) c->event_pool.push_back(sg.ready);
             sg.ready = nullptr;
         }
+        if (!final) cs.segs.clear();   // (the chunk's byte and read counters stay)
+    }
+    if (!final) {
+        for (auto &cur : c->mg_cursor) cur = 0;
+        c->mg_sent.clear();
+    }
     collect_spans(c);
     return SKM_OK;
 }
@@ -2705,6 +2704,7 @@ int32_t skm_mg_arena_create(skm_ctx *c, uint64_t bytes) {
     const size_t sub = ((size_t)(bytes / c->n_ranks) + 255) & ~(size_t)255;
     // cudaMalloc, not the stream-ordered pool: the block must be exportable through CUDA IPC
     CU(cudaMalloc((void **)&c->mg_arena, sub * c->n_ranks));
+    c->mem_budget -= std::min(c->mem_budget, sub * c->n_ranks - c->mg_arena_bytes);
     c->mg_arena_bytes = sub * c->n_ranks;
     c->mg_sub_bytes = sub;
     c->mg_peer[c->p.rank] = c->mg_arena;
@@ -2762,17 +2762,19 @@ int32_t skm_mg_bytes_sent(skm_ctx *c, uint64_t *out) {
     return SKM_OK;
 }
 
-int32_t skm_mg_finalize(skm_ctx *c, const skm_comm *comm) {
+static int32_t mg_finalize_or_flush(skm_ctx *c, const skm_comm *comm, bool final) {
     if (!c || !comm || !comm->allgather) return SKM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    if (c->finalized) return fail(c, SKM_ERR_STATE, "finalize called twice");
-    if (c->n_ranks == 1) return finalize_common(c);
+    if (c->finalized) return fail(c, SKM_ERR_STATE, final ? "finalize called twice" : "flush after finalize");
+    if (!final && c->p.chunks > 0)
+        return fail(c, SKM_ERR_STATE, "skm_mg_flush needs chunks == 0 (histogram columns fix the order of counting)");
+    if (c->n_ranks == 1) return final ? finalize_common(c) : fail(c, SKM_ERR_STATE, "skm_mg_flush needs n_ranks > 1");
     if (!c->mg_arena) return fail(c, SKM_ERR_STATE, "no receive arena: call skm_mg_arena_create and wire the peers first");
-    c->finalized = true;
+    c->finalized = final;
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     cudaEventRecord(e0, c->stream);
-    const int32_t rc = mg_finalize_impl(c, comm);
+    const int32_t rc = mg_finalize_impl(c, comm, final);
     cudaEventRecord(e1, c->stream);
     if (cudaStreamSynchronize(c->stream) == cudaSuccess) {
         float ms = 0;
@@ -2782,6 +2784,9 @@ int32_t skm_mg_finalize(skm_ctx *c, const skm_comm *comm) {
     c->event_pool.push_back(e1);
     return rc;
 }
+
+int32_t skm_mg_finalize(skm_ctx *c, const skm_comm *comm) { return mg_finalize_or_flush(c, comm, true); }
+int32_t skm_mg_flush(skm_ctx *c, const skm_comm *comm) { return mg_finalize_or_flush(c, comm, false); }
 
 }  // extern "C"
 
@@ -2866,7 +2871,11 @@ int32_t skm_group_create(const skm_params *params, uint32_t n_ranks, const int32
 
 skm_ctx *skm_group_ctx(skm_group *g, uint32_t rank) { return g && rank < g->ctx.size() ? g->ctx[rank] : nullptr; }
 
-int32_t skm_group_finalize(skm_group *g) {
+static int32_t group_collective(skm_group *g, bool final);
+int32_t skm_group_finalize(skm_group *g) { return group_collective(g, true); }
+int32_t skm_group_flush(skm_group *g) { return group_collective(g, false); }
+
+static int32_t group_collective(skm_group *g, bool final) {
     if (!g || g->ctx.empty()) return SKM_ERR_INVALID_ARG;
     const size_t n = g->ctx.size();
     std::vector<int32_t> rcs(n, SKM_OK);
@@ -2876,7 +2885,7 @@ int32_t skm_group_finalize(skm_group *g) {
         members[r] = GroupMember{g, (uint32_t)r};
         threads.emplace_back([&, r] {
             skm_comm comm{&members[r], group_allgather};
-            rcs[r] = skm_mg_finalize(g->ctx[r], &comm);
+            rcs[r] = final ? skm_mg_finalize(g->ctx[r], &comm) : skm_mg_flush(g->ctx[r], &comm);
         });
     }
     for (auto &t : threads) t.join();

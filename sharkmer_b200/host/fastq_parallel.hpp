@@ -514,7 +514,7 @@ class ParallelIngest {
 
     // everything handed over has been copied to the device
     void finish() {
-        e_.check(skm_sync(e_.raw()));
+        e_.sync();
         for (auto &s : stage_) s.in_flight = false;
     }
 
@@ -588,7 +588,7 @@ class ParallelIngest {
         }
         Stage &st = stage_[stage_next_++ & 1];
         if (st.in_flight) {  // its previous contents may still be on their way to the device
-            e_.check(skm_sync(e_.raw()));
+            e_.sync();
             for (auto &s : stage_) s.in_flight = false;
         }
         const size_t total = (size_t)chunk_base[n_chunks_];

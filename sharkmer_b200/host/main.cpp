@@ -9,6 +9,10 @@
 //   device table (pcr.hpp; no read threading) -> {outdir}{sample}_{gene}.fasta
 //   -t/--threads <n> (all cores): FASTQ framing threads (fastq_parallel.hpp); --serial: the
 //   reference-shaped one-thread reader (ingest.hpp).  Both give the same batches, bit for bit.
+//   --gpus <n> (1): shard the table by k-mer hash over n GPUs (skm_group_*; --devices a,b,.. to pick them,
+//   repeats allowed); --arena-mb <MiB per GPU> (8192): receive arena of the exchange.  Same output files.
+//   --host-mirror: copy the finished table once into a host hash table, so that the in silico PCR's
+//   point lookups are host probes (the route that leaves src/pcr unchanged)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,8 +26,10 @@ int main(int argc, char **argv) {
     uint32_t k = 19, chunks = 0, insert_mode = SKM_INSERT_AUTO;
     uint64_t histo_max = 10000, max_reads = 0, validate_every = 0, capacity_hint = 0;
     int device = -1;
-    unsigned threads = 0;
-    bool paired = false, serial = false;
+    unsigned threads = 0, n_gpus = 1;
+    uint64_t arena_mb = 8192;
+    std::vector<int32_t> devices;
+    bool paired = false, serial = false, host_mirror = false;
     std::vector<std::string> pcr_specs;
     uint32_t min_kmer_count = 2;
     size_t node_budget = 0;
@@ -48,6 +54,17 @@ int main(int argc, char **argv) {
         else if (a == "--validate-every") validate_every = std::strtoull(val(), nullptr, 10);
         else if (a == "--capacity-hint") capacity_hint = std::strtoull(val(), nullptr, 10);
         else if (a == "--device") device = std::atoi(val());
+        else if (a == "--gpus") n_gpus = (unsigned)std::strtoul(val(), nullptr, 10);
+        else if (a == "--arena-mb") arena_mb = std::strtoull(val(), nullptr, 10);
+        else if (a == "--devices") {
+            std::string v = val();
+            for (size_t at = 0; at <= v.size();) {
+                size_t e = v.find(',', at);
+                if (e == std::string::npos) e = v.size();
+                devices.push_back(std::atoi(v.substr(at, e - at).c_str()));
+                at = e + 1;
+            }
+        } else if (a == "--host-mirror") host_mirror = true;
         else if (a == "--paired") paired = true;
         else if (a == "--serial") serial = true;
         else if (a == "--pcr-primers") pcr_specs.push_back(val());
@@ -72,7 +89,7 @@ int main(int argc, char **argv) {
             auto errs = skm::pcr::validate_pcr_params(pcr_runs.back());
             if (!errs.empty()) throw skm::Error(SKM_ERR_INVALID_ARG, errs[0].first + " (" + errs[0].second + ")");
         }
-        skm::Engine eng(k, chunks, histo_max, capacity_hint, device, insert_mode);  // validates k, histo_max
+        skm::Engine eng(k, chunks, histo_max, capacity_hint, device, insert_mode, n_gpus, arena_mb << 20, devices);  // validates k, histo_max
         if (paired && max_reads > 0 && max_reads % 2 != 0) max_reads += 1;  // src/io.rs:483-485
         uint64_t n_reads_read = 0, n_bases_read = 0;
         if (serial) {
@@ -107,6 +124,7 @@ int main(int argc, char **argv) {
         std::vector<skm::pcr::GeneResult> pcr_results;
         if (!pcr_runs.empty()) {   // main.rs:146-177
             skm::KmerCounts table(eng);
+            if (host_mirror) table.mirror_to_host();
             const size_t budget = node_budget ? node_budget : skm::pcr::compute_node_budget(t.n_bases);
             pcr_results = skm::pcr::run_pcr(table, pcr_runs, sample, dir, min_kmer_count, budget);
             for (auto &r : pcr_results) {

@@ -218,10 +218,9 @@ class WaveLookups {
             kmers.reserve(todo.size() * 4);
             for (uint64_t q : todo)
                 for (uint64_t b = 0; b < 4; b++) kmers.push_back(candidate(q >> 1, (int)(q & 1), b));
-            std::vector<uint32_t> counts(kmers.size());
-            std::vector<uint8_t> found(kmers.size());
-            table_.engine().check(skm_lookup_batch(table_.engine().raw(), kmers.data(), kmers.size(), view_min_,
-                                                   SKM_LOOKUP_EITHER, counts.data(), found.data()));
+            std::vector<uint32_t> counts;
+            std::vector<uint8_t> found;
+            table_.lookup_found(kmers, view_min_, SKM_LOOKUP_EITHER, counts, found);
             calls++;
             kmers_asked += kmers.size();
             for (size_t i = 0; i < todo.size(); i++) {

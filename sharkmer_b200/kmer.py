@@ -189,6 +189,10 @@ class Engine:
         """Collective.  comm_struct: a ctypes skm_comm (sharkmer_b200.multigpu builds one over torch.distributed)."""
         self._ck(self.L.skm_mg_finalize(self._h, C.byref(comm_struct)))
 
+    def mg_flush(self, comm_struct):
+        """Collective, chunks == 0: count what was ingested so far, free lists and arenas."""
+        self._ck(self.L.skm_mg_flush(self._h, C.byref(comm_struct)))
+
     def mg_bytes_sent(self) -> int:
         n = C.c_uint64()
         self._ck(self.L.skm_mg_bytes_sent(self._h, C.byref(n)))

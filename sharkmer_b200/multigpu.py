@@ -132,6 +132,11 @@ class ShardedCounter:
             return None
         return np.stack([e.histogram(c) for c in range(e.n_chunks)])
 
+    def flush(self):
+        """Collective (chunks == 0): count what has been ingested so far and free the lists and arenas —
+        for inputs that do not fit the GPUs' memory in one piece."""
+        self.e.mg_flush(self.comm.struct)
+
     @property
     def bytes_sent(self) -> int:
         return self.e.mg_bytes_sent()
@@ -211,6 +216,9 @@ class Group:
 
     def finalize(self):
         self._ck(self.L.skm_group_finalize(self._h))
+
+    def flush(self):
+        self._ck(self.L.skm_group_flush(self._h))
 
     def reset(self):
         self._ck(self.L.skm_group_reset(self._h))

@@ -47,8 +47,23 @@ int32_t skm_histogram(skm_ctx *, uint32_t, uint64_t *, uint64_t) { return SKM_ER
 int32_t skm_totals_get(skm_ctx *, skm_totals *t) { std::memset(t, 0, sizeof *t); return SKM_OK; }
 int32_t skm_chunk_totals(skm_ctx *, uint32_t, skm_totals *t) { std::memset(t, 0, sizeof *t); return SKM_OK; }
 int32_t skm_stage_times(skm_ctx *, skm_stage_ms *t) { std::memset(t, 0, sizeof *t); return SKM_OK; }
-int32_t skm_table_len(skm_ctx *, uint64_t *n) { *n = 0; return SKM_OK; }
-int32_t skm_export(skm_ctx *, uint64_t *, uint32_t *, uint64_t, int32_t, uint64_t *n) { *n = 0; return SKM_OK; }
+int32_t skm_table_len(skm_ctx *c, uint64_t *n) { *n = c->table.size(); return SKM_OK; }
+int32_t skm_export(skm_ctx *c, uint64_t *keys, uint32_t *counts, uint64_t cap, int32_t, uint64_t *n) {
+    *n = c->table.size();
+    if (!keys || cap < *n) return keys ? SKM_ERR_INVALID_ARG : SKM_OK;
+    uint64_t i = 0;
+    for (auto &kv : c->table) {   // (ascending: std::map)
+        keys[i] = kv.first;
+        counts[i++] = kv.second;
+    }
+    return SKM_OK;
+}
+// the sharded entry points are not mocked: the host's group mode needs the real library
+int32_t skm_group_create(const skm_params *, uint32_t, const int32_t *, uint64_t, skm_group **out) { *out = nullptr; return SKM_ERR_STATE; }
+skm_ctx *skm_group_ctx(skm_group *, uint32_t) { return nullptr; }
+int32_t skm_group_finalize(skm_group *) { return SKM_ERR_STATE; }
+const char *skm_group_last_error(skm_group *) { return "not mocked"; }
+void skm_group_destroy(skm_group *) {}
 // the lookup contract of include/sharkmer_b200.h over the mock's std::map
 int32_t skm_lookup_batch(skm_ctx *c, const uint64_t *kmers, uint64_t n, uint32_t min_count, int32_t mode,
                          uint32_t *counts, uint8_t *found) {
@@ -95,6 +110,7 @@ int32_t skm_scan_oligos(skm_ctx *c, const uint64_t *oligos, uint64_t n_oligos, u
     }
     *n_out = out.size();
     if (!keys) return SKM_OK;
+    if (cap < out.size()) { c->err = "scan buffers too small"; return SKM_ERR_INVALID_ARG; }
     uint64_t i = 0;
     for (auto &kv : out) {
         if (i >= cap) break;
@@ -115,7 +131,7 @@ int main(int argc, char **argv) {
     uint64_t max_reads = 0, validate_every = 0;
     size_t buffer_bytes = 0, window_bytes = size_t(128) << 20;
     unsigned threads = 0;
-    bool paired = false, serial = false;
+    bool paired = false, serial = false, mirror = false, mirror_check = false;
     skm::PCRParams pcr;
     std::string table_path, sample = "sample", outdir = "./";
     std::vector<std::string> pcr_specs;
@@ -137,6 +153,8 @@ int main(int argc, char **argv) {
         else if (a == "--window-bytes") window_bytes = std::strtoull(argv[++i], nullptr, 10);
         else if (a == "--dump") dump = argv[++i];
         else if (a == "--table") table_path = argv[++i];
+        else if (a == "--host-mirror") mirror = true;
+        else if (a == "--mirror-check") mirror_check = true;
         else if (a == "--pcr-primers") pcr_specs.push_back(argv[++i]);
         else if (a == "--sample") sample = argv[++i];
         else if (a == "--outdir") outdir = argv[++i];
@@ -163,6 +181,27 @@ int main(int argc, char **argv) {
             skm::KmerCounts table(eng);
             while (f && std::fscanf(f, "%llu %llu", &km, &ct) == 2) table.insert((uint64_t)km, (uint32_t)ct);
             if (f) std::fclose(f);
+            if (mirror) table.mirror_to_host();
+            if (mirror_check) {
+                // host mirror vs the ABI's lookups: every key, its reverse complement and absent k-mers, three modes
+                skm::KmerCounts direct(eng);
+                table.mirror_to_host();
+                auto kv = direct.iter();
+                std::vector<uint64_t> probe = kv.first;
+                for (uint64_t x : kv.first) probe.push_back(skm::revcomp_kmer(x, k));
+                for (uint64_t i = 0; i < 500; i++) probe.push_back((i * 0x9e3779b97f4a7c15ull) >> (64 - 2 * k));
+                size_t bad = 0;
+                for (int mode = 0; mode < 3; mode++)
+                    for (uint32_t mc : {0u, 2u, 5u}) {
+                        std::vector<uint32_t> c1, c2;
+                        std::vector<uint8_t> f1, f2;
+                        table.lookup_found(probe, mc, mode, c1, f1);
+                        direct.lookup_found(probe, mc, mode, c2, f2);
+                        for (size_t i = 0; i < probe.size(); i++) bad += c1[i] != c2[i] || f1[i] != f2[i];
+                    }
+                std::printf("mirror %zu keys %zu probes %zu mismatches\n", kv.first.size(), probe.size(), bad);
+                return bad ? 1 : 0;
+            }
             if (!pcr_specs.empty()) {
                 // sPCR mode: one "gene status n_products lengths... | reason" line per primer pair
                 std::vector<skm::pcr::Params> runs;

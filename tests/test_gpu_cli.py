@@ -87,3 +87,19 @@ def test_cli_errors_match_reference_text(oracle, tmp_path):
     empty.write_text("")
     (rg, _), (ro, _) = run_both(tmp_path, ["-k", 21], [empty])
     assert rg.returncode == 1 and "No reads were ingested" in rg.stderr and "No reads were ingested" in ro.stderr
+
+
+@pytest.mark.parametrize("gpus,devices", [(2, "0,0"), (3, "0,0,0")])
+def test_sharded_cli_writes_identical_files(oracle, tmp_path, gpus, devices):
+    """`--gpus N` (skm_group_*: the multi-GPU path behind the C ABI, driven by the C++ host the way
+    src/main.rs:112-131 drives one table): the same .histo / .final.histo / stats bytes as the oracle,
+    with the N ranks sharing cuda:0."""
+    fq = tmp_path / "reads.fastq.gz"
+    oracle.synth_fastq(fq, seed=11, genome_len=80_000, read_len=150, sub_rate=0.01, n_rate=0.001, first=0, n=21_300, gzip=True)
+    (rg, dg), (ro, do) = run_both(tmp_path, ["-k", 25, "--chunks", 5, "--histo-max", 300], [fq],
+                                  ("--gpus", str(gpus), "--devices", devices, "--arena-mb", "128"))
+    assert rg.returncode == 0, rg.stderr
+    assert ro.returncode == 0, ro.stderr
+    for f in ("smp.histo", "smp.final.histo"):
+        assert open(dg / f, "rb").read() == open(do / f, "rb").read(), f
+    assert stats_fields(dg / "smp.stats.yaml") == stats_fields(do / "smp.stats.yaml")

@@ -631,3 +631,116 @@ def test_sharded_two_processes_one_gpu(oracle):
     okeys, ocounts = run.table().export_sorted()
     assert merged == dict(zip(okeys.tolist(), ocounts.tolist()))
     assert sum(t[4] for t in got) == run.n_kmers_ingested
+
+
+# ---- (8) BASELINE.json configurations at full size ----------------------------------------------------
+
+def _golden_full(name):
+    path = os.path.join(GOLDEN_DIR, "full_cases.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/full_cases.json missing (python tests/golden/make_golden_full.py)")
+    g = json.load(open(path))
+    if name not in g:
+        pytest.skip(f"{name} not in full_cases.json")
+    return g[name]
+
+
+def _run_config_on_device(skm, oracle, g, mode=0, hint=0):
+    """Device-generated reads of a full_cases.json configuration, fed like src/io.rs does."""
+    k, chunks, hmax, L, n = g["k"], g["chunks"], g["histo_max"], g["read_len"], g["n_reads"]
+    n_chunks = max(1, chunks)
+    st, nt = oracle.rate_to_thresh(g["sub_rate"]), oracle.rate_to_thresh(g["n_rate"])
+    e = skm.Engine(k, chunks, hmax, capacity_hint=hint, insert_mode=mode)
+    n_batches = (n + 999) // 1000
+    for c in range(n_chunks):
+        per = len(range(c, n_batches, n_chunks)) * 1000     # (n is a multiple of 1000 * n_chunks here)
+        d = e.device_alloc(per * (L + 1))
+        e.synth_device(g["seed"], g["genome_len"], L, st, nt, c, n_chunks, 0, per, d)
+        e.ingest_device(c, d, per * (L + 1))
+        e.sync()
+        e.device_free(d)
+    e.finalize()
+    return e
+
+
+def _check_against_golden(e, g):
+    t = e.totals()
+    assert (t.n_reads, t.n_bases, t.n_kmers, t.n_unique) == (g["n_reads_ingested"], g["n_bases_ingested"], g["n_kmers"], g["n_unique"])
+    assert e.digest() == g["digest"]
+    for c in range(g["chunks"]):
+        want = np.zeros(g["histo_max"] + 2, dtype=np.uint64)
+        for b, v in g["histograms"][c].items():
+            want[int(b)] = v
+        assert (e.histogram(c) == want).all(), c
+
+
+@pytest.mark.parametrize("name", ["C1_chunks0", "C1_chunks1"])
+def test_c1_full_size_vs_oracle_and_golden(skm, oracle, name):
+    """BASELINE config 1 (sharkmer -k 31 --max-reads 1000000, 1 M synthetic 150 bp reads), chunks 0 and 1:
+    the full sorted (k-mer, count) table and the histogram against the oracle run here, and against the
+    committed golden (digest, totals, histogram) the oracle produced in the build container."""
+    g = _golden_full(name)
+    e = _run_config_on_device(skm, oracle, g, hint=45_000_000)
+    _check_against_golden(e, g)
+    run = oracle.Run(g["k"], g["chunks"], g["histo_max"])
+    for first in range(0, g["n_reads"], 250_000):
+        run.push_lines(oracle.synth_reads(g["seed"], g["genome_len"], g["read_len"], g["sub_rate"], g["n_rate"], first, 250_000))
+    run.finish()
+    keys, counts = e.export(sorted=True)
+    okeys, ocounts = run.table().export_sorted()
+    assert keys.size == okeys.size == g["n_unique"]
+    assert (keys == okeys).all() and (counts == ocounts).all()
+    if g["chunks"]:
+        assert (e.histogram(0) == run.histogram(0)).all()
+    e.close()
+
+
+def test_c2_full_size_vs_golden(skm, oracle):
+    """BASELINE config 2 — the bench workload (k=21, 10 chunks, 10 M reads) at full size through the tiled
+    insert, against the oracle's committed result: table digest, totals and all ten histogram columns."""
+    g = _golden_full("C2")
+    e = _run_config_on_device(skm, oracle, g, hint=320_000_000)
+    assert e.stage_times().tiled_launches >= 1
+    _check_against_golden(e, g)
+    e.close()
+
+
+def test_memory_bounded_rounds(skm, oracle, monkeypatch):
+    """Inputs whose k-mer lists do not fit beside the table (BASELINE config 5 in miniature): with a small
+    memory budget the batches stay packed, and finalize builds and counts their lists a few at a time —
+    in the middle of a chunk if need be.  Same table, same histogram columns."""
+    L, n, k, chunks, hmax = 150, 400_000, 25, 2, 200
+    reads = oracle.synth_reads(61, 3_000_000, L, 0.01, 0.001, 0, n)
+    run = run_oracle(oracle, reads, k, chunks, hmax)
+    # budget = table (2^26 slots = 1 GiB) + 4 GiB slack + ~1.5 lists of 100 k reads (15 M cells, 130 MB each)
+    monkeypatch.setenv("SKM_MEM_BUDGET", str(1024 + 4096 + 200))
+    e = skm.Engine(k, chunks, hmax, capacity_hint=38_000_000, insert_mode=2)
+    line = L + 1
+    for b in range(0, n // 1000, 100):        # 100 batches (100 k reads) per call, alternating chunks
+        c = (b // 100) % chunks
+        e.ingest_batch(c, reads[b * 1000 * line:(b + 100) * 1000 * line])
+    e.finalize()
+    assert e.stage_times().tiled_launches >= 3
+    keys, counts = e.export(sorted=True)
+    okeys, ocounts = run.table().export_sorted()
+    # (the batches were dealt to the chunks 100 at a time, not round-robin: compare what does not depend on that)
+    assert (keys == okeys).all() and (counts == ocounts).all()
+    assert (e.histogram(chunks - 1) == run.histogram(chunks - 1)).all()
+    e.close()
+
+
+def test_sharded_group_flush_rounds(skm, oracle):
+    """skm_group_flush: a sharded count in several rounds (chunks == 0), lists and arenas freed in between."""
+    from sharkmer_b200.multigpu import Group
+    L, n, k, world = 100, 24_000, 31, 3
+    reads = oracle.synth_reads(8, 60_000, L, 0.01, 0.001, 0, n)
+    run = run_oracle(oracle, reads, k, 0, 100)
+    g = Group(k, 0, 100, [0] * world, arena_bytes_per_rank=64 << 20, insert_mode=2)
+    line = L + 1
+    for b in range(n // 1000):
+        g.engines[b % world].ingest_batch(0, reads[b * 1000 * line:(b + 1) * 1000 * line])
+        if b % 8 == 7:
+            g.flush()
+    g.finalize()
+    _check_sharded(g, g.engines, run, 0, world)
+    g.close()

@@ -565,3 +565,25 @@ def test_cpp_levenshtein_and_primer_spec_errors(harness, tmp_path):
     assert r.returncode == 1 and "min-count is 1, must be at least 2" in r.stderr
     r = spec("forward=ACGT,reverse=TTGA")
     assert r.returncode == 1 and "Gene name is empty" in r.stderr
+
+
+def test_cpp_host_mirror_equals_device_lookups(harness, oracle, tmp_path):
+    """KmerCounts::mirror_to_host (the route that leaves src/pcr's one-k-mer-at-a-time calls unchanged:
+    src/kmer/counting.rs:328-336 called from src/pcr/graph.rs:419-430): the host open-addressing copy
+    answers every lookup mode exactly like the ABI's skm_lookup_batch, and sPCR over the mirror writes the
+    same FASTA bytes as sPCR over batched ABI lookups."""
+    t = table_18s(oracle)
+    keys, counts = t.export_sorted()
+    tf = tmp_path / "table.txt"
+    with open(tf, "w") as f:
+        for a, b in zip(keys.tolist(), counts.tolist()):
+            f.write(f"{a} {b}\n")
+    r = subprocess.run([harness, "-k", "21", "--table", str(tf), "--mirror-check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith(f"mirror {keys.size} keys") and r.stdout.strip().endswith("0 mismatches")
+    spec = [spec_of(params_18s())]
+    a, out_a = run_cpp_pcr(harness, tmp_path, t, 21, spec, "smp", ["--min-kmer-count", "1"])
+    fasta_a = open(out_a / "smp_18s.fasta").read()
+    b, out_b = run_cpp_pcr(harness, tmp_path, t, 21, spec, "smp", ["--min-kmer-count", "1", "--host-mirror"])
+    assert a.returncode == 0 and b.returncode == 0 and a.stdout == b.stdout
+    assert open(out_b / "smp_18s.fasta").read() == fasta_a
