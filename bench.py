@@ -107,7 +107,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -322,7 +322,22 @@ def run_ours(args):
         cpu_group = dist.new_group(backend="gloo")   # carries the library's all-gathers (host bytes); NCCL: barriers only
         # receive arena: this rank's share of all ranks' k-mers = ~its own input x 8 B, +6 % capped-region
         # slack, +3 % tile offsets, + margin for imbalance
-        arena = int(in_bytes * 8 * 1.25) + (256 << 20)
+        # Rounds: when lists + arena of the whole input do not fit beside the table (chunks == 0 only), the input is
+        # counted in rounds with a collective flush in between (a flush empties lists and arenas).
+        global BUFS_PER_ROUND
+        if CHUNKS == 0:
+            table_bytes = 16 * (1 << int(np.ceil(np.log2(max(hint, 1) / 0.6))))
+            free_b = torch.cuda.mem_get_info(dev)[0]
+            rounds = 1 if not BUFS_PER_ROUND else N_BUF // BUFS_PER_ROUND
+            while rounds < N_BUF and in_bytes / rounds * (9.7 + 9.7 + 10.4) + (8 << 30) > free_b - table_bytes:
+                rounds += 1
+                while N_BUF % rounds:
+                    rounds += 1
+            BUFS_PER_ROUND = N_BUF // rounds if rounds > 1 else 0
+        per_round = in_bytes * (BUFS_PER_ROUND / N_BUF if BUFS_PER_ROUND else 1.0)
+        # (every source's list for this rank: 1/N of its positions x 8 B, +12 % owner imbalance, +6 % bucket slack,
+        #  +3 % tile offsets, + the fixed slack of a capped list per batch)
+        arena = int(per_round * 8 * 1.3) + (256 << 20) + (10 << 20) * len(d_bufs) * world
         sharded = ShardedCounter(eng, dev, cpu_group=cpu_group, arena_bytes=arena)
 
     def step(host_buffers: bool):
@@ -378,7 +393,7 @@ def run_ours(args):
         chk_sh = None
         if world > 1:
             chk_sh = ShardedCounter(chk, dev, cpu_group=cpu_group,
-                                    arena_bytes=int(sum(t.numel() for t in s_bufs) * 8 * 1.5) + (64 << 20))
+                                    arena_bytes=int(sum(t.numel() for t in s_bufs) * 8 * 1.5) + (64 << 20) * world)
         for i, t in enumerate(s_bufs):
             if t.numel():
                 chk.ingest_device(i if CHUNKS > 0 else 0, t.data_ptr(), t.numel())
@@ -536,6 +551,7 @@ def run_ours(args):
                          "kmers_per_sec_in_kernel": n_kmers_local / (max(stt.insert, 1e-6) * 1e-3)},
             "gpu_launches": int(stt.kernel_launches) * args.steps,
             "nvlink_bytes_sent_per_step_rank0": sharded.bytes_sent if sharded else 0,
+            "rounds": (N_BUF // BUFS_PER_ROUND) if BUFS_PER_ROUND else 1,
             "exchange": None if world == 1 else "copy-engine peer copies over NVLink into per-source sub-arenas at ingest time "
                         "(no SM time); NCCL carries only the bench's barriers and all-reduces, gloo the library's all-gathers",
             "clocks": clocks,

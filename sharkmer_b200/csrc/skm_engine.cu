@@ -35,7 +35,22 @@ constexpr uint32_t kMinLog2Cap = 16;
 
 enum Stage { ST_H2D, ST_PACK, ST_COUNT, ST_PART, ST_INSERT, ST_HISTO, ST_GROW, ST_FINALIZE, ST_SCAN, ST_SORT, ST_N };
 
+// Multi-GPU: the k-mers of one batch that belong to ONE owner rank, bucketed by that owner's kFineRegions
+// table regions and tile-sorted — the same geometry a single GPU builds for itself.  The owner's own list
+// stays here; the others are shipped whole into the owners' receive arenas.
+struct OwnerList {
+    unsigned long long *list = nullptr, *meta = nullptr;
+    uint16_t *tile_off = nullptr;
+    uint32_t max_tiles = 0;
+    uint64_t cap = 0;           // capped layout: cells per bucket (0 = exact layout)
+    size_t cells = 0;
+    uint64_t *h_off = nullptr;  // pinned: capped = kFineRegions totals + overflow total; exact = kFineRegions + 1 offsets
+    bool shipped = false;
+    size_t rec = 0;             // its record in skm_ctx::mg_sent
+};
+
 struct Segment {
+    std::vector<OwnerList> owners;   // n_ranks > 1 only
     uint64_t *codes = nullptr;
     uint32_t *breaks = nullptr;
     uint64_t n_units = 0;
@@ -227,6 +242,16 @@ int32_t fail(skm_ctx *c, int32_t code, const char *fmt, ...) {
         if (e_ != cudaSuccess)                                                                     \
             return fail(c, e_ == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA,           \
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// SKM_SYNC_DEBUG=1: synchronise the device after the marked launches and report where a fault surfaced
+#define DBG_SYNC(where)                                                                                  \
+    do {                                                                                                 \
+        static const bool dbg_ = getenv("SKM_SYNC_DEBUG") != nullptr;                                    \
+        if (dbg_) {                                                                                      \
+            cudaError_t e_ = cudaDeviceSynchronize();                                                    \
+            if (e_ != cudaSuccess) return fail(c, SKM_ERR_CUDA, "fault after %s: %s", where, cudaGetErrorString(e_)); \
+        }                                                                                                \
     } while (0)
 
 struct DeviceGuard {
@@ -560,8 +585,9 @@ int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketF
 void release_list(skm_ctx *c, Segment &sg, cudaStream_t st);
 int32_t drop_capped_list(skm_ctx *c, uint32_t chunk, Segment &sg, cudaStream_t st) {
     CU(cudaEventSynchronize(sg.ready));
-    uint64_t counted = 0;
-    for (uint32_t r = 0; r < sg.n_buckets; r++) counted += sg.h_offsets[r];
+    uint64_t counted = 0;   // windows the bucketing of this batch added to the chunk's counter
+    if (sg.cap) for (uint32_t r = 0; r < sg.n_buckets; r++) counted += sg.h_offsets[r];
+    else counted = sg.h_offsets[sg.n_buckets];
     adjust_counter_kernel<<<1, 1, 0, st>>>(&c->d_cc[chunk].n_windows, 0ull - counted);
     c->launches++;
     release_list(c, sg, st);
@@ -773,6 +799,15 @@ void release_list(skm_ctx *c, Segment &sg, cudaStream_t st) {
         c->list_bytes -= std::min<size_t>(c->list_bytes, (size_t)sg.max_tiles * ((1u << c->g2) + 1) * sizeof(uint16_t));
     }
     if (sg.d_counts) cudaFreeAsync(sg.d_counts, st);
+    for (auto &ol : sg.owners) {
+        if (ol.list) {
+            cudaFreeAsync(ol.list, st);
+            c->list_bytes -= std::min<size_t>(c->list_bytes, ol.cells * sizeof(uint64_t));
+        }
+        if (ol.meta) cudaFreeAsync(ol.meta, st);
+        if (ol.tile_off) cudaFreeAsync(ol.tile_off, st);
+    }
+    sg.owners.clear();
     sg.list = nullptr;
     sg.meta = nullptr;
     sg.tile_off = nullptr;
@@ -781,13 +816,17 @@ void release_list(skm_ctx *c, Segment &sg, cudaStream_t st) {
     sg.cap = 0;
 }
 
-ListGeom list_geom(const skm_ctx *c) { return ListGeom{c->n_ranks, route_log2_regions(c), c->g2}; }
+// geometry of the lists the insert kernel reads: on one GPU the buckets of pass A are the table regions; across
+// GPUs every owner's slice is re-bucketed into kFineRegions regions of that owner (tile_rebucket_kernel)
+uint32_t list_log2_regions(const skm_ctx *c) { return c->n_ranks > 1 ? kFineLog2 : route_log2_regions(c); }
+ListGeom list_geom(const skm_ctx *c) { return ListGeom{c->n_ranks, list_log2_regions(c), c->g2}; }
 
 // Passes A and B for one packed segment, on c->work: bucket its k-mers by (owner, table region)
 // into a list — capped one-pass layout, or exact two-pass layout — then sort every tile of every
 // bucket by sub-bucket in place (tile_sort_kernel).  `must`: fail instead of skipping when memory
 // is short.  Leaves sg.list == nullptr when skipped.
-int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off, bool exact, bool must, int reserve_tables = 3) {
+int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off, bool exact, bool must, int reserve_tables = 3,
+                   bool sort = true) {
     Segment &sg = c->chunks[chunk].segs[seg_index];
     const BucketFn fn = route_fn(c);
     const uint32_t nb = c->n_ranks << fn.log2_regions;
@@ -806,7 +845,7 @@ int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off
         cells = sg.n_bytes;
         max_tiles = (uint32_t)(sg.n_bytes / kTile) + nb + 1;
     }
-    const size_t off_bytes = (size_t)max_tiles * (F + 1) * sizeof(uint16_t);
+    const size_t off_bytes = sort ? (size_t)max_tiles * (F + 1) * sizeof(uint16_t) : 16;
     const size_t need = cells * 8 + off_bytes;
     // budget = device memory that was free when the ctx was created (no cudaMemGetInfo here: it would serialise
     // the ingest path); room is kept for `reserve_tables` tables of the current size (growth) plus slack
@@ -853,6 +892,12 @@ int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off
         CU(cudaFreeAsync(sg.breaks, c->work));
         sg.codes = nullptr;
         sg.breaks = nullptr;
+    }
+    if (!sort) {   // multi-GPU: the coarse list is refined per owner first (refine_owner_lists)
+        CU(cudaGetLastError());
+        DBG_SYNC("coarse bucketing");
+        CU(cudaEventRecord(sg.ready, c->work));
+        return SKM_OK;
     }
     // The tile sort runs on its own stream: it is bound by HBM bandwidth, the bucketing of the NEXT
     // batch (same `work` stream otherwise) by instruction issue, so the two share the chip well.
@@ -992,6 +1037,7 @@ int32_t launch_tiled(skm_ctx *c, const std::vector<SegDesc> &segs, uint32_t chun
         if (histo) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_insert_kernel<true>, kInsThreads, smem));
         else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_insert_kernel<false>, kInsThreads, smem));
         const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(L.n_parts, (uint64_t)c->sm_count * std::max(occ, 1)));
+        DBG_SYNC("descriptor upload before tile_insert");
         if (getenv("SKM_DEBUG"))
             std::fprintf(stderr, "[skm] tile_insert: grid %u (occ %d) smem %zu k_low %u chunks %u lists %u parts %llu g1 %u g2 %u log2cap %u fresh %d attempt %u\n",
                          grid, occ, smem, L.k_low, n_chunks_l, n, (unsigned long long)L.n_parts, L.g1, L.g2, L.log2cap, L.fresh, attempt);
@@ -1072,7 +1118,8 @@ int32_t launch_tiled(skm_ctx *c, const std::vector<SegDesc> &segs, uint32_t chun
     return SKM_OK;
 }
 
-int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index);
+int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on_host);
+int32_t refine_owner_lists(skm_ctx *c, uint32_t chunk, size_t seg_index, bool exact);
 
 // Bucket a freshly packed segment by table region right away (single GPU).  The work is queued
 // behind the pack kernel on the ctx's stream, so it overlaps the next batch's host-to-device copy,
@@ -1095,32 +1142,121 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force
     // batches whose bucket counts could overflow 32 bits, take the exact two-pass layout.
     const bool exact = force || !c->capped || sg.n_bytes >= (3ull << 30) || sg.n_bytes / nb < 4096;
     // (a table sized from a capacity_hint is not expected to grow: keep room for it alone)
-    int32_t rc = build_list(c, chunk, seg_index, h_off, exact, force, c->p.capacity_hint ? 1 : 3);
+    int32_t rc = build_list(c, chunk, seg_index, h_off, exact, force, c->p.capacity_hint ? 1 : 3, /*sort=*/c->n_ranks == 1);
+    if (rc || c->n_ranks == 1 || !sg.list) return rc;
+    rc = refine_owner_lists(c, chunk, seg_index, exact);
     if (rc) return rc;
-    if (c->n_ranks > 1 && sg.list && sg.cap) rc = ship_segment(c, chunk, seg_index);  // exchange starts at ingest time
-    return rc;
+    return ship_segment(c, chunk, seg_index, /*sizes_on_host=*/false);  // the exchange starts at ingest time (capped lists)
 }
 
-// Multi-GPU: push the other owners' slices of a tile-sorted list into their receive arenas (peer
-// copies by the copy engines, on the dma stream, ordered after the list's `ready` event).  A capped
-// list has a fixed geometry, so nothing here waits for the device; an exact list (a capped one that
-// overflowed) is shipped from skm_mg_finalize, where its offsets are known on the host.
-int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index) {
+// Multi-GPU, after pass A (coarse list of segment `sg`, bucketed by (owner, coarse region)): one OwnerList per
+// rank — re-bucketed into that owner's kFineRegions table regions (tile_rebucket_kernel), tile-sorted.  The
+// coarse list is freed.  `exact`: exact two-pass layouts (small batches, or the retry of an overflow).
+int32_t refine_owner_lists(skm_ctx *c, uint32_t chunk, size_t seg_index, bool exact) {
     Segment &sg = c->chunks[chunk].segs[seg_index];
-    if (sg.shipped || !sg.list || !sg.tiled) return SKM_OK;
+    const uint32_t N = c->n_ranks, g1c = route_log2_regions(c), R = 1u << g1c, nb_in = N << g1c;
+    const uint32_t F = 1u << c->g2;
+    const ListMeta m_in = list_meta_at(sg.meta, nb_in);
+    const uint64_t n_exp = sg.n_bytes / N + sg.n_bytes / (8ull * N) + 4096;   // an owner's share, with room for imbalance
+    exact = exact || n_exp / kFineRegions < 4096;
+    sg.owners.assign(N, OwnerList{});
+    const size_t smem = tile_rebucket_smem_bytes();
+    // tiles of the coarse list that can hold an owner's k-mers (grid size; the kernel finds the real ones)
+    const uint32_t grid_in = sg.cap ? R * (uint32_t)((sg.cap + kTile - 1) / kTile) : (uint32_t)(sg.n_bytes / kTile) + R + 1;
+    for (uint32_t o = 0; o < N; o++) {
+        OwnerList &ol = sg.owners[o];
+        ol.h_off = alloc_offsets(c, kFineRegions + 1);
+        if (!ol.h_off) return fail(c, SKM_ERR_OOM, "pinned allocation failed");
+        CapLayout lay{};
+        if (!exact) {
+            lay.cap = ((n_exp / kFineRegions + n_exp / (16ull * kFineRegions) + 1024) + 15) & ~15ull;
+            ol.cells = (size_t)lay.cap * kFineRegions;
+            ol.max_tiles = kFineRegions * (uint32_t)((lay.cap + kTile - 1) / kTile);
+        } else {
+            ol.cells = (size_t)sg.n_bytes + 16;   // (an owner cannot get more than the batch holds)
+            ol.max_tiles = (uint32_t)(ol.cells / kTile) + kFineRegions + 1;
+        }
+        ol.cap = lay.cap;
+        const size_t off_bytes = (size_t)ol.max_tiles * (F + 1) * sizeof(uint16_t);
+        if (cudaMallocAsync((void **)&ol.list, ol.cells * sizeof(uint64_t), c->work) != cudaSuccess ||
+            cudaMallocAsync((void **)&ol.tile_off, off_bytes, c->work) != cudaSuccess ||
+            cudaMallocAsync((void **)&ol.meta, list_meta_words(kFineRegions) * sizeof(uint64_t), c->work) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(c, SKM_ERR_OOM, "device allocation failed (owner list of %zu cells)", ol.cells);
+        }
+        c->list_bytes += ol.cells * sizeof(uint64_t);
+        const ListMeta m_o = list_meta_at(ol.meta, kFineRegions);
+        {
+            Span sp(c, ST_PART, c->work);
+            if (!exact) {
+                zero_async(c, c->d_bucket_cursors, (kFineRegions + 1) * sizeof(uint64_t), c->work);
+                tile_rebucket_kernel<0><<<grid_in, kSortThreads, smem, c->work>>>(sg.list, m_in, nb_in, o * R, (o + 1) * R, N,
+                                                                                 c->d_bucket_cursors, ol.list, lay.cap);
+                copy_words_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_cursors, (unsigned long long *)ol.h_off, kFineRegions + 1);
+                tile_plan_kernel<<<1, 1024, 0, c->work>>>(c->d_bucket_cursors, kFineRegions, lay.cap,
+                                                           (uint32_t)((lay.cap + kTile - 1) / kTile), m_o);
+                c->launches += 3;
+            } else {
+                zero_async(c, c->d_bucket_counts, (kFineRegions + 1) * sizeof(uint64_t), c->work);
+                tile_rebucket_kernel<1><<<grid_in, kSortThreads, smem, c->work>>>(sg.list, m_in, nb_in, o * R, (o + 1) * R, N,
+                                                                                 c->d_bucket_counts, nullptr, 0ull);
+                bucket_scan_kernel<<<1, kScanThreads, 0, c->work>>>(c->d_bucket_counts, kFineRegions, c->d_bucket_offsets,
+                                                                    c->d_bucket_cursors);
+                tile_rebucket_kernel<2><<<grid_in, kSortThreads, smem, c->work>>>(sg.list, m_in, nb_in, o * R, (o + 1) * R, N,
+                                                                                 c->d_bucket_cursors, ol.list, 0ull);
+                copy_words_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_offsets, (unsigned long long *)ol.h_off, kFineRegions + 1);
+                tile_plan_kernel<<<1, 1024, 0, c->work>>>(c->d_bucket_offsets, kFineRegions, 0ull, 0u, m_o);
+                c->launches += 5;
+            }
+            c->stage_launches[ST_PART]++;
+        }
+        CU(cudaGetLastError());
+        DBG_SYNC(exact ? "tile_rebucket (exact)" : "tile_rebucket (capped)");
+        cudaStream_t sort_st = c->sort_overlap ? c->sort_stream : c->work;
+        if (sort_st != c->work) {
+            CU(cudaEventRecord(c->ev_sort, c->work));
+            CU(cudaStreamWaitEvent(sort_st, c->ev_sort, 0));
+        }
+        {
+            Span sp(c, ST_SORT, sort_st);
+            tile_sort_kernel<<<ol.max_tiles, kSortThreads, tile_sort_smem_bytes(c->g2), sort_st>>>(ol.list, m_o, kFineRegions,
+                                                                                                  list_geom(c), ol.tile_off);
+            c->launches++;
+            c->stage_launches[ST_SORT]++;
+        }
+        CU(cudaGetLastError());
+        DBG_SYNC("tile_sort of an owner list");
+    }
+    // the coarse list has been consumed (on `work`); the packed form stays for the overflow retry
+    CU(cudaFreeAsync(sg.list, c->work));
+    CU(cudaFreeAsync(sg.meta, c->work));
+    if (sg.tile_off) CU(cudaFreeAsync(sg.tile_off, c->work));
+    c->list_bytes -= std::min<size_t>(c->list_bytes, sg.list_cells * sizeof(uint64_t) + 16);
+    sg.list = nullptr;
+    sg.meta = nullptr;
+    sg.tile_off = nullptr;
+    sg.tiled = true;
+    cudaStream_t last = c->sort_overlap ? c->sort_stream : c->work;
+    if (last != c->work) {   // everything queued on `work` so far happens before `ready` fires
+        CU(cudaEventRecord(c->ev_sort, c->work));
+        CU(cudaStreamWaitEvent(last, c->ev_sort, 0));
+    }
+    CU(cudaEventRecord(sg.ready, last));
+    return SKM_OK;
+}
+
+// Multi-GPU: push the other owners' lists of a batch into their receive arenas (peer copies by the copy
+// engines, on the dma stream, ordered after the batch's `ready` event).  A capped list has a fixed geometry,
+// so nothing here waits for the device; exact lists are shipped from skm_mg_finalize, where their sizes are
+// known on the host.
+int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on_host) {
+    Segment &sg = c->chunks[chunk].segs[seg_index];
+    if (sg.owners.empty()) return SKM_OK;
     const uint32_t me = c->p.rank, N = c->n_ranks;
     for (uint32_t o = 0; o < N; o++)
         if (o != me && !c->mg_peer[o]) return SKM_OK;  // arenas not wired yet: shipped at finalize
-    const uint32_t g1 = route_log2_regions(c), R = 1u << g1, F = 1u << c->g2;
-    const ListMeta m = list_meta_at(sg.meta, sg.n_buckets);
-    std::vector<uint64_t> tile_first;  // exact layout: first tile of every bucket (host copy)
-    if (!sg.cap) {
-        tile_first.assign(sg.n_buckets + 1, 0);
-        for (uint32_t b = 0; b < sg.n_buckets; b++)
-            tile_first[b + 1] = tile_first[b] + (sg.h_offsets[b + 1] - sg.h_offsets[b] + kTile - 1) / kTile;
-    }
-    CU(cudaStreamWaitEvent(c->dma_stream, sg.ready, 0));
-    sg.rec_first = c->mg_sent.size();
+    const uint32_t F = 1u << c->g2;
+    bool waited = false;
     auto take = [&](uint32_t o, size_t bytes, uint64_t *off) -> bool {
         const size_t at = (c->mg_cursor[o] + 255) & ~(size_t)255;
         if (at + bytes > c->mg_sub_bytes) return false;
@@ -1130,41 +1266,47 @@ int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index) {
     };
     for (uint32_t i = 1; i < N; i++) {
         const uint32_t o = (me + i) % N;  // stagger the destinations across ranks
-        uint64_t cell0, n_cells, tile0, n_tiles;
-        if (sg.cap) {
-            const uint64_t tpb = (sg.cap + kTile - 1) / kTile;
-            cell0 = (uint64_t)o * R * sg.cap;
-            n_cells = (uint64_t)R * sg.cap;
-            tile0 = (uint64_t)o * R * tpb;
-            n_tiles = (uint64_t)R * tpb;
+        OwnerList &ol = sg.owners[o];
+        if (ol.shipped || !ol.list) continue;
+        if (!ol.cap && !sizes_on_host) continue;   // exact layout: its offsets are still on their way to the host
+        uint64_t n_cells, n_tiles;
+        if (ol.cap) {
+            n_cells = ol.cells;
+            n_tiles = ol.max_tiles;
         } else {
-            cell0 = sg.h_offsets[(size_t)o * R];
-            n_cells = sg.h_offsets[(size_t)(o + 1) * R] - cell0;
-            tile0 = tile_first[(size_t)o * R];
-            n_tiles = tile_first[(size_t)(o + 1) * R] - tile0;
+            // exact layout: sizes from the offsets (the caller has waited for `ready`)
+            n_cells = ol.h_off[kFineRegions];
+            n_tiles = 0;
+            for (uint32_t b = 0; b < kFineRegions; b++) n_tiles += (ol.h_off[b + 1] - ol.h_off[b] + kTile - 1) / kTile;
+        }
+        if (!waited) {
+            CU(cudaStreamWaitEvent(c->dma_stream, sg.ready, 0));
+            waited = true;
         }
         MgRecord rec{};
         rec.src = me;
         rec.dst = o;
         rec.chunk = chunk;
-        rec.regions = R;
+        rec.regions = kFineRegions;
         rec.n_tiles = (uint32_t)n_tiles;
         rec.n_cells = n_cells;
         const size_t b_cells = n_cells * 8, b_off = n_tiles * (F + 1) * sizeof(uint16_t);
-        const size_t b_cb = (size_t)R * 8, b_tb = (size_t)(R + 1) * 4;
+        const size_t b_cb = (size_t)kFineRegions * 8, b_tb = (size_t)(kFineRegions + 1) * 4;
         if (!take(o, b_cells, &rec.off_cells) || !take(o, b_off, &rec.off_tile_off) || !take(o, b_cb, &rec.off_cell_begin) ||
             !take(o, b_tb, &rec.off_tile_begin))
             return fail(c, SKM_ERR_OOM, "receive arena of rank %u is too small for rank %u's k-mers (%zu bytes per source): create larger arenas",
                         o, me, c->mg_sub_bytes);
+        const ListMeta m = list_meta_at(ol.meta, kFineRegions);
         uint8_t *base = c->mg_peer[o] + (size_t)me * c->mg_sub_bytes;
-        if (b_cells) CU(cudaMemcpyAsync(base + rec.off_cells, sg.list + cell0, b_cells, cudaMemcpyDefault, c->dma_stream));
-        if (b_off) CU(cudaMemcpyAsync(base + rec.off_tile_off, sg.tile_off + tile0 * (F + 1), b_off, cudaMemcpyDefault, c->dma_stream));
-        CU(cudaMemcpyAsync(base + rec.off_cell_begin, m.cell_begin + (size_t)o * R, b_cb, cudaMemcpyDefault, c->dma_stream));
-        CU(cudaMemcpyAsync(base + rec.off_tile_begin, m.tile_begin + (size_t)o * R, b_tb, cudaMemcpyDefault, c->dma_stream));
+        if (b_cells) CU(cudaMemcpyAsync(base + rec.off_cells, ol.list, b_cells, cudaMemcpyDefault, c->dma_stream));
+        if (b_off) CU(cudaMemcpyAsync(base + rec.off_tile_off, ol.tile_off, b_off, cudaMemcpyDefault, c->dma_stream));
+        CU(cudaMemcpyAsync(base + rec.off_cell_begin, m.cell_begin, b_cb, cudaMemcpyDefault, c->dma_stream));
+        CU(cudaMemcpyAsync(base + rec.off_tile_begin, m.tile_begin, b_tb, cudaMemcpyDefault, c->dma_stream));
         c->mg_bytes_sent += b_cells + b_off + b_cb + b_tb;
+        ol.rec = c->mg_sent.size();
+        ol.shipped = true;
         c->mg_sent.push_back(rec);
     }
-    sg.shipped = true;
     return SKM_OK;
 }
 
@@ -1407,13 +1549,16 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     // partitions (one sub-bucket per partition); without one, 2^7 sub-buckets per region — a
     // partition then covers several adjacent sub-buckets, or filters a shared one
     {
-        const int g1 = (int)route_log2_regions(c);
+        const int g1 = (int)list_log2_regions(c);
         int g2 = c->p.capacity_hint ? (int)l2 - (int)kPartLog2 - g1 : 7;
         if (const char *g = getenv("SKM_G2")) g2 = atoi(g);
         c->g2 = (uint32_t)std::max(0, std::min<int>(g2, (int)kMaxSubLog2));
     }
     CU(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)tile_sort_smem_bytes(kMaxSubLog2)));
+    CU(cudaFuncSetAttribute(tile_rebucket_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_rebucket_smem_bytes()));
+    CU(cudaFuncSetAttribute(tile_rebucket_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_rebucket_smem_bytes()));
+    CU(cudaFuncSetAttribute(tile_rebucket_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_rebucket_smem_bytes()));
     CU(cudaFuncSetAttribute(tile_insert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileInsertSmemBudget));
     CU(cudaFuncSetAttribute(tile_insert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileInsertSmemBudget));
     CU(cudaStreamSynchronize(c->stream));
@@ -1437,6 +1582,11 @@ void skm_destroy(skm_ctx *c) {
                 cudaFree(sg.d_counts);
                 cudaFree(sg.meta);
                 cudaFree(sg.tile_off);
+                for (auto &ol : sg.owners) {
+                    cudaFree(ol.list);
+                    cudaFree(ol.meta);
+                    cudaFree(ol.tile_off);
+                }
             }
         cudaFree(c->d_delta);
         cudaFree(c->d_recount);
@@ -2411,49 +2561,54 @@ int32_t mg_prepare_local(skm_ctx *c) {
     CU(cudaStreamSynchronize(c->part_stream));
     CU(cudaStreamSynchronize(c->sort_stream));
     WorkStream ws(c, c->part_stream);
+    const uint32_t nb_coarse = c->n_ranks << route_log2_regions(c);
+    auto build = [&](uint32_t ch, size_t si, bool exact) -> int32_t {
+        Segment &sg = c->chunks[ch].segs[si];
+        uint64_t *h_off = alloc_offsets(c, nb_coarse + 1);
+        if (!h_off) return fail(c, SKM_ERR_OOM, "pinned allocation failed");
+        int32_t r = build_list(c, ch, si, h_off, exact || !c->capped || sg.n_bytes / nb_coarse < 4096, /*must=*/true, 1, /*sort=*/false);
+        if (r) return r;
+        r = refine_owner_lists(c, ch, si, exact);
+        if (r) return r;
+        CU(cudaEventSynchronize(sg.ready));
+        return SKM_OK;
+    };
     for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
         ChunkState &cs = c->chunks[ch];
         for (size_t si = 0; si < cs.segs.size(); si++) {
             Segment &sg = cs.segs[si];
-            if (!sg.list && sg.codes) {  // skipped at ingest time (memory): build it now
-                uint64_t *h_off = alloc_offsets(c, (c->n_ranks << route_log2_regions(c)) + 1);
-                if (!h_off) return fail(c, SKM_ERR_OOM, "pinned allocation failed");
-                rc = build_list(c, ch, si, h_off, /*exact=*/!c->capped, /*must=*/true);
+            if (sg.owners.empty() && sg.codes) {  // skipped at ingest time (memory): build it now
+                rc = build(ch, si, false);
                 if (rc) return rc;
-                CU(cudaEventSynchronize(sg.ready));
             }
-            if (!sg.list) continue;
-            if (sg.cap && sg.h_offsets[sg.n_buckets] > 0) {
-                // a capped list that overflowed: what was shipped is void; rebuild exactly and ship that
-                if (sg.shipped)
-                    for (size_t r = sg.rec_first; r < sg.rec_first + c->n_ranks - 1 && r < c->mg_sent.size(); r++)
-                        c->mg_sent[r].dead = 1;
-                sg.shipped = false;
-                CU(cudaStreamSynchronize(c->dma_stream));  // the copies still read the old list
+            if (sg.owners.empty()) continue;
+            bool overflow = sg.cap && sg.h_offsets[sg.n_buckets] > 0;
+            for (auto &ol : sg.owners) overflow = overflow || (ol.cap && ol.h_off[kFineRegions] > 0);
+            if (overflow) {
+                // a capped layout overflowed (heavily repeated k-mers, or a lopsided owner): what was shipped is
+                // void; rebuild the batch with exact layouts from the packed form and ship that
+                for (auto &ol : sg.owners)
+                    if (ol.shipped && ol.rec < c->mg_sent.size()) c->mg_sent[ol.rec].dead = 1;
+                CU(cudaStreamSynchronize(c->dma_stream));  // the copies still read the old lists
                 rc = drop_capped_list(c, ch, sg, c->part_stream);
                 if (rc) return rc;
+                sg.shipped = false;
                 c->n_capped_fallbacks++;
-                uint64_t *h_off = alloc_offsets(c, sg.n_buckets + 1);
-                if (!h_off) return fail(c, SKM_ERR_OOM, "pinned allocation failed");
-                rc = build_list(c, ch, si, h_off, /*exact=*/true, /*must=*/true);
+                rc = build(ch, si, true);
                 if (rc) return rc;
-                CU(cudaEventSynchronize(sg.ready));
             }
-            if (!sg.shipped) {
-                rc = ship_segment(c, ch, si);
-                if (rc) return rc;
-                if (!sg.shipped) return fail(c, SKM_ERR_STATE, "receive arenas are not wired (skm_mg_open_peer / skm_mg_set_peer for every peer)");
+            rc = ship_segment(c, ch, si, /*sizes_on_host=*/true);
+            if (rc) return rc;
+            for (uint32_t o = 0; o < c->n_ranks; o++) {
+                OwnerList &ol = sg.owners[o];
+                if (o == c->p.rank) continue;
+                if (!ol.shipped) return fail(c, SKM_ERR_STATE, "receive arenas are not wired (skm_mg_open_peer / skm_mg_set_peer for every peer)");
+                uint64_t nk = 0;   // k-mers for this destination, now that the totals are on the host
+                if (ol.cap) for (uint32_t b = 0; b < kFineRegions; b++) nk += std::min<uint64_t>(ol.h_off[b], ol.cap);
+                else nk = ol.h_off[kFineRegions];
+                c->mg_sent[ol.rec].n_kmers = nk;
             }
-            // k-mers per destination, now that the totals are on the host
-            const uint32_t R = 1u << route_log2_regions(c);
-            for (uint32_t i = 0; i + 1 < c->n_ranks; i++) {
-                MgRecord &rec = c->mg_sent[sg.rec_first + i];
-                uint64_t nk = 0;
-                for (uint32_t b = rec.dst * R; b < (rec.dst + 1) * R; b++)
-                    nk += sg.cap ? std::min<uint64_t>(sg.h_offsets[b], sg.cap) : sg.h_offsets[b + 1] - sg.h_offsets[b];
-                rec.n_kmers = nk;
-            }
-            if (sg.codes) {  // the packed form was kept for the overflow fallback only
+            if (sg.codes) {  // the packed form was kept for the overflow retry only
                 CU(cudaFreeAsync(sg.codes, c->part_stream));
                 CU(cudaFreeAsync(sg.breaks, c->part_stream));
                 sg.codes = nullptr;
@@ -2461,6 +2616,7 @@ int32_t mg_prepare_local(skm_ctx *c) {
             }
         }
     }
+    DBG_SYNC("mg_prepare_local (bucketing / shipping)");
     CU(cudaStreamSynchronize(c->part_stream));
     CU(cudaStreamSynchronize(c->sort_stream));
     CU(cudaStreamSynchronize(c->dma_stream));  // every slice of mine has landed
@@ -2519,15 +2675,17 @@ int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm, bool final) {
     // ---- phase 2: the lists this rank counts, in chunk order: its own + the slices in its arena ----
     struct Item { SegDesc d; uint32_t chunk; uint64_t n_kmers; };
     std::vector<Item> items;
-    const uint32_t g1 = route_log2_regions(c), R = 1u << g1;
+    const uint32_t g1 = list_log2_regions(c);
     uint64_t kmers_mine = 0;
     for (uint32_t ch = 0; ch < c->n_chunks; ch++)
         for (auto &sg : c->chunks[ch].segs) {
-            if (!sg.list || !sg.tiled) continue;
+            if (sg.owners.empty()) continue;
+            const OwnerList &ol = sg.owners[me];
             uint64_t nk = 0;
-            for (uint32_t b = me * R; b < (me + 1) * R; b++)
-                nk += sg.cap ? std::min<uint64_t>(sg.h_offsets[b], sg.cap) : sg.h_offsets[b + 1] - sg.h_offsets[b];
-            items.push_back(Item{local_desc(c, sg, 0), ch, nk});
+            if (ol.cap) for (uint32_t b = 0; b < kFineRegions; b++) nk += std::min<uint64_t>(ol.h_off[b], ol.cap);
+            else nk = ol.h_off[kFineRegions];
+            const ListMeta m = list_meta_at(ol.meta, kFineRegions);
+            items.push_back(Item{SegDesc{ol.list, ol.tile_off, m.tile_begin, m.cell_begin, 0u, 0u, 0u, 0u}, ch, nk});
             kmers_mine += nk;
         }
     for (uint32_t src = 0; src < N; src++)
@@ -2542,7 +2700,7 @@ int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm, bool final) {
             d.tile_begin = (const uint32_t *)(base + rec.off_tile_begin);
             d.cell_begin = (const unsigned long long *)(base + rec.off_cell_begin);
             d.bucket0 = 0;
-            d.rel = 1;
+            d.rel = 0;   // a whole owner list: its metadata is in the receiver's numbering already
             items.push_back(Item{d, rec.chunk, rec.n_kmers});
             kmers_mine += rec.n_kmers;
         }

@@ -1288,6 +1288,116 @@ tile_sort_kernel(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb,
     for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) cells[i] = stage[i];
 }
 
+// Multi-GPU senders: pass A buckets a batch by (owner, coarse region) — at most 1024 buckets in
+// all, so only 1024 / n_ranks regions per owner — and a table partition of an owner would find its
+// k-mers scattered over n_ranks times more, n_ranks times shorter runs than on one GPU.  This
+// kernel re-buckets ONE owner's slice of such a list into that owner's kFineRegions table
+// regions (tile by tile: a tile of a coarse bucket only feeds kFineRegions / coarse regions
+// fine buckets, so its k-mers leave in long runs).  The result is a list with exactly the
+// geometry a single GPU builds for itself; it is tile-sorted and shipped as a whole.
+//   MODE 0: capped output (bucket f owns cells [f * cap, (f + 1) * cap); what does not fit is counted in
+//           cursors[kFineRegions] and dropped: the host rebuilds the batch exactly)
+//   MODE 1: count only (cursors[f] += k-mers of fine bucket f)
+//   MODE 2: exact output (cursors[] start at the bucket offsets)
+static constexpr uint32_t kFineLog2 = 10;
+static constexpr uint32_t kFineRegions = 1u << kFineLog2;
+
+template <int MODE>
+__global__ void __launch_bounds__(kSortThreads, 2)
+tile_rebucket_kernel(const unsigned long long *__restrict__ in_list, ListMeta m, uint32_t nb_in, uint32_t b_lo,
+                     uint32_t b_hi, uint32_t n_ranks, unsigned long long *__restrict__ cursors,
+                     unsigned long long *__restrict__ out, unsigned long long cap) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long *stage = reinterpret_cast<unsigned long long *>(s_raw);     // kTile
+    unsigned long long *s_g = stage + kTile;                                        // kFineRegions: first cell of this tile's run
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(s_g + kFineRegions);               // kFineRegions: counts, then stage starts
+    uint32_t *room = cnt + kFineRegions;                                            // kFineRegions (capped)
+    __shared__ uint32_t s_warp[kSortThreads / 32];
+    // the tiles of the owner's coarse buckets [b_lo, b_hi): grid = tile_begin[b_hi] - tile_begin[b_lo] at most
+    const uint32_t t = m.tile_begin[b_lo] + blockIdx.x;
+    if (t >= m.tile_begin[b_hi]) return;
+    uint32_t lo = b_lo, hi = b_hi;  // last bucket whose tile_begin <= t
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (m.tile_begin[mid] <= t) lo = mid; else hi = mid;
+    }
+    (void)nb_in;
+    const uint32_t j = t - m.tile_begin[lo];
+    const unsigned long long bn = m.bucket_n[lo];
+    const unsigned long long first = (unsigned long long)j * kTile;
+    const uint32_t n = first >= bn ? 0u : (uint32_t)(bn - first < kTile ? bn - first : kTile);
+    if (n == 0) return;
+    const unsigned long long *cells = in_list + m.cell_begin[lo] + first;
+    for (uint32_t f = threadIdx.x; f < kFineRegions; f += kSortThreads) cnt[f] = 0;
+    __syncthreads();
+    unsigned long long km[kSortPer];
+    uint32_t fr[kSortPer];
+#pragma unroll
+    for (uint32_t r = 0; r < kSortPer; r++) {
+        const uint32_t i = threadIdx.x + r * kSortThreads;
+        km[r] = i < n ? cells[i] : 0ull;
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < kSortPer; r++) {
+        const uint32_t i = threadIdx.x + r * kSortThreads;
+        if (i < n) {
+            const uint64_t lh = skm_local_hash(skm_hash_kmer(km[r]), n_ranks);
+            const uint32_t f = (uint32_t)(lh >> (64u - kFineLog2));
+            fr[r] = f | (atomicAdd(&cnt[f], 1u) << kMaxSubLog2);
+        }
+    }
+    __syncthreads();
+    const uint32_t a = threadIdx.x * 2;   // kFineRegions = 2 * kSortThreads
+    const uint32_t c0 = cnt[a], c1 = cnt[a + 1];
+    if (MODE == 1) {
+        if (c0) atomicAdd(&cursors[a], (unsigned long long)c0);
+        if (c1) atomicAdd(&cursors[a + 1], (unsigned long long)c1);
+        return;
+    }
+    // reserve this tile's run in every fine bucket it feeds, and lay the k-mers out in bucket order in the stage
+    const unsigned long long g0 = c0 ? atomicAdd(&cursors[a], (unsigned long long)c0) : 0ull;
+    const unsigned long long g1 = c1 ? atomicAdd(&cursors[a + 1], (unsigned long long)c1) : 0ull;
+    uint32_t incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= (uint32_t)o) incl += v;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) base += s_warp[w];
+    const uint32_t start0 = base + incl - c0 - c1;
+    cnt[a] = start0;
+    cnt[a + 1] = start0 + c0;
+    if (MODE == 0) {
+        const uint32_t r0 = g0 >= cap ? 0u : (uint32_t)(c0 < cap - g0 ? c0 : cap - g0);
+        const uint32_t r1 = g1 >= cap ? 0u : (uint32_t)(c1 < cap - g1 ? c1 : cap - g1);
+        room[a] = r0;
+        room[a + 1] = r1;
+        if (c0 + c1 > r0 + r1) atomicAdd(&cursors[kFineRegions], (unsigned long long)(c0 + c1 - r0 - r1));
+        s_g[a] = (unsigned long long)a * cap + (g0 < cap ? g0 : cap);
+        s_g[a + 1] = (unsigned long long)(a + 1) * cap + (g1 < cap ? g1 : cap);
+    } else {
+        s_g[a] = g0;
+        s_g[a + 1] = g1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t r = 0; r < kSortPer; r++) {
+        const uint32_t i = threadIdx.x + r * kSortThreads;
+        if (i < n) stage[cnt[fr[r] & ((1u << kMaxSubLog2) - 1)] + (fr[r] >> kMaxSubLog2)] = km[r];
+    }
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < n; p += kSortThreads) {
+        const unsigned long long kmer = stage[p];
+        const uint32_t f = (uint32_t)(skm_local_hash(skm_hash_kmer(kmer), n_ranks) >> (64u - kFineLog2));
+        const uint32_t rel = p - cnt[f];
+        if (MODE == 2 || rel < room[f]) out[s_g[f] + rel] = kmer;   // (capped: the rest was counted as overflow)
+    }
+}
+__host__ __device__ inline size_t tile_rebucket_smem_bytes() { return (size_t)kTile * 8 + (size_t)kFineRegions * 16 + 16; }
+
 __host__ __device__ inline size_t tile_sort_smem_bytes(uint32_t g2) { return (size_t)kTile * 8 + ((size_t)1 << g2) * 4 + 16; }
 
 // One bucketed, tile-sorted list as the insert kernel sees it.  `list` and `tile_off` are biased by
