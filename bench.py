@@ -340,8 +340,20 @@ def run_ours(args):
         arena = int(per_round * 8 * 1.3) + (256 << 20) + (10 << 20) * len(d_bufs) * world
         sharded = ShardedCounter(eng, dev, cpu_group=cpu_group, arena_bytes=arena)
 
+    dbg = os.environ.get("SKM_BENCH_DEBUG") and rank == 0
+
     def step(host_buffers: bool):
+        t0 = time.perf_counter()
         eng.reset()
+        t1 = time.perf_counter()
+        r = _step(host_buffers)
+        if dbg:
+            print(f"[bench] reset {1e3 * (t1 - t0):.1f} ms, ingest+finalize {1e3 * (time.perf_counter() - t1):.1f} ms "
+                  f"(host={host_buffers})", file=sys.stderr)
+        return r
+
+    def _step(host_buffers: bool):
+        t_in = time.perf_counter()
         for i in range(len(d_bufs)):
             c = i if CHUNKS > 0 else 0
             if d_bufs[i].numel() == 0:
@@ -352,6 +364,8 @@ def run_ours(args):
                 eng.ingest_device(c, d_bufs[i].data_ptr(), d_bufs[i].numel())
             if sharded is not None and BUFS_PER_ROUND and (i + 1) % BUFS_PER_ROUND == 0 and i + 1 < len(d_bufs):
                 sharded.flush()    # collective: count this round, free its lists and the arenas
+        if dbg:
+            print(f"[bench]   ingest calls {1e3 * (time.perf_counter() - t_in):.1f} ms", file=sys.stderr)
         if world == 1:
             eng.finalize()
             return eng.histogram(CHUNKS - 1) if CHUNKS else None

@@ -9,6 +9,7 @@
 //
 // There is no CPU fallback anywhere in this file.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -70,6 +71,7 @@ struct Segment {
     uint16_t *tile_off = nullptr;         // max_tiles * (2^g2 + 1)
     uint32_t max_tiles = 0;
     bool tiled = false;
+    cudaEvent_t copied = nullptr;   // host-fed batch: fires when its host-to-device copy has finished
     bool shipped = false;       // multi-GPU: the other owners' slices are on their way (or there)
     size_t rec_first = 0;       // first of this list's n_ranks - 1 records in skm_ctx::mg_sent
 };
@@ -202,6 +204,18 @@ struct skm_ctx {
 
     std::vector<cudaStream_t> read_streams;  // idle private streams of the read-side calls
 
+    // Cache of the big device buffers (k-mer lists, tile offsets).  cudaMallocAsync blocked the host for
+    // milliseconds per list once peers were mapped and lists were freed on another stream than they were
+    // allocated on (new physical memory every batch: 50-400 ms of host time per step at N=2, profiles/
+    // experiments_r02.md); a freed buffer is kept here with an event that marks its last use instead.
+    struct CachedBuf {
+        void *p;
+        size_t bytes;
+        cudaEvent_t done;
+    };
+    std::vector<CachedBuf> buf_cache;
+    std::vector<std::pair<void *, size_t>> buf_live;
+
     // tiled insert (tile_insert_kernel)
     uint32_t g2 = 7;                         // sub-bucket bits of the lists built by this ctx
     bool table_fresh = true;                 // logically empty: no key was ever inserted since create / reset
@@ -216,6 +230,7 @@ struct skm_ctx {
     void *h_segs = nullptr, *d_segs = nullptr;   // SegDesc[] + chunk_first_seg[] of one launch (pinned / device)
     size_t segs_bytes = 0;
     uint32_t n_tiled_launches = 0, n_tiled_retries = 0;
+    double host_ms[6] = {0, 0, 0, 0, 0, 0};  // SKM_DEBUG: host time in build / refine-alloc / refine-launch / ship / pack / other
     bool recount_valid = false;              // d_recount / last_tot describe the whole table as it is now
 
     std::string err;
@@ -254,6 +269,13 @@ int32_t fail(skm_ctx *c, int32_t code, const char *fmt, ...) {
         }                                                                                                \
     } while (0)
 
+struct HostTimer {
+    double *acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit HostTimer(double *a) : acc(a) {}
+    ~HostTimer() { *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {
@@ -276,6 +298,67 @@ cudaEvent_t get_event(skm_ctx *c) {
     cudaEvent_t e;
     cudaEventCreate(&e);
     return e;
+}
+
+size_t buf_round(size_t bytes) {
+    size_t gran = 1 << 20;
+    while (gran * 16 < bytes) gran <<= 1;   // <= 12.5 % above the request
+    return (bytes + gran - 1) / gran * gran;
+}
+
+// A buffer of >= `bytes` bytes, usable on stream `st` (stream-ordered: a cached buffer's last use is waited for).
+cudaError_t buf_alloc(skm_ctx *c, void **out, size_t bytes, cudaStream_t st) {
+    bytes = buf_round(std::max<size_t>(bytes, 16));
+    size_t best = SIZE_MAX;
+    for (size_t i = 0; i < c->buf_cache.size(); i++)
+        if (c->buf_cache[i].bytes >= bytes && c->buf_cache[i].bytes <= bytes + bytes / 4 &&
+            (best == SIZE_MAX || c->buf_cache[i].bytes < c->buf_cache[best].bytes))
+            best = i;
+    if (best != SIZE_MAX) {
+        skm_ctx::CachedBuf cb = c->buf_cache[best];
+        c->buf_cache.erase(c->buf_cache.begin() + best);
+        cudaStreamWaitEvent(st, cb.done, 0);
+        c->event_pool.push_back(cb.done);
+        c->buf_live.emplace_back(cb.p, cb.bytes);
+        *out = cb.p;
+        return cudaSuccess;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {   // give the cached buffers back and retry
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        for (auto &cb : c->buf_cache) {
+            cudaFree(cb.p);
+            c->event_pool.push_back(cb.done);
+        }
+        c->buf_cache.clear();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) return e;
+    c->buf_live.emplace_back(p, bytes);
+    *out = p;
+    return cudaSuccess;
+}
+
+// Stream-ordered free: everything that uses `p` has been queued on `st` (or on streams `st` waits for).
+void buf_free(skm_ctx *c, void *p, cudaStream_t st) {
+    if (!p) return;
+    size_t bytes = 0;
+    for (size_t i = 0; i < c->buf_live.size(); i++)
+        if (c->buf_live[i].first == p) {
+            bytes = c->buf_live[i].second;
+            c->buf_live[i] = c->buf_live.back();
+            c->buf_live.pop_back();
+            break;
+        }
+    if (!bytes) {   // not from the cache (should not happen): hand it to the stream-ordered pool
+        cudaFreeAsync(p, st);
+        return;
+    }
+    cudaEvent_t e = get_event(c);
+    cudaEventRecord(e, st);
+    c->buf_cache.push_back(skm_ctx::CachedBuf{p, bytes, e});
 }
 
 struct Span {
@@ -790,22 +873,22 @@ bool want_partitioned(const skm_ctx *c, uint64_t n_bytes) {
 
 void release_list(skm_ctx *c, Segment &sg, cudaStream_t st) {
     if (sg.list) {
-        cudaFreeAsync(sg.list, st);
+        buf_free(c, sg.list, st);
         c->list_bytes -= std::min<size_t>(c->list_bytes, sg.list_cells * sizeof(uint64_t));
     }
-    if (sg.meta) cudaFreeAsync(sg.meta, st);
+    if (sg.meta) buf_free(c, sg.meta, st);
     if (sg.tile_off) {
-        cudaFreeAsync(sg.tile_off, st);
+        buf_free(c, sg.tile_off, st);
         c->list_bytes -= std::min<size_t>(c->list_bytes, (size_t)sg.max_tiles * ((1u << c->g2) + 1) * sizeof(uint16_t));
     }
     if (sg.d_counts) cudaFreeAsync(sg.d_counts, st);
     for (auto &ol : sg.owners) {
         if (ol.list) {
-            cudaFreeAsync(ol.list, st);
+            buf_free(c, ol.list, st);
             c->list_bytes -= std::min<size_t>(c->list_bytes, ol.cells * sizeof(uint64_t));
         }
-        if (ol.meta) cudaFreeAsync(ol.meta, st);
-        if (ol.tile_off) cudaFreeAsync(ol.tile_off, st);
+        buf_free(c, ol.meta, st);
+        buf_free(c, ol.tile_off, st);
     }
     sg.owners.clear();
     sg.list = nullptr;
@@ -853,14 +936,18 @@ int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off
     CU(cudaStreamWaitEvent(c->work, sg.ready, 0));
     unsigned long long *list = nullptr, *meta = nullptr;
     uint16_t *tile_off = nullptr;
-    if (cudaMallocAsync((void **)&list, cells * sizeof(uint64_t), c->work) != cudaSuccess ||
-        cudaMallocAsync((void **)&tile_off, off_bytes, c->work) != cudaSuccess ||
-        cudaMallocAsync((void **)&meta, list_meta_words(nb) * sizeof(uint64_t), c->work) != cudaSuccess) {
+    HostTimer t_malloc(&c->host_ms[4]);
+    if (buf_alloc(c, (void **)&list, cells * sizeof(uint64_t), c->work) != cudaSuccess ||
+        buf_alloc(c, (void **)&tile_off, off_bytes, c->work) != cudaSuccess ||
+        buf_alloc(c, (void **)&meta, list_meta_words(nb) * sizeof(uint64_t), c->work) != cudaSuccess) {
         cudaGetLastError();
-        if (list) cudaFreeAsync(list, c->work);
-        if (tile_off) cudaFreeAsync(tile_off, c->work);
+        if (list) buf_free(c, list, c->work);
+        if (tile_off) buf_free(c, tile_off, c->work);
         return must ? fail(c, SKM_ERR_OOM, "device allocation failed (k-mer list of %llu cells)", (unsigned long long)cells) : SKM_OK;
     }
+    t_malloc.~HostTimer();
+    t_malloc.acc = &c->host_ms[5];   // (the rest of the function: launches)
+    t_malloc.t0 = std::chrono::steady_clock::now();
     sg.list = list;
     sg.meta = meta;
     sg.tile_off = tile_off;
@@ -1142,10 +1229,18 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force
     // batches whose bucket counts could overflow 32 bits, take the exact two-pass layout.
     const bool exact = force || !c->capped || sg.n_bytes >= (3ull << 30) || sg.n_bytes / nb < 4096;
     // (a table sized from a capacity_hint is not expected to grow: keep room for it alone)
-    int32_t rc = build_list(c, chunk, seg_index, h_off, exact, force, c->p.capacity_hint ? 1 : 3, /*sort=*/c->n_ranks == 1);
+    int32_t rc;
+    {
+        HostTimer t(&c->host_ms[0]);
+        rc = build_list(c, chunk, seg_index, h_off, exact, force, c->p.capacity_hint ? 1 : 3, /*sort=*/c->n_ranks == 1);
+    }
     if (rc || c->n_ranks == 1 || !sg.list) return rc;
-    rc = refine_owner_lists(c, chunk, seg_index, exact);
+    {
+        HostTimer t(&c->host_ms[2]);
+        rc = refine_owner_lists(c, chunk, seg_index, exact);
+    }
     if (rc) return rc;
+    HostTimer t(&c->host_ms[3]);
     return ship_segment(c, chunk, seg_index, /*sizes_on_host=*/false);  // the exchange starts at ingest time (capped lists)
 }
 
@@ -1178,11 +1273,14 @@ int32_t refine_owner_lists(skm_ctx *c, uint32_t chunk, size_t seg_index, bool ex
         }
         ol.cap = lay.cap;
         const size_t off_bytes = (size_t)ol.max_tiles * (F + 1) * sizeof(uint16_t);
-        if (cudaMallocAsync((void **)&ol.list, ol.cells * sizeof(uint64_t), c->work) != cudaSuccess ||
-            cudaMallocAsync((void **)&ol.tile_off, off_bytes, c->work) != cudaSuccess ||
-            cudaMallocAsync((void **)&ol.meta, list_meta_words(kFineRegions) * sizeof(uint64_t), c->work) != cudaSuccess) {
+        {
+        HostTimer t_alloc(&c->host_ms[1]);
+        if (buf_alloc(c, (void **)&ol.list, ol.cells * sizeof(uint64_t), c->work) != cudaSuccess ||
+            buf_alloc(c, (void **)&ol.tile_off, off_bytes, c->work) != cudaSuccess ||
+            buf_alloc(c, (void **)&ol.meta, list_meta_words(kFineRegions) * sizeof(uint64_t), c->work) != cudaSuccess) {
             cudaGetLastError();
             return fail(c, SKM_ERR_OOM, "device allocation failed (owner list of %zu cells)", ol.cells);
+        }
         }
         c->list_bytes += ol.cells * sizeof(uint64_t);
         const ListMeta m_o = list_meta_at(ol.meta, kFineRegions);
@@ -1228,9 +1326,9 @@ int32_t refine_owner_lists(skm_ctx *c, uint32_t chunk, size_t seg_index, bool ex
         DBG_SYNC("tile_sort of an owner list");
     }
     // the coarse list has been consumed (on `work`); the packed form stays for the overflow retry
-    CU(cudaFreeAsync(sg.list, c->work));
-    CU(cudaFreeAsync(sg.meta, c->work));
-    if (sg.tile_off) CU(cudaFreeAsync(sg.tile_off, c->work));
+    buf_free(c, sg.list, c->work);
+    buf_free(c, sg.meta, c->work);
+    buf_free(c, sg.tile_off, c->work);
     c->list_bytes -= std::min<size_t>(c->list_bytes, sg.list_cells * sizeof(uint64_t) + 16);
     sg.list = nullptr;
     sg.meta = nullptr;
@@ -1588,6 +1686,10 @@ void skm_destroy(skm_ctx *c) {
                     cudaFree(ol.tile_off);
                 }
             }
+        for (auto &cb : c->buf_cache) {
+            cudaFree(cb.p);
+            cudaEventDestroy(cb.done);
+        }
         cudaFree(c->d_delta);
         cudaFree(c->d_recount);
         cudaFree(c->d_fail);
@@ -1727,7 +1829,13 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
     CU(cudaStreamWaitEvent(c->part_stream, c->raw_copied[b], 0));
     WorkStream ws(c, c->part_stream);
     c->raw_in_use[b] = true;
-    return stage_device(c, chunk, c->raw_buf[b], n_bytes, c->part_stream, c->raw_packed[b]);
+    cudaEvent_t copied = get_event(c);
+    CU(cudaEventRecord(copied, c->copy_stream));
+    const size_t n_before = c->chunks[chunk].segs.size();
+    rc = stage_device(c, chunk, c->raw_buf[b], n_bytes, c->part_stream, c->raw_packed[b]);
+    if (c->chunks[chunk].segs.size() > n_before) c->chunks[chunk].segs.back().copied = copied;
+    else c->event_pool.push_back(copied);
+    return rc;
 }
 
 int32_t skm_ingest_reads(skm_ctx *c, uint32_t chunk, const uint8_t *bases, const uint64_t *offsets,
@@ -1860,8 +1968,25 @@ static int32_t finalize_common(skm_ctx *c) {
     };
     const uint32_t pbits_now = c->log2cap - kPartLog2, g1_now = route_log2_regions(c);
     const uint64_t nbr_now = pbits_now >= g1_now ? 1ull : (1ull << (g1_now - pbits_now));
+    uint64_t positions_all = 0, group_positions = 0;
+    for (auto &cs : c->chunks) positions_all += cs.n_bytes;
+    const bool early_flush = !getenv("SKM_NO_EARLY_FLUSH");
     for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
         ChunkState &cs = c->chunks[ch];
+        // Host-fed input that is still on its way over PCIe: rather than idle until the last batch has arrived,
+        // count what is listed so far (one more pass over the table, hidden behind the copies).
+        if (early_flush && !group.empty() && group_positions >= std::max<uint64_t>(64ull << 20, positions_all / 4)) {
+            bool arriving = false;
+            for (auto &sg : cs.segs)
+                if (sg.copied && cudaEventQuery(sg.copied) == cudaErrorNotReady) arriving = true;
+            cudaGetLastError();
+            if (arriving) {
+                rc = flush_group(ch);
+                if (rc) return rc;
+                group_positions = 0;
+            }
+        }
+        group_positions += cs.n_bytes;
         for (auto &sg : cs.segs) {
             if (!sg.ready) continue;
             if (sg.list) CU(cudaEventSynchronize(sg.ready));      // host needs the bucket totals
@@ -1968,7 +2093,9 @@ static int32_t finalize_common(skm_ctx *c) {
     for (auto &cs : c->chunks)
         for (auto &sg : cs.segs) {
             if (sg.ready) c->event_pool.push_back(sg.ready);
+            if (sg.copied) c->event_pool.push_back(sg.copied);
             sg.ready = nullptr;
+            sg.copied = nullptr;
         }
     // Totals for the conservation checks and an independent recount of the final histogram: the
     // tiled insert histograms every partition as it writes it back; otherwise one scan of the table.
@@ -2045,6 +2172,7 @@ int32_t skm_reset(skm_ctx *c) {
     for (auto &cs : c->chunks) {
         for (auto &sg : cs.segs) {
             if (sg.ready) c->event_pool.push_back(sg.ready);
+            if (sg.copied) c->event_pool.push_back(sg.copied);
             if (sg.codes) CU(cudaFreeAsync(sg.codes, c->stream));
             if (sg.breaks) CU(cudaFreeAsync(sg.breaks, c->stream));
             release_list(c, sg, c->stream);
@@ -2922,6 +3050,11 @@ int32_t skm_mg_bytes_sent(skm_ctx *c, uint64_t *out) {
 
 static int32_t mg_finalize_or_flush(skm_ctx *c, const skm_comm *comm, bool final) {
     if (!c || !comm || !comm->allgather) return SKM_ERR_INVALID_ARG;
+    if (getenv("SKM_DEBUG")) {
+        std::fprintf(stderr, "[skm] rank %u host ms since last report: build %.1f (mallocs %.1f, launches %.1f) refine %.1f (mallocs %.1f) ship %.1f\n",
+                     c->p.rank, c->host_ms[0], c->host_ms[4], c->host_ms[5], c->host_ms[2], c->host_ms[1], c->host_ms[3]);
+        for (auto &x : c->host_ms) x = 0;
+    }
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     if (c->finalized) return fail(c, SKM_ERR_STATE, final ? "finalize called twice" : "flush after finalize");

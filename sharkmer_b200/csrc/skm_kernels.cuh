@@ -521,46 +521,6 @@ struct RunDesc {
     unsigned long long tile_begin;   // index of this run's first warp tile
 };
 
-// Descriptor-driven copy: every warp pulls the next 2048-word tile of a sequence of (src, dst, n)
-// pieces.  Used to push already-bucketed runs into the peers' receive arenas (peer stores over
-// NVLink) and to merge the runs of several segments region-major on the way.
-struct CopyDesc {
-    const unsigned long long *src;
-    unsigned long long *dst;
-    unsigned long long n;
-    unsigned long long tile_begin;
-};
-static constexpr uint32_t kCopyTile = 2048;
-
-__global__ void __launch_bounds__(256)
-copy_runs_kernel(const CopyDesc *__restrict__ descs, uint32_t n_desc, unsigned long long n_tiles,
-                 unsigned long long *__restrict__ tile_counter) {
-    const uint32_t lane = threadIdx.x & 31;
-    for (;;) {
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(tile_counter, 1ull);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n_tiles) break;
-        uint32_t lo = 0, hi = n_desc;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (descs[mid].tile_begin <= t) lo = mid; else hi = mid;
-        }
-        const CopyDesc d = descs[lo];
-        const uint64_t base = (t - d.tile_begin) * kCopyTile;
-#pragma unroll 4
-        for (uint32_t j = lane; j < kCopyTile; j += 32) {
-            const uint64_t i = base + j;
-            if (i < d.n) d.dst[i] = d.src[i];
-        }
-    }
-}
-
-__global__ void add_counts_kernel(unsigned long long *__restrict__ dst, const unsigned long long *__restrict__ src,
-                                  uint32_t n) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] += src[i];
-}
-
 // Zero-fill by kernel.  cudaMemsetAsync may be serviced by a copy engine, where it queues behind
 // host-to-device batches already submitted (measured: a routing pass submitted after ten 151 MB
 // copies did not start until the last copy had finished).
@@ -570,13 +530,9 @@ __global__ void zero_kernel(unsigned long long *__restrict__ p, uint64_t n_words
         p[i] = 0ull;
 }
 
-// Run descriptors reach the device through a kernel that reads them from pinned host memory:
-// a cudaMemcpy would queue on the host-to-device copy engine BEHIND the read batches still in
-// flight, and the first insert could not start until every batch had arrived.
-__global__ void copy_descs_kernel(const RunDesc *__restrict__ src, RunDesc *__restrict__ dst, uint32_t n) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
-}
-
+// Small host <-> device transfers go through kernels that read / write pinned host memory: a
+// cudaMemcpy would queue on a copy engine BEHIND the read batches still in flight (measured in
+// round 1: the first insert could not start until every batch had arrived).
 // Same reason, other direction: small results the host waits for (bucket totals) are stored to
 // pinned host memory by a kernel instead of a device-to-host copy.
 __global__ void copy_words_kernel(const unsigned long long *__restrict__ src, unsigned long long *__restrict__ dst,
@@ -1312,6 +1268,7 @@ tile_rebucket_kernel(const unsigned long long *__restrict__ in_list, ListMeta m,
     unsigned long long *s_g = stage + kTile;                                        // kFineRegions: first cell of this tile's run
     uint32_t *cnt = reinterpret_cast<uint32_t *>(s_g + kFineRegions);               // kFineRegions: counts, then stage starts
     uint32_t *room = cnt + kFineRegions;                                            // kFineRegions (capped)
+    uint16_t *stage_f = reinterpret_cast<uint16_t *>(room + kFineRegions);          // kTile: fine bucket of every staged k-mer
     __shared__ uint32_t s_warp[kSortThreads / 32];
     // the tiles of the owner's coarse buckets [b_lo, b_hi): grid = tile_begin[b_hi] - tile_begin[b_lo] at most
     const uint32_t t = m.tile_begin[b_lo] + blockIdx.x;
@@ -1386,17 +1343,22 @@ tile_rebucket_kernel(const unsigned long long *__restrict__ in_list, ListMeta m,
 #pragma unroll
     for (uint32_t r = 0; r < kSortPer; r++) {
         const uint32_t i = threadIdx.x + r * kSortThreads;
-        if (i < n) stage[cnt[fr[r] & ((1u << kMaxSubLog2) - 1)] + (fr[r] >> kMaxSubLog2)] = km[r];
+        if (i < n) {
+            const uint32_t f = fr[r] & ((1u << kMaxSubLog2) - 1);
+            const uint32_t at = cnt[f] + (fr[r] >> kMaxSubLog2);
+            stage[at] = km[r];
+            stage_f[at] = (uint16_t)f;
+        }
     }
     __syncthreads();
     for (uint32_t p = threadIdx.x; p < n; p += kSortThreads) {
         const unsigned long long kmer = stage[p];
-        const uint32_t f = (uint32_t)(skm_local_hash(skm_hash_kmer(kmer), n_ranks) >> (64u - kFineLog2));
+        const uint32_t f = stage_f[p];
         const uint32_t rel = p - cnt[f];
         if (MODE == 2 || rel < room[f]) out[s_g[f] + rel] = kmer;   // (capped: the rest was counted as overflow)
     }
 }
-__host__ __device__ inline size_t tile_rebucket_smem_bytes() { return (size_t)kTile * 8 + (size_t)kFineRegions * 16 + 16; }
+__host__ __device__ inline size_t tile_rebucket_smem_bytes() { return (size_t)kTile * 10 + (size_t)kFineRegions * 16 + 16; }
 
 __host__ __device__ inline size_t tile_sort_smem_bytes(uint32_t g2) { return (size_t)kTile * 8 + ((size_t)1 << g2) * 4 + 16; }
 
