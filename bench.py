@@ -107,7 +107,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("SKM_SAMPLER_MS", "100"),
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -438,7 +438,7 @@ def run_ours(args):
         del s_bufs
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("SKM_NO_SAMPLER"):
         sampler.start()
     def global_state():
         """Totals and the table digest of the last run, summed over the partitions."""
@@ -590,6 +590,33 @@ def run_ours(args):
                           "ms_per_step": ms_e2e, "ms_per_step_wall": ms_e2e_wall,
                           "stage_ms": {"h2d": st2.h2d, "pack": st2.pack, "insert": st2.insert, "histogram": st2.histogram},
                           "api": "skm_ingest_batch(pinned host buffers) x10 -> skm_finalize -> skm_histogram"}
+        if world == 1 and not args.no_services:
+            # the table services the consumers call: one oligo scan = one streaming pass over the table
+            # (16 B per slot); batched canonical lookups = random 16 B probes, through the C ABI with host buffers
+            rng = np.random.default_rng(1)
+            oligos = rng.integers(0, 1 << 30, size=64, dtype=np.uint64)
+            eng.scan_oligos(oligos, 15, 2)
+            s0 = eng.stage_times().scan
+            for _ in range(3):
+                eng.scan_oligos(oligos, 15, 2)
+            scan_ms = (eng.stage_times().scan - s0) / 3
+            sample = d_bufs[0][:30_000 * line].cpu().numpy()
+            q = eng.extract_kmers(sample)
+            q = q[q != np.uint64(0xFFFFFFFFFFFFFFFF)]
+            eng.lookup(q[:1000], 0, 0)
+            t0 = time.perf_counter()
+            cnt, found = eng.lookup(q, 0, 0)
+            lk_s = time.perf_counter() - t0
+            out["services"] = {
+                "scan_oligos": {"ms_per_scan": scan_ms, "GB_per_s": 16.0 * slots / (scan_ms * 1e-3) / 1e9,
+                                "frac_of_hbm_peak": 16.0 * slots / (scan_ms * 1e-3) / 1e9 / peak,
+                                "what": "find_oligos_in_kmers (src/pcr/primers.rs:163-226) as one table pass, 64 oligos of 15 bases, "
+                                        "kernel time (CUDA events)"},
+                "lookup_batch": {"queries": int(q.size), "found": int(found.sum()), "lookups_per_s": q.size / lk_s,
+                                 "what": "get_canonical_count (src/kmer/counting.rs:205-209) for every k-mer of 30 k reads in ONE call, "
+                                         "host buffers in and out, wall time of the call"}}
+            if "gups" in out:
+                out["services"]["lookup_batch"]["frac_of_random_load_rate"] = q.size / lk_s / out["gups"]["load_only"]
         if cpu:
             out["cpu_baseline"] = cpu
         emit(out)
@@ -644,6 +671,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gups", action="store_true", help="skip the random-access roofline probe")
+    ap.add_argument("--no-services", action="store_true", help="skip timing the table services (oligo scan, batched lookups)")
     ap.add_argument("--gups", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--exchange", default="dma", help="(ignored: the exchange is the copy-engine path; kept for old command lines)")
     ap.add_argument("--chunks", type=int, default=None, help="EXPERIMENT ONLY: override the workload's chunk count")

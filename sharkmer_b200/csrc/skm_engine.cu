@@ -560,6 +560,13 @@ int32_t insert_segment_direct(skm_ctx *c, const Segment &sg, uint32_t chunk) {
         sg.codes, sg.breaks, u, u + tile_units, c->p.k, tref(c), &c->d_cc[chunk], c->d_gc,              \
         c->d_hist, c->p.histo_max)
             const bool h = c->track_histo;
+            static const bool coop = getenv("SKM_WARP_COOP") != nullptr;   // A/B: warp-cooperative probing
+            if (coop) {
+                if (h) extract_insert_coop_kernel<true><<<grid_for(tile_units, 256), 256, 0, c->stream>>>(
+                    sg.codes, sg.breaks, u, u + tile_units, c->p.k, tref(c), &c->d_cc[chunk], c->d_gc, c->d_hist, c->p.histo_max);
+                else extract_insert_coop_kernel<false><<<grid_for(tile_units, 256), 256, 0, c->stream>>>(
+                    sg.codes, sg.breaks, u, u + tile_units, c->p.k, tref(c), &c->d_cc[chunk], c->d_gc, c->d_hist, c->p.histo_max);
+            } else
             switch (c->pipe_depth) {
             case 1: if (h) SKM_LAUNCH_EI(1, true); else SKM_LAUNCH_EI(1, false); break;
             case 2: if (h) SKM_LAUNCH_EI(2, true); else SKM_LAUNCH_EI(2, false); break;
@@ -2467,7 +2474,7 @@ int32_t skm_scan_oligos(skm_ctx *c, const uint64_t *oligos, uint64_t n_oligos, u
         Span sp(c, ST_SCAN, c->stream);
         scan_oligos_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->table, c->capacity, k, d_sets.p, d_sets.p + n_oligos,
                                                                    (uint32_t)n_oligos, mask, rc_mask, min_count, d_keys.p,
-                                                                   d_counts.p, out_cap, d_cursor.p);
+                                                                   d_counts.p, out_cap, d_cursor.p, oligo_length);
         c->launches++;
         c->stage_launches[ST_SCAN]++;
     }

@@ -495,6 +495,101 @@ extract_insert_kernel(const uint64_t *__restrict__ codes, const uint32_t *__rest
     if (kHisto) histo_smem_flush(s_low, g_hist);
 }
 
+// Warp-cooperative probing (the variant BASELINE.json's north star names), kept as an A/B switch for the
+// direct kernel (SKM_WARP_COOP=1): 8 lanes inspect the 8 slots from the home slot on (one 128-byte line when
+// the home slot is line-aligned), ballot for a match or an empty slot, and the first in probe order wins.
+// A warp counts 4 k-mers at a time instead of 32.  Measured slower than one thread per k-mer at loads
+// 0.5 and 0.7 (profiles/experiments_r02.md): a probe sequence is 1.3-2.2 slots long, so seven of the eight
+// loads are wasted, and the table is bound by sector throughput, not by the latency of a probe chain.
+template <bool kHisto>
+__global__ void __launch_bounds__(256)
+extract_insert_coop_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
+                           uint64_t u_begin, uint64_t u_end, uint32_t k, TableRef table,
+                           ChunkCounters *__restrict__ cc, GlobalCounters *__restrict__ gc,
+                           unsigned long long *__restrict__ g_hist, unsigned long long histo_max) {
+    __shared__ int s_low[kHisto ? kLowBins * 32 : 1];
+    if (kHisto) histo_smem_init(s_low);
+    const uint32_t lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
+    const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const UnitInput in = load_unit(codes, breaks, u, u_end);
+    HistoSink hs{s_low, g_hist, histo_max, lane};
+    Slot *slots = table.slots;
+    unsigned long long n_new = 0, n_win = 0;
+    bool part_full = false;
+    // the rolling state of extract_unit, advanced for every lane in lockstep
+    const uint64_t kmask = (1ull << (2 * k)) - 1;
+    const uint32_t top = 2 * (k - 1);
+    uint64_t fwd = in.prev;
+    uint64_t rev = rc64(in.prev) >> (64 - 2 * k);
+    uint32_t n_valid = in.prev_inv ? (uint32_t)(__ffs(in.prev_inv) - 1) : 32u;
+    const bool unit_has_bases = in.inv != 0xFFFFFFFFu;
+    for (int j = 0; j < 32; j++) {
+        const uint64_t b = (in.cur >> (62 - 2 * j)) & 3ull;
+        fwd = (fwd << 2) | b;
+        rev = (rev >> 2) | ((3ull - b) << top);
+        const bool brk = (in.inv >> (31 - j)) & 1u;
+        n_valid = brk ? 0u : n_valid + 1u;
+        const bool have = unit_has_bases && n_valid >= k;
+        const uint64_t f = fwd & kmask;
+        const unsigned long long mine = f < rev ? f : rev;
+        n_win += have;
+        const uint32_t have_mask = __ballot_sync(0xffffffffu, have);
+        // eight rounds: round r serves the k-mers of lanes 4r .. 4r+3, one per 8-lane group
+        for (uint32_t r = 0; r < 8; r++) {
+            const uint32_t src = 4 * r + grp;
+            if (!((have_mask >> (4 * r)) & 0xFu)) continue;   // (uniform: nobody in this round has a k-mer)
+            const unsigned long long kmer = __shfl_sync(0xffffffffu, mine, src);
+            bool active = (have_mask >> src) & 1u;
+            uint64_t s = table.home(kmer);
+            uint32_t probes = 0;
+            while (__any_sync(0xffffffffu, active)) {
+                uint64_t slot = s;
+                for (uint32_t q = 0; q < sub; q++) slot = TableRef::next(slot);
+                const unsigned long long key = active ? ld_cg_u64(&slots[slot].key) : 0ull;
+                const uint32_t m_match = (__ballot_sync(0xffffffffu, active && key == kmer) >> (8 * grp)) & 0xFFu;
+                const uint32_t m_empty = (__ballot_sync(0xffffffffu, active && key == SKM_EMPTY_KEY) >> (8 * grp)) & 0xFFu;
+                if (!active) continue;
+                const int i_match = m_match ? __ffs(m_match) - 1 : 8, i_empty = m_empty ? __ffs(m_empty) - 1 : 8;
+                int target = -1;       // the slot (sub-lane) that gets the count
+                bool retry = false;
+                if (i_match < i_empty) {
+                    target = i_match;
+                } else if (i_empty < 8) {
+                    unsigned long long prev = 0;
+                    if ((int)sub == i_empty) prev = atomicCAS(&slots[slot].key, (unsigned long long)SKM_EMPTY_KEY, kmer);
+                    prev = __shfl_sync(__activemask(), prev, 8 * grp + i_empty);
+                    if (prev == SKM_EMPTY_KEY) {
+                        target = i_empty;
+                        if ((int)sub == i_empty) n_new++;
+                    } else if (prev == kmer) {
+                        target = i_empty;
+                    } else {
+                        retry = true;   // another k-mer took the slot: look at the same window again
+                    }
+                }
+                if (target >= 0) {
+                    if ((int)sub == target) {
+                        if (kHisto) hs.move(atomicAdd(&slots[slot].count, 1ull), 1);
+                        else red_add_u64(&slots[slot].count, 1ull);
+                    }
+                    active = false;
+                } else if (!retry) {
+                    probes += 8;
+                    if (probes >= kPartSlots) {
+                        part_full = true;
+                        active = false;
+                    }
+                    for (uint32_t q = 0; q < 8; q++) s = TableRef::next(s);
+                }
+            }
+        }
+    }
+    if (part_full) gc->part_full = 1ull;
+    block_add(&gc->n_distinct, n_new);
+    block_add(&cc->n_windows, n_win);
+    if (kHisto) histo_smem_flush(s_low, g_hist);
+}
+
 // Count the windows of a unit range (conservation checks, list sizing).
 __global__ void __launch_bounds__(256)
 count_windows_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
@@ -806,12 +901,32 @@ __device__ __forceinline__ bool sorted_contains(const unsigned long long *__rest
     return false;
 }
 
+// A 2^16-bit filter per set on the first (up to) 8 bases of the masked value rejects almost every slot
+// with two shared-memory loads, so the scan streams the table instead of bisecting for every slot
+// (6.2 ms -> per 8.6 GB table before, profiles/experiments_r02.md).
+static constexpr uint32_t kScanFilterWords = 2048;   // 65536 bits
 __global__ void __launch_bounds__(256)
 scan_oligos_kernel(const Slot *__restrict__ table, uint64_t capacity, uint32_t k,
                    const unsigned long long *__restrict__ fwd_set, const unsigned long long *__restrict__ rc_set,
                    uint32_t n_set, unsigned long long mask, unsigned long long rc_mask, uint32_t min_count,
                    unsigned long long *__restrict__ out_keys, uint32_t *__restrict__ out_counts,
-                   uint64_t out_cap, unsigned long long *__restrict__ cursor) {
+                   uint64_t out_cap, unsigned long long *__restrict__ cursor, uint32_t oligo_length) {
+    __shared__ uint32_t f_fwd[kScanFilterWords], f_rc[kScanFilterWords];
+    for (uint32_t i = threadIdx.x; i < kScanFilterWords; i += blockDim.x) {
+        f_fwd[i] = 0;
+        f_rc[i] = 0;
+    }
+    __syncthreads();
+    // filter key = the leading min(8, oligo_length) bases of the oligo
+    const uint32_t fbits = 2 * (oligo_length < 8 ? oligo_length : 8);
+    const uint32_t sh_fwd = 2 * k - fbits;               // masked forward value: oligo sits at the top of the 2k bits
+    const uint32_t sh_rc = 2 * oligo_length - fbits;     // masked suffix value: 2 * oligo_length bits
+    for (uint32_t i = threadIdx.x; i < n_set; i += blockDim.x) {
+        const uint32_t a = (uint32_t)(fwd_set[i] >> sh_fwd), b = (uint32_t)(rc_set[i] >> sh_rc);
+        atomicOr(&f_fwd[a >> 5], 1u << (a & 31));
+        atomicOr(&f_rc[b >> 5], 1u << (b & 31));
+    }
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -828,10 +943,11 @@ scan_oligos_kernel(const Slot *__restrict__ table, uint64_t capacity, uint32_t k
             c = cnt >= kU32Max ? kU32Max : (uint32_t)cnt;
         }
         if (key != SKM_EMPTY_KEY && c >= min_count) {
-            if (sorted_contains(fwd_set, n_set, key & mask)) {
+            const uint32_t a = (uint32_t)((key & mask) >> sh_fwd), b = (uint32_t)((key & rc_mask) >> sh_rc);
+            if (((f_fwd[a >> 5] >> (a & 31)) & 1u) && sorted_contains(fwd_set, n_set, key & mask)) {
                 hit = true;
                 out = key;
-            } else if (sorted_contains(rc_set, n_set, key & rc_mask)) {
+            } else if (((f_rc[b >> 5] >> (b & 31)) & 1u) && sorted_contains(rc_set, n_set, key & rc_mask)) {
                 hit = true;
                 out = skm_revcomp_kmer(key, k);
             }

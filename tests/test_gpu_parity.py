@@ -448,7 +448,7 @@ def test_device_synth_matches_host(skm, oracle):
 
 # ---- (6) properties at larger size --------------------------------------------------------------------
 
-def test_chunk_invariance_and_digest_1m_reads(skm, oracle):
+def test_chunk_invariance_and_digest_300k_reads(skm, oracle):
     """tests/spcr_18s.rs:437-528 (final histogram independent of --chunks), on
     device-generated reads, plus the oracle's digest on the same input."""
     L, n = 150, 300_000
