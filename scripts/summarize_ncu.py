@@ -28,6 +28,11 @@ METRICS = [
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__inst_executed_op_shared_atom.sum",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
 ]
 
 
