@@ -1263,15 +1263,18 @@ int32_t refine_owner_lists(skm_ctx *c, uint32_t chunk, size_t seg_index, bool ex
     exact = exact || n_exp / kFineRegions < 4096;
     sg.owners.assign(N, OwnerList{});
     const size_t smem = tile_rebucket_smem_bytes();
-    // tiles of the coarse list that can hold an owner's k-mers (grid size; the kernel finds the real ones)
-    const uint32_t grid_in = sg.cap ? R * (uint32_t)((sg.cap + kTile - 1) / kTile) : (uint32_t)(sg.n_bytes / kTile) + R + 1;
+    // every tile slot of the coarse list (grid size; the kernel skips the empty ones)
+    const uint32_t grid_in = sg.cap ? nb_in * (uint32_t)((sg.cap + kTile - 1) / kTile) : (uint32_t)(sg.n_bytes / kTile) + nb_in + 1;
+    const uint32_t W = kFineRegions + 1;   // words per owner in the scratch arrays and in h_off
+    uint64_t *h_off_all = alloc_offsets(c, N * W);
+    if (!h_off_all) return fail(c, SKM_ERR_OOM, "pinned allocation failed");
+    CapLayout lay{};
+    if (!exact) lay.cap = ((n_exp / kFineRegions + n_exp / (16ull * kFineRegions) + 1024) + 15) & ~15ull;
+    OwnerArrays oa{};
     for (uint32_t o = 0; o < N; o++) {
         OwnerList &ol = sg.owners[o];
-        ol.h_off = alloc_offsets(c, kFineRegions + 1);
-        if (!ol.h_off) return fail(c, SKM_ERR_OOM, "pinned allocation failed");
-        CapLayout lay{};
+        ol.h_off = h_off_all + (size_t)o * W;
         if (!exact) {
-            lay.cap = ((n_exp / kFineRegions + n_exp / (16ull * kFineRegions) + 1024) + 15) & ~15ull;
             ol.cells = (size_t)lay.cap * kFineRegions;
             ol.max_tiles = kFineRegions * (uint32_t)((lay.cap + kTile - 1) / kTile);
         } else {
@@ -1281,57 +1284,56 @@ int32_t refine_owner_lists(skm_ctx *c, uint32_t chunk, size_t seg_index, bool ex
         ol.cap = lay.cap;
         const size_t off_bytes = (size_t)ol.max_tiles * (F + 1) * sizeof(uint16_t);
         {
-        HostTimer t_alloc(&c->host_ms[1]);
-        if (buf_alloc(c, (void **)&ol.list, ol.cells * sizeof(uint64_t), c->work) != cudaSuccess ||
-            buf_alloc(c, (void **)&ol.tile_off, off_bytes, c->work) != cudaSuccess ||
-            buf_alloc(c, (void **)&ol.meta, list_meta_words(kFineRegions) * sizeof(uint64_t), c->work) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(c, SKM_ERR_OOM, "device allocation failed (owner list of %zu cells)", ol.cells);
-        }
+            HostTimer t_alloc(&c->host_ms[1]);
+            if (buf_alloc(c, (void **)&ol.list, ol.cells * sizeof(uint64_t), c->work) != cudaSuccess ||
+                buf_alloc(c, (void **)&ol.tile_off, off_bytes, c->work) != cudaSuccess ||
+                buf_alloc(c, (void **)&ol.meta, list_meta_words(kFineRegions) * sizeof(uint64_t), c->work) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(c, SKM_ERR_OOM, "device allocation failed (owner list of %zu cells)", ol.cells);
+            }
         }
         c->list_bytes += ol.cells * sizeof(uint64_t);
-        const ListMeta m_o = list_meta_at(ol.meta, kFineRegions);
-        {
-            Span sp(c, ST_PART, c->work);
-            if (!exact) {
-                zero_async(c, c->d_bucket_cursors, (kFineRegions + 1) * sizeof(uint64_t), c->work);
-                tile_rebucket_kernel<0><<<grid_in, kSortThreads, smem, c->work>>>(sg.list, m_in, nb_in, o * R, (o + 1) * R, N,
-                                                                                 c->d_bucket_cursors, ol.list, lay.cap);
-                copy_words_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_cursors, (unsigned long long *)ol.h_off, kFineRegions + 1);
-                tile_plan_kernel<<<1, 1024, 0, c->work>>>(c->d_bucket_cursors, kFineRegions, lay.cap,
-                                                           (uint32_t)((lay.cap + kTile - 1) / kTile), m_o);
-                c->launches += 3;
-            } else {
-                zero_async(c, c->d_bucket_counts, (kFineRegions + 1) * sizeof(uint64_t), c->work);
-                tile_rebucket_kernel<1><<<grid_in, kSortThreads, smem, c->work>>>(sg.list, m_in, nb_in, o * R, (o + 1) * R, N,
-                                                                                 c->d_bucket_counts, nullptr, 0ull);
-                bucket_scan_kernel<<<1, kScanThreads, 0, c->work>>>(c->d_bucket_counts, kFineRegions, c->d_bucket_offsets,
-                                                                    c->d_bucket_cursors);
-                tile_rebucket_kernel<2><<<grid_in, kSortThreads, smem, c->work>>>(sg.list, m_in, nb_in, o * R, (o + 1) * R, N,
-                                                                                 c->d_bucket_cursors, ol.list, 0ull);
-                copy_words_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_offsets, (unsigned long long *)ol.h_off, kFineRegions + 1);
-                tile_plan_kernel<<<1, 1024, 0, c->work>>>(c->d_bucket_offsets, kFineRegions, 0ull, 0u, m_o);
-                c->launches += 5;
-            }
-            c->stage_launches[ST_PART]++;
+        oa.list[o] = ol.list;
+        oa.meta[o] = ol.meta;
+        oa.tile_off[o] = ol.tile_off;
+    }
+    // one launch of each kernel serves all owners (owner = coarse bucket >> g1c)
+    {
+        Span sp(c, ST_PART, c->work);
+        if (!exact) {
+            zero_async(c, c->d_bucket_cursors, (size_t)N * W * sizeof(uint64_t), c->work);
+            tile_rebucket_kernel<0><<<grid_in, kSortThreads, smem, c->work>>>(sg.list, m_in, nb_in, g1c, N, c->d_bucket_cursors, oa, lay.cap);
+            copy_words_kernel<<<8, 256, 0, c->work>>>(c->d_bucket_cursors, (unsigned long long *)h_off_all, N * W);
+            tile_plan_owners_kernel<<<N, 1024, 0, c->work>>>(c->d_bucket_cursors, kFineRegions, lay.cap,
+                                                             (uint32_t)((lay.cap + kTile - 1) / kTile), oa);
+            c->launches += 3;
+        } else {
+            zero_async(c, c->d_bucket_counts, (size_t)N * W * sizeof(uint64_t), c->work);
+            tile_rebucket_kernel<1><<<grid_in, kSortThreads, smem, c->work>>>(sg.list, m_in, nb_in, g1c, N, c->d_bucket_counts, oa, 0ull);
+            bucket_scan_kernel<<<N, kScanThreads, 0, c->work>>>(c->d_bucket_counts, kFineRegions, c->d_bucket_offsets, c->d_bucket_cursors);
+            tile_rebucket_kernel<2><<<grid_in, kSortThreads, smem, c->work>>>(sg.list, m_in, nb_in, g1c, N, c->d_bucket_cursors, oa, 0ull);
+            copy_words_kernel<<<8, 256, 0, c->work>>>(c->d_bucket_offsets, (unsigned long long *)h_off_all, N * W);
+            tile_plan_owners_kernel<<<N, 1024, 0, c->work>>>(c->d_bucket_offsets, kFineRegions, 0ull, 0u, oa);
+            c->launches += 5;
         }
-        CU(cudaGetLastError());
-        DBG_SYNC(exact ? "tile_rebucket (exact)" : "tile_rebucket (capped)");
+        c->stage_launches[ST_PART]++;
+    }
+    CU(cudaGetLastError());
+    DBG_SYNC(exact ? "tile_rebucket (exact)" : "tile_rebucket (capped)");
+    {
         cudaStream_t sort_st = c->sort_overlap ? c->sort_stream : c->work;
         if (sort_st != c->work) {
             CU(cudaEventRecord(c->ev_sort, c->work));
             CU(cudaStreamWaitEvent(sort_st, c->ev_sort, 0));
         }
-        {
-            Span sp(c, ST_SORT, sort_st);
-            tile_sort_kernel<<<ol.max_tiles, kSortThreads, tile_sort_smem_bytes(c->g2), sort_st>>>(ol.list, m_o, kFineRegions,
-                                                                                                  list_geom(c), ol.tile_off);
-            c->launches++;
-            c->stage_launches[ST_SORT]++;
-        }
-        CU(cudaGetLastError());
-        DBG_SYNC("tile_sort of an owner list");
+        Span sp(c, ST_SORT, sort_st);
+        tile_sort_owners_kernel<<<dim3(sg.owners[0].max_tiles, N), kSortThreads, tile_sort_smem_bytes(c->g2), sort_st>>>(
+            oa, kFineRegions, list_geom(c));
+        c->launches++;
+        c->stage_launches[ST_SORT]++;
     }
+    CU(cudaGetLastError());
+    DBG_SYNC("tile_sort of the owner lists");
     // the coarse list has been consumed (on `work`); the packed form stays for the overflow retry
     buf_free(c, sg.list, c->work);
     buf_free(c, sg.meta, c->work);
@@ -1546,7 +1548,7 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     c->n_chunks = c->p.chunks == 0 ? 1 : c->p.chunks;  // src/io.rs:378
     c->n_ranks = c->p.n_ranks == 0 ? 1 : c->p.n_ranks;
     if (c->p.rank >= c->n_ranks) return fail(c, SKM_ERR_INVALID_ARG, "rank %u >= n_ranks %u", c->p.rank, c->n_ranks);
-    if (c->n_ranks > kMaxBuckets) return fail(c, SKM_ERR_INVALID_ARG, "n_ranks too large");
+    if (c->n_ranks > kMaxOwners) return fail(c, SKM_ERR_INVALID_ARG, "at most %u ranks, got %u", kMaxOwners, c->n_ranks);
     if (c->p.insert_mode > SKM_INSERT_PARTITIONED) return fail(c, SKM_ERR_INVALID_ARG, "bad insert_mode");
 
     int n_dev = 0;
@@ -1629,9 +1631,11 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     c->h_pinned_words = kMaxBuckets + 16;
     CU(cudaMallocHost((void **)&c->h_pinned, c->h_pinned_words * sizeof(uint64_t)));
     CU(cudaMallocHost((void **)&c->h_snap, skm_ctx::kSnapRing * sizeof(uint64_t)));
-    CU(cudaMalloc((void **)&c->d_bucket_counts, (kMaxBuckets + 1) * sizeof(uint64_t)));
-    CU(cudaMalloc((void **)&c->d_bucket_offsets, (kMaxBuckets + 1) * sizeof(uint64_t)));
-    CU(cudaMalloc((void **)&c->d_bucket_cursors, (kMaxBuckets + 1) * sizeof(uint64_t)));
+    // (multi-GPU senders keep one array of kFineRegions + 1 entries per owner in each of the three)
+    const size_t scratch_words = std::max<size_t>(kMaxBuckets + 1, (size_t)std::max(c->n_ranks, 1u) * (kFineRegions + 1));
+    CU(cudaMalloc((void **)&c->d_bucket_counts, scratch_words * sizeof(uint64_t)));
+    CU(cudaMalloc((void **)&c->d_bucket_offsets, scratch_words * sizeof(uint64_t)));
+    CU(cudaMalloc((void **)&c->d_bucket_cursors, scratch_words * sizeof(uint64_t)));
 
     c->chunks.resize(c->n_chunks);
     c->histos.resize(c->n_chunks);
@@ -1660,6 +1664,8 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
         c->g2 = (uint32_t)std::max(0, std::min<int>(g2, (int)kMaxSubLog2));
     }
     CU(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)tile_sort_smem_bytes(kMaxSubLog2)));
+    CU(cudaFuncSetAttribute(tile_sort_owners_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)tile_sort_smem_bytes(kMaxSubLog2)));
     CU(cudaFuncSetAttribute(tile_rebucket_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_rebucket_smem_bytes()));
     CU(cudaFuncSetAttribute(tile_rebucket_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_rebucket_smem_bytes()));
@@ -2760,15 +2766,24 @@ int32_t mg_prepare_local(skm_ctx *c) {
     return refresh_chunk_counters(c);
 }
 
+// The collective part of a finalize is host all-gathers through a callback (gloo over loopback under
+// torchrun: some 0.5 ms each at 8 ranks, and 10 ms for 8 x 800 KB of histogram columns).  So the two
+// messages that are almost always small travel inside the fixed-size ones: up to kInlineRecs
+// directory records inside the header, and the first kInlineBins bins of every column behind the
+// totals (bins above a rank's highest occupied one are zero).  Two all-gathers per finalize then.
+constexpr uint32_t kInlineRecs = 160;
+constexpr size_t kInlineBins = 512;
+
 struct MgHeader {
     int32_t status;
     uint32_t n_records;
     uint64_t n_windows, n_reads;
+    MgRecord rec[kInlineRecs];
 };
 
 struct MgTotals {
     int32_t status;
-    uint32_t pad;
+    uint32_t top_bin;   // 1 + the highest occupied bin over this rank's columns
     uint64_t n_kmers, n_distinct_scan, n_distinct, n_saturated, n_windows;
 };
 
@@ -2779,14 +2794,16 @@ int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm, bool final) {
     const size_t nbins = c->p.histo_max + 2;
     // ---- phase 1: local work, then the directory of what everybody shipped (doubles as the
     //      "all slices have landed" barrier: a rank joins only after its own copies are done) ----
-    MgHeader mine{};
+    std::vector<MgHeader> hdrs(N + 1);
+    MgHeader &mine = hdrs[N];
+    mine = MgHeader{};
     mine.status = mg_prepare_local(c);
     mine.n_records = (uint32_t)c->mg_sent.size();
     for (auto &cc : c->h_cc) {
         mine.n_windows += cc.n_windows;
         mine.n_reads += cc.n_reads;
     }
-    std::vector<MgHeader> hdrs(N);
+    std::copy(c->mg_sent.begin(), c->mg_sent.begin() + std::min<size_t>(c->mg_sent.size(), kInlineRecs), mine.rec);
     int32_t rc = mg_allgather(c, comm, &mine, hdrs.data(), sizeof(MgHeader));
     if (rc) return rc;
     uint32_t max_rec = 0;
@@ -2802,10 +2819,16 @@ int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm, bool final) {
     }
     if (reads_all == 0 && final)  // src/io.rs:578-580
         return fail(c, SKM_ERR_NO_READS, "No reads were ingested. Check that input files contain valid FASTQ records.");
-    std::vector<MgRecord> all((size_t)N * std::max(max_rec, 1u)), sendbuf(std::max(max_rec, 1u));
-    std::copy(c->mg_sent.begin(), c->mg_sent.end(), sendbuf.begin());
-    rc = mg_allgather(c, comm, sendbuf.data(), all.data(), (uint64_t)sendbuf.size() * sizeof(MgRecord));
-    if (rc) return rc;
+    std::vector<MgRecord> all, sendbuf(std::max(max_rec, 1u));
+    if (max_rec > kInlineRecs) {   // a long directory (many batches): one more all-gather for all of it
+        all.resize((size_t)N * sendbuf.size());
+        std::copy(c->mg_sent.begin(), c->mg_sent.end(), sendbuf.begin());
+        rc = mg_allgather(c, comm, sendbuf.data(), all.data(), (uint64_t)sendbuf.size() * sizeof(MgRecord));
+        if (rc) return rc;
+    }
+    auto record = [&](uint32_t src, uint32_t i) -> const MgRecord & {
+        return max_rec > kInlineRecs ? all[(size_t)src * sendbuf.size() + i] : hdrs[src].rec[i];
+    };
 
     // ---- phase 2: the lists this rank counts, in chunk order: its own + the slices in its arena ----
     struct Item { SegDesc d; uint32_t chunk; uint64_t n_kmers; };
@@ -2825,7 +2848,7 @@ int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm, bool final) {
         }
     for (uint32_t src = 0; src < N; src++)
         for (uint32_t i = 0; i < hdrs[src].n_records; i++) {
-            const MgRecord &rec = all[(size_t)src * sendbuf.size() + i];
+            const MgRecord &rec = record(src, i);
             if (rec.dst != me || rec.dead) continue;
             if (rec.chunk >= c->n_chunks) return fail(c, SKM_ERR_STATE, "rank %u shipped chunk %u (this ctx has %u chunks)", src, rec.chunk, c->n_chunks);
             uint8_t *base = c->mg_arena + (size_t)src * c->mg_sub_bytes;
@@ -2897,6 +2920,9 @@ int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm, bool final) {
     }
 
     // ---- phase 4: totals and histogram columns over all ranks ----
+    const size_t wbins = c->p.chunks > 0 ? std::min(nbins, kInlineBins) : 0;
+    const size_t msg_words = (sizeof(MgTotals) + 7) / 8 + (size_t)c->n_chunks * wbins;
+    std::vector<uint64_t> msg(msg_words, 0), msgs((size_t)N * msg_words);
     MgTotals tm{};
     tm.status = status;
     if (status == SKM_OK) {
@@ -2915,20 +2941,35 @@ int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm, bool final) {
         tm.n_distinct = d;
         tm.n_saturated = c->last_tot.n_saturated;
         tm.n_windows = mine.n_windows;
+        for (uint32_t ch = 0; ch < c->n_chunks && c->p.chunks > 0 && tm.status == SKM_OK; ch++) {
+            if (!c->have_histo[ch] || c->histos[ch].size() != nbins) {
+                tm.status = fail(c, SKM_ERR_STATE, "internal: column %u missing", ch);
+                break;
+            }
+            const std::vector<uint64_t> &h = c->histos[ch];
+            size_t top = nbins;
+            while (top > 0 && h[top - 1] == 0) top--;
+            tm.top_bin = std::max(tm.top_bin, (uint32_t)top);
+            std::copy(h.begin(), h.begin() + wbins, msg.begin() + (sizeof(MgTotals) + 7) / 8 + (size_t)ch * wbins);
+        }
     }
-    std::vector<MgTotals> tots(N);
-    rc = mg_allgather(c, comm, &tm, tots.data(), sizeof(MgTotals));
+    std::memcpy(msg.data(), &tm, sizeof(MgTotals));
+    rc = mg_allgather(c, comm, msg.data(), msgs.data(), (uint64_t)msg_words * 8);
     if (rc) return rc;
     uint64_t g_kmers = 0, g_scan = 0, g_distinct = 0, g_sat = 0;
+    uint32_t g_top = 0;
     for (uint32_t r = 0; r < N; r++) {
-        if (tots[r].status != SKM_OK) {
+        MgTotals t;
+        std::memcpy(&t, msgs.data() + (size_t)r * msg_words, sizeof(MgTotals));
+        if (t.status != SKM_OK) {
             if (tm.status != SKM_OK) return tm.status;
-            return fail(c, tots[r].status, "rank %u failed while counting (see its skm_last_error)", r);
+            return fail(c, t.status, "rank %u failed while counting (see its skm_last_error)", r);
         }
-        g_kmers += tots[r].n_kmers;
-        g_scan += tots[r].n_distinct_scan;
-        g_distinct += tots[r].n_distinct;
-        g_sat += tots[r].n_saturated;
+        g_kmers += t.n_kmers;
+        g_scan += t.n_distinct_scan;
+        g_distinct += t.n_distinct;
+        g_sat += t.n_saturated;
+        g_top = std::max(g_top, t.top_bin);
     }
     // conservation identities on the global totals (src/io.rs:1042-1047, 1120-1132)
     if (g_sat == 0 && g_kmers != windows_all)
@@ -2941,19 +2982,26 @@ int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm, bool final) {
                     (unsigned long long)g_scan, (unsigned long long)g_distinct);
     if (c->p.chunks > 0) {
         // column i = sum over the partitions' columns (a k-mer lives in exactly one partition)
-        std::vector<uint64_t> mycols((size_t)c->n_chunks * nbins), allcols((size_t)N * c->n_chunks * nbins);
-        for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
-            if (!c->have_histo[ch] || c->histos[ch].size() != nbins) return fail(c, SKM_ERR_STATE, "internal: column %u missing", ch);
-            std::copy(c->histos[ch].begin(), c->histos[ch].end(), mycols.begin() + (size_t)ch * nbins);
+        const uint64_t *src0 = msgs.data() + (sizeof(MgTotals) + 7) / 8;
+        size_t stride_rank = msg_words, stride_chunk = wbins, width = wbins;
+        std::vector<uint64_t> mycols, allcols;
+        if (g_top > wbins) {   // somebody has counts beyond the inline bins: gather the whole columns
+            mycols.resize((size_t)c->n_chunks * nbins);
+            allcols.resize((size_t)N * c->n_chunks * nbins);
+            for (uint32_t ch = 0; ch < c->n_chunks; ch++)
+                std::copy(c->histos[ch].begin(), c->histos[ch].end(), mycols.begin() + (size_t)ch * nbins);
+            rc = mg_allgather(c, comm, mycols.data(), allcols.data(), (uint64_t)mycols.size() * sizeof(uint64_t));
+            if (rc) return rc;
+            src0 = allcols.data();
+            stride_rank = (size_t)c->n_chunks * nbins;
+            stride_chunk = width = nbins;
         }
-        rc = mg_allgather(c, comm, mycols.data(), allcols.data(), (uint64_t)mycols.size() * sizeof(uint64_t));
-        if (rc) return rc;
         for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
             std::vector<uint64_t> &h = c->histos[ch];
             std::fill(h.begin(), h.end(), 0);
             for (uint32_t r = 0; r < N; r++) {
-                const uint64_t *src = allcols.data() + ((size_t)r * c->n_chunks + ch) * nbins;
-                for (size_t b = 0; b < nbins; b++) h[b] += src[b];
+                const uint64_t *src = src0 + (size_t)r * stride_rank + (size_t)ch * stride_chunk;
+                for (size_t b = 0; b < width; b++) h[b] += src[b];
             }
         }
         const std::vector<uint64_t> &last = c->histos[c->n_chunks - 1];

@@ -1030,6 +1030,10 @@ __global__ void __launch_bounds__(kScanThreads)
 bucket_scan_kernel(const unsigned long long *__restrict__ counts, uint32_t n_buckets,
                    unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ cursors) {
     __shared__ unsigned long long part[kScanThreads];
+    // (one CTA per array of n_buckets + 1 entries: the multi-GPU sender scans all owners' counts in one launch)
+    counts += (size_t)blockIdx.x * (n_buckets + 1);
+    offsets += (size_t)blockIdx.x * (n_buckets + 1);
+    cursors += (size_t)blockIdx.x * (n_buckets + 1);
     const uint32_t per = (n_buckets + blockDim.x - 1) / blockDim.x;
     const uint32_t a = threadIdx.x * per;
     unsigned long long s = 0;
@@ -1250,9 +1254,31 @@ __host__ __device__ inline ListMeta list_meta_at(unsigned long long *base, uint3
 
 // src: capped layout (cap > 0) = the scatter kernel's per-bucket totals; exact layout (cap == 0) =
 // the nb+1 bucket offsets.  One CTA of 1024 threads.
+__device__ __forceinline__ void tile_plan_body(const unsigned long long *__restrict__ src, uint32_t nb,
+                                               unsigned long long cap, uint32_t tiles_per_bucket, ListMeta m);
 __global__ void __launch_bounds__(1024)
 tile_plan_kernel(const unsigned long long *__restrict__ src, uint32_t nb, unsigned long long cap,
                  uint32_t tiles_per_bucket, ListMeta m) {
+    tile_plan_body(src, nb, cap, tiles_per_bucket, m);
+}
+
+// The lists of all owners of one batch (multi-GPU sender): one launch serves them all.
+static constexpr uint32_t kMaxOwners = 16;
+struct OwnerArrays {
+    unsigned long long *list[kMaxOwners];
+    unsigned long long *meta[kMaxOwners];   // list_meta_words(nb) words each
+    uint16_t *tile_off[kMaxOwners];
+};
+
+// CTA o plans owner o's list from the o-th array of nb + 1 totals / offsets.
+__global__ void __launch_bounds__(1024)
+tile_plan_owners_kernel(const unsigned long long *__restrict__ src, uint32_t nb, unsigned long long cap,
+                        uint32_t tiles_per_bucket, OwnerArrays oa) {
+    tile_plan_body(src + (size_t)blockIdx.x * (nb + 1), nb, cap, tiles_per_bucket, list_meta_at(oa.meta[blockIdx.x], nb));
+}
+
+__device__ __forceinline__ void tile_plan_body(const unsigned long long *__restrict__ src, uint32_t nb,
+                                               unsigned long long cap, uint32_t tiles_per_bucket, ListMeta m) {
     __shared__ uint32_t s_warp[32];
     const uint32_t b = threadIdx.x;
     uint32_t tiles = 0;
@@ -1284,15 +1310,27 @@ tile_plan_kernel(const unsigned long long *__restrict__ src, uint32_t nb, unsign
 }
 
 // tile_off[t * (F + 1) + f] = first cell (relative to the tile) of sub-bucket f; [.. + F] = tile length
+__device__ __forceinline__ void tile_sort_body(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb,
+                                               ListGeom geom, uint16_t *__restrict__ tile_off, uint32_t t);
 __global__ void __launch_bounds__(kSortThreads, 2)
 tile_sort_kernel(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb, ListGeom geom,
                  uint16_t *__restrict__ tile_off) {
+    tile_sort_body(list, m, nb, geom, tile_off, blockIdx.x);
+}
+// grid (tile slots per owner, owners)
+__global__ void __launch_bounds__(kSortThreads, 2)
+tile_sort_owners_kernel(OwnerArrays oa, uint32_t nb, ListGeom geom) {
+    const uint32_t o = blockIdx.y;
+    tile_sort_body(oa.list[o], list_meta_at(oa.meta[o], nb), nb, geom, oa.tile_off[o], blockIdx.x);
+}
+
+__device__ __forceinline__ void tile_sort_body(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb,
+                                               ListGeom geom, uint16_t *__restrict__ tile_off, uint32_t t) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long *stage = reinterpret_cast<unsigned long long *>(s_raw);   // kTile
     uint32_t *cnt = reinterpret_cast<uint32_t *>(stage + kTile);                  // F (+1)
     __shared__ uint32_t s_warp[kSortThreads / 32];
     const uint32_t F = 1u << geom.g2;
-    const uint32_t t = blockIdx.x;
     if (t >= m.tile_begin[nb]) return;
     uint32_t lo = 0, hi = nb;  // last bucket whose tile_begin <= t
     while (hi - lo > 1) {
@@ -1376,9 +1414,9 @@ static constexpr uint32_t kFineRegions = 1u << kFineLog2;
 
 template <int MODE>
 __global__ void __launch_bounds__(kSortThreads, 2)
-tile_rebucket_kernel(const unsigned long long *__restrict__ in_list, ListMeta m, uint32_t nb_in, uint32_t b_lo,
-                     uint32_t b_hi, uint32_t n_ranks, unsigned long long *__restrict__ cursors,
-                     unsigned long long *__restrict__ out, unsigned long long cap) {
+tile_rebucket_kernel(const unsigned long long *__restrict__ in_list, ListMeta m, uint32_t nb_in, uint32_t log2_coarse,
+                     uint32_t n_ranks, unsigned long long *__restrict__ cursors_all, OwnerArrays oa,
+                     unsigned long long cap) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long *stage = reinterpret_cast<unsigned long long *>(s_raw);     // kTile
     unsigned long long *s_g = stage + kTile;                                        // kFineRegions: first cell of this tile's run
@@ -1386,15 +1424,17 @@ tile_rebucket_kernel(const unsigned long long *__restrict__ in_list, ListMeta m,
     uint32_t *room = cnt + kFineRegions;                                            // kFineRegions (capped)
     uint16_t *stage_f = reinterpret_cast<uint16_t *>(room + kFineRegions);          // kTile: fine bucket of every staged k-mer
     __shared__ uint32_t s_warp[kSortThreads / 32];
-    // the tiles of the owner's coarse buckets [b_lo, b_hi): grid = tile_begin[b_hi] - tile_begin[b_lo] at most
-    const uint32_t t = m.tile_begin[b_lo] + blockIdx.x;
-    if (t >= m.tile_begin[b_hi]) return;
-    uint32_t lo = b_lo, hi = b_hi;  // last bucket whose tile_begin <= t
+    // every tile of the coarse list; its bucket says whose k-mers it holds (bucket = owner << log2_coarse | region)
+    const uint32_t t = blockIdx.x;
+    if (t >= m.tile_begin[nb_in]) return;
+    uint32_t lo = 0, hi = nb_in;  // last bucket whose tile_begin <= t
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
         if (m.tile_begin[mid] <= t) lo = mid; else hi = mid;
     }
-    (void)nb_in;
+    const uint32_t owner = lo >> log2_coarse;
+    unsigned long long *cursors = cursors_all + (size_t)owner * (kFineRegions + 1);
+    unsigned long long *out = oa.list[owner];
     const uint32_t j = t - m.tile_begin[lo];
     const unsigned long long bn = m.bucket_n[lo];
     const unsigned long long first = (unsigned long long)j * kTile;
@@ -1410,14 +1450,21 @@ tile_rebucket_kernel(const unsigned long long *__restrict__ in_list, ListMeta m,
         const uint32_t i = threadIdx.x + r * kSortThreads;
         km[r] = i < n ? cells[i] : 0ull;
     }
+    // A tile of one coarse bucket feeds only kFineRegions / (coarse regions per owner) = n_ranks fine buckets, so
+    // the lanes of a warp collide on a handful of counters: the warp groups its lanes by fine bucket
+    // (match.any) and one lane per group reserves the group's ranks with a single shared-memory atomic.
+    const uint32_t lane = threadIdx.x & 31;
 #pragma unroll
     for (uint32_t r = 0; r < kSortPer; r++) {
         const uint32_t i = threadIdx.x + r * kSortThreads;
-        if (i < n) {
-            const uint64_t lh = skm_local_hash(skm_hash_kmer(km[r]), n_ranks);
-            const uint32_t f = (uint32_t)(lh >> (64u - kFineLog2));
-            fr[r] = f | (atomicAdd(&cnt[f], 1u) << kMaxSubLog2);
-        }
+        uint32_t f = 0xffffffffu;   // lanes past the end of the tile form a group of their own
+        if (i < n) f = (uint32_t)(skm_local_hash(skm_hash_kmer(km[r]), n_ranks) >> (64u - kFineLog2));
+        const uint32_t peers = __match_any_sync(0xffffffffu, f);
+        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+        uint32_t base = 0;
+        if (lane == leader && i < n) base = atomicAdd(&cnt[f], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        fr[r] = f | ((base + (uint32_t)__popc(peers & ((1u << lane) - 1u))) << kMaxSubLog2);
     }
     __syncthreads();
     const uint32_t a = threadIdx.x * 2;   // kFineRegions = 2 * kSortThreads

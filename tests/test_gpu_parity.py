@@ -507,24 +507,30 @@ def _feed_ranks(engines, reads, n_reads, line, chunks, world):
 
 def _check_sharded(group_like, engines, run, chunks, world):
     from sharkmer_b200 import common
-    merged = {}
+    all_keys, all_counts = [], []
     for r, e in enumerate(engines):
         keys, cnts = e.export(sorted=True)
         assert all(common.owner_rank(common.hash_kmer(int(x)), world) == r for x in keys[:3000])
-        assert not (set(keys[:3000].tolist()) & set(merged))
-        merged.update(zip(keys.tolist(), cnts.tolist()))
+        all_keys.append(keys)
+        all_counts.append(cnts)
     okeys, ocounts = run.table().export_sorted()
-    assert len(merged) == okeys.size
-    assert merged == dict(zip(okeys.tolist(), ocounts.tolist()))
+    all_keys, all_counts = np.concatenate(all_keys), np.concatenate(all_counts)
+    order = np.argsort(all_keys, kind="stable")
+    # the oracle's keys are sorted and distinct: equality also says the partitions are disjoint
+    assert all_keys.size == okeys.size
+    assert np.array_equal(all_keys[order], okeys)
+    assert np.array_equal(all_counts[order].astype(np.uint64), ocounts.astype(np.uint64))
     for c in range(chunks):   # every rank holds the columns summed over all ranks
-        for e in engines:
-            assert (e.histogram(c) == run.histogram(c)).all(), c
+        for r, e in enumerate(engines):
+            got, want = e.histogram(c), run.histogram(c)
+            bad = np.nonzero(got != want)[0]
+            assert bad.size == 0, (c, r, bad[:8].tolist(), got[bad[:8]].tolist(), want[bad[:8]].tolist())
     assert sum(int(e.totals().n_kmers) for e in engines) == run.n_kmers_ingested
     assert sum(int(e.totals().n_unique) for e in engines) == okeys.size
     assert sum(int(e.totals().n_reads) for e in engines) == run.n_reads_ingested
 
 
-@pytest.mark.parametrize("world,k,chunks,mode", [(2, 25, 3, 0), (3, 21, 5, 0), (2, 31, 0, 0), (4, 21, 2, 2)])
+@pytest.mark.parametrize("world,k,chunks,mode", [(2, 25, 3, 0), (3, 21, 5, 0), (2, 31, 0, 0), (4, 21, 2, 2), (8, 21, 2, 0)])
 def test_sharded_group_vs_oracle(skm, oracle, world, k, chunks, mode):
     """skm_group_*: `world` ranks in one process on ONE GPU — bucketing by (owner, region), tile sort,
     copy-engine exchange into the peers' arenas, collective finalize, column sum.  Sorted table
@@ -570,6 +576,39 @@ def test_sharded_group_skewed_and_unbalanced(skm, oracle):
         g.engines[(b // n_chunks) % 2].ingest_batch(b % n_chunks, reads[b * 1000 * (L + 1):(b + 1) * 1000 * (L + 1)])
     g.finalize()
     _check_sharded(g, g.engines, run, chunks, world)
+    g.close()
+
+
+@pytest.mark.parametrize("world,k,chunks,skew", [(2, 21, 2, False), (4, 31, 1, True)])
+def test_sharded_group_capped_layouts(skm, oracle, world, k, chunks, skew):
+    """Batches large enough for the one-pass capped layouts on the senders (coarse list by (owner, region),
+    then every owner's list re-bucketed into its 1024 regions by ONE launch for all owners).  skew: a tenth
+    of the reads are poly-A, so a capped bucket overflows, the batch is rebuilt exactly and shipped again."""
+    from sharkmer_b200.multigpu import Group
+    L, hmax = 100, 1000
+    per_batch = (4_200_000 * world) // (L + 1)          # reads per (rank, chunk) batch: past the capped threshold
+    n = per_batch * world * chunks
+    reads = oracle.synth_reads(90 + world, 2_000_000, L, 0.002, 0.001, 0, n).copy()
+    if skew:
+        reads.reshape(n, L + 1)[::10, :L] = ord("A")
+    run = run_oracle(oracle, reads, k, chunks, hmax)
+    line = L + 1
+    g = Group(k, chunks, hmax, [0] * world, arena_bytes_per_rank=per_batch * line * 24 * chunks + (64 << 20), insert_mode=0)
+    # the reference deals 1000-read batches round-robin over the chunks (src/io.rs:355-361); here every rank
+    # ingests its share of a chunk's batches as ONE large batch
+    by_chunk = [[] for _ in range(chunks)]
+    for b in range((n + 999) // 1000):
+        by_chunk[b % chunks].append(reads[b * 1000 * line:min((b + 1) * 1000, n) * line])
+    for c in range(chunks):
+        whole = np.concatenate(by_chunk[c])
+        n_c = whole.size // line
+        cuts = [n_c * r // world for r in range(world + 1)]
+        for r in range(world):
+            g.engines[r].ingest_batch(c, whole[cuts[r] * line:cuts[r + 1] * line])
+    g.finalize()
+    _check_sharded(g, g.engines, run, chunks, world)
+    st = [e.stage_times() for e in g.engines]
+    assert all(t.tiled_launches >= 1 for t in st)
     g.close()
 
 

@@ -587,3 +587,28 @@ def test_cpp_host_mirror_equals_device_lookups(harness, oracle, tmp_path):
     b, out_b = run_cpp_pcr(harness, tmp_path, t, 21, spec, "smp", ["--min-kmer-count", "1", "--host-mirror"])
     assert a.returncode == 0 and b.returncode == 0 and a.stdout == b.stdout
     assert open(out_b / "smp_18s.fasta").read() == fasta_a
+
+
+def test_c4_reduced_cpp_equals_python_and_truth(harness, oracle, tmp_path):
+    """BASELINE config C4 at 1/27 size on the oracle table (the full-size run on the device table is
+    tests/test_gpu_zz_c4.py): the cnidaria panel from the committed fixture, templates at 50x copy number in a
+    random genome, 0.5 % read errors, k = 25.  The C++ host and the Python host write byte-identical FASTA for
+    every gene and the first product is the planted amplicon."""
+    import c4_data
+    k, L = 25, 150
+    prm = c4_data.load_panel()
+    pool, truth = c4_data.build_pool(prm, k, 100_000, copies=50, seed=4)
+    n = pool.size * 75 // L
+    lines = c4_data.sample_reads(pool, n, L, 0.005, np.random.default_rng(4))
+    t = oracle.KmerCounts(k)
+    for i in range(n):
+        t.ingest_seq(lines[i, :L].tobytes().decode())
+    compare_with_python(harness, tmp_path, t, k, prm, sample="c4")
+    for p in prm:
+        fa = open(tmp_path / "py" / f"c4_{p.gene_name}.fasta").read().split("\n")
+        first = []
+        for line in fa[1:]:
+            if line.startswith(">") or not line:
+                break
+            first.append(line)
+        assert "".join(first) == truth[p.gene_name], p.gene_name
