@@ -372,6 +372,8 @@ def run_ours(args):
         cols = sharded.finalize()
         return cols[-1] if cols is not None else None
 
+    per_step = []   # wall ms of every timed step of the last timed() call (rank 0's view; for spotting outliers)
+
     def timed(host_buffers: bool, steps: int, warmup: int):
         for _ in range(warmup):
             step(host_buffers)
@@ -379,8 +381,11 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
+        per_step.clear()
         for _ in range(steps):
-            hist = step(host_buffers)
+            t_s = time.perf_counter()
+            hist = step(host_buffers)          # (ends with a blocking read of the result)
+            per_step.append(round((time.perf_counter() - t_s) * 1e3, 3))
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
@@ -452,6 +457,7 @@ def run_ours(args):
                 "digest": int(np.int64(int(v[3])).astype(np.uint64))}
 
     ms_dev, ms_wall, hist_dev = timed(False, args.steps, args.warmup)
+    steps_dev_ms = list(per_step)
     stt = eng.stage_times()
     tot = eng.totals()
     gs_dev = global_state()
@@ -459,6 +465,7 @@ def run_ours(args):
             "histogram_support_equals_distinct": hist_dev is None or int(hist_dev[1:].sum()) == gs_dev["distinct"]}  # :1120-1132
     if not args.no_e2e:
         ms_e2e, ms_e2e_wall, hist_e2e = timed(True, args.steps, args.warmup)
+        steps_e2e_ms = list(per_step)
         gs_e2e = global_state()
         full["host_buffer_run_equals_device_run"] = bool((hist_dev is None or (hist_e2e == hist_dev).all())
                                                          and gs_e2e == gs_dev)
@@ -539,7 +546,7 @@ def run_ours(args):
             "scaling": SCALING, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(world),
             "bases_per_sec": n_bases / (ms_dev / 1e3),
-            "ms_per_step_wall": ms_wall,
+            "ms_per_step_wall": ms_wall, "steps_ms_wall": steps_dev_ms,
             "insert_mode": args.mode,
             "n_kmers": n_kmers, "n_distinct_rank0": int(tot.n_unique),
             "stage_ms": {"pack": stt.pack, "count": stt.count, "partition": stt.partition, "sort": stt.sort,
@@ -587,7 +594,7 @@ def run_ours(args):
             out["e2e"] = {"value": n_kmers / (ms_e2e / 1e3), "unit": "kmers/s",
                           "h2d_bytes_per_step": int(in_bytes) * world,
                           "d2h_bytes_per_step": int(CHUNKS * (HISTO_MAX + 2) * 8 + 64) * world,   # histogram columns + totals
-                          "ms_per_step": ms_e2e, "ms_per_step_wall": ms_e2e_wall,
+                          "ms_per_step": ms_e2e, "ms_per_step_wall": ms_e2e_wall, "steps_ms_wall": steps_e2e_ms,
                           "stage_ms": {"h2d": st2.h2d, "pack": st2.pack, "insert": st2.insert, "histogram": st2.histogram},
                           "api": "skm_ingest_batch(pinned host buffers) x10 -> skm_finalize -> skm_histogram"}
         if world == 1 and not args.no_services:

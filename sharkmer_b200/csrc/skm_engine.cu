@@ -645,23 +645,15 @@ int32_t bucket_count(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn 
 
 // Pass 2: scatter the k-mers into `d_out`, grouped by bucket (uses the cursors of pass 1).
 int32_t bucket_scatter(skm_ctx *c, uint32_t chunk, size_t s0, size_t s1, BucketFn fn, uint32_t n_buckets,
-                       unsigned long long *d_out, const OwnerBases *p2p = nullptr) {
+                       unsigned long long *d_out) {
     const ChunkState &cs = c->chunks[chunk];
     Span sp(c, ST_PART, c->work);
     const size_t smem = scatter_smem_bytes(n_buckets);
-    OwnerBases bases{};
-    if (p2p) {
-        bases = *p2p;
-    } else {
-        bases.dst[0] = d_out;
-        bases.uniform = 1;
-        bases.log2_regions = fn.log2_regions;
-    }
     for (size_t s = s0; s < s1; s++) {
         const Segment &sg = cs.segs[s];
         if (!sg.n_units || !sg.codes) continue;
         bucket_scatter_kernel<false><<<grid_for(sg.n_units, kScatterThreads), kScatterThreads, smem, c->work>>>(
-            sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, bases, CapLayout{},
+            sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, d_out, CapLayout{},
             nullptr);
         c->launches++;
         c->stage_launches[ST_PART]++;
@@ -689,13 +681,9 @@ int32_t bucket_scatter_capped(skm_ctx *c, uint32_t chunk, const Segment &sg, Buc
                               unsigned long long *d_out, CapLayout lay) {
     zero_async(c, c->d_bucket_cursors, (n_buckets + 1) * sizeof(uint64_t), c->work);
     Span sp(c, ST_PART, c->work);
-    OwnerBases bases{};
-    bases.dst[0] = d_out;
-    bases.uniform = 1;
-    bases.log2_regions = fn.log2_regions;
     bucket_scatter_kernel<true><<<grid_for(sg.n_units, kScatterThreads), kScatterThreads,
                                   scatter_smem_bytes(n_buckets, true), c->work>>>(
-        sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, bases, lay, &c->d_cc[chunk]);
+        sg.codes, sg.breaks, 0, sg.n_units, c->p.k, fn, n_buckets, c->d_bucket_cursors, d_out, lay, &c->d_cc[chunk]);
     c->launches++;
     c->stage_launches[ST_PART]++;
     CU(cudaGetLastError());
@@ -1981,14 +1969,18 @@ static int32_t finalize_common(skm_ctx *c) {
     };
     const uint32_t pbits_now = c->log2cap - kPartLog2, g1_now = route_log2_regions(c);
     const uint64_t nbr_now = pbits_now >= g1_now ? 1ull : (1ull << (g1_now - pbits_now));
-    uint64_t positions_all = 0, group_positions = 0;
+    uint64_t positions_all = 0, group_positions = 0, positions_seen = 0;
     for (auto &cs : c->chunks) positions_all += cs.n_bytes;
     const bool early_flush = !getenv("SKM_NO_EARLY_FLUSH");
     for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
         ChunkState &cs = c->chunks[ch];
         // Host-fed input that is still on its way over PCIe: rather than idle until the last batch has arrived,
-        // count what is listed so far (one more pass over the table, hidden behind the copies).
-        if (early_flush && !group.empty() && group_positions >= std::max<uint64_t>(64ull << 20, positions_all / 4)) {
+        // count what is listed so far (one more pass over the table, hidden behind the copies).  Only while a
+        // good part of the input is still to come: a launch just before the last batch lands costs a table
+        // pass and holds the SMs when that batch wants to be bucketed (measured: 3 + 6 + 1 chunks 50.7 ms,
+        // 3 + 7 chunks 48.0 ms end to end on C2).
+        if (early_flush && !group.empty() && group_positions >= std::max<uint64_t>(64ull << 20, positions_all / 4) &&
+            positions_all - positions_seen >= positions_all / 4) {
             bool arriving = false;
             for (auto &sg : cs.segs)
                 if (sg.copied && cudaEventQuery(sg.copied) == cudaErrorNotReady) arriving = true;
@@ -2000,6 +1992,7 @@ static int32_t finalize_common(skm_ctx *c) {
             }
         }
         group_positions += cs.n_bytes;
+        positions_seen += cs.n_bytes;
         for (auto &sg : cs.segs) {
             if (!sg.ready) continue;
             if (sg.list) CU(cudaEventSynchronize(sg.ready));      // host needs the bucket totals

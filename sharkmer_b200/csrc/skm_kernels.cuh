@@ -1062,13 +1062,22 @@ bucket_scan_kernel(const unsigned long long *__restrict__ counts, uint32_t n_buc
 // shared memory, then copied out so that consecutive threads write consecutive cells of a
 // bucket run (whole 32-byte sectors / 128-byte lines instead of lone 8-byte stores, which cost
 // one L2 request each).  One CTA = kScatterThreads units = kScatterThreads*32 bases.
-static constexpr uint32_t kMaxBuckets = 1024;  // scatter stages a CTA's k-mers in bucket order: runs stay >= 12 k-mers
-static constexpr uint32_t kScatterThreads = 384;                    // 12288 positions per CTA
+//
+// The kernel is bound by instruction issue, so every k-mer is hashed ONCE: round 1 extracts the
+// unit's windows, hashes them, and takes each k-mer's rank inside its bucket from the one
+// shared-memory atomic that also counts the bucket; (bucket, rank) of the unit's 32 windows stay in
+// registers.  After the scan of the bucket counts, round 2 re-extracts (a rolling update, no hash,
+// no atomic) and drops every k-mer at start[bucket] + rank, with its bucket id beside it (u16), so
+// the copy-out needs no hash either.
+static constexpr uint32_t kMaxBuckets = 1024;  // scatter stages a CTA's k-mers in bucket order: runs stay >= 10 k-mers
+static constexpr uint32_t kScatterThreads = 320;                    // 10240 positions per CTA
 static constexpr uint32_t kScatterStage = kScatterThreads * 32;     // max k-mers per CTA
 
 __host__ __device__ inline size_t scatter_smem_bytes(uint32_t n_buckets, bool capped = false) {
-    // staging (u64) | exact: s_gbase (u64) + s_cs (u32) | capped: s_cs, s_g, s_room, s_obase (u32 each)
-    return (size_t)kScatterStage * 8 + (size_t)n_buckets * (capped ? 16 : 12);
+    // stage (u64) + bucket ids (u16) | per bucket 8 B (exact: s_gbase u64; capped: count / s_g, s_obase u32) +
+    // s_room u16 + s_start u16.  112 KiB at 1024 buckets: two CTAs per SM.
+    (void)capped;
+    return (size_t)kScatterStage * 10 + (size_t)n_buckets * 12;
 }
 
 // Capped layout (single GPU, no counting pass): bucket b owns cells [b * cap, (b + 1) * cap) of the
@@ -1080,62 +1089,94 @@ struct CapLayout {
     unsigned long long cap, ovf_base, ovf_cap;
 };
 
-// Where each owner's buckets go.  dst[o] is biased so that `dst[o] + global cursor value` is the
-// right cell: on one GPU every entry is the local list; in the fused multi-GPU route entry o is
-// rank o's receive arena mapped through CUDA IPC, and the copy-out loop below becomes the
-// NVLink transfer (contiguous runs of a bucket => full-width peer stores), overlapped tile by
-// tile with the extraction of the other CTAs.
-static constexpr uint32_t kMaxP2PRanks = 16;
-struct OwnerBases {
-    unsigned long long *dst[kMaxP2PRanks];
-    uint32_t log2_regions;  // bucket >> log2_regions = owner
-    uint32_t uniform;       // 1 => all owners share dst[0]
-};
+// The state machine of extract_unit with the loop fully unrolled (j is a compile-time constant in
+// `emit`, so per-window values can live in a register array).  kValidity = false: the caller knows
+// which windows exist (round 2) and only wants the canonical k-mer of every position.
+// The reverse strand is kept top-aligned (newest complement at bits 63:62), so its update is a
+// constant shift; one shift by 64 - 2k brings the window down when it is emitted.
+template <bool kValidity, class Emit>
+__device__ __forceinline__ void extract_unit_unrolled(const UnitInput &in, uint32_t k, Emit &&emit) {
+    const uint64_t kmask = (1ull << (2 * k)) - 1;  // k <= 31
+    const uint32_t down = 64 - 2 * k;
+    uint64_t fwd = in.prev;
+    uint64_t rev_top = rc64(in.prev);
+    uint32_t n_valid = in.prev_inv ? (uint32_t)(__ffs(in.prev_inv) - 1) : 32u;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const uint64_t b = (in.cur >> (62 - 2 * j)) & 3ull;
+        fwd = (fwd << 2) | b;
+        rev_top = (rev_top >> 2) | ((3ull - b) << 62);
+        bool have = true;
+        if (kValidity) {
+            const bool brk = (in.inv >> (31 - j)) & 1u;
+            n_valid = brk ? 0u : n_valid + 1u;
+            have = n_valid >= k;
+        }
+        const uint64_t f = fwd & kmask, r = rev_top >> down;
+        emit(f < r ? f : r, j, have);
+    }
+}
+
+static constexpr uint32_t kScatterPer = (kMaxBuckets + kScatterThreads - 1) / kScatterThreads;  // buckets per thread
+static constexpr uint32_t kScatterRankShift = 10;   // (bucket | rank << 10): kMaxBuckets = 2^10, ranks < kScatterStage < 2^14
+static_assert(kMaxBuckets <= (1u << kScatterRankShift) && kScatterStage < (1u << 16), "bucket, rank and stage offsets share small words");
 
 // kCapped = false: cursors[] start at the exact bucket offsets of the counting pass.
 // kCapped = true : cursors[] start at 0 and end as the bucket totals (cursors[n_buckets] = overflow
-//                  total); the CTA also adds its windows to cc->n_windows (no counting pass did).
-static constexpr uint32_t kScatterPer = (kMaxBuckets + kScatterThreads - 1) / kScatterThreads;  // buckets per thread
-static_assert(kScatterStage < (1u << 16), "stage offsets and ranks share one 32-bit word");
-
+//                  total); also counts the windows of the chunk (the exact path does that in pass 1).
 template <bool kCapped>
-__global__ void __launch_bounds__(kScatterThreads, 5)  // <= 32 registers: one CTA fits beside the inserts
+__global__ void __launch_bounds__(kScatterThreads, 2)
 bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ breaks,
                       uint64_t u_begin, uint64_t u_end, uint32_t k, BucketFn fn, uint32_t n_buckets,
-                      unsigned long long *__restrict__ cursors, OwnerBases bases, CapLayout lay,
+                      unsigned long long *__restrict__ cursors, unsigned long long *__restrict__ out, CapLayout lay,
                       ChunkCounters *__restrict__ cc) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long *stage = reinterpret_cast<unsigned long long *>(s_raw);
-    unsigned long long *s_gbase = stage + kScatterStage;  // exact: first list cell of this CTA's run
-    // s_cs[b]: round 1 = this CTA's count of bucket b; afterwards (start in the stage << 16) | rank
-    uint32_t *s_cs = reinterpret_cast<uint32_t *>(s_gbase + (kCapped ? 0 : n_buckets));
-    uint32_t *s_g = s_cs + n_buckets;       // capped: the run's first cell inside the bucket's region
-    uint32_t *s_room = s_g + n_buckets;     // capped: how many of the run's k-mers fit the region
-    uint32_t *s_obase = s_room + n_buckets; // capped: first overflow cell of the others
+    uint16_t *stage_b = reinterpret_cast<uint16_t *>(stage + kScatterStage);       // bucket of every staged k-mer
+    unsigned char *per_bucket = reinterpret_cast<unsigned char *>(stage_b + kScatterStage);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(per_bucket);            // round 1: this CTA's count per bucket
+    // (a thread reads the counts of ITS buckets into registers, everybody passes a barrier, and only then
+    //  are the arrays below, which overlay the counts, written)
+    unsigned long long *s_gbase = reinterpret_cast<unsigned long long *>(per_bucket);   // exact: first list cell of the run
+    uint32_t *s_g = cnt;                        // capped: the run's first cell inside the bucket's region
+    uint32_t *s_obase = cnt + n_buckets;        // capped: first overflow cell of what does not fit
+    uint16_t *s_room = reinterpret_cast<uint16_t *>(per_bucket + (size_t)8 * n_buckets);  // capped: how many of the run fit
+    uint16_t *s_start = s_room + n_buckets;     // first stage slot of the bucket
     __shared__ uint32_t s_warp_tot[kScatterThreads / 32];
 
-    for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) s_cs[i] = 0;
+    for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
     const uint64_t u = u_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const UnitInput in = load_unit(codes, breaks, u, u_end);
-    // round 1: this CTA's count per bucket
-    extract_unit(in, k, [&](uint64_t kmer, int) { atomicAdd(&s_cs[fn(kmer)], 1u); });
+    const bool has_bases = in.inv != 0xFFFFFFFFu;
+    // round 1: hash, count, rank
+    uint32_t br[32];
+    if (has_bases) {
+        extract_unit_unrolled<true>(in, k, [&](uint64_t kmer, int j, bool have) {
+            uint32_t v = 0xFFFFFFFFu;
+            if (have) {
+                const uint32_t b = fn(kmer);
+                v = b | (atomicAdd(&cnt[b], 1u) << kScatterRankShift);
+            }
+            br[j] = v;
+        });
+    }
     __syncthreads();
     // exclusive scan of the counts (bucket starts inside the stage) + global reservation; the
     // reservations of a thread's buckets are all issued before any result is used
     const uint32_t per = (n_buckets + blockDim.x - 1) / blockDim.x;  // <= kScatterPer
     const uint32_t b0 = threadIdx.x * per;
-    uint32_t cnt[kScatterPer];
+    uint32_t c_[kScatterPer];
     unsigned long long g[kScatterPer];
     uint32_t mine = 0;
 #pragma unroll
     for (uint32_t j = 0; j < kScatterPer; j++) {
-        cnt[j] = (j < per && b0 + j < n_buckets) ? s_cs[b0 + j] : 0u;
-        mine += cnt[j];
+        c_[j] = (j < per && b0 + j < n_buckets) ? cnt[b0 + j] : 0u;
+        mine += c_[j];
     }
 #pragma unroll
     for (uint32_t j = 0; j < kScatterPer; j++)
-        g[j] = cnt[j] ? atomicAdd(&cursors[b0 + j], (unsigned long long)cnt[j]) : 0ull;
+        g[j] = c_[j] ? atomicAdd(&cursors[b0 + j], (unsigned long long)c_[j]) : 0ull;
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1143,7 +1184,7 @@ bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__rest
         if ((threadIdx.x & 31) >= (uint32_t)o) incl += t;
     }
     if ((threadIdx.x & 31) == 31) s_warp_tot[threadIdx.x >> 5] = incl;
-    __syncthreads();
+    __syncthreads();   // (every count has been read: the overlays may be written)
     uint32_t warp_off = 0;
     for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) warp_off += s_warp_tot[w];
     uint32_t run = warp_off + incl - mine;
@@ -1151,43 +1192,55 @@ bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__rest
     for (uint32_t j = 0; j < kScatterPer; j++) {
         const uint32_t i = b0 + j;
         if (j < per && i < n_buckets) {
-            if (kCapped) {
-                const uint32_t room = g[j] >= lay.cap ? 0u : (uint32_t)min((unsigned long long)cnt[j], lay.cap - g[j]);
-                s_g[i] = (uint32_t)min(g[j], lay.cap);
-                s_room[i] = room;
-                s_obase[i] = cnt[j] > room
-                                 ? (uint32_t)min(atomicAdd(&cursors[n_buckets], (unsigned long long)(cnt[j] - room)),
-                                                 0xffff0000ull)
-                                 : 0u;
-            } else {
-                s_gbase[i] = g[j];
-            }
-            s_cs[i] = run << 16;
-            run += cnt[j];
+            s_start[i] = (uint16_t)run;
+            run += c_[j];
         }
     }
     __syncthreads();
     uint32_t total = 0;
     for (uint32_t w = 0; w < kScatterThreads / 32; w++) total += s_warp_tot[w];
-    // round 2: re-extract (ALU is free here) and place every k-mer at its bucket-ordered stage slot
-    extract_unit(in, k, [&](uint64_t kmer, int) {
-        const uint32_t cs = atomicAdd(&s_cs[fn(kmer)], 1u);
-        stage[(cs >> 16) + (cs & 0xffffu)] = kmer;
-    });
+    // round 2: re-extract and place every k-mer at its bucket-ordered stage slot.  (The global reservations
+    // g[] are first used after this round: their round trip to L2 is hidden behind it.)
+    if (has_bases) {
+        extract_unit_unrolled<false>(in, k, [&](uint64_t kmer, int j, bool) {
+            const uint32_t v = br[j];
+            if (v != 0xFFFFFFFFu) {
+                const uint32_t b = v & ((1u << kScatterRankShift) - 1u);
+                const uint32_t at = (uint32_t)s_start[b] + (v >> kScatterRankShift);
+                stage[at] = kmer;
+                stage_b[at] = (uint16_t)b;
+            }
+        });
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < kScatterPer; j++) {
+        const uint32_t i = b0 + j;
+        if (j < per && i < n_buckets) {
+            if (kCapped) {
+                const uint32_t room = g[j] >= lay.cap ? 0u : (uint32_t)min((unsigned long long)c_[j], lay.cap - g[j]);
+                s_g[i] = (uint32_t)min(g[j], lay.cap);
+                s_room[i] = (uint16_t)room;
+                s_obase[i] = c_[j] > room
+                                 ? (uint32_t)min(atomicAdd(&cursors[n_buckets], (unsigned long long)(c_[j] - room)),
+                                                 0xffff0000ull)
+                                 : 0u;
+            } else {
+                s_gbase[i] = g[j];
+            }
+        }
+    }
     __syncthreads();
-    // copy-out: stage position p belongs to bucket fn(kmer); consecutive threads write consecutive
-    // cells of a bucket run
+    // copy-out: consecutive threads write consecutive cells of a bucket run
     for (uint32_t p = threadIdx.x; p < total; p += blockDim.x) {
         const unsigned long long kmer = stage[p];
-        const uint32_t b = fn(kmer);
-        const uint32_t rel = p - (s_cs[b] >> 16);
-        unsigned long long *out = bases.dst[bases.uniform ? 0u : (b >> bases.log2_regions)];
+        const uint32_t b = stage_b[p];
+        const uint32_t rel = p - (uint32_t)s_start[b];
         if (!kCapped) {
             out[s_gbase[b] + rel] = kmer;
-        } else if (rel < s_room[b]) {
+        } else if (rel < (uint32_t)s_room[b]) {
             out[(unsigned long long)b * lay.cap + s_g[b] + rel] = kmer;
         } else {
-            const unsigned long long o = (unsigned long long)s_obase[b] + (rel - s_room[b]);
+            const unsigned long long o = (unsigned long long)s_obase[b] + (rel - (uint32_t)s_room[b]);
             if (o < lay.ovf_cap) out[lay.ovf_base + o] = kmer;  // else: dropped, the host re-buckets the batch
         }
     }
