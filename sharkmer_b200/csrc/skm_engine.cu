@@ -41,7 +41,7 @@ enum Stage { ST_H2D, ST_PACK, ST_COUNT, ST_PART, ST_INSERT, ST_HISTO, ST_GROW, S
 // stays here; the others are shipped whole into the owners' receive arenas.
 struct OwnerList {
     unsigned long long *list = nullptr, *meta = nullptr;
-    uint16_t *tile_off = nullptr;
+    tile_off_t *tile_off = nullptr;
     uint32_t max_tiles = 0;
     uint64_t cap = 0;           // capped layout: cells per bucket (0 = exact layout)
     size_t cells = 0;
@@ -68,7 +68,7 @@ struct Segment {
     size_t list_cells = 0;  // cells allocated for `list`
     // tile-sorted form (tiled insert): where the buckets' tiles are + the sub-bucket offsets of every tile
     unsigned long long *meta = nullptr;   // ListMeta arrays (list_meta_words(n_buckets) words)
-    uint16_t *tile_off = nullptr;         // max_tiles * (2^g2 + 1)
+    tile_off_t *tile_off = nullptr;       // max_tiles * (2^g2 + 1)
     uint32_t max_tiles = 0;
     bool tiled = false;
     cudaEvent_t copied = nullptr;   // host-fed batch: fires when its host-to-device copy has finished
@@ -218,6 +218,11 @@ struct skm_ctx {
 
     // tiled insert (tile_insert_kernel)
     uint32_t g2 = 7;                         // sub-bucket bits of the lists built by this ctx
+    uint32_t tile_log2 = kTileLog2;          // cells per tile of those lists: 2^13 (one CTA sorts a tile) .. 2^16 (a cluster
+                                             // of 8 does), SKM_TILE_LOG2
+    bool mg_slices = true;                   // multi-GPU: an owner gets its SLICE of the sender's one list, sorted by a
+                                             // cluster straight down to the owner's partitions (SKM_MG_SLICES=0: every
+                                             // owner's slice is re-bucketed into a list of its own first)
     bool table_fresh = true;                 // logically empty: no key was ever inserted since create / reset
     bool table_zombie = false;               // logically empty but NOT physically cleared (skm_reset defers the clear:
                                              // the tiled insert starts every partition empty and rewrites the whole table)
@@ -874,7 +879,7 @@ void release_list(skm_ctx *c, Segment &sg, cudaStream_t st) {
     if (sg.meta) buf_free(c, sg.meta, st);
     if (sg.tile_off) {
         buf_free(c, sg.tile_off, st);
-        c->list_bytes -= std::min<size_t>(c->list_bytes, (size_t)sg.max_tiles * ((1u << c->g2) + 1) * sizeof(uint16_t));
+        c->list_bytes -= std::min<size_t>(c->list_bytes, (size_t)sg.max_tiles * ((1u << c->g2) + 1) * sizeof(tile_off_t));
     }
     if (sg.d_counts) cudaFreeAsync(sg.d_counts, st);
     for (auto &ol : sg.owners) {
@@ -896,8 +901,42 @@ void release_list(skm_ctx *c, Segment &sg, cudaStream_t st) {
 
 // geometry of the lists the insert kernel reads: on one GPU the buckets of pass A are the table regions; across
 // GPUs every owner's slice is re-bucketed into kFineRegions regions of that owner (tile_rebucket_kernel)
-uint32_t list_log2_regions(const skm_ctx *c) { return c->n_ranks > 1 ? kFineLog2 : route_log2_regions(c); }
+uint32_t list_log2_regions(const skm_ctx *c) { return c->n_ranks > 1 && !c->mg_slices ? kFineLog2 : route_log2_regions(c); }
+uint32_t list_tile_log2(const skm_ctx *c) { return c->n_ranks > 1 && !c->mg_slices ? kTileLog2 : c->tile_log2; }
 ListGeom list_geom(const skm_ctx *c) { return ListGeom{c->n_ranks, list_log2_regions(c), c->g2}; }
+
+// Pass B over `tiles` tile slots of 2^tile_log2 cells: one CTA per tile, or a cluster of 2^(tile_log2 - 13) CTAs
+template <int C>
+cudaError_t launch_cluster_sort(uint32_t tiles, cudaStream_t st, unsigned long long *list, ListMeta m, uint32_t nb, ListGeom geom,
+                                tile_off_t *tile_off) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tiles * (uint32_t)C);
+    cfg.blockDim = dim3(kSortThreads);
+    cfg.dynamicSmemBytes = tile_sort_cluster_smem_bytes();
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tile_sort_cluster_kernel<C>, list, m, nb, geom, tile_off);
+}
+
+cudaError_t launch_tile_sort(uint32_t tile_log2, uint32_t g2, uint32_t tiles, cudaStream_t st, unsigned long long *list, ListMeta m,
+                             uint32_t nb, ListGeom geom, tile_off_t *tile_off) {
+    if (tiles == 0) return cudaSuccess;
+    switch (tile_log2) {
+        case kTileLog2:
+            tile_sort_kernel<<<tiles, kSortThreads, tile_sort_smem_bytes(g2), st>>>(list, m, nb, geom, tile_off);
+            return cudaGetLastError();
+        case kTileLog2 + 1: return launch_cluster_sort<2>(tiles, st, list, m, nb, geom, tile_off);
+        case kTileLog2 + 2: return launch_cluster_sort<4>(tiles, st, list, m, nb, geom, tile_off);
+        case kTileLog2 + 3: return launch_cluster_sort<8>(tiles, st, list, m, nb, geom, tile_off);
+        default: return cudaErrorInvalidValue;
+    }
+}
 
 // Passes A and B for one packed segment, on c->work: bucket its k-mers by (owner, table region)
 // into a list — capped one-pass layout, or exact two-pass layout — then sort every tile of every
@@ -912,25 +951,27 @@ int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off
     CapLayout lay{};
     size_t cells;
     uint32_t tpb = 0, max_tiles;
+    const uint32_t tl = list_tile_log2(c);
+    const uint64_t T = 1ull << tl;
     if (!exact) {
         lay.cap = ((sg.n_bytes / nb + sg.n_bytes / (16ull * nb) + 1024) + 15) & ~15ull;
         lay.ovf_base = lay.cap * nb;
         lay.ovf_cap = 4096;  // any k-mer that lands here sends the segment to the exact path
         cells = (size_t)(lay.ovf_base + lay.ovf_cap);
-        tpb = (uint32_t)((lay.cap + kTile - 1) / kTile);
+        tpb = (uint32_t)((lay.cap + T - 1) / T);
         max_tiles = nb * tpb;
     } else {
         cells = sg.n_bytes;
-        max_tiles = (uint32_t)(sg.n_bytes / kTile) + nb + 1;
+        max_tiles = (uint32_t)(sg.n_bytes / T) + nb + 1;
     }
-    const size_t off_bytes = sort ? (size_t)max_tiles * (F + 1) * sizeof(uint16_t) : 16;
+    const size_t off_bytes = sort ? (size_t)max_tiles * (F + 1) * sizeof(tile_off_t) : 16;
     const size_t need = cells * 8 + off_bytes;
     // budget = device memory that was free when the ctx was created (no cudaMemGetInfo here: it would serialise
     // the ingest path); room is kept for `reserve_tables` tables of the current size (growth) plus slack
     if (!must && c->list_bytes + need + (size_t)reserve_tables * c->capacity * sizeof(Slot) + (4ull << 30) > c->mem_budget) return SKM_OK;
     CU(cudaStreamWaitEvent(c->work, sg.ready, 0));
     unsigned long long *list = nullptr, *meta = nullptr;
-    uint16_t *tile_off = nullptr;
+    tile_off_t *tile_off = nullptr;
     HostTimer t_malloc(&c->host_ms[4]);
     if (buf_alloc(c, (void **)&list, cells * sizeof(uint64_t), c->work) != cudaSuccess ||
         buf_alloc(c, (void **)&tile_off, off_bytes, c->work) != cudaSuccess ||
@@ -957,7 +998,7 @@ int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off
         rc = bucket_scatter_capped(c, chunk, sg, fn, nb, sg.list, lay);
         if (rc) return rc;
         copy_words_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_cursors, (unsigned long long *)h_off, nb + 1);
-        tile_plan_kernel<<<1, 1024, 0, c->work>>>(c->d_bucket_cursors, nb, lay.cap, tpb, m);
+        tile_plan_kernel<<<1, 1024, 0, c->work>>>(c->d_bucket_cursors, nb, lay.cap, tpb, m, tl);
         c->launches += 2;
         sg.cap = lay.cap;
         sg.ovf_cap = 0;  // capped lists have no usable overflow run: h_offsets[nb] > 0 => rebuild exactly
@@ -967,7 +1008,7 @@ int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off
         rc = bucket_scatter(c, chunk, seg_index, seg_index + 1, fn, nb, sg.list);
         if (rc) return rc;
         copy_words_kernel<<<4, 256, 0, c->work>>>(c->d_bucket_offsets, (unsigned long long *)h_off, nb + 1);
-        tile_plan_kernel<<<1, 1024, 0, c->work>>>(c->d_bucket_offsets, nb, 0ull, 0u, m);
+        tile_plan_kernel<<<1, 1024, 0, c->work>>>(c->d_bucket_offsets, nb, 0ull, 0u, m, tl);
         c->launches += 2;
         sg.cap = 0;
         CU(cudaFreeAsync(sg.codes, c->work));
@@ -990,7 +1031,7 @@ int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off
     }
     {
         Span sp(c, ST_SORT, sort_st);
-        tile_sort_kernel<<<max_tiles, kSortThreads, tile_sort_smem_bytes(c->g2), sort_st>>>(sg.list, m, nb, list_geom(c), sg.tile_off);
+        CU(launch_tile_sort(tl, c->g2, max_tiles, sort_st, sg.list, m, nb, list_geom(c), sg.tile_off));
         c->launches++;
         c->stage_launches[ST_SORT]++;
     }
@@ -1074,6 +1115,7 @@ int32_t launch_tiled(skm_ctx *c, const std::vector<SegDesc> &segs, uint32_t chun
     L.n_ranks = c->n_ranks;
     L.g1 = geom.g1;
     L.g2 = geom.g2;
+    L.tile_log2 = list_tile_log2(c);
     L.segs = (const SegDesc *)c->d_segs;
     L.chunk_first_seg = (const uint32_t *)((const SegDesc *)c->d_segs + n);
     L.n_segs = n;
@@ -1201,6 +1243,7 @@ int32_t launch_tiled(skm_ctx *c, const std::vector<SegDesc> &segs, uint32_t chun
 }
 
 int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on_host);
+int32_t ship_slices(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on_host);
 int32_t refine_owner_lists(skm_ctx *c, uint32_t chunk, size_t seg_index, bool exact);
 
 // Bucket a freshly packed segment by table region right away (single GPU).  The work is queued
@@ -1227,9 +1270,13 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force
     int32_t rc;
     {
         HostTimer t(&c->host_ms[0]);
-        rc = build_list(c, chunk, seg_index, h_off, exact, force, c->p.capacity_hint ? 1 : 3, /*sort=*/c->n_ranks == 1);
+        rc = build_list(c, chunk, seg_index, h_off, exact, force, c->p.capacity_hint ? 1 : 3, /*sort=*/c->n_ranks == 1 || c->mg_slices);
     }
     if (rc || c->n_ranks == 1 || !sg.list) return rc;
+    if (c->mg_slices) {
+        HostTimer t(&c->host_ms[3]);
+        return ship_slices(c, chunk, seg_index, /*sizes_on_host=*/false);  // the exchange starts at ingest time (capped lists)
+    }
     {
         HostTimer t(&c->host_ms[2]);
         rc = refine_owner_lists(c, chunk, seg_index, exact);
@@ -1270,7 +1317,7 @@ int32_t refine_owner_lists(skm_ctx *c, uint32_t chunk, size_t seg_index, bool ex
             ol.max_tiles = (uint32_t)(ol.cells / kTile) + kFineRegions + 1;
         }
         ol.cap = lay.cap;
-        const size_t off_bytes = (size_t)ol.max_tiles * (F + 1) * sizeof(uint16_t);
+        const size_t off_bytes = (size_t)ol.max_tiles * (F + 1) * sizeof(tile_off_t);
         {
             HostTimer t_alloc(&c->host_ms[1]);
             if (buf_alloc(c, (void **)&ol.list, ol.cells * sizeof(uint64_t), c->work) != cudaSuccess ||
@@ -1385,7 +1432,7 @@ int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on
         rec.regions = kFineRegions;
         rec.n_tiles = (uint32_t)n_tiles;
         rec.n_cells = n_cells;
-        const size_t b_cells = n_cells * 8, b_off = n_tiles * (F + 1) * sizeof(uint16_t);
+        const size_t b_cells = n_cells * 8, b_off = n_tiles * (F + 1) * sizeof(tile_off_t);
         const size_t b_cb = (size_t)kFineRegions * 8, b_tb = (size_t)(kFineRegions + 1) * 4;
         if (!take(o, b_cells, &rec.off_cells) || !take(o, b_off, &rec.off_tile_off) || !take(o, b_cb, &rec.off_cell_begin) ||
             !take(o, b_tb, &rec.off_tile_begin))
@@ -1402,6 +1449,76 @@ int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on
         ol.shipped = true;
         c->mg_sent.push_back(rec);
     }
+    return SKM_OK;
+}
+
+// Multi-GPU, slices: the batch has ONE list, bucketed by (owner, coarse region) and tile-sorted down to the owners'
+// partitions; owner o's k-mers are the buckets [o << g1, (o + 1) << g1) — contiguous cells, contiguous tile
+// slots, contiguous metadata.  Each of the four pieces goes to the owner's receive arena as one peer copy; the
+// receiver reads them with SegDesc::rel = 1 (indices relative to the slice's first entries).
+int32_t ship_slices(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on_host) {
+    Segment &sg = c->chunks[chunk].segs[seg_index];
+    if (!sg.list || !sg.tiled || sg.shipped) return SKM_OK;
+    const uint32_t me = c->p.rank, N = c->n_ranks;
+    for (uint32_t o = 0; o < N; o++)
+        if (o != me && !c->mg_peer[o]) return SKM_OK;  // arenas not wired yet: shipped at finalize
+    if (!sg.cap && !sizes_on_host) return SKM_OK;      // exact layout: its offsets are still on their way to the host
+    const uint32_t g1c = route_log2_regions(c), R = 1u << g1c, F = 1u << c->g2, tl = list_tile_log2(c);
+    const uint64_t T = 1ull << tl;
+    // first cell / first tile slot of every owner's slice
+    std::vector<uint64_t> cell0(N + 1), tile0(N + 1);
+    if (sg.cap) {
+        const uint64_t tpb = (sg.cap + T - 1) / T;
+        for (uint32_t o = 0; o <= N; o++) {
+            cell0[o] = (uint64_t)o * R * sg.cap;
+            tile0[o] = (uint64_t)o * R * tpb;
+        }
+    } else {
+        uint64_t tiles = 0;
+        for (uint32_t b = 0; b < sg.n_buckets; b++) {
+            if (b % R == 0) {
+                cell0[b / R] = sg.h_offsets[b];
+                tile0[b / R] = tiles;
+            }
+            tiles += (sg.h_offsets[b + 1] - sg.h_offsets[b] + T - 1) / T;
+        }
+        cell0[N] = sg.h_offsets[sg.n_buckets];
+        tile0[N] = tiles;
+    }
+    auto take = [&](uint32_t o, size_t bytes, uint64_t *off) -> bool {
+        const size_t at = (c->mg_cursor[o] + 255) & ~(size_t)255;
+        if (at + bytes > c->mg_sub_bytes) return false;
+        *off = at;
+        c->mg_cursor[o] = at + bytes;
+        return true;
+    };
+    CU(cudaStreamWaitEvent(c->dma_stream, sg.ready, 0));
+    const ListMeta m = list_meta_at(sg.meta, sg.n_buckets);
+    sg.rec_first = c->mg_sent.size();
+    for (uint32_t i = 1; i < N; i++) {
+        const uint32_t o = (me + i) % N;  // stagger the destinations across ranks
+        MgRecord rec{};
+        rec.src = me;
+        rec.dst = o;
+        rec.chunk = chunk;
+        rec.regions = R;
+        rec.n_tiles = (uint32_t)(tile0[o + 1] - tile0[o]);
+        rec.n_cells = cell0[o + 1] - cell0[o];
+        const size_t b_cells = rec.n_cells * 8, b_off = (size_t)rec.n_tiles * (F + 1) * sizeof(tile_off_t);
+        const size_t b_cb = (size_t)R * 8, b_tb = (size_t)(R + 1) * 4;
+        if (!take(o, b_cells, &rec.off_cells) || !take(o, b_off, &rec.off_tile_off) || !take(o, b_cb, &rec.off_cell_begin) ||
+            !take(o, b_tb, &rec.off_tile_begin))
+            return fail(c, SKM_ERR_OOM, "receive arena of rank %u is too small for rank %u's k-mers (%zu bytes per source): create larger arenas",
+                        o, me, c->mg_sub_bytes);
+        uint8_t *base = c->mg_peer[o] + (size_t)me * c->mg_sub_bytes;
+        if (b_cells) CU(cudaMemcpyAsync(base + rec.off_cells, sg.list + cell0[o], b_cells, cudaMemcpyDefault, c->dma_stream));
+        if (b_off) CU(cudaMemcpyAsync(base + rec.off_tile_off, sg.tile_off + tile0[o] * (F + 1), b_off, cudaMemcpyDefault, c->dma_stream));
+        CU(cudaMemcpyAsync(base + rec.off_cell_begin, m.cell_begin + (size_t)o * R, b_cb, cudaMemcpyDefault, c->dma_stream));
+        CU(cudaMemcpyAsync(base + rec.off_tile_begin, m.tile_begin + (size_t)o * R, b_tb, cudaMemcpyDefault, c->dma_stream));
+        c->mg_bytes_sent += b_cells + b_off + b_cb + b_tb;
+        c->mg_sent.push_back(rec);
+    }
+    sg.shipped = true;
     return SKM_OK;
 }
 
@@ -1646,11 +1763,20 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     // partitions (one sub-bucket per partition); without one, 2^7 sub-buckets per region — a
     // partition then covers several adjacent sub-buckets, or filters a shared one
     {
+        if (const char *g = getenv("SKM_MG_SLICES")) c->mg_slices = atoi(g) != 0;
+        // tile size: one CTA sorts 2^13 k-mers; a cluster of 2 / 4 / 8 CTAs sorts 2^14 / 2^15 / 2^16 as one tile.
+        // Multi-GPU slices need the large tile: an owner's coarse bucket is sorted by log2(n_ranks) more bits.
+        c->tile_log2 = c->n_ranks > 1 && c->mg_slices ? kMaxTileLog2 : kTileLog2;
+        if (const char *g = getenv("SKM_TILE_LOG2")) c->tile_log2 = (uint32_t)std::max<int>(kTileLog2, std::min<int>(atoi(g), kMaxTileLog2));
         const int g1 = (int)list_log2_regions(c);
-        int g2 = c->p.capacity_hint ? (int)l2 - (int)kPartLog2 - g1 : 7;
+        // without a hint: as fine as the partitions of a 2^29-slot table (2^17 of them)
+        int g2 = c->p.capacity_hint ? (int)l2 - (int)kPartLog2 - g1 : 17 - g1;
         if (const char *g = getenv("SKM_G2")) g2 = atoi(g);
         c->g2 = (uint32_t)std::max(0, std::min<int>(g2, (int)kMaxSubLog2));
     }
+    CU(cudaFuncSetAttribute(tile_sort_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_sort_cluster_smem_bytes()));
+    CU(cudaFuncSetAttribute(tile_sort_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_sort_cluster_smem_bytes()));
+    CU(cudaFuncSetAttribute(tile_sort_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_sort_cluster_smem_bytes()));
     CU(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)tile_sort_smem_bytes(kMaxSubLog2)));
     CU(cudaFuncSetAttribute(tile_sort_owners_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2707,7 +2833,56 @@ int32_t mg_prepare_local(skm_ctx *c) {
         CU(cudaEventSynchronize(sg.ready));
         return SKM_OK;
     };
-    for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
+    // k-mers of owner o in a list bucketed by (owner, coarse region), from its bucket totals / offsets
+    const uint32_t R = 1u << route_log2_regions(c);
+    auto owner_kmers = [&](const Segment &sg, uint32_t o) -> uint64_t {
+        uint64_t nk = 0;
+        for (uint32_t b = o * R; b < (o + 1) * R; b++)
+            nk += sg.cap ? std::min<uint64_t>(sg.h_offsets[b], sg.cap) : sg.h_offsets[b + 1] - sg.h_offsets[b];
+        return nk;
+    };
+    for (uint32_t ch = 0; ch < c->n_chunks && c->mg_slices; ch++) {
+        ChunkState &cs = c->chunks[ch];
+        for (size_t si = 0; si < cs.segs.size(); si++) {
+            Segment &sg = cs.segs[si];
+            auto build_sorted = [&](bool exact) -> int32_t {
+                uint64_t *h_off = alloc_offsets(c, nb_coarse + 1);
+                if (!h_off) return fail(c, SKM_ERR_OOM, "pinned allocation failed");
+                return build_list(c, ch, si, h_off, exact || !c->capped || sg.n_bytes / nb_coarse < 4096, /*must=*/true, 1, /*sort=*/true);
+            };
+            if (!sg.list && sg.codes) {  // skipped at ingest time (memory): build it now
+                rc = build_sorted(false);
+                if (rc) return rc;
+            }
+            if (!sg.list) continue;
+            CU(cudaEventSynchronize(sg.ready));   // the bucket totals are on the host
+            if (sg.cap && sg.h_offsets[sg.n_buckets] > 0) {
+                // the capped layout overflowed (heavily repeated k-mers): what was shipped is void; rebuild the
+                // batch with the exact layout from the packed form and ship that
+                if (sg.shipped)
+                    for (uint32_t i = 0; i + 1 < c->n_ranks; i++) c->mg_sent[sg.rec_first + i].dead = 1;
+                CU(cudaStreamSynchronize(c->dma_stream));  // the copies still read the old list
+                rc = drop_capped_list(c, ch, sg, c->part_stream);
+                if (rc) return rc;
+                sg.shipped = false;
+                c->n_capped_fallbacks++;
+                rc = build_sorted(true);
+                if (rc) return rc;
+                CU(cudaEventSynchronize(sg.ready));
+            }
+            rc = ship_slices(c, ch, si, /*sizes_on_host=*/true);
+            if (rc) return rc;
+            if (!sg.shipped) return fail(c, SKM_ERR_STATE, "receive arenas are not wired (skm_mg_open_peer / skm_mg_set_peer for every peer)");
+            for (uint32_t i = 1; i < c->n_ranks; i++) c->mg_sent[sg.rec_first + i - 1].n_kmers = owner_kmers(sg, (c->p.rank + i) % c->n_ranks);
+            if (sg.codes) {  // the packed form was kept for the overflow retry only
+                CU(cudaFreeAsync(sg.codes, c->part_stream));
+                CU(cudaFreeAsync(sg.breaks, c->part_stream));
+                sg.codes = nullptr;
+                sg.breaks = nullptr;
+            }
+        }
+    }
+    for (uint32_t ch = 0; ch < c->n_chunks && !c->mg_slices; ch++) {
         ChunkState &cs = c->chunks[ch];
         for (size_t si = 0; si < cs.segs.size(); si++) {
             Segment &sg = cs.segs[si];
@@ -2828,7 +3003,18 @@ int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm, bool final) {
     std::vector<Item> items;
     const uint32_t g1 = list_log2_regions(c);
     uint64_t kmers_mine = 0;
-    for (uint32_t ch = 0; ch < c->n_chunks; ch++)
+    for (uint32_t ch = 0; ch < c->n_chunks && c->mg_slices; ch++)
+        for (auto &sg : c->chunks[ch].segs) {
+            if (!sg.list || !sg.tiled) continue;
+            // this rank's own slice of its own list, read in place (bucket0 = rank << g1)
+            uint64_t nk = 0;
+            const uint32_t R = 1u << g1;
+            for (uint32_t b = me * R; b < (me + 1) * R; b++)
+                nk += sg.cap ? std::min<uint64_t>(sg.h_offsets[b], sg.cap) : sg.h_offsets[b + 1] - sg.h_offsets[b];
+            items.push_back(Item{local_desc(c, sg, 0u), ch, nk});
+            kmers_mine += nk;
+        }
+    for (uint32_t ch = 0; ch < c->n_chunks && !c->mg_slices; ch++)
         for (auto &sg : c->chunks[ch].segs) {
             if (sg.owners.empty()) continue;
             const OwnerList &ol = sg.owners[me];
@@ -2847,11 +3033,13 @@ int32_t mg_finalize_impl(skm_ctx *c, const skm_comm *comm, bool final) {
             uint8_t *base = c->mg_arena + (size_t)src * c->mg_sub_bytes;
             SegDesc d{};
             d.list = (const unsigned long long *)(base + rec.off_cells);
-            d.tile_off = (const uint16_t *)(base + rec.off_tile_off);
+            d.tile_off = (const tile_off_t *)(base + rec.off_tile_off);
             d.tile_begin = (const uint32_t *)(base + rec.off_tile_begin);
             d.cell_begin = (const unsigned long long *)(base + rec.off_cell_begin);
             d.bucket0 = 0;
-            d.rel = 0;   // a whole owner list: its metadata is in the receiver's numbering already
+            // slices: the arrays are the sender's, cut at this owner's first bucket (indices relative to entry 0);
+            // a whole owner list has its metadata in the receiver's numbering already
+            d.rel = c->mg_slices ? 1u : 0u;
             items.push_back(Item{d, rec.chunk, rec.n_kmers});
             kmers_mine += rec.n_kmers;
         }

@@ -18,6 +18,7 @@
 // sector access); no tensor cores are involved.
 #pragma once
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -1268,7 +1269,10 @@ bucket_scatter_kernel(const uint64_t *__restrict__ codes, const uint32_t *__rest
 //   larger table shares a sub-bucket with its neighbours and filters by home slot.
 // ---------------------------------------------------------------------------
 
-static constexpr uint32_t kTile = 8192;                       // k-mers per tile (64 KiB)
+static constexpr uint32_t kTileLog2 = 13;
+static constexpr uint32_t kTile = 1u << kTileLog2;            // k-mers one CTA sorts (64 KiB)
+static constexpr uint32_t kMaxTileLog2 = 16;                  // a cluster of 8 CTAs sorts 65536 k-mers as ONE tile
+typedef uint32_t tile_off_t;                                  // sub-bucket offsets inside a tile (<= 2^16 inclusive)
 static constexpr uint32_t kSortThreads = 512;
 static constexpr uint32_t kSortPer = kTile / kSortThreads;    // k-mers per thread
 static constexpr uint32_t kMaxSubLog2 = 10;                   // g2 <= 10: sub-bucket and rank share a 32-bit word
@@ -1288,7 +1292,8 @@ struct ListGeom {
 // Where the tiles of a bucketed list are (device arrays, one set per list):
 //   cell_begin[b]  first cell of bucket b          bucket_n[b]  k-mers in bucket b
 //   tile_begin[b]  index of bucket b's first tile; tile_begin[nb] = number of tiles
-// Tile t of bucket b covers cells [cell_begin[b] + j*kTile, +min(kTile, bucket_n[b] - j*kTile)),
+// Tile t of bucket b covers cells [cell_begin[b] + j*T, +min(T, bucket_n[b] - j*T)), T = 2^tile_log2 (a
+// property of the list: kTile when one CTA sorts a tile, up to 2^kMaxTileLog2 when a cluster does),
 // j = t - tile_begin[b]; a tile past the end of its bucket is empty (capped layout: every bucket
 // owns the same number of tile slots).
 struct ListMeta {
@@ -1308,11 +1313,12 @@ __host__ __device__ inline ListMeta list_meta_at(unsigned long long *base, uint3
 // src: capped layout (cap > 0) = the scatter kernel's per-bucket totals; exact layout (cap == 0) =
 // the nb+1 bucket offsets.  One CTA of 1024 threads.
 __device__ __forceinline__ void tile_plan_body(const unsigned long long *__restrict__ src, uint32_t nb,
-                                               unsigned long long cap, uint32_t tiles_per_bucket, ListMeta m);
+                                               unsigned long long cap, uint32_t tiles_per_bucket, ListMeta m,
+                                               uint32_t tile_log2);
 __global__ void __launch_bounds__(1024)
 tile_plan_kernel(const unsigned long long *__restrict__ src, uint32_t nb, unsigned long long cap,
-                 uint32_t tiles_per_bucket, ListMeta m) {
-    tile_plan_body(src, nb, cap, tiles_per_bucket, m);
+                 uint32_t tiles_per_bucket, ListMeta m, uint32_t tile_log2) {
+    tile_plan_body(src, nb, cap, tiles_per_bucket, m, tile_log2);
 }
 
 // The lists of all owners of one batch (multi-GPU sender): one launch serves them all.
@@ -1320,18 +1326,19 @@ static constexpr uint32_t kMaxOwners = 16;
 struct OwnerArrays {
     unsigned long long *list[kMaxOwners];
     unsigned long long *meta[kMaxOwners];   // list_meta_words(nb) words each
-    uint16_t *tile_off[kMaxOwners];
+    tile_off_t *tile_off[kMaxOwners];
 };
 
 // CTA o plans owner o's list from the o-th array of nb + 1 totals / offsets.
 __global__ void __launch_bounds__(1024)
 tile_plan_owners_kernel(const unsigned long long *__restrict__ src, uint32_t nb, unsigned long long cap,
                         uint32_t tiles_per_bucket, OwnerArrays oa) {
-    tile_plan_body(src + (size_t)blockIdx.x * (nb + 1), nb, cap, tiles_per_bucket, list_meta_at(oa.meta[blockIdx.x], nb));
+    tile_plan_body(src + (size_t)blockIdx.x * (nb + 1), nb, cap, tiles_per_bucket, list_meta_at(oa.meta[blockIdx.x], nb), kTileLog2);
 }
 
 __device__ __forceinline__ void tile_plan_body(const unsigned long long *__restrict__ src, uint32_t nb,
-                                               unsigned long long cap, uint32_t tiles_per_bucket, ListMeta m) {
+                                               unsigned long long cap, uint32_t tiles_per_bucket, ListMeta m,
+                                               uint32_t tile_log2) {
     __shared__ uint32_t s_warp[32];
     const uint32_t b = threadIdx.x;
     uint32_t tiles = 0;
@@ -1344,7 +1351,7 @@ __device__ __forceinline__ void tile_plan_body(const unsigned long long *__restr
         } else {
             n = src[b + 1] - src[b];
             m.cell_begin[b] = src[b];
-            tiles = (uint32_t)((n + kTile - 1) / kTile);
+            tiles = (uint32_t)((n + (1ull << tile_log2) - 1) >> tile_log2);
         }
         m.bucket_n[b] = (uint32_t)n;
     }
@@ -1364,10 +1371,10 @@ __device__ __forceinline__ void tile_plan_body(const unsigned long long *__restr
 
 // tile_off[t * (F + 1) + f] = first cell (relative to the tile) of sub-bucket f; [.. + F] = tile length
 __device__ __forceinline__ void tile_sort_body(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb,
-                                               ListGeom geom, uint16_t *__restrict__ tile_off, uint32_t t);
+                                               ListGeom geom, tile_off_t *__restrict__ tile_off, uint32_t t);
 __global__ void __launch_bounds__(kSortThreads, 2)
 tile_sort_kernel(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb, ListGeom geom,
-                 uint16_t *__restrict__ tile_off) {
+                 tile_off_t *__restrict__ tile_off) {
     tile_sort_body(list, m, nb, geom, tile_off, blockIdx.x);
 }
 // grid (tile slots per owner, owners)
@@ -1378,7 +1385,7 @@ tile_sort_owners_kernel(OwnerArrays oa, uint32_t nb, ListGeom geom) {
 }
 
 __device__ __forceinline__ void tile_sort_body(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb,
-                                               ListGeom geom, uint16_t *__restrict__ tile_off, uint32_t t) {
+                                               ListGeom geom, tile_off_t *__restrict__ tile_off, uint32_t t) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long *stage = reinterpret_cast<unsigned long long *>(s_raw);   // kTile
     uint32_t *cnt = reinterpret_cast<uint32_t *>(stage + kTile);                  // F (+1)
@@ -1394,7 +1401,7 @@ __device__ __forceinline__ void tile_sort_body(unsigned long long *__restrict__ 
     const unsigned long long bn = m.bucket_n[lo];
     const unsigned long long first = (unsigned long long)j * kTile;
     const uint32_t n = first >= bn ? 0u : (uint32_t)(bn - first < kTile ? bn - first : kTile);
-    uint16_t *off = tile_off + (size_t)t * (F + 1);
+    tile_off_t *off = tile_off + (size_t)t * (F + 1);
     if (n == 0) {  // empty tile slot: all offsets zero, so every run read from it has length 0
         for (uint32_t f = threadIdx.x; f <= F; f += kSortThreads) off[f] = 0;
         return;
@@ -1434,13 +1441,13 @@ __device__ __forceinline__ void tile_sort_body(unsigned long long *__restrict__ 
     const uint32_t start0 = base + incl - c0 - c1;
     if (a < F) {
         cnt[a] = start0;
-        off[a] = (uint16_t)start0;
+        off[a] = start0;
     }
     if (a + 1 < F) {
         cnt[a + 1] = start0 + c0;
-        off[a + 1] = (uint16_t)(start0 + c0);
+        off[a + 1] = start0 + c0;
     }
-    if (threadIdx.x == 0) off[F] = (uint16_t)n;  // kTile = 8192 fits
+    if (threadIdx.x == 0) off[F] = n;
     __syncthreads();
 #pragma unroll
     for (uint32_t r = 0; r < kSortPer; r++) {
@@ -1449,6 +1456,139 @@ __device__ __forceinline__ void tile_sort_body(unsigned long long *__restrict__ 
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) cells[i] = stage[i];
+}
+
+// Pass B with a CLUSTER per tile: C * kTile k-mers are sorted as ONE tile by the C CTAs of a
+// thread-block cluster.  Each CTA loads its kTile cells and ranks its k-mers per sub-bucket in its
+// own shared memory (as tile_sort_kernel does); after a cluster barrier every CTA reads the others'
+// counts through distributed shared memory: the tile-wide start of every sub-bucket (a scan of the
+// summed counts) plus the k-mers that lower-ranked CTAs hold for the same sub-bucket give the first
+// cell of this CTA's piece.  The CTA lays its k-mers out by sub-bucket in its stage and copies every
+// piece to its place in the tile — in place: nobody writes before everybody has loaded (the barrier).
+// Why: a tile C times larger gives the insert kernel runs C times longer, or C times more
+// sub-buckets at the same run length — which is what lets a multi-GPU sender sort an owner's coarse
+// bucket straight down to that owner's table partitions, without a re-bucketing pass.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <int C>
+__global__ void __launch_bounds__(kSortThreads, 2)
+tile_sort_cluster_kernel(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb, ListGeom geom,
+                         tile_off_t *__restrict__ tile_off) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    constexpr uint32_t kMaxF = 1u << kMaxSubLog2;
+    unsigned long long *stage = reinterpret_cast<unsigned long long *>(s_raw);   // kTile
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(stage + kTile);                  // this CTA's counts (the cluster reads them)
+    uint32_t *lstart = cnt + kMaxF;                                               // first stage slot of sub-bucket f
+    uint32_t *gbase = lstart + kMaxF;                                             // first tile cell of this CTA's piece of f
+    uint16_t *stage_f = reinterpret_cast<uint16_t *>(gbase + kMaxF);              // kTile: sub-bucket of every staged k-mer
+    __shared__ unsigned long long s_warp[kSortThreads / 32];
+    constexpr uint32_t T = (uint32_t)C * kTile;
+    const uint32_t F = 1u << geom.g2;
+    const uint32_t cr = cluster.block_rank();
+    const uint32_t t = blockIdx.x / C;
+    if (t >= m.tile_begin[nb]) return;   // (the same decision in every CTA of the cluster)
+    uint32_t lo = 0, hi = nb;  // last bucket whose tile_begin <= t
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (m.tile_begin[mid] <= t) lo = mid; else hi = mid;
+    }
+    const uint32_t j = t - m.tile_begin[lo];
+    const unsigned long long bn = m.bucket_n[lo];
+    const unsigned long long first = (unsigned long long)j * T;
+    const uint32_t n_tile = first >= bn ? 0u : (uint32_t)(bn - first < T ? bn - first : T);
+    tile_off_t *off = tile_off + (size_t)t * (F + 1);
+    if (n_tile == 0) {  // empty tile slot (also the same in every CTA): all offsets zero
+        if (cr == 0)
+            for (uint32_t f = threadIdx.x; f <= F; f += kSortThreads) off[f] = 0;
+        return;
+    }
+    const uint32_t my0 = cr * kTile;
+    const uint32_t n = my0 >= n_tile ? 0u : (n_tile - my0 < kTile ? n_tile - my0 : kTile);
+    unsigned long long *tile_cells = list + m.cell_begin[lo] + first;
+    const unsigned long long *cells = tile_cells + my0;
+    for (uint32_t f = threadIdx.x; f < F; f += kSortThreads) cnt[f] = 0;
+    __syncthreads();
+    unsigned long long km[kSortPer];
+    uint32_t fr[kSortPer];  // sub-bucket | rank inside (CTA, sub-bucket) << 10
+#pragma unroll
+    for (uint32_t r = 0; r < kSortPer; r++) {
+        const uint32_t i = threadIdx.x + r * kSortThreads;
+        km[r] = i < n ? cells[i] : 0ull;
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < kSortPer; r++) {
+        const uint32_t i = threadIdx.x + r * kSortThreads;
+        if (i < n) {
+            const uint32_t f = geom.sub(km[r]);
+            fr[r] = f | (atomicAdd(&cnt[f], 1u) << kMaxSubLog2);
+        }
+    }
+    cluster.sync();   // every CTA's counts are complete, and every CTA holds its cells in registers
+    // sub-buckets a, a + 1 of this thread: tile-wide totals, and what lower-ranked CTAs hold
+    const uint32_t a = threadIdx.x * 2;
+    uint32_t tot0 = 0, tot1 = 0, bef0 = 0, bef1 = 0;
+#pragma unroll
+    for (uint32_t c = 0; c < (uint32_t)C; c++) {
+        const uint32_t *rc = cluster.map_shared_rank(cnt, c);
+        const uint32_t x0 = a < F ? rc[a] : 0u, x1 = a + 1 < F ? rc[a + 1] : 0u;
+        tot0 += x0;
+        tot1 += x1;
+        if (c < cr) {
+            bef0 += x0;
+            bef1 += x1;
+        }
+    }
+    const uint32_t c0 = a < F ? cnt[a] : 0u, c1 = a + 1 < F ? cnt[a + 1] : 0u;
+    cluster_arrive();   // this CTA has read the others' counts (waited for before anybody leaves)
+    // ONE exclusive scan for both: high word = tile-wide totals, low word = this CTA's counts
+    const unsigned long long mine = ((unsigned long long)(tot0 + tot1) << 32) | (unsigned long long)(c0 + c1);
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= (uint32_t)o) incl += v;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned long long base = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) base += s_warp[w];
+    const unsigned long long start = base + incl - mine;
+    const uint32_t gs0 = (uint32_t)(start >> 32), ls0 = (uint32_t)start;
+    if (a < F) {
+        lstart[a] = ls0;
+        gbase[a] = gs0 + bef0;
+        if (cr == 0) off[a] = gs0;
+    }
+    if (a + 1 < F) {
+        lstart[a + 1] = ls0 + c0;
+        gbase[a + 1] = gs0 + tot0 + bef1;
+        if (cr == 0) off[a + 1] = gs0 + tot0;
+    }
+    if (cr == 0 && threadIdx.x == 0) off[F] = n_tile;
+    __syncthreads();
+#pragma unroll
+    for (uint32_t r = 0; r < kSortPer; r++) {
+        const uint32_t i = threadIdx.x + r * kSortThreads;
+        if (i < n) {
+            const uint32_t f = fr[r] & ((1u << kMaxSubLog2) - 1);
+            const uint32_t at = lstart[f] + (fr[r] >> kMaxSubLog2);
+            stage[at] = km[r];
+            stage_f[at] = (uint16_t)f;
+        }
+    }
+    __syncthreads();
+    // consecutive threads write consecutive cells of a piece
+    for (uint32_t p = threadIdx.x; p < n; p += kSortThreads) {
+        const uint32_t f = stage_f[p];
+        tile_cells[gbase[f] + (p - lstart[f])] = stage[p];
+    }
+    cluster_wait();   // nobody leaves while its counts may still be read
+}
+__host__ __device__ inline size_t tile_sort_cluster_smem_bytes() {
+    return (size_t)kTile * 10 + ((size_t)3 << kMaxSubLog2) * 4 + 16;
 }
 
 // Multi-GPU senders: pass A buckets a batch by (owner, coarse region) — at most 1024 buckets in
@@ -1584,7 +1724,7 @@ __host__ __device__ inline size_t tile_sort_smem_bytes(uint32_t g2) { return (si
 // owner's block inside a receive arena.
 struct SegDesc {
     const unsigned long long *list;
-    const uint16_t *tile_off;
+    const tile_off_t *tile_off;
     const uint32_t *tile_begin;
     const unsigned long long *cell_begin;
     uint32_t bucket0;   // first bucket of this table's owner in the list's numbering (rank << g1)
@@ -1621,6 +1761,7 @@ struct InsertLaunch {
     Slot *table;
     uint32_t log2cap, n_ranks;
     uint32_t g1, g2;
+    uint32_t tile_log2;                  // the lists' tiles hold 2^tile_log2 cells
     const SegDesc *segs;                 // sorted by chunk
     const uint32_t *chunk_first_seg;     // [n_chunks + 1]
     uint32_t n_segs, n_chunks;
@@ -1839,9 +1980,9 @@ tile_insert_kernel(const InsertLaunch L) {
                 }
                 const SegDesc &sg = L.segs[lo / nbr];
                 const uint32_t jt = r - vs_first[lo];
-                const uint16_t *off = sg.tile_off + (size_t)(vs_tb[lo] + jt) * (F + 1);
+                const tile_off_t *off = sg.tile_off + (size_t)(vs_tb[lo] + jt) * (F + 1);
                 const uint32_t o0 = off[f0], o1 = off[f1];
-                run_src[r - w0] = reinterpret_cast<unsigned long long>(sg.list + vs_cell[lo] + (unsigned long long)jt * kTile + o0);
+                run_src[r - w0] = reinterpret_cast<unsigned long long>(sg.list + vs_cell[lo] + ((unsigned long long)jt << L.tile_log2) + o0);
                 run_len[r - w0] = o1 - o0;
             }
             __syncthreads();

@@ -163,6 +163,25 @@ def test_count_parity_vs_oracle(skm, oracle, k, chunks, mode):
     compare(e, run, chunks)
 
 
+@pytest.mark.parametrize("tile_log2,max_buckets,k,chunks", [(14, 16, 21, 3), (15, 16, 31, 0), (16, 16, 21, 10), (16, 1024, 25, 2),
+                                                             (15, 4, 15, 4)])
+def test_cluster_tile_sort_vs_oracle(skm, oracle, monkeypatch, tile_log2, max_buckets, k, chunks):
+    """Pass B by a thread-block cluster (tile_sort_cluster_kernel): 2 / 4 / 8 CTAs sort 2^14 / 2^15 / 2^16 k-mers as one
+    tile, counts exchanged through distributed shared memory.  Few buckets, so that a bucket spans several full
+    tiles and every CTA of a cluster has cells; 1024 buckets: every tile is a partial one."""
+    monkeypatch.setenv("SKM_TILE_LOG2", str(tile_log2))
+    monkeypatch.setenv("SKM_MAX_BUCKETS", str(max_buckets))
+    L = 150
+    reads = oracle.synth_reads(seed=300 + tile_log2, genome_len=80_000, read_len=L, sub_rate=0.01, n_rate=0.001,
+                               first=0, n=25_000)
+    run = run_oracle(oracle, reads, k, chunks, 200)
+    for hint in (0, 600_000):   # without / with a capacity hint (sub-bucket bits follow the table's partitions)
+        e = run_gpu(skm, reads, k, chunks, 200, L, mode=2, capacity_hint=hint)
+        compare(e, run, chunks)
+        assert e.stage_times().tiled_launches >= 1
+        e.close()
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 def test_count_parity_goldens(skm, oracle, mode):
     """Committed goldens (tests/golden/synth_cases.json, made by make_golden.py)."""
@@ -557,6 +576,45 @@ def test_sharded_group_vs_oracle(skm, oracle, world, k, chunks, mode):
     _feed_ranks(g.engines, reads2, 8000, L + 1, chunks, world)
     g.finalize()
     _check_sharded(g, g.engines, run2, chunks, world)
+    g.close()
+
+
+def test_sharded_group_owner_lists_path(skm, oracle, monkeypatch):
+    """SKM_MG_SLICES=0: the earlier exchange layout (every owner's slice re-bucketed into a list of its own by
+    tile_rebucket_kernel, whole owner lists shipped) stays selectable and exact."""
+    from sharkmer_b200.multigpu import Group
+    monkeypatch.setenv("SKM_MG_SLICES", "0")
+    L, n, hmax, world, k, chunks = 120, 23_000, 100, 3, 21, 4
+    reads = oracle.synth_reads(131, 50_000, L, 0.01, 0.001, 0, n)
+    run = run_oracle(oracle, reads, k, chunks, hmax)
+    g = Group(k, chunks, hmax, [0] * world, arena_bytes_per_rank=96 << 20, insert_mode=0)
+    _feed_ranks(g.engines, reads, n, L + 1, chunks, world)
+    g.finalize()
+    _check_sharded(g, g.engines, run, chunks, world)
+    g.close()
+
+
+@pytest.mark.parametrize("world,chunks", [(2, 3), (4, 0), (3, 2)])
+def test_sharded_group_few_buckets_full_cluster_tiles(skm, oracle, monkeypatch, world, chunks):
+    """Sender lists with few, large buckets (SKM_MAX_BUCKETS=16): an owner's coarse bucket spans several full
+    cluster tiles, so the slices shipped hold whole 2^16-cell tiles sorted by all eight CTAs."""
+    from sharkmer_b200.multigpu import Group
+    monkeypatch.setenv("SKM_MAX_BUCKETS", "16")
+    L, n, hmax, k = 150, 24_000, 100, 21
+    reads = oracle.synth_reads(171 + world, 60_000, L, 0.01, 0.001, 0, n)
+    run = run_oracle(oracle, reads, k, chunks, hmax)
+    g = Group(k, chunks, hmax, [0] * world, arena_bytes_per_rank=128 << 20, insert_mode=0)
+    # a rank ingests all of a chunk's share at once: one list per (rank, chunk) with ~100 k k-mers per bucket
+    line, n_chunks = L + 1, max(1, chunks)
+    per = [[[] for _ in range(n_chunks)] for _ in range(world)]
+    for b in range((n + 999) // 1000):
+        per[(b // n_chunks) % world][b % n_chunks].append(reads[b * 1000 * line:min((b + 1) * 1000, n) * line])
+    for r in range(world):
+        for c in range(n_chunks):
+            if per[r][c]:
+                g.engines[r].ingest_batch(c, np.concatenate(per[r][c]))
+    g.finalize()
+    _check_sharded(g, g.engines, run, chunks, world)
     g.close()
 
 
