@@ -104,8 +104,45 @@ class ClockSampler:
         self.rows = []
         self.proc = None
 
+    def _nvml_loop(self, period_s):
+        """In-process NVML sampling (the library nvidia-smi itself reads): the same fields, one handle kept open."""
+        import pynvml as nv
+        h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+        slow = getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8))
+        therm_hw = getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40))
+        therm_sw = getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20))
+        pcap = getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                r = int(get_reasons(h))
+                f = lambda bit: "Active" if r & bit else "Not Active"
+                self.rows.append(f"{self.gpu}, {sm}, {mx}, {pw:.2f}, 0x{r:016x}, {f(slow)}, {f(therm_hw)}, {f(therm_sw)}, {f(pcap)}")
+            except Exception:
+                pass
+            self._stop.wait(period_s)
+
     def start(self):
+        period_ms = os.environ.get("SKM_SAMPLER_MS", "100")
+        # default: NVML in-process (r2_43: the nvidia-smi child process perturbed 6 of 10 end-to-end steps by 2-24 ms,
+        # the in-process reader none); SKM_SAMPLER=smi runs the recipe's nvidia-smi -lms loop instead
+        if os.environ.get("SKM_SAMPLER", "nvml") == "nvml":
+            try:
+                import pynvml as nv
+                nv.nvmlInit()
+                self._stop = threading.Event()
+                self.source = "nvml (in-process, the library behind nvidia-smi)"
+                self.t = threading.Thread(target=self._nvml_loop, args=(float(period_ms) / 1e3,), daemon=True)
+                self.t.start()
+                self.proc = "nvml"
+                return
+            except Exception:
+                self.proc = None
         try:
+            self.source = "nvidia-smi -lms " + period_ms
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("SKM_SAMPLER_MS", "100"),
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -122,11 +159,15 @@ class ClockSampler:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.proc == "nvml":
+            self._stop.set()
+            self.t.join(timeout=2)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
@@ -144,7 +185,8 @@ class ClockSampler:
         # "under load" = samples drawing the most power
         order = np.argsort(power)[len(power) // 2:]
         return {"sm_mhz": float(np.median(np.asarray(sm)[order])), "sm_max_mhz": float(max(mx)),
-                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons),
+                "source": getattr(self, "source", "nvidia-smi")}
 
 
 # ----------------------------------------------------------------------------

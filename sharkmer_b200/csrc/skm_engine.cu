@@ -110,7 +110,10 @@ struct skm_ctx {
                                           // engine never queues behind a kernel that waits for an SM
     cudaStream_t dma_stream = nullptr;   // peer copies of routed k-mers (copy engines)
     cudaEvent_t ev_dma = nullptr;
-    cudaStream_t part_stream = nullptr;  // pack + bucketing of incoming batches (overlaps inserts on `stream`)
+    cudaStream_t part_stream = nullptr;  // bucketing of incoming batches (overlaps inserts on `stream`)
+    cudaStream_t pack_stream = nullptr;  // pack kernels of incoming batches.  A stream of their own (high priority): on the
+                                         // bucketing stream, pack(b+1) sat between pass A of b and of b+1, ran 12x slower
+                                         // beside the tile sort of b, and so kept pass A(b+1) from overlapping that sort
     cudaStream_t sort_stream = nullptr;  // tile sort of a bucketed batch (overlaps the bucketing of the next one)
     cudaEvent_t ev_sort = nullptr;
     bool sort_overlap = true;            // SKM_SORT_OVERLAP=0: tile sort on the bucketing stream
@@ -607,6 +610,7 @@ struct WorkStream {  // selects the stream the bucketing helpers launch on, for 
 
 int32_t sync_all(skm_ctx *c) {
     CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->pack_stream));
     CU(cudaStreamSynchronize(c->part_stream));
     CU(cudaStreamSynchronize(c->sort_stream));
     CU(cudaStreamSynchronize(c->dma_stream));
@@ -1679,6 +1683,11 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     }
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->part_stream, cudaStreamNonBlocking));
+    {
+        int prio_least = 0, prio_greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        CU(cudaStreamCreateWithPriority(&c->pack_stream, cudaStreamNonBlocking, prio_greatest));
+    }
     CU(cudaStreamCreateWithFlags(&c->dma_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->sort_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_sort, cudaEventDisableTiming));
@@ -1766,7 +1775,9 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
         if (const char *g = getenv("SKM_MG_SLICES")) c->mg_slices = atoi(g) != 0;
         // tile size: one CTA sorts 2^13 k-mers; a cluster of 2 / 4 / 8 CTAs sorts 2^14 / 2^15 / 2^16 as one tile.
         // Multi-GPU slices need the large tile: an owner's coarse bucket is sorted by log2(n_ranks) more bits.
-        c->tile_log2 = c->n_ranks > 1 && c->mg_slices ? kMaxTileLog2 : kTileLog2;
+        // The tile grows with the number of owners, so that an owner's partition still finds runs of ~64 k-mers.
+        c->tile_log2 = kTileLog2;
+        if (c->n_ranks > 1 && c->mg_slices) c->tile_log2 = std::min<uint32_t>(kMaxTileLog2, kTileLog2 + ceil_log2(c->n_ranks));
         if (const char *g = getenv("SKM_TILE_LOG2")) c->tile_log2 = (uint32_t)std::max<int>(kTileLog2, std::min<int>(atoi(g), kMaxTileLog2));
         const int g1 = (int)list_log2_regions(c);
         // without a hint: as fine as the partitions of a 2^29-slot table (2^17 of them)
@@ -1796,6 +1807,7 @@ void skm_destroy(skm_ctx *c) {
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->pack_stream);
         cudaStreamSynchronize(c->part_stream);
         cudaStreamSynchronize(c->sort_stream);
         cudaStreamSynchronize(c->dma_stream);
@@ -1857,6 +1869,7 @@ void skm_destroy(skm_ctx *c) {
         if (c->own_stream) cudaStreamDestroy(c->stream);
         cudaStreamDestroy(c->copy_stream);
         cudaStreamDestroy(c->part_stream);
+        cudaStreamDestroy(c->pack_stream);
         cudaStreamDestroy(c->dma_stream);
         cudaStreamDestroy(c->sort_stream);
         if (c->ev_sort) cudaEventDestroy(c->ev_sort);
@@ -1923,13 +1936,14 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
     // The copy runs on its own stream, into a ring of persistent raw buffers, so that it overlaps
     // the kernels of earlier batches (a buffer is reused once its pack kernel has finished):
     //   copy stream   : wait [packed(b-R)] -> H2D(b) -> [copied(b)] -> H2D(b+1) -> ...
-    //   routing stream: wait [copied(b)] -> pack(b) -> [packed(b)] -> bucket(b) -> [ready] -> pack(b+1) ...
+    //   pack stream   : wait [copied(b)] -> pack(b) -> [packed(b)]
+    //   routing stream: wait [packed(b)] -> pass A(b) -> wait [packed(b+1)] -> pass A(b+1) ...
+    //   sort stream   : pass B(b) beside pass A(b+1)
     //   main stream   : inserts (skm_finalize)
-    // The copies have a stream of their own: a pack kernel that is waiting for the (persistent)
-    // insert kernel to leave it room must not hold back the next batch's copy.  Pack and bucketing
-    // share ONE stream on purpose: beside the insert kernel there is room for one of their CTAs per
-    // SM, and two kernels fighting for it (pack of batch b+1 against bucketing of batch b) slowed
-    // both them and the inserts down (profiles/experiments_r01.md #26).
+    // The copies have a stream of their own: a pack kernel that is waiting for room on the SMs must
+    // not hold back the next batch's copy.  So have the pack kernels (round 1 kept them on the routing
+    // stream, beside a persistent insert kernel that left room for one CTA per SM): between pass A of
+    // two batches, a pack kernel ran 12x slower beside the tile sort and kept pass A from overlapping it.
     const uint32_t b = c->raw_next++ % skm_ctx::kRawRing;
     if (!c->raw_copied[b]) {
         CU(cudaEventCreateWithFlags(&c->raw_copied[b], cudaEventDisableTiming));
@@ -1953,13 +1967,13 @@ int32_t skm_ingest_batch(skm_ctx *c, uint32_t chunk, const uint8_t *seqs, uint64
     }
     CU(cudaEventRecord(c->raw_copied[b], c->copy_stream));
     if (!(flags & SKM_INGEST_ASYNC)) CU(cudaEventSynchronize(c->raw_copied[b]));
-    CU(cudaStreamWaitEvent(c->part_stream, c->raw_copied[b], 0));
+    CU(cudaStreamWaitEvent(c->pack_stream, c->raw_copied[b], 0));
     WorkStream ws(c, c->part_stream);
     c->raw_in_use[b] = true;
     cudaEvent_t copied = get_event(c);
     CU(cudaEventRecord(copied, c->copy_stream));
     const size_t n_before = c->chunks[chunk].segs.size();
-    rc = stage_device(c, chunk, c->raw_buf[b], n_bytes, c->part_stream, c->raw_packed[b]);
+    rc = stage_device(c, chunk, c->raw_buf[b], n_bytes, c->pack_stream, c->raw_packed[b]);
     if (c->chunks[chunk].segs.size() > n_before) c->chunks[chunk].segs.back().copied = copied;
     else c->event_pool.push_back(copied);
     return rc;
@@ -2012,9 +2026,9 @@ int32_t skm_ingest_device(skm_ctx *c, uint32_t chunk, const uint8_t *d_seqs, uin
     DeviceGuard g(c->device);
     // d_seqs was produced on the ctx's main stream (or is already complete): order the pack after it
     CU(cudaEventRecord(c->ev_main, c->stream));
-    CU(cudaStreamWaitEvent(c->part_stream, c->ev_main, 0));
+    CU(cudaStreamWaitEvent(c->pack_stream, c->ev_main, 0));
     WorkStream ws(c, c->part_stream);
-    return stage_device(c, chunk, d_seqs, n_bytes);
+    return stage_device(c, chunk, d_seqs, n_bytes, c->pack_stream);
 }
 
 int32_t skm_sync(skm_ctx *c) {
@@ -2818,6 +2832,7 @@ int32_t mg_allgather(skm_ctx *c, const skm_comm *comm, const void *send, void *r
 int32_t mg_prepare_local(skm_ctx *c) {
     int32_t rc;
     CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->pack_stream));
     CU(cudaStreamSynchronize(c->part_stream));
     CU(cudaStreamSynchronize(c->sort_stream));
     WorkStream ws(c, c->part_stream);

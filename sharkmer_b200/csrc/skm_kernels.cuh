@@ -119,6 +119,27 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Shared-memory accesses by 32-bit shared-window address (the generic-pointer forms re-derive the
+// window base, S2R + LEA, at every use inside the probe loop of tile_insert_kernel).
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t saddr) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long atoms_cas_u64(uint32_t saddr, unsigned long long cmp, unsigned long long val) {
+    unsigned long long old;
+    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(saddr), "l"(cmp), "l"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t atoms_add_u32(uint32_t saddr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void reds_add_u32(uint32_t saddr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -1483,9 +1504,10 @@ tile_sort_cluster_kernel(unsigned long long *__restrict__ list, ListMeta m, uint
     uint32_t *cnt = reinterpret_cast<uint32_t *>(stage + kTile);                  // this CTA's counts (the cluster reads them)
     uint32_t *lstart = cnt + kMaxF;                                               // first stage slot of sub-bucket f
     uint32_t *gbase = lstart + kMaxF;                                             // first tile cell of this CTA's piece of f
-    uint16_t *stage_f = reinterpret_cast<uint16_t *>(gbase + kMaxF);              // kTile: sub-bucket of every staged k-mer
+    uint16_t *stage_d = reinterpret_cast<uint16_t *>(gbase + kMaxF);              // kTile: tile cell every staged k-mer goes to
     __shared__ unsigned long long s_warp[kSortThreads / 32];
     constexpr uint32_t T = (uint32_t)C * kTile;
+    static_assert(T <= 65536u, "tile-relative cell indices are kept in 16 bits");
     const uint32_t F = 1u << geom.g2;
     const uint32_t cr = cluster.block_rank();
     const uint32_t t = blockIdx.x / C;
@@ -1573,18 +1595,15 @@ tile_sort_cluster_kernel(unsigned long long *__restrict__ list, ListMeta m, uint
     for (uint32_t r = 0; r < kSortPer; r++) {
         const uint32_t i = threadIdx.x + r * kSortThreads;
         if (i < n) {
-            const uint32_t f = fr[r] & ((1u << kMaxSubLog2) - 1);
-            const uint32_t at = lstart[f] + (fr[r] >> kMaxSubLog2);
+            const uint32_t f = fr[r] & ((1u << kMaxSubLog2) - 1), rank = fr[r] >> kMaxSubLog2;
+            const uint32_t at = lstart[f] + rank;
             stage[at] = km[r];
-            stage_f[at] = (uint16_t)f;
+            stage_d[at] = (uint16_t)(gbase[f] + rank);
         }
     }
     __syncthreads();
     // consecutive threads write consecutive cells of a piece
-    for (uint32_t p = threadIdx.x; p < n; p += kSortThreads) {
-        const uint32_t f = stage_f[p];
-        tile_cells[gbase[f] + (p - lstart[f])] = stage[p];
-    }
+    for (uint32_t p = threadIdx.x; p < n; p += kSortThreads) tile_cells[stage_d[p]] = stage[p];
     cluster_wait();   // nobody leaves while its counts may still be read
 }
 __host__ __device__ inline size_t tile_sort_cluster_smem_bytes() {
@@ -1827,6 +1846,10 @@ tile_insert_kernel(const InsertLaunch L) {
     __shared__ uint32_t s_nspans, s_more, s_next_run;
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = kInsThreads / 32;
+    uint32_t keys_s = (uint32_t)__cvta_generic_to_shared(keys), counts_s = (uint32_t)__cvta_generic_to_shared(counts);
+    uint32_t phist_s = (uint32_t)__cvta_generic_to_shared(phist);
+    // (opaque to the compiler, which otherwise re-derives the window base, S2UR + ULEA, inside the probe loop)
+    asm volatile("" : "+r"(keys_s), "+r"(counts_s), "+r"(phist_s));
     const uint32_t pbits = L.log2cap - kPartLog2;
     const uint32_t F = 1u << L.g2;
     const unsigned long long top = L.histo_max + 1;
@@ -2083,7 +2106,68 @@ tile_insert_kernel(const InsertLaunch L) {
                 cp_async_commit();
                 const uint32_t c = s_span[i][0], span_n = s_span[i][4];
                 const unsigned long long n_new_before = n_new;
-                if (!s_fail) {
+                // Fewer occupied slots + k-mers in this span than slots: an empty slot exists throughout the span, so
+                // every probe sequence ends and the loop needs no probe counter.  (s_occ only grows while it is read.)
+                const bool roomy = s_occ + span_n < kPartSlots;
+                if (!s_fail && roomy) {
+                    const unsigned long long *src = stage + (i % kStageDepth) * kStageCap;
+                    const uint32_t ph_s = phist_s + c * L.k_low * 4u;   // this chunk's histogram moves
+                    uint32_t new_here = 0;
+                    for (uint32_t i0 = 0; i0 < span_n; i0 += kInsThreads) {
+                        const uint32_t k = i0 + threadIdx.x;
+                        const unsigned long long kmer = k < span_n ? src[k] : SKM_EMPTY_KEY;
+                        uint32_t active = kmer != SKM_EMPTY_KEY;
+                        uint32_t s = 0;
+                        if (active) {
+                            const uint64_t h = skm_hash_kmer(kmer);
+                            const uint64_t home = skm_home_slot(L.n_ranks == 1 ? h : skm_local_hash(h, L.n_ranks), L.log2cap);
+                            if (filter && (home >> kPartLog2) != q) active = 0;
+                            s = (uint32_t)home & (kPartSlots - 1);
+                        }
+                        const uint32_t counted = active;
+                        uint32_t off = s * 8u;   // byte offset of the probed slot's key
+                        // warp-uniform probe loop (lanes that are done idle, predicated off)
+                        for (;;) {
+                            if (active) {
+                                const uint32_t sa = keys_s + off;
+                                unsigned long long key = lds_u64(sa);
+                                if (key == SKM_EMPTY_KEY) {
+                                    key = atoms_cas_u64(sa, (unsigned long long)SKM_EMPTY_KEY, kmer);
+                                    if (key == SKM_EMPTY_KEY) {
+                                        key = kmer;
+                                        new_here++;
+                                    }
+                                }
+                                if (key == kmer) active = 0;
+                                else off = (off + 8u) & (kPartSlots * 8u - 8u);
+                            }
+                            if (!__any_sync(0xffffffffu, active)) break;
+                        }
+                        if (!counted) continue;
+                        s = off >> 3;
+                        if (!kHisto) {
+                            reds_add_u32(counts_s + s * 4u, 1u);
+                        } else {
+                            const uint32_t old = atoms_add_u32(counts_s + s * 4u, 1u);
+                            if (old + 1 < fast_lim) {   // (see the guarded loop below)
+                                reds_add_u32(ph_s + old * 4u, 0xFFFFFFFFu);
+                                reds_add_u32(ph_s + old * 4u + 4u, 1u);
+                            } else {
+                                const uint32_t ob = old > hm ? top32 : old;
+                                const uint32_t nb2 = old >= hm ? top32 : old + 1;
+                                if (ob != nb2) {
+                                    if (old) {
+                                        if (ob < L.k_low) reds_add_u32(ph_s + ob * 4u, 0xFFFFFFFFu);
+                                        else hlog_push(hlog, &s_hlog_n, &s_dirty, L, c, ob, true);
+                                    }
+                                    if (nb2 < L.k_low) reds_add_u32(ph_s + nb2 * 4u, 1u);
+                                    else hlog_push(hlog, &s_hlog_n, &s_dirty, L, c, nb2, false);
+                                }
+                            }
+                        }
+                    }
+                    n_new += new_here;
+                } else if (!s_fail) {
                     const unsigned long long *src = stage + (i % kStageDepth) * kStageCap;
                     int *ph = phist + c * L.k_low;  // this chunk's histogram moves
                     (void)ph;
