@@ -1,7 +1,7 @@
 #!/bin/bash
 # tile_insert_kernel: probe loop without a probe counter while the partition has room, 32-bit shared-window addresses
 mkdir -p gpurun_out
-TAG=r2_44
+TAG=${TAG:-r2_44}
 timeout 1200 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "count_parity or skewed or growth or reset or chunk_invariance or saturation or cluster_tile or sharded_group_vs or memory_bounded or c1_full" > gpurun_out/${TAG}_pytest.log 2>&1
 echo "pytest exit $?"; tail -5 gpurun_out/${TAG}_pytest.log
 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-gups --no-services > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err

@@ -1847,9 +1847,10 @@ tile_insert_kernel(const InsertLaunch L) {
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = kInsThreads / 32;
     uint32_t keys_s = (uint32_t)__cvta_generic_to_shared(keys), counts_s = (uint32_t)__cvta_generic_to_shared(counts);
-    uint32_t phist_s = (uint32_t)__cvta_generic_to_shared(phist);
+    uint32_t phist_s = (uint32_t)__cvta_generic_to_shared(phist), stage_s = (uint32_t)__cvta_generic_to_shared(stage);
     // (opaque to the compiler, which otherwise re-derives the window base, S2UR + ULEA, inside the probe loop)
-    asm volatile("" : "+r"(keys_s), "+r"(counts_s), "+r"(phist_s));
+    asm volatile("" : "+r"(keys_s), "+r"(counts_s), "+r"(phist_s), "+r"(stage_s));
+    const uint32_t home_shift = 64u - L.log2cap;   // log2cap >= kPartLog2: a table has at least one partition
     const uint32_t pbits = L.log2cap - kPartLog2;
     const uint32_t F = 1u << L.g2;
     const unsigned long long top = L.histo_max + 1;
@@ -2051,12 +2052,16 @@ tile_insert_kernel(const InsertLaunch L) {
         };
         auto issue_copy = [&](uint32_t i) {   // span i of the table -> stage buffer i % kStageDepth
             const uint32_t r0 = s_span[i][1], r1 = s_span[i][2], a = s_span[i][3], n = s_span[i][4];
-            unsigned long long *dst = stage + (i % kStageDepth) * kStageCap;
             for (uint32_t r = r0 + warp; r < r1; r += n_warps) {
                 const uint32_t rp = run_pos[r - w0], len = run_len[r - w0];
                 const uint32_t lo = max(rp, a), hi = min(rp + len, a + n);
                 const unsigned long long *src = reinterpret_cast<const unsigned long long *>(run_src[r - w0]);
-                for (uint32_t k = lo + lane; k < hi; k += 32) cp_async8(dst + (k - a), src + (k - rp));
+                // (runs are ~64 k-mers = two trips: the 4x-unrolled form the compiler builds, with its remainder
+                //  ladders, costs more instructions than the copies)
+                const uint32_t dst_s = stage_s + ((i % kStageDepth) * kStageCap - a) * 8u;
+#pragma unroll 1
+                for (uint32_t k = lo + lane; k < hi; k += 32)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_s + k * 8u), "l"(src + (k - rp)) : "memory");
             }
         };
         uint32_t from = spos;
@@ -2110,17 +2115,18 @@ tile_insert_kernel(const InsertLaunch L) {
                 // every probe sequence ends and the loop needs no probe counter.  (s_occ only grows while it is read.)
                 const bool roomy = s_occ + span_n < kPartSlots;
                 if (!s_fail && roomy) {
-                    const unsigned long long *src = stage + (i % kStageDepth) * kStageCap;
+                    const uint32_t src_s = stage_s + (i % kStageDepth) * kStageCap * 8u;
                     const uint32_t ph_s = phist_s + c * L.k_low * 4u;   // this chunk's histogram moves
                     uint32_t new_here = 0;
                     for (uint32_t i0 = 0; i0 < span_n; i0 += kInsThreads) {
                         const uint32_t k = i0 + threadIdx.x;
-                        const unsigned long long kmer = k < span_n ? src[k] : SKM_EMPTY_KEY;
+                        const unsigned long long kmer = k < span_n ? lds_u64(src_s + k * 8u) : SKM_EMPTY_KEY;
                         uint32_t active = kmer != SKM_EMPTY_KEY;
                         uint32_t s = 0;
                         if (active) {
-                            const uint64_t h = skm_hash_kmer(kmer);
-                            const uint64_t home = skm_home_slot(L.n_ranks == 1 ? h : skm_local_hash(h, L.n_ranks), L.log2cap);
+                            uint64_t h = skm_hash_kmer(kmer);
+                            if (L.n_ranks != 1) h = skm_local_hash(h, L.n_ranks);
+                            const uint64_t home = h >> home_shift;   // skm_home_slot, log2cap > 0
                             if (filter && (home >> kPartLog2) != q) active = 0;
                             s = (uint32_t)home & (kPartSlots - 1);
                         }
