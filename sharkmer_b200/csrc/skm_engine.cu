@@ -223,6 +223,10 @@ struct skm_ctx {
     uint32_t g2 = 7;                         // sub-bucket bits of the lists built by this ctx
     uint32_t tile_log2 = kTileLog2;          // cells per tile of those lists: 2^13 (one CTA sorts a tile) .. 2^16 (a cluster
                                              // of 8 does), SKM_TILE_LOG2
+    int sort_clusters[3] = {0, 0, 0};        // resident clusters of tile_sort_cluster_kernel<2 / 4 / 8> (persistent grid)
+    static constexpr uint32_t kSortCounters = 64;
+    unsigned int *d_sort_counters = nullptr; // tile counters of the cluster sorts in flight (a ring)
+    uint32_t sort_counter_next = 0;
     bool mg_slices = true;                   // multi-GPU: an owner gets its SLICE of the sender's one list, sorted by a
                                              // cluster straight down to the owner's partitions (SKM_MG_SLICES=0: every
                                              // owner's slice is re-bucketed into a list of its own first)
@@ -911,10 +915,12 @@ ListGeom list_geom(const skm_ctx *c) { return ListGeom{c->n_ranks, list_log2_reg
 
 // Pass B over `tiles` tile slots of 2^tile_log2 cells: one CTA per tile, or a cluster of 2^(tile_log2 - 13) CTAs
 template <int C>
-cudaError_t launch_cluster_sort(uint32_t tiles, cudaStream_t st, unsigned long long *list, ListMeta m, uint32_t nb, ListGeom geom,
+cudaError_t launch_cluster_sort(skm_ctx *c, uint32_t tiles, cudaStream_t st, unsigned long long *list, ListMeta m, uint32_t nb, ListGeom geom,
                                 tile_off_t *tile_off) {
+    // persistent clusters: as many as the device holds at once (a power-of-two index into the cache)
+    int &resident = c->sort_clusters[C == 2 ? 0 : C == 4 ? 1 : 2];
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(tiles * (uint32_t)C);
+    cfg.gridDim = dim3((uint32_t)c->sm_count * 2u / (uint32_t)C * (uint32_t)C);
     cfg.blockDim = dim3(kSortThreads);
     cfg.dynamicSmemBytes = tile_sort_cluster_smem_bytes();
     cfg.stream = st;
@@ -925,19 +931,32 @@ cudaError_t launch_cluster_sort(uint32_t tiles, cudaStream_t st, unsigned long l
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, tile_sort_cluster_kernel<C>, list, m, nb, geom, tile_off);
+    if (resident == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, tile_sort_cluster_kernel<C>, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = c->sm_count * 2 / C;
+        }
+        resident = n;
+    }
+    cfg.gridDim = dim3((uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)resident)) * (uint32_t)C);
+    // the tile counter of this launch: a ring of words, so that launches queued behind each other do not share one
+    unsigned int *counter = c->d_sort_counters + (c->sort_counter_next++ % skm_ctx::kSortCounters);
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    return cudaLaunchKernelEx(&cfg, tile_sort_cluster_kernel<C>, list, m, nb, geom, tile_off, counter);
 }
 
-cudaError_t launch_tile_sort(uint32_t tile_log2, uint32_t g2, uint32_t tiles, cudaStream_t st, unsigned long long *list, ListMeta m,
+cudaError_t launch_tile_sort(skm_ctx *c, uint32_t tile_log2, uint32_t g2, uint32_t tiles, cudaStream_t st, unsigned long long *list, ListMeta m,
                              uint32_t nb, ListGeom geom, tile_off_t *tile_off) {
     if (tiles == 0) return cudaSuccess;
     switch (tile_log2) {
         case kTileLog2:
             tile_sort_kernel<<<tiles, kSortThreads, tile_sort_smem_bytes(g2), st>>>(list, m, nb, geom, tile_off);
             return cudaGetLastError();
-        case kTileLog2 + 1: return launch_cluster_sort<2>(tiles, st, list, m, nb, geom, tile_off);
-        case kTileLog2 + 2: return launch_cluster_sort<4>(tiles, st, list, m, nb, geom, tile_off);
-        case kTileLog2 + 3: return launch_cluster_sort<8>(tiles, st, list, m, nb, geom, tile_off);
+        case kTileLog2 + 1: return launch_cluster_sort<2>(c, tiles, st, list, m, nb, geom, tile_off);
+        case kTileLog2 + 2: return launch_cluster_sort<4>(c, tiles, st, list, m, nb, geom, tile_off);
+        case kTileLog2 + 3: return launch_cluster_sort<8>(c, tiles, st, list, m, nb, geom, tile_off);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -1035,7 +1054,7 @@ int32_t build_list(skm_ctx *c, uint32_t chunk, size_t seg_index, uint64_t *h_off
     }
     {
         Span sp(c, ST_SORT, sort_st);
-        CU(launch_tile_sort(tl, c->g2, max_tiles, sort_st, sg.list, m, nb, list_geom(c), sg.tile_off));
+        CU(launch_tile_sort(c, tl, c->g2, max_tiles, sort_st, sg.list, m, nb, list_geom(c), sg.tile_off));
         c->launches++;
         c->stage_launches[ST_SORT]++;
     }
@@ -1750,6 +1769,7 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     CU(cudaMalloc((void **)&c->d_bucket_counts, scratch_words * sizeof(uint64_t)));
     CU(cudaMalloc((void **)&c->d_bucket_offsets, scratch_words * sizeof(uint64_t)));
     CU(cudaMalloc((void **)&c->d_bucket_cursors, scratch_words * sizeof(uint64_t)));
+    CU(cudaMalloc((void **)&c->d_sort_counters, skm_ctx::kSortCounters * sizeof(unsigned int)));
 
     c->chunks.resize(c->n_chunks);
     c->histos.resize(c->n_chunks);
@@ -1858,6 +1878,7 @@ void skm_destroy(skm_ctx *c) {
         cudaFree(c->d_bucket_counts);
         cudaFree(c->d_bucket_offsets);
         cudaFree(c->d_bucket_cursors);
+        cudaFree(c->d_sort_counters);
         cudaFree(c->d_list);
         cudaFreeHost(c->h_pinned);
         for (auto &t : c->spans) {

@@ -1495,7 +1495,7 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 template <int C>
 __global__ void __launch_bounds__(kSortThreads, 2)
 tile_sort_cluster_kernel(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb, ListGeom geom,
-                         tile_off_t *__restrict__ tile_off) {
+                         tile_off_t *__restrict__ tile_off, unsigned int *__restrict__ tile_counter) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -1506,105 +1506,116 @@ tile_sort_cluster_kernel(unsigned long long *__restrict__ list, ListMeta m, uint
     uint32_t *gbase = lstart + kMaxF;                                             // first tile cell of this CTA's piece of f
     uint16_t *stage_d = reinterpret_cast<uint16_t *>(gbase + kMaxF);              // kTile: tile cell every staged k-mer goes to
     __shared__ unsigned long long s_warp[kSortThreads / 32];
+    __shared__ uint32_t s_next[2];   // (CTA 0 of the cluster) the cluster's next tile, double-buffered
     constexpr uint32_t T = (uint32_t)C * kTile;
     static_assert(T <= 65536u, "tile-relative cell indices are kept in 16 bits");
     const uint32_t F = 1u << geom.g2;
     const uint32_t cr = cluster.block_rank();
-    const uint32_t t = blockIdx.x / C;
-    if (t >= m.tile_begin[nb]) return;   // (the same decision in every CTA of the cluster)
-    uint32_t lo = 0, hi = nb;  // last bucket whose tile_begin <= t
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (m.tile_begin[mid] <= t) lo = mid; else hi = mid;
-    }
-    const uint32_t j = t - m.tile_begin[lo];
-    const unsigned long long bn = m.bucket_n[lo];
-    const unsigned long long first = (unsigned long long)j * T;
-    const uint32_t n_tile = first >= bn ? 0u : (uint32_t)(bn - first < T ? bn - first : T);
-    tile_off_t *off = tile_off + (size_t)t * (F + 1);
-    if (n_tile == 0) {  // empty tile slot (also the same in every CTA): all offsets zero
-        if (cr == 0)
-            for (uint32_t f = threadIdx.x; f <= F; f += kSortThreads) off[f] = 0;
-        return;
-    }
-    const uint32_t my0 = cr * kTile;
-    const uint32_t n = my0 >= n_tile ? 0u : (n_tile - my0 < kTile ? n_tile - my0 : kTile);
-    unsigned long long *tile_cells = list + m.cell_begin[lo] + first;
-    const unsigned long long *cells = tile_cells + my0;
-    for (uint32_t f = threadIdx.x; f < F; f += kSortThreads) cnt[f] = 0;
-    __syncthreads();
-    unsigned long long km[kSortPer];
-    uint32_t fr[kSortPer];  // sub-bucket | rank inside (CTA, sub-bucket) << 10
-#pragma unroll
-    for (uint32_t r = 0; r < kSortPer; r++) {
-        const uint32_t i = threadIdx.x + r * kSortThreads;
-        km[r] = i < n ? cells[i] : 0ull;
-    }
-#pragma unroll
-    for (uint32_t r = 0; r < kSortPer; r++) {
-        const uint32_t i = threadIdx.x + r * kSortThreads;
-        if (i < n) {
-            const uint32_t f = geom.sub(km[r]);
-            fr[r] = f | (atomicAdd(&cnt[f], 1u) << kMaxSubLog2);
+    const uint32_t n_tiles = m.tile_begin[nb];
+    const uint32_t n_clusters = gridDim.x / C;
+    // PERSISTENT clusters: as many as the chip holds; cluster g starts with tile g and then takes tiles from a
+    // counter.  (One cluster per tile left CTA slots idle: a new cluster starts only when C slots of one GPC are
+    // free at the same time, and the CTAs of a cluster leave together.)
+    uint32_t t = blockIdx.x / C;
+    for (uint32_t it = 0;; it++) {
+        if (t >= n_tiles) {   // (the same in every CTA of the cluster)
+            cluster.sync();   // nobody leaves while s_next of CTA 0 may still be read
+            break;
         }
-    }
-    cluster.sync();   // every CTA's counts are complete, and every CTA holds its cells in registers
-    // sub-buckets a, a + 1 of this thread: tile-wide totals, and what lower-ranked CTAs hold
-    const uint32_t a = threadIdx.x * 2;
-    uint32_t tot0 = 0, tot1 = 0, bef0 = 0, bef1 = 0;
-#pragma unroll
-    for (uint32_t c = 0; c < (uint32_t)C; c++) {
-        const uint32_t *rc = cluster.map_shared_rank(cnt, c);
-        const uint32_t x0 = a < F ? rc[a] : 0u, x1 = a + 1 < F ? rc[a + 1] : 0u;
-        tot0 += x0;
-        tot1 += x1;
-        if (c < cr) {
-            bef0 += x0;
-            bef1 += x1;
+        uint32_t lo = 0, hi = nb;  // last bucket whose tile_begin <= t
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (m.tile_begin[mid] <= t) lo = mid; else hi = mid;
         }
-    }
-    const uint32_t c0 = a < F ? cnt[a] : 0u, c1 = a + 1 < F ? cnt[a + 1] : 0u;
-    cluster_arrive();   // this CTA has read the others' counts (waited for before anybody leaves)
-    // ONE exclusive scan for both: high word = tile-wide totals, low word = this CTA's counts
-    const unsigned long long mine = ((unsigned long long)(tot0 + tot1) << 32) | (unsigned long long)(c0 + c1);
-    unsigned long long incl = mine;
+        const uint32_t j = t - m.tile_begin[lo];
+        const unsigned long long bn = m.bucket_n[lo];
+        const unsigned long long first = (unsigned long long)j * T;
+        // (an empty tile slot takes the same path with zero cells everywhere: all its offsets come out zero)
+        const uint32_t n_tile = first >= bn ? 0u : (uint32_t)(bn - first < T ? bn - first : T);
+        tile_off_t *off = tile_off + (size_t)t * (F + 1);
+        const uint32_t my0 = cr * kTile;
+        const uint32_t n = my0 >= n_tile ? 0u : (n_tile - my0 < kTile ? n_tile - my0 : kTile);
+        unsigned long long *tile_cells = list + m.cell_begin[lo] + first;
+        const unsigned long long *cells = tile_cells + my0;
+        // (cnt was last read by the cluster before the arrive that the wait at the end of the previous trip matched)
+        for (uint32_t f = threadIdx.x; f < F; f += kSortThreads) cnt[f] = 0;
+        __syncthreads();
+        unsigned long long km[kSortPer];
+        uint32_t fr[kSortPer];  // sub-bucket | rank inside (CTA, sub-bucket) << 10
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((threadIdx.x & 31) >= (uint32_t)o) incl += v;
-    }
-    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    unsigned long long base = 0;
-    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) base += s_warp[w];
-    const unsigned long long start = base + incl - mine;
-    const uint32_t gs0 = (uint32_t)(start >> 32), ls0 = (uint32_t)start;
-    if (a < F) {
-        lstart[a] = ls0;
-        gbase[a] = gs0 + bef0;
-        if (cr == 0) off[a] = gs0;
-    }
-    if (a + 1 < F) {
-        lstart[a + 1] = ls0 + c0;
-        gbase[a + 1] = gs0 + tot0 + bef1;
-        if (cr == 0) off[a + 1] = gs0 + tot0;
-    }
-    if (cr == 0 && threadIdx.x == 0) off[F] = n_tile;
-    __syncthreads();
-#pragma unroll
-    for (uint32_t r = 0; r < kSortPer; r++) {
-        const uint32_t i = threadIdx.x + r * kSortThreads;
-        if (i < n) {
-            const uint32_t f = fr[r] & ((1u << kMaxSubLog2) - 1), rank = fr[r] >> kMaxSubLog2;
-            const uint32_t at = lstart[f] + rank;
-            stage[at] = km[r];
-            stage_d[at] = (uint16_t)(gbase[f] + rank);
+        for (uint32_t r = 0; r < kSortPer; r++) {
+            const uint32_t i = threadIdx.x + r * kSortThreads;
+            km[r] = i < n ? cells[i] : 0ull;
         }
+#pragma unroll
+        for (uint32_t r = 0; r < kSortPer; r++) {
+            const uint32_t i = threadIdx.x + r * kSortThreads;
+            if (i < n) {
+                const uint32_t f = geom.sub(km[r]);
+                fr[r] = f | (atomicAdd(&cnt[f], 1u) << kMaxSubLog2);
+            }
+        }
+        cluster.sync();   // every CTA's counts are complete, and every CTA holds its cells in registers
+        if (cr == 0 && threadIdx.x == 0) s_next[it & 1] = n_clusters + atomicAdd(tile_counter, 1u);
+        // sub-buckets a, a + 1 of this thread: tile-wide totals, and what lower-ranked CTAs hold
+        const uint32_t a = threadIdx.x * 2;
+        uint32_t tot0 = 0, tot1 = 0, bef0 = 0, bef1 = 0;
+#pragma unroll
+        for (uint32_t c = 0; c < (uint32_t)C; c++) {
+            const uint32_t *rc = cluster.map_shared_rank(cnt, c);
+            const uint32_t x0 = a < F ? rc[a] : 0u, x1 = a + 1 < F ? rc[a + 1] : 0u;
+            tot0 += x0;
+            tot1 += x1;
+            if (c < cr) {
+                bef0 += x0;
+                bef1 += x1;
+            }
+        }
+        const uint32_t c0 = a < F ? cnt[a] : 0u, c1 = a + 1 < F ? cnt[a + 1] : 0u;
+        cluster_arrive();   // this CTA has read the others' counts; CTA 0 has published the next tile
+        // ONE exclusive scan for both: high word = tile-wide totals, low word = this CTA's counts
+        const unsigned long long mine = ((unsigned long long)(tot0 + tot1) << 32) | (unsigned long long)(c0 + c1);
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= (uint32_t)o) incl += v;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        unsigned long long base = 0;
+        for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) base += s_warp[w];
+        const unsigned long long start = base + incl - mine;
+        const uint32_t gs0 = (uint32_t)(start >> 32), ls0 = (uint32_t)start;
+        if (a < F) {
+            lstart[a] = ls0;
+            gbase[a] = gs0 + bef0;
+            if (cr == 0) off[a] = gs0;
+        }
+        if (a + 1 < F) {
+            lstart[a + 1] = ls0 + c0;
+            gbase[a + 1] = gs0 + tot0 + bef1;
+            if (cr == 0) off[a + 1] = gs0 + tot0;
+        }
+        if (cr == 0 && threadIdx.x == 0) off[F] = n_tile;
+        __syncthreads();
+#pragma unroll
+        for (uint32_t r = 0; r < kSortPer; r++) {
+            const uint32_t i = threadIdx.x + r * kSortThreads;
+            if (i < n) {
+                const uint32_t f = fr[r] & ((1u << kMaxSubLog2) - 1), rank = fr[r] >> kMaxSubLog2;
+                const uint32_t at = lstart[f] + rank;
+                stage[at] = km[r];
+                stage_d[at] = (uint16_t)(gbase[f] + rank);
+            }
+        }
+        __syncthreads();
+        // consecutive threads write consecutive cells of a piece
+        for (uint32_t p = threadIdx.x; p < n; p += kSortThreads) tile_cells[stage_d[p]] = stage[p];
+        cluster_wait();   // everybody has read this CTA's counts; s_next of CTA 0 is visible
+        t = *cluster.map_shared_rank(&s_next[it & 1], 0);
+        __syncthreads();  // (s_warp, lstart, gbase and the stage are rewritten by the next trip)
     }
-    __syncthreads();
-    // consecutive threads write consecutive cells of a piece
-    for (uint32_t p = threadIdx.x; p < n; p += kSortThreads) tile_cells[stage_d[p]] = stage[p];
-    cluster_wait();   // nobody leaves while its counts may still be read
 }
 __host__ __device__ inline size_t tile_sort_cluster_smem_bytes() {
     return (size_t)kTile * 10 + ((size_t)3 << kMaxSubLog2) * 4 + 16;
@@ -1896,12 +1907,14 @@ tile_insert_kernel(const InsertLaunch L) {
             filter = true;
         }
         Slot *tp = L.table + (q << kPartLog2);
-        // ---- load the partition (or start empty) ----
-        {
+        // ---- load the partition (or start empty): slots [first, first + n) by `nthr` threads (whole warps).
+        //      Done in two halves by warps 1.., each beside one of warp 0's two single-warp jobs below (the scan
+        //      of the tile counts; the scan of the run lengths + the span plan), which otherwise leave them idle.
+        auto load_part = [&](uint32_t first, uint32_t n, uint32_t tid, uint32_t nthr) {
             uint32_t occ = 0, big = 0;
             if (!L.fresh) {
 #pragma unroll 4
-                for (uint32_t i = threadIdx.x; i < kPartSlots; i += kInsThreads) {
+                for (uint32_t i = first + tid; i < first + n; i += nthr) {
                     const uint4 v = ld_nc_v4(reinterpret_cast<const uint4 *>(tp) + i);
                     const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
                     keys[i] = key;
@@ -1911,7 +1924,7 @@ tile_insert_kernel(const InsertLaunch L) {
                     big |= is_big && key != SKM_EMPTY_KEY;
                 }
             } else {
-                for (uint32_t i = threadIdx.x; i < kPartSlots; i += kInsThreads) {
+                for (uint32_t i = first + tid; i < first + n; i += nthr) {
                     keys[i] = SKM_EMPTY_KEY;
                     counts[i] = 0;
                 }
@@ -1919,7 +1932,8 @@ tile_insert_kernel(const InsertLaunch L) {
             occ = __reduce_add_sync(0xffffffffu, occ);
             if (lane == 0 && occ) atomicAdd(&s_occ, occ);
             if (big) s_big = 1;
-        }
+        };
+        bool part_ready = false;   // the second half is in shared memory
         // ---- which tiles: one "virtual segment" per (list, bucket) ----
         const uint32_t n_vseg = L.n_segs * nbr;   // <= kMaxVseg (the host splits launches)
         for (uint32_t v = threadIdx.x; v < n_vseg; v += kInsThreads) {
@@ -1946,6 +1960,8 @@ tile_insert_kernel(const InsertLaunch L) {
                 run += __shfl_sync(0xffffffffu, incl, 31);
             }
             if (lane == 0) vs_first[n_vseg] = run;
+        } else {
+            load_part(0, kPartSlots / 2, threadIdx.x - 32, kInsThreads - 32);
         }
         __syncthreads();
         const uint32_t total_runs = vs_first[n_vseg];
@@ -2028,26 +2044,66 @@ tile_insert_kernel(const InsertLaunch L) {
                 }
                 if (lane == 0) run_pos[nw] = run;
                 __syncwarp();
-                // the plan: spans of this window, in order
-                uint32_t ns = 0;
-                int st = 0;
-                Span sp;
-                while (ns < kMaxSpans && (st = next_span(sp)) == 0) {
-                    if (lane == 0) {
-                        s_span[ns][0] = sp.c;
-                        s_span[ns][1] = sp.r0;
-                        s_span[ns][2] = sp.r1;
-                        s_span[ns][3] = sp.a;
-                        s_span[ns][4] = sp.n;
+                // the plan: spans of this window, in order.  The usual case — every run of the partition is in this
+                // window, at most 32 chunks — is planned by one lane per chunk; else warp 0 walks the runs serially.
+                bool planned = false;
+                if (w0 == 0 && w1 == total_runs && L.n_chunks <= 32) {
+                    uint32_t r0 = 0, r1 = 0, gb = 0, gl = 0, ns_c = 0;
+                    if (lane < L.n_chunks) {
+                        r0 = vs_first[L.chunk_first_seg[lane] * nbr];
+                        r1 = vs_first[L.chunk_first_seg[lane + 1] * nbr];
+                        gb = run_pos[r0];
+                        gl = run_pos[r1] - gb;
+                        ns_c = (gl + kStageCap - 1) / kStageCap;
                     }
-                    ns++;
+                    uint32_t incl = ns_c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= (uint32_t)o) incl += t;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total <= kMaxSpans) {
+                        uint32_t at = incl - ns_c;
+                        for (uint32_t j = 0; j < ns_c; j++, at++) {
+                            s_span[at][0] = lane;
+                            s_span[at][1] = r0;
+                            s_span[at][2] = r1;
+                            s_span[at][3] = gb + j * kStageCap;
+                            s_span[at][4] = min(kStageCap, gl - j * kStageCap);
+                        }
+                        if (lane == 0) {
+                            s_nspans = total;
+                            s_more = 2;
+                            s_next_run = total_runs;
+                        }
+                        planned = true;
+                    }
                 }
-                if (lane == 0) {
-                    s_nspans = ns;
-                    s_more = ns == kMaxSpans ? 0 : st;   // 0: this window has more spans; 1: next window; 2: done
-                    s_next_run = spos;
+                if (!planned) {
+                    uint32_t ns = 0;
+                    int st = 0;
+                    Span sp;
+                    while (ns < kMaxSpans && (st = next_span(sp)) == 0) {
+                        if (lane == 0) {
+                            s_span[ns][0] = sp.c;
+                            s_span[ns][1] = sp.r0;
+                            s_span[ns][2] = sp.r1;
+                            s_span[ns][3] = sp.a;
+                            s_span[ns][4] = sp.n;
+                        }
+                        ns++;
+                    }
+                    if (lane == 0) {
+                        s_nspans = ns;
+                        s_more = ns == kMaxSpans ? 0 : st;   // 0: this window has more spans; 1: next window; 2: done
+                        s_next_run = spos;
+                    }
                 }
+            } else if (!part_ready) {
+                load_part(kPartSlots / 2, kPartSlots / 2, threadIdx.x - 32, kInsThreads - 32);
             }
+            part_ready = true;
             __syncthreads();
         };
         auto issue_copy = [&](uint32_t i) {   // span i of the table -> stage buffer i % kStageDepth
@@ -2067,7 +2123,10 @@ tile_insert_kernel(const InsertLaunch L) {
         uint32_t from = spos;
         bool replan_same_window = false;
         for (;;) {
-            if (!total_runs) break;
+            if (!total_runs) {   // nothing for this partition: it is only loaded and written back
+                load_part(kPartSlots / 2, kPartSlots / 2, threadIdx.x, kInsThreads);
+                break;
+            }
             if (replan_same_window) {
                 // the span table was full: warp 0 continues from its cursor over the same window
                 __syncthreads();
