@@ -228,8 +228,9 @@ struct skm_ctx {
     unsigned int *d_sort_counters = nullptr; // tile counters of the cluster sorts in flight (a ring)
     uint32_t sort_counter_next = 0;
     bool mg_slices = true;                   // multi-GPU: an owner gets its SLICE of the sender's one list, sorted by a
-                                             // cluster straight down to the owner's partitions (SKM_MG_SLICES=0: every
-                                             // owner's slice is re-bucketed into a list of its own first)
+                                             // cluster straight down to the owner's partitions; false: every owner's
+                                             // slice is re-bucketed into a list of its own first (skm_create decides;
+                                             // SKM_MG_SLICES=1/0 forces)
     bool table_fresh = true;                 // logically empty: no key was ever inserted since create / reset
     bool table_zombie = false;               // logically empty but NOT physically cleared (skm_reset defers the clear:
                                              // the tiled insert starts every partition empty and rewrites the whole table)
@@ -1792,6 +1793,11 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     // partitions (one sub-bucket per partition); without one, 2^7 sub-buckets per region — a
     // partition then covers several adjacent sub-buckets, or filters a shared one
     {
+        // Multi-GPU exchange layout.  Slices need the owner's partitions to be no finer than a sender can sort a
+        // coarse bucket (2^kMaxSubLog2 sub-buckets per coarse region), which is known only when a capacity_hint
+        // sized the table (the same hint on every rank); beyond that (tables of more than 2^(g1 + 10 + 12) slots per
+        // rank: BASELINE config 5) and without a hint, every owner gets a re-bucketed list of its own.
+        c->mg_slices = c->p.capacity_hint && l2 - kPartLog2 <= route_log2_regions(c) + kMaxSubLog2;
         if (const char *g = getenv("SKM_MG_SLICES")) c->mg_slices = atoi(g) != 0;
         // tile size: one CTA sorts 2^13 k-mers; a cluster of 2 / 4 / 8 CTAs sorts 2^14 / 2^15 / 2^16 as one tile.
         // Multi-GPU slices need the large tile: an owner's coarse bucket is sorted by log2(n_ranks) more bits.

@@ -1870,16 +1870,21 @@ tile_insert_kernel(const InsertLaunch L) {
         for (uint32_t i = threadIdx.x; i < 2 * L.n_chunks * L.k_low; i += kInsThreads) chist[i] = 0;
     unsigned long long n_new_cta = 0, n_kmers_cta = 0, n_dist_cta = 0, n_sat_cta = 0;
 
+    // (thread 0) the partition counter is read one partition ahead: the atomic's round trip to L2 is over
+    // long before the value is needed, instead of holding the whole CTA at the top of every trip
+    unsigned long long next_i = 0;
+    if (threadIdx.x == 0) next_i = atomicAdd(L.part_counter, 1ull);
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            const unsigned long long i = atomicAdd(L.part_counter, 1ull);
+            const unsigned long long i = next_i;
             s_q = i < L.n_parts ? (L.part_ids ? (unsigned long long)L.part_ids[i] : i) : ~0ull;
             s_occ = 0;
             s_fail = 0;
             s_big = 0;
             s_hlog_n = 0;
             s_dirty = 0;
+            if (i < L.n_parts) next_i = atomicAdd(L.part_counter, 1ull);
         }
         __syncthreads();
         const unsigned long long q = s_q;
@@ -2304,6 +2309,7 @@ tile_insert_kernel(const InsertLaunch L) {
                     const uint32_t add = __reduce_add_sync(0xffffffffu, (uint32_t)(n_new - n_new_before));
                     if (lane == 0 && add) atomicAdd(&s_occ, add);
                 }
+
                 cp_async_wait<kStageDepth - 2>();   // span i+1 has landed (this thread's part)
                 __syncthreads();   // span i is counted everywhere; span i+1 is visible to everybody
                 if (s_occ > L.max_occupied) s_fail = 1;   // too full to go on: roll the partition back, grow, retry

@@ -549,12 +549,16 @@ def _check_sharded(group_like, engines, run, chunks, world):
     assert sum(int(e.totals().n_reads) for e in engines) == run.n_reads_ingested
 
 
+@pytest.mark.parametrize("slices", ["1", "0"])
 @pytest.mark.parametrize("world,k,chunks,mode", [(2, 25, 3, 0), (3, 21, 5, 0), (2, 31, 0, 0), (4, 21, 2, 2), (8, 21, 2, 0)])
-def test_sharded_group_vs_oracle(skm, oracle, world, k, chunks, mode):
+def test_sharded_group_vs_oracle(skm, oracle, monkeypatch, world, k, chunks, mode, slices):
     """skm_group_*: `world` ranks in one process on ONE GPU — bucketing by (owner, region), tile sort,
     copy-engine exchange into the peers' arenas, collective finalize, column sum.  Sorted table
-    (partition by partition, each key on its owner) and every histogram column vs the oracle."""
+    (partition by partition, each key on its owner) and every histogram column vs the oracle.
+    Both exchange layouts: slices of one cluster-sorted list (what a capacity_hint selects), and one
+    re-bucketed list per owner (no hint, or tables too fine for the slices)."""
     from sharkmer_b200.multigpu import Group
+    monkeypatch.setenv("SKM_MG_SLICES", slices)
     L, n, hmax = 120, 23_000, 100
     reads = oracle.synth_reads(31 + world, 50_000, L, 0.01, 0.001, 0, n)
     run = run_oracle(oracle, reads, k, chunks, hmax)
@@ -579,27 +583,13 @@ def test_sharded_group_vs_oracle(skm, oracle, world, k, chunks, mode):
     g.close()
 
 
-def test_sharded_group_owner_lists_path(skm, oracle, monkeypatch):
-    """SKM_MG_SLICES=0: the earlier exchange layout (every owner's slice re-bucketed into a list of its own by
-    tile_rebucket_kernel, whole owner lists shipped) stays selectable and exact."""
-    from sharkmer_b200.multigpu import Group
-    monkeypatch.setenv("SKM_MG_SLICES", "0")
-    L, n, hmax, world, k, chunks = 120, 23_000, 100, 3, 21, 4
-    reads = oracle.synth_reads(131, 50_000, L, 0.01, 0.001, 0, n)
-    run = run_oracle(oracle, reads, k, chunks, hmax)
-    g = Group(k, chunks, hmax, [0] * world, arena_bytes_per_rank=96 << 20, insert_mode=0)
-    _feed_ranks(g.engines, reads, n, L + 1, chunks, world)
-    g.finalize()
-    _check_sharded(g, g.engines, run, chunks, world)
-    g.close()
-
-
 @pytest.mark.parametrize("world,chunks", [(2, 3), (4, 0), (3, 2)])
 def test_sharded_group_few_buckets_full_cluster_tiles(skm, oracle, monkeypatch, world, chunks):
     """Sender lists with few, large buckets (SKM_MAX_BUCKETS=16): an owner's coarse bucket spans several full
     cluster tiles, so the slices shipped hold whole 2^16-cell tiles sorted by all eight CTAs."""
     from sharkmer_b200.multigpu import Group
     monkeypatch.setenv("SKM_MAX_BUCKETS", "16")
+    monkeypatch.setenv("SKM_MG_SLICES", "1")
     L, n, hmax, k = 150, 24_000, 100, 21
     reads = oracle.synth_reads(171 + world, 60_000, L, 0.01, 0.001, 0, n)
     run = run_oracle(oracle, reads, k, chunks, hmax)
@@ -618,10 +608,27 @@ def test_sharded_group_few_buckets_full_cluster_tiles(skm, oracle, monkeypatch, 
     g.close()
 
 
-def test_sharded_group_skewed_and_unbalanced(skm, oracle):
+def test_sharded_group_with_capacity_hint(skm, oracle):
+    """No override: with a capacity_hint the ctx picks the exchange layout itself (slices of one cluster-sorted list
+    when the hinted table's partitions are coarse enough for them), and the sub-bucket bits follow the hinted table."""
+    from sharkmer_b200.multigpu import Group
+    L, n, hmax, k = 120, 23_000, 100, 21
+    reads = oracle.synth_reads(201, 50_000, L, 0.01, 0.001, 0, n)
+    for world, chunks, hint in ((2, 3, 400_000), (4, 0, 150_000), (3, 2, 40_000_000)):
+        run = run_oracle(oracle, reads, k, chunks, hmax)
+        g = Group(k, chunks, hmax, [0] * world, arena_bytes_per_rank=96 << 20, capacity_hint=hint, insert_mode=2)
+        _feed_ranks(g.engines, reads, n, L + 1, chunks, world)
+        g.finalize()
+        _check_sharded(g, g.engines, run, chunks, world)
+        g.close()
+
+
+@pytest.mark.parametrize("slices", ["1", "0"])
+def test_sharded_group_skewed_and_unbalanced(skm, oracle, monkeypatch, slices):
     """Overflowing capped buckets on a sender (poly-A reads: one k-mer millions of times) take the
     exact re-bucketing path and are shipped again; one rank gets no reads at all."""
     from sharkmer_b200.multigpu import Group
+    monkeypatch.setenv("SKM_MG_SLICES", slices)
     L, n, k, chunks, hmax, world = 100, 16_000, 21, 2, 1000, 3
     reads = oracle.synth_reads(5, 40_000, L, 0.01, 0.001, 0, n).copy()
     lines = reads.reshape(n, L + 1)
@@ -637,12 +644,15 @@ def test_sharded_group_skewed_and_unbalanced(skm, oracle):
     g.close()
 
 
+@pytest.mark.parametrize("slices", ["1", "0"])
 @pytest.mark.parametrize("world,k,chunks,skew", [(2, 21, 2, False), (4, 31, 1, True)])
-def test_sharded_group_capped_layouts(skm, oracle, world, k, chunks, skew):
-    """Batches large enough for the one-pass capped layouts on the senders (coarse list by (owner, region),
-    then every owner's list re-bucketed into its 1024 regions by ONE launch for all owners).  skew: a tenth
-    of the reads are poly-A, so a capped bucket overflows, the batch is rebuilt exactly and shipped again."""
+def test_sharded_group_capped_layouts(skm, oracle, monkeypatch, world, k, chunks, skew, slices):
+    """Batches large enough for the one-pass capped layouts on the senders (coarse list by (owner, region); then
+    either slices of it, cluster-sorted, or every owner's list re-bucketed into its 1024 regions by ONE launch for
+    all owners).  skew: a tenth of the reads are poly-A, so a capped bucket overflows, the batch is rebuilt exactly
+    and shipped again."""
     from sharkmer_b200.multigpu import Group
+    monkeypatch.setenv("SKM_MG_SLICES", slices)
     L, hmax = 100, 1000
     per_batch = (4_200_000 * world) // (L + 1)          # reads per (rank, chunk) batch: past the capped threshold
     n = per_batch * world * chunks
@@ -697,13 +707,15 @@ def _mp_worker(rank, world, port, q, k, chunks, hmax, L, n, seed):
     dist.destroy_process_group()
 
 
-def test_sharded_two_processes_one_gpu(oracle):
+@pytest.mark.parametrize("slices", ["1", "0"])
+def test_sharded_two_processes_one_gpu(oracle, monkeypatch, slices):
     """The torchrun shape of the multi-GPU path on a one-GPU box: two PROCESSES (two ranks) share
     cuda:0, arenas mapped through CUDA IPC, the library's all-gather carried by gloo
     (sharkmer_b200.multigpu.ShardedCounter, what bench.py uses at --gpus N).  No NCCL and no
     kernel that waits for another rank: peer copies + host-side collectives only."""
     import socket
     import torch.multiprocessing as mp
+    monkeypatch.setenv("SKM_MG_SLICES", slices)   # (inherited by the spawned ranks)
     world, k, chunks, hmax, L, n, seed = 2, 21, 4, 100, 100, 16_000, 44
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -826,9 +838,11 @@ def test_memory_bounded_rounds(skm, oracle, monkeypatch):
     e.close()
 
 
-def test_sharded_group_flush_rounds(skm, oracle):
+@pytest.mark.parametrize("slices", ["1", "0"])
+def test_sharded_group_flush_rounds(skm, oracle, monkeypatch, slices):
     """skm_group_flush: a sharded count in several rounds (chunks == 0), lists and arenas freed in between."""
     from sharkmer_b200.multigpu import Group
+    monkeypatch.setenv("SKM_MG_SLICES", slices)
     L, n, k, world = 100, 24_000, 31, 3
     reads = oracle.synth_reads(8, 60_000, L, 0.01, 0.001, 0, n)
     run = run_oracle(oracle, reads, k, 0, 100)
