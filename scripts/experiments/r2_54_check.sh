@@ -1,12 +1,11 @@
 #!/bin/bash
-# persistent clusters in the cluster tile sort
+# sort kernels compiled for 2 / 4 sub-buckets per thread: parity subset, then the one-GPU bench at tile 2^13 (default) and 2^16
 mkdir -p gpurun_out
-TAG=${TAG:-r2_47}
-timeout 1200 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "cluster_tile or sharded or count_parity_vs_oracle" > gpurun_out/${TAG}_pytest.log 2>&1
-echo "pytest exit $?"; tail -5 gpurun_out/${TAG}_pytest.log
-for TL in 14 16; do
+TAG=r2_54
+timeout 1200 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "cluster_tile or sharded_group_vs or sharded_group_few or count_parity_vs_oracle or with_capacity_hint" > gpurun_out/${TAG}_pytest.log 2>&1
+echo "pytest exit $?"; tail -4 gpurun_out/${TAG}_pytest.log
+for TL in 13 16; do
   SKM_TILE_LOG2=$TL timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-gups --no-services > gpurun_out/${TAG}_tl${TL}.json 2> gpurun_out/${TAG}_tl${TL}.err
-  echo "bench tl=$TL exit $?"; tail -2 gpurun_out/${TAG}_tl${TL}.err
   python - <<PY
 import json
 try:

@@ -915,7 +915,7 @@ uint32_t list_tile_log2(const skm_ctx *c) { return c->n_ranks > 1 && !c->mg_slic
 ListGeom list_geom(const skm_ctx *c) { return ListGeom{c->n_ranks, list_log2_regions(c), c->g2}; }
 
 // Pass B over `tiles` tile slots of 2^tile_log2 cells: one CTA per tile, or a cluster of 2^(tile_log2 - 13) CTAs
-template <int C>
+template <int C, uint32_t SP>
 cudaError_t launch_cluster_sort(skm_ctx *c, uint32_t tiles, cudaStream_t st, unsigned long long *list, ListMeta m, uint32_t nb, ListGeom geom,
                                 tile_off_t *tile_off) {
     // persistent clusters: as many as the device holds at once (a power-of-two index into the cache)
@@ -934,7 +934,7 @@ cudaError_t launch_cluster_sort(skm_ctx *c, uint32_t tiles, cudaStream_t st, uns
     cfg.numAttrs = 1;
     if (resident == 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, tile_sort_cluster_kernel<C>, &cfg) != cudaSuccess || n <= 0) {
+        if (cudaOccupancyMaxActiveClusters(&n, tile_sort_cluster_kernel<C, SP>, &cfg) != cudaSuccess || n <= 0) {
             cudaGetLastError();
             n = c->sm_count * 2 / C;
         }
@@ -945,19 +945,27 @@ cudaError_t launch_cluster_sort(skm_ctx *c, uint32_t tiles, cudaStream_t st, uns
     unsigned int *counter = c->d_sort_counters + (c->sort_counter_next++ % skm_ctx::kSortCounters);
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
-    return cudaLaunchKernelEx(&cfg, tile_sort_cluster_kernel<C>, list, m, nb, geom, tile_off, counter);
+    return cudaLaunchKernelEx(&cfg, tile_sort_cluster_kernel<C, SP>, list, m, nb, geom, tile_off, counter);
 }
 
 cudaError_t launch_tile_sort(skm_ctx *c, uint32_t tile_log2, uint32_t g2, uint32_t tiles, cudaStream_t st, unsigned long long *list, ListMeta m,
                              uint32_t nb, ListGeom geom, tile_off_t *tile_off) {
     if (tiles == 0) return cudaSuccess;
     switch (tile_log2) {
+        // (two sub-buckets per thread in the kernels' scans up to 2^10 sub-buckets, four for 2^11)
         case kTileLog2:
-            tile_sort_kernel<<<tiles, kSortThreads, tile_sort_smem_bytes(g2), st>>>(list, m, nb, geom, tile_off);
+            if (g2 <= 10) tile_sort_kernel<2><<<tiles, kSortThreads, tile_sort_smem_bytes(g2), st>>>(list, m, nb, geom, tile_off);
+            else tile_sort_kernel<4><<<tiles, kSortThreads, tile_sort_smem_bytes(g2), st>>>(list, m, nb, geom, tile_off);
             return cudaGetLastError();
-        case kTileLog2 + 1: return launch_cluster_sort<2>(c, tiles, st, list, m, nb, geom, tile_off);
-        case kTileLog2 + 2: return launch_cluster_sort<4>(c, tiles, st, list, m, nb, geom, tile_off);
-        case kTileLog2 + 3: return launch_cluster_sort<8>(c, tiles, st, list, m, nb, geom, tile_off);
+        case kTileLog2 + 1:
+            return g2 <= 10 ? launch_cluster_sort<2, 2>(c, tiles, st, list, m, nb, geom, tile_off)
+                            : launch_cluster_sort<2, 4>(c, tiles, st, list, m, nb, geom, tile_off);
+        case kTileLog2 + 2:
+            return g2 <= 10 ? launch_cluster_sort<4, 2>(c, tiles, st, list, m, nb, geom, tile_off)
+                            : launch_cluster_sort<4, 4>(c, tiles, st, list, m, nb, geom, tile_off);
+        case kTileLog2 + 3:
+            return g2 <= 10 ? launch_cluster_sort<8, 2>(c, tiles, st, list, m, nb, geom, tile_off)
+                            : launch_cluster_sort<8, 4>(c, tiles, st, list, m, nb, geom, tile_off);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -1811,10 +1819,15 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
         if (const char *g = getenv("SKM_G2")) g2 = atoi(g);
         c->g2 = (uint32_t)std::max(0, std::min<int>(g2, (int)kMaxSubLog2));
     }
-    CU(cudaFuncSetAttribute(tile_sort_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_sort_cluster_smem_bytes()));
-    CU(cudaFuncSetAttribute(tile_sort_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_sort_cluster_smem_bytes()));
-    CU(cudaFuncSetAttribute(tile_sort_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_sort_cluster_smem_bytes()));
-    CU(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(tile_sort_cluster_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_sort_cluster_smem_bytes()));
+    CU(cudaFuncSetAttribute(tile_sort_cluster_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_sort_cluster_smem_bytes()));
+    CU(cudaFuncSetAttribute(tile_sort_cluster_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_sort_cluster_smem_bytes()));
+    CU(cudaFuncSetAttribute(tile_sort_cluster_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_sort_cluster_smem_bytes()));
+    CU(cudaFuncSetAttribute(tile_sort_cluster_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_sort_cluster_smem_bytes()));
+    CU(cudaFuncSetAttribute(tile_sort_cluster_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_sort_cluster_smem_bytes()));
+    CU(cudaFuncSetAttribute(tile_sort_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)tile_sort_smem_bytes(kMaxSubLog2)));
+    CU(cudaFuncSetAttribute(tile_sort_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)tile_sort_smem_bytes(kMaxSubLog2)));
     CU(cudaFuncSetAttribute(tile_sort_owners_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)tile_sort_smem_bytes(kMaxSubLog2)));

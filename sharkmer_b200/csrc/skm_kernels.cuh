@@ -1296,7 +1296,8 @@ static constexpr uint32_t kMaxTileLog2 = 16;                  // a cluster of 8 
 typedef uint32_t tile_off_t;                                  // sub-bucket offsets inside a tile (<= 2^16 inclusive)
 static constexpr uint32_t kSortThreads = 512;
 static constexpr uint32_t kSortPer = kTile / kSortThreads;    // k-mers per thread
-static constexpr uint32_t kMaxSubLog2 = 10;                   // g2 <= 10: sub-bucket and rank share a 32-bit word
+// (the sort kernels are compiled for 2 and for 4 sub-buckets per thread in their scans: up to 2^10, and 2^11 sub-buckets)
+static constexpr uint32_t kMaxSubLog2 = 11;                   // g2 <= 11: sub-bucket and rank (< 2^14) share a 32-bit word
 static_assert(kTile <= (1u << 14), "rank must fit 14 bits");
 
 struct ListGeom {
@@ -1391,20 +1392,23 @@ __device__ __forceinline__ void tile_plan_body(const unsigned long long *__restr
 }
 
 // tile_off[t * (F + 1) + f] = first cell (relative to the tile) of sub-bucket f; [.. + F] = tile length
+template <uint32_t kSubPer>
 __device__ __forceinline__ void tile_sort_body(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb,
                                                ListGeom geom, tile_off_t *__restrict__ tile_off, uint32_t t);
+template <uint32_t kSubPer>   // sub-buckets per thread in the scan: 2 (g2 <= 10) or 4 (g2 = 11)
 __global__ void __launch_bounds__(kSortThreads, 2)
 tile_sort_kernel(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb, ListGeom geom,
                  tile_off_t *__restrict__ tile_off) {
-    tile_sort_body(list, m, nb, geom, tile_off, blockIdx.x);
+    tile_sort_body<kSubPer>(list, m, nb, geom, tile_off, blockIdx.x);
 }
 // grid (tile slots per owner, owners)
 __global__ void __launch_bounds__(kSortThreads, 2)
 tile_sort_owners_kernel(OwnerArrays oa, uint32_t nb, ListGeom geom) {
     const uint32_t o = blockIdx.y;
-    tile_sort_body(oa.list[o], list_meta_at(oa.meta[o], nb), nb, geom, oa.tile_off[o], blockIdx.x);
+    tile_sort_body<2>(oa.list[o], list_meta_at(oa.meta[o], nb), nb, geom, oa.tile_off[o], blockIdx.x);   // owner lists: g2 <= 10
 }
 
+template <uint32_t kSubPer>
 __device__ __forceinline__ void tile_sort_body(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb,
                                                ListGeom geom, tile_off_t *__restrict__ tile_off, uint32_t t) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -1446,10 +1450,16 @@ __device__ __forceinline__ void tile_sort_body(unsigned long long *__restrict__ 
         }
     }
     __syncthreads();
-    // exclusive scan of cnt[0..F) (F <= 1024 = 2 entries per thread)
-    const uint32_t a = threadIdx.x * 2;
-    const uint32_t c0 = a < F ? cnt[a] : 0u, c1 = a + 1 < F ? cnt[a + 1] : 0u;
-    uint32_t incl = c0 + c1;
+    // exclusive scan of cnt[0..F) (F <= 2^kMaxSubLog2 = kSubPer entries per thread)
+    const uint32_t a = threadIdx.x * kSubPer;
+    uint32_t cj[kSubPer];
+    uint32_t mine = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < kSubPer; j++) {
+        cj[j] = a + j < F ? cnt[a + j] : 0u;
+        mine += cj[j];
+    }
+    uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -1459,14 +1469,14 @@ __device__ __forceinline__ void tile_sort_body(unsigned long long *__restrict__ 
     __syncthreads();
     uint32_t base = 0;
     for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) base += s_warp[w];
-    const uint32_t start0 = base + incl - c0 - c1;
-    if (a < F) {
-        cnt[a] = start0;
-        off[a] = start0;
-    }
-    if (a + 1 < F) {
-        cnt[a + 1] = start0 + c0;
-        off[a + 1] = start0 + c0;
+    uint32_t run = base + incl - mine;
+#pragma unroll
+    for (uint32_t j = 0; j < kSubPer; j++) {
+        if (a + j < F) {
+            cnt[a + j] = run;
+            off[a + j] = run;
+        }
+        run += cj[j];
     }
     if (threadIdx.x == 0) off[F] = n;
     __syncthreads();
@@ -1492,7 +1502,7 @@ __device__ __forceinline__ void tile_sort_body(unsigned long long *__restrict__ 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
-template <int C>
+template <int C, uint32_t kSubPer>
 __global__ void __launch_bounds__(kSortThreads, 2)
 tile_sort_cluster_kernel(unsigned long long *__restrict__ list, ListMeta m, uint32_t nb, ListGeom geom,
                          tile_off_t *__restrict__ tile_off, unsigned int *__restrict__ tile_counter) {
@@ -1557,24 +1567,39 @@ tile_sort_cluster_kernel(unsigned long long *__restrict__ list, ListMeta m, uint
         }
         cluster.sync();   // every CTA's counts are complete, and every CTA holds its cells in registers
         if (cr == 0 && threadIdx.x == 0) s_next[it & 1] = n_clusters + atomicAdd(tile_counter, 1u);
-        // sub-buckets a, a + 1 of this thread: tile-wide totals, and what lower-ranked CTAs hold
-        const uint32_t a = threadIdx.x * 2;
-        uint32_t tot0 = 0, tot1 = 0, bef0 = 0, bef1 = 0;
+        // sub-buckets a .. a + kSubPer - 1 of this thread: tile-wide totals, and what lower-ranked CTAs hold
+        // (parked in this thread's entries of lstart / gbase until the scan is done: no registers held across it)
+        const uint32_t a = threadIdx.x * kSubPer;
+        uint32_t tot_sum = 0, own_sum = 0;
+        if (a < F) {   // (F is a power of two: a thread's kSubPer sub-buckets are all inside or all outside, F >= kSubPer,
+                       //  or only the first F of thread 0's are inside)
+            uint32_t tot[kSubPer], bef[kSubPer];
 #pragma unroll
-        for (uint32_t c = 0; c < (uint32_t)C; c++) {
-            const uint32_t *rc = cluster.map_shared_rank(cnt, c);
-            const uint32_t x0 = a < F ? rc[a] : 0u, x1 = a + 1 < F ? rc[a + 1] : 0u;
-            tot0 += x0;
-            tot1 += x1;
-            if (c < cr) {
-                bef0 += x0;
-                bef1 += x1;
+            for (uint32_t j = 0; j < kSubPer; j++) tot[j] = bef[j] = 0;
+            // all remote loads first (independent), then the stores
+#pragma unroll
+            for (uint32_t c = 0; c < (uint32_t)C; c++) {
+                const uint32_t *rc = cluster.map_shared_rank(cnt, c);
+#pragma unroll
+                for (uint32_t j = 0; j < kSubPer; j++) {
+                    const uint32_t x = a + j < F ? rc[a + j] : 0u;
+                    tot[j] += x;
+                    if (c < cr) bef[j] += x;
+                }
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < kSubPer; j++) {
+                if (a + j < F) {
+                    lstart[a + j] = tot[j];
+                    gbase[a + j] = bef[j];
+                    tot_sum += tot[j];
+                    own_sum += cnt[a + j];
+                }
             }
         }
-        const uint32_t c0 = a < F ? cnt[a] : 0u, c1 = a + 1 < F ? cnt[a + 1] : 0u;
         cluster_arrive();   // this CTA has read the others' counts; CTA 0 has published the next tile
         // ONE exclusive scan for both: high word = tile-wide totals, low word = this CTA's counts
-        const unsigned long long mine = ((unsigned long long)(tot0 + tot1) << 32) | (unsigned long long)(c0 + c1);
+        const unsigned long long mine = ((unsigned long long)tot_sum << 32) | (unsigned long long)own_sum;
         unsigned long long incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1586,16 +1611,17 @@ tile_sort_cluster_kernel(unsigned long long *__restrict__ list, ListMeta m, uint
         unsigned long long base = 0;
         for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) base += s_warp[w];
         const unsigned long long start = base + incl - mine;
-        const uint32_t gs0 = (uint32_t)(start >> 32), ls0 = (uint32_t)start;
-        if (a < F) {
-            lstart[a] = ls0;
-            gbase[a] = gs0 + bef0;
-            if (cr == 0) off[a] = gs0;
-        }
-        if (a + 1 < F) {
-            lstart[a + 1] = ls0 + c0;
-            gbase[a + 1] = gs0 + tot0 + bef1;
-            if (cr == 0) off[a + 1] = gs0 + tot0;
+        uint32_t gs = (uint32_t)(start >> 32), ls = (uint32_t)start;
+#pragma unroll
+        for (uint32_t j = 0; j < kSubPer; j++) {
+            if (a + j < F) {
+                const uint32_t tot = lstart[a + j], bef = gbase[a + j];
+                lstart[a + j] = ls;
+                gbase[a + j] = gs + bef;
+                if (cr == 0) off[a + j] = gs;
+                gs += tot;
+                ls += cnt[a + j];
+            }
         }
         if (cr == 0 && threadIdx.x == 0) off[F] = n_tile;
         __syncthreads();

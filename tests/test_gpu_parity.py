@@ -163,14 +163,17 @@ def test_count_parity_vs_oracle(skm, oracle, k, chunks, mode):
     compare(e, run, chunks)
 
 
-@pytest.mark.parametrize("tile_log2,max_buckets,k,chunks", [(14, 16, 21, 3), (15, 16, 31, 0), (16, 16, 21, 10), (16, 1024, 25, 2),
-                                                             (15, 4, 15, 4)])
-def test_cluster_tile_sort_vs_oracle(skm, oracle, monkeypatch, tile_log2, max_buckets, k, chunks):
+@pytest.mark.parametrize("tile_log2,max_buckets,k,chunks,g2", [(14, 16, 21, 3, None), (15, 16, 31, 0, None), (16, 16, 21, 10, None),
+                                                                (16, 1024, 25, 2, None), (15, 4, 15, 4, None),
+                                                                (13, 64, 21, 3, 11), (16, 16, 31, 2, 11), (14, 8, 25, 0, 9)])
+def test_cluster_tile_sort_vs_oracle(skm, oracle, monkeypatch, tile_log2, max_buckets, k, chunks, g2):
     """Pass B by a thread-block cluster (tile_sort_cluster_kernel): 2 / 4 / 8 CTAs sort 2^14 / 2^15 / 2^16 k-mers as one
     tile, counts exchanged through distributed shared memory.  Few buckets, so that a bucket spans several full
     tiles and every CTA of a cluster has cells; 1024 buckets: every tile is a partial one."""
     monkeypatch.setenv("SKM_TILE_LOG2", str(tile_log2))
     monkeypatch.setenv("SKM_MAX_BUCKETS", str(max_buckets))
+    if g2 is not None:   # forced sub-bucket bits (2^11 = the most a tile is sorted by; also the one-CTA sort at 2^13)
+        monkeypatch.setenv("SKM_G2", str(g2))
     L = 150
     reads = oracle.synth_reads(seed=300 + tile_log2, genome_len=80_000, read_len=L, sub_rate=0.01, n_rate=0.001,
                                first=0, n=25_000)
@@ -583,13 +586,15 @@ def test_sharded_group_vs_oracle(skm, oracle, monkeypatch, world, k, chunks, mod
     g.close()
 
 
-@pytest.mark.parametrize("world,chunks", [(2, 3), (4, 0), (3, 2)])
-def test_sharded_group_few_buckets_full_cluster_tiles(skm, oracle, monkeypatch, world, chunks):
+@pytest.mark.parametrize("world,chunks,g2", [(2, 3, None), (4, 0, None), (3, 2, None), (4, 2, 11)])
+def test_sharded_group_few_buckets_full_cluster_tiles(skm, oracle, monkeypatch, world, chunks, g2):
     """Sender lists with few, large buckets (SKM_MAX_BUCKETS=16): an owner's coarse bucket spans several full
     cluster tiles, so the slices shipped hold whole 2^16-cell tiles sorted by all eight CTAs."""
     from sharkmer_b200.multigpu import Group
     monkeypatch.setenv("SKM_MAX_BUCKETS", "16")
     monkeypatch.setenv("SKM_MG_SLICES", "1")
+    if g2 is not None:
+        monkeypatch.setenv("SKM_G2", str(g2))
     L, n, hmax, k = 150, 24_000, 100, 21
     reads = oracle.synth_reads(171 + world, 60_000, L, 0.01, 0.001, 0, n)
     run = run_oracle(oracle, reads, k, chunks, hmax)
