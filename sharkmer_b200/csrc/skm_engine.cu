@@ -109,6 +109,9 @@ struct skm_ctx {
     cudaStream_t copy_stream = nullptr;   // host->device copies of raw batches, nothing else: the copy
                                           // engine never queues behind a kernel that waits for an SM
     cudaStream_t dma_stream = nullptr;   // peer copies of routed k-mers (copy engines)
+    std::vector<cudaStream_t> dma_peer;  // n_ranks > 1: one copy stream per destination rank.  (On ONE stream the seven
+                                         // peers' copies of a batch ran one after the other on one copy engine: at N=8
+                                         // 9.5 GB per rank and step took ~38 ms and the insert waited 11 ms for the tail.)
     cudaEvent_t ev_dma = nullptr;
     cudaStream_t part_stream = nullptr;  // bucketing of incoming batches (overlaps inserts on `stream`)
     cudaStream_t pack_stream = nullptr;  // pack kernels of incoming batches.  A stream of their own (high priority): on the
@@ -613,12 +616,22 @@ struct WorkStream {  // selects the stream the bucketing helpers launch on, for 
     ~WorkStream() { c->work = prev; }
 };
 
+int32_t sync_dma(skm_ctx *c) {
+    CU(cudaStreamSynchronize(c->dma_stream));
+    for (cudaStream_t s : c->dma_peer) CU(cudaStreamSynchronize(s));
+    return SKM_OK;
+}
+cudaStream_t dma_stream_for(const skm_ctx *c, uint32_t dst) { return dst < c->dma_peer.size() ? c->dma_peer[dst] : c->dma_stream; }
+
 int32_t sync_all(skm_ctx *c) {
     CU(cudaStreamSynchronize(c->copy_stream));
     CU(cudaStreamSynchronize(c->pack_stream));
     CU(cudaStreamSynchronize(c->part_stream));
     CU(cudaStreamSynchronize(c->sort_stream));
-    CU(cudaStreamSynchronize(c->dma_stream));
+    {
+        int32_t rc = sync_dma(c);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(c->stream));
     return SKM_OK;
 }
@@ -1453,10 +1466,9 @@ int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on
             n_tiles = 0;
             for (uint32_t b = 0; b < kFineRegions; b++) n_tiles += (ol.h_off[b + 1] - ol.h_off[b] + kTile - 1) / kTile;
         }
-        if (!waited) {
-            CU(cudaStreamWaitEvent(c->dma_stream, sg.ready, 0));
-            waited = true;
-        }
+        cudaStream_t ds = dma_stream_for(c, o);
+        CU(cudaStreamWaitEvent(ds, sg.ready, 0));
+        waited = true;
         MgRecord rec{};
         rec.src = me;
         rec.dst = o;
@@ -1472,10 +1484,10 @@ int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on
                         o, me, c->mg_sub_bytes);
         const ListMeta m = list_meta_at(ol.meta, kFineRegions);
         uint8_t *base = c->mg_peer[o] + (size_t)me * c->mg_sub_bytes;
-        if (b_cells) CU(cudaMemcpyAsync(base + rec.off_cells, ol.list, b_cells, cudaMemcpyDefault, c->dma_stream));
-        if (b_off) CU(cudaMemcpyAsync(base + rec.off_tile_off, ol.tile_off, b_off, cudaMemcpyDefault, c->dma_stream));
-        CU(cudaMemcpyAsync(base + rec.off_cell_begin, m.cell_begin, b_cb, cudaMemcpyDefault, c->dma_stream));
-        CU(cudaMemcpyAsync(base + rec.off_tile_begin, m.tile_begin, b_tb, cudaMemcpyDefault, c->dma_stream));
+        if (b_cells) CU(cudaMemcpyAsync(base + rec.off_cells, ol.list, b_cells, cudaMemcpyDefault, ds));
+        if (b_off) CU(cudaMemcpyAsync(base + rec.off_tile_off, ol.tile_off, b_off, cudaMemcpyDefault, ds));
+        CU(cudaMemcpyAsync(base + rec.off_cell_begin, m.cell_begin, b_cb, cudaMemcpyDefault, ds));
+        CU(cudaMemcpyAsync(base + rec.off_tile_begin, m.tile_begin, b_tb, cudaMemcpyDefault, ds));
         c->mg_bytes_sent += b_cells + b_off + b_cb + b_tb;
         ol.rec = c->mg_sent.size();
         ol.shipped = true;
@@ -1524,7 +1536,6 @@ int32_t ship_slices(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on_
         c->mg_cursor[o] = at + bytes;
         return true;
     };
-    CU(cudaStreamWaitEvent(c->dma_stream, sg.ready, 0));
     const ListMeta m = list_meta_at(sg.meta, sg.n_buckets);
     sg.rec_first = c->mg_sent.size();
     for (uint32_t i = 1; i < N; i++) {
@@ -1543,10 +1554,12 @@ int32_t ship_slices(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on_
             return fail(c, SKM_ERR_OOM, "receive arena of rank %u is too small for rank %u's k-mers (%zu bytes per source): create larger arenas",
                         o, me, c->mg_sub_bytes);
         uint8_t *base = c->mg_peer[o] + (size_t)me * c->mg_sub_bytes;
-        if (b_cells) CU(cudaMemcpyAsync(base + rec.off_cells, sg.list + cell0[o], b_cells, cudaMemcpyDefault, c->dma_stream));
-        if (b_off) CU(cudaMemcpyAsync(base + rec.off_tile_off, sg.tile_off + tile0[o] * (F + 1), b_off, cudaMemcpyDefault, c->dma_stream));
-        CU(cudaMemcpyAsync(base + rec.off_cell_begin, m.cell_begin + (size_t)o * R, b_cb, cudaMemcpyDefault, c->dma_stream));
-        CU(cudaMemcpyAsync(base + rec.off_tile_begin, m.tile_begin + (size_t)o * R, b_tb, cudaMemcpyDefault, c->dma_stream));
+        cudaStream_t ds = dma_stream_for(c, o);   // one copy stream per destination: the peers' copies run side by side
+        CU(cudaStreamWaitEvent(ds, sg.ready, 0));
+        if (b_cells) CU(cudaMemcpyAsync(base + rec.off_cells, sg.list + cell0[o], b_cells, cudaMemcpyDefault, ds));
+        if (b_off) CU(cudaMemcpyAsync(base + rec.off_tile_off, sg.tile_off + tile0[o] * (F + 1), b_off, cudaMemcpyDefault, ds));
+        CU(cudaMemcpyAsync(base + rec.off_cell_begin, m.cell_begin + (size_t)o * R, b_cb, cudaMemcpyDefault, ds));
+        CU(cudaMemcpyAsync(base + rec.off_tile_begin, m.tile_begin + (size_t)o * R, b_tb, cudaMemcpyDefault, ds));
         c->mg_bytes_sent += b_cells + b_off + b_cb + b_tb;
         c->mg_sent.push_back(rec);
     }
@@ -1717,6 +1730,10 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
         CU(cudaStreamCreateWithPriority(&c->pack_stream, cudaStreamNonBlocking, prio_greatest));
     }
     CU(cudaStreamCreateWithFlags(&c->dma_stream, cudaStreamNonBlocking));
+    if (c->n_ranks > 1) {
+        c->dma_peer.assign(c->n_ranks, nullptr);
+        for (auto &ds : c->dma_peer) CU(cudaStreamCreateWithFlags(&ds, cudaStreamNonBlocking));
+    }
     CU(cudaStreamCreateWithFlags(&c->sort_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_sort, cudaEventDisableTiming));
     if (const char *g = getenv("SKM_SORT_OVERLAP")) c->sort_overlap = atoi(g) != 0;
@@ -1801,11 +1818,12 @@ int32_t skm_create(const skm_params *params, skm_ctx **out) {
     // partitions (one sub-bucket per partition); without one, 2^7 sub-buckets per region — a
     // partition then covers several adjacent sub-buckets, or filters a shared one
     {
-        // Multi-GPU exchange layout.  Slices need the owner's partitions to be no finer than a sender can sort a
-        // coarse bucket (2^kMaxSubLog2 sub-buckets per coarse region), which is known only when a capacity_hint
-        // sized the table (the same hint on every rank); beyond that (tables of more than 2^(g1 + 10 + 12) slots per
-        // rank: BASELINE config 5) and without a hint, every owner gets a re-bucketed list of its own.
-        c->mg_slices = c->p.capacity_hint && l2 - kPartLog2 <= route_log2_regions(c) + kMaxSubLog2;
+        // Multi-GPU exchange layout.  Slices need the owner's partitions to be no finer than a sender sorts a coarse
+        // bucket, which is known only when a capacity_hint sized the table (the same hint on every rank).  Up to 2^10
+        // sub-buckets per coarse bucket the cluster sort pays (C2 at N=8: 54.7 vs 75.2 ms per step); at 2^11 it did not
+        // (C3 at N=8: 93.5 ms with slices, 88.6 ms with owner lists), so finer tables (C3, C5) and ctxs without a hint
+        // give every owner a re-bucketed list of its own.
+        c->mg_slices = c->p.capacity_hint && l2 - kPartLog2 <= route_log2_regions(c) + 10;
         if (const char *g = getenv("SKM_MG_SLICES")) c->mg_slices = atoi(g) != 0;
         // tile size: one CTA sorts 2^13 k-mers; a cluster of 2 / 4 / 8 CTAs sorts 2^14 / 2^15 / 2^16 as one tile.
         // Multi-GPU slices need the large tile: an owner's coarse bucket is sorted by log2(n_ranks) more bits.
@@ -1850,6 +1868,7 @@ void skm_destroy(skm_ctx *c) {
         cudaStreamSynchronize(c->part_stream);
         cudaStreamSynchronize(c->sort_stream);
         cudaStreamSynchronize(c->dma_stream);
+        for (cudaStream_t ds : c->dma_peer) cudaStreamSynchronize(ds);
         for (auto &cs : c->chunks)
             for (auto &sg : cs.segs) {
                 cudaFree(sg.codes);
@@ -1911,6 +1930,7 @@ void skm_destroy(skm_ctx *c) {
         cudaStreamDestroy(c->part_stream);
         cudaStreamDestroy(c->pack_stream);
         cudaStreamDestroy(c->dma_stream);
+        for (cudaStream_t ds : c->dma_peer) cudaStreamDestroy(ds);
         cudaStreamDestroy(c->sort_stream);
         if (c->ev_sort) cudaEventDestroy(c->ev_sort);
         if (c->ev_dma) cudaEventDestroy(c->ev_dma);
@@ -2916,7 +2936,8 @@ int32_t mg_prepare_local(skm_ctx *c) {
                 // batch with the exact layout from the packed form and ship that
                 if (sg.shipped)
                     for (uint32_t i = 0; i + 1 < c->n_ranks; i++) c->mg_sent[sg.rec_first + i].dead = 1;
-                CU(cudaStreamSynchronize(c->dma_stream));  // the copies still read the old list
+                rc = sync_dma(c);  // the copies still read the old list
+                if (rc) return rc;
                 rc = drop_capped_list(c, ch, sg, c->part_stream);
                 if (rc) return rc;
                 sg.shipped = false;
@@ -2953,7 +2974,8 @@ int32_t mg_prepare_local(skm_ctx *c) {
                 // void; rebuild the batch with exact layouts from the packed form and ship that
                 for (auto &ol : sg.owners)
                     if (ol.shipped && ol.rec < c->mg_sent.size()) c->mg_sent[ol.rec].dead = 1;
-                CU(cudaStreamSynchronize(c->dma_stream));  // the copies still read the old lists
+                rc = sync_dma(c);  // the copies still read the old lists
+                if (rc) return rc;
                 rc = drop_capped_list(c, ch, sg, c->part_stream);
                 if (rc) return rc;
                 sg.shipped = false;
@@ -2983,7 +3005,8 @@ int32_t mg_prepare_local(skm_ctx *c) {
     DBG_SYNC("mg_prepare_local (bucketing / shipping)");
     CU(cudaStreamSynchronize(c->part_stream));
     CU(cudaStreamSynchronize(c->sort_stream));
-    CU(cudaStreamSynchronize(c->dma_stream));  // every slice of mine has landed
+    rc = sync_dma(c);  // every slice of mine has landed
+    if (rc) return rc;
     rc = check_sticky(c);
     if (rc) return rc;
     return refresh_chunk_counters(c);
