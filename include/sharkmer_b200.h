@@ -56,7 +56,9 @@ typedef struct skm_params {
     uint32_t chunks;         /* --chunks; 0 => one internal chunk, no histograms (src/io.rs:378) */
     uint32_t insert_mode;    /* SKM_INSERT_* */
     uint64_t histo_max;      /* 1..1000000           (src/cli.rs:668-673) */
-    uint64_t capacity_hint;  /* expected distinct k-mers owned by this ctx; 0 => grow on demand */
+    uint64_t capacity_hint;  /* expected distinct k-mers owned by this ctx; 0 => grow on demand.
+                              * n_ranks > 1: the same value on every rank (it fixes the geometry of the
+                              * k-mer lists the ranks exchange) */
     int32_t device;          /* CUDA ordinal; -1 => current device */
     uint32_t n_ranks;        /* table partitions (GPUs); 0/1 => single GPU */
     uint32_t rank;           /* this ctx owns k-mers with skm_owner_rank(hash, n_ranks) == rank (a contiguous hash range) */

@@ -1336,7 +1336,7 @@ int32_t eager_partition(skm_ctx *c, uint32_t chunk, size_t seg_index, bool force
 // coarse list is freed.  `exact`: exact two-pass layouts (small batches, or the retry of an overflow).
 int32_t refine_owner_lists(skm_ctx *c, uint32_t chunk, size_t seg_index, bool exact) {
     Segment &sg = c->chunks[chunk].segs[seg_index];
-    const uint32_t N = c->n_ranks, g1c = route_log2_regions(c), R = 1u << g1c, nb_in = N << g1c;
+    const uint32_t N = c->n_ranks, g1c = route_log2_regions(c), nb_in = N << g1c;
     const uint32_t F = 1u << c->g2;
     const ListMeta m_in = list_meta_at(sg.meta, nb_in);
     const uint64_t n_exp = sg.n_bytes / N + sg.n_bytes / (8ull * N) + 4096;   // an owner's share, with room for imbalance
@@ -1443,7 +1443,6 @@ int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on
     for (uint32_t o = 0; o < N; o++)
         if (o != me && !c->mg_peer[o]) return SKM_OK;  // arenas not wired yet: shipped at finalize
     const uint32_t F = 1u << c->g2;
-    bool waited = false;
     auto take = [&](uint32_t o, size_t bytes, uint64_t *off) -> bool {
         const size_t at = (c->mg_cursor[o] + 255) & ~(size_t)255;
         if (at + bytes > c->mg_sub_bytes) return false;
@@ -1468,7 +1467,6 @@ int32_t ship_segment(skm_ctx *c, uint32_t chunk, size_t seg_index, bool sizes_on
         }
         cudaStream_t ds = dma_stream_for(c, o);
         CU(cudaStreamWaitEvent(ds, sg.ready, 0));
-        waited = true;
         MgRecord rec{};
         rec.src = me;
         rec.dst = o;
