@@ -1131,7 +1131,11 @@ int32_t ensure_tiled_buffers(skm_ctx *c, uint32_t n_chunks_l, size_t seg_bytes) 
 // One launch (plus retries after growth) of tile_insert_kernel over the given lists, which hold
 // chunks [chunk0, chunk0 + n_chunks_l) in chunk order.  Histogram columns of those chunks are
 // produced when the ctx tracks the histogram.  Synchronises the main stream.
-int32_t launch_tiled(skm_ctx *c, const std::vector<SegDesc> &segs, uint32_t chunk0, uint32_t n_chunks_l) {
+constexpr int32_t kSpecAborted = -1;   // launch_tiled (internal; the SKM_ERR_* codes are positive): the speculative launch
+                                       // was called off on the device, nothing changed
+
+int32_t launch_tiled(skm_ctx *c, const std::vector<SegDesc> &segs, uint32_t chunk0, uint32_t n_chunks_l,
+                     const unsigned long long *abort_if = nullptr) {
     const bool histo = c->track_histo;
     const size_t nbins = c->p.histo_max + 2;
     const uint32_t n = (uint32_t)segs.size();
@@ -1175,6 +1179,7 @@ int32_t launch_tiled(skm_ctx *c, const std::vector<SegDesc> &segs, uint32_t chun
     L.part_counter = &c->d_gc->scratch[0];
     L.fail_list = c->d_fail;
     L.fail_cap = skm_ctx::kFailCap;
+    L.abort_if = abort_if;
     const size_t smem = tile_insert_smem_bytes(n_chunks_l, L.k_low, histo);
     if (histo) zero_async(c, c->d_delta, (size_t)n_chunks_l * nbins * sizeof(uint64_t), c->stream);
     zero_async(c, c->d_recount, nbins * sizeof(uint64_t), c->stream);
@@ -1220,11 +1225,15 @@ int32_t launch_tiled(skm_ctx *c, const std::vector<SegDesc> &segs, uint32_t chun
         }
         CU(cudaGetLastError());
         const bool was_fresh = c->table_fresh;
-        c->table_fresh = false;
-        c->table_zombie = false;  // every partition was written (failed ones: written empty)
         GlobalCounters *hgc = (GlobalCounters *)c->h_pinned;
         CU(cudaMemcpyAsync(hgc, c->d_gc, sizeof(GlobalCounters), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
+        if (abort_if && hgc->pad) {   // (abort_if == &d_gc->pad) called off on the device: no partition was touched
+            c->n_tiled_launches--;
+            return kSpecAborted;
+        }
+        c->table_fresh = false;
+        c->table_zombie = false;  // every partition was written (failed ones: written empty)
         c->distinct_ub = hgc->n_distinct;
         for (auto &pnd : c->snap_pending) pnd = false;
         const uint64_t n_failed = hgc->n_failed;
@@ -2170,7 +2179,56 @@ static int32_t finalize_common(skm_ctx *c) {
     uint64_t positions_all = 0, group_positions = 0, positions_seen = 0;
     for (auto &cs : c->chunks) positions_all += cs.n_bytes;
     const bool early_flush = !getenv("SKM_NO_EARLY_FLUSH");
-    for (uint32_t ch = 0; ch < c->n_chunks; ch++) {
+
+    // SPECULATIVE LAUNCH.  When the whole input is already on the device and every batch was bucketed at ingest time
+    // with the capped layout, the insert is queued behind the lists' events NOW — before the host has waited for
+    // any of them — so that a host that is late (a descheduled thread: about one step in ten stalled for 40-70 ms
+    // between the last tile sort and the launch, profiles/experiments_r02.md #14) does not leave the GPU idle.
+    // The one thing the host would have checked first, an overflowed capped list, is checked on the device
+    // (spec_guard_kernel): then the launch does nothing and the loop below takes over.
+    bool spec_done = false;
+    if (c->table_fresh && c->n_ranks == 1 && c->n_chunks <= kMaxChunksPerLaunch && !getenv("SKM_NO_SPEC")) {
+        std::vector<SegDesc> all;
+        GuardWords gw{};
+        uint32_t n_words = 0;
+        bool ok = true;
+        for (uint32_t ch = 0; ch < c->n_chunks && ok; ch++)
+            for (auto &sg : c->chunks[ch].segs) {
+                const bool arriving = sg.copied && cudaEventQuery(sg.copied) == cudaErrorNotReady;
+                if (!sg.ready || !sg.list || !sg.tiled || !sg.cap || arriving || n_words >= kMaxGuardWords) {
+                    ok = false;
+                    break;
+                }
+                all.push_back(local_desc(c, sg, ch));
+                gw.w[n_words++] = (const unsigned long long *)(sg.h_offsets + sg.n_buckets);
+            }
+        cudaGetLastError();
+        if (ok && !all.empty() && all.size() * nbr_now <= kMaxVseg) {
+            for (auto &cs : c->chunks)
+                for (auto &sg : cs.segs) CU(cudaStreamWaitEvent(c->stream, sg.ready, 0));
+            unsigned long long *flag = &c->d_gc->pad;
+            spec_guard_kernel<<<1, 32, 0, c->stream>>>(gw, n_words, flag);
+            c->launches++;
+            rc = launch_tiled(c, all, 0, c->n_chunks, flag);
+            if (rc > 0) return rc;
+            if (rc == SKM_OK) {
+                for (auto &cs : c->chunks) {
+                    for (auto &sg : cs.segs) {
+                        for (uint32_t b = 0; b < sg.n_buckets; b++) c->insert_kmers += sg.h_offsets[b];
+                        if (sg.codes) CU(cudaFreeAsync(sg.codes, c->stream));
+                        if (sg.breaks) CU(cudaFreeAsync(sg.breaks, c->stream));
+                        sg.codes = nullptr;
+                        sg.breaks = nullptr;
+                        release_list(c, sg, c->stream);
+                    }
+                    cs.counted = true;
+                }
+                spec_done = true;
+            }
+            // (rc == kSpecAborted: some list overflowed; nothing was counted)
+        }
+    }
+    for (uint32_t ch = 0; ch < c->n_chunks && !spec_done; ch++) {
         ChunkState &cs = c->chunks[ch];
         // Host-fed input that is still on its way over PCIe: rather than idle until the last batch has arrived,
         // count what is listed so far (one more pass over the table, hidden behind the copies).  Only while a

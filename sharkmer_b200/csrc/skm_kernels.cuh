@@ -1834,7 +1834,22 @@ struct InsertLaunch {
     unsigned long long *part_counter;
     uint32_t *fail_list;
     uint32_t fail_cap;
+    const unsigned long long *abort_if;  // speculative launch: non-null and != 0 on the device => the launch does nothing
 };
+
+// Speculative insert launches (skm_finalize queues the insert behind the lists' events before the host has seen
+// their bucket totals): a capped list that overflowed makes the launch a no-op — the flag is set on the device
+// from the overflow words the bucketing kernels left in pinned host memory — and the host takes the slow path.
+static constexpr uint32_t kMaxGuardWords = 64;
+struct GuardWords {
+    const unsigned long long *w[kMaxGuardWords];
+};
+__global__ void spec_guard_kernel(GuardWords g, uint32_t n, unsigned long long *flag) {
+    unsigned long long any = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) any |= *reinterpret_cast<const volatile unsigned long long *>(g.w[i]);
+    any = __reduce_or_sync(0xffffffffu, (unsigned)(any != 0));
+    if (threadIdx.x == 0) *flag = any;
+}
 
 __host__ __device__ inline size_t tile_insert_smem_bytes(uint32_t n_chunks, uint32_t k_low, bool histo) {
     size_t b = (size_t)kPartSlots * 12;                    // keys + counts
@@ -1882,6 +1897,7 @@ tile_insert_kernel(const InsertLaunch L) {
     __shared__ uint32_t s_span[kMaxSpans][5];     // the plan: chunk, first run, end run, first k-mer, k-mers of each span
     __shared__ uint32_t s_nspans, s_more, s_next_run;
 
+    if (L.abort_if && *L.abort_if) return;   // (speculative launch called off: the same in every thread)
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = kInsThreads / 32;
     uint32_t keys_s = (uint32_t)__cvta_generic_to_shared(keys), counts_s = (uint32_t)__cvta_generic_to_shared(counts);
     uint32_t phist_s = (uint32_t)__cvta_generic_to_shared(phist), stage_s = (uint32_t)__cvta_generic_to_shared(stage);
