@@ -239,6 +239,32 @@ def test_skewed_buckets_overflow_and_fallback(skm, oracle, poly_frac):
         compare(e, run, chunks)
 
 
+@pytest.mark.parametrize("skew", [False, True])
+def test_speculative_insert_launch_and_its_guard(skm, oracle, skew):
+    """Batches large enough for the one-pass capped layout on ONE GPU (>= 4096 k-mers per bucket), all on the device by
+    the time skm_finalize runs: the insert is launched speculatively, behind the lists' events, with the overflow check
+    on the device (spec_guard_kernel).  skew: a tenth of the reads are poly-A, a capped bucket overflows, the
+    speculative launch must do NOTHING and the batch is rebuilt with the exact layout.  Either way: the oracle's table."""
+    L, chunks = 100, 2
+    per_batch = 4_600_000 // (L + 1)
+    n = per_batch * chunks
+    reads = oracle.synth_reads(61, 1_000_000, L, 0.005, 0.001, 0, n).copy()
+    if skew:
+        reads.reshape(n, L + 1)[::10, :L] = ord("A")
+    run = run_oracle(oracle, reads, 21, chunks, 500)
+    e = skm.Engine(21, chunks, 500, insert_mode=2)
+    line = L + 1
+    by_chunk = [[] for _ in range(chunks)]
+    for b in range((n + 999) // 1000):
+        by_chunk[b % chunks].append(reads[b * 1000 * line:min((b + 1) * 1000, n) * line])
+    for c in range(chunks):
+        e.ingest_batch(c, np.concatenate(by_chunk[c]))   # one large batch per chunk
+    e.finalize()
+    compare(e, run, chunks)
+    assert e.stage_times().tiled_launches >= 1
+    e.close()
+
+
 def test_table_growth_from_tiny(skm, oracle):
     """capacity_hint = 0: the table starts at 2^16 slots and must grow several times."""
     L = 100
